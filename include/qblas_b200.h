@@ -1,0 +1,137 @@
+/*
+ * qblas_b200.h — C ABI of libqblas_b200.so: binary128 (IEEE quad) BLAS hot path on NVIDIA B200.
+ *
+ * Drop-in boundary for SwayamInSync/QBLAS ("QuadBLAS").  The reference is header-only: its C
+ * entry points are `inline` definitions inside extern "C" in
+ *   /root/reference/include/quadblas/interface/c_interface.hpp:15-146
+ * and its C++ surface (QuadBLAS::gemm/gemv/dot/axpy, Vector<>, Matrix<>) calls the same free
+ * functions.  This library exports
+ *   (1) the reference C entry points under their exact names and signatures (section A), so an
+ *       FFI consumer (ctypes / cffi / numpy-quaddtype style, c_interface.hpp:13) binds the same
+ *       symbols, and
+ *   (2) a quad-typed, device-pointer-aware, stream-aware extended API (section B) that the
+ *       drop-in C++ headers in include/quadblas/ forward to and that bench.py / torch callers use.
+ *
+ * Data type: 16-byte little-endian IEEE-754 binary128 = SLEEF `Sleef_quad` = GCC `__float128`
+ * (lo 64 mantissa bits first).  Only 16-byte element alignment is assumed (std::vector<Sleef_quad>,
+ * /root/reference/test_quadblas.cpp:207).
+ *
+ * Pointers: every matrix/vector pointer may be a device pointer, managed memory, pinned host or
+ * pageable host memory; it is classified with cudaPointerGetAttributes.  Host operands are staged
+ * to the current CUDA device and results copied back before the call returns (calls are
+ * synchronous, like the reference).  The *_dev entry points take device pointers only and are
+ * asynchronous on the given stream.
+ *
+ * Numerical modes (qb_set_mode):
+ *   QB_MODE_REFERENCE (default) reproduces the reference's reduction order bit for bit
+ *       (SURVEY.md Appendix B): gemm k-panels of kc=126, dot chunked by quadblas_get_num_threads().
+ *   QB_MODE_FAST is free to reorder; results satisfy |c^ - c| <= gamma_k (|A||B|)_ij,
+ *       gamma_k = k u / (1 - k u), u = 2^-113.
+ * There is no CPU fallback: every compute entry point fails with QB_ERR_CUDA when no sm_100 device
+ * is usable.
+ *
+ * Errors: the reference has no error channel (void/double returns, c_interface.hpp).  Here the
+ * reference-named functions keep their signatures and record failures in a thread-local sticky
+ * error (qb_last_error / qb_last_error_code); outputs are left untouched on failure, qdot/qnrm2
+ * return NaN.  The qb_* functions return the code directly.  Nothing throws across the ABI.
+ */
+#ifndef QBLAS_B200_H
+#define QBLAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qb_quad { uint64_t lo, hi; } qb_quad; /* bit pattern of one binary128 */
+
+enum { QB_OK = 0, QB_ERR_CUDA = 1, QB_ERR_ARG = 2, QB_ERR_ALLOC = 3 };
+enum { QB_MODE_REFERENCE = 0, QB_MODE_FAST = 1 };
+
+/* ------------------------------------------------------------------ A. reference C ABI */
+/* c_interface.hpp:21  — returns (double)dot; full precision via qb_dot */
+double quadblas_qdot(int n, void *x, int incx, void *y, int incy);
+/* c_interface.hpp:34 */
+double quadblas_qnrm2(int n, void *x, int incx);
+/* c_interface.hpp:47 */
+void quadblas_qaxpy(int n, double alpha, void *x, int incx, void *y, int incy);
+/* c_interface.hpp:64  — trans in {T,t,C,c}: swap(m,n) and flip layout (lda unchanged) */
+void quadblas_qgemv(char layout, char trans, int m, int n, double alpha, void *A, int lda, void *x, int incx,
+                    double beta, void *y, int incy);
+/* c_interface.hpp:95  — transa/transb accepted and IGNORED, exactly like the reference
+ * (c_interface.hpp:109-112), unless qb_set_honor_trans(1) */
+void quadblas_qgemm(char layout, char transa, char transb, int m, int n, int k, double alpha, void *A, int lda,
+                    void *B, int ldb, double beta, void *C, int ldc);
+/* c_interface.hpp:122,128 — T feeds the reference-order dot chunking (level1.hpp:46-65) */
+void quadblas_set_num_threads(int num_threads);
+int quadblas_get_num_threads(void);
+/* c_interface.hpp:134 */
+const char *quadblas_get_version(void);
+/* c_interface.hpp:140 — 32-byte test (core/constants.hpp:18) */
+int quadblas_is_aligned(const void *ptr);
+
+/* ------------------------------------------------------------------ B. extended API */
+int qb_init(void);                       /* create the context on the current CUDA device */
+const char *qb_last_error(void);         /* thread-local sticky message ("" if none) */
+int qb_last_error_code(void);
+void qb_clear_error(void);
+const char *qb_build_info(void);
+
+void qb_set_mode(int mode);              /* QB_MODE_REFERENCE | QB_MODE_FAST */
+int qb_get_mode(void);
+void qb_set_kc(int kc);                  /* gemm k-panel (detail/blocking.hpp:21-66): 126 x86-64, 256 Apple */
+int qb_get_kc(void);
+void qb_set_honor_trans(int on);         /* extension: honour transa/transb in qgemm (default 0) */
+int qb_get_honor_trans(void);
+
+/* Quad-typed, host-or-device pointers, synchronous.  alpha/beta/result are HOST pointers to one
+ * binary128 each.  Semantics = QuadBLAS::gemm/gemv/dot/axpy (level3.hpp:215, level2.hpp:85,
+ * level1.hpp:80,190) and Vector::dot / Vector::norm (cpp_classes.hpp:66-81). */
+int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t k, const qb_quad *alpha,
+            const void *A, int64_t lda, const void *B, int64_t ldb, const qb_quad *beta, void *C, int64_t ldc);
+int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *A, int64_t lda, const void *x,
+            int64_t incx, const qb_quad *beta, void *y, int64_t incy);
+int qb_dot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, qb_quad *result);
+int qb_nrm2(int64_t n, const void *x, int64_t incx, qb_quad *result);
+int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *y, int64_t incy);
+
+/* Device pointers only, asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream).
+ * d_result is a DEVICE pointer to 16 bytes.  No host synchronisation inside. */
+int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int64_t k, const qb_quad *alpha,
+                const void *dA, int64_t lda, const void *dB, int64_t ldb, const qb_quad *beta, void *dC,
+                int64_t ldc, void *stream);
+int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda,
+                const void *dx, int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream);
+int qb_dot_dev(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t incy, void *d_result,
+               void *stream);
+int qb_nrm2_dev(int64_t n, const void *dx, int64_t incx, void *d_result, void *stream);
+int qb_axpy_dev(int64_t n, const qb_quad *alpha, const void *dx, int64_t incx, void *dy, int64_t incy,
+                void *stream);
+/* Combine `count` binary128 partials (device) in index order with add from +0 — the exchange step
+ * of a sharded dot: partials are all-gathered as bytes, then folded on device. */
+int qb_fold_partials_dev(int64_t count, const void *d_partials, int do_sqrt, void *d_result, void *stream);
+
+/* Elementwise scalar ops on device arrays, for parity tests of the arithmetic core against
+ * Sleef_{fma,mul,add,sqrt}q1_u05.  op: 0 fma (generic), 1 fma (chain form used by the kernels),
+ * 2 mul, 3 add, 4 sqrt, 5 quad->double->quad round trip of casts. */
+int qb_elementwise_dev(int op, int64_t n, const void *da, const void *db, const void *dc, void *dout,
+                       void *stream);
+
+/* Scalar casts (host, integer code; replace Sleef_cast_from_doubleq1 / Sleef_cast_to_doubleq1) */
+qb_quad qb_from_double(double d);
+double qb_to_double(qb_quad q);
+
+/* number of kernel launches issued by this library in this process (bench.py's gpu_launches) */
+int64_t qb_launch_count(void);
+
+/* register-resident qFMA throughput microbenchmark (the empirical integer-pipe roofline,
+ * SURVEY.md §8d): runs `iters` dependent-chain steps on `ilp` independent accumulators per thread
+ * over grid x block threads; returns total qFMAs issued through *n_fma.  d_sink: >=16 bytes. */
+int qb_fma_microbench_dev(int variant, int blocks, int threads, int iters, void *d_sink, int64_t *n_fma,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBLAS_B200_H */

@@ -1,0 +1,217 @@
+"""Python mirror of the reference's operator interface for the binary128 hot path.
+
+Same names, argument meaning and marshalling as the reference's C entry points
+(/root/reference/include/quadblas/interface/c_interface.hpp:21-146) plus quad-typed variants that
+mirror QuadBLAS::gemm/gemv/dot/axpy and Vector::dot/norm (cpp_classes.hpp:66-81,143-154).
+
+Operands are binary128 bit patterns:
+  * numpy uint64 arrays of shape (..., 2)  -> host path (the library stages H2D/D2H itself), or
+  * torch CUDA tensors (int64, shape (..., 2)) -> device path, asynchronous on torch's current
+    stream, no host synchronisation.
+Every call goes through libqblas_b200.so; nothing here computes.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import quad
+from ._lib import QbQuad, check, lib
+
+MODE_REFERENCE = 0
+MODE_FAST = 1
+
+
+# ------------------------------------------------------------------ scalars / pointers
+def _q(v):
+    """Python float | (hi, lo) tuple | numpy (2,) uint64 -> QbQuad (exact)."""
+    if isinstance(v, QbQuad):
+        return v
+    if isinstance(v, (float, int)) and not isinstance(v, bool):
+        return lib().qb_from_double(float(v))
+    if isinstance(v, tuple):
+        return QbQuad(lo=int(v[1]), hi=int(v[0]))
+    a = np.asarray(v, dtype=np.uint64).reshape(2)
+    return QbQuad(lo=int(a[0]), hi=int(a[1]))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if _is_torch(x):
+        if not x.is_cuda:
+            raise TypeError("torch operands must be CUDA tensors (use numpy arrays for host data)")
+        if x.element_size() * x.shape[-1] != 16:
+            raise TypeError("torch quad tensors must have a trailing dimension of 16 bytes (int64 x 2)")
+        return C.c_void_p(x.data_ptr())
+    if not (isinstance(x, np.ndarray) and x.dtype == np.uint64 and x.shape[-1] == 2):
+        raise TypeError("host quads must be numpy uint64 arrays of shape (..., 2)")
+    return C.c_void_p(x.ctypes.data)
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(ch):
+    return ch.encode() if isinstance(ch, str) else ch
+
+
+# ------------------------------------------------------------------ configuration
+def init():
+    check(lib().qb_init(), "qb_init")
+
+
+def set_mode(mode):
+    lib().qb_set_mode(int(mode))
+
+
+def get_mode():
+    return lib().qb_get_mode()
+
+
+def set_kc(kc):
+    lib().qb_set_kc(int(kc))
+
+
+def set_honor_trans(on):
+    lib().qb_set_honor_trans(1 if on else 0)
+
+
+def quadblas_set_num_threads(t):
+    lib().quadblas_set_num_threads(int(t))
+
+
+def quadblas_get_num_threads():
+    return lib().quadblas_get_num_threads()
+
+
+def quadblas_get_version():
+    return lib().quadblas_get_version().decode()
+
+
+def quadblas_is_aligned(arr):
+    return lib().quadblas_is_aligned(_ptr(arr))
+
+
+def launch_count():
+    return lib().qb_launch_count()
+
+
+# ------------------------------------------------------------------ reference C ABI (double scalars)
+def quadblas_qdot(n, x, incx, y, incy):
+    r = lib().quadblas_qdot(n, _ptr(x), incx, _ptr(y), incy)
+    _raise_if_error("quadblas_qdot")
+    return r
+
+
+def quadblas_qnrm2(n, x, incx):
+    r = lib().quadblas_qnrm2(n, _ptr(x), incx)
+    _raise_if_error("quadblas_qnrm2")
+    return r
+
+
+def quadblas_qaxpy(n, alpha, x, incx, y, incy):
+    lib().quadblas_qaxpy(n, float(alpha), _ptr(x), incx, _ptr(y), incy)
+    _raise_if_error("quadblas_qaxpy")
+
+
+def quadblas_qgemv(layout, trans, m, n, alpha, A, lda, x, incx, beta, y, incy):
+    lib().quadblas_qgemv(_c(layout), _c(trans), m, n, float(alpha), _ptr(A), lda, _ptr(x), incx, float(beta), _ptr(y), incy)
+    _raise_if_error("quadblas_qgemv")
+
+
+def quadblas_qgemm(layout, transa, transb, m, n, k, alpha, A, lda, B, ldb, beta, C_, ldc):
+    lib().quadblas_qgemm(_c(layout), _c(transa), _c(transb), m, n, k, float(alpha), _ptr(A), lda, _ptr(B), ldb,
+                         float(beta), _ptr(C_), ldc)
+    _raise_if_error("quadblas_qgemm")
+
+
+def _raise_if_error(what):
+    L = lib()
+    code = L.qb_last_error_code()
+    if code:
+        msg = L.qb_last_error().decode()
+        L.qb_clear_error()
+        from ._lib import QblasError
+        raise QblasError(f"{what} failed (code {code}): {msg}")
+
+
+# ------------------------------------------------------------------ quad-typed API (QuadBLAS:: free functions)
+def gemm(layout, m, n, k, alpha, A, lda, B, ldb, beta, C_, ldc, transa="N", transb="N"):
+    """QuadBLAS::gemm (level3.hpp:215).  Device tensors -> async on the current torch stream."""
+    L = lib()
+    a, b = _q(alpha), _q(beta)
+    if _is_torch(C_):
+        check(L.qb_gemm_dev(_c(layout), _c(transa), _c(transb), m, n, k, C.byref(a), _ptr(A), lda, _ptr(B), ldb,
+                            C.byref(b), _ptr(C_), ldc, _stream()), "qb_gemm_dev")
+    else:
+        check(L.qb_gemm(_c(layout), _c(transa), _c(transb), m, n, k, C.byref(a), _ptr(A), lda, _ptr(B), ldb,
+                        C.byref(b), _ptr(C_), ldc), "qb_gemm")
+
+
+def gemv(layout, m, n, alpha, A, lda, x, incx, beta, y, incy):
+    """QuadBLAS::gemv (level2.hpp:85) — AFTER any transpose relabelling."""
+    L = lib()
+    a, b = _q(alpha), _q(beta)
+    if _is_torch(y):
+        check(L.qb_gemv_dev(_c(layout), m, n, C.byref(a), _ptr(A), lda, _ptr(x), incx, C.byref(b), _ptr(y), incy,
+                            _stream()), "qb_gemv_dev")
+    else:
+        check(L.qb_gemv(_c(layout), m, n, C.byref(a), _ptr(A), lda, _ptr(x), incx, C.byref(b), _ptr(y), incy), "qb_gemv")
+
+
+def dot(n, x, incx, y, incy, out=None):
+    """QuadBLAS::dot / Vector::dot (level1.hpp:80, cpp_classes.hpp:66): full binary128 result.
+    Host arrays -> returns numpy (2,) uint64.  Device tensors -> writes `out` (device, 16 B), async."""
+    L = lib()
+    if _is_torch(x):
+        check(L.qb_dot_dev(n, _ptr(x), incx, _ptr(y), incy, _ptr(out), _stream()), "qb_dot_dev")
+        return out
+    r = QbQuad()
+    check(L.qb_dot(n, _ptr(x), incx, _ptr(y), incy, C.byref(r)), "qb_dot")
+    return np.array([r.lo, r.hi], dtype=np.uint64)
+
+
+def nrm2(n, x, incx, out=None):
+    """Vector::norm (cpp_classes.hpp:78): sqrt(dot(x,x)), full binary128 result."""
+    L = lib()
+    if _is_torch(x):
+        check(L.qb_nrm2_dev(n, _ptr(x), incx, _ptr(out), _stream()), "qb_nrm2_dev")
+        return out
+    r = QbQuad()
+    check(L.qb_nrm2(n, _ptr(x), incx, C.byref(r)), "qb_nrm2")
+    return np.array([r.lo, r.hi], dtype=np.uint64)
+
+
+def axpy(n, alpha, x, incx, y, incy):
+    """QuadBLAS::axpy (level1.hpp:190)."""
+    L = lib()
+    a = _q(alpha)
+    if _is_torch(y):
+        check(L.qb_axpy_dev(n, C.byref(a), _ptr(x), incx, _ptr(y), incy, _stream()), "qb_axpy_dev")
+    else:
+        check(L.qb_axpy(n, C.byref(a), _ptr(x), incx, _ptr(y), incy), "qb_axpy")
+
+
+def fold_partials(count, partials, out, do_sqrt=False):
+    """Exchange step of a sharded dot: fold `count` device partials in index order."""
+    check(lib().qb_fold_partials_dev(count, _ptr(partials), 1 if do_sqrt else 0, _ptr(out), _stream()), "qb_fold_partials_dev")
+    return out
+
+
+def elementwise(op, a, b, c, out):
+    """Scalar-op probe on device tensors: op 0 fma, 1 chain fma, 2 mul, 3 add, 4 sqrt, 5 cast round trip."""
+    n = out.numel() // 2
+    pb = _ptr(b) if b is not None else C.c_void_p(0)
+    pc = _ptr(c) if c is not None else C.c_void_p(0)
+    check(lib().qb_elementwise_dev(op, n, _ptr(a), pb, pc, _ptr(out), _stream()), "qb_elementwise_dev")
+    return out
+
+
+def fma_microbench(variant, blocks, threads, iters, sink):
+    n = C.c_int64(0)
+    check(lib().qb_fma_microbench_dev(variant, blocks, threads, iters, _ptr(sink), C.byref(n), _stream()), "qb_fma_microbench_dev")
+    return n.value

@@ -24,7 +24,7 @@
 
 #if defined(__CUDACC__)
 #define QB_HD __host__ __device__ __forceinline__
-#define QB_HD_NOINLINE __host__ __device__ __noinline__
+#define QB_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define QB_HD static inline __attribute__((always_inline))
 #define QB_HD_NOINLINE static __attribute__((noinline))

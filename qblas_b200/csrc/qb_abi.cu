@@ -1,0 +1,403 @@
+/*
+ * qb_abi.cu — the C ABI of libqblas_b200.so (see include/qblas_b200.h).
+ *
+ * Host-side mirror of the reference's public surface:
+ *   quadblas_q{dot,nrm2,axpy,gemv,gemm}, set/get_num_threads, get_version, is_aligned
+ *     (/root/reference/include/quadblas/interface/c_interface.hpp:21-146) — same names, argument
+ *     meaning and marshalling (double alpha/beta widened exactly, layout char, gemv transpose by
+ *     relabelling :79-85, gemm transa/transb ignored :109-112);
+ *   qb_* = QuadBLAS::gemm/gemv/dot/axpy with quad-typed scalars (level3.hpp:215, level2.hpp:85,
+ *     level1.hpp:80,190) for the drop-in C++ headers and for device-resident callers.
+ * There is no CPU compute path here: if CUDA is unusable the calls fail (QB_ERR_CUDA).
+ */
+#include "../../include/qblas_b200.h"
+#include "qb_internal.h"
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <limits>
+
+namespace qb {
+
+static std::atomic<int64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_mode{QB_MODE_REFERENCE};
+static std::atomic<int> g_kc{126};
+static std::atomic<int> g_honor_trans{0};
+static std::atomic<int> g_threads{0}; /* 0 = not set -> hardware concurrency (omp_get_max_threads analogue) */
+
+static thread_local int t_err_code = 0;
+static thread_local char t_err_msg[512] = "";
+
+static int fail(int code, const char *what, cudaError_t ce = cudaSuccess)
+{
+  t_err_code = code;
+  if (ce != cudaSuccess) snprintf(t_err_msg, sizeof t_err_msg, "%s: %s", what, cudaGetErrorString(ce));
+  else snprintf(t_err_msg, sizeof t_err_msg, "%s", what);
+  return code;
+}
+
+static int num_threads()
+{
+  int t = g_threads.load();
+  if (t <= 0) { t = (int)std::thread::hardware_concurrency(); if (t <= 0) t = 1; }
+  return t;
+}
+
+/* ---- per-process device scratch (dot partials, staged scalars), guarded by a mutex ---- */
+struct Scratch {
+  std::recursive_mutex mu;
+  int device = -1;
+  q128 *work = nullptr; int64_t work_elems = 0;
+  q128 *result = nullptr;
+  void *stage[3] = {nullptr, nullptr, nullptr}; size_t stage_bytes[3] = {0, 0, 0};
+};
+static Scratch g_s;
+
+static int ensure_device()
+{
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "no usable CUDA device (cudaGetDevice)", e);
+  if (g_s.device != dev) {
+    /* scratch belongs to one device; a different current device gets fresh scratch */
+    if (g_s.device >= 0) {
+      /* best effort release on the old device */
+      int cur = dev; cudaSetDevice(g_s.device);
+      cudaFree(g_s.work); cudaFree(g_s.result);
+      for (int i = 0; i < 3; ++i) { cudaFree(g_s.stage[i]); g_s.stage[i] = nullptr; g_s.stage_bytes[i] = 0; }
+      cudaSetDevice(cur);
+      g_s.work = nullptr; g_s.work_elems = 0; g_s.result = nullptr;
+    }
+    e = cudaMalloc((void **)&g_s.result, 64);
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMalloc(result)", e);
+    g_s.device = dev;
+  }
+  return QB_OK;
+}
+
+static int ensure_work(int64_t elems)
+{
+  if (elems <= g_s.work_elems) return QB_OK;
+  cudaFree(g_s.work);
+  g_s.work = nullptr; g_s.work_elems = 0;
+  cudaError_t e = cudaMalloc((void **)&g_s.work, (size_t)elems * 16);
+  if (e != cudaSuccess) return fail(QB_ERR_ALLOC, "cudaMalloc(work)", e);
+  g_s.work_elems = elems;
+  return QB_OK;
+}
+
+static bool is_device_ptr(const void *p)
+{
+  cudaPointerAttributes at;
+  cudaError_t e = cudaPointerGetAttributes(&at, p);
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+/* staging slot: returns a device pointer holding `bytes` copied from host `src` (or src itself if
+ * it is already device-accessible) */
+static int stage_in(int slot, const void *src, size_t bytes, bool copy, const void **dptr, bool *staged)
+{
+  if (bytes == 0 || is_device_ptr(src)) { *dptr = src; *staged = false; return QB_OK; }
+  if (g_s.stage_bytes[slot] < bytes) {
+    cudaFree(g_s.stage[slot]); g_s.stage[slot] = nullptr; g_s.stage_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&g_s.stage[slot], bytes);
+    if (e != cudaSuccess) return fail(QB_ERR_ALLOC, "cudaMalloc(staging)", e);
+    g_s.stage_bytes[slot] = bytes;
+  }
+  if (copy) {
+    cudaError_t e = cudaMemcpy(g_s.stage[slot], src, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMemcpy H2D", e);
+  }
+  *dptr = g_s.stage[slot];
+  *staged = true;
+  return QB_OK;
+}
+
+static inline q128 toq(const qb_quad *p) { q128 r; r.lo = p->lo; r.hi = p->hi; return r; }
+static inline bool is_col(char layout) { return layout == 'C' || layout == 'c'; }
+static inline bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' || t == 'c'; }
+
+/* extent in elements of a strided vector / matrix footprint */
+static inline size_t vec_bytes(int64_t n, int64_t inc) { return n <= 0 ? 0 : (size_t)((n - 1) * inc + 1) * 16; }
+static inline size_t mat_bytes(int64_t outer, int64_t inner, int64_t ld) { return (outer <= 0 || inner <= 0) ? 0 : (size_t)((outer - 1) * ld + inner) * 16; }
+
+static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, int64_t k, q128 alpha, const void *dA,
+                         int64_t lda, const void *dB, int64_t ldb, q128 beta, void *dC, int64_t ldc, cudaStream_t st)
+{
+  if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
+  const bool col = is_col(layout);
+  const bool honor = g_honor_trans.load() != 0;
+  const bool tA = honor && is_trans(ta), tB = honor && is_trans(tb);
+  GemmArgs g;
+  g.m = m; g.n = n; g.k = k; g.alpha = alpha; g.beta = beta;
+  g.A = (const q128 *)dA; g.B = (const q128 *)dB; g.C = (q128 *)dC;
+  /* element (i,l) of op(A): row-walk storage iff (col != tA) is false */
+  if (col != tA) { g.sai = 1; g.sal = lda; } else { g.sai = lda; g.sal = 1; }
+  if (col != tB) { g.sbl = 1; g.sbj = ldb; } else { g.sbl = ldb; g.sbj = 1; }
+  if (col) { g.sci = 1; g.scj = ldc; } else { g.sci = ldc; g.scj = 1; }
+  g.kc = g_kc.load();
+  cudaError_t e = launch_gemm(g, g_mode.load(), st);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm kernel launch", e);
+  return QB_OK;
+}
+
+} // namespace qb
+
+using namespace qb;
+
+extern "C" {
+
+/* ------------------------------------------------------------------ housekeeping */
+int qb_init(void)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaDeviceProp pr;
+  cudaError_t e = cudaGetDeviceProperties(&pr, g_s.device);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaGetDeviceProperties", e);
+  if (pr.major < 10) return fail(QB_ERR_CUDA, "qblas_b200 is built for sm_100a only; this device is older");
+  return QB_OK;
+}
+const char *qb_last_error(void) { return t_err_msg; }
+int qb_last_error_code(void) { return t_err_code; }
+void qb_clear_error(void) { t_err_code = 0; t_err_msg[0] = 0; }
+const char *qb_build_info(void) { return "qblas_b200 1.0.0 (sm_100a, integer-limb binary128; modes: reference-order, fast)"; }
+
+void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : QB_MODE_REFERENCE); }
+int qb_get_mode(void) { return g_mode.load(); }
+void qb_set_kc(int kc) { g_kc.store(kc > 0 ? kc : 126); }
+int qb_get_kc(void) { return g_kc.load(); }
+void qb_set_honor_trans(int on) { g_honor_trans.store(on ? 1 : 0); }
+int qb_get_honor_trans(void) { return g_honor_trans.load(); }
+int64_t qb_launch_count(void) { return g_launches.load(); }
+
+void quadblas_set_num_threads(int num_threads) { g_threads.store(num_threads); }
+int quadblas_get_num_threads(void) { return num_threads(); }
+const char *quadblas_get_version(void) { return "QuadBLAS 1.0.0 - High Performance Quad Precision BLAS"; }
+int quadblas_is_aligned(const void *ptr) { return ((uintptr_t)ptr % 32) == 0; }
+
+qb_quad qb_from_double(double d)
+{
+  uint64_t b; memcpy(&b, &d, 8);
+  q128 q = q_from_double_bits(b);
+  qb_quad r; r.lo = q.lo; r.hi = q.hi; return r;
+}
+double qb_to_double(qb_quad v)
+{
+  q128 q; q.lo = v.lo; q.hi = v.hi;
+  uint64_t b = q_to_double_bits(q);
+  double d; memcpy(&d, &b, 8); return d;
+}
+
+/* ------------------------------------------------------------------ device-pointer API */
+int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int64_t k, const qb_quad *alpha,
+                const void *dA, int64_t lda, const void *dB, int64_t ldb, const qb_quad *beta, void *dC,
+                int64_t ldc, void *stream)
+{
+  return gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), dC, ldc, (cudaStream_t)stream);
+}
+
+int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,
+                int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream)
+{
+  if (m < 0 || n < 0) return fail(QB_ERR_ARG, "qgemv: negative dimension");
+  GemvArgs g;
+  g.m = m; g.n = n; g.alpha = toq(alpha); g.beta = toq(beta);
+  g.A = (const q128 *)dA; g.lda = lda; g.col_major = is_col(layout);
+  g.x = (const q128 *)dx; g.incx = incx; g.y = (q128 *)dy; g.incy = incy;
+  cudaError_t e = launch_gemv(g, g_mode.load(), (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv kernel launch", e);
+  return QB_OK;
+}
+
+static int dot_dev_impl(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t incy, int do_sqrt,
+                        void *d_result, cudaStream_t st)
+{
+  if (n < 0) return fail(QB_ERR_ARG, "qdot: negative n");
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  const int mode = g_mode.load();
+  const int T = num_threads();
+  rc = ensure_work(dot_work_elems(n, T, mode));
+  if (rc) return rc;
+  DotArgs g;
+  g.n = n; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
+  g.T = T; g.do_sqrt = do_sqrt; g.result = (q128 *)d_result; g.work = g_s.work; g.work_elems = g_s.work_elems;
+  cudaError_t e = launch_dot(g, mode, st);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot kernel launch", e);
+  return QB_OK;
+}
+
+int qb_dot_dev(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t incy, void *d_result, void *stream)
+{ return dot_dev_impl(n, dx, incx, dy, incy, 0, d_result, (cudaStream_t)stream); }
+int qb_nrm2_dev(int64_t n, const void *dx, int64_t incx, void *d_result, void *stream)
+{ return dot_dev_impl(n, dx, incx, dx, incx, 1, d_result, (cudaStream_t)stream); }
+
+int qb_axpy_dev(int64_t n, const qb_quad *alpha, const void *dx, int64_t incx, void *dy, int64_t incy, void *stream)
+{
+  cudaError_t e = launch_axpy(n, toq(alpha), (const q128 *)dx, incx, (q128 *)dy, incy, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qaxpy kernel launch", e);
+  return QB_OK;
+}
+
+int qb_fold_partials_dev(int64_t count, const void *d_partials, int do_sqrt, void *d_result, void *stream)
+{
+  cudaError_t e = launch_fold(count, (const q128 *)d_partials, do_sqrt, (q128 *)d_result, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "fold kernel launch", e);
+  return QB_OK;
+}
+
+int qb_elementwise_dev(int op, int64_t n, const void *da, const void *db, const void *dc, void *dout, void *stream)
+{
+  cudaError_t e = launch_elementwise(op, n, (const q128 *)da, (const q128 *)db, (const q128 *)dc, (q128 *)dout, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "elementwise kernel launch", e);
+  return QB_OK;
+}
+
+int qb_fma_microbench_dev(int variant, int blocks, int threads, int iters, void *d_sink, int64_t *n_fma, void *stream)
+{
+  cudaError_t e = launch_fma_microbench(variant, blocks, threads, iters, (q128 *)d_sink, n_fma, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "microbench launch", e);
+  return QB_OK;
+}
+
+/* ------------------------------------------------------------------ host-or-device synchronous API */
+int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t k, const qb_quad *alpha, const void *A,
+            int64_t lda, const void *B, int64_t ldb, const qb_quad *beta, void *C, int64_t ldc)
+{
+  if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
+  if (m == 0 || n == 0 || k == 0) return QB_OK; /* level3.hpp:221 */
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  const bool col = is_col(layout);
+  const bool honor = g_honor_trans.load() != 0;
+  const bool tA = honor && is_trans(transa), tB = honor && is_trans(transb);
+  /* footprints: A is (col != tA) ? k-major : m-major */
+  const size_t a_bytes = (col != tA) ? mat_bytes(k, m, lda) : mat_bytes(m, k, lda);
+  const size_t b_bytes = (col != tB) ? mat_bytes(n, k, ldb) : mat_bytes(k, n, ldb);
+  const size_t c_bytes = col ? mat_bytes(n, m, ldc) : mat_bytes(m, n, ldc);
+  const void *dA, *dB, *dC; bool sa, sb, sc;
+  if ((rc = stage_in(0, A, a_bytes, true, &dA, &sa))) return rc;
+  if ((rc = stage_in(1, B, b_bytes, true, &dB, &sb))) return rc;
+  if ((rc = stage_in(2, C, c_bytes, true, &dC, &sc))) return rc; /* beta*C is always read (level3.hpp:107) */
+  rc = gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), (void *)dC, ldc, 0);
+  if (rc) return rc;
+  cudaError_t e;
+  if (sc) e = cudaMemcpy(C, dC, c_bytes, cudaMemcpyDeviceToHost); else e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm completion", e);
+  return QB_OK;
+}
+
+int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *A, int64_t lda, const void *x,
+            int64_t incx, const qb_quad *beta, void *y, int64_t incy)
+{
+  if (m < 0 || n < 0) return fail(QB_ERR_ARG, "qgemv: negative dimension");
+  if (m == 0 || n == 0) return QB_OK;
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  const bool col = is_col(layout);
+  const size_t a_bytes = col ? mat_bytes(n, m, lda) : mat_bytes(m, n, lda);
+  const size_t x_bytes = vec_bytes(n, incx), y_bytes = vec_bytes(m, incy);
+  const void *dA, *dx, *dy; bool sa, sx, sy;
+  if ((rc = stage_in(0, A, a_bytes, true, &dA, &sa))) return rc;
+  if ((rc = stage_in(1, x, x_bytes, true, &dx, &sx))) return rc;
+  if ((rc = stage_in(2, y, y_bytes, true, &dy, &sy))) return rc;
+  rc = qb_gemv_dev(layout, m, n, alpha, dA, lda, dx, incx, beta, (void *)dy, incy, 0);
+  if (rc) return rc;
+  cudaError_t e;
+  if (sy) e = cudaMemcpy(y, dy, y_bytes, cudaMemcpyDeviceToHost); else e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv completion", e);
+  return QB_OK;
+}
+
+static int dot_host_impl(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, int do_sqrt, qb_quad *result)
+{
+  if (n < 0) return fail(QB_ERR_ARG, "qdot: negative n");
+  const void *dx, *dy; bool sx = false, sy = false;
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  if ((rc = stage_in(0, x, vec_bytes(n, incx), true, &dx, &sx))) return rc;
+  if (y == x) { dy = dx; }
+  else if ((rc = stage_in(1, y, vec_bytes(n, incy), true, &dy, &sy))) return rc;
+  rc = dot_dev_impl(n, dx, incx, dy, incy, do_sqrt, g_s.result, 0);
+  if (rc) return rc;
+  q128 r;
+  cudaError_t e = cudaMemcpy(&r, g_s.result, 16, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot result copy", e);
+  result->lo = r.lo; result->hi = r.hi;
+  return QB_OK;
+}
+
+int qb_dot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, qb_quad *result)
+{ return dot_host_impl(n, x, incx, y, incy, 0, result); }
+int qb_nrm2(int64_t n, const void *x, int64_t incx, qb_quad *result)
+{ return dot_host_impl(n, x, incx, x, incx, 1, result); }
+
+int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *y, int64_t incy)
+{
+  if (n <= 0) return QB_OK; /* c_interface.hpp:49 */
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  const void *dx, *dy; bool sx, sy;
+  if ((rc = stage_in(0, x, vec_bytes(n, incx), true, &dx, &sx))) return rc;
+  if ((rc = stage_in(1, y, vec_bytes(n, incy), true, &dy, &sy))) return rc;
+  rc = qb_axpy_dev(n, alpha, dx, incx, (void *)dy, incy, 0);
+  if (rc) return rc;
+  cudaError_t e;
+  if (sy) e = cudaMemcpy(y, dy, vec_bytes(n, incy), cudaMemcpyDeviceToHost); else e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qaxpy completion", e);
+  return QB_OK;
+}
+
+/* ------------------------------------------------------------------ reference C ABI */
+double quadblas_qdot(int n, void *x, int incx, void *y, int incy)
+{
+  qb_quad r;
+  if (qb_dot(n, x, incx, y, incy, &r)) return std::numeric_limits<double>::quiet_NaN();
+  return qb_to_double(r); /* c_interface.hpp:30 */
+}
+
+double quadblas_qnrm2(int n, void *x, int incx)
+{
+  qb_quad r;
+  if (qb_nrm2(n, x, incx, &r)) return std::numeric_limits<double>::quiet_NaN();
+  return qb_to_double(r); /* c_interface.hpp:42-43 */
+}
+
+void quadblas_qaxpy(int n, double alpha, void *x, int incx, void *y, int incy)
+{
+  if (n <= 0) return; /* c_interface.hpp:49 */
+  qb_quad a = qb_from_double(alpha);
+  qb_axpy(n, &a, x, incx, y, incy);
+}
+
+void quadblas_qgemv(char layout, char trans, int m, int n, double alpha, void *A, int lda, void *x, int incx, double beta,
+                    void *y, int incy)
+{
+  qb_quad a = qb_from_double(alpha), b = qb_from_double(beta);
+  bool col = is_col(layout);
+  if (is_trans(trans)) { int t = m; m = n; n = t; col = !col; } /* c_interface.hpp:79-85 */
+  qb_gemv(col ? 'C' : 'R', m, n, &a, A, lda, x, incx, &b, y, incy);
+}
+
+void quadblas_qgemm(char layout, char transa, char transb, int m, int n, int k, double alpha, void *A, int lda, void *B,
+                    int ldb, double beta, void *C, int ldc)
+{
+  qb_quad a = qb_from_double(alpha), b = qb_from_double(beta);
+  qb_gemm(layout, transa, transb, m, n, k, &a, A, lda, B, ldb, &b, C, ldc);
+}
+
+} /* extern "C" */

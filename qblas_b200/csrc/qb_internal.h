@@ -1,0 +1,49 @@
+/* qb_internal.h — launcher prototypes shared by the kernel TUs and the C-ABI TU. */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "q128.cuh"
+
+namespace qb {
+
+/* strides are in elements (16 B each) */
+struct GemmArgs {
+  int64_t m, n, k;
+  q128 alpha, beta;
+  const q128 *A; int64_t sai, sal;   /* op(A)(i,l) = A[i*sai + l*sal] */
+  const q128 *B; int64_t sbl, sbj;   /* op(B)(l,j) = B[l*sbl + j*sbj] */
+  q128 *C; int64_t sci, scj;         /* C(i,j)    = C[i*sci + j*scj] */
+  int64_t kc;                        /* reference-order k-panel; >= k means a single chain */
+};
+cudaError_t launch_gemm(const GemmArgs &a, int mode, cudaStream_t st);
+
+struct GemvArgs {
+  int64_t m, n;                      /* y has m entries, x has n (after the C ABI's relabelling) */
+  q128 alpha, beta;
+  const q128 *A; int64_t lda;
+  int col_major;                     /* 0: A[i*lda+j] (level2.hpp:15-50), 1: A[j*lda+i] (level2.hpp:53-82) */
+  const q128 *x; int64_t incx;
+  q128 *y; int64_t incy;
+};
+cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st);
+
+struct DotArgs {
+  int64_t n;
+  const q128 *x; int64_t incx;
+  const q128 *y; int64_t incy;
+  int T;                             /* reference-order chunk count (quadblas_get_num_threads) */
+  int do_sqrt;                       /* nrm2 */
+  q128 *result;                      /* device, 16 B */
+  q128 *work; int64_t work_elems;    /* device scratch for partials */
+};
+int64_t dot_work_elems(int64_t n, int T, int mode);
+cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st);
+cudaError_t launch_fold(int64_t count, const q128 *partials, int do_sqrt, q128 *result, cudaStream_t st);
+
+cudaError_t launch_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy, cudaStream_t st);
+cudaError_t launch_elementwise(int op, int64_t n, const q128 *a, const q128 *b, const q128 *c, q128 *out, cudaStream_t st);
+cudaError_t launch_fma_microbench(int variant, int blocks, int threads, int iters, q128 *sink, int64_t *n_fma, cudaStream_t st);
+
+void count_launch(int n = 1);
+
+} // namespace qb

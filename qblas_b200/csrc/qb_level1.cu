@@ -1,0 +1,226 @@
+/*
+ * qb_level1.cu — binary128 dot / nrm2 (grid reduction) and axpy.
+ *
+ * Replaces QuadBLAS::dot (/root/reference/include/quadblas/algorithms/level1.hpp:80-137),
+ * dot_parallel (:38-77), dot_kernel_vectorized (:14-35), QuadBLAS::axpy (:190-223) and the
+ * sqrt in quadblas_qnrm2 / Vector::norm (interface/c_interface.hpp:34-44, cpp_classes.hpp:78-81).
+ *
+ * REFERENCE ORDER (mode 0): the reference's result depends on T = quadblas_get_num_threads()
+ * (threading/openmp_utils.hpp:10-17): unit stride and n >= 500 -> T contiguous chunks of n/T
+ * (last takes the remainder), each reduced by the two-lane kernel (even chain, odd chain,
+ * lane0+lane1, odd tail), partials folded with add from +0 in tid order; n < 500 -> one two-lane
+ * kernel; strided -> same chunking with ONE ascending chain per chunk (:104-120) or a single
+ * chain (:128-134).  One GPU thread runs one chain, so the bits are the reference's for any T.
+ *
+ * FAST (mode 1): a deterministic two-level tree.  Level 1: thread t of a fixed G x B grid
+ * accumulates elements t, t+GB, t+2GB, ... (fully coalesced 128-bit loads) with exact-rounded
+ * fma chains; the B partials of a CTA are reduced by a fixed binary tree in shared memory.
+ * Level 2: one CTA reduces the G block partials with the same fixed tree.  For fixed (n, G, B)
+ * the summation tree is fixed, hence run-to-run and GPU-to-GPU reproducible.
+ */
+#include "qb_internal.h"
+#include "q128_chain.cuh"
+
+namespace qb {
+
+__device__ __forceinline__ q128 ldg128_l1(const q128 *p)
+{
+  uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+  q128 r;
+  r.lo = ((uint64_t)v.y << 32) | v.x;
+  r.hi = ((uint64_t)v.w << 32) | v.z;
+  return r;
+}
+__device__ __noinline__ q128 l1_add(q128 a, q128 b) { return q_add(a, b); }
+
+/* ------------------------------------------------------------------ reference order */
+/* one thread = one chain.  lanes = 2: thread (t, lane) walks x[s + 2p + lane]; lanes = 1: thread t
+ * walks the whole chunk.  Output: part[t*lanes + lane]. */
+__global__ void k_dot_ref_chains(DotArgs g, int64_t chunk, int nchunks, int lanes)
+{
+  const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= (int64_t)nchunks * lanes) return;
+  const int64_t t = gt / lanes;
+  const int lane = (int)(gt % lanes);
+  const int64_t s = t * chunk;
+  const int64_t e = (t == nchunks - 1) ? g.n : s + chunk;
+  const int64_t len = e > s ? e - s : 0;
+  qacc acc = qacc_zero();
+  if (lanes == 2) {
+    const int64_t h = len / 2;
+    const q128 *xp = g.x + (s + lane) * g.incx, *yp = g.y + (s + lane) * g.incy;
+    for (int64_t p = 0; p < h; ++p)
+      qacc_fma(acc, qop_load(ldg128_l1(xp + 2 * p * g.incx)), qop_load(ldg128_l1(yp + 2 * p * g.incy)));
+  } else {
+    const q128 *xp = g.x + s * g.incx, *yp = g.y + s * g.incy;
+    for (int64_t p = 0; p < len; ++p)
+      qacc_fma(acc, qop_load(ldg128_l1(xp + p * g.incx)), qop_load(ldg128_l1(yp + p * g.incy)));
+  }
+  g.work[gt] = qacc_pack(acc);
+}
+
+/* per chunk: lane0 + lane1, then the odd tail (level1.hpp:27-32).  In place: work[t] <- chunk t. */
+__global__ void k_dot_ref_lanes(DotArgs g, int64_t chunk, int nchunks)
+{
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const int64_t s = t * chunk;
+  const int64_t e = (t == nchunks - 1) ? g.n : s + chunk;
+  const int64_t len = e > s ? e - s : 0;
+  q128 r = q_zero(0);
+  if (len > 0) {
+    r = l1_add(g.work[2 * t], g.work[2 * t + 1]);
+    if (len & 1) r = q_fma_slow_packed(g.x[(e - 1) * g.incx], g.y[(e - 1) * g.incy], r);
+  }
+  g.work[2 * (int64_t)nchunks + t] = r;
+}
+
+/* result = fold_t add(result, part[t]) from +0 in index order (level1.hpp:67-73); optional sqrt.
+ * A single thread: the order is the contract. `direct` = no fold (n < 500 path, level1.hpp:40-43). */
+__global__ void k_fold(const q128 *part, int64_t count, int direct, int do_sqrt, q128 *result)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  q128 r = q_zero(0);
+  if (direct) r = part[0];
+  else for (int64_t t = 0; t < count; ++t) r = l1_add(r, part[t]);
+  if (do_sqrt) r = q_sqrt(r);
+  *result = r;
+}
+
+/* ------------------------------------------------------------------ fast mode */
+template <int B>
+__device__ __forceinline__ q128 block_tree(q128 v, q128 *sh)
+{
+  sh[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll 1
+  for (int s = B / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = l1_add(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  return sh[0];
+}
+
+template <int B, int U>
+__global__ void __launch_bounds__(B)
+k_dot_fast_l1(DotArgs g)
+{
+  __shared__ q128 sh[B];
+  const int64_t nthreads = (int64_t)gridDim.x * B;
+  const int64_t t = (int64_t)blockIdx.x * B + threadIdx.x;
+  qacc acc[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) acc[u] = qacc_zero();
+  int64_t i = t;
+  /* U independent chains per thread: U loads in flight, U-way ILP in the integer pipes */
+  for (; i + (U - 1) * nthreads < g.n; i += U * nthreads) {
+    q128 xv[U], yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      xv[u] = ldg128_l1(g.x + (i + u * nthreads) * g.incx);
+      yv[u] = ldg128_l1(g.y + (i + u * nthreads) * g.incy);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) qacc_fma(acc[u], qop_load(xv[u]), qop_load(yv[u]));
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if (i + u * nthreads < g.n)
+      qacc_fma(acc[u], qop_load(ldg128_l1(g.x + (i + u * nthreads) * g.incx)), qop_load(ldg128_l1(g.y + (i + u * nthreads) * g.incy)));
+  q128 v = qacc_pack(acc[0]);
+#pragma unroll
+  for (int u = 1; u < U; ++u) v = l1_add(v, qacc_pack(acc[u]));
+  v = block_tree<B>(v, sh);
+  if (threadIdx.x == 0) g.work[blockIdx.x] = v;
+}
+
+template <int B>
+__global__ void __launch_bounds__(B)
+k_dot_fast_l2(const q128 *part, int count, int do_sqrt, q128 *result)
+{
+  __shared__ q128 sh[B];
+  q128 v = q_zero(0);
+  /* fixed assignment: thread t folds part[t], part[t+B], ... in order */
+  for (int i = threadIdx.x; i < count; i += B) v = l1_add(v, part[i]);
+  v = block_tree<B>(v, sh);
+  if (threadIdx.x == 0) *result = do_sqrt ? q_sqrt(v) : v;
+}
+
+static constexpr int FAST_B = 256;
+static constexpr int FAST_GRID = 148 * 4;
+
+int64_t dot_work_elems(int64_t n, int T, int mode)
+{
+  (void)n;
+  if (mode != 0) return FAST_GRID;
+  return 3 * (int64_t)(T < 1 ? 1 : T) + 4;
+}
+
+cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
+{
+  DotArgs g = a;
+  if (g.n == 0) { /* level1.hpp:83-84: +0 (sqrt(+0) = +0) */
+    cudaError_t e = cudaMemsetAsync(g.result, 0, 16, st);
+    return e;
+  }
+  if (mode != 0) {
+    int grid = FAST_GRID;
+    const int64_t need = (g.n + FAST_B - 1) / FAST_B;
+    if (need < grid) grid = (int)need;
+    k_dot_fast_l1<FAST_B, 4><<<grid, FAST_B, 0, st>>>(g);
+    k_dot_fast_l2<FAST_B><<<1, FAST_B, 0, st>>>(g.work, grid, g.do_sqrt, g.result);
+    count_launch(2);
+    return cudaGetLastError();
+  }
+  const bool unit = (g.incx == 1 && g.incy == 1);
+  const int T = g.T < 1 ? 1 : g.T;
+  int nchunks;
+  int64_t chunk;
+  if (g.n < 500) { nchunks = 1; chunk = g.n; }         /* PARALLEL_THRESHOLD, core/constants.hpp:15 */
+  else { nchunks = T; chunk = g.n / T; }
+  const int lanes = unit ? 2 : 1;
+  const int64_t nth = (int64_t)nchunks * lanes;
+  const int B = 64;
+  k_dot_ref_chains<<<(unsigned)((nth + B - 1) / B), B, 0, st>>>(g, chunk, nchunks, lanes);
+  const q128 *parts = g.work;
+  if (unit) {
+    k_dot_ref_lanes<<<(unsigned)((nchunks + B - 1) / B), B, 0, st>>>(g, chunk, nchunks);
+    parts = g.work + 2 * (int64_t)nchunks;
+    count_launch();
+  }
+  k_fold<<<1, 32, 0, st>>>(parts, nchunks, g.n < 500 ? 1 : 0, g.do_sqrt, g.result);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fold(int64_t count, const q128 *partials, int do_sqrt, q128 *result, cudaStream_t st)
+{
+  k_fold<<<1, 32, 0, st>>>(partials, count, 0, do_sqrt, result);
+  count_launch();
+  return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------ axpy */
+/* y_i = fma(alpha, x_i, y_i) (level1.hpp:140-223); order-free, so one kernel serves every mode */
+__global__ void k_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy)
+{
+  const qop al = qop_load(alpha);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    qacc acc = qacc_from(y[i * incy]);
+    qacc_fma(acc, al, qop_load(ldg128_l1(x + i * incx)));
+    y[i * incy] = qacc_pack(acc);
+  }
+}
+
+cudaError_t launch_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy, cudaStream_t st)
+{
+  if (n <= 0) return cudaSuccess;
+  const int B = 256;
+  int64_t grid = (n + B - 1) / B;
+  if (grid > 148 * 8) grid = 148 * 8;
+  k_axpy<<<(unsigned)grid, B, 0, st>>>(n, alpha, x, incx, y, incy);
+  count_launch();
+  return cudaGetLastError();
+}
+
+} // namespace qb

@@ -1,0 +1,128 @@
+/*
+ * qb_level3.cu — binary128 GEMM on the SM integer pipes.
+ *
+ * Replaces QuadBLAS::gemm and everything under it
+ * (/root/reference/include/quadblas/algorithms/level3.hpp:215-336 driver, :128-185 macro kernel,
+ * :20-126 micro kernels, :187-213 gemm_simple; blocking from detail/blocking.hpp:21-66).
+ *
+ * Reference order (what the bits depend on): per C element, k is cut into
+ * panels of kc (126); inside a panel s = fma chain from +0 in ascending l; panels are folded with
+ * C = fma(alpha, s, mul(q == 0 ? beta : 1, C)).  mc/nc/MR/NR and the thread count do not matter,
+ * so the whole M x N plane is parallel and only the k order is kept.
+ *
+ * Kernel shape: a CTA owns a BM x BN tile of C; A/B k-slices are staged in shared memory as raw
+ * 16-byte quads; each thread owns TM x TN accumulators kept UNPACKED in registers (qacc) and
+ * steps them with qacc_fma.  One qFMA costs ~150 integer instructions, so operand traffic
+ * (1 LDS.128 per several hundred instructions) is irrelevant: the kernel is bound by the
+ * IMAD/ALU issue rate, not by HBM, L2 or shared memory.
+ */
+#include "qb_internal.h"
+#include "q128_chain.cuh"
+
+namespace qb {
+
+/* C = fma(alpha, s, bq * C) with the reference's epilogue (level3.hpp:102-109 / :206-210). */
+__device__ __noinline__ q128 gemm_fold(q128 alpha, q128 s, q128 bq, q128 c, int apply_b)
+{
+  q128 t = apply_b ? q_mul(bq, c) : c; /* mul(1, c) == c exactly; skipping it changes no bit */
+  return q_fma(alpha, s, t);
+}
+
+template <int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+k_gemm(GemmArgs g)
+{
+  constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
+  __shared__ q128 sA[BK][BM];
+  __shared__ q128 sB[BK][BN];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int64_t i0 = (int64_t)blockIdx.y * BM, j0 = (int64_t)blockIdx.x * BN;
+  const q128 fill = q_one(); /* out-of-range rows/cols compute on 1.0 so they stay on the fast path */
+
+  qacc acc[TM][TN];
+  q128 cv[TM][TN];
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) {
+      acc[a][b] = qacc_zero();
+      const int64_t i = i0 + ty + a * TY, j = j0 + tx + b * TX;
+      cv[a][b] = (i < g.m && j < g.n) ? g.C[i * g.sci + j * g.scj] : q_zero(0);
+    }
+
+  int64_t pc = 0;     /* position inside the current k-panel */
+  int first = 1;      /* first panel uses beta, later ones 1 (level3.hpp:299) */
+  const bool a_l_contig = (g.sal == 1);
+  const bool b_j_contig = (g.sbj == 1);
+
+  for (int64_t l0 = 0; l0 < g.k; l0 += BK) {
+    /* ---- stage A[i0:i0+BM, l0:l0+BK] and B[l0:l0+BK, j0:j0+BN] ---- */
+    for (int idx = tid; idx < BM * BK; idx += NT) {
+      int i, l;
+      if (a_l_contig) { l = idx % BK; i = idx / BK; } else { i = idx % BM; l = idx / BM; }
+      const int64_t gi = i0 + i, gl = l0 + l;
+      sA[l][i] = (gi < g.m && gl < g.k) ? g.A[gi * g.sai + gl * g.sal] : fill;
+    }
+    for (int idx = tid; idx < BN * BK; idx += NT) {
+      int j, l;
+      if (b_j_contig) { j = idx % BN; l = idx / BN; } else { l = idx % BK; j = idx / BK; }
+      const int64_t gj = j0 + j, gl = l0 + l;
+      sB[l][j] = (gj < g.n && gl < g.k) ? g.B[gl * g.sbl + gj * g.sbj] : fill;
+    }
+    __syncthreads();
+
+    const int lim = (int)((g.k - l0) < BK ? (g.k - l0) : BK);
+    for (int l = 0; l < lim; ++l) {
+      qop a[TM], b[TN];
+#pragma unroll
+      for (int x = 0; x < TM; ++x) a[x] = qop_load(sA[l][ty + x * TY]);
+#pragma unroll
+      for (int x = 0; x < TN; ++x) b[x] = qop_load(sB[l][tx + x * TX]);
+#pragma unroll
+      for (int x = 0; x < TM; ++x)
+#pragma unroll
+        for (int y = 0; y < TN; ++y) qacc_fma(acc[x][y], a[x], b[y]);
+      if (++pc == g.kc) {
+#pragma unroll
+        for (int x = 0; x < TM; ++x)
+#pragma unroll
+          for (int y = 0; y < TN; ++y) {
+            cv[x][y] = gemm_fold(g.alpha, qacc_pack(acc[x][y]), g.beta, cv[x][y], first);
+            acc[x][y] = qacc_zero();
+          }
+        pc = 0;
+        first = 0;
+      }
+    }
+    __syncthreads();
+  }
+  if (pc > 0) {
+#pragma unroll
+    for (int x = 0; x < TM; ++x)
+#pragma unroll
+      for (int y = 0; y < TN; ++y) cv[x][y] = gemm_fold(g.alpha, qacc_pack(acc[x][y]), g.beta, cv[x][y], first);
+  }
+#pragma unroll
+  for (int a = 0; a < TM; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) {
+      const int64_t i = i0 + ty + a * TY, j = j0 + tx + b * TX;
+      if (i < g.m && j < g.n) g.C[i * g.sci + j * g.scj] = cv[a][b];
+    }
+}
+
+cudaError_t launch_gemm(const GemmArgs &a, int mode, cudaStream_t st)
+{
+  if (a.m == 0 || a.n == 0 || a.k == 0) return cudaSuccess; /* level3.hpp:221: C untouched */
+  GemmArgs g = a;
+  if (mode != 0 || g.kc <= 0) g.kc = (mode != 0) ? g.k : 126;
+  constexpr int BM = 32, BN = 32, BK = 16, TM = 2, TN = 2;
+  dim3 grid((unsigned)((g.n + BN - 1) / BN), (unsigned)((g.m + BM - 1) / BM));
+  k_gemm<BM, BN, BK, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(g);
+  count_launch();
+  return cudaGetLastError();
+}
+
+} // namespace qb

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <cstdint>
 #include <omp.h>
+#define QB_CHAIN_STATS 1
 #include "../../qblas_b200/csrc/q128.cuh"
 #include "../../qblas_b200/csrc/q128_chain.cuh"
 
@@ -256,9 +257,11 @@ int main(int argc, char **argv)
       }
     }
     total += n;
+    double fastfrac = (double)qb_chain_fast_hits / (double)(qb_chain_fast_hits + qb_chain_slow_hits + 1e-9);
+    qb_chain_fast_hits = qb_chain_slow_hits = 0;
     bool ok = !(bad_fma | bad_mul | bad_add | bad_sqrt | bad_cast | bad_chain);
-    printf("%-18s n=%ld fma_bad=%ld chain_bad=%ld mul_bad=%ld add_bad=%ld sqrt_bad=%ld cast_bad=%ld %s\n", names[reg], n, bad_fma,
-           bad_chain, bad_mul, bad_add, bad_sqrt, bad_cast, ok ? "OK" : "FAIL");
+    printf("%-18s n=%ld fma_bad=%ld chain_bad=%ld mul_bad=%ld add_bad=%ld sqrt_bad=%ld cast_bad=%ld fast=%.3f %s\n", names[reg], n, bad_fma,
+           bad_chain, bad_mul, bad_add, bad_sqrt, bad_cast, fastfrac, ok ? "OK" : "FAIL");
     if (!ok) ++failed;
   }
   printf("TOTAL fma vectors: %ld, failing regimes: %d\n", total, failed);

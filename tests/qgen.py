@@ -1,0 +1,103 @@
+"""TEST INFRASTRUCTURE: vectorised generators of binary128 test vectors (numpy, bit level)."""
+import numpy as np
+
+from qblas_b200 import quad
+
+BIAS = 16383
+
+
+def mk(sign, e, mh, ml):
+    out = np.zeros(np.shape(e) + (2,), dtype=np.uint64)
+    out[..., 0] = ml
+    out[..., 1] = (np.asarray(sign, dtype=np.uint64) << np.uint64(63)) | (np.asarray(e, dtype=np.uint64) << np.uint64(48)) | (
+        np.asarray(mh, dtype=np.uint64) & np.uint64((1 << 48) - 1))
+    return out
+
+
+def mantissas(rng, n):
+    """mixture: mostly full random, some double-like / sparse / all-ones / trailing zeros"""
+    mh = rng.integers(0, 1 << 48, size=n, dtype=np.uint64)
+    ml = rng.integers(0, 1 << 64, size=n, dtype=np.uint64)
+    kind = rng.integers(0, 12, size=n)
+    ml = np.where(kind == 5, ml & np.uint64(0xF000000000000000), ml)
+    ml = np.where(kind == 6, np.uint64(0), ml)
+    mh = np.where(kind == 6, mh & np.uint64(0xFFFFFF000000), mh)
+    ml = np.where(kind == 7, np.uint64(0xFFFFFFFFFFFFFFFF), ml)
+    mh = np.where(kind == 8, np.uint64(0), mh)
+    ml = np.where(kind == 8, np.uint64(0), ml)
+    ml = np.where(kind == 9, ml & np.uint64(1), ml)
+    mh = np.where(kind == 9, np.uint64(0), mh)
+    ml = np.where(kind == 10, ml & ~np.uint64(0xFFFFFFFFFF), ml)
+    return mh, ml
+
+
+def exp_of(q):
+    return ((q[..., 1] >> np.uint64(48)) & np.uint64(0x7FFF)).astype(np.int64)
+
+
+def triples(rng, n, regime):
+    """(a, b, c) arrays of n quads for fma(a, b, c); regimes mirror tests/host/q128_host_test.cpp"""
+    sa, sb, sc = (rng.integers(0, 2, size=n, dtype=np.uint64) for _ in range(3))
+    amh, aml = mantissas(rng, n)
+    bmh, bml = mantissas(rng, n)
+    cmh, cml = mantissas(rng, n)
+    r = rng.integers(0, 1 << 40, size=n)
+    clip = lambda e: np.clip(e, 0, 0x7FFE)
+    if regime == "any":
+        ea, eb, ec = (1 + rng.integers(0, 0x7FFE, size=n) for _ in range(3))
+    elif regime == "similar":
+        ea, eb, ec = (BIAS - 40 + rng.integers(0, 80, size=n) for _ in range(3))
+    elif regime == "cancel":
+        ea = BIAS - 20 + rng.integers(0, 40, size=n)
+        eb = BIAS - 20 + rng.integers(0, 40, size=n)
+        ec = ea + eb - BIAS + rng.integers(-2, 3, size=n)
+        sc = (sa ^ sb) ^ np.uint64(1)
+    elif regime == "gaps":
+        ea = BIAS - 10 + rng.integers(0, 20, size=n)
+        eb = BIAS - 10 + rng.integers(0, 20, size=n)
+        ec = ea + eb - BIAS + rng.integers(-260, 140, size=n)
+    elif regime == "tiny":
+        ea = np.where(r % 3 == 0, 0, rng.integers(0, 120, size=n))
+        eb = np.where((r >> 3) % 3 == 0, 0, rng.integers(0, 120, size=n))
+        ec = np.where((r >> 6) % 3 == 0, 0, rng.integers(0, 120, size=n))
+    elif regime == "subres":
+        ea = 1 + rng.integers(0, BIAS, size=n)
+        eb = clip(BIAS - ea - 60 + rng.integers(0, 200, size=n))
+        ec = np.where(r % 4 == 0, 0, rng.integers(0, 140, size=n))
+    elif regime == "overflow":
+        ea, eb, ec = (0x7FFE - rng.integers(0, 60, size=n) for _ in range(3))
+    elif regime == "nearovf":
+        ea = BIAS + rng.integers(0, BIAS, size=n)
+        eb = np.clip(0x7FFE + BIAS - ea - rng.integers(0, 8, size=n) + 2, 1, 0x7FFE)
+        ec = 0x7FFE - rng.integers(0, 130, size=n)
+    elif regime == "specials":
+        def sp(s, mh, ml):
+            k = rng.integers(0, 12, size=n)
+            e = BIAS - 3 + rng.integers(0, 6, size=n)
+            e = np.where(k == 0, 0, e); mh = np.where(k == 0, 0, mh); ml = np.where(k == 0, 0, ml)       # zero
+            e = np.where(k == 1, 0x7FFF, e); mh = np.where(k == 1, 0, mh); ml = np.where(k == 1, 0, ml)  # inf
+            e = np.where(k == 2, 0x7FFF, e); mh = np.where(k == 2, 1 << 47, mh)                          # nan
+            e = np.where(k == 3, 0, e); mh = np.where(k == 3, 0, mh); ml = np.where(k == 3, 1, ml)       # min subnormal
+            e = np.where(k == 4, 0, e)                                                                   # subnormal
+            e = np.where(k == 5, 0x7FFE, e)                                                              # huge
+            e = np.where(k == 6, 1, e)                                                                   # min normal range
+            return e, mh.astype(np.uint64), ml.astype(np.uint64)
+        ea, amh, aml = sp(sa, amh, aml)
+        eb, bmh, bml = sp(sb, bmh, bml)
+        ec, cmh, cml = sp(sc, cmh, cml)
+    else:
+        raise ValueError(regime)
+    a = mk(sa, clip(ea), amh, aml)
+    b = mk(sb, clip(eb), bmh, bml)
+    c = mk(sc, clip(ec), cmh, cml)
+    return a, b, c
+
+
+REGIMES = ["any", "similar", "cancel", "gaps", "tiny", "subres", "overflow", "nearovf", "specials"]
+
+
+def matrix(rng, rows, cols, kind="D113", ld=None):
+    """rows x cols quads stored with leading dimension ld >= cols (row-walk storage)."""
+    ld = cols if ld is None else ld
+    buf = quad.random_quads(rng, (rows, ld), "D113" if kind == "pad" else kind)
+    return np.ascontiguousarray(buf.reshape(rows * ld, 2))

@@ -1,0 +1,80 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/qblas_b200.h
+declares; non-compute entry points behave like the reference's; compute entry points fail loudly
+(never fall back to a CPU path) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import qblas_b200
+from qblas_b200 import quad
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "qblas_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:qb|quadblas)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_exports_every_declared_symbol():
+    L = qblas_b200.lib()
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(L, n), f"libqblas_b200.so does not export {n}"
+    assert set(names) == set(L._qb_signatures), "ctypes binding and header disagree"
+
+
+def test_version_threads_alignment():
+    assert qblas_b200.quadblas_get_version() == "QuadBLAS 1.0.0 - High Performance Quad Precision BLAS"  # c_interface.hpp:136
+    assert qblas_b200.quadblas_get_num_threads() == (os.cpu_count() or 1)
+    qblas_b200.quadblas_set_num_threads(5)
+    assert qblas_b200.quadblas_get_num_threads() == 5
+    qblas_b200.quadblas_set_num_threads(0)
+    L = qblas_b200.lib()
+    assert L.quadblas_is_aligned(C.c_void_p(64)) == 1 and L.quadblas_is_aligned(C.c_void_p(48)) == 0  # ALIGNMENT = 32
+
+
+def test_mode_and_kc_setters():
+    qblas_b200.set_mode(qblas_b200.MODE_FAST); assert qblas_b200.get_mode() == 1
+    qblas_b200.set_mode(qblas_b200.MODE_REFERENCE); assert qblas_b200.get_mode() == 0
+    L = qblas_b200.lib()
+    assert L.qb_get_kc() == 126
+    L.qb_set_kc(256); assert L.qb_get_kc() == 256
+    L.qb_set_kc(126)
+    assert L.qb_get_honor_trans() == 0
+
+
+def test_casts_match_oracle(oracle):
+    L = qblas_b200.lib()
+    rng = np.random.default_rng(1)
+    vals = list(rng.standard_normal(200)) + [0.0, -0.0, 5e-324, -2.2250738585072014e-308, 1.7976931348623157e308, float("inf")]
+    for d in vals:
+        q = L.qb_from_double(float(d))
+        o = oracle.from_double(d)
+        assert (q.lo, q.hi) == (int(o[0]), int(o[1]))
+        assert L.qb_to_double(q) == d or (d != d)
+    # narrowing with rounding: random full-mantissa quads, incl. the double-subnormal range
+    qs = quad.random_quads(rng, 4000, "D113", -1100, 1030)
+    for v in qs:
+        got = L.qb_to_double(qblas_b200._lib.QbQuad(lo=int(v[0]), hi=int(v[1])))
+        assert got == oracle.to_double(v)
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = quad.from_double(np.ones(4))
+    with pytest.raises(qblas_b200.QblasError):
+        qblas_b200.dot(4, x, 1, x, 1)
+    with pytest.raises(qblas_b200.QblasError):
+        qblas_b200.quadblas_qdot(4, x, 1, x, 1)
+    y = x.copy()
+    with pytest.raises(qblas_b200.QblasError):
+        qblas_b200.quadblas_qgemv("R", "N", 2, 2, 1.0, x, 2, x, 1, 0.0, y, 1)
+    assert quad.same_bits(x, y).all()  # outputs untouched on failure
