@@ -108,6 +108,12 @@ int qb_dot_dev(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t 
 int qb_nrm2_dev(int64_t n, const void *dx, int64_t incx, void *d_result, void *stream);
 int qb_axpy_dev(int64_t n, const qb_quad *alpha, const void *dx, int64_t incx, void *dy, int64_t incy,
                 void *stream);
+/* Reference-order partials of a SHARD of a dot: the reference cuts [0,n) into T chunks of n/T
+ * (level1.hpp:46-53); a rank that owns whole chunks calls this with its local vectors, the global
+ * chunk length and its number of chunks (the last local chunk runs to n_local) and gets one
+ * two-lane partial per chunk (unit strides) or one single-chain partial per chunk (strided). */
+int qb_dot_partials_dev(int64_t n_local, const void *dx, int64_t incx, const void *dy, int64_t incy, int64_t chunk,
+                        int64_t nchunks, void *d_partials, void *stream);
 /* Combine `count` binary128 partials (device) in index order with add from +0 — the exchange step
  * of a sharded dot: partials are all-gathered as bytes, then folded on device. */
 int qb_fold_partials_dev(int64_t count, const void *d_partials, int do_sqrt, void *d_result, void *stream);

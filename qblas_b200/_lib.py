@@ -68,6 +68,7 @@ def lib():
         "qb_dot_dev": (ci, [i64, vp, i64, vp, i64, vp, vp]),
         "qb_nrm2_dev": (ci, [i64, vp, i64, vp, vp]),
         "qb_axpy_dev": (ci, [i64, qp, vp, i64, vp, i64, vp]),
+        "qb_dot_partials_dev": (ci, [i64, vp, i64, vp, i64, i64, i64, vp, vp]),
         "qb_fold_partials_dev": (ci, [i64, vp, ci, vp, vp]),
         "qb_elementwise_dev": (ci, [ci, i64, vp, vp, vp, vp, vp]),
         "qb_from_double": (QbQuad, [cd]),

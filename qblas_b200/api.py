@@ -196,6 +196,12 @@ def axpy(n, alpha, x, incx, y, incy):
         check(L.qb_axpy(n, C.byref(a), _ptr(x), incx, _ptr(y), incy), "qb_axpy")
 
 
+def dot_partials(n_local, x, incx, y, incy, chunk, nchunks, out):
+    """Reference-order chunk partials of a local shard (see qb_dot_partials_dev)."""
+    check(lib().qb_dot_partials_dev(n_local, _ptr(x), incx, _ptr(y), incy, chunk, nchunks, _ptr(out), _stream()), "qb_dot_partials_dev")
+    return out
+
+
 def fold_partials(count, partials, out, do_sqrt=False):
     """Exchange step of a sharded dot: fold `count` device partials in index order."""
     check(lib().qb_fold_partials_dev(count, _ptr(partials), 1 if do_sqrt else 0, _ptr(out), _stream()), "qb_fold_partials_dev")

@@ -276,8 +276,78 @@ QB_HD uint32_t inc4c(uint32_t &n0, uint32_t &n1, uint32_t &n2, uint32_t &n3, uin
  * or consume non-normal accumulators. */
 QB_HD_NOINLINE q128 q_fma_slow_packed(q128 a, q128 b, q128 c) { return q_fma(a, b, c); }
 
-/* S <- RNE(A*B + S), bit-exact IEEE-754 binary128 FMA (Sleef_fmaq1_u05 semantics) */
-QB_HD void qacc_fma(qacc &S, const qop &A, const qop &B)
+/* ---- pipe-balancing primitives -------------------------------------------------------------
+ * ncu on the first version of the GEMM showed the ALU pipe (LOP3/SHF/SEL/IADD3) at 80 % and the
+ * FMA pipe (IMAD) at 16 % (profiles/r1a_gemm_ncu_full.txt).  The two pipes issue in parallel, so
+ * shifts and conditional complements are expressed as integer multiply-adds below: same bits,
+ * but the work lands on the idle pipe. */
+
+/* Hide a value's provenance from the compiler (no instruction is emitted).  Without it NVVM
+ * strength-reduces "multiply by a power of two" back into SHF and "x * +-1 + c" into LOP3. */
+QB_HD uint32_t opaque(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+  asm volatile("" : "+r"(x));
+#endif
+  return x;
+}
+
+/* conditional complement as ONE IMAD: with (sg, ad) = (1, 0) it returns x, with (0xffffffff,
+ * 0xffffffff) it returns -x - 1 == ~x.  cnot_coef builds the pair from a 0/1 flag. */
+struct cnot_coef { uint32_t sg, ad; };
+QB_HD cnot_coef cnot_make(uint32_t flag01)
+{
+  cnot_coef c;
+  c.ad = opaque(0u - flag01);
+  c.sg = opaque(c.ad | 1u);
+  return c;
+}
+QB_HD uint32_t cnot(uint32_t x, const cnot_coef &c) { return x * c.sg + c.ad; }
+
+QB_HD uint32_t umulhi32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+/* Multi-limb funnel shifts on the multiplier (IMAD.HI + IMAD, no 64-bit register pairs):
+ *   right by r in [1,32], M = 2^(32-r):  out = (hi >> r) | (lo... ) = lo32(hi_limb * M) + hi32(lo_limb * M)
+ *   left  by q in [0,31], M = 2^q     :  out = lo32(hi_limb * M) + hi32(lo_limb * M)
+ * i.e. the same formula; the two terms never overlap, so + is |. */
+QB_HD uint32_t mfunnel(uint32_t lo_limb, uint32_t hi_limb, uint32_t M) { return hi_limb * M + umulhi32(lo_limb, M); }
+
+/* number of trailing zero bits of a 113-bit mantissa (normal operands have m3 bit 16 set) */
+QB_HD uint32_t qop_tz(const qop &o)
+{
+  uint32_t w = o.m3, off = 96;
+  if (o.m2) { w = o.m2; off = 64; }
+  if (o.m1) { w = o.m1; off = 32; }
+  if (o.m0) { w = o.m0; off = 0; }
+#if defined(__CUDA_ARCH__)
+  return off + (uint32_t)(__ffs((int)w) - 1);
+#else
+  return off + (w ? (uint32_t)__builtin_ctz(w) : 32u);
+#endif
+}
+
+/* Per-thread scratch column for the whole-word part of the alignment shift.  On the GPU it lives
+ * in shared memory, laid out [word][thread] (stride = threads per CTA, a multiple of 32) so that
+ * the dynamically indexed loads are bank-conflict free whatever each lane's shift is; words 6..11
+ * must be zero and are never written.  This moves ~25 SEL/LOP3 per FMA from the saturated ALU pipe
+ * to the idle LSU pipe. */
+struct qscratch {
+  uint32_t *col;
+  uint32_t stride;
+};
+
+/* S <- RNE(A*B + S), bit-exact IEEE-754 binary128 FMA (Sleef_fmaq1_u05 semantics).
+ * USE_SCRATCH: whole-word alignment through the scratch column + jam bit from trailing-zero counts
+ * (tzsum = tz(A) + tz(B) = tz(A*B)); otherwise a select network with explicit OR tracking. */
+template <bool USE_SCRATCH>
+QB_HD void qacc_fma_t(qacc &S, const qop &A, const qop &B, const qscratch &scr, uint32_t tzsum)
 {
   /* ---- product (always computed; the slow path recomputes from the packed operands) ---- */
   uint32_t p[8];
@@ -289,60 +359,75 @@ QB_HD void qacc_fma(qacc &S, const qop &A, const qop &B)
   const uint32_t sp = A.s ^ B.s;
   const int32_t es = s_zero ? ep : S.e;
   const uint32_t ss = s_zero ? sp : S.s;
-  int32_t sh = es - ep + 97;                  /* frame bit 127 <-> accumulator MSB */
+  int32_t sh = es - ep + 97;                  /* P >> sh puts the product into the frame (bit 127 <-> MSB of S) */
   bool bad = !ab_normal || (S.e < 0) || (sh < 67);
   sh = sh > 255 ? 255 : sh;
-  const uint32_t wq = ((uint32_t)sh >> 5) - 2u;   /* extra whole words, 0..5 (garbage if bad) */
-  const uint32_t r = (uint32_t)sh & 31u;
+  sh = sh < 67 ? 67 : sh;                     /* keep the scratch index in range on the bad path */
+  /* sh = 32 * (wq + 2) + r with r in [1, 32]: the bit part is done by multiplying with 2^(32-r) */
+  const uint32_t shm1 = (uint32_t)sh - 1u;
+  const uint32_t wq = (shm1 >> 5) - 2u;       /* extra whole words, 0..5 */
+  const uint32_t M = opaque(0x80000000u >> (shm1 & 31u)); /* 2^(32-r) */
 
-  /* ---- P >> sh into the 160-bit frame, low bits jammed ---- */
-  /* p[0], p[1] always fall below the frame */
-  uint32_t lost = p[0] | p[1];
-  uint32_t t0, t1, t2, t3, t4, t5;
-  { /* stage A: by 4 words */
-    const bool w4 = (wq & 4u) != 0;
-    lost |= w4 ? (p[2] | p[3] | p[4] | p[5]) : 0u;
-    t0 = w4 ? p[6] : p[2]; t1 = w4 ? p[7] : p[3]; t2 = w4 ? 0u : p[4]; t3 = w4 ? 0u : p[5];
-    t4 = w4 ? 0u : p[6];   t5 = w4 ? 0u : p[7];
+  uint32_t t0, t1, t2, t3, t4, t5, jam;
+  if (USE_SCRATCH) {
+    /* whole-word part: t[j] = p[2 + wq + j] by dynamic indexing of the thread's scratch column */
+    uint32_t *c = scr.col;
+    const uint32_t st = scr.stride;
+    c[0] = p[2]; c[st] = p[3]; c[2 * st] = p[4]; c[3 * st] = p[5]; c[4 * st] = p[6]; c[5 * st] = p[7];
+    const uint32_t *q = c + wq * st;
+    t0 = q[0]; t1 = q[st]; t2 = q[2 * st]; t3 = q[3 * st]; t4 = q[4 * st]; t5 = q[5 * st];
+    /* bits of P below the frame are non-zero iff tz(P) < sh, and tz(a*b) = tz(a) + tz(b) */
+    jam = (tzsum < (uint32_t)sh) ? 1u : 0u;
+  } else {
+    uint32_t lost = p[0] | p[1];
+    { /* stage A: by 4 words */
+      const bool w4 = (wq & 4u) != 0;
+      lost |= w4 ? (p[2] | p[3] | p[4] | p[5]) : 0u;
+      t0 = w4 ? p[6] : p[2]; t1 = w4 ? p[7] : p[3]; t2 = w4 ? 0u : p[4]; t3 = w4 ? 0u : p[5];
+      t4 = w4 ? 0u : p[6];   t5 = w4 ? 0u : p[7];
+    }
+    { /* stage B: by 2 words */
+      const bool w2 = (wq & 2u) != 0;
+      lost |= w2 ? (t0 | t1) : 0u;
+      t0 = w2 ? t2 : t0; t1 = w2 ? t3 : t1; t2 = w2 ? t4 : t2; t3 = w2 ? t5 : t3;
+      t4 = w2 ? 0u : t4; t5 = w2 ? 0u : t5;
+    }
+    { /* stage C: by 1 word */
+      const bool w1 = (wq & 1u) != 0;
+      lost |= w1 ? t0 : 0u;
+      t0 = w1 ? t1 : t0; t1 = w1 ? t2 : t1; t2 = w1 ? t3 : t2; t3 = w1 ? t4 : t3;
+      t4 = w1 ? t5 : t4; t5 = w1 ? 0u : t5;
+    }
+    lost |= t0 * M;                              /* the bits of t0 that the bit part shifts out */
+    jam = (lost != 0) ? 1u : 0u;
   }
-  { /* stage B: by 2 words */
-    const bool w2 = (wq & 2u) != 0;
-    lost |= w2 ? (t0 | t1) : 0u;
-    t0 = w2 ? t2 : t0; t1 = w2 ? t3 : t1; t2 = w2 ? t4 : t2; t3 = w2 ? t5 : t3;
-    t4 = w2 ? 0u : t4; t5 = w2 ? 0u : t5;
-  }
-  { /* stage C: by 1 word */
-    const bool w1 = (wq & 1u) != 0;
-    lost |= w1 ? t0 : 0u;
-    t0 = w1 ? t1 : t0; t1 = w1 ? t2 : t1; t2 = w1 ? t3 : t2; t3 = w1 ? t4 : t3;
-    t4 = w1 ? t5 : t4; t5 = w1 ? 0u : t5;
-  }
-  lost |= t0 & ~(0xffffffffu << r);
-  uint32_t f0 = fshr(t0, t1, r), f1 = fshr(t1, t2, r), f2 = fshr(t2, t3, r), f3 = fshr(t3, t4, r),
-           f4 = fshr(t4, t5, r);
-  f0 |= (lost != 0);
+  /* ---- bit part: (t >> r) on the multiplier ---- */
+  const uint32_t f0 = mfunnel(t0, t1, M) | jam, f1 = mfunnel(t1, t2, M), f2 = mfunnel(t2, t3, M), f3 = mfunnel(t3, t4, M),
+                 f4 = mfunnel(t4, t5, M);
 
   /* ---- S +- P with end-around carry (one's complement subtract) ---- */
-  const bool sub = (ss != sp);
-  const uint32_t mk = sub ? 0xffffffffu : 0u;
+  const uint32_t sub = ss ^ sp;                 /* 0/1 */
+  const cnot_coef mk = cnot_make(sub);
   uint32_t g0, g1, g2, g3, g4;
-  const uint32_t cout = add5(S.m0, S.m1, S.m2, S.m3, f0 ^ mk, f1 ^ mk, f2 ^ mk, f3 ^ mk, f4 ^ mk, g0, g1, g2, g3, g4);
-  const bool neg = sub && !cout;                /* |P| > |S| : magnitude = ~T, sign flips */
-  const uint32_t nm = neg ? 0xffffffffu : 0u;
-  g0 ^= nm; g1 ^= nm; g2 ^= nm; g3 ^= nm; g4 ^= nm;
-  inc5(g0, g1, g2, g3, g4, sub ? cout : 0u);
-  const uint32_t sr = neg ? sp : ss;
+  const uint32_t cout = add5(S.m0, S.m1, S.m2, S.m3, cnot(f0, mk), cnot(f1, mk), cnot(f2, mk), cnot(f3, mk), cnot(f4, mk),
+                             g0, g1, g2, g3, g4);
+  const uint32_t neg = sub & (cout ^ 1u);       /* |P| > |S| : magnitude = ~T, sign flips */
+  const cnot_coef nm = cnot_make(neg);
+  g0 = cnot(g0, nm); g1 = cnot(g1, nm); g2 = cnot(g2, nm); g3 = cnot(g3, nm); g4 = cnot(g4, nm);
+  inc5(g0, g1, g2, g3, g4, sub & cout);
+  const uint32_t sr = ss ^ neg;                 /* sign flips iff the magnitudes swapped (then sp == ss ^ 1) */
 
-  /* ---- normalise: MSB to frame bit 159 ---- */
-  const bool top0 = (g4 == 0);
-  const uint32_t h4 = top0 ? g3 : g4, h3 = top0 ? g2 : g3, h2 = top0 ? g1 : g2, h1 = top0 ? g0 : g1,
-                 h0 = top0 ? 0u : g0;
-  const int lzw = clz32(h4);                    /* 32 if h4 == 0 -> bad */
-  const int lz = lzw + (top0 ? 32 : 0);
+  /* ---- normalise: MSB to frame bit 159.  lz in [0, 45] is split as q1 + q2 (each <= 31) and both
+   *      left shifts run on the multiplier ---- */
+  const int lz4 = clz32(g4);
+  const int lz = (g4 != 0) ? lz4 : 32 + clz32(g3);
   bad = bad || (lz > 45);                       /* > 13 bits of cancellation (or exact zero) */
-  const uint32_t q = (uint32_t)lzw & 31u;
-  uint32_t n3 = fshl(h3, h4, q), n2 = fshl(h2, h3, q), n1 = fshl(h1, h2, q), n0 = fshl(h0, h1, q);
-  const uint32_t rest = h0 << q;
+  const uint32_t q1 = (uint32_t)(lz > 31 ? 31 : lz) & 31u, q2 = (uint32_t)(lz > 31 ? lz - 31 : 0) & 31u;
+  const uint32_t M1 = opaque(1u << q1), M2 = opaque(1u << q2);
+  const uint32_t h0 = g0 * M1, h1 = mfunnel(g0, g1, M1), h2 = mfunnel(g1, g2, M1), h3 = mfunnel(g2, g3, M1),
+                 h4 = mfunnel(g3, g4, M1);
+  const uint32_t rest = h0 * M2;
+  uint32_t n0 = mfunnel(h0, h1, M2), n1 = mfunnel(h1, h2, M2), n2 = mfunnel(h2, h3, M2), n3 = mfunnel(h3, h4, M2);
   int32_t en = es + 32 - lz;
 
   /* ---- round to nearest even at bit 15 of n0 ---- */
@@ -363,11 +448,32 @@ QB_HD void qacc_fma(qacc &S, const qop &A, const qop &B)
   }
 }
 
-/* packed convenience wrapper (tests, epilogues) */
+/* register-only form (select network) */
+QB_HD void qacc_fma(qacc &S, const qop &A, const qop &B)
+{
+  qscratch none; none.col = nullptr; none.stride = 0;
+  qacc_fma_t<false>(S, A, B, none, 0u);
+}
+/* scratch-column form: tzsum = qop_tz(A) + qop_tz(B) */
+QB_HD void qacc_fma_sc(qacc &S, const qop &A, const qop &B, const qscratch &scr, uint32_t tzsum)
+{
+  qacc_fma_t<true>(S, A, B, scr, tzsum);
+}
+
+/* packed convenience wrappers (tests, epilogues) */
 QB_HD q128 q_fma_fast(q128 a, q128 b, q128 c)
 {
   qacc s = qacc_from(c);
   qacc_fma(s, qop_load(a), qop_load(b));
+  return qacc_pack(s);
+}
+/* scratch-column variant; `col` must have 12 words at the given stride with words 6..11 zero */
+QB_HD q128 q_fma_fast_sc(q128 a, q128 b, q128 c, uint32_t *col, uint32_t stride)
+{
+  qacc s = qacc_from(c);
+  const qop A = qop_load(a), B = qop_load(b);
+  qscratch scr; scr.col = col; scr.stride = stride;
+  qacc_fma_sc(s, A, B, scr, qop_tz(A) + qop_tz(B));
   return qacc_pack(s);
 }
 

@@ -249,6 +249,23 @@ int qb_axpy_dev(int64_t n, const qb_quad *alpha, const void *dx, int64_t incx, v
   return QB_OK;
 }
 
+int qb_dot_partials_dev(int64_t n_local, const void *dx, int64_t incx, const void *dy, int64_t incy, int64_t chunk,
+                        int64_t nchunks, void *d_partials, void *stream)
+{
+  if (n_local < 0 || nchunks < 0 || chunk < 0) return fail(QB_ERR_ARG, "qdot partials: negative argument");
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  rc = ensure_work(3 * nchunks + 4);
+  if (rc) return rc;
+  DotArgs g;
+  g.n = n_local; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
+  g.T = (int)nchunks; g.do_sqrt = 0; g.result = nullptr; g.work = g_s.work; g.work_elems = g_s.work_elems;
+  cudaError_t e = launch_dot_partials(g, chunk, (int)nchunks, (q128 *)d_partials, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot partials launch", e);
+  return QB_OK;
+}
+
 int qb_fold_partials_dev(int64_t count, const void *d_partials, int do_sqrt, void *d_result, void *stream)
 {
   cudaError_t e = launch_fold(count, (const q128 *)d_partials, do_sqrt, (q128 *)d_result, (cudaStream_t)stream);

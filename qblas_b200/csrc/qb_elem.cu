@@ -36,27 +36,41 @@ cudaError_t launch_elementwise(int op, int64_t n, const q128 *a, const q128 *b, 
 }
 
 /* ILP independent accumulators per thread, operands generated in registers (xorshift mantissas,
- * exponents near the bias, random signs) so that no memory traffic is involved.  Every step is a
- * full correctly rounded FMA through the same qacc_fma the kernels use. */
-template <int ILP>
-__global__ void k_fma_microbench(int iters, q128 *sink)
+ * exponents near the bias, random signs) so that no global memory traffic is involved.  Every step
+ * is a full correctly rounded FMA through the same qacc_fma / qacc_fma_sc the kernels use.
+ * SC = scratch-column form (the one k_gemm runs). */
+template <int ILP, bool SC, int NT>
+__global__ void __launch_bounds__(NT) k_fma_microbench(int iters, q128 *sink)
 {
+  __shared__ uint32_t scr[SC ? 12 * NT : 1];
+  qscratch sc;
+  sc.col = scr + threadIdx.x;
+  sc.stride = NT;
+  if (SC) {
+    for (int w = threadIdx.x; w < 12 * NT; w += NT) scr[w] = 0u;
+    __syncthreads();
+  }
   uint32_t s = 0x9e3779b9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
   auto next = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; };
   qop a[ILP], b;
+  uint32_t tza[ILP];
   qacc acc[ILP];
 #pragma unroll
   for (int u = 0; u < ILP; ++u) {
-    a[u].m0 = next(); a[u].m1 = next(); a[u].m2 = next(); a[u].m3 = (next() & 0xffffu) | 0x10000u;
+    a[u].m0 = next() | 1u; a[u].m1 = next(); a[u].m2 = next(); a[u].m3 = (next() & 0xffffu) | 0x10000u;
     a[u].e = 16383 - (int)(next() & 3); a[u].s = next() & 1;
+    tza[u] = 0;
     acc[u] = qacc_zero();
   }
-  b.m0 = next(); b.m1 = next(); b.m2 = next(); b.m3 = (next() & 0xffffu) | 0x10000u; b.e = 16383; b.s = 0;
+  b.m0 = next() | 1u; b.m1 = next(); b.m2 = next(); b.m3 = (next() & 0xffffu) | 0x10000u; b.e = 16383; b.s = 0;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int u = 0; u < ILP; ++u) qacc_fma(acc[u], a[u], b);
-    /* perturb the shared operand so that nothing is loop invariant */
-    b.m0 += 0x9e3779b9u; b.m1 ^= b.m0; b.s ^= (b.m0 >> 7) & 1u;
+    for (int u = 0; u < ILP; ++u) {
+      if (SC) qacc_fma_sc(acc[u], a[u], b, sc, tza[u]);  /* odd mantissas: tz(a) + tz(b) = 0 */
+      else qacc_fma(acc[u], a[u], b);
+    }
+    /* perturb the shared operand so that nothing is loop invariant (bit 0 stays set) */
+    b.m0 += 0x9e3779b8u; b.m1 ^= b.m0; b.s ^= (b.m0 >> 7) & 1u;
   }
   q128 r = qacc_pack(acc[0]);
 #pragma unroll
@@ -64,14 +78,20 @@ __global__ void k_fma_microbench(int iters, q128 *sink)
   if (r.lo == 0x1234567 && r.hi == 0x7654321) sink[0] = r; /* keep the result alive */
 }
 
+/* variant = 100 * SC + ILP (ILP in {1,2,4}); threads must be 128 or 256 */
 cudaError_t launch_fma_microbench(int variant, int blocks, int threads, int iters, q128 *sink, int64_t *n_fma, cudaStream_t st)
 {
-  int ilp = 1;
-  switch (variant) {
-  case 1: k_fma_microbench<1><<<blocks, threads, 0, st>>>(iters, sink); ilp = 1; break;
-  case 2: k_fma_microbench<2><<<blocks, threads, 0, st>>>(iters, sink); ilp = 2; break;
-  default: k_fma_microbench<4><<<blocks, threads, 0, st>>>(iters, sink); ilp = 4; break;
+  const int ilp = variant % 100, scv = variant / 100;
+  if ((ilp != 1 && ilp != 2 && ilp != 4) || (threads != 128 && threads != 256)) return cudaErrorInvalidValue;
+#define QB_MB(I, S, T) k_fma_microbench<I, S, T><<<blocks, T, 0, st>>>(iters, sink)
+  if (threads == 128) {
+    if (!scv) { if (ilp == 1) QB_MB(1, false, 128); else if (ilp == 2) QB_MB(2, false, 128); else QB_MB(4, false, 128); }
+    else      { if (ilp == 1) QB_MB(1, true, 128);  else if (ilp == 2) QB_MB(2, true, 128);  else QB_MB(4, true, 128); }
+  } else {
+    if (!scv) { if (ilp == 1) QB_MB(1, false, 256); else if (ilp == 2) QB_MB(2, false, 256); else QB_MB(4, false, 256); }
+    else      { if (ilp == 1) QB_MB(1, true, 256);  else if (ilp == 2) QB_MB(2, true, 256);  else QB_MB(4, true, 256); }
   }
+#undef QB_MB
   if (n_fma) *n_fma = (int64_t)blocks * threads * iters * ilp;
   count_launch();
   return cudaGetLastError();

@@ -38,6 +38,7 @@ struct DotArgs {
 };
 int64_t dot_work_elems(int64_t n, int T, int mode);
 cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st);
+cudaError_t launch_dot_partials(const DotArgs &a, int64_t chunk, int nchunks, q128 *partials, cudaStream_t st);
 cudaError_t launch_fold(int64_t count, const q128 *partials, int do_sqrt, q128 *result, cudaStream_t st);
 
 cudaError_t launch_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy, cudaStream_t st);

@@ -193,6 +193,28 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
   return cudaGetLastError();
 }
 
+/* partials of `nchunks` reference-order chunks of a local shard; work must hold 3*nchunks quads */
+cudaError_t launch_dot_partials(const DotArgs &a, int64_t chunk, int nchunks, q128 *partials, cudaStream_t st)
+{
+  DotArgs g = a;
+  if (nchunks <= 0) return cudaSuccess;
+  const bool unit = (g.incx == 1 && g.incy == 1);
+  const int lanes = unit ? 2 : 1;
+  const int64_t nth = (int64_t)nchunks * lanes;
+  const int B = 64;
+  k_dot_ref_chains<<<(unsigned)((nth + B - 1) / B), B, 0, st>>>(g, chunk, nchunks, lanes);
+  count_launch();
+  const q128 *src = g.work;
+  if (unit) {
+    k_dot_ref_lanes<<<(unsigned)((nchunks + B - 1) / B), B, 0, st>>>(g, chunk, nchunks);
+    count_launch();
+    src = g.work + 2 * (int64_t)nchunks;
+  }
+  cudaError_t e = cudaMemcpyAsync(partials, src, (size_t)nchunks * 16, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
 cudaError_t launch_fold(int64_t count, const q128 *partials, int do_sqrt, q128 *result, cudaStream_t st)
 {
   k_fold<<<1, 32, 0, st>>>(partials, count, 0, do_sqrt, result);

@@ -33,13 +33,20 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_gemm(GemmArgs g)
 {
   constexpr int TX = BN / TN, TY = BM / TM, NT = TX * TY;
+  static_assert(NT % 32 == 0, "scratch columns need a multiple of 32 threads");
   __shared__ q128 sA[BK][BM];
   __shared__ q128 sB[BK][BN];
+  __shared__ unsigned char zA[BK][BM], zB[BK][BN]; /* trailing-zero counts of the mantissas (jam test) */
+  __shared__ uint32_t scr[12 * NT];                /* per-thread scratch columns, [word][thread] */
 
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int64_t i0 = (int64_t)blockIdx.y * BM, j0 = (int64_t)blockIdx.x * BN;
   const q128 fill = q_one(); /* out-of-range rows/cols compute on 1.0 so they stay on the fast path */
+  for (int w = tid; w < 12 * NT; w += NT) scr[w] = 0u; /* words 6..11 of every column stay zero */
+  qscratch sc;
+  sc.col = scr + tid;
+  sc.stride = NT;
 
   qacc acc[TM][TN];
   q128 cv[TM][TN];
@@ -63,27 +70,32 @@ k_gemm(GemmArgs g)
       int i, l;
       if (a_l_contig) { l = idx % BK; i = idx / BK; } else { i = idx % BM; l = idx / BM; }
       const int64_t gi = i0 + i, gl = l0 + l;
-      sA[l][i] = (gi < g.m && gl < g.k) ? g.A[gi * g.sai + gl * g.sal] : fill;
+      const q128 v = (gi < g.m && gl < g.k) ? g.A[gi * g.sai + gl * g.sal] : fill;
+      sA[l][i] = v;
+      zA[l][i] = (unsigned char)qop_tz(qop_load(v));
     }
     for (int idx = tid; idx < BN * BK; idx += NT) {
       int j, l;
       if (b_j_contig) { j = idx % BN; l = idx / BN; } else { l = idx % BK; j = idx / BK; }
       const int64_t gj = j0 + j, gl = l0 + l;
-      sB[l][j] = (gj < g.n && gl < g.k) ? g.B[gl * g.sbl + gj * g.sbj] : fill;
+      const q128 v = (gj < g.n && gl < g.k) ? g.B[gl * g.sbl + gj * g.sbj] : fill;
+      sB[l][j] = v;
+      zB[l][j] = (unsigned char)qop_tz(qop_load(v));
     }
     __syncthreads();
 
     const int lim = (int)((g.k - l0) < BK ? (g.k - l0) : BK);
     for (int l = 0; l < lim; ++l) {
       qop a[TM], b[TN];
+      uint32_t za[TM], zb[TN];
 #pragma unroll
-      for (int x = 0; x < TM; ++x) a[x] = qop_load(sA[l][ty + x * TY]);
+      for (int x = 0; x < TM; ++x) { a[x] = qop_load(sA[l][ty + x * TY]); za[x] = zA[l][ty + x * TY]; }
 #pragma unroll
-      for (int x = 0; x < TN; ++x) b[x] = qop_load(sB[l][tx + x * TX]);
+      for (int x = 0; x < TN; ++x) { b[x] = qop_load(sB[l][tx + x * TX]); zb[x] = zB[l][tx + x * TX]; }
 #pragma unroll
       for (int x = 0; x < TM; ++x)
 #pragma unroll
-        for (int y = 0; y < TN; ++y) qacc_fma(acc[x][y], a[x], b[y]);
+        for (int y = 0; y < TN; ++y) qacc_fma_sc(acc[x][y], a[x], b[y], sc, za[x] + zb[y]);
       if (++pc == g.kc) {
 #pragma unroll
         for (int x = 0; x < TM; ++x)

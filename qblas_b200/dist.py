@@ -1,0 +1,144 @@
+"""Multi-GPU sharding of the hot path: one process per GPU, torch.distributed for the plumbing
+(NCCL over NVLink on the GPU box, gloo in the CPU tests).  SURVEY.md §8e:
+
+  qgemm : C (and A) split into contiguous row blocks; B broadcast as bytes; C blocks all-gathered
+          as bytes.  The per-element reduction order does not depend on the row split, so the
+          result is bitwise the 1-GPU result in both modes.
+  qgemv : row blocks of A / y; x broadcast; y blocks all-gathered.
+  qdot  : contiguous index ranges.  NCCL has no binary128 sum, so there is NO all-reduce: the
+          16-byte partials are all-gathered as bytes and folded on every rank in a fixed order
+          with the library's own add.  In reference-order mode the ranges are whole reference
+          chunks (n/T each, level1.hpp:46-53), so the fold over all T partials in tid order is
+          exactly the reference's.
+
+`compute` is the per-rank engine (default: the CUDA library through qblas_b200.api).  The CPU
+tests inject a stand-in so that the partition / collective logic is covered without a GPU.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def row_block(m: int, world: int, rank: int):
+    """Contiguous block [lo, hi) of `m` rows for `rank`; the first m % world ranks get one extra row."""
+    base, rem = divmod(m, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def chunk_block(T: int, world: int, rank: int):
+    """Contiguous block of reference-order dot chunks [c0, c1) owned by `rank`."""
+    return row_block(T, world, rank)
+
+
+def _bytes(t: torch.Tensor) -> torch.Tensor:
+    return t.view(torch.uint8)
+
+
+class _CudaEngine:
+    """Default per-rank engine: libqblas_b200.so on the current CUDA device."""
+
+    def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+        from . import api
+        api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+
+    def gemv(self, m, n, alpha, A, lda, x, beta, y):
+        from . import api
+        api.gemv("R", m, n, alpha, A, lda, x, 1, beta, y, 1)
+
+    def dot_partials(self, n_local, x, y, chunk, nchunks, out):
+        from . import api
+        api.dot_partials(n_local, x, 1, y, 1, chunk, nchunks, out)
+
+    def dot_fast(self, n_local, x, y, out):
+        from . import api
+        api.dot(n_local, x, 1, y, 1, out)
+
+    def fold(self, count, partials, out, do_sqrt=False):
+        from . import api
+        api.fold_partials(count, partials, out, do_sqrt)
+
+
+def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None):
+    """C_full (m x n, row-major, identical buffer shape on every rank) <- alpha*A*B + beta*C.
+    A_blk holds this rank's rows [lo, hi) of A (row-major, lda = k); B (k x n) is valid on `src`
+    and is overwritten by the broadcast elsewhere.  Returns (lo, hi)."""
+    compute = compute or _CudaEngine()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = row_block(m, world, rank)
+    dist.broadcast(_bytes(B), src=src, group=group)
+    C_blk = C_full[lo * n:hi * n]
+    if hi > lo:
+        compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
+    if m % world == 0:
+        dist.all_gather_into_tensor(_bytes(C_full), _bytes(C_blk), group=group)
+    else:  # ragged: one broadcast per owner (grouped broadcasts)
+        for r in range(world):
+            l2, h2 = row_block(m, world, r)
+            if h2 > l2:
+                dist.broadcast(_bytes(C_full[l2 * n:h2 * n]), src=r, group=group)
+    return lo, hi
+
+
+def qgemv_row_sharded(m, n, alpha, A_blk, x, beta, y_full, *, src=0, compute=None, group=None):
+    compute = compute or _CudaEngine()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = row_block(m, world, rank)
+    dist.broadcast(_bytes(x), src=src, group=group)
+    if hi > lo:
+        compute.gemv(hi - lo, n, alpha, A_blk, n, x, beta, y_full[lo:hi])
+    for r in range(world):
+        l2, h2 = row_block(m, world, r)
+        if h2 > l2:
+            dist.broadcast(_bytes(y_full[l2:h2]), src=r, group=group)
+    return lo, hi
+
+
+def dot_shard_range(n: int, T: int, world: int, rank: int, reference_order: bool):
+    """Element range [lo, hi) of the vectors that `rank` must hold."""
+    if reference_order and n >= 500:
+        chunk = n // T
+        c0, c1 = chunk_block(T, world, rank)
+        lo = c0 * chunk
+        hi = n if c1 == T else c1 * chunk
+        return lo, hi
+    if reference_order:          # n < 500: the reference runs one kernel over everything (level1.hpp:40)
+        return (0, n) if rank == 0 else (0, 0)
+    return row_block(n, world, rank)
+
+
+def qdot_sharded(n, x_loc, y_loc, T, out, *, reference_order=True, do_sqrt=False, compute=None, group=None):
+    """x_loc / y_loc: this rank's slice (see dot_shard_range).  `out`: 16-byte device buffer that
+    receives the full result on EVERY rank (all ranks fold the same gathered partials)."""
+    compute = compute or _CudaEngine()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev, dt = x_loc.device, x_loc.dtype
+    if reference_order:
+        if n < 500:
+            Tn, chunk = 1, n
+        else:
+            Tn, chunk = T, n // T
+        c0, c1 = chunk_block(Tn, world, rank)
+        per = -(-Tn // world)  # padded slots per rank so that one all_gather serves ragged splits
+        mine = torch.zeros((per, 2), dtype=dt, device=dev)
+        lo, hi = dot_shard_range(n, T, world, rank, True)
+        if c1 > c0:
+            compute.dot_partials(hi - lo, x_loc, y_loc, chunk, c1 - c0, mine[:c1 - c0])
+        gathered = torch.zeros((world * per, 2), dtype=dt, device=dev)
+        dist.all_gather_into_tensor(_bytes(gathered), _bytes(mine), group=group)
+        # compact to tid order (drop the padding slots of ragged splits)
+        parts = torch.cat([gathered[r * per:r * per + (chunk_block(Tn, world, r)[1] - chunk_block(Tn, world, r)[0])] for r in range(world)])
+        if n < 500:
+            # the reference returns the single kernel result directly (no +0 fold)
+            out.copy_(parts[:1].reshape(out.shape)) if not do_sqrt else compute.fold(1, parts, out, True)
+        else:
+            compute.fold(Tn, parts.contiguous(), out, do_sqrt)
+        return out
+    mine = torch.zeros((1, 2), dtype=dt, device=dev)
+    lo, hi = dot_shard_range(n, T, world, rank, False)
+    compute.dot_fast(hi - lo, x_loc, y_loc, mine)
+    gathered = torch.zeros((world, 2), dtype=dt, device=dev)
+    dist.all_gather_into_tensor(_bytes(gathered), _bytes(mine), group=group)
+    compute.fold(world, gathered, out, do_sqrt)
+    return out

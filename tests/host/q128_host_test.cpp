@@ -210,6 +210,9 @@ int main(int argc, char **argv)
         /* chain-form fma (the kernels' primitive) must agree with the generic one */
         {
           q128 rc = qb::q_fma_fast(a, b, c);
+          uint32_t col[24] = {0};
+          q128 rc2 = qb::q_fma_fast_sc(a, b, c, col, 2);
+          if (!same(rc2, e)) rc = rc2;
           if (!same(rc, e)) {
             ++bad_chain;
             if (!printed) {
