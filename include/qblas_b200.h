@@ -85,6 +85,20 @@ int qb_get_kc(void);
 void qb_set_honor_trans(int on);         /* extension: honour transa/transb in qgemm (default 0) */
 int qb_get_honor_trans(void);
 
+/* Fast-mode qgemm on the tensor cores (exact int8 slicing + tcgen05 kind::i8, csrc/qb_ozaki.cu):
+ * 0 = never (integer-limb kernel only), 1 = automatic (m,n >= 128 and k >= 256; default),
+ * 2 = whenever the planner accepts the operands.  Ignored in QB_MODE_REFERENCE. */
+void qb_set_tensor_path(int v);
+int qb_get_tensor_path(void);
+/* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, S_A*S_B int8 GEMMs,
+ * workspace bytes, 0} */
+void qb_oz_last_stats(int64_t *out8);
+/* The tensor-core kernel alone (tests/profiling): D[d] = sum_{s+t=d} A_s B_t^T over k-blocks
+ * [kb_begin, kb_begin+nkb) of 128; planes are int8 [S][rows][Kp] (device), D is int32
+ * [S_A+S_B-1][Mp][Np] with Mp % 128 == 0, Np % 256 == 0. */
+int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp,
+                     int64_t kb_begin, int64_t nkb, void *dD, int64_t Mp, int64_t Np, void *stream);
+
 /* Quad-typed, host-or-device pointers, synchronous.  alpha/beta/result are HOST pointers to one
  * binary128 each.  Semantics = QuadBLAS::gemm/gemv/dot/axpy (level3.hpp:215, level2.hpp:85,
  * level1.hpp:80,190) and Vector::dot / Vector::norm (cpp_classes.hpp:66-81). */

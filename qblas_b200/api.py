@@ -221,3 +221,32 @@ def fma_microbench(variant, blocks, threads, iters, sink):
     n = C.c_int64(0)
     check(lib().qb_fma_microbench_dev(variant, blocks, threads, iters, _ptr(sink), C.byref(n), _stream()), "qb_fma_microbench_dev")
     return n.value
+
+
+# ------------------------------------------------------------------ fast-mode tensor path (csrc/qb_ozaki.cu)
+TENSOR_OFF, TENSOR_AUTO, TENSOR_ALWAYS = 0, 1, 2
+
+
+def set_tensor_path(v):
+    lib().qb_set_tensor_path(int(v))
+
+
+def get_tensor_path():
+    return lib().qb_get_tensor_path()
+
+
+def oz_last_stats():
+    """Plan of the last tensor-path qgemm."""
+    out = (C.c_int64 * 8)()
+    lib().qb_oz_last_stats(out)
+    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes"]
+    return {k: int(out[i]) for i, k in enumerate(keys)}
+
+
+def oz_i8gemm(planesA, planesB, m, n, D, kb_begin=0, nkb=None):
+    """The tcgen05 kernel alone: planes are torch int8 CUDA tensors [S][rows][Kp], D int32 [SA+SB-1][Mp][Np]."""
+    SA, _, Kp = planesA.shape
+    SB = planesB.shape[0]
+    nkb = Kp // 128 - kb_begin if nkb is None else nkb
+    check(lib().qb_oz_i8gemm_dev(C.c_void_p(planesA.data_ptr()), C.c_void_p(planesB.data_ptr()), SA, SB, m, n, Kp, kb_begin, nkb,
+                                 C.c_void_p(D.data_ptr()), D.shape[1], D.shape[2], _stream()), "qb_oz_i8gemm_dev")

@@ -29,6 +29,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_mode{QB_MODE_REFERENCE};
 static std::atomic<int> g_kc{126};
 static std::atomic<int> g_honor_trans{0};
+static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_threads{0}; /* 0 = not set -> hardware concurrency (omp_get_max_threads analogue) */
 
 static thread_local int t_err_code = 0;
@@ -143,7 +144,19 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
   if (col != tB) { g.sbl = 1; g.sbj = ldb; } else { g.sbl = ldb; g.sbj = 1; }
   if (col) { g.sci = 1; g.scj = ldc; } else { g.sci = ldc; g.scj = 1; }
   g.kc = g_kc.load();
-  cudaError_t e = launch_gemm(g, g_mode.load(), st);
+  const int mode = g_mode.load(), tp = g_tensor.load();
+  if (mode == QB_MODE_FAST && m > 0 && n > 0 && k > 0 && (tp == 2 || (tp == 1 && m >= 128 && n >= 128 && k >= 256))) {
+    /* tensor-core path (exact int8 slicing, qb_ozaki.cu); declines -> integer-limb kernel below */
+    std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
+    int used = 0;
+    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget);
+    if (oe != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm tensor path", oe);
+    if (used) return QB_OK;
+  }
+  cudaError_t e = launch_gemm(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm kernel launch", e);
   return QB_OK;
 }
@@ -173,6 +186,23 @@ const char *qb_build_info(void) { return "qblas_b200 1.0.0 (sm_100a, integer-lim
 
 void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : QB_MODE_REFERENCE); }
 int qb_get_mode(void) { return g_mode.load(); }
+void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
+int qb_get_tensor_path(void) { return g_tensor.load(); }
+void qb_oz_last_stats(int64_t *out8)
+{
+  const OzStats s = oz_last_stats();
+  out8[0] = s.SA; out8[1] = s.SB; out8[2] = s.ndiag; out8[3] = s.nchunks; out8[4] = s.row_passes; out8[5] = s.pairs; out8[6] = s.ws_bytes; out8[7] = 0;
+}
+int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int64_t kb_begin,
+                     int64_t nkb, void *dD, int64_t Mp, int64_t Np, void *stream)
+{
+  if (SA < 1 || SB < 1 || SA > QB_OZ_MAX_SLICES || SB > QB_OZ_MAX_SLICES || Kp % 128 || Mp % 128 || Np % 256 || Mp < m || Np < n)
+    return fail(QB_ERR_ARG, "qb_oz_i8gemm_dev: bad geometry");
+  cudaError_t e = launch_oz_mma((const int8_t *)dPlanesA, (const int8_t *)dPlanesB, SA, SB, m, n, Kp, (int)kb_begin, (int)nkb, (int32_t *)dD, Mp,
+                                Np, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "int8 diagonal GEMM launch", e);
+  return QB_OK;
+}
 void qb_set_kc(int kc) { g_kc.store(kc > 0 ? kc : 126); }
 int qb_get_kc(void) { return g_kc.load(); }
 void qb_set_honor_trans(int on) { g_honor_trans.store(on ? 1 : 0); }

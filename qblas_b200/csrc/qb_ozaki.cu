@@ -1,0 +1,607 @@
+/*
+ * qb_ozaki.cu — fast-mode binary128 GEMM on the 5th-generation tensor cores.
+ *
+ * What it replaces: the arithmetic of QuadBLAS::gemm (/root/reference/include/quadblas/algorithms/
+ * level3.hpp:215-336; hot loop :77-85 = one Sleef_fmaq2_u05 per two products) when the library is
+ * in QB_MODE_FAST.  Fast mode is free to re-associate (last paragraph); this
+ * path goes further and computes every dot product EXACTLY, then rounds once:
+ *
+ *   scan   : per row of op(A) / column of op(B): largest exponent and lowest set mantissa bit
+ *   plan   : W = widest row span in bits  ->  S = ceil((W + 2) / 8) signed 8-bit slices, so that
+ *            every element is represented EXACTLY as  x = 2^base(row) * sum_s d_s 256^(S-1-s),
+ *            d_s in [-128, 127]  (row-wise block fixed point, no truncation at all)
+ *   slice  : write the S int8 digit planes, K-major, for A ([S_A][m][Kp]) and B ([S_B][n][Kp])
+ *   mma    : for every diagonal d = s + t:  D_d = sum_{s+t=d} A_s * B_t^T  as ONE K-concatenated
+ *            int8 x int8 -> int32 GEMM on tcgen05 (kind::i8), operands staged by TMA into 128-byte
+ *            swizzled shared memory, accumulators in TMEM, warp-specialised persistent kernel.
+ *            Exact: |d| <= 128 and Kc * min(S_A, S_B) * 2^14 < 2^31 (K is cut into chunks of Kc).
+ *   fold   : I = sum_d D_d 256^(ndiag-1-d) as a 448-bit two's complement integer per C element
+ *            (accumulated across K chunks in a workspace), one correctly rounded conversion to
+ *            binary128, then the reference epilogue  C = fma(alpha, s, mul(beta, C))
+ *            (level3.hpp:102-109).
+ *
+ * Accuracy: the inner product is exact, so |c^ - c| <= u |A B|_ij (+ the two epilogue roundings),
+ * far inside the fast-mode contract  gamma_k (|A||B|)_ij.  Inputs this cannot represent (Inf/NaN,
+ * or a row whose exponent span needs more than QB_OZ_MAX_SLICES digits) make the planner decline
+ * and the caller runs the integer-limb kernel (qb_level3.cu) instead; that is a different CUDA
+ * kernel of this library, not a CPU fallback.
+ */
+#include "qb_internal.h"
+#include "qb_tc.cuh"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace qb {
+
+/* ------------------------------------------------------------------ geometry */
+static constexpr int OZ_BM = 128;            /* C tile rows   = UMMA M */
+static constexpr int OZ_BN = 256;            /* C tile cols   = UMMA N */
+static constexpr int OZ_BK = 128;            /* bytes (= int8 elements) of K per pipeline stage = one 128 B swizzle row */
+static constexpr int OZ_UK = 32;             /* K per tcgen05.mma kind::i8 */
+static constexpr int OZ_STAGES = 4;
+static constexpr int OZ_A_BYTES = OZ_BM * OZ_BK; /* 16 KiB */
+static constexpr int OZ_B_BYTES = OZ_BN * OZ_BK; /* 32 KiB */
+static constexpr int OZ_STAGE_BYTES = OZ_A_BYTES + OZ_B_BYTES;
+static constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+static constexpr int OZ_THREADS = 192;       /* warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue */
+static constexpr int OZ_MAX_S = QB_OZ_MAX_SLICES;
+static constexpr int OZ_MAX_DIAG = 2 * OZ_MAX_S - 1;
+static constexpr int OZ_NL = 14;             /* 32-bit limbs of the exact integer (448 bits) */
+
+struct OzMmaArgs {
+  int32_t *D;                 /* [ndiag][Mp][Np] int32 */
+  int64_t Mp, Np;             /* padded to tile multiples */
+  int SA, SB, ndiag;
+  int m_tiles, n_tiles;
+  int kb_begin, nkb;          /* k-blocks of OZ_BK for this K chunk */
+  uint8_t order[OZ_MAX_DIAG + 1]; /* diagonals, heaviest first */
+};
+
+/* ------------------------------------------------------------------ the tensor-core kernel */
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzMmaArgs g)
+{
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *bars = (uint64_t *)(smem + OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t *full = bars;                       /* [OZ_STAGES] TMA -> MMA */
+  uint64_t *empty = bars + OZ_STAGES;          /* [OZ_STAGES] MMA -> TMA */
+  uint64_t *tfull = bars + 2 * OZ_STAGES;      /* [2] MMA -> epilogue */
+  uint64_t *tempty = bars + 2 * OZ_STAGES + 2; /* [2] epilogue -> MMA */
+  uint32_t *tmem_slot = (uint32_t *)(bars + 2 * OZ_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tc::prefetch_tmap(&tmA);
+    tc::prefetch_tmap(&tmB);
+    for (int s = 0; s < OZ_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tfull[a], 1); tc::mbar_init(&tempty[a], 4); }
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512); /* 2 accumulators x 256 columns */
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_diag = g.m_tiles * g.n_tiles;
+  const int total = g.ndiag * tiles_per_diag;
+
+  if (warp == 0) {
+    /* ===================== TMA producer (one thread) ===================== */
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int d = g.order[tile / tiles_per_diag];
+        const int rem = tile % tiles_per_diag;
+        const int mt = rem / g.n_tiles, nt = rem % g.n_tiles;
+        const int s_lo = d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0;
+        const int s_hi = d < g.SA - 1 ? d : g.SA - 1;
+        for (int s = s_lo; s <= s_hi; ++s) {
+          const int t = d - s;
+          for (int kb = 0; kb < g.nkb; ++kb) {
+            tc::mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t *sa = smem + stage * OZ_STAGE_BYTES;
+            uint8_t *sb = sa + OZ_A_BYTES;
+            tc::mbar_expect_tx(&full[stage], OZ_STAGE_BYTES);
+            const int kc = (g.kb_begin + kb) * OZ_BK;
+            tc::tma_load_3d(sa, &tmA, &full[stage], kc, mt * OZ_BM, s);
+            tc::tma_load_3d(sb, &tmB, &full[stage], kc, nt * OZ_BN, t);
+            if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    /* ===================== MMA issuer (one thread) ===================== */
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_i8(OZ_BM, OZ_BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int d = g.order[tile / tiles_per_diag];
+        const int s_lo = d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0;
+        const int s_hi = d < g.SA - 1 ? d : g.SA - 1;
+        const int iters = (s_hi - s_lo + 1) * g.nkb;
+        tc::mbar_wait(&tempty[acc], acc_phase ^ 1); /* epilogue has drained this accumulator */
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * OZ_BN;
+        for (int it = 0; it < iters; ++it) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + stage * OZ_STAGE_BYTES);
+          const uint64_t adesc = tc::make_kmajor_sw128_desc(sa);
+          const uint64_t bdesc = tc::make_kmajor_sw128_desc(sa + OZ_A_BYTES);
+#pragma unroll
+          for (int k = 0; k < OZ_BK / OZ_UK; ++k)
+            tc::mma_i8_ss(tmem_d, adesc + (uint64_t)(k * OZ_UK >> 4), bdesc + (uint64_t)(k * OZ_UK >> 4), idesc,
+                          (it | k) != 0 ? 1u : 0u);
+          tc::tc_commit(&empty[stage]); /* frees the smem slot when these MMAs have read it */
+          if (++stage == OZ_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc::tc_commit(&tfull[acc]);     /* accumulator complete */
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    /* ===================== epilogue: TMEM -> registers -> D (int32) ===================== */
+    const int quarter = warp & 3;       /* TMEM lanes 32*quarter .. +31 are the ones this warp may read */
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int d = g.order[tile / tiles_per_diag];
+      const int rem = tile % tiles_per_diag;
+      const int mt = rem / g.n_tiles, nt = rem % g.n_tiles;
+      tc::mbar_wait(&tfull[acc], acc_phase);
+      tc::tc_fence_after();
+      const int64_t row = (int64_t)mt * OZ_BM + quarter * 32 + lane;
+      int32_t *dst = g.D + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * OZ_BN;
+#pragma unroll 1
+      for (int c = 0; c < OZ_BN / 32; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(taddr + c * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4 *>(dst + c * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+/* ------------------------------------------------------------------ scan: row spans */
+/* element fields: value = (-1)^s * M * 2^(ee - 16495), M < 2^113 */
+struct OzElem { uint64_t lo, hi; int ee; uint32_t sign; int special; };
+__device__ __forceinline__ OzElem oz_unpack(q128 a)
+{
+  OzElem o;
+  const uint32_t ef = (uint32_t)(a.hi >> 48) & 0x7fffu;
+  o.sign = (uint32_t)(a.hi >> 63);
+  o.special = ef == 0x7fffu;
+  o.lo = a.lo;
+  o.hi = (a.hi & Q_MANT_HI_MASK) | (ef ? Q_IMPLICIT : 0);
+  o.ee = ef ? (int)ef : 1;
+  return o;
+}
+__device__ __forceinline__ int oz_tz(uint64_t lo, uint64_t hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
+
+/* rows x K view: X[r * sr + k * sk].  emax[r] = max ee over non-zero elements (0 if none),
+ * lmin[r] = min (ee + tz(M)); flags |= 1 on Inf/NaN.  One warp per (row, 1024-wide k chunk) when k
+ * is the contiguous direction, otherwise one thread per (row, chunk) with lanes along rows. */
+__global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, int *emax, int *lmin, int *flags)
+{
+  constexpr int CH = 1024;
+  const int64_t nchunk = (K + CH - 1) / CH;
+  int em = 0, lm = 0x7fffffff, sp = 0;
+  int64_t r;
+  if (sk == 1 || sr != 1) { /* warp per (row, chunk), lanes along k */
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= rows * nchunk) return;
+    r = w / nchunk;
+    const int64_t k0 = (w % nchunk) * CH, k1 = k0 + CH < K ? k0 + CH : K;
+    for (int64_t k = k0 + lane; k < k1; k += 32) {
+      const OzElem e = oz_unpack(X[r * sr + k * sk]);
+      sp |= e.special;
+      if (e.lo | e.hi) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      em = max(em, __shfl_xor_sync(0xffffffffu, em, o));
+      lm = min(lm, __shfl_xor_sync(0xffffffffu, lm, o));
+      sp |= __shfl_xor_sync(0xffffffffu, sp, o);
+    }
+    if (lane != 0) return;
+  } else { /* rows contiguous: thread per (row, chunk), lanes along rows */
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= rows * nchunk) return;
+    r = t % rows;
+    const int64_t k0 = (t / rows) * CH, k1 = k0 + CH < K ? k0 + CH : K;
+    for (int64_t k = k0; k < k1; ++k) {
+      const OzElem e = oz_unpack(X[r * sr + k * sk]);
+      sp |= e.special;
+      if (e.lo | e.hi) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
+    }
+  }
+  if (em) { atomicMax(&emax[r], em); atomicMin(&lmin[r], lm); }
+  if (sp) atomicOr(flags, 1);
+}
+
+/* out[0] = widest span of A rows, out[1] = widest span of B columns, out[2] = flags */
+__global__ void k_oz_plan(const int *emaxA, const int *lminA, int64_t m, const int *emaxB, const int *lminB, int64_t n, const int *flags, int *out)
+{
+  __shared__ int sw[2];
+  if (threadIdx.x == 0) { sw[0] = 0; sw[1] = 0; }
+  __syncthreads();
+  int wa = 0, wb = 0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) if (emaxA[i]) wa = max(wa, emaxA[i] + 113 - lminA[i]);
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) if (emaxB[j]) wb = max(wb, emaxB[j] + 113 - lminB[j]);
+  atomicMax(&sw[0], wa);
+  atomicMax(&sw[1], wb);
+  __syncthreads();
+  if (threadIdx.x == 0) { out[0] = sw[0]; out[1] = sw[1]; out[2] = *flags; }
+}
+
+/* ------------------------------------------------------------------ slice: exact signed 8-bit digits */
+/* thread = (row r, 4 consecutive k); plane s (0 = most significant digit) is [rows][Kp] int8.
+ * x = X_int * 2^(base - 16495), base = emax[r] + 115 - 8 S, |X_int| < 2^(8S-2); digits are the
+ * balanced base-256 expansion of X_int (so the sign needs no separate plane). */
+template <int MAXS>
+__global__ void k_oz_slice(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax, int S, int64_t Kp,
+                           int8_t *__restrict__ planes)
+{
+  const int64_t groups = Kp >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= rows * groups) return;
+  int64_t r, g4;
+  if (sk == 1 || sr != 1) { r = tid / groups; g4 = tid % groups; }   /* lanes along k */
+  else { r = tid % rows; g4 = tid / rows; }                          /* lanes along rows (rows contiguous in memory) */
+  const int base = emax[r] + 115 - 8 * S;
+  uint32_t word[MAXS];
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) word[s] = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t k = g4 * 4 + q;
+    if (k >= K) continue;
+    const OzElem e = oz_unpack(X[r * sr + k * sk]);
+    if (!(e.lo | e.hi) || e.special) continue;
+    u256 v; v.w0 = e.lo; v.w1 = e.hi; v.w2 = 0; v.w3 = 0;
+    const int sh = e.ee - base;
+    v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact by construction of S */
+    const uint64_t w[4] = {v.w0, v.w1, v.w2, v.w3};
+    /* balanced digits, least significant first; a negative number takes digits of its magnitude
+     * in [-127, 128] and negates them, so both signs land in [-128, 127] */
+    uint32_t carry = 0;
+    const uint32_t thr = 128u + e.sign;
+#pragma unroll
+    for (int j = 0; j < MAXS; ++j) {
+      if (j < S) {
+        uint32_t t = (uint32_t)((w[j >> 3] >> (8 * (j & 7))) & 0xffu) + carry;
+        carry = t >= thr ? 1u : 0u;                 /* digit = t - 256 */
+        const uint32_t dig = e.sign ? (0u - t) : t; /* low 8 bits are the int8 digit either way */
+        word[j] |= (dig & 0xffu) << (8 * q);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXS; ++j)
+    if (j < S) *reinterpret_cast<uint32_t *>(planes + ((int64_t)(S - 1 - j) * rows + r) * Kp + g4 * 4) = word[j];
+}
+
+/* ------------------------------------------------------------------ fold: diagonals -> binary128 */
+struct OzFoldArgs {
+  const int32_t *D; int64_t Mp, Np; int ndiag;
+  int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
+  const int *emaxA, *emaxB; int SA, SB;
+  uint32_t *W; int w_in, w_out;      /* 448-bit running sums across K chunks: [OZ_NL][Mp*Np] */
+  q128 alpha, beta; q128 *C; int64_t sci, scj;
+};
+
+__global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
+{
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = idx / g.n, j = idx % g.n;
+  if (i >= g.m) return;
+  const int64_t plane = g.Mp * g.Np, off = i * g.Np + j;
+  uint32_t L[OZ_NL];
+  long long carry = 0;
+#pragma unroll
+  for (int l = 0; l < OZ_NL; ++l) {
+    long long acc = carry;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int d = g.ndiag - 1 - (4 * l + b);
+      if (d >= 0) acc += (long long)g.D[(int64_t)d * plane + off] << (8 * b);
+    }
+    L[l] = (uint32_t)acc;
+    carry = acc >> 32;
+  }
+  if (g.w_in) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int l = 0; l < OZ_NL; ++l) {
+      const uint64_t t = (uint64_t)L[l] + g.W[(int64_t)l * plane + off] + c;
+      L[l] = (uint32_t)t; c = (uint32_t)(t >> 32);
+    }
+  }
+  if (g.w_out) {
+#pragma unroll
+    for (int l = 0; l < OZ_NL; ++l) g.W[(int64_t)l * plane + off] = L[l];
+    return;
+  }
+  /* ---- sign / magnitude ---- */
+  const uint32_t neg = L[OZ_NL - 1] >> 31;
+  if (neg) {
+    uint32_t c = 1;
+#pragma unroll
+    for (int l = 0; l < OZ_NL; ++l) { const uint64_t t = (uint64_t)(~L[l]) + c; L[l] = (uint32_t)t; c = (uint32_t)(t >> 32); }
+  }
+  int top = -1;
+#pragma unroll
+  for (int l = 0; l < OZ_NL; ++l) if (L[l]) top = l;
+  q128 sum;
+  if (top < 0) {
+    sum = q_zero(0); /* an exact zero sum is +0 (a +0-seeded chain never yields -0) */
+  } else {
+    /* 9-limb window ending at the top limb, through a local buffer (dynamic index) */
+    uint32_t buf[OZ_NL + 8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) buf[l] = 0;
+#pragma unroll
+    for (int l = 0; l < OZ_NL; ++l) buf[8 + l] = L[l];
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = buf[top + k];
+    uint32_t sticky = 0;
+#pragma unroll
+    for (int l = 0; l < OZ_NL; ++l) if (l < top - 8) sticky |= L[l];
+    const int lz = __clz((int)w[8]);
+    uint32_t R[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) R[k] = __funnelshift_l(w[k], w[k + 1], lz);
+    sticky |= w[0] << lz; /* lz == 0: w[0] is entirely below the window */
+    if (lz == 0) sticky |= w[0];
+    u256 Rq;
+    Rq.w0 = ((uint64_t)R[1] << 32) | R[0] | (sticky != 0);
+    Rq.w1 = ((uint64_t)R[3] << 32) | R[2];
+    Rq.w2 = ((uint64_t)R[5] << 32) | R[4];
+    Rq.w3 = ((uint64_t)R[7] << 32) | R[6];
+    /* I * 2^Eb, Eb = baseA + baseB - 2 * 16495; MSB of I at bit p = 32 top + 31 - lz  ->  er = p + Eb + QBIAS */
+    const int baseA = g.emaxA[g.row0 + i] + 115 - 8 * g.SA, baseB = g.emaxB[j] + 115 - 8 * g.SB;
+    const int p = 32 * top + 31 - lz;
+    const int er = p + baseA + baseB - 2 * 16495 + QBIAS;
+    sum = q_round_pack(neg, er, Rq);
+  }
+  q128 *c = g.C + i * g.sci + j * g.scj;
+  *c = q_fma(g.alpha, sum, q_mul(g.beta, *c)); /* level3.hpp:102-109: beta*C is always evaluated */
+}
+
+/* ------------------------------------------------------------------ host side */
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode()
+{
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  });
+  return fn;
+}
+
+/* planes [S][rows][Kp] int8 -> 3-D map {Kp, rows, S}, box {128, box_rows, 1}, 128-byte swizzle; rows
+ * beyond `rows` are zero-filled by the TMA unit */
+static bool make_plane_map(CUtensorMap *tm, const int8_t *planes, int S, int64_t rows, int64_t Kp, int box_rows)
+{
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static int g_sm_count = 0;
+static int sm_count()
+{
+  if (!g_sm_count) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+/* D[d] = sum_{s+t=d} A_s B_t^T over k-blocks [kb_begin, kb_begin + nkb) */
+cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
+                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_oz_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!make_plane_map(&tmA, pA, SA, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, SB, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
+  OzMmaArgs g;
+  g.D = D; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
+  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
+  g.kb_begin = kb_begin; g.nkb = nkb;
+  /* heaviest diagonals first so the static round-robin over CTAs stays balanced */
+  int idx[OZ_MAX_DIAG + 1];
+  for (int d = 0; d < g.ndiag; ++d) idx[d] = d;
+  auto pairs = [&](int d) { return std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; };
+  std::stable_sort(idx, idx + g.ndiag, [&](int a, int b) { return pairs(a) > pairs(b); });
+  for (int d = 0; d < g.ndiag; ++d) g.order[d] = (uint8_t)idx[d];
+  const int total = g.ndiag * g.m_tiles * g.n_tiles;
+  const int grid = std::min(total, sm_count());
+  k_oz_mma<<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+  count_launch();
+  return cudaGetLastError();
+}
+
+/* ---- workspaces (grow-only, per process; callers hold the library mutex) ----
+ * meta: per-row exponent data + plan (small, survives a regrowth of the big buffer)
+ * buf : digit planes, diagonals, wide accumulators */
+struct OzWork {
+  void *buf = nullptr; size_t bytes = 0;
+  void *meta = nullptr; size_t meta_bytes = 0;
+  int device = -1;
+  int *h_plan = nullptr; /* pinned, 16 ints */
+};
+static OzWork g_oz;
+static cudaError_t oz_grow(void **p, size_t *have, size_t want)
+{
+  if (want <= *have) return cudaSuccess;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *have = 0;
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) return e;
+  *have = want;
+  return cudaSuccess;
+}
+static cudaError_t oz_reserve(size_t meta_bytes, size_t bytes)
+{
+  int dev = 0; cudaGetDevice(&dev);
+  if (g_oz.device != dev) { /* buffers of another device are left to that context */
+    g_oz.buf = nullptr; g_oz.bytes = 0; g_oz.meta = nullptr; g_oz.meta_bytes = 0; g_oz.device = dev;
+  }
+  if (!g_oz.h_plan) { cudaError_t e = cudaMallocHost((void **)&g_oz.h_plan, 64); if (e != cudaSuccess) return e; }
+  cudaError_t e = oz_grow(&g_oz.meta, &g_oz.meta_bytes, meta_bytes);
+  if (e != cudaSuccess) return e;
+  return oz_grow(&g_oz.buf, &g_oz.bytes, bytes);
+}
+void oz_release()
+{
+  if (g_oz.buf) cudaFree(g_oz.buf);
+  if (g_oz.meta) cudaFree(g_oz.meta);
+  g_oz.buf = nullptr; g_oz.bytes = 0; g_oz.meta = nullptr; g_oz.meta_bytes = 0;
+}
+
+static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static OzStats g_last_stats;
+OzStats oz_last_stats() { return g_last_stats; }
+
+/* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget)
+{
+  *used = 0;
+  { const int64_t keep = g_last_stats.ws_bytes; g_last_stats = OzStats(); g_last_stats.ws_bytes = keep; }
+  if (!get_encode()) return cudaSuccess;
+  const int64_t m = a.m, n = a.n, k = a.k;
+  const int64_t Kp = rup(k, OZ_BK);
+  /* ---- scan + plan ---- */
+  const size_t meta_ints = (size_t)(2 * m + 2 * n + 16);
+  cudaError_t e = oz_reserve(meta_ints * 4, 0);
+  if (e != cudaSuccess) return e;
+  int *meta = (int *)g_oz.meta;
+  int *emaxA = meta, *lminA = meta + m, *emaxB = meta + 2 * m, *lminB = meta + 2 * m + n, *flags = meta + 2 * m + 2 * n, *plan = flags + 4;
+  {
+    cudaMemsetAsync(emaxA, 0, (size_t)m * 4, st); cudaMemsetAsync(lminA, 0x7f, (size_t)m * 4, st);
+    cudaMemsetAsync(emaxB, 0, (size_t)n * 4, st); cudaMemsetAsync(lminB, 0x7f, (size_t)n * 4, st);
+    cudaMemsetAsync(flags, 0, 64, st);
+    const int64_t nch = (k + 1023) / 1024;
+    {
+      const bool warp_mode = (a.sal == 1 || a.sai != 1);
+      const int64_t threads = warp_mode ? m * nch * 32 : m * nch;
+      k_oz_scan<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.A, m, k, a.sai, a.sal, emaxA, lminA, flags);
+    }
+    {
+      const bool warp_mode = (a.sbl == 1 || a.sbj != 1);
+      const int64_t threads = warp_mode ? n * nch * 32 : n * nch;
+      k_oz_scan<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.B, n, k, a.sbj, a.sbl, emaxB, lminB, flags);
+    }
+    k_oz_plan<<<1, 1024, 0, st>>>(emaxA, lminA, m, emaxB, lminB, n, flags, plan);
+    count_launch(3);
+    e = cudaMemcpyAsync(g_oz.h_plan, plan, 16, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+  }
+  const int WA = g_oz.h_plan[0], WB = g_oz.h_plan[1], fl = g_oz.h_plan[2];
+  const int SA = std::max(1, (WA + 2 + 7) / 8), SB = std::max(1, (WB + 2 + 7) / 8);
+  if (fl != 0 || SA > OZ_MAX_S || SB > OZ_MAX_S) return cudaSuccess; /* decline: Inf/NaN or span too wide */
+  const int ndiag = SA + SB - 1;
+  /* int32 exactness: Kc * min(SA, SB) * 2^14 <= 2^31 - 1 */
+  int64_t kc_blocks = ((((int64_t)1 << 17) - 1) / std::min(SA, SB)) / OZ_BK;
+  if (kc_blocks < 1) return cudaSuccess;
+  const int64_t nkb_total = Kp / OZ_BK;
+  const int nchunks = (int)((nkb_total + kc_blocks - 1) / kc_blocks);
+  /* ---- workspace: planes B | planes A (per row pass) | D | W ---- */
+  const int64_t Np = rup(n, OZ_BN);
+  const size_t pb_b = rup((int64_t)SB * n * Kp, 1024);
+  auto pass_bytes = [&](int64_t mb) -> size_t {
+    const int64_t Mp = rup(mb, OZ_BM);
+    size_t b = rup((int64_t)SA * mb * Kp, 1024) + (size_t)ndiag * Mp * Np * 4;
+    if (nchunks > 1) b += (size_t)OZ_NL * Mp * Np * 4;
+    return b;
+  };
+  int64_t mb = m;
+  while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
+  if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess; /* does not fit: decline */
+  e = oz_reserve(meta_ints * 4, pb_b + pass_bytes(mb));
+  if (e != cudaSuccess) return e;
+  int8_t *pB = (int8_t *)g_oz.buf;
+  int8_t *pA = pB + pb_b;
+  /* ---- slice B once ---- */
+  {
+    const int64_t threads = n * (Kp / 4);
+    k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.B, n, k, a.sbj, a.sbl, emaxB, SB, Kp, pB);
+    count_launch();
+  }
+  for (int64_t r0 = 0; r0 < m; r0 += mb) {
+    const int64_t mr = std::min(mb, m - r0);
+    const int64_t Mp = rup(mr, OZ_BM);
+    int32_t *D = (int32_t *)(pA + rup((int64_t)SA * mb * Kp, 1024));
+    uint32_t *W = (uint32_t *)(D + (size_t)ndiag * rup(mb, OZ_BM) * Np);
+    {
+      const int64_t threads = mr * (Kp / 4);
+      k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, SA, Kp, pA);
+      count_launch();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
+      e = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D, Mp, Np, st);
+      if (e != cudaSuccess) return e;
+      OzFoldArgs f;
+      f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = ndiag; f.m = mr; f.n = n; f.row0 = r0;
+      f.emaxA = emaxA; f.emaxB = emaxB; f.SA = SA; f.SB = SB;
+      f.W = W; f.w_in = c > 0; f.w_out = c + 1 < nchunks;
+      f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
+      const int64_t elems = mr * n;
+      k_oz_fold<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(f);
+      count_launch();
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    }
+  }
+  g_last_stats.SA = SA; g_last_stats.SB = SB; g_last_stats.ndiag = ndiag; g_last_stats.nchunks = nchunks;
+  g_last_stats.pairs = (int64_t)SA * SB; g_last_stats.row_passes = (int)((m + mb - 1) / mb);
+  g_last_stats.ws_bytes = (int64_t)g_oz.bytes;
+  *used = 1;
+  return cudaSuccess;
+}
+
+} // namespace qb

@@ -1,0 +1,153 @@
+"""GPU tests of the fast-mode tensor-core qgemm (csrc/qb_ozaki.cu): the int8 tcgen05 kernel alone
+against integer matmul, and the whole path (scan -> slice -> mma -> fold) against EXACT inner
+products rounded once (tests/exact_ref.py) followed by the reference epilogue
+C = fma(alpha, s, mul(beta, C)) (/root/reference/include/quadblas/algorithms/level3.hpp:102-109)."""
+import numpy as np
+import pytest
+import torch
+
+import qgen
+from exact_ref import exact_matmul_rounded
+from gpu_util import dev_random, to_dev, to_host
+from qblas_b200 import quad
+
+pytestmark = pytest.mark.gpu
+
+
+def _diag_ref(pa, pb, m, n):
+    SA, SB = pa.shape[0], pb.shape[0]
+    a = pa.cpu().numpy().astype(np.int64)
+    b = pb.cpu().numpy().astype(np.int64)
+    out = np.zeros((SA + SB - 1, m, n), dtype=np.int64)
+    for s in range(SA):
+        for t in range(SB):
+            out[s + t] += a[s, :m] @ b[t, :n].T
+    return out
+
+
+@pytest.mark.parametrize("SA,SB,m,n,Kp", [(1, 1, 128, 256, 128), (1, 1, 128, 256, 512), (3, 2, 200, 300, 384), (2, 5, 130, 513, 1024),
+                                           (4, 4, 640, 1024, 256)])
+def test_i8_diagonal_gemm_kernel(qb, SA, SB, m, n, Kp):
+    g = torch.Generator(device="cuda"); g.manual_seed(SA * 100 + SB)
+    pa = torch.randint(-128, 128, (SA, m, Kp), generator=g, device="cuda", dtype=torch.int8)
+    pb = torch.randint(-128, 128, (SB, n, Kp), generator=g, device="cuda", dtype=torch.int8)
+    Mp, Np = (m + 127) // 128 * 128, (n + 255) // 256 * 256
+    D = torch.full((SA + SB - 1, Mp, Np), 77, device="cuda", dtype=torch.int32)
+    qb.oz_i8gemm(pa, pb, m, n, D)
+    torch.cuda.synchronize()
+    ref = _diag_ref(pa, pb, m, n)
+    got = D.cpu().numpy()[:, :m, :n].astype(np.int64)
+    assert (got == ref).all(), f"mismatch: {np.argwhere(got != ref)[:5]}"
+    # rows / columns beyond m, n come from TMA zero fill
+    assert (D.cpu().numpy()[:, m:, :] == 0).all() and (D.cpu().numpy()[:, :, n:] == 0).all()
+
+
+def test_i8_kernel_k_chunks(qb):
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    SA, SB, m, n, Kp = 2, 3, 256, 256, 1024
+    pa = torch.randint(-128, 128, (SA, m, Kp), generator=g, device="cuda", dtype=torch.int8)
+    pb = torch.randint(-128, 128, (SB, n, Kp), generator=g, device="cuda", dtype=torch.int8)
+    D1 = torch.zeros((SA + SB - 1, m, n), device="cuda", dtype=torch.int32)
+    D2 = torch.zeros_like(D1)
+    qb.oz_i8gemm(pa, pb, m, n, D1, kb_begin=0, nkb=3)
+    qb.oz_i8gemm(pa, pb, m, n, D2, kb_begin=3, nkb=5)
+    torch.cuda.synchronize()
+    ref = _diag_ref(pa, pb, m, n)
+    assert ((D1 + D2).cpu().numpy().astype(np.int64) == ref).all()
+
+
+def _epilogue(oracle, alpha, s, beta, C0):
+    al = np.broadcast_to(np.asarray(alpha, dtype=np.uint64).reshape(1, 2), s.shape).copy()
+    be = np.broadcast_to(np.asarray(beta, dtype=np.uint64).reshape(1, 2), s.shape).copy()
+    return oracle.fma(al, s, oracle.mul(be, np.ascontiguousarray(C0)))
+
+
+@pytest.mark.parametrize("m,n,k,kind,layout", [(40, 33, 300, "D113", "R"), (17, 50, 129, "Dexp", "R"), (33, 20, 257, "D53", "C"),
+                                               (130, 260, 64, "D113", "R"), (5, 7, 1000, "D113", "C")])
+def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, layout):
+    rng = np.random.default_rng(m + n + k)
+    ar, ac = (m, k) if layout == "R" else (k, m)
+    br, bc = (k, n) if layout == "R" else (n, k)
+    cr, cc = (m, n) if layout == "R" else (n, m)
+    lda, ldb, ldc = ac + 1, bc + 2, cc + 3
+    def mk(r, c, ld):
+        if kind == "Dexp":  # +-28 binades: 113 + 56 + 2 bits -> 22 digits (the full +-40 of qgen needs 25 > 24 and is declined)
+            return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-28, emax=28).reshape(r * ld, 2))
+        return qgen.matrix(rng, r, c, kind, ld)
+    A = mk(ar, ac, lda); B = mk(br, bc, ldb); C0 = mk(cr, cc, ldc)
+    alpha, beta = quad.random_quads(rng, 2)
+    s = exact_matmul_rounded(A, lda, B, ldb, m, n, k, layout)          # (m*n, 2) in (i, j) order
+    idx = np.array([[(i * ldc + j) if layout == "R" else (j * ldc + i) for j in range(n)] for i in range(m)]).reshape(-1)
+    want = _epilogue(oracle, alpha, s, beta, C0[idx])
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
+    try:
+        dC = to_dev(C0)
+        qb.gemm(layout, m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    got = to_host(dC)
+    assert st["pairs"] > 0, "tensor path declined"
+    assert quad.same_bits(got[idx], want).all(), f"{(~quad.same_bits(got[idx], want)).sum()} mismatches, plan {st}"
+    # untouched padding
+    mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False
+    assert (got[mask] == C0[mask]).all()
+
+
+def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle):
+    """README:141-158 / test_quadblas.cpp:715-739: rows (1e20, 1, -1e20, 0...) times ones -> exactly 1."""
+    m, n, k = 128, 128, 256
+    A = np.zeros((m, k)); A[:, 0] = 1e20; A[:, 1] = 1.0; A[:, 2] = -1e20
+    Aq = quad.from_double(A).reshape(-1, 2); Bq = quad.from_double(np.ones((k, n))).reshape(-1, 2)
+    C0 = quad.from_double(np.zeros((m, n))).reshape(-1, 2)
+    qb.set_mode(qb.MODE_FAST)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, 1.0, to_dev(Aq), k, to_dev(Bq), n, 0.0, dC, n)
+        torch.cuda.synchronize()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    one = quad.from_double(np.ones(m * n))
+    assert quad.same_bits(to_host(dC), one).all()
+
+
+def test_fast_gemm_declines_specials_and_wide_spans(qb, oracle):
+    """Inf/NaN or a row spanning more than 24 digits: the planner declines, the integer kernel runs (fast mode = single chain)."""
+    rng = np.random.default_rng(3)
+    m, n, k = 130, 140, 260
+    A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    A[5] = quad.from_double(np.array([np.inf]))[0]
+    A[700] = quad.from_double(np.array([1e-300]))[0] ; A[701] = quad.from_double(np.array([1e300]))[0]
+    Co = C0.copy()
+    oracle.gemm("R", m, n, k, 1.0, A, k, B, n, 1.0, Co, n, kc=k)       # single chain = fast-mode integer kernel
+    qb.set_mode(qb.MODE_FAST)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 1.0, dC, n)
+        torch.cuda.synchronize()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert quad.same_bits(to_host(dC), Co).all()
+
+
+def test_fast_gemm_large_matches_sampled_exact(qb, oracle):
+    """1024 x 768 x 2304 (two K chunks at 18 slices would need k > 7281; force chunks via D113 + k): sampled entries vs exact."""
+    m, n, k = 1024, 768, 2304
+    A = dev_random((m * k,), "D113", seed=1); B = dev_random((k * n,), "D113", seed=2); C = dev_random((m * n,), "D113", seed=3)
+    C0 = to_host(C).copy()
+    qb.set_mode(qb.MODE_FAST)
+    try:
+        qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert st["pairs"] > 0
+    Ah, Bh, got = to_host(A), to_host(B), to_host(C)
+    rng = np.random.default_rng(0)
+    for _ in range(12):
+        i, j = int(rng.integers(m)), int(rng.integers(n))
+        s = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, np.ascontiguousarray(Bh[j::n][:k]), 1, 1, 1, k)
+        want = _epilogue(oracle, quad.from_double(np.array([1.0]))[0], s, quad.from_double(np.array([0.0]))[0], C0[i * n + j:i * n + j + 1])
+        assert quad.same_bits(got[i * n + j:i * n + j + 1], want).all(), (i, j, st)
