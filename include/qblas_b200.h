@@ -91,8 +91,11 @@ int qb_get_honor_trans(void);
 void qb_set_tensor_path(int v);
 int qb_get_tensor_path(void);
 /* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, S_A*S_B int8 GEMMs,
- * workspace bytes, 0} */
+ * workspace bytes, padded K} */
 void qb_oz_last_stats(int64_t *out8);
+/* Summed device time (ms, CUDA events on the launching stream) of the tcgen05 kernel launches of
+ * the last tensor-path qgemm; waits for them to finish.  *launches (optional) = how many. */
+double qb_oz_last_mma_ms(int *launches);
 /* The tensor-core kernel alone (tests/profiling): D[d] = sum_{s+t=d} A_s B_t^T over k-blocks
  * [kb_begin, kb_begin+nkb) of 128; planes are int8 [S][rows][Kp] (device), D is int32
  * [S_A+S_B-1][Mp][Np] with Mp % 128 == 0, Np % 256 == 0. */

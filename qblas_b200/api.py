@@ -239,8 +239,15 @@ def oz_last_stats():
     """Plan of the last tensor-path qgemm."""
     out = (C.c_int64 * 8)()
     lib().qb_oz_last_stats(out)
-    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes"]
+    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes", "Kp"]
     return {k: int(out[i]) for i, k in enumerate(keys)}
+
+
+def oz_last_mma_ms():
+    """(summed ms, launches) of the tcgen05 kernel in the last tensor-path qgemm (CUDA events, blocks)."""
+    n = C.c_int(0)
+    ms = lib().qb_oz_last_mma_ms(C.byref(n))
+    return float(ms), int(n.value)
 
 
 def oz_i8gemm(planesA, planesB, m, n, D, kb_begin=0, nkb=None):

@@ -191,7 +191,12 @@ int qb_get_tensor_path(void) { return g_tensor.load(); }
 void qb_oz_last_stats(int64_t *out8)
 {
   const OzStats s = oz_last_stats();
-  out8[0] = s.SA; out8[1] = s.SB; out8[2] = s.ndiag; out8[3] = s.nchunks; out8[4] = s.row_passes; out8[5] = s.pairs; out8[6] = s.ws_bytes; out8[7] = 0;
+  out8[0] = s.SA; out8[1] = s.SB; out8[2] = s.ndiag; out8[3] = s.nchunks; out8[4] = s.row_passes; out8[5] = s.pairs; out8[6] = s.ws_bytes; out8[7] = s.Kp;
+}
+double qb_oz_last_mma_ms(int *launches)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  return oz_last_mma_ms(launches);
 }
 int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int64_t kb_begin,
                      int64_t nkb, void *dD, int64_t Mp, int64_t Np, void *stream)

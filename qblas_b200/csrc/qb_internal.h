@@ -49,12 +49,13 @@ void count_launch(int n = 1);
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24
-struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes; };
+struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; };
 /* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st);
 OzStats oz_last_stats();
+double oz_last_mma_ms(int *launches);
 void oz_release();
 
 } // namespace qb

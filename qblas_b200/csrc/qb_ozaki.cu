@@ -59,6 +59,20 @@ struct OzMmaArgs {
   uint8_t order[OZ_MAX_DIAG + 1]; /* diagonals, heaviest first */
 };
 
+/* Tile order inside one diagonal: bands of OZ_GM m-tiles, n-tile outer / m-tile inner inside a band, so
+ * that the ~148 tiles in flight form a compact 16 x 9 block of C: every A row panel is shared by ~9
+ * CTAs and every B column panel by 16 through L2 (profiles/r1c: the n-fastest order re-read the
+ * planes from HBM 3.4x more often than this needs at 8192^3). */
+static constexpr int OZ_GM = 16;
+__device__ __forceinline__ void oz_tile_decode(int rem, int m_tiles, int n_tiles, int &mt, int &nt)
+{
+  const int band_sz = OZ_GM * n_tiles;
+  const int band = rem / band_sz, r = rem % band_sz;
+  const int rows = min(OZ_GM, m_tiles - band * OZ_GM);
+  nt = r / rows;
+  mt = band * OZ_GM + r % rows;
+}
+
 /* ------------------------------------------------------------------ the tensor-core kernel */
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzMmaArgs g)
@@ -96,8 +110,8 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int d = g.order[tile / tiles_per_diag];
-        const int rem = tile % tiles_per_diag;
-        const int mt = rem / g.n_tiles, nt = rem % g.n_tiles;
+        int mt, nt;
+        oz_tile_decode(tile % tiles_per_diag, g.m_tiles, g.n_tiles, mt, nt);
         const int s_lo = d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0;
         const int s_hi = d < g.SA - 1 ? d : g.SA - 1;
         for (int s = s_lo; s <= s_hi; ++s) {
@@ -151,8 +165,8 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int d = g.order[tile / tiles_per_diag];
-      const int rem = tile % tiles_per_diag;
-      const int mt = rem / g.n_tiles, nt = rem % g.n_tiles;
+      int mt, nt;
+      oz_tile_decode(tile % tiles_per_diag, g.m_tiles, g.n_tiles, mt, nt);
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
       const int64_t row = (int64_t)mt * OZ_BM + quarter * 32 + lane;
@@ -504,10 +518,35 @@ static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static OzStats g_last_stats;
 OzStats oz_last_stats() { return g_last_stats; }
 
+/* CUDA events around every k_oz_mma launch of the last qgemm, on the launching stream (bench.py's
+ * roofline needs the kernel's own duration, not the whole call's) */
+static constexpr int OZ_MAX_EV = 64;
+static cudaEvent_t g_ev[2 * OZ_MAX_EV];
+static int g_ev_made = 0, g_ev_used = 0;
+static void oz_ev_record(int which, cudaStream_t st)
+{
+  if (g_ev_used >= OZ_MAX_EV) return;
+  if (!g_ev_made) { for (int i = 0; i < 2 * OZ_MAX_EV; ++i) cudaEventCreate(&g_ev[i]); g_ev_made = 1; }
+  cudaEventRecord(g_ev[2 * g_ev_used + which], st);
+  if (which == 1) ++g_ev_used;
+}
+/* blocks until the last recorded launch has finished; returns the summed duration in ms */
+double oz_last_mma_ms(int *launches)
+{
+  double tot = 0;
+  for (int i = 0; i < g_ev_used; ++i) {
+    float ms = 0;
+    if (cudaEventSynchronize(g_ev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]) == cudaSuccess) tot += ms;
+  }
+  if (launches) *launches = g_ev_used;
+  return tot;
+}
+
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget)
 {
   *used = 0;
+  g_ev_used = 0;
   { const int64_t keep = g_last_stats.ws_bytes; g_last_stats = OzStats(); g_last_stats.ws_bytes = keep; }
   if (!get_encode()) return cudaSuccess;
   const int64_t m = a.m, n = a.n, k = a.k;
@@ -583,7 +622,9 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     }
     for (int c = 0; c < nchunks; ++c) {
       const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
+      oz_ev_record(0, st);
       e = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D, Mp, Np, st);
+      oz_ev_record(1, st);
       if (e != cudaSuccess) return e;
       OzFoldArgs f;
       f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = ndiag; f.m = mr; f.n = n; f.row0 = r0;
@@ -599,7 +640,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   }
   g_last_stats.SA = SA; g_last_stats.SB = SB; g_last_stats.ndiag = ndiag; g_last_stats.nchunks = nchunks;
   g_last_stats.pairs = (int64_t)SA * SB; g_last_stats.row_passes = (int)((m + mb - 1) / mb);
-  g_last_stats.ws_bytes = (int64_t)g_oz.bytes;
+  g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
   *used = 1;
   return cudaSuccess;
 }
