@@ -38,6 +38,7 @@
 #ifndef QBLAS_B200_H
 #define QBLAS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -140,6 +141,11 @@ int qb_fold_partials_dev(int64_t count, const void *d_partials, int do_sqrt, voi
  * 2 mul, 3 add, 4 sqrt, 5 quad->double->quad round trip of casts. */
 int qb_elementwise_dev(int op, int64_t n, const void *da, const void *db, const void *dc, void *dout,
                        void *stream);
+
+/* Host buffers for QuadBLAS::aligned_alloc / aligned_free (memory/allocation.hpp:18-41): page-locked
+ * (so staging copies run at full rate), at least 32-byte aligned; NULL on failure. */
+void *qb_host_alloc(size_t bytes);
+void qb_host_free(void *p);
 
 /* Scalar casts (host, integer code; replace Sleef_cast_from_doubleq1 / Sleef_cast_to_doubleq1) */
 qb_quad qb_from_double(double d);

@@ -76,6 +76,8 @@ def lib():
         "qb_dot_partials_dev": (ci, [i64, vp, i64, vp, i64, i64, i64, vp, vp]),
         "qb_fold_partials_dev": (ci, [i64, vp, ci, vp, vp]),
         "qb_elementwise_dev": (ci, [ci, i64, vp, vp, vp, vp, vp]),
+        "qb_host_alloc": (vp, [C.c_size_t]),
+        "qb_host_free": (None, [vp]),
         "qb_from_double": (QbQuad, [cd]),
         "qb_to_double": (cd, [QbQuad]),
         "qb_launch_count": (i64, []),

@@ -19,6 +19,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <unordered_set>
+#include <cstdlib>
 #include <limits>
 
 namespace qb {
@@ -213,6 +215,31 @@ int qb_get_kc(void) { return g_kc.load(); }
 void qb_set_honor_trans(int on) { g_honor_trans.store(on ? 1 : 0); }
 int qb_get_honor_trans(void) { return g_honor_trans.load(); }
 int64_t qb_launch_count(void) { return g_launches.load(); }
+
+/* QuadBLAS::aligned_alloc / aligned_free (memory/allocation.hpp:18-41): page-locked host memory so the
+ * staging copies run at full rate; plain 32-byte aligned memory when pinning is refused. */
+static std::mutex g_pin_mu;
+static std::unordered_set<void *> g_pinned;
+void *qb_host_alloc(size_t bytes)
+{
+  if (bytes == 0) bytes = 16;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess && p) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pinned.insert(p);
+    return p;
+  }
+  cudaGetLastError();
+  if (posix_memalign(&p, 32, bytes) != 0) return nullptr;
+  return p;
+}
+void qb_host_free(void *p)
+{
+  if (!p) return;
+  bool pinned;
+  { std::lock_guard<std::mutex> lk(g_pin_mu); pinned = g_pinned.erase(p) != 0; }
+  if (pinned) cudaFreeHost(p); else free(p);
+}
 
 void quadblas_set_num_threads(int num_threads) { g_threads.store(num_threads); }
 int quadblas_get_num_threads(void) { return num_threads(); }
