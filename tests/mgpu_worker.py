@@ -1,0 +1,80 @@
+"""TEST worker (launched by tests/test_gpu_multi.py under torch.distributed.run, one rank per GPU, NCCL):
+row-sharded qgemm / qgemv and chunk-sharded qdot through qblas_b200.dist on real GPUs.  The sharded
+result must be bitwise the single-GPU result (both modes) and, in reference-order mode, the oracle's."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    import qblas_b200 as qb
+    from qblas_b200 import dist as qd, quad
+    import oracle_lib
+    from gpu_util import to_dev, to_host
+    qb.init()
+    orc = oracle_lib.load_oracle()
+    rng = np.random.default_rng(3)
+    fails = []
+    # ---- qgemm: reference order (bit exact vs oracle) and fast mode (tensor path; bitwise equal to the 1-GPU call)
+    for mode, (m, n, k) in ((qb.MODE_REFERENCE, (70, 33, 260)), (qb.MODE_REFERENCE, (37, 20, 127)), (qb.MODE_FAST, (512, 384, 640)), (qb.MODE_FAST, (301, 256, 300))):
+        A = quad.random_quads(rng, m * k); B = quad.random_quads(rng, k * n); C0 = quad.random_quads(rng, m * n)
+        alpha, beta = quad.random_quads(rng, 2)
+        qb.set_mode(mode)
+        one = to_dev(C0.copy())
+        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, one, n)      # single-GPU result on this rank
+        lo, hi = qd.row_block(m, world, rank)
+        Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+        Cf = to_dev(C0.copy())
+        qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cf)
+        torch.cuda.synchronize()
+        if not (to_host(Cf) == to_host(one)).all():
+            fails.append(("gemm vs 1-GPU", mode, m, n, k))
+        if mode == qb.MODE_REFERENCE:
+            want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
+            if not quad.same_bits(to_host(Cf), want).all():
+                fails.append(("gemm vs oracle", m, n, k))
+    qb.set_mode(qb.MODE_REFERENCE)
+    # ---- qgemv
+    m, n = 1031, 517
+    A = quad.random_quads(rng, m * n); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)
+    want = y0.copy(); orc.gemv("R", m, n, 1.5, A, n, x, 1, 0.5, want, 1)
+    lo, hi = qd.row_block(m, world, rank)
+    xt = to_dev(x) if rank == 0 else torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+    yf = to_dev(y0.copy())
+    qd.qgemv_row_sharded(m, n, 1.5, to_dev(A[lo * n:hi * n]), xt, 0.5, yf)
+    torch.cuda.synchronize()
+    if not quad.same_bits(to_host(yf), want).all():
+        fails.append(("gemv",))
+    # ---- qdot in reference order: T chunks over the ranks, all-gather of 16-byte partials, fixed-order fold
+    for nn, T in ((100003, 8), (5000, 3), (499, 4)):
+        x = quad.random_quads(rng, nn); y = quad.random_quads(rng, nn)
+        want = orc.dot(nn, x, 1, y, 1, T)
+        lo, hi = qd.dot_shard_range(nn, T, world, rank, True)
+        out = torch.zeros((1, 2), dtype=torch.int64, device="cuda")
+        qd.qdot_sharded(nn, to_dev(x[lo:hi]) if hi > lo else torch.zeros((0, 2), dtype=torch.int64, device="cuda"),
+                        to_dev(y[lo:hi]) if hi > lo else torch.zeros((0, 2), dtype=torch.int64, device="cuda"), T, out, reference_order=True)
+        torch.cuda.synchronize()
+        if not (to_host(out).reshape(2) == want).all():
+            fails.append(("dot", nn, T))
+    t = torch.tensor([len(fails)], device="cuda")
+    dist.all_reduce(t)
+    if fails:
+        print(f"rank {rank} FAILS: {fails}", flush=True)
+    if rank == 0:
+        print("mgpu_worker: all passed" if t.item() == 0 else f"mgpu_worker: {int(t.item())} failures", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if t.item() == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
