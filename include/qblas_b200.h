@@ -91,6 +91,11 @@ int qb_get_honor_trans(void);
  * 2 = whenever the planner accepts the operands.  Ignored in QB_MODE_REFERENCE. */
 void qb_set_tensor_path(int v);
 int qb_get_tensor_path(void);
+/* Fast-mode accumulate of qdot / qnrm2 / qgemv: 1 (default) = unrounded 192-bit window accumulator
+ * (csrc/qwide.cuh, one rounding per result), 0 = chains of correctly rounded FMAs (the
+ * reference's per-element operation, level1.hpp:24, re-associated).  Ignored in QB_MODE_REFERENCE. */
+void qb_set_fast_variant(int v);
+int qb_get_fast_variant(void);
 /* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, S_A*S_B int8 GEMMs,
  * workspace bytes, padded K} */
 void qb_oz_last_stats(int64_t *out8);

@@ -235,6 +235,15 @@ def get_tensor_path():
     return lib().qb_get_tensor_path()
 
 
+def set_fast_variant(v):
+    """Fast-mode accumulate of dot/nrm2/gemv: 1 = window accumulator (csrc/qwide.cuh), 0 = rounded-FMA chains."""
+    lib().qb_set_fast_variant(int(v))
+
+
+def get_fast_variant():
+    return lib().qb_get_fast_variant()
+
+
 def oz_last_stats():
     """Plan of the last tensor-path qgemm."""
     out = (C.c_int64 * 8)()

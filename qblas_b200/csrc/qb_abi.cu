@@ -32,6 +32,8 @@ static std::atomic<int> g_mode{QB_MODE_REFERENCE};
 static std::atomic<int> g_kc{126};
 static std::atomic<int> g_honor_trans{0};
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
+static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
+int fast_variant() { return g_fastvar.load(); }
 static std::atomic<int> g_threads{0}; /* 0 = not set -> hardware concurrency (omp_get_max_threads analogue) */
 
 static thread_local int t_err_code = 0;
@@ -190,6 +192,8 @@ void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : 
 int qb_get_mode(void) { return g_mode.load(); }
 void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
+void qb_set_fast_variant(int v) { g_fastvar.store(v ? 1 : 0); }
+int qb_get_fast_variant(void) { return g_fastvar.load(); }
 void qb_oz_last_stats(int64_t *out8)
 {
   const OzStats s = oz_last_stats();
@@ -275,7 +279,19 @@ int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const v
   g.m = m; g.n = n; g.alpha = toq(alpha); g.beta = toq(beta);
   g.A = (const q128 *)dA; g.lda = lda; g.col_major = is_col(layout);
   g.x = (const q128 *)dx; g.incx = incx; g.y = (q128 *)dy; g.incy = incy;
-  cudaError_t e = launch_gemv(g, g_mode.load(), (cudaStream_t)stream);
+  g.work = nullptr; g.work_elems = 0;
+  const int mode = g_mode.load();
+  const int64_t need = gemv_work_elems(m, n, g.col_major, mode);
+  std::unique_lock<std::recursive_mutex> lk(g_s.mu, std::defer_lock);
+  if (need > 0) { /* the shared scratch is held until the launch is queued (stream order protects its reuse) */
+    lk.lock();
+    int rc = ensure_device();
+    if (rc) return rc;
+    rc = ensure_work(need);
+    if (rc) return rc;
+    g.work = g_s.work; g.work_elems = g_s.work_elems;
+  }
+  cudaError_t e = launch_gemv(g, mode, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv kernel launch", e);
   return QB_OK;
 }

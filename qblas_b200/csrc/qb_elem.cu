@@ -5,6 +5,7 @@
  */
 #include "qb_internal.h"
 #include "q128_chain.cuh"
+#include "qwide.cuh"
 
 namespace qb {
 
@@ -78,9 +79,47 @@ __global__ void __launch_bounds__(NT) k_fma_microbench(int iters, q128 *sink)
   if (r.lo == 0x1234567 && r.hi == 0x7654321) sink[0] = r; /* keep the result alive */
 }
 
-/* variant = 100 * SC + ILP (ILP in {1,2,4}); threads must be 128 or 256 */
+/* Same harness for the fast-mode window accumulate (qwide.cuh): the register-resident ceiling of
+ * qdot / qnrm2 / qgemv in fast mode. */
+template <int ILP, int NT>
+__global__ void __launch_bounds__(NT) k_wide_microbench(int iters, q128 *sink)
+{
+  uint32_t s = 0x9e3779b9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
+  auto next = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; };
+  qop a[ILP], b;
+  qwide acc[ILP];
+  uint32_t bad = 0;
+#pragma unroll
+  for (int u = 0; u < ILP; ++u) {
+    a[u].m0 = next() | 1u; a[u].m1 = next(); a[u].m2 = next(); a[u].m3 = (next() & 0xffffu) | 0x10000u;
+    a[u].e = 16383 - (int)(next() & 3); a[u].s = next() & 1;
+    acc[u] = qw_zero();
+  }
+  b.m0 = next() | 1u; b.m1 = next(); b.m2 = next(); b.m3 = (next() & 0xffffu) | 0x10000u; b.e = 16383; b.s = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < ILP; ++u) qw_fma(acc[u], a[u], b, bad);
+    b.m0 += 0x9e3779b8u; b.m1 ^= b.m0; b.s ^= (b.m0 >> 7) & 1u;
+    b.e = 16383 - (int)((b.m0 >> 9) & 7u);   /* alignment shifts 0..10 bits, as U(-1,1) data give */
+  }
+  q128 r = qw_finish(acc[0], bad);
+#pragma unroll
+  for (int u = 1; u < ILP; ++u) { q128 t = qw_finish(acc[u], bad); r.lo ^= t.lo; r.hi ^= t.hi; }
+  if (r.lo == 0x1234567 && r.hi == 0x7654321) sink[0] = r;
+}
+
+/* variant = 100 * SC + ILP (ILP in {1,2,4}); 1000 + ILP = window accumulate; threads must be 128 or 256 */
 cudaError_t launch_fma_microbench(int variant, int blocks, int threads, int iters, q128 *sink, int64_t *n_fma, cudaStream_t st)
 {
+  if (variant >= 1000) {
+    const int il = variant - 1000;
+    if ((il != 1 && il != 2 && il != 4) || (threads != 128 && threads != 256)) return cudaErrorInvalidValue;
+    if (threads == 128) { if (il == 1) k_wide_microbench<1, 128><<<blocks, 128, 0, st>>>(iters, sink); else if (il == 2) k_wide_microbench<2, 128><<<blocks, 128, 0, st>>>(iters, sink); else k_wide_microbench<4, 128><<<blocks, 128, 0, st>>>(iters, sink); }
+    else { if (il == 1) k_wide_microbench<1, 256><<<blocks, 256, 0, st>>>(iters, sink); else if (il == 2) k_wide_microbench<2, 256><<<blocks, 256, 0, st>>>(iters, sink); else k_wide_microbench<4, 256><<<blocks, 256, 0, st>>>(iters, sink); }
+    if (n_fma) *n_fma = (int64_t)blocks * threads * iters * il;
+    count_launch();
+    return cudaGetLastError();
+  }
   const int ilp = variant % 100, scv = variant / 100;
   if ((ilp != 1 && ilp != 2 && ilp != 4) || (threads != 128 && threads != 256)) return cudaErrorInvalidValue;
 #define QB_MB(I, S, T) k_fma_microbench<I, S, T><<<blocks, T, 0, st>>>(iters, sink)

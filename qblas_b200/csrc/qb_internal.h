@@ -24,7 +24,9 @@ struct GemvArgs {
   int col_major;                     /* 0: A[i*lda+j] (level2.hpp:15-50), 1: A[j*lda+i] (level2.hpp:53-82) */
   const q128 *x; int64_t incx;
   q128 *y; int64_t incy;
+  q128 *work; int64_t work_elems;    /* device scratch (fast col-major split windows), gemv_work_elems() */
 };
+int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode);
 cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st);
 
 struct DotArgs {
@@ -46,6 +48,7 @@ cudaError_t launch_elementwise(int op, int64_t n, const q128 *a, const q128 *b, 
 cudaError_t launch_fma_microbench(int variant, int blocks, int threads, int iters, q128 *sink, int64_t *n_fma, cudaStream_t st);
 
 void count_launch(int n = 1);
+int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 0 = rounded-FMA chains */
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24

@@ -12,14 +12,18 @@
  * kernel; strided -> same chunking with ONE ascending chain per chunk (:104-120) or a single
  * chain (:128-134).  One GPU thread runs one chain, so the bits are the reference's for any T.
  *
- * FAST (mode 1): a deterministic two-level tree.  Level 1: thread t of a fixed G x B grid
- * accumulates elements t, t+GB, t+2GB, ... (fully coalesced 128-bit loads) with exact-rounded
- * fma chains; the B partials of a CTA are reduced by a fixed binary tree in shared memory.
- * Level 2: one CTA reduces the G block partials with the same fixed tree.  For fixed (n, G, B)
- * the summation tree is fixed, hence run-to-run and GPU-to-GPU reproducible.
+ * FAST (mode 1): a deterministic two-level tree on the unrounded 192-bit window accumulator of
+ * qwide.cuh.  Level 1: thread t of a fixed G x B grid accumulates elements t, t+GB, t+2GB, ...
+ * (fully coalesced 128-bit loads, ~100 integer instructions per element instead of ~170 for a
+ * rounded FMA); the B windows of a CTA are merged by a fixed shuffle/shared-memory tree.  Level 2:
+ * one CTA merges the G block windows with the same fixed tree and rounds ONCE.  For fixed
+ * (n, G, B) the tree is fixed, hence run-to-run and GPU-to-GPU reproducible.  The previous
+ * generation of this path (rounded FMA chains, k_dot_fast_l1) is kept as `fast variant 0` for the
+ * bench's side-by-side (qb_set_fast_variant).
  */
 #include "qb_internal.h"
 #include "q128_chain.cuh"
+#include "qwide.cuh"
 
 namespace qb {
 
@@ -146,13 +150,115 @@ k_dot_fast_l2(const q128 *part, int count, int do_sqrt, q128 *result)
   if (threadIdx.x == 0) *result = do_sqrt ? q_sqrt(v) : v;
 }
 
+
+/* ---- fast mode, unrounded window accumulator (qwide.cuh) ---- */
+__device__ __noinline__ qwide qw_merge_ni(qwide a, qwide b) { qw_merge(a, b); return a; }
+
+__device__ __forceinline__ qwide qw_shfl_down(const qwide &s, int off)
+{
+  qwide t;
+  t.w0 = __shfl_down_sync(0xffffffffu, s.w0, off); t.w1 = __shfl_down_sync(0xffffffffu, s.w1, off);
+  t.w2 = __shfl_down_sync(0xffffffffu, s.w2, off); t.w3 = __shfl_down_sync(0xffffffffu, s.w3, off);
+  t.w4 = __shfl_down_sync(0xffffffffu, s.w4, off); t.w5 = __shfl_down_sync(0xffffffffu, s.w5, off);
+  t.E = __shfl_down_sync(0xffffffffu, s.E, off);
+  return t;
+}
+/* partial record: 8 words {w0..w5, E, bad} = 32 B */
+__device__ __forceinline__ void qw_store(uint32_t *dst, const qwide &s, uint32_t bad)
+{
+  reinterpret_cast<uint4 *>(dst)[0] = make_uint4(s.w0, s.w1, s.w2, s.w3);
+  reinterpret_cast<uint4 *>(dst)[1] = make_uint4(s.w4, s.w5, (uint32_t)s.E, bad);
+}
+__device__ __forceinline__ qwide qw_load(const uint32_t *src, uint32_t &bad)
+{
+  const uint4 a = reinterpret_cast<const uint4 *>(src)[0], b = reinterpret_cast<const uint4 *>(src)[1];
+  qwide s;
+  s.w0 = a.x; s.w1 = a.y; s.w2 = a.z; s.w3 = a.w; s.w4 = b.x; s.w5 = b.y; s.E = (int32_t)b.z;
+  bad |= b.w;
+  return s;
+}
+
+/* fixed tree over the B threads of a CTA: shuffle tree inside each warp (lane l += lane l+off),
+ * then warp 0's thread 0 folds the warp results in warp order.  Result valid in thread 0. */
+template <int B>
+__device__ __forceinline__ qwide qw_block_tree(qwide v, uint32_t &bad, uint32_t *sh /* 8 * B/32 words */)
+{
+#pragma unroll 1
+  for (int off = 16; off > 0; off >>= 1) v = qw_merge_ni(v, qw_shfl_down(v, off));
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) qw_store(sh + 8 * warp, v, bad);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll 1
+    for (int w = 1; w < B / 32; ++w) {
+      uint32_t bw = 0;
+      const qwide t = qw_load(sh + 8 * w, bw);
+      bad |= bw;
+      v = qw_merge_ni(v, t);
+    }
+  }
+  return v;
+}
+
+template <int B, int U, bool SAME>
+__global__ void __launch_bounds__(B)
+k_dot_wide_l1(DotArgs g)
+{
+  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  const int64_t nthreads = (int64_t)gridDim.x * B;
+  const int64_t t = (int64_t)blockIdx.x * B + threadIdx.x;
+  qwide acc = qw_zero();
+  uint32_t bad = 0;
+  int64_t i = t;
+  /* U element pairs (2U 128-bit loads) in flight per thread */
+  for (; i + (U - 1) * nthreads < g.n; i += U * nthreads) {
+    q128 xv[U], yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      xv[u] = ldg128_l1(g.x + (i + u * nthreads) * g.incx);
+      if (!SAME) yv[u] = ldg128_l1(g.y + (i + u * nthreads) * g.incy);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const qop a = qop_load(xv[u]);
+      qw_fma(acc, a, SAME ? a : qop_load(yv[u]), bad);
+    }
+  }
+  for (; i < g.n; i += nthreads) {
+    const qop a = qop_load(ldg128_l1(g.x + i * g.incx));
+    qw_fma(acc, a, SAME ? a : qop_load(ldg128_l1(g.y + i * g.incy)), bad);
+  }
+  acc = qw_block_tree<B>(acc, bad, sh);
+  if (threadIdx.x == 0) qw_store(reinterpret_cast<uint32_t *>(g.work) + 8 * (int64_t)blockIdx.x, acc, bad);
+}
+
+template <int B>
+__global__ void __launch_bounds__(B)
+k_dot_wide_l2(const uint32_t *part, int count, int do_sqrt, q128 *result)
+{
+  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  qwide v = qw_zero();
+  uint32_t bad = 0;
+  /* fixed assignment: thread t merges records t, t+B, ... in order */
+  for (int i = threadIdx.x; i < count; i += B) {
+    const qwide p = qw_load(part + 8 * (int64_t)i, bad);
+    v = qw_merge_ni(v, p);
+  }
+  v = qw_block_tree<B>(v, bad, sh);
+  if (threadIdx.x == 0) {
+    const q128 r = qw_finish(v, bad);
+    *result = do_sqrt ? q_sqrt(r) : r;
+  }
+}
+
 static constexpr int FAST_B = 256;
 static constexpr int FAST_GRID = 148 * 4;
 
 int64_t dot_work_elems(int64_t n, int T, int mode)
 {
   (void)n;
-  if (mode != 0) return FAST_GRID;
+  if (mode != 0) return 2 * FAST_GRID;   /* 32-byte window records */
   return 3 * (int64_t)(T < 1 ? 1 : T) + 4;
 }
 
@@ -167,8 +273,15 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
     int grid = FAST_GRID;
     const int64_t need = (g.n + FAST_B - 1) / FAST_B;
     if (need < grid) grid = (int)need;
-    k_dot_fast_l1<FAST_B, 4><<<grid, FAST_B, 0, st>>>(g);
-    k_dot_fast_l2<FAST_B><<<1, FAST_B, 0, st>>>(g.work, grid, g.do_sqrt, g.result);
+    if (fast_variant() == 0) { /* rounded-FMA chains (previous generation, kept for comparison) */
+      k_dot_fast_l1<FAST_B, 4><<<grid, FAST_B, 0, st>>>(g);
+      k_dot_fast_l2<FAST_B><<<1, FAST_B, 0, st>>>(g.work, grid, g.do_sqrt, g.result);
+    } else {
+      const bool same = (g.x == g.y && g.incx == g.incy);
+      if (same) k_dot_wide_l1<FAST_B, 4, true><<<grid, FAST_B, 0, st>>>(g);
+      else k_dot_wide_l1<FAST_B, 4, false><<<grid, FAST_B, 0, st>>>(g);
+      k_dot_wide_l2<FAST_B><<<1, FAST_B, 0, st>>>(reinterpret_cast<const uint32_t *>(g.work), grid, g.do_sqrt, g.result);
+    }
     count_launch(2);
     return cudaGetLastError();
   }

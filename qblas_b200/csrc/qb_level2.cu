@@ -14,9 +14,16 @@
  * (a warp reads 32 consecutive quads of one row) into padded shared memory and each chain thread
  * then walks its own row.  col-major kernel: thread per row, consecutive threads read consecutive
  * quads of a column, so the loads are coalesced without staging.
+ *
+ * FAST mode (k_gemv_row_wide / k_gemv_col_wide): S_i = sum_j A_ij x_j is accumulated in the unrounded
+ * 192-bit window of qwide.cuh (~95 integer instructions per element instead of ~280 for the rounded
+ * two-lane chain) and rounded once, then y_i = fma(alpha, S_i, mul(beta, y_i)) for both layouts.
+ * Contract: |y^_i - y_i| <= gamma_n (|alpha| |A||x| + |beta y|)_i; for fixed shapes
+ * the merge tree is fixed, so results are reproducible.
  */
 #include "qb_internal.h"
 #include "q128_chain.cuh"
+#include "qwide.cuh"
 
 namespace qb {
 
@@ -113,10 +120,186 @@ k_gemv_col(GemvArgs g)
   if (live) g.y[i * g.incy] = qacc_pack(acc);
 }
 
+
+/* ------------------------------------------------------------------ fast mode (window accumulator) */
+__device__ __noinline__ qwide gv_merge(qwide a, qwide b) { qw_merge(a, b); return a; }
+__device__ __forceinline__ qwide gv_shfl_down(const qwide &s, int off)
+{
+  qwide t;
+  t.w0 = __shfl_down_sync(0xffffffffu, s.w0, off); t.w1 = __shfl_down_sync(0xffffffffu, s.w1, off);
+  t.w2 = __shfl_down_sync(0xffffffffu, s.w2, off); t.w3 = __shfl_down_sync(0xffffffffu, s.w3, off);
+  t.w4 = __shfl_down_sync(0xffffffffu, s.w4, off); t.w5 = __shfl_down_sync(0xffffffffu, s.w5, off);
+  t.E = __shfl_down_sync(0xffffffffu, s.E, off);
+  return t;
+}
+__device__ __forceinline__ void gv_store(uint32_t *dst, const qwide &s, uint32_t bad)
+{
+  reinterpret_cast<uint4 *>(dst)[0] = make_uint4(s.w0, s.w1, s.w2, s.w3);
+  reinterpret_cast<uint4 *>(dst)[1] = make_uint4(s.w4, s.w5, (uint32_t)s.E, bad);
+}
+__device__ __forceinline__ qwide gv_load(const uint32_t *src, uint32_t &bad)
+{
+  const uint4 a = reinterpret_cast<const uint4 *>(src)[0], b = reinterpret_cast<const uint4 *>(src)[1];
+  qwide s;
+  s.w0 = a.x; s.w1 = a.y; s.w2 = a.z; s.w3 = a.w; s.w4 = b.x; s.w5 = b.y; s.E = (int32_t)b.z;
+  bad |= b.w;
+  return s;
+}
+
+/* Row-major: a CTA of NT threads owns R consecutive rows; thread t walks columns t, t+NT, ... of all
+ * R rows (a warp reads 512 contiguous bytes of each row per step, x_j is unpacked once for R rows).
+ * End of row: shuffle tree per warp, then thread r folds the NT/32 warp windows of row r in order. */
+template <int R, int NT>
+__global__ void __launch_bounds__(NT)
+k_gemv_row_wide(GemvArgs g)
+{
+  constexpr int NW = NT / 32;
+  __shared__ __align__(16) uint32_t sh[R * NW * 8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  qwide acc[R];
+  uint32_t bad[R];
+  const q128 *rowp[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    acc[r] = qw_zero();
+    bad[r] = 0;
+    const int64_t gr = (row0 + r < g.m) ? row0 + r : g.m - 1;   /* clamp: duplicate work, never stored */
+    rowp[r] = g.A + gr * g.lda;
+  }
+  int64_t j = tid;
+  q128 av[R], xv;
+  if (j < g.n) {
+    xv = ldg128(g.x + j * g.incx);
+#pragma unroll
+    for (int r = 0; r < R; ++r) av[r] = ldg128(rowp[r] + j);
+  }
+  while (j < g.n) {
+    /* software pipeline: issue the next step's loads before this step's arithmetic */
+    const int64_t jn = j + NT;
+    q128 an[R], xn;
+    if (jn < g.n) {
+      xn = ldg128(g.x + jn * g.incx);
+#pragma unroll
+      for (int r = 0; r < R; ++r) an[r] = ldg128(rowp[r] + jn);
+    }
+    const qop X = qop_load(xv);
+#pragma unroll
+    for (int r = 0; r < R; ++r) qw_fma(acc[r], qop_load(av[r]), X, bad[r]);
+    if (jn < g.n) {
+      xv = xn;
+#pragma unroll
+      for (int r = 0; r < R; ++r) av[r] = an[r];
+    }
+    j = jn;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    qwide v = acc[r];
+#pragma unroll 1
+    for (int off = 16; off > 0; off >>= 1) v = gv_merge(v, gv_shfl_down(v, off));
+    const uint32_t b = __reduce_or_sync(0xffffffffu, bad[r]);
+    if (lane == 0) gv_store(sh + (r * NW + warp) * 8, v, b);
+  }
+  __syncthreads();
+  if (tid < R && row0 + tid < g.m) {
+    uint32_t b = 0;
+    qwide v = gv_load(sh + (tid * NW) * 8, b);
+#pragma unroll 1
+    for (int w = 1; w < NW; ++w) v = gv_merge(v, gv_load(sh + (tid * NW + w) * 8, b));
+    q128 *yp = g.y + (row0 + tid) * g.incy;
+    *yp = gemv_epilogue(g.alpha, qw_finish(v, b), g.beta, *yp);
+  }
+}
+
+/* Col-major (and row-major transposed): thread per row, consecutive threads read consecutive quads
+ * of a column; the column range is split over gridDim.y CTAs so that the grid fills the chip, each
+ * writing its window to part[split][row]; k_gemv_col_fin folds the splits in order and applies the
+ * epilogue. */
+template <int ROWS, int TW>
+__global__ void __launch_bounds__(ROWS)
+k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
+{
+  __shared__ q128 sx[TW];
+  const int tid = threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * ROWS + tid;
+  const bool live = i < g.m;
+  const int64_t jb = (int64_t)blockIdx.y * jchunk;
+  const int64_t je = (jb + jchunk < g.n) ? jb + jchunk : g.n;
+  qwide acc = qw_zero();
+  uint32_t bad = 0;
+  for (int64_t j0 = jb; j0 < je; j0 += TW) {
+    for (int idx = tid; idx < TW; idx += ROWS) {
+      const int64_t j = j0 + idx;
+      sx[idx] = (j < je) ? g.x[j * g.incx] : q_zero(0);
+    }
+    __syncthreads();
+    const int lim = (int)((je - j0) < TW ? (je - j0) : TW);
+    const q128 *col = g.A + j0 * g.lda + (live ? i : 0);
+#pragma unroll 4
+    for (int j = 0; j < lim; ++j) {
+      const q128 a = ldg128(col + (int64_t)j * g.lda);
+      qw_fma(acc, qop_load(a), qop_load(sx[j]), bad);
+    }
+    __syncthreads();
+  }
+  if (live) gv_store(part + ((int64_t)blockIdx.y * g.m + i) * 8, acc, bad);
+}
+
+__global__ void k_gemv_col_fin(GemvArgs g, int splits, const uint32_t *part)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.m) return;
+  uint32_t b = 0;
+  qwide v = gv_load(part + i * 8, b);
+#pragma unroll 1
+  for (int s = 1; s < splits; ++s) v = gv_merge(v, gv_load(part + ((int64_t)s * g.m + i) * 8, b));
+  q128 *yp = g.y + i * g.incy;
+  *yp = gemv_epilogue(g.alpha, qw_finish(v, b), g.beta, *yp);
+}
+
+static constexpr int GV_COL_ROWS = 128;
+static int gemv_col_splits(int64_t m, int64_t n)
+{
+  /* enough CTAs for ~4 per SM, at least 64 columns per split */
+  const int64_t rb = (m + GV_COL_ROWS - 1) / GV_COL_ROWS;
+  int64_t s = (148 * 4 + rb - 1) / rb;
+  const int64_t smax = (n + 63) / 64;
+  if (s > smax) s = smax;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return (int)s;
+}
+
+/* 16-byte elements of device scratch the fast col-major path needs (32-byte window per split x row) */
+int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode)
+{
+  if (mode == 0 || !col_major || fast_variant() == 0 || m <= 0 || n <= 0) return 0;
+  return 2 * (int64_t)gemv_col_splits(m, n) * m;
+}
+
 cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st)
 {
-  (void)mode; /* the reference order is already fully parallel over rows; fast mode shares it for now */
   if (a.m == 0 || a.n == 0) return cudaSuccess; /* level2.hpp:21,59: y untouched */
+  if (mode != 0 && fast_variant() != 0) {
+    if (!a.col_major) {
+      /* R rows per CTA: 4 when that still gives >= 2 CTAs per SM, else fewer rows for more CTAs */
+      if (a.m >= 4 * 148 * 2) k_gemv_row_wide<4, 256><<<(unsigned)((a.m + 3) / 4), 256, 0, st>>>(a);
+      else if (a.m >= 2 * 148) k_gemv_row_wide<2, 256><<<(unsigned)((a.m + 1) / 2), 256, 0, st>>>(a);
+      else k_gemv_row_wide<1, 256><<<(unsigned)a.m, 256, 0, st>>>(a);
+      count_launch();
+    } else {
+      const int splits = gemv_col_splits(a.m, a.n);
+      if (a.work == nullptr || a.work_elems < 2 * (int64_t)splits * a.m) return cudaErrorInvalidValue;
+      const int64_t jchunk = (((a.n + splits - 1) / splits) + 31) / 32 * 32;
+      const int gy = (int)((a.n + jchunk - 1) / jchunk);
+      dim3 grid((unsigned)((a.m + GV_COL_ROWS - 1) / GV_COL_ROWS), (unsigned)gy);
+      k_gemv_col_wide<GV_COL_ROWS, 32><<<grid, GV_COL_ROWS, 0, st>>>(a, jchunk, reinterpret_cast<uint32_t *>(a.work));
+      k_gemv_col_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, gy, reinterpret_cast<const uint32_t *>(a.work));
+      count_launch(2);
+    }
+    return cudaGetLastError();
+  }
   if (!a.col_major) {
     if (a.incx == 1) {
       constexpr int ROWS = 64, TW = 32;
