@@ -57,6 +57,21 @@ QB_HD qop qop_load(q128 a)
   return o;
 }
 
+/* hot-path variant: the implicit bit is set unconditionally.  Only valid where a zero / subnormal
+ * operand (exponent field 0) is detected from .e and handled from the PACKED value (qwa_fma). */
+QB_HD qop qop_load_n(q128 a)
+{
+  qop o;
+  uint32_t h = (uint32_t)(a.hi >> 32);
+  o.m0 = (uint32_t)a.lo;
+  o.m1 = (uint32_t)(a.lo >> 32);
+  o.m2 = (uint32_t)a.hi;
+  o.e = (int32_t)((h >> 16) & 0x7fff);
+  o.s = h >> 31;
+  o.m3 = (h & 0xffffu) | 0x10000u;
+  return o;
+}
+
 QB_HD q128 qop_pack(const qop &o)
 {
   q128 r;

@@ -79,32 +79,41 @@ __global__ void __launch_bounds__(NT) k_fma_microbench(int iters, q128 *sink)
   if (r.lo == 0x1234567 && r.hi == 0x7654321) sink[0] = r; /* keep the result alive */
 }
 
-/* Same harness for the fast-mode window accumulate (qwide.cuh): the register-resident ceiling of
- * qdot / qnrm2 / qgemv in fast mode. */
+/* Same harness for the fast-mode window accumulate (qwide.cuh: qwa_fma on a scratch column, exactly what
+ * the qdot / qnrm2 / qgemv kernels run per element): the register-resident ceiling of those kernels.
+ * Every word of both operands changes every step, so that no partial product is loop invariant. */
 template <int ILP, int NT>
 __global__ void __launch_bounds__(NT) k_wide_microbench(int iters, q128 *sink)
 {
+  __shared__ uint32_t scr[ILP * QWA_COL_WORDS * NT];
   uint32_t s = 0x9e3779b9u * (blockIdx.x * blockDim.x + threadIdx.x + 1);
   auto next = [&]() { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; };
   qop a[ILP], b;
-  qwide acc[ILP];
+  qwacc acc[ILP];
   uint32_t bad = 0;
 #pragma unroll
   for (int u = 0; u < ILP; ++u) {
     a[u].m0 = next() | 1u; a[u].m1 = next(); a[u].m2 = next(); a[u].m3 = (next() & 0xffffu) | 0x10000u;
     a[u].e = 16383 - (int)(next() & 3); a[u].s = next() & 1;
-    acc[u] = qw_zero();
+    acc[u] = qwa_zero();
+    qwa_col_init(scr + u * QWA_COL_WORDS * NT + threadIdx.x, NT);
   }
   b.m0 = next() | 1u; b.m1 = next(); b.m2 = next(); b.m3 = (next() & 0xffffu) | 0x10000u; b.e = 16383; b.s = 0;
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int u = 0; u < ILP; ++u) qw_fma(acc[u], a[u], b, bad);
-    b.m0 += 0x9e3779b8u; b.m1 ^= b.m0; b.s ^= (b.m0 >> 7) & 1u;
+    for (int u = 0; u < ILP; ++u)
+      if (qwa_fma(acc[u], a[u], b, scr + u * QWA_COL_WORDS * NT + threadIdx.x, NT)) qwa_fma_rare(acc[u], qop_pack(a[u]), qop_pack(b), bad);
+    b.m0 += 0x9e3779b8u; b.m1 ^= b.m0; b.m2 += b.m1 | 1u; b.m3 = ((b.m3 + (b.m2 >> 20)) & 0xffffu) | 0x10000u; b.s ^= (b.m0 >> 7) & 1u;
     b.e = 16383 - (int)((b.m0 >> 9) & 7u);   /* alignment shifts 0..10 bits, as U(-1,1) data give */
-  }
-  q128 r = qw_finish(acc[0], bad);
 #pragma unroll
-  for (int u = 1; u < ILP; ++u) { q128 t = qw_finish(acc[u], bad); r.lo ^= t.lo; r.hi ^= t.hi; }
+    for (int u = 0; u < ILP; ++u) {
+      a[u].m0 ^= b.m1; a[u].m1 += b.m2; a[u].m2 ^= b.m0; a[u].m3 = ((a[u].m3 + (b.m1 >> 24)) & 0xffffu) | 0x10000u;
+      a[u].s ^= (b.m1 >> 3) & 1u;
+    }
+  }
+  q128 r = qw_finish(qwa_fold(acc[0]), bad);
+#pragma unroll
+  for (int u = 1; u < ILP; ++u) { q128 t = qw_finish(qwa_fold(acc[u]), bad); r.lo ^= t.lo; r.hi ^= t.hi; }
   if (r.lo == 0x1234567 && r.hi == 0x7654321) sink[0] = r;
 }
 

@@ -201,36 +201,55 @@ __device__ __forceinline__ qwide qw_block_tree(qwide v, uint32_t &bad, uint32_t 
   return v;
 }
 
-template <int B, int U, bool SAME>
-__global__ void __launch_bounds__(B)
+/* U element pairs (2U 128-bit loads) in flight per thread; the U accumulate steps are branch-free
+ * (qwa_fma, one scratch column each) and go into ONE accumulator — the window update is a plain sum,
+ * so the order in which fast and declined steps are applied does not matter. */
+template <int B, int U, bool SAME, int MINB>
+__global__ void __launch_bounds__(B, MINB)
 k_dot_wide_l1(DotArgs g)
 {
-  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  static_assert(8 * (B / 32) <= U * QWA_COL_WORDS * B, "the reduction records reuse the scratch columns");
+  __shared__ __align__(16) uint32_t scr[U * QWA_COL_WORDS * B];
+  uint32_t *sh = scr;
   const int64_t nthreads = (int64_t)gridDim.x * B;
   const int64_t t = (int64_t)blockIdx.x * B + threadIdx.x;
-  qwide acc = qw_zero();
+  qwacc acc = qwa_zero();
   uint32_t bad = 0;
-  int64_t i = t;
-  /* U element pairs (2U 128-bit loads) in flight per thread */
-  for (; i + (U - 1) * nthreads < g.n; i += U * nthreads) {
+#pragma unroll
+  for (int u = 0; u < U; ++u) qwa_col_init(scr + u * QWA_COL_WORDS * B + threadIdx.x, B);
+  /* running pointers (element t, t + nthreads, ...): no 64-bit index multiplies in the loop */
+  const q128 *xp = g.x + t * g.incx, *yp = g.y + t * g.incy;
+  const int64_t xs = nthreads * g.incx, ys = nthreads * g.incy;
+  int64_t left = (g.n > t) ? (g.n - t + nthreads - 1) / nthreads : 0;   /* elements of this thread */
+  for (; left >= U; left -= U) {
     q128 xv[U], yv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      xv[u] = ldg128_l1(g.x + (i + u * nthreads) * g.incx);
-      if (!SAME) yv[u] = ldg128_l1(g.y + (i + u * nthreads) * g.incy);
+      xv[u] = ldg128_l1(xp); xp += xs;
+      if (!SAME) { yv[u] = ldg128_l1(yp); yp += ys; }
     }
+    bool rare = false, rr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const qop a = qop_load(xv[u]);
-      qw_fma(acc, a, SAME ? a : qop_load(yv[u]), bad);
+      const qop a = qop_load_n(xv[u]);
+      rr[u] = qwa_fma(acc, a, SAME ? a : qop_load_n(yv[u]), scr + u * QWA_COL_WORDS * B + threadIdx.x, B);
+      rare |= rr[u];
+    }
+    if (rare) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rr[u]) qwa_fma_rare(acc, xv[u], SAME ? xv[u] : yv[u], bad);
     }
   }
-  for (; i < g.n; i += nthreads) {
-    const qop a = qop_load(ldg128_l1(g.x + i * g.incx));
-    qw_fma(acc, a, SAME ? a : qop_load(ldg128_l1(g.y + i * g.incy)), bad);
+  for (; left > 0; --left) {
+    const q128 xv = ldg128_l1(xp);
+    const q128 yv = SAME ? xv : ldg128_l1(yp);
+    xp += xs; yp += ys;
+    if (qwa_fma(acc, qop_load_n(xv), qop_load_n(yv), scr + threadIdx.x, B)) qwa_fma_rare(acc, xv, yv, bad);
   }
-  acc = qw_block_tree<B>(acc, bad, sh);
-  if (threadIdx.x == 0) qw_store(reinterpret_cast<uint32_t *>(g.work) + 8 * (int64_t)blockIdx.x, acc, bad);
+  __syncthreads();                       /* the scratch columns become the reduction records */
+  qwide v = qw_block_tree<B>(qwa_fold(acc), bad, sh);
+  if (threadIdx.x == 0) qw_store(reinterpret_cast<uint32_t *>(g.work) + 8 * (int64_t)blockIdx.x, v, bad);
 }
 
 template <int B>
@@ -252,13 +271,15 @@ k_dot_wide_l2(const uint32_t *part, int count, int do_sqrt, q128 *result)
   }
 }
 
-static constexpr int FAST_B = 256;
+static constexpr int FAST_B = 256;       /* rounded-chain variant and the second-level CTA */
 static constexpr int FAST_GRID = 148 * 4;
+static constexpr int WIDE_B = 128;       /* window variant: 4 scratch columns per thread = 24 KB per CTA */
+static constexpr int WIDE_GRID = 148 * 6;
 
 int64_t dot_work_elems(int64_t n, int T, int mode)
 {
   (void)n;
-  if (mode != 0) return 2 * FAST_GRID;   /* 32-byte window records */
+  if (mode != 0) return 2 * WIDE_GRID;   /* 32-byte window records */
   return 3 * (int64_t)(T < 1 ? 1 : T) + 4;
 }
 
@@ -270,16 +291,21 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
     return e;
   }
   if (mode != 0) {
-    int grid = FAST_GRID;
-    const int64_t need = (g.n + FAST_B - 1) / FAST_B;
-    if (need < grid) grid = (int)need;
     if (fast_variant() == 0) { /* rounded-FMA chains (previous generation, kept for comparison) */
+      int grid = FAST_GRID;
+      const int64_t need = (g.n + FAST_B - 1) / FAST_B;
+      if (need < grid) grid = (int)need;
       k_dot_fast_l1<FAST_B, 4><<<grid, FAST_B, 0, st>>>(g);
       k_dot_fast_l2<FAST_B><<<1, FAST_B, 0, st>>>(g.work, grid, g.do_sqrt, g.result);
     } else {
       const bool same = (g.x == g.y && g.incx == g.incy);
-      if (same) k_dot_wide_l1<FAST_B, 4, true><<<grid, FAST_B, 0, st>>>(g);
-      else k_dot_wide_l1<FAST_B, 4, false><<<grid, FAST_B, 0, st>>>(g);
+      /* 128 threads x 4 elements in flight, 6 CTAs per SM resident (80 registers, 24 KB of scratch columns):
+       * the grid is exactly one wave, every thread strides over the whole vector */
+      int grid = WIDE_GRID;
+      const int64_t need = (g.n + WIDE_B - 1) / WIDE_B;
+      if (need < grid) grid = (int)need;
+      if (same) k_dot_wide_l1<WIDE_B, 4, true, WIDE_GRID / 148><<<grid, WIDE_B, 0, st>>>(g);
+      else k_dot_wide_l1<WIDE_B, 4, false, WIDE_GRID / 148><<<grid, WIDE_B, 0, st>>>(g);
       k_dot_wide_l2<FAST_B><<<1, FAST_B, 0, st>>>(reinterpret_cast<const uint32_t *>(g.work), grid, g.do_sqrt, g.result);
     }
     count_launch(2);

@@ -148,54 +148,81 @@ __device__ __forceinline__ qwide gv_load(const uint32_t *src, uint32_t &bad)
 
 /* Row-major: a CTA of NT threads owns R consecutive rows; thread t walks columns t, t+NT, ... of all
  * R rows (a warp reads 512 contiguous bytes of each row per step, x_j is unpacked once for R rows).
- * End of row: shuffle tree per warp, then thread r folds the NT/32 warp windows of row r in order. */
+ * The R accumulate steps of one column are branch-free (qwa_fma) so that they interleave; a step that
+ * qwa_fma declines (zero / subnormal / Inf / NaN operand, product above the anchor) is redone out of
+ * line.  End of row: shuffle tree per warp, then thread r folds the NT/32 warp windows of row r in order. */
+/* one column step of R rows: branch-free accumulate, then the declined steps out of line */
 template <int R, int NT>
-__global__ void __launch_bounds__(NT)
+__device__ __forceinline__ void gv_row_step(qwacc (&acc)[R], uint32_t (&bad)[R], const q128 (&av)[R], const q128 &xv, uint32_t *col0)
+{
+  const qop X = qop_load_n(xv);
+  bool rare = false, rr[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    rr[r] = qwa_fma(acc[r], qop_load_n(av[r]), X, col0 + r * QWA_COL_WORDS * NT, NT);
+    rare |= rr[r];
+  }
+  if (rare) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (rr[r]) qwa_fma_rare(acc[r], av[r], xv, bad[r]);
+  }
+}
+
+template <int R, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_gemv_row_wide(GemvArgs g)
 {
   constexpr int NW = NT / 32;
-  __shared__ __align__(16) uint32_t sh[R * NW * 8];
+  static_assert(R * NW * 8 <= R * QWA_COL_WORDS * NT, "the reduction records reuse the scratch columns");
+  __shared__ __align__(16) uint32_t scr[R * QWA_COL_WORDS * NT];
+  uint32_t *sh = scr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * R;
-  qwide acc[R];
+  qwacc acc[R];
   uint32_t bad[R];
-  const q128 *rowp[R];
+  const q128 *ap[R];                     /* running pointers: element (row r, column tid + k * NT) */
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    acc[r] = qw_zero();
+    acc[r] = qwa_zero();
     bad[r] = 0;
     const int64_t gr = (row0 + r < g.m) ? row0 + r : g.m - 1;   /* clamp: duplicate work, never stored */
-    rowp[r] = g.A + gr * g.lda;
+    ap[r] = g.A + gr * g.lda + tid;
+    qwa_col_init(scr + r * QWA_COL_WORDS * NT + tid, NT);
   }
-  int64_t j = tid;
-  q128 av[R], xv;
-  if (j < g.n) {
-    xv = ldg128(g.x + j * g.incx);
+  const q128 *xp = g.x + (int64_t)tid * g.incx;
+  const int64_t xstep = (int64_t)NT * g.incx;
+  /* software pipeline over two register sets (no copies): the loads of step k + 1 are issued before
+   * the arithmetic of step k */
+  int left = (g.n > tid) ? (int)((g.n - tid + NT - 1) / NT) : 0;   /* column steps of this thread */
+  q128 a0[R], a1[R], x0, x1;
+  if (left > 0) {
+    x0 = ldg128(xp);
 #pragma unroll
-    for (int r = 0; r < R; ++r) av[r] = ldg128(rowp[r] + j);
+    for (int r = 0; r < R; ++r) a0[r] = ldg128(ap[r]);
   }
-  while (j < g.n) {
-    /* software pipeline: issue the next step's loads before this step's arithmetic */
-    const int64_t jn = j + NT;
-    q128 an[R], xn;
-    if (jn < g.n) {
-      xn = ldg128(g.x + jn * g.incx);
+  while (left > 0) {
+    if (left > 1) {
+      xp += xstep;
+      x1 = ldg128(xp);
 #pragma unroll
-      for (int r = 0; r < R; ++r) an[r] = ldg128(rowp[r] + jn);
+      for (int r = 0; r < R; ++r) { ap[r] += NT; a1[r] = ldg128(ap[r]); }
     }
-    const qop X = qop_load(xv);
+    gv_row_step<R, NT>(acc, bad, a0, x0, scr + tid);
+    if (--left == 0) break;
+    if (left > 1) {
+      xp += xstep;
+      x0 = ldg128(xp);
 #pragma unroll
-    for (int r = 0; r < R; ++r) qw_fma(acc[r], qop_load(av[r]), X, bad[r]);
-    if (jn < g.n) {
-      xv = xn;
-#pragma unroll
-      for (int r = 0; r < R; ++r) av[r] = an[r];
+      for (int r = 0; r < R; ++r) { ap[r] += NT; a0[r] = ldg128(ap[r]); }
     }
-    j = jn;
+    gv_row_step<R, NT>(acc, bad, a1, x1, scr + tid);
+    --left;
   }
+  __syncthreads();                       /* the scratch columns become the reduction records */
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    qwide v = acc[r];
+    qwide v = qwa_fold(acc[r]);
 #pragma unroll 1
     for (int off = 16; off > 0; off >>= 1) v = gv_merge(v, gv_shfl_down(v, off));
     const uint32_t b = __reduce_or_sync(0xffffffffu, bad[r]);
@@ -220,14 +247,19 @@ template <int ROWS, int TW>
 __global__ void __launch_bounds__(ROWS)
 k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
 {
+  constexpr int U = 4;                  /* columns in flight per thread, one scratch column each */
+  static_assert(TW % U == 0, "tile width");
   __shared__ q128 sx[TW];
+  __shared__ uint32_t scr[U * QWA_COL_WORDS * ROWS];
   const int tid = threadIdx.x;
   const int64_t i = (int64_t)blockIdx.x * ROWS + tid;
   const bool live = i < g.m;
   const int64_t jb = (int64_t)blockIdx.y * jchunk;
   const int64_t je = (jb + jchunk < g.n) ? jb + jchunk : g.n;
-  qwide acc = qw_zero();
+  qwacc acc = qwa_zero();
   uint32_t bad = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) qwa_col_init(scr + u * QWA_COL_WORDS * ROWS + tid, ROWS);
   for (int64_t j0 = jb; j0 < je; j0 += TW) {
     for (int idx = tid; idx < TW; idx += ROWS) {
       const int64_t j = j0 + idx;
@@ -236,14 +268,30 @@ k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
     __syncthreads();
     const int lim = (int)((je - j0) < TW ? (je - j0) : TW);
     const q128 *col = g.A + j0 * g.lda + (live ? i : 0);
-#pragma unroll 4
-    for (int j = 0; j < lim; ++j) {
+    int j = 0;
+    for (; j + U <= lim; j += U) {
+      q128 a[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) a[u] = ldg128(col + (int64_t)(j + u) * g.lda);
+      bool rare = false, rr[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        rr[u] = qwa_fma(acc, qop_load_n(a[u]), qop_load_n(sx[j + u]), scr + u * QWA_COL_WORDS * ROWS + tid, ROWS);
+        rare |= rr[u];
+      }
+      if (rare) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (rr[u]) qwa_fma_rare(acc, a[u], sx[j + u], bad);
+      }
+    }
+    for (; j < lim; ++j) {
       const q128 a = ldg128(col + (int64_t)j * g.lda);
-      qw_fma(acc, qop_load(a), qop_load(sx[j]), bad);
+      if (qwa_fma(acc, qop_load_n(a), qop_load_n(sx[j]), scr + tid, ROWS)) qwa_fma_rare(acc, a, sx[j], bad);
     }
     __syncthreads();
   }
-  if (live) gv_store(part + ((int64_t)blockIdx.y * g.m + i) * 8, acc, bad);
+  if (live) gv_store(part + ((int64_t)blockIdx.y * g.m + i) * 8, qwa_fold(acc), bad);
 }
 
 __global__ void k_gemv_col_fin(GemvArgs g, int splits, const uint32_t *part)
@@ -284,9 +332,13 @@ cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st)
   if (mode != 0 && fast_variant() != 0) {
     if (!a.col_major) {
       /* R rows per CTA: 4 when that still gives >= 2 CTAs per SM, else fewer rows for more CTAs */
-      if (a.m >= 4 * 148 * 2) k_gemv_row_wide<4, 256><<<(unsigned)((a.m + 3) / 4), 256, 0, st>>>(a);
-      else if (a.m >= 2 * 148) k_gemv_row_wide<2, 256><<<(unsigned)((a.m + 1) / 2), 256, 0, st>>>(a);
-      else k_gemv_row_wide<1, 256><<<(unsigned)a.m, 256, 0, st>>>(a);
+      /* R rows per CTA share the unpacked x_j; 2 x 128 measured best at m = 32768 (96 registers, 5 CTAs per SM);
+       * fewer rows per CTA when m alone cannot fill the chip */
+#define GV_LAUNCH(R_, NT_, MB_) k_gemv_row_wide<R_, NT_, MB_><<<(unsigned)((a.m + R_ - 1) / R_), NT_, 0, st>>>(a)
+      if (a.m >= 2 * 148 * 5) GV_LAUNCH(2, 128, 5);
+      else if (a.m >= 148 * 2) GV_LAUNCH(1, 128, 8);
+      else GV_LAUNCH(1, 256, 4);
+#undef GV_LAUNCH
       count_launch();
     } else {
       const int splits = gemv_col_splits(a.m, a.n);

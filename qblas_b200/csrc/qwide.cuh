@@ -9,15 +9,17 @@
  * only promises |r^ - r| <= gamma_k * sum|a_i||b_i|, so the per-step normalise and
  * round are dropped:
  *
- *   value(S) = W * 2^(E - 2*QW_EOFF + 64),   W = signed 192-bit integer (w5 = top limb)
+ *   value(S) = W * 2^(E - 2*QW_EOFF + QW_SH0),   W = signed 192-bit integer (w5 = top limb), QW_SH0 = 65
  *   step     : P = ma * mb (exact, 226 bits), d = E - (ea + eb) >= 0,
- *              W += sign * floor(P / 2^(64 + d))                    (truncate the magnitude)
+ *              W += sign * floor(P / 2^(QW_SH0 + d))                (truncate the magnitude)
  *   re-anchor: a product with ea + eb > E first shifts W right (arithmetic) and raises E.
  *
- * A product at the anchor has its MSB at window bit 160/161, so every term is truncated at least
- * 160 bits below the largest product: error per term <= 2^-160 * max_i|a_i b_i| — forty-seven bits
- * below the u = 2^-113 of a single correctly rounded operation — and the window has 29 bits of
- * carry headroom (2^29 terms per accumulator; the kernels stay far below that).  One RNE rounding
+ * A product at the anchor has its MSB at window bit 159/160 and the anchor is never more than
+ * QW_SLACK = 24 bits above the largest product seen so far, so every term is truncated at least
+ * 135 bits below the largest product: error per term < 2^-133 * max_i|a_i b_i| for every variant
+ * below (the hot-loop form qwa_fma may be off by two window units, see there) — twenty bits below
+ * the u = 2^-113 of a single correctly rounded operation — and the window has 30 bits of carry
+ * headroom (2^30 terms per accumulator; the kernels stay far below that).  One RNE rounding
  * happens at the very end (qw_round).  Zeros and subnormal operands take a slower exact path;
  * Inf/NaN operands only record the class of their product in `bad` (+Inf, -Inf, NaN incl. Inf*0),
  * and qw_finish turns the flags into the IEEE result of the chain: NaN if any NaN or Inf - Inf,
@@ -32,6 +34,10 @@ namespace qb {
 
 constexpr int32_t QW_EOFF = QBIAS + 112;      /* value(a) = ma * 2^(ea - QW_EOFF) */
 constexpr int32_t QW_EMPTY = -(1 << 28);      /* anchor of an accumulator that has seen nothing */
+constexpr int32_t QW_SLACK = 24;              /* a re-anchor leaves this many bits of room: 32 lanes x several accumulators
+                                                 per warp each meet a new largest product O(log n) times, and every one of
+                                                 them sends the whole warp through the out-of-line path */
+constexpr int32_t QW_SH0 = 65;                /* P >> QW_SH0 is what a product AT the anchor adds (= 32*2 + 1: see qwa_fma) */
 
 /* `bad` flags collected next to an accumulator: which non-finite products were seen */
 constexpr uint32_t QW_PINF = 1u, QW_NINF = 2u, QW_NAN = 4u;
@@ -131,11 +137,12 @@ QB_HD_NOINLINE qwide qw_fma_rare(qwide S, q128 a, q128 b, uint32_t *bad)
   if (q_is_zero(a) || q_is_zero(b)) return S;
   const qunp ua = q_unpack_finite(a), ub = q_unpack_finite(b);  /* subnormals normalised, e <= 0 */
   const int32_t ep = ua.e + ub.e;
-  if (ep > S.E) {
-    if (S.E != QW_EMPTY) qw_shr(S, (uint32_t)(ep - S.E));
-    S.E = ep;
+  if (ep > S.E) { /* re-anchor QW_SLACK bits above the new largest product */
+    const int32_t ne = ep + QW_SLACK;
+    if (S.E != QW_EMPTY) qw_shr(S, (uint32_t)(ne - S.E));
+    S.E = ne;
   }
-  int32_t d = S.E - ep;
+  int32_t d = S.E - ep + (QW_SH0 - 64);
   d = d > 192 ? 192 : d;
   uint32_t p[8];
   mul4x4((uint32_t)ua.ml, (uint32_t)(ua.ml >> 32), (uint32_t)ua.mh, (uint32_t)(ua.mh >> 32),
@@ -160,10 +167,227 @@ QB_HD void qw_fma(qwide &S, const qop &A, const qop &B, uint32_t &bad)
   }
   uint32_t p[8];
   mul4x4(A.m0, A.m1, A.m2, A.m3, B.m0, B.m1, B.m2, B.m3, p);
+  d += QW_SH0 - 64;
   d = d > 192 ? 192 : d;
   uint32_t f0, f1, f2, f3, f4, f5;
   qw_align(p, (uint32_t)d >> 5, (uint32_t)d & 31u, f0, f1, f2, f3, f4, f5);
   qw_addsub6(S, f0, f1, f2, f3, f4, f5, 0u - (A.s ^ B.s));
+}
+
+/* p2..p7 = words 2..7 of a*b for 113-bit mantissas (a3, b3 < 2^17), without the column-0 product a0*b0
+ * and without the low halves of the two column-1 products: the value is short of the exact
+ * (a*b) >> 64 by less than 3 units of p2, i.e. 3 * 2^-160 of the product.  13 wide multiplies and 2
+ * high multiplies instead of 16 wide ones; the two carry-save chains are ordered so that every carry
+ * is consumed by the next multiply-add (no carry is ever parked in a register):
+ *   even words:  C = (3:2) <- a0b2 + a1b1 + a2b0,  D = (5:4) <- a1b3 + a3b1 + a2b2 + carries(C),  F = (7:6) <- a3b3 + carry(D)
+ *   odd words :  A = (4:3) <- a0b3 + a3b0 + a1b2 + a2b1,  B = (6:5) <- a2b3 + a3b2 + carries(A)
+ * (a_i b_3 and a_3 b_j are below 2^49, which is why D's and B's first sums cannot carry). */
+QB_HD void mul4x4_top6(const uint32_t a0, const uint32_t a1, const uint32_t a2, const uint32_t a3, const uint32_t b0,
+                       const uint32_t b1, const uint32_t b2, const uint32_t b3, uint32_t &p2, uint32_t &p3, uint32_t &p4,
+                       uint32_t &p5, uint32_t &p6, uint32_t &p7)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t e2, e3, e4, e5, e6, e7, o3, o4, o5, o6;
+  asm("{\n\t"
+      "mul.lo.u32      %0, %10, %16;\n\t"      "mul.hi.u32      %1, %10, %16;\n\t"       /* C  = a0*b2 */
+      "mad.lo.cc.u32   %0, %11, %15, %0;\n\t"  "madc.hi.cc.u32  %1, %11, %15, %1;\n\t"   /* C += a1*b1 */
+      "madc.lo.cc.u32  %2, %11, %17, 0;\n\t"   "madc.hi.u32     %3, %11, %17, 0;\n\t"    /* D  = a1*b3 + cy */
+      "mad.lo.cc.u32   %0, %12, %14, %0;\n\t"  "madc.hi.cc.u32  %1, %12, %14, %1;\n\t"   /* C += a2*b0 */
+      "madc.lo.cc.u32  %2, %13, %15, %2;\n\t"  "madc.hi.u32     %3, %13, %15, %3;\n\t"   /* D += a3*b1 + cy */
+      "mad.lo.cc.u32   %2, %12, %16, %2;\n\t"  "madc.hi.cc.u32  %3, %12, %16, %3;\n\t"   /* D += a2*b2 */
+      "madc.lo.cc.u32  %4, %13, %17, 0;\n\t"   "madc.hi.u32     %5, %13, %17, 0;\n\t"    /* F  = a3*b3 + cy */
+      "mul.lo.u32      %6, %10, %17;\n\t"      "mul.hi.u32      %7, %10, %17;\n\t"       /* A  = a0*b3 */
+      "mad.lo.cc.u32   %6, %13, %14, %6;\n\t"  "madc.hi.u32     %7, %13, %14, %7;\n\t"   /* A += a3*b0 */
+      "mad.lo.cc.u32   %6, %11, %16, %6;\n\t"  "madc.hi.cc.u32  %7, %11, %16, %7;\n\t"   /* A += a1*b2 */
+      "madc.lo.cc.u32  %8, %12, %17, 0;\n\t"   "madc.hi.u32     %9, %12, %17, 0;\n\t"    /* B  = a2*b3 + cy */
+      "mad.lo.cc.u32   %6, %12, %15, %6;\n\t"  "madc.hi.cc.u32  %7, %12, %15, %7;\n\t"   /* A += a2*b1 */
+      "madc.lo.cc.u32  %8, %13, %16, %8;\n\t"  "madc.hi.u32     %9, %13, %16, %9;\n\t"   /* B += a3*b2 + cy */
+      "}"
+      : "=&r"(e2), "=&r"(e3), "=&r"(e4), "=&r"(e5), "=&r"(e6), "=&r"(e7), "=&r"(o3), "=&r"(o4), "=&r"(o5), "=&r"(o6)
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3));
+  /* word 2 also takes the high halves of the column-1 products; then even + (odd << 32).  opaque(): keep
+   * the two high multiplies as plain IMAD.HI (fused into a multiply-add they need a zeroed register pair) */
+  const uint32_t h1 = opaque(__umulhi(a0, b1)), h2 = opaque(__umulhi(a1, b0));
+  uint64_t t = (uint64_t)e2 + h1 + h2;
+  p2 = (uint32_t)t; t = (t >> 32) + e3 + o3;
+  p3 = (uint32_t)t; t = (t >> 32) + e4 + o4;
+  p4 = (uint32_t)t; t = (t >> 32) + e5 + o5;
+  p5 = (uint32_t)t; t = (t >> 32) + e6 + o6;
+  p6 = (uint32_t)t; t = (t >> 32) + e7;
+  p7 = (uint32_t)t;
+#else
+  typedef unsigned __int128 u128;
+  const u128 c2 = (u128)((uint64_t)a0 * b2) + (uint64_t)a1 * b1 + (uint64_t)a2 * b0 +
+                  (uint32_t)(((uint64_t)a0 * b1) >> 32) + (uint32_t)(((uint64_t)a1 * b0) >> 32);
+  const u128 c3 = (u128)((uint64_t)a0 * b3) + (uint64_t)a1 * b2 + (uint64_t)a2 * b1 + (uint64_t)a3 * b0;
+  const u128 c4 = (u128)((uint64_t)a1 * b3) + (uint64_t)a2 * b2 + (uint64_t)a3 * b1;
+  const u128 c5 = (u128)((uint64_t)a2 * b3) + (uint64_t)a3 * b2;
+  const u128 c6 = (u128)((uint64_t)a3 * b3);
+  u128 t = c2;
+  p2 = (uint32_t)t; t = (t >> 32) + c3;
+  p3 = (uint32_t)t; t = (t >> 32) + c4;
+  p4 = (uint32_t)t; t = (t >> 32) + c5;
+  p5 = (uint32_t)t; t = (t >> 32) + c6;
+  p6 = (uint32_t)t; t >>= 32;
+  p7 = (uint32_t)t;
+#endif
+}
+
+/* ------------------------------------------------------------------ hot-loop form (qdot / qnrm2 / qgemv kernels)
+ * The generic step above spends most of its instructions on the ALU pipe (a 3-stage word multiplexer,
+ * six funnel shifts, six XORs and a seven-add carry chain per element) while the multiplier pipe idles.
+ * qwa_fma does the same update with
+ *   - the whole-word part of the alignment through a per-thread shared-memory column (6 STS + 6 LDS at a
+ *     dynamic word offset: the load/store pipe instead of 18 SELs),
+ *   - the bit part and the accumulation fused into seven multiply-adds  W += t_j * 2^(32-r)  that land
+ *     directly on the accumulator limbs.  Adjacent 64-bit products overlap by one word, so the window is
+ *     kept as two carry-save halves, W = e + v (mod 2^192): e takes the products that start on an even
+ *     word, v the ones that start on an odd word; they are only added together when the accumulator
+ *     leaves the loop (qwa_fold),
+ *   - subtraction by complementing the aligned words (t -> -t - 1, on the multiplier pipe) plus a
+ *     carry-in of 1: the complemented zero words above the product are the two's-complement sign
+ *     extension, and because M is a power of two the seven complemented products sum to exactly ~F,
+ *     so a negative term subtracts exactly what the positive term of the same magnitude adds
+ *     (x*y - x*y cancels to zero, as the README's 1e20 + 1 - 1e20 case needs).
+ * With sh = QW_SH0 + d = 32*(wq+2) + r, r in [1,32], M = 2^(32-r):  P >> sh = (T*M) >> 64 where
+ * T = P >> 32*(wq+1).  The word t_0 lies entirely below the window and is dropped, so the magnitude
+ * added is F = floor(P/2^sh) or one unit less: |error| < 2 units = 2^-158 of a product at the anchor. */
+struct qwacc {
+  uint64_t e01, e23, e45;          /* even half, words (1:0) (3:2) (5:4): 64-bit so that they live in register pairs */
+  uint32_t v0;                     /* odd half: word 0, words (2:1) (4:3), word 5 */
+  uint64_t v12, v34;
+  uint32_t v5;
+  int32_t E;
+};
+
+constexpr int QWA_COL_WORDS = 12;  /* scratch column: 6 product words + 6 zero words (written once) */
+
+QB_HD qwacc qwa_zero()
+{
+  qwacc z;
+  z.e01 = z.e23 = z.e45 = z.v12 = z.v34 = 0;
+  z.v0 = z.v5 = 0;
+  z.E = QW_EMPTY;
+  return z;
+}
+
+/* W = e + v */
+QB_HD qwide qwa_fold(const qwacc &a)
+{
+  qwide s;
+  s.w0 = (uint32_t)a.e01; s.w1 = (uint32_t)(a.e01 >> 32); s.w2 = (uint32_t)a.e23; s.w3 = (uint32_t)(a.e23 >> 32);
+  s.w4 = (uint32_t)a.e45; s.w5 = (uint32_t)(a.e45 >> 32);
+  s.E = a.E;
+  qw_addsub6(s, a.v0, (uint32_t)a.v12, (uint32_t)(a.v12 >> 32), (uint32_t)a.v34, (uint32_t)(a.v34 >> 32), a.v5, 0u);
+  return s;
+}
+
+QB_HD void qwa_set(qwacc &a, const qwide &s)
+{
+  a.e01 = ((uint64_t)s.w1 << 32) | s.w0; a.e23 = ((uint64_t)s.w3 << 32) | s.w2; a.e45 = ((uint64_t)s.w5 << 32) | s.w4;
+  a.v12 = a.v34 = 0;
+  a.v0 = a.v5 = 0;
+  a.E = s.E;
+}
+
+/* the zero half of a scratch column; each thread owns col[k * stride], k < QWA_COL_WORDS */
+QB_HD void qwa_col_init(uint32_t *col, uint32_t stride)
+{
+  for (int k = 6; k < QWA_COL_WORDS; ++k) col[k * stride] = 0u;
+}
+
+/* S <- S + A*B when that is the common case (both operands normal, product not above the anchor).
+ * Otherwise S is left untouched and the function returns true: the caller then runs qwa_fma_rare.
+ * Branch-free, so that several independent accumulators interleave in one instruction stream. */
+QB_HD bool qwa_fma(qwacc &S, const qop &A, const qop &B, uint32_t *col, uint32_t stride)
+{
+  const bool normal = ((uint32_t)A.e - 1u < 0x7ffeu) && ((uint32_t)B.e - 1u < 0x7ffeu);
+  const int32_t d = normal ? S.E - A.e - B.e : -1;
+  const bool rare = d < 0;
+  uint32_t p2, p3, p4, p5, p6, p7;
+  mul4x4_top6(A.m0, A.m1, A.m2, A.m3, B.m0, B.m1, B.m2, B.m3, p2, p3, p4, p5, p6, p7);
+  col[0] = p2; col[stride] = p3; col[2 * stride] = p4; col[3 * stride] = p5; col[4 * stride] = p6;
+  col[5 * stride] = p7;
+  uint32_t du = (uint32_t)d;
+  du = du > 223u ? 223u : du;                      /* a declined step (d < 0) lands here too: wq = 6 reads only zero words */
+  const uint32_t wq = du >> 5;
+  const uint32_t r = (du & 31u) + 1u;              /* bit part of the shift, 1..32 */
+  const uint32_t M = 0x80000000u >> (du & 31u);    /* 2^(32-r) */
+  const uint32_t mask = rare ? 0u : (0u - (A.s ^ B.s));   /* 0 for a declined step: zero words, nothing is added */
+  const uint32_t *q = col + wq * stride;
+  /* aligned words, complemented when subtracting (their zero extension becomes the sign extension) */
+  const uint32_t t1 = q[0] ^ mask, t2 = q[stride] ^ mask, t3 = q[2 * stride] ^ mask, t4 = q[3 * stride] ^ mask,
+                 t5 = q[4 * stride] ^ mask, t6 = q[5 * stride] ^ mask;
+#if defined(__CUDA_ARCH__)
+  const uint32_t t1s = __funnelshift_rc(t1, 0u, r);   /* hi(t1 * M) = t1 >> r (0 when r = 32) */
+  asm("{\n\t"
+      ".reg .u32 cy, a0, a1, a2, a3, a4, a5, b1, b2, b3, b4;\n\t"
+      "mov.b64 {a0, a1}, %0;\n\t" "mov.b64 {a2, a3}, %1;\n\t" "mov.b64 {a4, a5}, %2;\n\t"
+      "mov.b64 {b1, b2}, %4;\n\t" "mov.b64 {b3, b4}, %5;\n\t"
+      "add.cc.u32      cy, %13, %13;\n\t"                                           /* carry <- 1 when subtracting */
+      "madc.lo.cc.u32  a0, %8, %14, a0;\n\t"   "madc.hi.cc.u32 a1, %8, %14, a1;\n\t"    /* t2*M -> (e1:e0) */
+      "madc.lo.cc.u32  a2, %10, %14, a2;\n\t"  "madc.hi.cc.u32 a3, %10, %14, a3;\n\t"   /* t4*M -> (e3:e2) */
+      "madc.lo.cc.u32  a4, %12, %14, a4;\n\t"  "madc.hi.u32    a5, %12, %14, a5;\n\t"   /* t6*M -> (e5:e4) */
+      "add.cc.u32      %3, %3, %7;\n\t"                                                 /* hi(t1*M) -> v0 */
+      "madc.lo.cc.u32  b1, %9, %14, b1;\n\t"   "madc.hi.cc.u32 b2, %9, %14, b2;\n\t"    /* t3*M -> (v2:v1) */
+      "madc.lo.cc.u32  b3, %11, %14, b3;\n\t"  "madc.hi.cc.u32 b4, %11, %14, b4;\n\t"   /* t5*M -> (v4:v3) */
+      "madc.lo.u32     %6, %13, %14, %6;\n\t"                                           /* lo(t7*M) -> v5, t7 = sign words */
+      "mov.b64 %0, {a0, a1};\n\t" "mov.b64 %1, {a2, a3};\n\t" "mov.b64 %2, {a4, a5};\n\t"
+      "mov.b64 %4, {b1, b2};\n\t" "mov.b64 %5, {b3, b4};\n\t"
+      "}"
+      : "+l"(S.e01), "+l"(S.e23), "+l"(S.e45), "+r"(S.v0), "+l"(S.v12), "+l"(S.v34), "+r"(S.v5)
+      : "r"(t1s), "r"(t2), "r"(t3), "r"(t4), "r"(t5), "r"(t6), "r"(mask), "r"(M));
+#else
+  (void)r;
+  const uint32_t t[8] = {0u, t1, t2, t3, t4, t5, t6, mask};
+  {
+    uint64_t *e[3] = {&S.e01, &S.e23, &S.e45};
+    uint64_t c = mask & 1u;
+    for (int j = 0; j < 3; ++j) { /* t_{2j+2} * M at words (2j, 2j+1) */
+      const uint64_t pr = (uint64_t)t[2 * j + 2] * M;
+      const unsigned __int128 sum = (unsigned __int128)*e[j] + pr + c;
+      *e[j] = (uint64_t)sum;
+      c = (uint64_t)(sum >> 64);
+    }
+  }
+  {
+    uint64_t c = (uint64_t)S.v0 + (uint32_t)(((uint64_t)t[1] * M) >> 32);
+    S.v0 = (uint32_t)c; c >>= 32;
+    uint64_t *v[2] = {&S.v12, &S.v34};
+    for (int j = 0; j < 2; ++j) { /* t_{2j+3} * M at words (2j+1, 2j+2) */
+      const uint64_t pr = (uint64_t)t[2 * j + 3] * M;
+      const unsigned __int128 sum = (unsigned __int128)*v[j] + pr + c;
+      *v[j] = (uint64_t)sum;
+      c = (uint64_t)(sum >> 64);
+    }
+    S.v5 = (uint32_t)(c + S.v5 + (uint32_t)((uint64_t)t[7] * M));
+  }
+#endif
+  return rare;
+}
+
+/* the step qwa_fma declined: through the generic window code, out of line.  Everything goes through
+ * memory (w = the 8-word record {w0..w5, E, bad} of the FOLDED accumulator) so that the call does not
+ * pin the hot loop's registers to the ABI's argument registers. */
+QB_HD_NOINLINE void qwa_fma_rare_mem(uint32_t *w, const q128 *a, const q128 *b)
+{
+  qwide s;
+  s.w0 = w[0]; s.w1 = w[1]; s.w2 = w[2]; s.w3 = w[3]; s.w4 = w[4]; s.w5 = w[5]; s.E = (int32_t)w[6];
+  uint32_t bad = 0;
+  s = qw_fma_rare(s, *a, *b, &bad);
+  w[0] = s.w0; w[1] = s.w1; w[2] = s.w2; w[3] = s.w3; w[4] = s.w4; w[5] = s.w5; w[6] = (uint32_t)s.E; w[7] |= bad;
+}
+
+QB_HD void qwa_fma_rare(qwacc &S, const q128 &a, const q128 &b, uint32_t &bad)
+{
+  const qwide f = qwa_fold(S);
+  uint32_t w[8] = {f.w0, f.w1, f.w2, f.w3, f.w4, f.w5, (uint32_t)f.E, 0u};
+  q128 ab[2] = {a, b};
+  qwa_fma_rare_mem(w, &ab[0], &ab[1]);
+  qwide g;
+  g.w0 = w[0]; g.w1 = w[1]; g.w2 = w[2]; g.w3 = w[3]; g.w4 = w[4]; g.w5 = w[5]; g.E = (int32_t)w[6];
+  qwa_set(S, g);
+  bad |= w[7];
 }
 
 /* S <- S + T (exact up to the window truncation of the lower-anchored one) */
@@ -200,9 +424,9 @@ QB_HD q128 qw_round(const qwide &S)
   if (u256_is_zero(R)) return q_zero(0);
   const int lz = u256_clz(R);
   R = u256_shl(R, (uint32_t)lz);
-  /* value = Wmag * 2^(E - 2*EOFF + 64); R = Wmag << (64 + lz), MSB at bit 255:
-   * value = R * 2^(er - QBIAS - 255)  =>  er = E - 2*EOFF - lz + QBIAS + 255 */
-  const int32_t er = S.E - 2 * QW_EOFF - lz + QBIAS + 255;
+  /* value = Wmag * 2^(E - 2*EOFF + SH0); R = Wmag << (64 + lz), MSB at bit 255:
+   * value = R * 2^(er - QBIAS - 255)  =>  er = E - 2*EOFF + SH0 - 64 - lz + QBIAS + 255 */
+  const int32_t er = S.E - 2 * QW_EOFF + (QW_SH0 - 64) - lz + QBIAS + 255;
   return q_round_pack(sign, er, R);
 }
 
