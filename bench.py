@@ -258,6 +258,12 @@ def own_arm(args, rank, world, local_rank):
     S = args.size
     m_loc, n, k = S, S, S
     M = S * world
+    strong = False
+    if args.shape:   # BASELINE config 4: a FIXED global problem, C row-blocks of M / world rows per GPU (strong scaling)
+        M, n, k = (int(v) for v in args.shape.split(","))
+        assert M % world == 0, "--shape M must be a multiple of the number of GPUs"
+        m_loc = M // world
+        strong = True
     dev = torch.device("cuda", local_rank)
 
     # inputs resident in HBM before the timed region (3 x 1 GiB at S=8192: far larger than the 126 MB L2)
@@ -323,24 +329,29 @@ def own_arm(args, rank, world, local_rank):
     rng = np.random.default_rng(5 + rank)
     ns = 48 if mode == qb.MODE_REFERENCE else 16
     idx = np.stack([rng.integers(0, m_loc, ns), rng.integers(0, n, ns)], axis=1)
-    Ah, Bh = to_host(A), to_host(B)
-    got = to_host(Cblk.reshape(m_loc, n, 2)[torch.as_tensor(idx[:, 0], device=dev), torch.as_tensor(idx[:, 1], device=dev)].contiguous())
+    ri, ci = torch.as_tensor(idx[:, 0], device=dev), torch.as_tensor(idx[:, 1], device=dev)
+    got = to_host(Cblk.reshape(m_loc, n, 2)[ri, ci].contiguous())
+    # only the sampled rows of A and columns of B leave the device: a (ns x k) by (k x ns) problem whose
+    # diagonal holds the sampled entries (same k order, so the reference-order oracle applies unchanged)
+    Ah = to_host(A.reshape(m_loc, k, 2)[ri].contiguous().reshape(ns * k, 2))
+    Bh = to_host(B.reshape(k, n, 2)[:, ci].contiguous().reshape(k * ns, 2))
+    didx = np.stack([np.arange(ns), np.arange(ns)], axis=1)
     if mode == qb.MODE_REFERENCE:
         # C_in = None -> +0 in the oracle; mul(0, c_in) = +-0 and fma(alpha, s, +-0) == s unless s == 0
-        exp = orc.gemm_sample("R", m_loc, n, k, 1.0, Ah, k, Bh, n, 0.0, None, n, idx)
+        exp = orc.gemm_sample("R", ns, ns, k, 1.0, Ah, k, Bh, ns, 0.0, None, ns, didx)
         mism = int((~quad.same_bits(got, exp)).sum())
         against = "oracle/qoracle.c, reference order, bit exact"
     else:
         from fractions import Fraction
         from exact_ref import exact_matmul_rounded
         mism = 0
-        exp_ref = orc.gemm_sample("R", m_loc, n, k, 1.0, Ah, k, Bh, n, 0.0, None, n, idx)
-        ab = orc.absdot_sample("R", k, Ah, k, Bh, n, idx)
+        exp_ref = orc.gemm_sample("R", ns, ns, k, 1.0, Ah, k, Bh, ns, 0.0, None, ns, didx)
+        ab = orc.absdot_sample("R", k, Ah, k, Bh, ns, didx)
         u = Fraction(1, 2 ** 113); gam = k * u / (1 - k * u)
         f = lambda v: quad.to_fraction(int(v[1]), int(v[0]))
-        for q, (i, j) in enumerate(idx):
+        for q in range(ns):
             if plan and plan["pairs"] > 0:   # tensor path: the exact inner product rounded once
-                s_ex = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, np.ascontiguousarray(Bh[j::n][:k]), 1, 1, 1, k)
+                s_ex = exact_matmul_rounded(Ah[q * k:(q + 1) * k], k, np.ascontiguousarray(Bh[q::ns][:k]), 1, 1, 1, k)
                 if not quad.same_bits(got[q:q + 1], s_ex).all():
                     mism += 1
             if abs(f(got[q]) - f(exp_ref[q])) > 2 * gam * f(ab[q]):   # and always inside the fast-mode contract vs the reference order
@@ -375,10 +386,14 @@ def own_arm(args, rank, world, local_rank):
                     "unit": "GFLOP/s (binary128)", "frac": kern_gflops / pk, "traffic": None,
                     "peak_source": "live register-resident qFMA microbenchmark (qb_fma_microbench_dev, best of 5 shapes; same qacc_fma as k_gemm, no global memory)",
                     "algorithmic": f"2*m*n*k = {2.0 * m_loc * n * k:.4g} binary128 flops per launch; avg launch {call_ms:.2f} ms (CUDA events)"}
-        if not args.no_extra:
+        if not args.no_extra and not strong:
             _secondary(qb, torch, dev, args, S, mode, extra)
 
     # ---- e2e: reference-named C entry point with HOST buffers (pinned), copies inside the timed region
+    if strong:   # config-4 tool runs report the device-resident + collective figure only (B alone is 16 GiB of pinned host memory)
+        _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_step, M, n, k, m_loc, None, launches, clk, roof, None, ns, mism, against,
+                    call_ms, extra, strong)
+        return
     torch.cuda.empty_cache()
     hA = torch.empty((m_loc * k, 2), dtype=torch.int64).pin_memory(); hA.copy_(A)
     hB = torch.empty((k * n, 2), dtype=torch.int64).pin_memory(); hB.copy_(B)
@@ -398,24 +413,31 @@ def own_arm(args, rank, world, local_rank):
     e2e = {"value": e2e_val, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * (m_loc * k + k * n + m_loc * n), "d2h_bytes_per_step": 16 * m_loc * n,
            "ms_per_step": float(te.item()) * 1e3,
            "api": "quadblas_qgemm (reference C ABI), pinned host buffers, synchronous; per-rank row block, no collective", "steps": e2e_steps}
+    _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_step, M, n, k, m_loc, e2e, launches, clk, roof, "time", ns, mism, against,
+                call_ms, extra, strong)
+
+
+def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_step, M, n, k, m_loc, e2e, launches, clk, roof, cpu, ns, mism, against,
+                call_ms, extra, strong):
     mism_t = torch.tensor([mism], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(mism_t)
 
     if rank == 0:
-        try:
-            cpu = time_reference_gemm(12.0)
-            cpu = {k2: cpu[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
-        except Exception as e:
-            cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
+        if cpu == "time":
+            try:
+                cpu = time_reference_gemm(12.0)
+                cpu = {k2: cpu[k2] for k2 in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:
+                cpu = {"value": None, "unit": "GFLOP/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e!r}"}
         fast = mode == qb.MODE_FAST
         line = {
             "metric": "binary128 qgemm GFLOPS", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "binary128 (exact signed 8-bit slices on the int8 tensor cores, 448-bit integer recombination, one rounding)" if fast
                      else "binary128 (software, u32 integer limbs)",
             "data": "synthetic",
-            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' if world > 1 else 'BASELINE config 3, 1xB200'})",
+            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
                        "mode": "fast: Ozaki-style exact int8 slicing on tcgen05 (inner products exact, rounded once; inside the gamma_k bound)" if fast
                                else "reference-order (bit exact, kc=126), integer-limb kernel",
                        "inputs": f"{args.dist}: full 113-bit random mantissas, device resident" if args.dist != "D53" else "D53: doubles U(-1,1) cast to quad (the reference's own benchmark distribution)",
@@ -437,6 +459,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--shape", default=None, help="M,N,K of a fixed global problem split into M/world-row blocks (BASELINE config 4, e.g. 32768,32768,32768)")
     ap.add_argument("--mode", default="fast", choices=["ref", "fast"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary qgemv/qdot/reference-order figures")
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
