@@ -96,9 +96,17 @@ int qb_get_tensor_path(void);
  * reference's per-element operation, level1.hpp:24, re-associated).  Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
-/* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, S_A*S_B int8 GEMMs,
- * workspace bytes, padded K} */
-void qb_oz_last_stats(int64_t *out8);
+/* Accuracy setting of the tensor path.  keep = 0: every digit-plane product is computed, the inner
+ * products are EXACT and rounded once.  keep = d > 0 (default 17): only the d most significant
+ * diagonals are multiplied; every element is checked (|J| >= 2^125, csrc/qb_ozaki.cu) and the few that
+ * fail are recomputed in the window accumulator, so the result always satisfies the fast-mode
+ * contract |c^ - c| <= gamma_k (|A||B|)_ij, but it is no longer the exact sum rounded once. */
+void qb_set_tensor_keep(int keep);
+int qb_get_tensor_keep(void);
+/* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, digit-plane products
+ * per row pass, workspace bytes, padded K, diagonals kept, elements sent to the fix-up, row passes
+ * redone with all diagonals, 0} */
+void qb_oz_last_stats(int64_t *out12);
 /* Summed device time (ms, CUDA events on the launching stream) of the tcgen05 kernel launches of
  * the last tensor-path qgemm; waits for them to finish.  *launches (optional) = how many. */
 double qb_oz_last_mma_ms(int *launches);

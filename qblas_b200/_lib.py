@@ -60,6 +60,8 @@ def lib():
         "qb_get_honor_trans": (ci, []),
         "qb_set_tensor_path": (None, [ci]),
         "qb_get_tensor_path": (ci, []),
+        "qb_set_tensor_keep": (None, [ci]),
+        "qb_get_tensor_keep": (ci, []),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),

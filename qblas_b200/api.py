@@ -235,6 +235,15 @@ def get_tensor_path():
     return lib().qb_get_tensor_path()
 
 
+def set_tensor_keep(keep):
+    """Tensor-path accuracy: 0 = all diagonals (exact inner products), d > 0 = the d leading diagonals + per-element check and fix-up."""
+    lib().qb_set_tensor_keep(int(keep))
+
+
+def get_tensor_keep():
+    return lib().qb_get_tensor_keep()
+
+
 def set_fast_variant(v):
     """Fast-mode accumulate of dot/nrm2/gemv: 1 = window accumulator (csrc/qwide.cuh), 0 = rounded-FMA chains."""
     lib().qb_set_fast_variant(int(v))
@@ -246,9 +255,9 @@ def get_fast_variant():
 
 def oz_last_stats():
     """Plan of the last tensor-path qgemm."""
-    out = (C.c_int64 * 8)()
+    out = (C.c_int64 * 12)()
     lib().qb_oz_last_stats(out)
-    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes", "Kp"]
+    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes", "Kp", "keep", "flagged", "redo_passes"]
     return {k: int(out[i]) for i, k in enumerate(keys)}
 
 

@@ -194,10 +194,17 @@ void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
 void qb_set_fast_variant(int v) { g_fastvar.store(v ? 1 : 0); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
-void qb_oz_last_stats(int64_t *out8)
+void qb_set_tensor_keep(int keep)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  oz_set_keep(keep);
+}
+int qb_get_tensor_keep(void) { return oz_get_keep(); }
+void qb_oz_last_stats(int64_t *out12)
 {
   const OzStats s = oz_last_stats();
-  out8[0] = s.SA; out8[1] = s.SB; out8[2] = s.ndiag; out8[3] = s.nchunks; out8[4] = s.row_passes; out8[5] = s.pairs; out8[6] = s.ws_bytes; out8[7] = s.Kp;
+  out12[0] = s.SA; out12[1] = s.SB; out12[2] = s.ndiag; out12[3] = s.nchunks; out12[4] = s.row_passes; out12[5] = s.pairs; out12[6] = s.ws_bytes;
+  out12[7] = s.Kp; out12[8] = s.keep; out12[9] = s.flagged; out12[10] = s.redo_passes; out12[11] = 0;
 }
 double qb_oz_last_mma_ms(int *launches)
 {

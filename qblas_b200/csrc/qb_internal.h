@@ -52,12 +52,14 @@ int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24
-struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; };
+struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; };
 /* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
-                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st);
+                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);
 OzStats oz_last_stats();
+void oz_set_keep(int keep);   /* leading diagonals multiplied (bounded setting); 0 = all = exact inner products */
+int oz_get_keep();
 double oz_last_mma_ms(int *launches);
 void oz_release();
 

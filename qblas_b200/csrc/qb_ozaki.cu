@@ -20,14 +20,27 @@
  *            binary128, then the reference epilogue  C = fma(alpha, s, mul(beta, C))
  *            (level3.hpp:102-109).
  *
- * Accuracy: the inner product is exact, so |c^ - c| <= u |A B|_ij (+ the two epilogue roundings),
- * far inside the fast-mode contract  gamma_k (|A||B|)_ij.  Inputs this cannot represent (Inf/NaN,
+ * Accuracy, exact setting (qb_set_tensor_keep(0)): the inner product is exact, so |c^ - c| <= u |A B|_ij
+ * (+ the two epilogue roundings), far inside the fast-mode contract  gamma_k (|A||B|)_ij.
+ *
+ * Bounded setting (default, qb_set_tensor_keep(17)): only the `keep` most significant diagonals
+ * d = 0 .. keep-1 are multiplied (153 digit-plane products instead of 18 x 18 = 324 for full 113-bit
+ * mantissas).  With J = sum_{d<keep} D_d 256^(keep-1-d), the dropped diagonals amount to less than
+ * min(S_A,S_B) * k * 64.3 units of J, so whenever |J| >= 2^125 the truncation is below
+ * (k-1) u |c_ij| and the rounded J meets  |c^ - c| <= k u |c| <= gamma_k (|A||B|)_ij  (k >= 2,
+ * S <= 24; derivation in DESIGN.md §4.1).  The fold checks that per element; an element that fails
+ * it (heavy cancellation: |c_ij| more than ~2^18 below the typical size) is NOT written by the fold
+ * and is recomputed by k_oz_fixup, one warp per element, in the unrounded window accumulator of
+ * qwide.cuh (error < k 2^-133 max|a b|, also inside the contract).  If more than 1/64 of a row pass
+ * fails (structured cancellation), the pass is redone with all diagonals for the failed elements.  Inputs this cannot represent (Inf/NaN,
  * or a row whose exponent span needs more than QB_OZ_MAX_SLICES digits) make the planner decline
  * and the caller runs the integer-limb kernel (qb_level3.cu) instead; that is a different CUDA
  * kernel of this library, not a CPU fallback.
  */
 #include "qb_internal.h"
 #include "qb_tc.cuh"
+#include "q128_chain.cuh"
+#include "qwide.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -323,7 +336,14 @@ struct OzFoldArgs {
   const int *emaxA, *emaxB; int SA, SB;
   uint32_t *W; int w_in, w_out;      /* 448-bit running sums across K chunks: [OZ_NL][Mp*Np] */
   q128 alpha, beta; q128 *C; int64_t sci, scj;
+  /* bounded setting: ndiag = kept diagonals, the integer is J (units of 256^exp8 above the full one) */
+  int exp8;                          /* dropped diagonals (0 in the exact setting) */
+  int check;                         /* 1: elements with |J| < 2^OZ_JMIN_BIT are flagged and left unwritten */
+  int only_flagged;                  /* 1: (exact redo) write only the elements flagged earlier */
+  uint8_t *flag;                     /* [Mp*Np] */
+  int2 *list; int list_cap; int *counter;
 };
+static constexpr int OZ_JMIN_BIT = 125;
 
 __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
 {
@@ -357,6 +377,7 @@ __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
     for (int l = 0; l < OZ_NL; ++l) g.W[(int64_t)l * plane + off] = L[l];
     return;
   }
+  if (g.only_flagged && !g.flag[off]) return;
   /* ---- sign / magnitude ---- */
   const uint32_t neg = L[OZ_NL - 1] >> 31;
   if (neg) {
@@ -365,8 +386,19 @@ __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
     for (int l = 0; l < OZ_NL; ++l) { const uint64_t t = (uint64_t)(~L[l]) + c; L[l] = (uint32_t)t; c = (uint32_t)(t >> 32); }
   }
   int top = -1;
+  uint32_t topv = 0;
 #pragma unroll
-  for (int l = 0; l < OZ_NL; ++l) if (L[l]) top = l;
+  for (int l = 0; l < OZ_NL; ++l) if (L[l]) { top = l; topv = L[l]; }
+  if (g.check) { /* |J| >= 2^125 or the element goes to the fix-up (header comment) */
+    const int msb = top < 0 ? -1 : 32 * top + 31 - __clz((int)topv);
+    const bool weak = msb < OZ_JMIN_BIT;
+    g.flag[off] = weak ? 1 : 0;
+    if (weak) {
+      const int slot = atomicAdd(g.counter, 1);
+      if (slot < g.list_cap) g.list[slot] = make_int2((int)(g.row0 + i), (int)j);
+      return;
+    }
+  }
   q128 sum;
   if (top < 0) {
     sum = q_zero(0); /* an exact zero sum is +0 (a +0-seeded chain never yields -0) */
@@ -397,11 +429,55 @@ __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
     /* I * 2^Eb, Eb = baseA + baseB - 2 * 16495; MSB of I at bit p = 32 top + 31 - lz  ->  er = p + Eb + QBIAS */
     const int baseA = g.emaxA[g.row0 + i] + 115 - 8 * g.SA, baseB = g.emaxB[j] + 115 - 8 * g.SB;
     const int p = 32 * top + 31 - lz;
-    const int er = p + baseA + baseB - 2 * 16495 + QBIAS;
+    const int er = p + 8 * g.exp8 + baseA + baseB - 2 * 16495 + QBIAS;
     sum = q_round_pack(neg, er, Rq);
   }
   q128 *c = g.C + i * g.sci + j * g.scj;
   *c = q_fma(g.alpha, sum, q_mul(g.beta, *c)); /* level3.hpp:102-109: beta*C is always evaluated */
+}
+
+/* ------------------------------------------------------------------ fix-up of the flagged elements (bounded setting) */
+struct OzFixArgs {
+  const int2 *list; const int *counter; int list_cap;
+  const q128 *A; int64_t sai, sal; const q128 *B; int64_t sbl, sbj; int64_t k;
+  q128 alpha, beta; q128 *C; int64_t sci, scj;
+};
+__device__ __noinline__ qwide oz_merge(qwide a, qwide b) { qw_merge(a, b); return a; }
+/* one warp per flagged C element: the k products go into the unrounded window accumulator (lanes
+ * stride over k), a shuffle tree merges the 32 windows, lane 0 rounds once and applies the epilogue */
+__global__ void __launch_bounds__(128) k_oz_fixup(const OzFixArgs g)
+{
+  __shared__ uint32_t scr[QWA_COL_WORDS * 128];
+  const int lane = threadIdx.x & 31;
+  uint32_t *col = scr + threadIdx.x;
+  qwa_col_init(col, 128);
+  int count = *g.counter;
+  if (count > g.list_cap) count = g.list_cap;
+  const int nwarps = gridDim.x * 4;
+  for (int e = blockIdx.x * 4 + (threadIdx.x >> 5); e < count; e += nwarps) {
+    const int2 ij = g.list[e];
+    const q128 *ap = g.A + (int64_t)ij.x * g.sai, *bp = g.B + (int64_t)ij.y * g.sbj;
+    qwacc acc = qwa_zero();
+    uint32_t bad = 0;
+    for (int64_t l = lane; l < g.k; l += 32) {
+      const q128 a = ap[l * g.sal], b = bp[l * g.sbl];
+      if (qwa_fma(acc, qop_load_n(a), qop_load_n(b), col, 128)) qwa_fma_rare(acc, a, b, bad);
+    }
+    qwide v = qwa_fold(acc);
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      qwide t;
+      t.w0 = __shfl_down_sync(0xffffffffu, v.w0, o); t.w1 = __shfl_down_sync(0xffffffffu, v.w1, o);
+      t.w2 = __shfl_down_sync(0xffffffffu, v.w2, o); t.w3 = __shfl_down_sync(0xffffffffu, v.w3, o);
+      t.w4 = __shfl_down_sync(0xffffffffu, v.w4, o); t.w5 = __shfl_down_sync(0xffffffffu, v.w5, o);
+      t.E = __shfl_down_sync(0xffffffffu, v.E, o);
+      v = oz_merge(v, t);
+    }
+    if (lane == 0) {
+      q128 *c = g.C + (int64_t)ij.x * g.sci + (int64_t)ij.y * g.scj;
+      *c = q_fma(g.alpha, qw_finish(v, bad), q_mul(g.beta, *c));
+    }
+  }
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -448,7 +524,7 @@ static int sm_count()
 
 /* D[d] = sum_{s+t=d} A_s B_t^T over k-blocks [kb_begin, kb_begin + nkb) */
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
-                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st)
+                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep)
 {
   static bool attr_set = false;
   if (!attr_set) {
@@ -460,6 +536,7 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
   if (!make_plane_map(&tmA, pA, SA, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, SB, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
   OzMmaArgs g;
   g.D = D; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
+  if (keep > 0 && keep < g.ndiag) g.ndiag = keep;   /* diagonals 0 .. keep-1 only */
   g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
   g.kb_begin = kb_begin; g.nkb = nkb;
   /* heaviest diagonals first so the static round-robin over CTAs stays balanced */
@@ -517,6 +594,9 @@ static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 static OzStats g_last_stats;
 OzStats oz_last_stats() { return g_last_stats; }
+static int g_oz_keep = 17;      /* leading diagonals multiplied in the bounded setting; 0 = all (exact) */
+void oz_set_keep(int keep) { g_oz_keep = keep < 0 ? 0 : keep; }
+int oz_get_keep() { return g_oz_keep; }
 
 /* CUDA events around every k_oz_mma launch of the last qgemm, on the launching stream (bench.py's
  * roofline needs the kernel's own duration, not the whole call's) */
@@ -541,6 +621,9 @@ double oz_last_mma_ms(int *launches)
   if (launches) *launches = g_ev_used;
   return tot;
 }
+
+/* capacity of the fix-up list of one row pass: above 1/64 of the pass the exact redo is cheaper */
+static inline int64_t oz_list_cap(int64_t mb, int64_t n) { return std::max<int64_t>(1024, std::min<int64_t>((mb * n) / 64, (int64_t)1 << 22)); }
 
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget)
@@ -583,6 +666,9 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   const int SA = std::max(1, (WA + 2 + 7) / 8), SB = std::max(1, (WB + 2 + 7) / 8);
   if (fl != 0 || SA > OZ_MAX_S || SB > OZ_MAX_S) return cudaSuccess; /* decline: Inf/NaN or span too wide */
   const int ndiag = SA + SB - 1;
+  /* bounded setting: multiply only the leading diagonals (needs k >= 2 for the error budget, header comment) */
+  const int keep = (g_oz_keep > 0 && g_oz_keep < ndiag && k >= 2) ? g_oz_keep : ndiag;
+  const bool bounded = keep < ndiag;
   /* int32 exactness: Kc * min(SA, SB) * 2^14 <= 2^31 - 1 */
   int64_t kc_blocks = ((((int64_t)1 << 17) - 1) / std::min(SA, SB)) / OZ_BK;
   if (kc_blocks < 1) return cudaSuccess;
@@ -595,6 +681,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     const int64_t Mp = rup(mb, OZ_BM);
     size_t b = rup((int64_t)SA * mb * Kp, 1024) + (size_t)ndiag * Mp * Np * 4;
     if (nchunks > 1) b += (size_t)OZ_NL * Mp * Np * 4;
+    if (bounded) b += (size_t)rup(Mp * Np, 1024) + (size_t)oz_list_cap(mb, n) * sizeof(int2);
     return b;
   };
   int64_t mb = m;
@@ -610,36 +697,82 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.B, n, k, a.sbj, a.sbl, emaxB, SB, Kp, pB);
     count_launch();
   }
+  int64_t flagged_total = 0, pairs_done = 0;
+  int redo_passes = 0;
+  auto npairs = [&](int nd) { int64_t p = 0; for (int d = 0; d < nd; ++d) p += std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; return p; };
+  int *counter = flags + 8;   /* meta: one int, zeroed per row pass */
   for (int64_t r0 = 0; r0 < m; r0 += mb) {
     const int64_t mr = std::min(mb, m - r0);
     const int64_t Mp = rup(mr, OZ_BM);
     int32_t *D = (int32_t *)(pA + rup((int64_t)SA * mb * Kp, 1024));
     uint32_t *W = (uint32_t *)(D + (size_t)ndiag * rup(mb, OZ_BM) * Np);
+    uint8_t *flagp = (uint8_t *)(W + (nchunks > 1 ? (size_t)OZ_NL * rup(mb, OZ_BM) * Np : 0));
+    int2 *list = (int2 *)(flagp + rup(rup(mb, OZ_BM) * Np, 1024));
+    const int list_cap = (int)oz_list_cap(mb, n);
     {
       const int64_t threads = mr * (Kp / 4);
       k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, SA, Kp, pA);
       count_launch();
     }
-    for (int c = 0; c < nchunks; ++c) {
-      const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
-      oz_ev_record(0, st);
-      e = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D, Mp, Np, st);
-      oz_ev_record(1, st);
+    /* one sweep over the K chunks with `nd` leading diagonals; `redo` = exact redo of the flagged elements */
+    auto sweep = [&](int nd, bool check, bool redo) -> cudaError_t {
+      for (int c = 0; c < nchunks; ++c) {
+        const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
+        oz_ev_record(0, st);
+        cudaError_t e2 = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D, Mp, Np, st, nd);
+        oz_ev_record(1, st);
+        if (e2 != cudaSuccess) return e2;
+        OzFoldArgs f;
+        f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = nd; f.m = mr; f.n = n; f.row0 = r0;
+        f.emaxA = emaxA; f.emaxB = emaxB; f.SA = SA; f.SB = SB;
+        f.W = W; f.w_in = c > 0; f.w_out = c + 1 < nchunks;
+        f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
+        f.exp8 = ndiag - nd; f.check = check ? 1 : 0; f.only_flagged = redo ? 1 : 0;
+        f.flag = flagp; f.list = list; f.list_cap = list_cap; f.counter = counter;
+        const int64_t elems = mr * n;
+        k_oz_fold<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(f);
+        count_launch();
+        e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) return e2;
+      }
+      pairs_done += npairs(nd);
+      return cudaSuccess;
+    };
+    if (!bounded) {
+      e = sweep(ndiag, false, false);
       if (e != cudaSuccess) return e;
-      OzFoldArgs f;
-      f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = ndiag; f.m = mr; f.n = n; f.row0 = r0;
-      f.emaxA = emaxA; f.emaxB = emaxB; f.SA = SA; f.SB = SB;
-      f.W = W; f.w_in = c > 0; f.w_out = c + 1 < nchunks;
-      f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
-      const int64_t elems = mr * n;
-      k_oz_fold<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(f);
+      continue;
+    }
+    cudaMemsetAsync(counter, 0, 4, st);
+    e = sweep(keep, true, false);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(g_oz.h_plan + 8, counter, 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    const int nflag = g_oz.h_plan[8];
+    flagged_total += nflag;
+    if (nflag == 0) continue;
+    if (nflag <= list_cap) {
+      OzFixArgs x;
+      x.list = list; x.counter = counter; x.list_cap = list_cap;
+      x.A = a.A; x.sai = a.sai; x.sal = a.sal; x.B = a.B; x.sbl = a.sbl; x.sbj = a.sbj; x.k = k;
+      x.alpha = a.alpha; x.beta = a.beta; x.C = a.C; x.sci = a.sci; x.scj = a.scj;
+      const int blocks = (int)std::min<int64_t>((nflag + 3) / 4, (int64_t)sm_count() * 8);
+      k_oz_fixup<<<blocks, 128, 0, st>>>(x);
       count_launch();
       e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+    } else { /* structured cancellation: all diagonals, written for the flagged elements only */
+      ++redo_passes;
+      e = sweep(ndiag, false, true);
       if (e != cudaSuccess) return e;
     }
   }
   g_last_stats.SA = SA; g_last_stats.SB = SB; g_last_stats.ndiag = ndiag; g_last_stats.nchunks = nchunks;
-  g_last_stats.pairs = (int64_t)SA * SB; g_last_stats.row_passes = (int)((m + mb - 1) / mb);
+  g_last_stats.row_passes = (int)((m + mb - 1) / mb);
+  g_last_stats.pairs = pairs_done / g_last_stats.row_passes;   /* digit-plane products per row pass (bounded + any redo) */
+  g_last_stats.keep = keep; g_last_stats.flagged = flagged_total; g_last_stats.redo_passes = redo_passes;
   g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
   *used = 1;
   return cudaSuccess;

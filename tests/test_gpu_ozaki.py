@@ -14,6 +14,16 @@ from qblas_b200 import quad
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True)
+def _exact_setting(qb):
+    """The tests of this file that compare bit for bit run the tensor path with ALL diagonals (qb_set_tensor_keep(0));
+    the bounded setting (the default) is covered by the test_bounded_* tests, which select it themselves."""
+    old = qb.get_tensor_keep()
+    qb.set_tensor_keep(0)
+    yield
+    qb.set_tensor_keep(old)
+
+
 def _diag_ref(pa, pb, m, n):
     SA, SB = pa.shape[0], pb.shape[0]
     a = pa.cpu().numpy().astype(np.int64)
@@ -151,3 +161,107 @@ def test_fast_gemm_large_matches_sampled_exact(qb, oracle):
         s = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, np.ascontiguousarray(Bh[j::n][:k]), 1, 1, 1, k)
         want = _epilogue(oracle, quad.from_double(np.array([1.0]))[0], s, quad.from_double(np.array([0.0]))[0], C0[i * n + j:i * n + j + 1])
         assert quad.same_bits(got[i * n + j:i * n + j + 1], want).all(), (i, j, st)
+
+
+# ------------------------------------------------------------------ bounded setting (qb_set_tensor_keep(d), default d = 17)
+def _contract_check(qb, oracle, m, n, k, A, B, got, C0=None, beta0=True):
+    """|c^ - c| <= gamma_k (|A||B|)_ij for every entry, c = exact inner product (alpha = 1, beta = 0)."""
+    from fractions import Fraction
+    s = exact_matmul_rounded(A, k, B, n, m, n, k, "R")                 # exact, rounded once: within u|c| of c
+    idx = np.stack(np.meshgrid(np.arange(m), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
+    ab = oracle.absdot_sample("R", k, A, k, B, n, idx)
+    u = Fraction(1, 2 ** 113); gam = k * u / (1 - k * u)
+    f = lambda v: quad.to_fraction(int(v[1]), int(v[0]))
+    worst = Fraction(0)
+    for q in range(m * n):
+        err = abs(f(got[q]) - f(s[q]))
+        bound = gam * f(ab[q])
+        assert err <= bound + u * abs(f(s[q])), (q, float(err), float(bound))
+        if bound: worst = max(worst, err / bound)
+    return float(worst)
+
+
+@pytest.mark.parametrize("m,n,k,kind", [(130, 257, 300, "D113"), (128, 256, 1024, "D113"), (140, 260, 520, "Dexp")])
+def test_bounded_tensor_path_meets_contract(qb, oracle, m, n, k, kind):
+    rng = np.random.default_rng(m * 7 + k)
+    mk = (lambda r, c: np.ascontiguousarray(quad.random_quads(rng, (r, c), "D113", emin=-28, emax=28).reshape(r * c, 2))) if kind == "Dexp" \
+        else (lambda r, c: qgen.matrix(rng, r, c, kind, c))
+    A = mk(m, k); B = mk(k, n); C0 = qgen.matrix(rng, m, n, "D113", n)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 0.0, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+        dC2 = to_dev(C0)
+        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 0.0, dC2, n)
+        torch.cuda.synchronize()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["pairs"] > 0 and st["keep"] == 17 and st["keep"] < st["ndiag"], st
+    want_pairs = sum(min(d, st["SA"] - 1) - max(0, d - (st["SB"] - 1)) + 1 for d in range(17))
+    assert st["pairs"] == want_pairs < st["SA"] * st["SB"], st        # e.g. 153 digit-plane products instead of 18 * 18
+    got = to_host(dC)
+    assert quad.same_bits(got, to_host(dC2)).all()                    # deterministic
+    worst = _contract_check(qb, oracle, m, n, k, A, B, got)
+    assert worst < 0.5                                                # typically ~1/k: far inside the bound
+
+
+def test_bounded_fixup_on_cancelling_entries(qb, oracle):
+    """Columns of B built so that some inner products cancel to ~2^-60 of their terms: those entries fail the
+    |J| >= 2^125 check, are left to k_oz_fixup and must still meet the contract."""
+    rng = np.random.default_rng(77)
+    m, n, k = 128, 256, 512
+    A = qgen.matrix(rng, m, k, "D113", k)
+    Bm = quad.random_quads(rng, (k, n), "D113")
+    # column j (odd) = -(column j-1) in the first half of k, + the same in the second half, applied to rows of A
+    # that repeat their first half: A[i, k/2 + l] = A[i, l] for i < 4  ->  c[i, j] cancels to ~2^-107 for those (i, j odd)
+    Am = A.reshape(m, k, 2).copy()
+    Am[:4, k // 2:] = Am[:4, :k // 2]
+    Bm[k // 2:, 1::2] = Bm[:k // 2, 1::2] ^ np.array([0, 1 << 63], dtype=np.uint64)   # negated copy
+    Bm[k // 2:, 1::2, 0] ^= np.uint64(1) << np.uint64(5)                               # ... up to one low mantissa bit
+    A2 = np.ascontiguousarray(Am.reshape(m * k, 2)); B2 = np.ascontiguousarray(Bm.reshape(k * n, 2))
+    C0 = qgen.matrix(rng, m, n, "D113", n)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, 1.0, to_dev(A2), k, to_dev(B2), n, 0.0, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert 4 * (n // 2) <= st["flagged"] <= 1024 and st["redo_passes"] == 0, st   # 512 entries <= list capacity: k_oz_fixup, no redo
+    _contract_check(qb, oracle, m, n, k, A2, B2, to_host(dC))
+
+
+def test_bounded_redo_when_many_entries_vanish(qb, oracle):
+    """A quarter of the rows of A are zero: every entry of those C rows is an exact 0, far more than 1/64 of the pass, so the
+    pass is redone with all diagonals for them; alpha/beta epilogue included (C_in of the flagged entries must be intact)."""
+    rng = np.random.default_rng(78)
+    m, n, k = 256, 256, 384
+    A = qgen.matrix(rng, m, k, "D113", k).reshape(m, k, 2)
+    A[::4] = 0
+    A = np.ascontiguousarray(A.reshape(m * k, 2)); B = qgen.matrix(rng, k, n, "D113", n); C0 = qgen.matrix(rng, m, n, "D113", n)
+    alpha, beta = quad.random_quads(rng, 2)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["redo_passes"] == 1 and st["flagged"] >= (m // 4) * n, st
+    got = to_host(dC).reshape(m, n, 2)
+    # the vanished rows: exact sum 0 -> C = fma(alpha, +0, mul(beta, C_in)), bit for bit
+    z = np.zeros(((m // 4) * n, 2), dtype=np.uint64)
+    want = _epilogue(oracle, alpha, z, beta, np.ascontiguousarray(C0.reshape(m, n, 2)[::4].reshape(-1, 2)))
+    assert quad.same_bits(got[::4].reshape(-1, 2), want).all()
+    # the other rows went through the bounded path: exact-rounded sums agree to within the contract (sampled)
+    s = exact_matmul_rounded(A, k, B, n, m, n, k, "R").reshape(m, n, 2)
+    rows = [1, 2, 3, 129, 255]
+    for i in rows:
+        w = _epilogue(oracle, alpha, np.ascontiguousarray(s[i]), beta, np.ascontiguousarray(C0.reshape(m, n, 2)[i]))
+        for j in (0, 100, 255):
+            fg, fw = quad.to_fraction(int(got[i, j, 1]), int(got[i, j, 0])), quad.to_fraction(int(w[j, 1]), int(w[j, 0]))
+            assert abs(fg - fw) <= abs(fw) / 2 ** 90
