@@ -12,6 +12,7 @@
  */
 #include "../../include/qblas_b200.h"
 #include "qb_internal.h"
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -389,6 +390,83 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
   const size_t b_bytes = (col != tB) ? mat_bytes(n, k, ldb) : mat_bytes(k, n, ldb);
   const size_t c_bytes = col ? mat_bytes(n, m, ldc) : mat_bytes(m, n, ldc);
   const void *dA, *dB, *dC; bool sa, sb, sc;
+  /* Large all-host problems: pipeline the transfers against the compute.  The operand that every block
+   * needs (B for row-major, A for col-major) goes first; then C is cut into P contiguous slabs (row
+   * blocks for row-major, column blocks for col-major) and for each slab the matching block of the
+   * other operand and the slab of C_in are uploaded on a copy stream while earlier slabs compute, and
+   * each finished slab is downloaded on a third stream while the next one computes.  Every slab is an
+   * ordinary qgemm on device pointers, so the arithmetic (and, in reference-order mode, every bit) is
+   * the same as the unpipelined call. */
+  const int64_t split = col ? n : m;
+  const bool all_host = !is_device_ptr(A) && !is_device_ptr(B) && !is_device_ptr(C);
+  if (all_host && split >= 1024 && a_bytes + b_bytes + c_bytes >= ((size_t)64 << 20)) {
+    if ((rc = stage_in(0, A, a_bytes, false, &dA, &sa))) return rc;
+    if ((rc = stage_in(1, B, b_bytes, false, &dB, &sb))) return rc;
+    if ((rc = stage_in(2, C, c_bytes, false, &dC, &sc))) return rc;
+    static cudaStream_t cs = nullptr, ks = nullptr, ds = nullptr;
+    if (!cs) {
+      if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(QB_ERR_CUDA, "qgemm: stream creation", cudaGetLastError());
+    }
+    constexpr int P = 4;
+    cudaEvent_t ev_in[P + 1], ev_done[P];
+    for (int i = 0; i <= P; ++i) cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
+    for (int i = 0; i < P; ++i) cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
+    /* block [c0, c0+cnt) of a matrix X(outer, inner) with leading dimension ld, taken along `along_outer`:
+     * a contiguous slab when taken along the strided direction, a 2-D copy otherwise */
+    auto xfer = [&](void *dev, void *host, bool to_dev, bool along_outer, int64_t outer, int64_t inner, int64_t ld, int64_t c0, int64_t cnt,
+                    cudaStream_t st) -> cudaError_t {
+      if (cnt <= 0) return cudaSuccess;
+      char *d = (char *)dev, *h = (char *)host;
+      if (along_outer) {
+        const size_t off = (size_t)c0 * ld * 16, bytes = ((size_t)(cnt - 1) * ld + inner) * 16;
+        return to_dev ? cudaMemcpyAsync(d + off, h + off, bytes, cudaMemcpyHostToDevice, st) : cudaMemcpyAsync(h + off, d + off, bytes, cudaMemcpyDeviceToHost, st);
+      }
+      const size_t off = (size_t)c0 * 16;
+      return to_dev ? cudaMemcpy2DAsync(d + off, (size_t)ld * 16, h + off, (size_t)ld * 16, (size_t)cnt * 16, (size_t)outer, cudaMemcpyHostToDevice, st)
+                    : cudaMemcpy2DAsync(h + off, (size_t)ld * 16, d + off, (size_t)ld * 16, (size_t)cnt * 16, (size_t)outer, cudaMemcpyDeviceToHost, st);
+    };
+    cudaError_t e = cudaSuccess;
+    /* storage shapes (outer x inner): A is k x m when (col != tA) else m x k; B is n x k when (col != tB) else k x n */
+    const bool a_m_outer = !(col != tA), b_n_outer = (col != tB);
+    if (!col) e = cudaMemcpyAsync((void *)dB, B, b_bytes, cudaMemcpyHostToDevice, cs);   /* shared operand first */
+    else e = cudaMemcpyAsync((void *)dA, A, a_bytes, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventRecord(ev_in[P], cs);
+    const int64_t blk = ((split + P - 1) / P + 127) / 128 * 128;
+    for (int p = 0; p < P && e == cudaSuccess; ++p) {
+      const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
+      if (cnt <= 0) { e = cudaEventRecord(ev_in[p], cs); continue; }
+      if (!col) e = xfer((void *)dA, (void *)A, true, a_m_outer, a_m_outer ? m : k, a_m_outer ? k : m, lda, c0, cnt, cs);
+      else e = xfer((void *)dB, (void *)B, true, b_n_outer, b_n_outer ? n : k, b_n_outer ? k : n, ldb, c0, cnt, cs);
+      if (e == cudaSuccess) e = xfer((void *)dC, C, true, true, col ? n : m, col ? m : n, ldc, c0, cnt, cs);   /* beta*C is always read */
+      if (e == cudaSuccess) e = cudaEventRecord(ev_in[p], cs);
+    }
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, ev_in[P], 0);
+    for (int p = 0; p < P && e == cudaSuccess && rc == QB_OK; ++p) {
+      const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
+      if (cnt <= 0) break;
+      e = cudaStreamWaitEvent(ks, ev_in[p], 0);
+      if (e != cudaSuccess) break;
+      /* element offsets of the block inside A / B / C (same strides as gemm_dev_impl derives) */
+      const int64_t a_off = !col ? c0 * (a_m_outer ? lda : 1) : 0;
+      const int64_t b_off = col ? c0 * (b_n_outer ? ldb : 1) : 0;
+      const int64_t c_off = c0 * ldc;
+      rc = gemm_dev_impl(layout, transa, transb, col ? m : cnt, col ? cnt : n, k, toq(alpha), (const q128 *)dA + a_off, lda, (const q128 *)dB + b_off, ldb,
+                         toq(beta), (q128 *)dC + c_off, ldc, ks);
+      if (rc) break;
+      e = cudaEventRecord(ev_done[p], ks);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ds, ev_done[p], 0);
+      if (e == cudaSuccess) e = xfer((void *)dC, C, false, true, col ? n : m, col ? m : n, ldc, c0, cnt, ds);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ks), e4 = cudaStreamSynchronize(ds);
+    for (int i = 0; i <= P; ++i) cudaEventDestroy(ev_in[i]);
+    for (int i = 0; i < P; ++i) cudaEventDestroy(ev_done[i]);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm pipelined host path", e);
+    return QB_OK;
+  }
   if ((rc = stage_in(0, A, a_bytes, true, &dA, &sa))) return rc;
   if ((rc = stage_in(1, B, b_bytes, true, &dB, &sb))) return rc;
   if ((rc = stage_in(2, C, c_bytes, true, &dC, &sc))) return rc; /* beta*C is always read (level3.hpp:107) */

@@ -286,18 +286,11 @@ __global__ void k_oz_plan(const int *emaxA, const int *lminA, int64_t m, const i
 /* thread = (row r, 4 consecutive k); plane s (0 = most significant digit) is [rows][Kp] int8.
  * x = X_int * 2^(base - 16495), base = emax[r] + 115 - 8 S, |X_int| < 2^(8S-2); digits are the
  * balanced base-256 expansion of X_int (so the sign needs no separate plane). */
+/* digits of the 4 elements (row r, k = 4 g4 .. 4 g4 + 3): word[j] = byte q is digit j (0 = least significant) of element q */
 template <int MAXS>
-__global__ void k_oz_slice(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax, int S, int64_t Kp,
-                           int8_t *__restrict__ planes)
+__device__ __forceinline__ void oz_slice4(const q128 *__restrict__ X, int64_t r, int64_t g4, int64_t K, int64_t sr, int64_t sk, int base, int S,
+                                          uint32_t (&word)[MAXS])
 {
-  const int64_t groups = Kp >> 2;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= rows * groups) return;
-  int64_t r, g4;
-  if (sk == 1 || sr != 1) { r = tid / groups; g4 = tid % groups; }   /* lanes along k */
-  else { r = tid % rows; g4 = tid / rows; }                          /* lanes along rows (rows contiguous in memory) */
-  const int base = emax[r] + 115 - 8 * S;
-  uint32_t word[MAXS];
 #pragma unroll
   for (int s = 0; s < MAXS; ++s) word[s] = 0;
 #pragma unroll
@@ -324,14 +317,56 @@ __global__ void k_oz_slice(const q128 *__restrict__ X, int64_t rows, int64_t K, 
       }
     }
   }
+}
+
+/* k contiguous in memory (or fully strided): thread = (row, 4 consecutive k), lanes along k; every thread
+ * stores one 32-bit word per plane and a warp's stores are 128 contiguous bytes of one plane row. */
+template <int MAXS>
+__global__ void k_oz_slice(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax, int S, int64_t Kp,
+                           int8_t *__restrict__ planes)
+{
+  const int64_t groups = Kp >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= rows * groups) return;
+  const int64_t r = tid / groups, g4 = tid % groups;
+  uint32_t word[MAXS];
+  oz_slice4<MAXS>(X, r, g4, K, sr, sk, emax[r] + 115 - 8 * S, S, word);
 #pragma unroll
   for (int j = 0; j < MAXS; ++j)
     if (j < S) *reinterpret_cast<uint32_t *>(planes + ((int64_t)(S - 1 - j) * rows + r) * Kp + g4 * 4) = word[j];
 }
 
+/* rows contiguous in memory (B of a row-major product, A of a col-major one): a CTA of 32 x 8 threads takes a tile of
+ * 32 rows x 32 k with lanes along the rows, so the 16-byte loads coalesce; the plane words are transposed through
+ * shared memory and leave as 32-byte runs along K (the direct store would scatter 4-byte words Kp bytes apart). */
+template <int MAXS>
+__global__ void __launch_bounds__(256) k_oz_slice_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
+                                                   int S, int64_t Kp, int8_t *__restrict__ planes)
+{
+  __shared__ uint32_t sm[MAXS][32][9];            /* [digit][row][k-group], padded against bank conflicts */
+  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, g0 = (int64_t)blockIdx.y * 8;
+  const int64_t r = r0 + lane, g4 = g0 + wg;
+  if (r < rows) {
+    uint32_t word[MAXS];
+    oz_slice4<MAXS>(X, r, g4, K, sr, sk, emax[r] + 115 - 8 * S, S, word);
+#pragma unroll
+    for (int j = 0; j < MAXS; ++j)
+      if (j < S) sm[j][lane][wg] = word[j];
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < S * 64; q += 256) {
+    const int j = q >> 6, row = (q & 63) >> 1, half = q & 1;
+    if (r0 + row >= rows) continue;
+    const uint32_t *src = &sm[j][row][half * 4];
+    *reinterpret_cast<uint4 *>(planes + ((int64_t)(S - 1 - j) * rows + r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
+  }
+}
+
 /* ------------------------------------------------------------------ fold: diagonals -> binary128 */
 struct OzFoldArgs {
   const int32_t *D; int64_t Mp, Np; int ndiag;
+  int nsets; int64_t set_stride;     /* K chunks kept as separate int32 diagonal sets (summed here in 64 bits) */
   int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
   const int *emaxA, *emaxB; int SA, SB;
   uint32_t *W; int w_in, w_out;      /* 448-bit running sums across K chunks: [OZ_NL][Mp*Np] */
@@ -345,6 +380,8 @@ struct OzFoldArgs {
 };
 static constexpr int OZ_JMIN_BIT = 125;
 
+/* NSETS > 0: that many diagonal sets, unrolled; NSETS = 0: g.nsets of them (any count) */
+template <int NSETS>
 __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
 {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -359,7 +396,17 @@ __global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int d = g.ndiag - 1 - (4 * l + b);
-      if (d >= 0) acc += (long long)g.D[(int64_t)d * plane + off] << (8 * b);
+      if (d >= 0) {
+        const int32_t *dp = g.D + (int64_t)d * plane + off;
+        long long v = dp[0];
+        if (NSETS > 0) {
+#pragma unroll
+          for (int c = 1; c < NSETS; ++c) v += dp[c * g.set_stride];
+        } else {
+          for (int c = 1; c < g.nsets; ++c) v += dp[c * g.set_stride];
+        }
+        acc += v << (8 * b);
+      }
     }
     L[l] = (uint32_t)acc;
     carry = acc >> 32;
@@ -622,6 +669,18 @@ double oz_last_mma_ms(int *launches)
   return tot;
 }
 
+static void launch_oz_slice(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int S, int64_t Kp, int8_t *planes, cudaStream_t st)
+{
+  if (sk == 1 || sr != 1) {
+    const int64_t threads = rows * (Kp / 4);
+    k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, rows, K, sr, sk, emax, S, Kp, planes);
+  } else {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)(Kp / 32));
+    k_oz_slice_t<OZ_MAX_S><<<grid, 256, 0, st>>>(X, rows, K, sr, sk, emax, S, Kp, planes);
+  }
+  count_launch();
+}
+
 /* capacity of the fix-up list of one row pass: above 1/64 of the pass the exact redo is cheaper */
 static inline int64_t oz_list_cap(int64_t mb, int64_t n) { return std::max<int64_t>(1024, std::min<int64_t>((mb * n) / 64, (int64_t)1 << 22)); }
 
@@ -674,16 +733,24 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   if (kc_blocks < 1) return cudaSuccess;
   const int64_t nkb_total = Kp / OZ_BK;
   const int nchunks = (int)((nkb_total + kc_blocks - 1) / kc_blocks);
+  kc_blocks = (nkb_total + nchunks - 1) / nchunks;   /* equal chunks: a short last chunk runs the tensor kernel at a worse duty cycle */
   /* ---- workspace: planes B | planes A (per row pass) | D | W ---- */
   const int64_t Np = rup(n, OZ_BN);
   const size_t pb_b = rup((int64_t)SB * n * Kp, 1024);
-  auto pass_bytes = [&](int64_t mb) -> size_t {
+  /* K chunks: either every chunk keeps its own int32 diagonal set and ONE fold sums them (`sets` = nchunks, no wide
+   * workspace, least traffic), or - when that does not fit next to the full-diagonal redo buffer - one set is
+   * folded after every chunk into the 448-bit running sums W */
+  const int nd_main = keep;                      /* diagonals of the main sweep (== ndiag in the exact setting) */
+  auto d_planes = [&](bool multi) -> int64_t { return multi ? std::max<int64_t>((int64_t)nchunks * nd_main, ndiag) : ndiag; };
+  auto pass_bytes_v = [&](int64_t mb, bool multi) -> size_t {
     const int64_t Mp = rup(mb, OZ_BM);
-    size_t b = rup((int64_t)SA * mb * Kp, 1024) + (size_t)ndiag * Mp * Np * 4;
-    if (nchunks > 1) b += (size_t)OZ_NL * Mp * Np * 4;
+    size_t b = rup((int64_t)SA * mb * Kp, 1024) + (size_t)d_planes(multi) * Mp * Np * 4;
+    if (nchunks > 1) b += (size_t)OZ_NL * Mp * Np * 4;      /* W: always reserved (the redo sweep folds per chunk) */
     if (bounded) b += (size_t)rup(Mp * Np, 1024) + (size_t)oz_list_cap(mb, n) * sizeof(int2);
     return b;
   };
+  const bool multi = nchunks > 1 && pb_b + pass_bytes_v(m, true) <= ws_budget;
+  auto pass_bytes = [&](int64_t mb) -> size_t { return pass_bytes_v(mb, multi); };
   int64_t mb = m;
   while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
   if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess; /* does not fit: decline */
@@ -692,11 +759,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   int8_t *pB = (int8_t *)g_oz.buf;
   int8_t *pA = pB + pb_b;
   /* ---- slice B once ---- */
-  {
-    const int64_t threads = n * (Kp / 4);
-    k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.B, n, k, a.sbj, a.sbl, emaxB, SB, Kp, pB);
-    count_launch();
-  }
+  launch_oz_slice(a.B, n, k, a.sbj, a.sbl, emaxB, SB, Kp, pB, st);
   int64_t flagged_total = 0, pairs_done = 0;
   int redo_passes = 0;
   auto npairs = [&](int nd) { int64_t p = 0; for (int d = 0; d < nd; ++d) p += std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; return p; };
@@ -705,32 +768,40 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     const int64_t mr = std::min(mb, m - r0);
     const int64_t Mp = rup(mr, OZ_BM);
     int32_t *D = (int32_t *)(pA + rup((int64_t)SA * mb * Kp, 1024));
-    uint32_t *W = (uint32_t *)(D + (size_t)ndiag * rup(mb, OZ_BM) * Np);
+    uint32_t *W = (uint32_t *)(D + (size_t)d_planes(multi) * rup(mb, OZ_BM) * Np);
     uint8_t *flagp = (uint8_t *)(W + (nchunks > 1 ? (size_t)OZ_NL * rup(mb, OZ_BM) * Np : 0));
     int2 *list = (int2 *)(flagp + rup(rup(mb, OZ_BM) * Np, 1024));
     const int list_cap = (int)oz_list_cap(mb, n);
-    {
-      const int64_t threads = mr * (Kp / 4);
-      k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, SA, Kp, pA);
-      count_launch();
-    }
+    launch_oz_slice(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, SA, Kp, pA, st);
     /* one sweep over the K chunks with `nd` leading diagonals; `redo` = exact redo of the flagged elements */
     auto sweep = [&](int nd, bool check, bool redo) -> cudaError_t {
+      const bool sets = multi && !redo;          /* every chunk into its own diagonal set, one fold at the end */
+      const int64_t set_stride = (int64_t)nd * Mp * Np;
       for (int c = 0; c < nchunks; ++c) {
         const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
         oz_ev_record(0, st);
-        cudaError_t e2 = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D, Mp, Np, st, nd);
+        cudaError_t e2 = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D + (sets ? c * set_stride : 0), Mp, Np, st, nd);
         oz_ev_record(1, st);
         if (e2 != cudaSuccess) return e2;
+        if (sets && c + 1 < nchunks) continue;
         OzFoldArgs f;
         f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = nd; f.m = mr; f.n = n; f.row0 = r0;
+        f.nsets = sets ? nchunks : 1; f.set_stride = set_stride;
         f.emaxA = emaxA; f.emaxB = emaxB; f.SA = SA; f.SB = SB;
-        f.W = W; f.w_in = c > 0; f.w_out = c + 1 < nchunks;
+        f.W = W; f.w_in = !sets && c > 0; f.w_out = !sets && c + 1 < nchunks;
         f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
         f.exp8 = ndiag - nd; f.check = check ? 1 : 0; f.only_flagged = redo ? 1 : 0;
         f.flag = flagp; f.list = list; f.list_cap = list_cap; f.counter = counter;
         const int64_t elems = mr * n;
-        k_oz_fold<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(f);
+        const unsigned fg = (unsigned)((elems + 255) / 256);
+        switch (f.nsets) {
+        case 1: k_oz_fold<1><<<fg, 256, 0, st>>>(f); break;
+        case 2: k_oz_fold<2><<<fg, 256, 0, st>>>(f); break;
+        case 3: k_oz_fold<3><<<fg, 256, 0, st>>>(f); break;
+        case 4: k_oz_fold<4><<<fg, 256, 0, st>>>(f); break;
+        case 5: k_oz_fold<5><<<fg, 256, 0, st>>>(f); break;
+        default: k_oz_fold<0><<<fg, 256, 0, st>>>(f); break;
+        }
         count_launch();
         e2 = cudaGetLastError();
         if (e2 != cudaSuccess) return e2;
