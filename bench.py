@@ -274,12 +274,37 @@ def own_arm(args, rank, world, local_rank):
     Cfull = dev_random((M * n,), args.dist, 9, dev)          # C_in (beta=0 still reads it, level3.hpp:107)
     Cblk = Cfull[rank * m_loc * n:(rank + 1) * m_loc * n]
 
+    Cb3 = Cblk.reshape(m_loc, n, 2)
+    Cf3 = Cfull.reshape(world, m_loc, n, 2)
+
+    def gemm_and_gather():
+        """local qgemm + all-gather of the C blocks.  With --overlap P > 1 the rows are produced in P passes and the gather of
+        each pass's rows is issued from the library's row-pass hook (qb_set_gemm_pass_callback), so it runs on NCCL's stream
+        while the next pass computes; only the last pass's gather is exposed."""
+        if world == 1:
+            qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
+            return
+        if args.overlap <= 1:
+            qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
+            dist.all_gather_into_tensor(Cfull, Cblk)          # in place: Cblk is rank's slice of Cfull
+            return
+        works = []
+
+        def on_rows(r0, rows):
+            works.append(dist.all_gather([Cf3[q, r0:r0 + rows] for q in range(world)], Cb3[r0:r0 + rows], async_op=True))
+
+        qb.set_gemm_pass_callback(on_rows, args.overlap)
+        try:
+            qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
+        finally:
+            qb.set_gemm_pass_callback(None)
+        for w in works:
+            w.wait()
+
     def step():
         if world > 1:
             dist.broadcast(B, src=0)                          # byte-typed payload (int64 view of quads)
-        qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
-        if world > 1:
-            dist.all_gather_into_tensor(Cfull, Cblk)          # in place: Cblk is rank's slice of Cfull
+        gemm_and_gather()
 
     def sync():
         torch.cuda.synchronize()
@@ -302,10 +327,8 @@ def own_arm(args, rank, world, local_rank):
         if world > 1:
             dist.broadcast(B, src=0)
         kev[i][0].record()
-        qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
+        gemm_and_gather()
         kev[i][1].record()
-        if world > 1:
-            dist.all_gather_into_tensor(Cfull, Cblk)
         if mode == qb.MODE_FAST and rank == 0 and i == args.steps - 1:
             pass  # per-kernel events are read after the timed region (reading them blocks the host)
     ev1.record()
@@ -440,7 +463,7 @@ def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_s
             "dtype": "binary128 (exact signed 8-bit slices on the int8 tensor cores, wide-integer recombination, one rounding)" if fast
                      else "binary128 (software, u32 integer limbs)",
             "data": "synthetic",
-            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
+            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' + (f', all-gather issued per row pass ({args.overlap} passes) from the row-pass hook' if args.overlap > 1 else '') if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
                        "mode": ("fast: Ozaki-style exact int8 slicing on tcgen05; " + (f"{plan['keep']} leading diagonals + per-element check/fix-up ({plan['flagged']} entries fixed, {plan['redo_passes']} passes redone): inside the gamma_k bound"
                                 if plan and plan["keep"] < plan["ndiag"] else "all diagonals: inner products exact, rounded once")) if fast
                                else "reference-order (bit exact, kc=126), integer-limb kernel",
@@ -467,6 +490,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["ref", "fast"])
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary qgemv/qdot/reference-order figures")
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
+    ap.add_argument("--overlap", type=int, default=4, help="N > 1: row passes whose all-gathers overlap the next pass (1 = one all-gather after the qgemm)")
     ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 17)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -96,6 +96,14 @@ int qb_get_tensor_path(void);
  * reference's per-element operation, level1.hpp:24, re-associated).  Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
+/* Row-pass hook of the device qgemm (qb_gemm_dev).  When a callback is installed, the rows of C are produced in at
+ * least `min_passes` passes (tensor path; the integer-limb kernel makes one) and cb(row0, rows, user) runs on the
+ * calling host thread right after the work of each pass has been enqueued on the stream: a collective issued from the
+ * callback (e.g. an all-gather of those rows, ordered after the stream's work so far) overlaps the next pass.  rows are
+ * relative to the C passed to the call ("m" direction: rows for row-major, also rows of op(A) for col-major).  Every row
+ * is reported exactly once.  cb = NULL removes the hook.  Used by qblas_b200/dist.py. */
+typedef void (*qb_pass_cb)(int64_t row0, int64_t rows, void *user);
+void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes);
 /* Accuracy setting of the tensor path.  keep = 0: every digit-plane product is computed, the inner
  * products are EXACT and rounded once.  keep = d > 0 (default 17): only the d most significant
  * diagonals are multiplied; every element is checked (|J| >= 2^125, csrc/qb_ozaki.cu) and the few that

@@ -8,6 +8,9 @@ is missing the import of any compute entry point raises.
 import ctypes as C
 import os
 
+# void (*qb_pass_cb)(int64_t row0, int64_t rows, void *user)  (include/qblas_b200.h)
+PASS_CB = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_void_p)
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqblas_b200.so")
 
@@ -61,6 +64,7 @@ def lib():
         "qb_set_tensor_path": (None, [ci]),
         "qb_get_tensor_path": (ci, []),
         "qb_set_tensor_keep": (None, [ci]),
+        "qb_set_gemm_pass_callback": (None, [PASS_CB, vp, ci]),
         "qb_get_tensor_keep": (ci, []),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),

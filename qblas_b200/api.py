@@ -235,6 +235,23 @@ def get_tensor_path():
     return lib().qb_get_tensor_path()
 
 
+_pass_cb_ref = None
+
+
+def set_gemm_pass_callback(fn, min_passes=1):
+    """Row-pass hook of the device qgemm (qb_set_gemm_pass_callback): fn(row0, rows) is called after the work of each row pass has been
+    enqueued; fn = None removes it.  The ctypes thunk is kept alive here."""
+    global _pass_cb_ref
+    from ._lib import PASS_CB
+    if fn is None:
+        lib().qb_set_gemm_pass_callback(C.cast(None, PASS_CB), None, 1)
+        _pass_cb_ref = None
+        return
+    thunk = PASS_CB(lambda r0, rows, user: fn(int(r0), int(rows)))
+    lib().qb_set_gemm_pass_callback(thunk, None, int(min_passes))
+    _pass_cb_ref = thunk
+
+
 def set_tensor_keep(keep):
     """Tensor-path accuracy: 0 = all diagonals (exact inner products), d > 0 = the d leading diagonals + per-element check and fix-up."""
     lib().qb_set_tensor_keep(int(keep))

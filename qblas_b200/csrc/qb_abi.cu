@@ -32,6 +32,10 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_mode{QB_MODE_REFERENCE};
 static std::atomic<int> g_kc{126};
 static std::atomic<int> g_honor_trans{0};
+/* row-pass hook of the device qgemm (qb_set_gemm_pass_callback); used under the library mutex */
+static qb_pass_cb g_pass_cb = nullptr;
+static void *g_pass_user = nullptr;
+static int g_pass_min = 1;
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
 int fast_variant() { return g_fastvar.load(); }
@@ -157,12 +161,13 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
     cudaMemGetInfo(&fr, &tot);
     const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
     int used = 0;
-    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget);
+    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget, (oz_pass_cb)g_pass_cb, g_pass_user, g_pass_min);
     if (oe != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm tensor path", oe);
     if (used) return QB_OK;
   }
   cudaError_t e = launch_gemm(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm kernel launch", e);
+  if (g_pass_cb && m > 0) g_pass_cb(0, m, g_pass_user);   /* the integer-limb kernel produces all rows in one launch */
   return QB_OK;
 }
 
@@ -195,6 +200,11 @@ void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
 void qb_set_fast_variant(int v) { g_fastvar.store(v ? 1 : 0); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
+void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  g_pass_cb = cb; g_pass_user = user; g_pass_min = min_passes < 1 ? 1 : min_passes;
+}
 void qb_set_tensor_keep(int keep)
 {
   std::lock_guard<std::recursive_mutex> lk(g_s.mu);

@@ -54,7 +54,12 @@ int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 
 #define QB_OZ_MAX_SLICES 24
 struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; };
 /* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget);
+/* row-pass hook: when set, the C rows are produced in at least `min_passes` passes and cb(row0, rows, user) is called on the
+ * host after the work of each pass has been ENQUEUED on the stream (so a collective issued from the callback overlaps the
+ * next pass) */
+typedef void (*oz_pass_cb)(int64_t row0, int64_t rows, void *user);
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb = nullptr, void *cb_user = nullptr,
+                              int min_passes = 1);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);
 OzStats oz_last_stats();

@@ -685,7 +685,7 @@ static void launch_oz_slice(const q128 *X, int64_t rows, int64_t K, int64_t sr, 
 static inline int64_t oz_list_cap(int64_t mb, int64_t n) { return std::max<int64_t>(1024, std::min<int64_t>((mb * n) / 64, (int64_t)1 << 22)); }
 
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget)
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes)
 {
   *used = 0;
   g_ev_used = 0;
@@ -749,9 +749,11 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     if (bounded) b += (size_t)rup(Mp * Np, 1024) + (size_t)oz_list_cap(mb, n) * sizeof(int2);
     return b;
   };
-  const bool multi = nchunks > 1 && pb_b + pass_bytes_v(m, true) <= ws_budget;
+  const int64_t mb_hint = (cb && min_passes > 1) ? std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM)) : m;
+  const bool multi = nchunks > 1 && pb_b + pass_bytes_v(mb_hint, true) <= ws_budget;
   auto pass_bytes = [&](int64_t mb) -> size_t { return pass_bytes_v(mb, multi); };
   int64_t mb = m;
+  if (cb && min_passes > 1) mb = std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM));
   while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
   if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess; /* does not fit: decline */
   e = oz_reserve(meta_ints * 4, pb_b + pass_bytes(mb));
@@ -812,6 +814,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     if (!bounded) {
       e = sweep(ndiag, false, false);
       if (e != cudaSuccess) return e;
+      if (cb) cb(r0, mr, cb_user);
       continue;
     }
     cudaMemsetAsync(counter, 0, 4, st);
@@ -823,7 +826,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     if (e != cudaSuccess) return e;
     const int nflag = g_oz.h_plan[8];
     flagged_total += nflag;
-    if (nflag == 0) continue;
+    if (nflag == 0) { if (cb) cb(r0, mr, cb_user); continue; }
     if (nflag <= list_cap) {
       OzFixArgs x;
       x.list = list; x.counter = counter; x.list_cap = list_cap;
@@ -839,6 +842,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
       e = sweep(ndiag, false, true);
       if (e != cudaSuccess) return e;
     }
+    if (cb) cb(r0, mr, cb_user);
   }
   g_last_stats.SA = SA; g_last_stats.SB = SB; g_last_stats.ndiag = ndiag; g_last_stats.nchunks = nchunks;
   g_last_stats.row_passes = (int)((m + mb - 1) / mb);

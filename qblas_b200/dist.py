@@ -39,9 +39,18 @@ def _bytes(t: torch.Tensor) -> torch.Tensor:
 class _CudaEngine:
     """Default per-rank engine: libqblas_b200.so on the current CUDA device."""
 
-    def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, on_rows=None, min_passes=1):
+        """on_rows(row0, rows): called after the work producing C rows [row0, row0 + rows) has been enqueued on the current stream
+        (every row exactly once); with min_passes > 1 the tensor path produces the rows in that many passes."""
         from . import api
-        api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+        if on_rows is None:
+            api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+            return
+        api.set_gemm_pass_callback(on_rows, min_passes)
+        try:
+            api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
+        finally:
+            api.set_gemm_pass_callback(None)
 
     def gemv(self, m, n, alpha, A, lda, x, beta, y):
         from . import api
@@ -60,15 +69,32 @@ class _CudaEngine:
         api.fold_partials(count, partials, out, do_sqrt)
 
 
-def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None):
+def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1):
     """C_full (m x n, row-major, identical buffer shape on every rank) <- alpha*A*B + beta*C.
     A_blk holds this rank's rows [lo, hi) of A (row-major, lda = k); B (k x n) is valid on `src`
-    and is overwritten by the broadcast elsewhere.  Returns (lo, hi)."""
+    and is overwritten by the broadcast elsewhere.  Returns (lo, hi).
+
+    overlap_passes > 1 (even split only): the local block is produced in that many row passes and the all-gather of each
+    pass's rows is issued from the library's row-pass hook as soon as that pass is enqueued, so it runs on NCCL's stream
+    while the next pass computes; only the last pass's gather is exposed.  Same bytes, same result."""
     compute = compute or _CudaEngine()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = row_block(m, world, rank)
     dist.broadcast(_bytes(B), src=src, group=group)
     C_blk = C_full[lo * n:hi * n]
+    if m % world == 0 and overlap_passes > 1 and hi > lo:
+        m_loc = hi - lo
+        works = []
+
+        def on_rows(r0, rows):
+            # rows [r0, r0 + rows) of EVERY rank's block: rank q's copy lands at rows q * m_loc + r0 of C_full
+            outs = [_bytes(C_full[(q * m_loc + r0) * n:(q * m_loc + r0 + rows) * n]) for q in range(world)]
+            works.append(dist.all_gather(outs, _bytes(C_blk[r0 * n:(r0 + rows) * n]), group=group, async_op=True))
+
+        compute.gemm(m_loc, n, k, alpha, A_blk, k, B, n, beta, C_blk, n, on_rows=on_rows, min_passes=overlap_passes)
+        for w in works:
+            w.wait()
+        return lo, hi
     if hi > lo:
         compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
     if m % world == 0:

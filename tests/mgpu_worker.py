@@ -38,6 +38,13 @@ def main():
         torch.cuda.synchronize()
         if not (to_host(Cf) == to_host(one)).all():
             fails.append(("gemm vs 1-GPU", mode, m, n, k))
+        if m % world == 0:   # all-gather issued pass by pass from the library's row-pass hook: same bits
+            Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+            Cf = to_dev(C0.copy())
+            qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cf, overlap_passes=3)
+            torch.cuda.synchronize()
+            if not (to_host(Cf) == to_host(one)).all():
+                fails.append(("gemm overlapped vs 1-GPU", mode, m, n, k))
         if mode == qb.MODE_REFERENCE:
             want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
             if not quad.same_bits(to_host(Cf), want).all():

@@ -25,8 +25,12 @@ class OracleEngine:
     def _np(t):
         return t.numpy().view(np.uint64)
 
-    def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc):
+    def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, on_rows=None, min_passes=1):
         self.o.gemm("R", m, n, k, alpha, self._np(A), lda, self._np(B), ldb, beta, self._np(C), ldc)
+        if on_rows is not None:   # the library's row-pass hook: every row reported exactly once, in passes
+            step = -(-m // max(1, min_passes))
+            for r0 in range(0, m, step):
+                on_rows(r0, min(step, m - r0))
 
     def gemv(self, m, n, alpha, A, lda, x, beta, y):
         self.o.gemv("R", m, n, alpha, self._np(A), lda, self._np(x), 1, beta, self._np(y), 1)
@@ -78,6 +82,11 @@ def _worker(rank, world, port, q):
             Cf = t(C0.copy())
             qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cf, compute=eng)
             assert (Cf.numpy().view(np.uint64) == want).all(), ("gemm", m, n, k, rank)
+            # same call with the all-gather issued pass by pass from the row-pass hook (even splits only; ragged falls back)
+            Bt = t(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64)
+            Cf = t(C0.copy())
+            qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cf, compute=eng, overlap_passes=2)
+            assert (Cf.numpy().view(np.uint64) == want).all(), ("gemm overlapped", m, n, k, rank)
         # ---- qgemv
         m, n = 9, 33
         A = quad.random_quads(rng, m * n); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)
