@@ -334,6 +334,24 @@ QB_HD uint32_t umulhi32(uint32_t a, uint32_t b)
  * i.e. the same formula; the two terms never overlap, so + is |. */
 QB_HD uint32_t mfunnel(uint32_t lo_limb, uint32_t hi_limb, uint32_t M) { return hi_limb * M + umulhi32(lo_limb, M); }
 
+/* The same shifts and the conditional complement on the ALU (SHF / LOP3).  tools/exp/mb_pipes.cu measured, per SM
+ * sub-partition on sm_100a: IMAD 2 clk, IMAD.HI 4 clk, SHF / LOP3 2 clk, with little overlap between the pipes - so one
+ * SHF (2 clk) beats the IMAD.HI + IMAD pair (6 clk) that mfunnel costs.  QB_CHAIN_SHIFT_ON_ALU selects it. */
+#ifndef QB_CHAIN_SHIFT_ON_ALU
+#define QB_CHAIN_SHIFT_ON_ALU 1
+#endif
+/* low word of (hi:lo) >> r, r in [1, 32] */
+QB_HD uint32_t afunnel_r(uint32_t lo_limb, uint32_t hi_limb, uint32_t r)
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo_limb, hi_limb, r);
+#else
+  return r >= 32 ? hi_limb : (uint32_t)((((uint64_t)hi_limb << 32) | lo_limb) >> r);
+#endif
+}
+/* high word of (hi:lo) << q, q in [0, 31] */
+QB_HD uint32_t afunnel_l(uint32_t lo_limb, uint32_t hi_limb, uint32_t q) { return fshl(lo_limb, hi_limb, q); }
+
 /* number of trailing zero bits of a 113-bit mantissa (normal operands have m3 bit 16 set) */
 QB_HD uint32_t qop_tz(const qop &o)
 {
@@ -417,18 +435,32 @@ QB_HD void qacc_fma_t(qacc &S, const qop &A, const qop &B, const qscratch &scr, 
     jam = (lost != 0) ? 1u : 0u;
   }
   /* ---- bit part: (t >> r) on the multiplier ---- */
+#if QB_CHAIN_SHIFT_ON_ALU
+  const uint32_t rr = (shm1 & 31u) + 1u;
+  const uint32_t f0 = afunnel_r(t0, t1, rr) | jam, f1 = afunnel_r(t1, t2, rr), f2 = afunnel_r(t2, t3, rr), f3 = afunnel_r(t3, t4, rr),
+                 f4 = afunnel_r(t4, t5, rr);
+#else
   const uint32_t f0 = mfunnel(t0, t1, M) | jam, f1 = mfunnel(t1, t2, M), f2 = mfunnel(t2, t3, M), f3 = mfunnel(t3, t4, M),
                  f4 = mfunnel(t4, t5, M);
+#endif
 
   /* ---- S +- P with end-around carry (one's complement subtract) ---- */
   const uint32_t sub = ss ^ sp;                 /* 0/1 */
-  const cnot_coef mk = cnot_make(sub);
   uint32_t g0, g1, g2, g3, g4;
+#if QB_CHAIN_SHIFT_ON_ALU
+  const uint32_t mk = 0u - sub;
+  const uint32_t cout = add5(S.m0, S.m1, S.m2, S.m3, f0 ^ mk, f1 ^ mk, f2 ^ mk, f3 ^ mk, f4 ^ mk, g0, g1, g2, g3, g4);
+  const uint32_t neg = sub & (cout ^ 1u);       /* |P| > |S| : magnitude = ~T, sign flips */
+  const uint32_t nm = 0u - neg;
+  g0 ^= nm; g1 ^= nm; g2 ^= nm; g3 ^= nm; g4 ^= nm;
+#else
+  const cnot_coef mk = cnot_make(sub);
   const uint32_t cout = add5(S.m0, S.m1, S.m2, S.m3, cnot(f0, mk), cnot(f1, mk), cnot(f2, mk), cnot(f3, mk), cnot(f4, mk),
                              g0, g1, g2, g3, g4);
   const uint32_t neg = sub & (cout ^ 1u);       /* |P| > |S| : magnitude = ~T, sign flips */
   const cnot_coef nm = cnot_make(neg);
   g0 = cnot(g0, nm); g1 = cnot(g1, nm); g2 = cnot(g2, nm); g3 = cnot(g3, nm); g4 = cnot(g4, nm);
+#endif
   inc5(g0, g1, g2, g3, g4, sub & cout);
   const uint32_t sr = ss ^ neg;                 /* sign flips iff the magnitudes swapped (then sp == ss ^ 1) */
 
@@ -438,11 +470,17 @@ QB_HD void qacc_fma_t(qacc &S, const qop &A, const qop &B, const qscratch &scr, 
   const int lz = (g4 != 0) ? lz4 : 32 + clz32(g3);
   bad = bad || (lz > 45);                       /* > 13 bits of cancellation (or exact zero) */
   const uint32_t q1 = (uint32_t)(lz > 31 ? 31 : lz) & 31u, q2 = (uint32_t)(lz > 31 ? lz - 31 : 0) & 31u;
+#if QB_CHAIN_SHIFT_ON_ALU
+  const uint32_t h0 = g0 << q1, h1 = afunnel_l(g0, g1, q1), h2 = afunnel_l(g1, g2, q1), h3 = afunnel_l(g2, g3, q1), h4 = afunnel_l(g3, g4, q1);
+  const uint32_t rest = h0 << q2;
+  uint32_t n0 = afunnel_l(h0, h1, q2), n1 = afunnel_l(h1, h2, q2), n2 = afunnel_l(h2, h3, q2), n3 = afunnel_l(h3, h4, q2);
+#else
   const uint32_t M1 = opaque(1u << q1), M2 = opaque(1u << q2);
   const uint32_t h0 = g0 * M1, h1 = mfunnel(g0, g1, M1), h2 = mfunnel(g1, g2, M1), h3 = mfunnel(g2, g3, M1),
                  h4 = mfunnel(g3, g4, M1);
   const uint32_t rest = h0 * M2;
   uint32_t n0 = mfunnel(h0, h1, M2), n1 = mfunnel(h1, h2, M2), n2 = mfunnel(h2, h3, M2), n3 = mfunnel(h3, h4, M2);
+#endif
   int32_t en = es + 32 - lz;
 
   /* ---- round to nearest even at bit 15 of n0 ---- */
