@@ -397,11 +397,11 @@ def own_arm(args, rank, world, local_rank):
             bf16_sus = float(peaks.get("bf16_tflops_sustained", 1400.0)); bf16_burst = float(peaks.get("bf16_tflops", 1590.0))
             peak = 2.0 * bf16_sus
             # DRAM traffic per launch of k_oz_mma from the committed ncu --set full capture of THIS configuration
-            # (profiles/r1f_oz_mma_8192_ncu_full.txt: dram__bytes_read.sum 43.88 GB + dram__bytes_write.sum 4.52 GB); null for any other plan
-            profiled = (m_loc, n, plan["Kp"], plan["SA"], plan["SB"], plan["keep"], plan["nchunks"]) == (8192, 8192, 8192, 18, 18, 17, 2)
+            # (profiles/r1g_oz_mma_8192_ncu_full.txt: dram__bytes_read.sum 38.95 GB + dram__bytes_write.sum 4.25 GB); null for any other plan
+            profiled = (m_loc, n, plan["Kp"], plan["SA"], plan["SB"], plan["keep"], plan["nchunks"]) == (8192, 8192, 8192, 18, 18, 16, 2)
             roof = {"bound": "tensor", "kernel": "k_oz_mma (tcgen05.mma kind::i8, TMA-fed, TMEM accumulators)", "achieved": tops, "peak": peak,
-                    "unit": "TFLOP/s", "frac": tops / peak, "traffic": 48.39e9 if profiled else None,
-                    "traffic_note": "bytes per launch (2 launches per qgemm); algorithmic operand + result bytes per launch = 1.2 GB of digit planes + 4.56 GB of int32 diagonals: the planes are re-read once per diagonal pair through L2 (1.7 TB/s = 26% of HBM while the tensor pipe is 85% active - not the bound)" if profiled else None,
+                    "unit": "TFLOP/s", "frac": tops / peak, "traffic": 43.2e9 if profiled else None,
+                    "traffic_note": "bytes per launch (2 launches per qgemm); algorithmic operand + result bytes per launch = 1.2 GB of digit planes + 4.3 GB of int32 diagonals: the planes are re-read once per digit-plane pair through L2 (1.5 TB/s = 23% of HBM while the tensor pipe is 85% active - not the bound)" if profiled else None,
                     "peak_source": f"2 x MEASURED_PEAKS.json bf16_tflops_sustained ({bf16_sus}; burst {bf16_burst}) [{src}]: int8 dense issues at twice the bf16 rate on sm_100a, "
                                    "no int8 figure is driver-measured; sustained because the kernel runs inside a long back-to-back step",
                     "algorithmic": f"one binary128 flop = {plan['pairs']} int8 ops ({plan['SA']}x{plan['SB']} signed-digit slices, {plan['keep']} of {plan['ndiag']} diagonals multiplied): "
@@ -495,7 +495,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary qgemv/qdot/reference-order figures")
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
     ap.add_argument("--overlap", type=int, default=4, help="N > 1: row passes whose all-gathers overlap the next pass (1 = one all-gather after the qgemm)")
-    ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 17)")
+    ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 16)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -105,7 +105,7 @@ int qb_get_fast_variant(void);
 typedef void (*qb_pass_cb)(int64_t row0, int64_t rows, void *user);
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes);
 /* Accuracy setting of the tensor path.  keep = 0: every digit-plane product is computed, the inner
- * products are EXACT and rounded once.  keep = d > 0 (default 17): only the d most significant
+ * products are EXACT and rounded once.  keep = d > 0 (default 16): only the d most significant
  * diagonals are multiplied; every element is checked (|J| >= 2^125, csrc/qb_ozaki.cu) and the few that
  * fail are recomputed in the window accumulator, so the result always satisfies the fast-mode
  * contract |c^ - c| <= gamma_k (|A||B|)_ij, but it is no longer the exact sum rounded once. */
