@@ -257,6 +257,8 @@ def own_arm(args, rank, world, local_rank):
     qb.set_mode(mode)
     if args.keep is not None:
         qb.set_tensor_keep(args.keep)
+    if args.scheme is not None:
+        qb.set_tensor_scheme(1 if args.scheme == "residues" else 0)
     S = args.size
     m_loc, n, k = S, S, S
     M = S * world
@@ -375,13 +377,13 @@ def own_arm(args, rank, world, local_rank):
         u = Fraction(1, 2 ** 113); gam = k * u / (1 - k * u)
         f = lambda v: quad.to_fraction(int(v[1]), int(v[0]))
         for q in range(ns):
-            if plan and plan["pairs"] > 0 and plan["keep"] >= plan["ndiag"]:   # all diagonals: the exact inner product rounded once
+            if _plan_exact(plan):   # residue scheme / all diagonals: the exact inner product rounded once
                 s_ex = exact_matmul_rounded(Ah[q * k:(q + 1) * k], k, np.ascontiguousarray(Bh[q::ns][:k]), 1, 1, 1, k)
                 if not quad.same_bits(got[q:q + 1], s_ex).all():
                     mism += 1
             if abs(f(got[q]) - f(exp_ref[q])) > 2 * gam * f(ab[q]):   # and always inside the fast-mode contract vs the reference order
                 mism += 1
-        against = ("exact big-integer inner product rounded once (bit exact) AND " if plan and plan["keep"] >= plan["ndiag"] else "") + \
+        against = ("exact big-integer inner product rounded once (bit exact) AND " if _plan_exact(plan) else "") + \
             "gamma_k(|A||B|) bound vs the reference-order oracle"
     del Ah, Bh
 
@@ -398,13 +400,20 @@ def own_arm(args, rank, world, local_rank):
             peak = 2.0 * bf16_sus
             # DRAM traffic per launch of k_oz_mma from the committed ncu --set full capture of THIS configuration
             # (profiles/r1g_oz_mma_8192_ncu_full.txt: dram__bytes_read.sum 38.95 GB + dram__bytes_write.sum 4.25 GB); null for any other plan
-            profiled = (m_loc, n, plan["Kp"], plan["SA"], plan["SB"], plan["keep"], plan["nchunks"]) == (8192, 8192, 8192, 18, 18, 16, 2)
+            residues = plan.get("scheme") == "residues"
+            profiled = (not residues) and (m_loc, n, plan["Kp"], plan["SA"], plan["SB"], plan["keep"], plan["nchunks"]) == (8192, 8192, 8192, 18, 18, 16, 2)
+            if residues:
+                alg = (f"one binary128 flop = {plan['pairs']} int8 ops: row/column block fixed point (W_A = {plan['WA']}, W_B = {plan['WB']} bits), "
+                       f"one int8 GEMM per modulus, {plan['pairs']} pairwise coprime moduli <= 256 (product > 2 k 2^(W_A+W_B)), exact CRT reconstruction")
+            else:
+                alg = (f"one binary128 flop = {plan['pairs']} int8 ops ({plan['SA']}x{plan['SB']} signed-digit slices, {plan['keep']} of {plan['ndiag']} "
+                       "diagonals multiplied)")
             roof = {"bound": "tensor", "kernel": "k_oz_mma (tcgen05.mma kind::i8, TMA-fed, TMEM accumulators)", "achieved": tops, "peak": peak,
                     "unit": "TFLOP/s", "frac": tops / peak, "traffic": 43.2e9 if profiled else None,
                     "traffic_note": "bytes per launch (2 launches per qgemm); algorithmic operand + result bytes per launch = 1.2 GB of digit planes + 4.3 GB of int32 diagonals: the planes are re-read once per digit-plane pair through L2 (1.5 TB/s = 23% of HBM while the tensor pipe is 85% active - not the bound)" if profiled else None,
                     "peak_source": f"2 x MEASURED_PEAKS.json bf16_tflops_sustained ({bf16_sus}; burst {bf16_burst}) [{src}]: int8 dense issues at twice the bf16 rate on sm_100a, "
                                    "no int8 figure is driver-measured; sustained because the kernel runs inside a long back-to-back step",
-                    "algorithmic": f"one binary128 flop = {plan['pairs']} int8 ops ({plan['SA']}x{plan['SB']} signed-digit slices, {plan['keep']} of {plan['ndiag']} diagonals multiplied): "
+                    "algorithmic": f"{alg}: "
                                    f"{plan['pairs']} x 2*m*n*Kp = {int8_ops:.4g} int8 ops per qgemm in {mma_launches} launch(es) of k_oz_mma, "
                                    f"{mma_ms:.2f} ms summed (CUDA events on the launching stream, last timed step); whole qgemm call {call_ms:.2f} ms",
                     "kernel_ms": mma_ms, "kernel_share_of_step": mma_ms / call_ms, "plan": plan,
@@ -447,6 +456,19 @@ def own_arm(args, rank, world, local_rank):
                 call_ms, extra, strong)
 
 
+def _plan_exact(plan):
+    return bool(plan) and plan["pairs"] > 0 and (plan.get("scheme") == "residues" or plan["keep"] >= plan["ndiag"])
+
+
+def _mode_text(plan):
+    if plan and plan.get("scheme") == "residues":
+        return (f"fast: exact int8 residue planes on tcgen05 ({plan['pairs']} moduli, one GEMM each) + Chinese-remainder reconstruction: "
+                "inner products exact, rounded once")
+    return "fast: Ozaki-style exact int8 slicing on tcgen05; " + (
+        f"{plan['keep']} leading diagonals + per-element check/fix-up ({plan['flagged']} entries fixed, {plan['redo_passes']} passes redone): inside the gamma_k bound"
+        if plan and plan["keep"] < plan["ndiag"] else "all diagonals: inner products exact, rounded once")
+
+
 def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_step, M, n, k, m_loc, e2e, launches, clk, roof, cpu, ns, mism, against,
                 call_ms, extra, strong):
     mism_t = torch.tensor([mism], dtype=torch.int64, device=dev)
@@ -464,15 +486,15 @@ def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_s
         line = {
             "metric": "binary128 qgemm GFLOPS", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "binary128 (exact signed 8-bit slices on the int8 tensor cores, wide-integer recombination, one rounding)" if fast
+            "dtype": ("binary128 (exact int8 residues on the tensor cores, Chinese-remainder recombination, one rounding)" if plan and plan.get("scheme") == "residues"
+                      else "binary128 (exact signed 8-bit slices on the int8 tensor cores, wide-integer recombination, one rounding)") if fast
                      else "binary128 (software, u32 integer limbs)",
             "data": "synthetic",
             "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' + (f', all-gather issued per row pass ({args.overlap} passes) from the row-pass hook' if args.overlap > 1 else '') if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
-                       "mode": ("fast: Ozaki-style exact int8 slicing on tcgen05; " + (f"{plan['keep']} leading diagonals + per-element check/fix-up ({plan['flagged']} entries fixed, {plan['redo_passes']} passes redone): inside the gamma_k bound"
-                                if plan and plan["keep"] < plan["ndiag"] else "all diagonals: inner products exact, rounded once")) if fast
+                       "mode": _mode_text(plan) if fast
                                else "reference-order (bit exact, kc=126), integer-limb kernel",
                        "inputs": f"{args.dist}: full 113-bit random mantissas, device resident" if args.dist != "D53" else "D53: doubles U(-1,1) cast to quad (the reference's own benchmark distribution)",
-                       "l2": "inputs (3 x 1 GiB) and digit planes (2.4 GB) exceed the 126 MB L2; no flush needed", "parallelism": f"row-block x{world}"},
+                       "l2": "inputs (3 x 1 GiB at 8192^3) and the int8 planes (GBs) exceed the 126 MB L2; no flush needed", "parallelism": f"row-block x{world}"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "parity": {"checked_entries": ns * world, "mismatches": int(mism_t.item()), "against": against},
             "call_ms": call_ms, "extra": extra,
@@ -495,6 +517,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary qgemv/qdot/reference-order figures")
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
     ap.add_argument("--overlap", type=int, default=4, help="N > 1: row passes whose all-gathers overlap the next pass (1 = one all-gather after the qgemm)")
+    ap.add_argument("--scheme", default=None, choices=["residues", "digits"], help="tensor path: residue planes + CRT (library default) or digit diagonals")
     ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 16)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

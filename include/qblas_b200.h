@@ -111,9 +111,19 @@ void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes);
  * contract |c^ - c| <= gamma_k (|A||B|)_ij, but it is no longer the exact sum rounded once. */
 void qb_set_tensor_keep(int keep);
 int qb_get_tensor_keep(void);
+/* How the tensor path forms the exact integer inner products.  1 (default) = residue scheme
+ * (csrc/qb_crt.cuh): the block-fixed-point integers are reduced modulo N pairwise coprime moduli <= 256,
+ * ONE int8 GEMM per modulus, exact Chinese-remainder reconstruction, one rounding - always exact, so
+ * qb_set_tensor_keep does not apply; N = 41 for full 113-bit mantissas at k = 8192 (vs 324 / 136 digit-plane
+ * products).  0 = digit diagonals (csrc/qb_ozaki.cu).  The residue scheme hands over to the digit
+ * diagonals when its moduli cannot cover the operands' bit span (W_A + W_B + log2 k + 1 > 341) or k > 65536. */
+void qb_set_tensor_scheme(int scheme);
+int qb_get_tensor_scheme(void);
 /* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, digit-plane products
  * per row pass, workspace bytes, padded K, diagonals kept, elements sent to the fix-up, row passes
- * redone with all diagonals, 0} */
+ * redone with all diagonals, residue-scheme word}.  Residue scheme: S_A / S_B = bytes of the widest row /
+ * column integer, "diagonals" = "products" = N moduli, last word = 1 | W_A << 8 | W_B << 24 (bit spans);
+ * digit diagonals: last word = 0. */
 void qb_oz_last_stats(int64_t *out12);
 /* Summed device time (ms, CUDA events on the launching stream) of the tcgen05 kernel launches of
  * the last tensor-path qgemm; waits for them to finish.  *launches (optional) = how many. */

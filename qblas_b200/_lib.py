@@ -66,6 +66,8 @@ def lib():
         "qb_set_tensor_keep": (None, [ci]),
         "qb_set_gemm_pass_callback": (None, [PASS_CB, vp, ci]),
         "qb_get_tensor_keep": (ci, []),
+        "qb_set_tensor_scheme": (None, [ci]),
+        "qb_get_tensor_scheme": (ci, []),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),

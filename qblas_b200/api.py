@@ -261,6 +261,15 @@ def get_tensor_keep():
     return lib().qb_get_tensor_keep()
 
 
+def set_tensor_scheme(scheme):
+    """Tensor-path scheme: 1 = residue planes + Chinese-remainder reconstruction (default), 0 = digit diagonals."""
+    lib().qb_set_tensor_scheme(int(scheme))
+
+
+def get_tensor_scheme():
+    return lib().qb_get_tensor_scheme()
+
+
 def set_fast_variant(v):
     """Fast-mode accumulate of dot/nrm2/gemv: 1 = window accumulator (csrc/qwide.cuh), 0 = rounded-FMA chains."""
     lib().qb_set_fast_variant(int(v))
@@ -275,7 +284,12 @@ def oz_last_stats():
     out = (C.c_int64 * 12)()
     lib().qb_oz_last_stats(out)
     keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes", "Kp", "keep", "flagged", "redo_passes"]
-    return {k: int(out[i]) for i, k in enumerate(keys)}
+    d = {k: int(out[i]) for i, k in enumerate(keys)}
+    w = int(out[11])
+    d["scheme"] = "residues" if w & 1 else "digits"
+    if w & 1:
+        d["WA"] = (w >> 8) & 0xffff; d["WB"] = (w >> 24) & 0xffff; d["moduli"] = d["pairs"]
+    return d
 
 
 def oz_last_mma_ms():

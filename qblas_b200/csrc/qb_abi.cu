@@ -211,11 +211,18 @@ void qb_set_tensor_keep(int keep)
   oz_set_keep(keep);
 }
 int qb_get_tensor_keep(void) { return oz_get_keep(); }
+void qb_set_tensor_scheme(int scheme)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  oz_set_scheme(scheme);
+}
+int qb_get_tensor_scheme(void) { return oz_get_scheme(); }
 void qb_oz_last_stats(int64_t *out12)
 {
   const OzStats s = oz_last_stats();
   out12[0] = s.SA; out12[1] = s.SB; out12[2] = s.ndiag; out12[3] = s.nchunks; out12[4] = s.row_passes; out12[5] = s.pairs; out12[6] = s.ws_bytes;
-  out12[7] = s.Kp; out12[8] = s.keep; out12[9] = s.flagged; out12[10] = s.redo_passes; out12[11] = 0;
+  out12[7] = s.Kp; out12[8] = s.keep; out12[9] = s.flagged; out12[10] = s.redo_passes;
+  out12[11] = s.scheme ? (int64_t)1 | ((int64_t)s.WA << 8) | ((int64_t)s.WB << 24) : 0;
 }
 double qb_oz_last_mma_ms(int *launches)
 {

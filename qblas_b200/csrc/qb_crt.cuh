@@ -1,0 +1,294 @@
+/*
+ * qb_crt.cuh — residue (Chinese-remainder) arithmetic of the fast-mode tensor-core qgemm.
+ *
+ * What it is for: QuadBLAS::gemm (/root/reference/include/quadblas/algorithms/level3.hpp:215-336) in
+ * QB_MODE_FAST.  Rows of op(A) and columns of op(B) are block fixed point, x = X * 2^(base - 16495)
+ * with exact integers |X| < 2^W (qb_ozaki.cu, scan/plan), so every inner product is an exact integer
+ *     I_ij = sum_l XA_il XB_lj,   |I| < k 2^(W_A + W_B).
+ * The digit-diagonal scheme of qb_ozaki.cu spends S_A*S_B (or the ~S^2/2 leading) int8 GEMMs on it.
+ * Here the integer is computed modulo N pairwise coprime moduli p_i <= 256 instead:
+ *     residues : a_i = XA mod p_i, b_i = XB mod p_i as symmetric int8 (one byte plane per modulus)
+ *     mma      : R_i = (a_i b_i^T) mod p_i         -- ONE int8 GEMM per modulus (N, not S_A*S_B)
+ *     fold     : I = CRT(R_0 .. R_{N-1}) in (-P/2, P/2), P = prod p_i > 2 k 2^(W_A+W_B), exact,
+ *                then one correctly rounded conversion to binary128.
+ * Full 113-bit mantissas with the exponent spread of U(-1,1) rows (W ~ 139) at k = 8192 need
+ * P > 2^292: 41 moduli, against 324 digit-plane products (all diagonals) or 136 (16 diagonals).
+ * (The modular formulation of exact int8 matrix products is the published "Ozaki scheme II" idea; the
+ * arithmetic below - dp4a residues, grouped two-level reconstruction - is this library's own.)
+ *
+ * Host/device dual source: nvcc compiles it into qb_ozaki.cu, g++ compiles the same functions in
+ * tests/host/crt_host.cpp for the CPU checks against Python integers (tests/test_host_crt.py).
+ */
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define QCRT_HD __host__ __device__ __forceinline__
+#else
+#define QCRT_HD static inline __attribute__((always_inline))
+#endif
+#if defined(__CUDA_ARCH__)
+#define QCRT_UNROLL _Pragma("unroll")
+#else
+#define QCRT_UNROLL
+#endif
+
+namespace qb {
+namespace crt {
+
+static constexpr int NM = 49;       /* pairwise coprime moduli <= 256, largest first (greedy) */
+static constexpr int NMP = 52;      /* padded to whole groups of 4 */
+static constexpr int NGMAX = 13;    /* groups of <= 4 moduli, product of a group < 2^32 */
+static constexpr int NLMAX = 14;    /* 32-bit limbs: NG + 1 */
+static constexpr int NWMAX = 6;     /* 32-bit words of |X| (W <= 192) */
+static constexpr int WMAX = 32 * NWMAX;
+
+static const int MODULI[NM] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193, 191,
+                               181, 179, 173, 167, 163, 157, 151, 149, 139, 137, 131, 127, 113, 109, 107, 103, 101,
+                               97,  89,  83,  79,  73,  71,  67,  61,  59,  53,  47,  43,  41,  37,  29};
+
+/* per-modulus constants, the same for every plan (device copy lives in __constant__ memory) */
+struct Tables {
+  uint32_t p[NMP];      /* modulus (padding entries: 1) */
+  uint32_t half[NMP];   /* (p-1)/2, 128 for p = 256: symmetric residues are r - half for r = (x + half) mod p */
+  uint32_t cneg[NMP];   /* p*ceil(2^21/p) + 2*half: v_neg = cneg - v_pos is == -x + half (mod p) and stays >= 0 */
+  uint32_t minv[NMP];   /* ceil(2^32/p): umulhi(v, minv) == floor(v/p) exactly for v < 2^22 */
+  uint32_t off[NMP];    /* p*ceil(2^30/p): makes an int32 accumulator (|v| <= 2^30) non-negative, == 0 mod p */
+  uint32_t finv[NMP];   /* floor(2^32/p): umulhi(u, finv) in {floor(u/p)-1, floor(u/p)} for u < 2^32 */
+  uint32_t pw[NWMAX][NMP]; /* byte b of pw[j][i] = 256^(4j+b) mod p_i  (dp4a against the words of |X|) */
+};
+
+/* per-N constants of the reconstruction (kernel parameter) */
+struct Plan {
+  int N, NG;
+  uint32_t G[NGMAX];          /* group moduli G_g = product of the group's p */
+  uint32_t flo[NGMAX], fhi[NGMAX]; /* f_g = floor(2^64 / G_g) */
+  uint32_t cp[NMP];           /* c'_j: t_g = (sum_{j in g} r_j c'_j) mod G_g is the top-level CRT digit, already
+                                 multiplied by (P/G_g)^-1 mod G_g */
+  uint32_t M[NGMAX][NLMAX];   /* M_g = P / G_g */
+  uint32_t P[NLMAX], hP[NLMAX]; /* P and floor(P/2) */
+  double bits;                /* log2(P) */
+};
+
+/* ------------------------------------------------------------------ portable primitives */
+QCRT_HD uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+  return __dp4a(a, b, c);
+#else
+  for (int i = 0; i < 4; ++i) c += ((a >> (8 * i)) & 255u) * ((b >> (8 * i)) & 255u);
+  return c;
+#endif
+}
+QCRT_HD uint32_t mulhi_u(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+QCRT_HD uint64_t mul64hi_u(uint64_t a, uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * b) >> 64);
+#endif
+}
+
+/* ------------------------------------------------------------------ residues */
+/* int8 residue (as the low byte) of (-1)^sign * X modulo p_i, X = sum_{j<NW} w[j] 2^(32 j); branch-free.
+ * acc <= half + 24*255*255 < 2^21; a negative X turns it into cneg - acc in (0, 2^22); floor division exact (Tables). */
+template <int NW>
+QCRT_HD uint32_t residue_byte(const uint32_t (&w)[NWMAX], uint32_t sign, int i, const Tables &T)
+{
+  uint32_t acc = T.half[i];
+QCRT_UNROLL
+  for (int j = 0; j < NW; ++j) acc = dp4a_u(w[j], T.pw[j][i], acc);
+  const uint32_t m = 0u - sign;                 /* all ones for a negative X */
+  acc = acc * (1u + 2u * m) + (T.cneg[i] & m);  /* sign ? cneg - acc : acc */
+  const uint32_t q = mulhi_u(acc, T.minv[i]);
+  const uint32_t r = acc - q * T.p[i];          /* (+-X + half) mod p in [0, p) */
+  return (r - T.half[i]) & 0xffu;               /* symmetric residue in [-half, p-1-half] as int8 */
+}
+
+/* what the tensor kernel's epilogue does with one int32 accumulator v (|v| <= 2^30): v mod p_i in [0, p) */
+QCRT_HD uint32_t acc_mod(int32_t v, int i, const Tables &T)
+{
+  const uint32_t u = (uint32_t)v + T.off[i];
+  uint32_t r = u - mulhi_u(u, T.finv[i]) * T.p[i];
+  if (r >= T.p[i]) r -= T.p[i];
+  return r;
+}
+
+/* ------------------------------------------------------------------ reconstruction */
+/* a > b, or a >= b when or_equal */
+template <int NL>
+QCRT_HD bool limbs_cmp(const uint32_t (&a)[NL], const uint32_t *b, bool or_equal)
+{
+  bool res = or_equal;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l)
+    if (a[l] != b[l]) res = a[l] > b[l];
+  return res;
+}
+
+/* r[j] in [0, p_j) for j < N (entries j >= N ignored)  ->  |I| as NG+1 limbs and its sign, where
+ * I == r_j (mod p_j) and |I| < P/2. */
+template <int NG>
+QCRT_HD void reconstruct(const uint32_t (&r)[NMP], const Plan &pl, uint32_t (&Y)[NG + 1], uint32_t &neg)
+{
+  constexpr int NL = NG + 1;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l) Y[l] = 0;
+  uint64_t s_lo = 0; uint32_t s_hi = 0;     /* S = sum t_g f_g  (96 bits); floor(S / 2^64) estimates floor(X / P) */
+QCRT_UNROLL
+  for (int g = 0; g < NG; ++g) {
+    uint64_t v = 0;
+QCRT_UNROLL
+    for (int b = 0; b < 4; ++b)
+      if (4 * g + b < pl.N) v += (uint64_t)r[4 * g + b] * pl.cp[4 * g + b];
+    const uint64_t f = ((uint64_t)pl.fhi[g] << 32) | pl.flo[g];
+    uint64_t t64 = v - mul64hi_u(v, f) * pl.G[g];
+    if (t64 >= pl.G[g]) t64 -= pl.G[g];
+    const uint32_t t = (uint32_t)t64;
+    /* X += t * M_g */
+    uint32_t carry = 0;
+QCRT_UNROLL
+    for (int l = 0; l < NL; ++l) {
+      const uint64_t a = (uint64_t)t * pl.M[g][l] + Y[l] + carry;
+      Y[l] = (uint32_t)a; carry = (uint32_t)(a >> 32);
+    }
+    /* S += t * f */
+    const uint64_t lo = (uint64_t)t * pl.flo[g], hi = (uint64_t)t * pl.fhi[g];
+    const uint64_t add_lo = lo + (hi << 32);
+    const uint32_t c0 = add_lo < lo ? 1u : 0u;
+    s_lo += add_lo;
+    s_hi += (uint32_t)(hi >> 32) + c0 + (s_lo < add_lo ? 1u : 0u);
+  }
+  /* Y = X - qhat P in [0, 2P): qhat underestimates floor(X/P) by at most 1 (sum of NG truncations < NG 2^32 << 2^64) */
+  {
+    const uint32_t qh = s_hi;
+    uint32_t carry = 0; uint32_t borrow = 0;
+QCRT_UNROLL
+    for (int l = 0; l < NL; ++l) {
+      const uint64_t m = (uint64_t)qh * pl.P[l] + carry;
+      carry = (uint32_t)(m >> 32);
+      const uint64_t d = (uint64_t)Y[l] - (uint32_t)m - borrow;
+      Y[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63);
+    }
+  }
+  if (limbs_cmp<NL>(Y, pl.P, true)) {
+    uint32_t borrow = 0;
+QCRT_UNROLL
+    for (int l = 0; l < NL; ++l) { const uint64_t d = (uint64_t)Y[l] - pl.P[l] - borrow; Y[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63); }
+  }
+  neg = limbs_cmp<NL>(Y, pl.hP, false) ? 1u : 0u;
+  if (neg) { /* |I| = P - Y */
+    uint32_t borrow = 0;
+QCRT_UNROLL
+    for (int l = 0; l < NL; ++l) { const uint64_t d = (uint64_t)pl.P[l] - Y[l] - borrow; Y[l] = (uint32_t)d; borrow = (uint32_t)(d >> 63); }
+  }
+}
+
+/* ------------------------------------------------------------------ host: tables and plans */
+namespace host {
+
+static inline int64_t inv_mod(int64_t a, int64_t m) /* a^-1 mod m, gcd = 1 */
+{
+  int64_t g = m, x = 0, y = 1, aa = ((a % m) + m) % m;
+  while (aa) { const int64_t q = g / aa; int64_t t = g - q * aa; g = aa; aa = t; t = x - q * y; x = y; y = t; }
+  return ((x % m) + m) % m;
+}
+
+static inline void build_tables(Tables &T)
+{
+  memset(&T, 0, sizeof(T));
+  for (int i = 0; i < NMP; ++i) {
+    const uint32_t p = i < NM ? (uint32_t)MODULI[i] : 1u;
+    T.p[i] = p;
+    T.half[i] = p == 256 ? 128u : (p - 1) / 2;
+    T.cneg[i] = p * (((1u << 21) + p - 1) / p) + 2 * T.half[i];
+    T.minv[i] = (uint32_t)((((uint64_t)1 << 32) + p - 1) / p);
+    T.off[i] = p * (((1u << 30) + p - 1) / p);
+    T.finv[i] = p == 1 ? 0xffffffffu : (uint32_t)(((uint64_t)1 << 32) / p);
+    uint32_t pw = 1 % p;
+    for (int j = 0; j < NWMAX; ++j) {
+      uint32_t word = 0;
+      for (int b = 0; b < 4; ++b) { word |= pw << (8 * b); pw = (pw * 256u) % p; }
+      T.pw[j][i] = i < NM ? word : 0u;
+    }
+  }
+}
+
+/* little-endian multi-limb helpers on fixed NLMAX + 1 limbs */
+struct Big { uint32_t w[NLMAX + 2]; };
+static inline Big big_one() { Big b; memset(&b, 0, sizeof(b)); b.w[0] = 1; return b; }
+static inline void big_mul_small(Big &a, uint32_t m)
+{
+  uint64_t c = 0;
+  for (int l = 0; l < NLMAX + 2; ++l) { const uint64_t t = (uint64_t)a.w[l] * m + c; a.w[l] = (uint32_t)t; c = t >> 32; }
+}
+static inline uint32_t big_div_small(Big &a, uint32_t d) /* a /= d, returns the remainder */
+{
+  uint64_t r = 0;
+  for (int l = NLMAX + 1; l >= 0; --l) { const uint64_t t = (r << 32) | a.w[l]; a.w[l] = (uint32_t)(t / d); r = t % d; }
+  return (uint32_t)r;
+}
+static inline uint32_t big_mod_small(const Big &a, uint32_t d) { Big t = a; return big_div_small(t, d); }
+static inline double big_log2(const Big &a)
+{
+  int top = NLMAX + 1;
+  while (top > 0 && !a.w[top]) --top;
+  double v = 0;
+  for (int l = top; l >= 0 && l > top - 3; --l) v = v * 4294967296.0 + a.w[l];
+  int sh = top >= 2 ? top - 2 : 0;
+  return __builtin_log2(v) + 32.0 * sh;
+}
+
+/* plan for the first N moduli (1 <= N <= NM) */
+static inline void build_plan(int N, Plan &pl)
+{
+  memset(&pl, 0, sizeof(pl));
+  pl.N = N; pl.NG = (N + 3) / 4;
+  Big P = big_one();
+  for (int i = 0; i < N; ++i) big_mul_small(P, (uint32_t)MODULI[i]);
+  for (int l = 0; l < NLMAX; ++l) pl.P[l] = P.w[l];
+  { Big h = P; big_div_small(h, 2); for (int l = 0; l < NLMAX; ++l) pl.hP[l] = h.w[l]; }
+  pl.bits = big_log2(P);
+  for (int g = 0; g < pl.NG; ++g) {
+    uint64_t G = 1;
+    for (int b = 0; b < 4 && 4 * g + b < N; ++b) G *= (uint64_t)MODULI[4 * g + b];
+    pl.G[g] = (uint32_t)G;
+    const unsigned __int128 two64 = (unsigned __int128)1 << 64;
+    const uint64_t f = G == 1 ? ~(uint64_t)0 : (uint64_t)(two64 / G);
+    pl.flo[g] = (uint32_t)f; pl.fhi[g] = (uint32_t)(f >> 32);
+    Big M = P;
+    big_div_small(M, (uint32_t)G);
+    for (int l = 0; l < NLMAX; ++l) pl.M[g][l] = M.w[l];
+    const uint64_t y = G == 1 ? 0 : (uint64_t)inv_mod((int64_t)big_mod_small(M, (uint32_t)G), (int64_t)G);
+    for (int b = 0; b < 4 && 4 * g + b < N; ++b) {
+      const uint64_t p = (uint64_t)MODULI[4 * g + b], Gp = G / p;
+      const uint64_t e = (uint64_t)(((unsigned __int128)Gp * (uint64_t)inv_mod((int64_t)(Gp % p), (int64_t)p)) % G); /* == 1 mod p, 0 mod the others */
+      pl.cp[4 * g + b] = (uint32_t)(((unsigned __int128)e * y) % G);
+    }
+  }
+}
+
+/* smallest N with prod_{i<N} p_i > 2^need_bits, 0 if even all NM moduli are not enough */
+static inline int moduli_for_bits(int need_bits)
+{
+  double bits = 0;
+  for (int i = 0; i < NM; ++i) {
+    bits += __builtin_log2((double)MODULI[i]);
+    if (bits > need_bits + 1e-6) return i + 1;
+  }
+  return 0;
+}
+
+} // namespace host
+
+} // namespace crt
+} // namespace qb

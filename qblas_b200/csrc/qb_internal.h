@@ -52,7 +52,7 @@ int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24
-struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; };
+struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; int scheme, WA, WB; };
 /* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
 /* row-pass hook: when set, the C rows are produced in at least `min_passes` passes and cb(row0, rows, user) is called on the
  * host after the work of each pass has been ENQUEUED on the stream (so a collective issued from the callback overlaps the
@@ -65,6 +65,8 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
 OzStats oz_last_stats();
 void oz_set_keep(int keep);   /* leading diagonals multiplied (bounded setting); 0 = all = exact inner products */
 int oz_get_keep();
+void oz_set_scheme(int v); /* 1 = residue planes + CRT (qb_crt.cuh, default), 0 = digit diagonals */
+int oz_get_scheme();
 double oz_last_mma_ms(int *launches);
 void oz_release();
 

@@ -42,6 +42,7 @@
 #include "qb_tc.cuh"
 #include "q128_chain.cuh"
 #include "qwide.cuh"
+#include "qb_crt.cuh"
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -71,7 +72,11 @@ struct OzMmaArgs {
   int m_tiles, n_tiles;
   int kb_begin, nkb;          /* k-blocks of OZ_BK for this K chunk */
   uint8_t order[OZ_MAX_DIAG + 1]; /* diagonals, heaviest first */
+  uint8_t *R;                 /* residue scheme: [N][Mp][Np] bytes, R_i = (A_i B_i^T) mod p_i in [0, p_i); ndiag = N */
 };
+
+/* per-modulus constants of the residue scheme (qb_crt.cuh); uploaded once per device by crt_upload_tables() */
+__constant__ crt::Tables c_crt;
 
 /* Tile order inside one diagonal: bands of OZ_GM m-tiles, n-tile outer / m-tile inner inside a band, so
  * that the ~148 tiles in flight form a compact 16 x 9 block of C: every A row panel is shared by ~9
@@ -88,6 +93,9 @@ __device__ __forceinline__ void oz_tile_decode(int rem, int m_tiles, int n_tiles
 }
 
 /* ------------------------------------------------------------------ the tensor-core kernel */
+/* CRT = 0: digit diagonals, D_d = sum_{s+t=d} A_s B_t^T as int32.  CRT = 1: residue planes, one product A_i B_i^T per
+ * modulus, reduced mod p_i in the epilogue and stored as bytes. */
+template <int CRT>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzMmaArgs g)
 {
@@ -123,13 +131,13 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int d = g.order[tile / tiles_per_diag];
+        const int d = CRT ? tile / tiles_per_diag : g.order[tile / tiles_per_diag];
         int mt, nt;
         oz_tile_decode(tile % tiles_per_diag, g.m_tiles, g.n_tiles, mt, nt);
-        const int s_lo = d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0;
-        const int s_hi = d < g.SA - 1 ? d : g.SA - 1;
+        const int s_lo = CRT ? d : (d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0);
+        const int s_hi = CRT ? d : (d < g.SA - 1 ? d : g.SA - 1);
         for (int s = s_lo; s <= s_hi; ++s) {
-          const int t = d - s;
+          const int t = CRT ? s : d - s;
           for (int kb = 0; kb < g.nkb; ++kb) {
             tc::mbar_wait(&empty[stage], phase ^ 1);
             uint8_t *sa = smem + stage * OZ_STAGE_BYTES;
@@ -149,9 +157,9 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       constexpr uint32_t idesc = tc::make_idesc_i8(OZ_BM, OZ_BN);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int d = g.order[tile / tiles_per_diag];
-        const int s_lo = d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0;
-        const int s_hi = d < g.SA - 1 ? d : g.SA - 1;
+        const int d = CRT ? tile / tiles_per_diag : g.order[tile / tiles_per_diag];
+        const int s_lo = CRT ? d : (d - (g.SB - 1) > 0 ? d - (g.SB - 1) : 0);
+        const int s_hi = CRT ? d : (d < g.SA - 1 ? d : g.SA - 1);
         const int iters = (s_hi - s_lo + 1) * g.nkb;
         tc::mbar_wait(&tempty[acc], acc_phase ^ 1); /* epilogue has drained this accumulator */
         tc::tc_fence_after();
@@ -178,14 +186,40 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int quarter = warp & 3;       /* TMEM lanes 32*quarter .. +31 are the ones this warp may read */
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int d = g.order[tile / tiles_per_diag];
+      const int d = CRT ? tile / tiles_per_diag : g.order[tile / tiles_per_diag];
       int mt, nt;
       oz_tile_decode(tile % tiles_per_diag, g.m_tiles, g.n_tiles, mt, nt);
       tc::mbar_wait(&tfull[acc], acc_phase);
       tc::tc_fence_after();
       const int64_t row = (int64_t)mt * OZ_BM + quarter * 32 + lane;
-      int32_t *dst = g.D + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * OZ_BN;
+      if (CRT) {
+        /* accumulator mod p_d (crt::acc_mod), 32 residues = 32 bytes per thread and 32-column step */
+        uint8_t *dst = g.R + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
+        const uint32_t p = c_crt.p[d], off = c_crt.off[d], finv = c_crt.finv[d];
+#pragma unroll 1
+        for (int c = 0; c < OZ_BN / 32; ++c) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(taddr + c * 32, v);
+          tc::tmem_ld_wait();
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t u = v[4 * q + b] + off;
+              uint32_t r = u - __umulhi(u, finv) * p;
+              r = r >= p ? r - p : r;
+              word |= r << (8 * b);
+            }
+            w[q] = word;
+          }
+          *reinterpret_cast<uint4 *>(dst + c * 32) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4 *>(dst + c * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+      } else {
+      int32_t *dst = g.D + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
 #pragma unroll 1
       for (int c = 0; c < OZ_BN / 32; ++c) {
         uint32_t v[32];
@@ -194,6 +228,7 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4 *>(dst + c * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -528,6 +563,183 @@ __global__ void __launch_bounds__(128) k_oz_fixup(const OzFixArgs g)
   }
 }
 
+
+/* ================================================================== residue scheme (qb_crt.cuh) */
+/* The 4 elements (row r, k = 4 g4 .. 4 g4 + 3) as words of |X| and signs, X = x / 2^(base - 16495) an exact integer below 2^W. */
+struct Crt4 { uint32_t w[4][crt::NWMAX]; uint32_t sign[4]; };
+__device__ __forceinline__ void crt_load4(const q128 *__restrict__ X, int64_t r, int64_t g4, int64_t K, int64_t sr, int64_t sk, int base, Crt4 &c)
+{
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int j = 0; j < crt::NWMAX; ++j) c.w[q][j] = 0;
+    c.sign[q] = 0;
+    const int64_t k = g4 * 4 + q;
+    if (k >= K) continue;
+    const OzElem e = oz_unpack(X[r * sr + k * sk]);
+    if (!(e.lo | e.hi) || e.special) continue;
+    u256 v; v.w0 = e.lo; v.w1 = e.hi; v.w2 = 0; v.w3 = 0;
+    const int sh = e.ee - base;
+    v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact: base <= lowest set bit of the row */
+    c.w[q][0] = (uint32_t)v.w0; c.w[q][1] = (uint32_t)(v.w0 >> 32);
+    c.w[q][2] = (uint32_t)v.w1; c.w[q][3] = (uint32_t)(v.w1 >> 32);
+    c.w[q][4] = (uint32_t)v.w2; c.w[q][5] = (uint32_t)(v.w2 >> 32);
+    c.sign[q] = e.sign;
+  }
+}
+/* residues of the 4 elements modulo p_i packed as 4 int8 (byte q = element q) */
+template <int NW>
+__device__ __forceinline__ uint32_t crt_word(const Crt4 &c, int i)
+{
+  uint32_t word = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) word |= crt::residue_byte<NW>(c.w[q], c.sign[q], i, c_crt) << (8 * q);
+  return word;
+}
+
+/* k contiguous (or fully strided): thread = (row, 4 consecutive k); plane i is [rows][Kp] int8 */
+template <int NW>
+__global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
+                                                      int W, int N, int64_t Kp, int8_t *__restrict__ planes)
+{
+  const int64_t groups = Kp >> 2;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= rows * groups) return;
+  const int64_t r = tid / groups, g4 = tid % groups;
+  Crt4 c;
+  crt_load4(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
+#pragma unroll
+  for (int g = 0; g < crt::NGMAX; ++g) {
+    if (4 * g < N) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * g + b;
+        if (i < N) *reinterpret_cast<uint32_t *>(planes + ((int64_t)i * rows + r) * Kp + g4 * 4) = crt_word<NW>(c, i);
+      }
+    }
+  }
+}
+
+/* rows contiguous in memory: CTA = 32 rows x 32 k with lanes along the rows (coalesced 16-byte loads); the plane words are
+ * transposed through shared memory and leave as 32-byte runs along K (cf. k_oz_slice_t) */
+static constexpr int CRT_T_SMEM = crt::NMP * 32 * 9 * 4;
+template <int NW>
+__global__ void __launch_bounds__(256) k_crt_residues_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
+                                                        int W, int N, int64_t Kp, int8_t *__restrict__ planes)
+{
+  extern __shared__ uint32_t crt_sm[];            /* [plane][row][k-group], padded: 9 words per row */
+  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.x * 32, g0 = (int64_t)blockIdx.y * 8;
+  const int64_t r = r0 + lane, g4 = g0 + wg;
+  if (r < rows) {
+    Crt4 c;
+    crt_load4(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
+#pragma unroll
+    for (int g = 0; g < crt::NGMAX; ++g) {
+      if (4 * g < N) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = 4 * g + b;
+          if (i < N) crt_sm[(i * 32 + lane) * 9 + wg] = crt_word<NW>(c, i);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < N * 64; q += 256) {
+    const int i = q >> 6, row = (q & 63) >> 1, half = q & 1;
+    if (r0 + row >= rows) continue;
+    const uint32_t *src = &crt_sm[(i * 32 + row) * 9 + half * 4];
+    *reinterpret_cast<uint4 *>(planes + ((int64_t)i * rows + r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
+  }
+}
+
+/* |I| (NL limbs, non-zero handled by the caller) times 2^Eb -> binary128, one rounding (RNE) */
+template <int NL>
+__device__ __forceinline__ q128 crt_limbs_to_q(const uint32_t (&L)[NL], uint32_t neg, int Eb)
+{
+  int top = -1;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) if (L[l]) top = l;
+  if (top < 0) return q_zero(0);   /* an exact zero sum is +0 (a +0-seeded chain never yields -0) */
+  uint32_t buf[NL + 8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) buf[l] = 0;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) buf[8 + l] = L[l];
+  uint32_t w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = buf[top + k];   /* limbs top-8 .. top */
+  uint32_t sticky = 0;
+#pragma unroll
+  for (int l = 0; l < NL; ++l) if (l < top - 8) sticky |= L[l];
+  const int lz = __clz((int)w[8]);
+  uint32_t R[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) R[k] = __funnelshift_l(w[k], w[k + 1], lz);
+  sticky |= w[0] << lz;
+  if (lz == 0) sticky |= w[0];
+  u256 Rq;
+  Rq.w0 = ((uint64_t)R[1] << 32) | R[0] | (sticky != 0);
+  Rq.w1 = ((uint64_t)R[3] << 32) | R[2];
+  Rq.w2 = ((uint64_t)R[5] << 32) | R[4];
+  Rq.w3 = ((uint64_t)R[7] << 32) | R[6];
+  const int p = 32 * top + 31 - lz;  /* MSB position of |I| */
+  return q_round_pack(neg, p + Eb + QBIAS, Rq);
+}
+
+struct CrtFoldArgs {
+  const uint8_t *R; int64_t Mp, Np;
+  int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
+  const int *emaxA, *emaxB; int WA, WB;
+  q128 alpha, beta; q128 *C; int64_t sci, scj;
+};
+/* thread = 4 consecutive columns of one C row: one 32-bit load per residue plane, then per element the reconstruction
+ * (crt::reconstruct), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109) */
+template <int NG>
+__global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __grid_constant__ crt::Plan pl)
+{
+  const int64_t n4 = (g.n + 3) >> 2;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = idx / n4, j0 = (idx % n4) * 4;
+  if (i >= g.m) return;
+  const int64_t plane = g.Mp * g.Np, off = i * g.Np + j0;
+  uint32_t rw[4 * NG];
+#pragma unroll
+  for (int c = 0; c < 4 * NG; ++c) rw[c] = c < pl.N ? *reinterpret_cast<const uint32_t *>(g.R + (int64_t)c * plane + off) : 0u;
+  const int baseA = g.emaxA[g.row0 + i] + 113 - g.WA;
+#pragma unroll 1
+  for (int e = 0; e < 4; ++e) {
+    const int64_t j = j0 + e;
+    if (j >= g.n) break;
+    uint32_t r[crt::NMP];
+#pragma unroll
+    for (int c = 0; c < 4 * NG; ++c) r[c] = (rw[c] >> (8 * e)) & 0xffu;
+    uint32_t Y[NG + 1], neg;
+    crt::reconstruct<NG>(r, pl, Y, neg);
+    const int baseB = g.emaxB[j] + 113 - g.WB;
+    const q128 sum = crt_limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
+    q128 *c = g.C + i * g.sci + j * g.scj;
+    *c = q_fma(g.alpha, sum, q_mul(g.beta, *c)); /* beta*C is always evaluated */
+  }
+}
+template <int NG>
+static void launch_crt_fold_ng(const CrtFoldArgs &f, const crt::Plan &pl, cudaStream_t st)
+{
+  const int64_t threads = f.m * ((f.n + 3) >> 2);
+  k_crt_fold<NG><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(f, pl);
+}
+static void launch_crt_fold(const CrtFoldArgs &f, const crt::Plan &pl, cudaStream_t st)
+{
+  switch (pl.NG) {
+#define QB_CRT_CASE(G) case G: launch_crt_fold_ng<G>(f, pl, st); break;
+    QB_CRT_CASE(1) QB_CRT_CASE(2) QB_CRT_CASE(3) QB_CRT_CASE(4) QB_CRT_CASE(5) QB_CRT_CASE(6) QB_CRT_CASE(7)
+    QB_CRT_CASE(8) QB_CRT_CASE(9) QB_CRT_CASE(10) QB_CRT_CASE(11) QB_CRT_CASE(12) QB_CRT_CASE(13)
+#undef QB_CRT_CASE
+  }
+  count_launch();
+}
+
 /* ------------------------------------------------------------------ host side */
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -576,14 +788,16 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
 {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_oz_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(k_oz_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_oz_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   CUtensorMap tmA, tmB;
   if (!make_plane_map(&tmA, pA, SA, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, SB, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
   OzMmaArgs g;
-  g.D = D; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
+  g.D = D; g.R = nullptr; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
   if (keep > 0 && keep < g.ndiag) g.ndiag = keep;   /* diagonals 0 .. keep-1 only */
   g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
   g.kb_begin = kb_begin; g.nkb = nkb;
@@ -595,7 +809,32 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
   for (int d = 0; d < g.ndiag; ++d) g.order[d] = (uint8_t)idx[d];
   const int total = g.ndiag * g.m_tiles * g.n_tiles;
   const int grid = std::min(total, sm_count());
-  k_oz_mma<<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+  k_oz_mma<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+  count_launch();
+  return cudaGetLastError();
+}
+
+/* residue scheme: R_i = (A_i B_i^T) mod p_i for the N residue planes, all k-blocks [0, nkb) in one accumulation
+ * (|acc| <= 128*128*Kp <= 2^30: Kp <= 65536) */
+static cudaError_t launch_crt_mma(const int8_t *pA, const int8_t *pB, int N, int64_t m, int64_t n, int64_t Kp, uint8_t *R, int64_t Mp, int64_t Np,
+                                  cudaStream_t st)
+{
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k_oz_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
+  OzMmaArgs g;
+  memset(&g, 0, sizeof(g));
+  g.R = R; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
+  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
+  g.kb_begin = 0; g.nkb = (int)(Kp / OZ_BK);
+  const int64_t total = (int64_t)N * g.m_tiles * g.n_tiles;
+  const int grid = (int)std::min<int64_t>(total, sm_count());
+  k_oz_mma<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
   count_launch();
   return cudaGetLastError();
 }
@@ -685,6 +924,114 @@ static void launch_oz_slice(const q128 *X, int64_t rows, int64_t K, int64_t sr, 
 /* capacity of the fix-up list of one row pass: above 1/64 of the pass the exact redo is cheaper */
 static inline int64_t oz_list_cap(int64_t mb, int64_t n) { return std::max<int64_t>(1024, std::min<int64_t>((mb * n) / 64, (int64_t)1 << 22)); }
 
+
+/* ---- residue scheme, host side ---- */
+static int g_oz_scheme = 1;     /* 1 = residues (qb_crt.cuh), 0 = digit diagonals */
+void oz_set_scheme(int v) { g_oz_scheme = v ? 1 : 0; }
+int oz_get_scheme() { return g_oz_scheme; }
+
+static cudaError_t crt_upload_tables()
+{
+  static int uploaded_dev = -1;
+  int dev = 0; cudaGetDevice(&dev);
+  if (uploaded_dev == dev) return cudaSuccess;
+  static crt::Tables T;
+  crt::host::build_tables(T);
+  cudaError_t e = cudaMemcpyToSymbol(c_crt, &T, sizeof(T));
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceSynchronize();   /* once per device: the copy from pageable memory must have landed before any stream reads it */
+  if (e != cudaSuccess) return e;
+#define QB_CRT_ATTR(NW) e = cudaFuncSetAttribute(k_crt_residues_t<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRT_T_SMEM); if (e != cudaSuccess) return e;
+  QB_CRT_ATTR(1) QB_CRT_ATTR(2) QB_CRT_ATTR(3) QB_CRT_ATTR(4) QB_CRT_ATTR(5) QB_CRT_ATTR(6)
+#undef QB_CRT_ATTR
+  uploaded_dev = dev;
+  return cudaSuccess;
+}
+static const crt::Plan &crt_plan(int N)
+{
+  static crt::Plan plans[crt::NM + 1];
+  static bool have[crt::NM + 1] = {false};
+  if (!have[N]) { crt::host::build_plan(N, plans[N]); have[N] = true; }
+  return plans[N];
+}
+static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int W, int N, int64_t Kp, int8_t *planes,
+                                cudaStream_t st)
+{
+  const int nw = std::min(crt::NWMAX, std::max(1, (W + 31) / 32));
+  const bool direct = (sk == 1 || sr != 1);
+  const int64_t threads = rows * (Kp / 4);
+  const unsigned g1 = (unsigned)((threads + 255) / 256);
+  const dim3 g2((unsigned)((rows + 31) / 32), (unsigned)(Kp / 32));
+  switch (nw) {
+#define QB_CRT_CASE(NW)                                                                                     \
+  case NW:                                                                                                  \
+    if (direct) k_crt_residues<NW><<<g1, 256, 0, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);          \
+    else k_crt_residues_t<NW><<<g2, 256, CRT_T_SMEM, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);      \
+    break;
+    QB_CRT_CASE(1) QB_CRT_CASE(2) QB_CRT_CASE(3) QB_CRT_CASE(4) QB_CRT_CASE(5) QB_CRT_CASE(6)
+#undef QB_CRT_CASE
+  }
+  count_launch();
+}
+
+/* The residue-scheme GEMM after scan + plan (WA, WB = widest row / column span in bits, no Inf/NaN).  *used = 0: declined. */
+static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes,
+                                   int WA, int WB, size_t meta_ints)
+{
+  const int64_t m = a.m, n = a.n, k = a.k;
+  const int64_t Kp = rup(k, OZ_BK);
+  WA = std::max(WA, 1); WB = std::max(WB, 1);
+  if (WA > crt::WMAX || WB > crt::WMAX || Kp > 65536) return cudaSuccess;
+  int lk = 0;
+  while (((int64_t)1 << lk) < k) ++lk;
+  const int need_bits = WA + WB + lk + 1;             /* P > 2 * k * 2^(WA + WB) >= 2 |I| */
+  const int N = crt::host::moduli_for_bits(need_bits);
+  if (N == 0) return cudaSuccess;
+  cudaError_t e = crt_upload_tables();
+  if (e != cudaSuccess) return e;
+  const crt::Plan &pl = crt_plan(N);
+  /* ---- workspace: residue planes of B | residue planes of A (per row pass) | R ---- */
+  const int64_t Np = rup(n, OZ_BN);
+  const size_t pb_b = rup((int64_t)N * n * Kp, 1024);
+  auto pass_bytes = [&](int64_t mb) -> size_t { return (size_t)rup((int64_t)N * mb * Kp, 1024) + (size_t)N * rup(mb, OZ_BM) * Np; };
+  int64_t mb = m;
+  if (cb && min_passes > 1) mb = std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM));
+  while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
+  if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess;
+  e = oz_reserve(meta_ints * 4, pb_b + pass_bytes(mb));
+  if (e != cudaSuccess) return e;
+  int *meta = (int *)g_oz.meta;
+  const int *emaxA = meta, *emaxB = meta + 2 * m;
+  int8_t *pB = (int8_t *)g_oz.buf;
+  int8_t *pA = pB + pb_b;
+  uint8_t *R = (uint8_t *)(pA + rup((int64_t)N * mb * Kp, 1024));
+  launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, st);
+  for (int64_t r0 = 0; r0 < m; r0 += mb) {
+    const int64_t mr = std::min(mb, m - r0);
+    const int64_t Mp = rup(mr, OZ_BM);
+    launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pA, st);
+    oz_ev_record(0, st);
+    e = launch_crt_mma(pA, pB, N, mr, n, Kp, R, Mp, Np, st);
+    oz_ev_record(1, st);
+    if (e != cudaSuccess) return e;
+    CrtFoldArgs f;
+    f.R = R; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = n; f.row0 = r0;
+    f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
+    f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
+    launch_crt_fold(f, pl, st);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (cb) cb(r0, mr, cb_user);
+  }
+  g_last_stats.SA = (WA + 7) / 8; g_last_stats.SB = (WB + 7) / 8; g_last_stats.ndiag = N; g_last_stats.nchunks = 1;
+  g_last_stats.row_passes = (int)((m + mb - 1) / mb);
+  g_last_stats.pairs = N; g_last_stats.keep = 0; g_last_stats.flagged = 0; g_last_stats.redo_passes = 0;
+  g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
+  g_last_stats.scheme = 1; g_last_stats.WA = WA; g_last_stats.WB = WB;
+  *used = 1;
+  return cudaSuccess;
+}
+
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes)
 {
@@ -723,6 +1070,10 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     if (e != cudaSuccess) return e;
   }
   const int WA = g_oz.h_plan[0], WB = g_oz.h_plan[1], fl = g_oz.h_plan[2];
+  if (g_oz_scheme == 1 && fl == 0) { /* residue scheme: one int8 GEMM per modulus; declines (-> digit diagonals) when the moduli cannot cover the span */
+    e = launch_gemm_crt(a, st, used, ws_budget, cb, cb_user, min_passes, WA, WB, meta_ints);
+    if (e != cudaSuccess || *used) return e;
+  }
   const int SA = std::max(1, (WA + 2 + 7) / 8), SB = std::max(1, (WB + 2 + 7) / 8);
   if (fl != 0 || SA > OZ_MAX_S || SB > OZ_MAX_S) return cudaSuccess; /* decline: Inf/NaN or span too wide */
   const int ndiag = SA + SB - 1;

@@ -16,12 +16,16 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture(autouse=True)
 def _exact_setting(qb):
-    """The tests of this file that compare bit for bit run the tensor path with ALL diagonals (qb_set_tensor_keep(0));
-    the bounded setting (the default) is covered by the test_bounded_* tests, which select it themselves."""
-    old = qb.get_tensor_keep()
+    """The tests of this file that compare bit for bit run the digit-diagonal scheme with ALL diagonals
+    (qb_set_tensor_keep(0)); the bounded setting is covered by the test_bounded_* tests, which select it themselves.
+    The residue scheme (qb_set_tensor_scheme(1), the default) is always exact."""
+    old, old_scheme = qb.get_tensor_keep(), qb.get_tensor_scheme()
     qb.set_tensor_keep(0)
     yield
-    qb.set_tensor_keep(old)
+    qb.set_tensor_keep(old); qb.set_tensor_scheme(old_scheme)
+
+
+SCHEMES = [pytest.param(1, id="residues"), pytest.param(0, id="digits")]
 
 
 def _diag_ref(pa, pb, m, n):
@@ -72,17 +76,25 @@ def _epilogue(oracle, alpha, s, beta, C0):
     return oracle.fma(al, s, oracle.mul(be, np.ascontiguousarray(C0)))
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("m,n,k,kind,layout", [(40, 33, 300, "D113", "R"), (17, 50, 129, "Dexp", "R"), (33, 20, 257, "D53", "C"),
-                                               (130, 260, 64, "D113", "R"), (5, 7, 1000, "D113", "C")])
-def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, layout):
+                                               (130, 260, 64, "D113", "R"), (5, 7, 1000, "D113", "C"), (24, 30, 140, "Dexp8", "R"),
+                                               (9, 300, 70, "Dint", "C"), (140, 12, 33, "D113", "C")])
+def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, layout, scheme):
+    qb.set_tensor_scheme(scheme)
     rng = np.random.default_rng(m + n + k)
     ar, ac = (m, k) if layout == "R" else (k, m)
     br, bc = (k, n) if layout == "R" else (n, k)
     cr, cc = (m, n) if layout == "R" else (n, m)
     lda, ldb, ldc = ac + 1, bc + 2, cc + 3
     def mk(r, c, ld):
-        if kind == "Dexp":  # +-28 binades: 113 + 56 + 2 bits -> 22 digits (the full +-40 of qgen needs 25 > 24 and is declined)
+        if kind == "Dexp":  # +-28 binades: 113 + 56 + 2 bits -> 22 digits (the full +-40 of qgen needs 25 > 24 and is declined);
+            # 2 x 171 bits + log2 k is also more than the residue scheme's 49 moduli cover: it hands over to the digit diagonals
             return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-28, emax=28).reshape(r * ld, 2))
+        if kind == "Dexp8":  # +-8 binades: spans of ~130 bits, inside the residue scheme
+            return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-8, emax=8).reshape(r * ld, 2))
+        if kind == "Dint":   # small integers (a few moduli, one reconstruction group), with zeros
+            return quad.from_double(rng.integers(-9, 10, size=(r, ld)).astype(np.float64)).reshape(r * ld, 2)
         return qgen.matrix(rng, r, c, kind, ld)
     A = mk(ar, ac, lda); B = mk(br, bc, ldb); C0 = mk(cr, cc, ldc)
     alpha, beta = quad.random_quads(rng, 2)
@@ -99,14 +111,17 @@ def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, lay
         qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
     got = to_host(dC)
     assert st["pairs"] > 0, "tensor path declined"
+    assert st["scheme"] == ("residues" if scheme == 1 and kind != "Dexp" else "digits"), st
     assert quad.same_bits(got[idx], want).all(), f"{(~quad.same_bits(got[idx], want)).sum()} mismatches, plan {st}"
     # untouched padding
     mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False
     assert (got[mask] == C0[mask]).all()
 
 
-def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle):
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle, scheme):
     """README:141-158 / test_quadblas.cpp:715-739: rows (1e20, 1, -1e20, 0...) times ones -> exactly 1."""
+    qb.set_tensor_scheme(scheme)
     m, n, k = 128, 128, 256
     A = np.zeros((m, k)); A[:, 0] = 1e20; A[:, 1] = 1.0; A[:, 2] = -1e20
     Aq = quad.from_double(A).reshape(-1, 2); Bq = quad.from_double(np.ones((k, n))).reshape(-1, 2)
@@ -122,8 +137,10 @@ def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle):
     assert quad.same_bits(to_host(dC), one).all()
 
 
-def test_fast_gemm_declines_specials_and_wide_spans(qb, oracle):
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_fast_gemm_declines_specials_and_wide_spans(qb, oracle, scheme):
     """Inf/NaN or a row spanning more than 24 digits: the planner declines, the integer kernel runs (fast mode = single chain)."""
+    qb.set_tensor_scheme(scheme)
     rng = np.random.default_rng(3)
     m, n, k = 130, 140, 260
     A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
@@ -141,8 +158,10 @@ def test_fast_gemm_declines_specials_and_wide_spans(qb, oracle):
     assert quad.same_bits(to_host(dC), Co).all()
 
 
-def test_fast_gemm_large_matches_sampled_exact(qb, oracle):
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_fast_gemm_large_matches_sampled_exact(qb, oracle, scheme):
     """1024 x 768 x 2304 (two K chunks at 18 slices would need k > 7281; force chunks via D113 + k): sampled entries vs exact."""
+    qb.set_tensor_scheme(scheme)
     m, n, k = 1024, 768, 2304
     A = dev_random((m * k,), "D113", seed=1); B = dev_random((k * n,), "D113", seed=2); C = dev_random((m * n,), "D113", seed=3)
     C0 = to_host(C).copy()
@@ -153,7 +172,7 @@ def test_fast_gemm_large_matches_sampled_exact(qb, oracle):
         st = qb.oz_last_stats()
     finally:
         qb.set_mode(qb.MODE_REFERENCE)
-    assert st["pairs"] > 0
+    assert st["pairs"] > 0 and st["scheme"] == ("residues" if scheme else "digits"), st
     Ah, Bh, got = to_host(A), to_host(B), to_host(C)
     rng = np.random.default_rng(0)
     for _ in range(12):
@@ -187,7 +206,7 @@ def test_bounded_tensor_path_meets_contract(qb, oracle, m, n, k, kind):
     mk = (lambda r, c: np.ascontiguousarray(quad.random_quads(rng, (r, c), "D113", emin=-28, emax=28).reshape(r * c, 2))) if kind == "Dexp" \
         else (lambda r, c: qgen.matrix(rng, r, c, kind, c))
     A = mk(m, k); B = mk(k, n); C0 = qgen.matrix(rng, m, n, "D113", n)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
     try:
         dC = to_dev(C0)
         qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 0.0, dC, n)
@@ -222,7 +241,7 @@ def test_bounded_fixup_on_cancelling_entries(qb, oracle):
     Bm[k // 2:, 1::2, 0] ^= np.uint64(1) << np.uint64(5)                               # ... up to one low mantissa bit
     A2 = np.ascontiguousarray(Am.reshape(m * k, 2)); B2 = np.ascontiguousarray(Bm.reshape(k * n, 2))
     C0 = qgen.matrix(rng, m, n, "D113", n)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
     try:
         dC = to_dev(C0)
         qb.gemm("R", m, n, k, 1.0, to_dev(A2), k, to_dev(B2), n, 0.0, dC, n)
@@ -243,7 +262,7 @@ def test_bounded_redo_when_many_entries_vanish(qb, oracle):
     A[::4] = 0
     A = np.ascontiguousarray(A.reshape(m * k, 2)); B = qgen.matrix(rng, k, n, "D113", n); C0 = qgen.matrix(rng, m, n, "D113", n)
     alpha, beta = quad.random_quads(rng, 2)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
     try:
         dC = to_dev(C0)
         qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
@@ -265,3 +284,52 @@ def test_bounded_redo_when_many_entries_vanish(qb, oracle):
         for j in (0, 100, 255):
             fg, fw = quad.to_fraction(int(got[i, j, 1]), int(got[i, j, 0])), quad.to_fraction(int(w[j, 1]), int(w[j, 0]))
             assert abs(fg - fw) <= abs(fw) / 2 ** 90
+
+
+# ------------------------------------------------------------------ residue scheme specifics (csrc/qb_crt.cuh)
+def test_residue_scheme_row_passes_and_epilogue(qb, oracle):
+    """Row passes (pass hook with min_passes = 3) + alpha/beta epilogue + padded leading dimensions: every pass slices its own A
+    rows, reuses the residue planes of B, and the result is the exact product rounded once, bit for bit."""
+    m, n, k = 384, 264, 200
+    rng = np.random.default_rng(11)
+    lda, ldb, ldc = k + 3, n + 1, n + 2
+    A = qgen.matrix(rng, m, k, "D113", lda); B = qgen.matrix(rng, k, n, "D113", ldb); C0 = qgen.matrix(rng, m, n, "D113", ldc)
+    alpha, beta = quad.random_quads(rng, 2)
+    rows_idx = rng.choice(m, 6, replace=False)
+    seen = []
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
+    try:
+        qb.set_gemm_pass_callback(lambda r0, rows: seen.append((r0, rows)), 3)
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_gemm_pass_callback(None)
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["scheme"] == "residues" and st["row_passes"] == 3 and seen == [(0, 128), (128, 128), (256, 128)], (st, seen)
+    got = to_host(dC)
+    for i in rows_idx:
+        s = exact_matmul_rounded(A[i * lda:(i + 1) * lda], lda, B, ldb, 1, n, k, "R")
+        want = _epilogue(oracle, alpha, s, beta, C0[i * ldc:i * ldc + n])
+        assert quad.same_bits(got[i * ldc:i * ldc + n], want).all(), (i, st)
+
+
+def test_residue_scheme_zero_operand(qb, oracle):
+    """An all-zero A (no span at all): the sums are +0 and C = fma(alpha, +0, mul(beta, C))."""
+    m, n, k = 130, 258, 130
+    rng = np.random.default_rng(12)
+    A = quad.from_double(np.zeros((m, k))).reshape(-1, 2); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    alpha, beta = quad.random_quads(rng, 2)
+    zero = quad.from_double(np.zeros(m * n))
+    want = _epilogue(oracle, alpha, zero, beta, C0)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["scheme"] == "residues", st
+    assert quad.same_bits(to_host(dC), want).all()

@@ -1,0 +1,120 @@
+"""CPU checks of the residue arithmetic of the tensor-path qgemm (qblas_b200/csrc/qb_crt.cuh, host/device
+dual source, built with g++ through tests/host/crt_host.cpp) against Python integers: int8 residues of
+signed multi-word integers, reduction of int32 accumulators, and the grouped Chinese-remainder
+reconstruction of the exact inner product."""
+import ctypes as C
+import os
+import random
+import subprocess
+from math import gcd, log2
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    so = tmp_path_factory.mktemp("crt") / "libcrt_host.so"
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=gnu++17", "-shared", "-fPIC", "-o", str(so),
+                    os.path.join(ROOT, "tests", "host", "crt_host.cpp")], check=True)
+    L = C.CDLL(str(so))
+    L.crt_plan_bits.restype = C.c_double
+    L.crt_residues.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.crt_fold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def _moduli(lib):
+    return [lib.crt_modulus(i) for i in range(lib.crt_num_moduli())]
+
+
+def test_moduli_pairwise_coprime_and_int8(lib):
+    m = _moduli(lib)
+    assert m == sorted(m, reverse=True) and max(m) <= 256
+    for i in range(len(m)):
+        for j in range(i):
+            assert gcd(m[i], m[j]) == 1
+    for g in range(0, len(m), 4):
+        prod = 1
+        for p in m[g:g + 4]:
+            prod *= p
+        assert prod < 2 ** 32
+    # capacity: full-mantissa operands (W ~ 142) at k = 2^15 and beyond
+    tot = sum(log2(p) for p in m)
+    assert tot > 142 * 2 + 15 + 1
+    assert abs(lib.crt_plan_bits(len(m)) - tot) < 1e-6
+    assert lib.crt_moduli_for_bits(292) == 41 and lib.crt_moduli_for_bits(400) == 0
+
+
+def _words(x):
+    return [(x >> (32 * j)) & 0xffffffff for j in range(6)]
+
+
+def _residues(lib, xs, nw, N):
+    words = np.array([_words(abs(x)) for x in xs], dtype=np.uint32)
+    sign = np.array([1 if x < 0 else 0 for x in xs], dtype=np.uint32)
+    out = np.zeros((len(xs), N), dtype=np.int8)
+    lib.crt_residues(len(xs), words.ctypes.data, sign.ctypes.data, nw, N, out.ctypes.data)
+    return out
+
+
+@pytest.mark.parametrize("W", [1, 8, 31, 32, 33, 54, 113, 139, 160, 192])
+def test_residues_are_symmetric_int8(lib, W):
+    rnd = random.Random(W)
+    m = _moduli(lib)
+    xs = [0, 1, -1, 2 ** W - 1, -(2 ** W - 1)] + [rnd.randrange(-(2 ** W) + 1, 2 ** W) for _ in range(300)]
+    nw = (W + 31) // 32
+    out = _residues(lib, xs, nw, len(m))
+    for x, row in zip(xs, out):
+        for p, r in zip(m, row):
+            r = int(r)
+            assert (r - x) % p == 0
+            assert -128 <= r <= 127 and (-(p - 1) // 2 <= r <= (p - 1) // 2 if p % 2 else -128 <= r <= 127)
+
+
+@pytest.mark.parametrize("WA,WB,k", [(139, 139, 64), (142, 137, 300), (54, 54, 128), (113, 113, 17), (192, 120, 8), (7, 5, 1000), (160, 160, 50)])
+def test_inner_product_reconstruction_exact(lib, WA, WB, k):
+    rnd = random.Random(WA * 1000 + WB + k)
+    need = WA + WB + (k - 1).bit_length() + 1
+    N = lib.crt_moduli_for_bits(need)
+    assert N > 0
+    m = _moduli(lib)[:N]
+    cases = 24
+    acc = np.zeros((cases, N), dtype=np.int32)
+    exact = []
+    for c in range(cases):
+        if c == 0:      # extreme: every product at the bound, same sign
+            a = [2 ** WA - 1] * k; b = [-(2 ** WB - 1)] * k
+        elif c == 1:    # exact cancellation
+            a = [rnd.randrange(-(2 ** WA) + 1, 2 ** WA) for _ in range(k // 2)]; a = a + a + [0] * (k - 2 * (k // 2))
+            b = [rnd.randrange(-(2 ** WB) + 1, 2 ** WB) for _ in range(k // 2)]; b = b + [-v for v in b] + [0] * (k - 2 * (k // 2))
+        else:
+            a = [rnd.randrange(-(2 ** WA) + 1, 2 ** WA) for _ in range(k)]
+            b = [rnd.randrange(-(2 ** WB) + 1, 2 ** WB) for _ in range(k)]
+        ra = _residues(lib, a, (WA + 31) // 32, N).astype(np.int64)
+        rb = _residues(lib, b, (WB + 31) // 32, N).astype(np.int64)
+        acc[c] = (ra * rb).sum(axis=0)       # what one int8 GEMM per modulus accumulates (|.| <= k 2^14)
+        exact.append(sum(x * y for x, y in zip(a, b)))
+    mag = np.zeros((cases, 14), dtype=np.uint32); neg = np.zeros(cases, dtype=np.uint32)
+    lib.crt_fold(cases, acc.ctypes.data, N, mag.ctypes.data, neg.ctypes.data)
+    for c in range(cases):
+        v = sum(int(mag[c, l]) << (32 * l) for l in range(14))
+        v = -v if neg[c] else v
+        assert v == exact[c], (c, N)
+    assert exact[1] == 0 and neg[1] == 0
+
+
+def test_accumulator_reduction_range(lib):
+    """int32 accumulators up to +-2^30 (k = 65536 products of +-128 * +-128) reduce exactly."""
+    N = 8
+    m = _moduli(lib)[:N]
+    vals = [0, 1, -1, 2 ** 30, -(2 ** 30), 2 ** 30 - 1, -(2 ** 30) + 1, 12345678, -87654321]
+    # reconstruction of small integers straight from their accumulators
+    acc = np.array([[v] * N for v in vals], dtype=np.int32)
+    mag = np.zeros((len(vals), 14), dtype=np.uint32); neg = np.zeros(len(vals), dtype=np.uint32)
+    lib.crt_fold(len(vals), acc.ctypes.data, N, mag.ctypes.data, neg.ctypes.data)
+    for c, v in enumerate(vals):
+        got = sum(int(mag[c, l]) << (32 * l) for l in range(14))
+        assert (-got if neg[c] else got) == v
