@@ -64,6 +64,8 @@ struct Plan {
   int N, NG;
   uint32_t G[NGMAX];          /* group moduli G_g = product of the group's p */
   uint32_t flo[NGMAX], fhi[NGMAX]; /* f_g = floor(2^64 / G_g) */
+  uint32_t gshr[NGMAX], gshl[NGMAX], ginv[NGMAX]; /* device quotient: G' = G << sh in [2^31, 2^32); a = (v << sh) >> 11 = (v >> gshr) << gshl,
+                                                     ginv = floor((2^63 - 1) / G'); floor(a ginv / 2^52) is floor(v / G) or one less */
   uint32_t cp[NMP];           /* c'_j: t_g = (sum_{j in g} r_j c'_j) mod G_g is the top-level CRT digit, already
                                  multiplied by (P/G_g)^-1 mod G_g */
   uint32_t M[NGMAX][NLMAX];   /* M_g = P / G_g */
@@ -193,6 +195,113 @@ QCRT_UNROLL
   }
 }
 
+
+/* ------------------------------------------------------------------ reconstruction, device form */
+#if defined(__CUDACC__)
+/* Same result as reconstruct<NG>() (the tested reference form above), written on PTX carry chains: the products t * M_g
+ * go into an even-column and an odd-column accumulator as mad.lo.cc / madc.hi.cc pairs (ptxas fuses each pair into one
+ * IMAD.WIDE with carry), the group digit t_g uses a 32-bit reciprocal of the normalised group modulus. */
+namespace ptx {
+#define QCRT_DI __device__ __forceinline__
+QCRT_DI uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+QCRT_DI uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+QCRT_DI uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+QCRT_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+QCRT_DI uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+QCRT_DI uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+QCRT_DI uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+QCRT_DI uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+QCRT_DI uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+QCRT_DI uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+/* acc (NL limbs, even or odd columns only) += t * m[l] for l = L0, L0 + 2, ... < NM; carries stay inside NL limbs */
+template <int NL, int NMUL, int L0>
+QCRT_DI void mad_columns(uint32_t (&acc)[NL], uint32_t t, const uint32_t *m)
+{
+  if (L0 >= NMUL) return;
+  acc[L0] = mad_lo_cc(t, m[L0], acc[L0]);
+  acc[L0 + 1] = madc_hi_cc(t, m[L0], acc[L0 + 1]);
+  int last = L0 + 1;
+#pragma unroll
+  for (int l = L0 + 2; l < NMUL; l += 2) {
+    acc[l] = madc_lo_cc(t, m[l], acc[l]);
+    acc[l + 1] = madc_hi_cc(t, m[l], acc[l + 1]);
+    last = l + 1;
+  }
+#pragma unroll
+  for (int l = 0; l < NL; ++l)
+    if (l > last) acc[l] = (l == NL - 1) ? addc(acc[l], 0u) : addc_cc(acc[l], 0u);
+}
+} // namespace ptx
+
+template <int NG>
+__device__ __forceinline__ void reconstruct_dev(const uint32_t (&r)[NMP], const Plan &pl, uint32_t (&Y)[NG + 1], uint32_t &neg)
+{
+  constexpr int NL = NG + 1;
+  uint32_t E[NL], O[NL];
+#pragma unroll
+  for (int l = 0; l < NL; ++l) { E[l] = 0; O[l] = 0; }
+  uint32_t s0 = 0, s1 = 0, s2 = 0;          /* S = sum t_g f_g (96 bits) */
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) v += (uint64_t)r[4 * g + b] * pl.cp[4 * g + b];   /* cp = 0 beyond N */
+    /* t = v mod G: quotient (< 2^10) from the top 31 bits of v 2^sh and a 32-bit reciprocal of G 2^sh in [2^31, 2^32) */
+    const uint32_t a = (uint32_t)(v >> pl.gshr[g]) << pl.gshl[g];  /* (v << sh) >> 11 < 2^31 */
+    const uint32_t qh = __umulhi(a, pl.ginv[g]) >> 20;             /* floor(v / G) or one less */
+    uint64_t t64 = v - (uint64_t)qh * pl.G[g];
+    if (t64 >= pl.G[g]) t64 -= pl.G[g];
+    const uint32_t t = (uint32_t)t64;
+    ptx::mad_columns<NL, NG, 0>(E, t, pl.M[g]);
+    ptx::mad_columns<NL, NG, 1>(O, t, pl.M[g]);
+    s0 = ptx::mad_lo_cc(t, pl.flo[g], s0); s1 = ptx::madc_hi_cc(t, pl.flo[g], s1); s2 = ptx::addc(s2, 0u);
+    s1 = ptx::mad_lo_cc(t, pl.fhi[g], s1); s2 = ptx::madc_hi(t, pl.fhi[g], s2);
+  }
+  /* Y = E + O - qhat P  in [0, 2P) */
+  {
+    uint32_t QE[NL], QO[NL];
+#pragma unroll
+    for (int l = 0; l < NL; ++l) { QE[l] = 0; QO[l] = 0; }
+    ptx::mad_columns<NL, NG, 0>(QE, s2, pl.P);
+    ptx::mad_columns<NL, NG, 1>(QO, s2, pl.P);
+    Y[0] = ptx::add_cc(E[0], O[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::addc(E[l], O[l]) : ptx::addc_cc(E[l], O[l]);
+    Y[0] = ptx::sub_cc(Y[0], QE[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::subc(Y[l], QE[l]) : ptx::subc_cc(Y[l], QE[l]);
+    Y[0] = ptx::sub_cc(Y[0], QO[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::subc(Y[l], QO[l]) : ptx::subc_cc(Y[l], QO[l]);
+  }
+  /* Y >= P: subtract P once */
+  {
+    uint32_t T[NL];
+    T[0] = ptx::sub_cc(Y[0], pl.P[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) T[l] = ptx::subc_cc(Y[l], pl.P[l]);
+    const uint32_t below = ptx::subc(0u, 0u);   /* all ones when Y < P */
+#pragma unroll
+    for (int l = 0; l < NL; ++l) Y[l] = below ? Y[l] : T[l];
+  }
+  /* |I| = min(Y, P - Y); negative when P - Y is the smaller one (Y = P/2 cannot happen: |I| < P/2) */
+  {
+    uint32_t U[NL];
+    U[0] = ptx::sub_cc(pl.P[0], Y[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) U[l] = (l == NL - 1) ? ptx::subc(pl.P[l], Y[l]) : ptx::subc_cc(pl.P[l], Y[l]);
+    (void)ptx::sub_cc(U[0], Y[0]);
+#pragma unroll
+    for (int l = 1; l < NL; ++l) (void)ptx::subc_cc(U[l], Y[l]);
+    const uint32_t u_below = ptx::subc(0u, 0u); /* all ones when U < Y */
+    neg = u_below ? 1u : 0u;
+#pragma unroll
+    for (int l = 0; l < NL; ++l) Y[l] = u_below ? U[l] : Y[l];
+  }
+}
+#endif
+
 /* ------------------------------------------------------------------ host: tables and plans */
 namespace host {
 
@@ -265,6 +374,14 @@ static inline void build_plan(int N, Plan &pl)
     const unsigned __int128 two64 = (unsigned __int128)1 << 64;
     const uint64_t f = G == 1 ? ~(uint64_t)0 : (uint64_t)(two64 / G);
     pl.flo[g] = (uint32_t)f; pl.fhi[g] = (uint32_t)(f >> 32);
+    {
+      int lg = 0;
+      while ((G >> (lg + 1)) != 0) ++lg;
+      const int sh = 31 - lg;                    /* G << sh in [2^31, 2^32) */
+      pl.gshr[g] = sh < 11 ? (uint32_t)(11 - sh) : 0u;
+      pl.gshl[g] = sh > 11 ? (uint32_t)(sh - 11) : 0u;
+      pl.ginv[g] = (uint32_t)((((uint64_t)1 << 63) - 1) / (G << sh));
+    }
     Big M = P;
     big_div_small(M, (uint32_t)G);
     for (int l = 0; l < NLMAX; ++l) pl.M[g][l] = M.w[l];

@@ -693,6 +693,7 @@ struct CrtFoldArgs {
   int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
   const int *emaxA, *emaxB; int WA, WB;
   q128 alpha, beta; q128 *C; int64_t sci, scj;
+  int simple;                        /* alpha == 1 and beta == +-0 */
 };
 /* thread = 4 consecutive columns of one C row: one 32-bit load per residue plane, then per element the reconstruction
  * (crt::reconstruct), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109) */
@@ -716,11 +717,15 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
 #pragma unroll
     for (int c = 0; c < 4 * NG; ++c) r[c] = (rw[c] >> (8 * e)) & 0xffu;
     uint32_t Y[NG + 1], neg;
-    crt::reconstruct<NG>(r, pl, Y, neg);
+    crt::reconstruct_dev<NG>(r, pl, Y, neg);
     const int baseB = g.emaxB[j] + 113 - g.WB;
     const q128 sum = crt_limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
     q128 *c = g.C + i * g.sci + j * g.scj;
-    *c = q_fma(g.alpha, sum, q_mul(g.beta, *c)); /* beta*C is always evaluated */
+    const q128 cin = *c;
+    /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
+     * general line below, without the two software roundings */
+    if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) *c = sum;
+    else *c = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
   }
 }
 template <int NG>
@@ -974,7 +979,38 @@ static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t 
   count_launch();
 }
 
-/* The residue-scheme GEMM after scan + plan (WA, WB = widest row / column span in bits, no Inf/NaN).  *used = 0: declined. */
+/* Internal streams of the residue scheme: the tensor kernel of row pass p (sM, highest priority) runs while the residues of
+ * the A rows of pass p+1 (sA) and the reconstruction of pass p-1 (sF) use the integer pipes of the same SMs (the persistent
+ * tensor kernel holds one 192-thread CTA per SM; the other two kernels need no shared memory and fit beside it). */
+struct CrtStreams {
+  cudaStream_t sM = nullptr, sA = nullptr, sF = nullptr;
+  cudaEvent_t in = nullptr, resA[2] = {nullptr, nullptr}, mma[2] = {nullptr, nullptr}, fold[2] = {nullptr, nullptr};
+  int device = -1;
+};
+static CrtStreams g_cs;
+static cudaError_t crt_streams()
+{
+  int dev = 0; cudaGetDevice(&dev);
+  if (g_cs.device == dev) return cudaSuccess;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaError_t e = cudaStreamCreateWithPriority(&g_cs.sM, cudaStreamNonBlocking, hi);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g_cs.sA, cudaStreamNonBlocking, lo);
+  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g_cs.sF, cudaStreamNonBlocking, lo);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.in, cudaEventDisableTiming);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaEventCreateWithFlags(&g_cs.resA[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.mma[b], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.fold[b], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) g_cs.device = dev;
+  return e;
+}
+
+/* The residue-scheme GEMM after scan + plan (WA, WB = widest row / column span in bits, no Inf/NaN).  *used = 0: declined.
+ * The C rows are produced in row passes, software-pipelined over three internal streams (CrtStreams); `st` waits for the
+ * reconstruction of every pass before the pass callback runs and before this function returns, so for the caller all the
+ * work is ordered on `st` as usual. */
 static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes,
                                    int WA, int WB, size_t meta_ints)
 {
@@ -989,42 +1025,69 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
   if (N == 0) return cudaSuccess;
   cudaError_t e = crt_upload_tables();
   if (e != cudaSuccess) return e;
+  e = crt_streams();
+  if (e != cudaSuccess) return e;
   const crt::Plan &pl = crt_plan(N);
-  /* ---- workspace: residue planes of B | residue planes of A (per row pass) | R ---- */
+  /* ---- workspace: residue planes of B | 2 x (residue planes of the A rows of a pass | R of the pass) ---- */
   const int64_t Np = rup(n, OZ_BN);
   const size_t pb_b = rup((int64_t)N * n * Kp, 1024);
-  auto pass_bytes = [&](int64_t mb) -> size_t { return (size_t)rup((int64_t)N * mb * Kp, 1024) + (size_t)N * rup(mb, OZ_BM) * Np; };
-  int64_t mb = m;
-  if (cb && min_passes > 1) mb = std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM));
-  while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
-  if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess;
-  e = oz_reserve(meta_ints * 4, pb_b + pass_bytes(mb));
+  auto pa_bytes = [&](int64_t mb) -> size_t { return (size_t)rup((int64_t)N * mb * Kp, 1024); };
+  auto pass_bytes = [&](int64_t mb) -> size_t { return pa_bytes(mb) + (size_t)rup((int64_t)N * rup(mb, OZ_BM) * Np, 1024); };
+  int want_passes = m >= 4096 ? 4 : (m >= 2048 ? 2 : 1);
+  if (cb && min_passes > want_passes) want_passes = min_passes;
+  int64_t mb = std::max<int64_t>(OZ_BM, rup((m + want_passes - 1) / want_passes, OZ_BM));
+  auto bufs = [&](int64_t mb_) -> int { return mb_ < m ? 2 : 1; };
+  while (mb > OZ_BM && pb_b + bufs(mb) * pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
+  if (pb_b + bufs(mb) * pass_bytes(mb) > ws_budget) return cudaSuccess;
+  const int nb = bufs(mb);
+  e = oz_reserve(meta_ints * 4, pb_b + nb * pass_bytes(mb));
   if (e != cudaSuccess) return e;
   int *meta = (int *)g_oz.meta;
   const int *emaxA = meta, *emaxB = meta + 2 * m;
   int8_t *pB = (int8_t *)g_oz.buf;
-  int8_t *pA = pB + pb_b;
-  uint8_t *R = (uint8_t *)(pA + rup((int64_t)N * mb * Kp, 1024));
-  launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, st);
-  for (int64_t r0 = 0; r0 < m; r0 += mb) {
+  int8_t *pA[2]; uint8_t *R[2];
+  for (int b = 0; b < 2; ++b) {
+    pA[b] = pB + pb_b + (size_t)(b % nb) * pass_bytes(mb);
+    R[b] = (uint8_t *)(pA[b] + pa_bytes(mb));
+  }
+  CrtStreams &cs = g_cs;
+  cudaEventRecord(cs.in, st);
+  cudaStreamWaitEvent(cs.sM, cs.in, 0); cudaStreamWaitEvent(cs.sA, cs.in, 0); cudaStreamWaitEvent(cs.sF, cs.in, 0);
+  launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, cs.sM);
+  int pass = 0;
+  for (int64_t r0 = 0; r0 < m; r0 += mb, ++pass) {
     const int64_t mr = std::min(mb, m - r0);
     const int64_t Mp = rup(mr, OZ_BM);
-    launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pA, st);
-    oz_ev_record(0, st);
-    e = launch_crt_mma(pA, pB, N, mr, n, Kp, R, Mp, Np, st);
-    oz_ev_record(1, st);
+    const int b = pass & 1;
+    /* residues of this pass's A rows: its buffer was last read by the tensor kernel of pass - 2 */
+    if (pass >= 2) cudaStreamWaitEvent(cs.sA, cs.mma[b], 0);
+    launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pA[b], cs.sA);
+    cudaEventRecord(cs.resA[b], cs.sA);
+    /* tensor kernel: needs the residues, and R[b] drained by the reconstruction of pass - 2 */
+    cudaStreamWaitEvent(cs.sM, cs.resA[b], 0);
+    if (pass >= 2) cudaStreamWaitEvent(cs.sM, cs.fold[b], 0);
+    oz_ev_record(0, cs.sM);
+    e = launch_crt_mma(pA[b], pB, N, mr, n, Kp, R[b], Mp, Np, cs.sM);
+    oz_ev_record(1, cs.sM);
     if (e != cudaSuccess) return e;
+    cudaEventRecord(cs.mma[b], cs.sM);
+    /* reconstruction + epilogue */
+    cudaStreamWaitEvent(cs.sF, cs.mma[b], 0);
     CrtFoldArgs f;
-    f.R = R; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = n; f.row0 = r0;
+    f.R = R[b]; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = n; f.row0 = r0;
     f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
     f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
-    launch_crt_fold(f, pl, st);
+    f.simple = (a.alpha.hi == 0x3fff000000000000ULL && a.alpha.lo == 0 && (a.beta.hi & 0x7fffffffffffffffULL) == 0 && a.beta.lo == 0) ? 1 : 0;
+    launch_crt_fold(f, pl, cs.sF);
     e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    cudaEventRecord(cs.fold[b], cs.sF);
+    e = cudaStreamWaitEvent(st, cs.fold[b], 0);   /* the caller's stream sees the rows of this pass */
     if (e != cudaSuccess) return e;
     if (cb) cb(r0, mr, cb_user);
   }
   g_last_stats.SA = (WA + 7) / 8; g_last_stats.SB = (WB + 7) / 8; g_last_stats.ndiag = N; g_last_stats.nchunks = 1;
-  g_last_stats.row_passes = (int)((m + mb - 1) / mb);
+  g_last_stats.row_passes = pass;
   g_last_stats.pairs = N; g_last_stats.keep = 0; g_last_stats.flagged = 0; g_last_stats.redo_passes = 0;
   g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
   g_last_stats.scheme = 1; g_last_stats.WA = WA; g_last_stats.WB = WB;
