@@ -163,7 +163,7 @@ def reference_arm(args, rank, world):
         "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": best["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 # ------------------------------------------------------------------ own arm
@@ -274,6 +274,19 @@ def own_arm(args, rank, world, local_rank):
     A = dev_random((m_loc * k,), args.dist, 100 + rank, dev)
     B = dev_random((k * n,), args.dist, 7, dev) if rank == 0 or world == 1 else torch.empty((k * n, 2), dtype=torch.int64, device=dev)
     Cfull = dev_random((M * n,), args.dist, 9, dev)          # C_in (beta=0 still reads it, level3.hpp:107)
+    peerbuf = None
+    if world > 1 and args.gather == "fused" and mode == qb.MODE_FAST:
+        # fused gather: C_full lives in peer-mapped memory; the reconstruction kernel stores every finished element into all
+        # ranks' copies over NVLink (qb_set_gemm_peer_outputs), so no all-gather re-reads and re-sends the blocks
+        from qblas_b200 import dist as qd
+        try:
+            peerbuf = qd.PeerBuffer(M * n * 16)
+            Cp = peerbuf.tensor.view(torch.int64).reshape(M * n, 2)
+            Cp.copy_(Cfull)
+            Cfull = Cp
+        except Exception as e:   # no peer access on this box: NCCL gather
+            print(f"[bench] fused gather unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr, flush=True)
+            peerbuf = None
     Cblk = Cfull[rank * m_loc * n:(rank + 1) * m_loc * n]
 
     Cb3 = Cblk.reshape(m_loc, n, 2)
@@ -285,6 +298,10 @@ def own_arm(args, rank, world, local_rank):
         while the next pass computes; only the last pass's gather is exposed."""
         if world == 1:
             qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
+            return
+        if fused["on"]:
+            qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)   # peer outputs are set: the fold kernel writes all ranks' copies
+            dist.all_reduce(fused["token"])                            # completion barrier of the peer stores, in stream order
             return
         if args.overlap <= 1:
             qb.gemm("R", m_loc, n, k, 1.0, A, k, B, n, 0.0, Cblk, n)
@@ -307,6 +324,19 @@ def own_arm(args, rank, world, local_rank):
         if world > 1:
             dist.broadcast(B, src=0)                          # byte-typed payload (int64 view of quads)
         gemm_and_gather()
+
+    fused = {"on": False, "token": torch.zeros(1, dtype=torch.int32, device=dev)}
+    if peerbuf is not None:
+        # one probing step: every rank must have run the path with the fused stores, otherwise all of them use the NCCL gather
+        qb.set_gemm_peer_outputs([peerbuf.ptrs[q] + rank * m_loc * n * 16 for q in range(world) if q != rank])
+        fused["on"] = True
+        step()
+        ok = torch.tensor([1 if qb.gemm_peer_written() == world - 1 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            fused["on"] = False
+            qb.set_gemm_peer_outputs(None)
+    args.gather_used = "fused" if fused["on"] else "nccl"
 
     def sync():
         torch.cuda.synchronize()
@@ -335,6 +365,8 @@ def own_arm(args, rank, world, local_rank):
             pass  # per-kernel events are read after the timed region (reading them blocks the host)
     ev1.record()
     sync()
+    if fused["on"]:
+        qb.set_gemm_peer_outputs(None)    # nothing after the timed region may write into the peers
     launches = qb.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
@@ -410,8 +442,11 @@ def own_arm(args, rank, world, local_rank):
                 alg = (f"one binary128 flop = {plan['pairs']} int8 ops ({plan['SA']}x{plan['SB']} signed-digit slices, {plan['keep']} of {plan['ndiag']} "
                        "diagonals multiplied)")
             roof = {"bound": "tensor", "kernel": "k_oz_mma (tcgen05.mma kind::i8, TMA-fed, TMEM accumulators)", "achieved": tops, "peak": peak,
-                    "unit": "TFLOP/s", "frac": tops / peak, "traffic": 43.2e9 if profiled else None,
-                    "traffic_note": "bytes per launch (2 launches per qgemm); algorithmic operand + result bytes per launch = 1.2 GB of digit planes + 4.3 GB of int32 diagonals: the planes are re-read once per digit-plane pair through L2 (1.5 TB/s = 23% of HBM while the tensor pipe is 85% active - not the bound)" if profiled else None,
+                    "unit": "TFLOP/s", "frac": tops / peak,
+                    "traffic": 43.2e9 if profiled else (4.02e9 * plan["pairs"] / 40.0 if residues and (m_loc, n, plan["Kp"], plan["row_passes"]) == (8192, 8192, 8192, 4) else None),
+                    "traffic_note": ("bytes per launch (4 launches per qgemm, one per pass of 2048 rows), from profiles/r1h_crt_mma_8192_ncu_full.txt (40 moduli: dram read 3.36 GB + write 0.66 GB, "
+                                     "scaled to this plan's moduli): equal to the algorithmic bytes N*(2048*Kp + n*Kp) of int8 planes read once + N*2048*n residue bytes written "
+                                     "(1.1 TB/s = 17% of HBM while the tensor pipe is 88% active)") if residues else "bytes per launch (2 launches per qgemm); algorithmic operand + result bytes per launch = 1.2 GB of digit planes + 4.3 GB of int32 diagonals: the planes are re-read once per digit-plane pair through L2 (1.5 TB/s = 23% of HBM while the tensor pipe is 85% active - not the bound)" if profiled else None,
                     "peak_source": (f"2 x MEASURED_PEAKS.json bf16_tflops (burst {bf16_burst}; sustained {bf16_sus}) [{src}]: int8 dense issues at twice the bf16 rate on sm_100a, "
                                     "no int8 figure is driver-measured; burst because each launch lasts a few ms (measured 3177 TOPS when timed alone)") if plan.get("scheme") == "residues" else
                                    (f"2 x MEASURED_PEAKS.json bf16_tflops_sustained ({bf16_sus}; burst {bf16_burst}) [{src}]: int8 dense issues at twice the bf16 rate on sm_100a, "
@@ -493,7 +528,7 @@ def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_s
                       else "binary128 (exact signed 8-bit slices on the int8 tensor cores, wide-integer recombination, one rounding)") if fast
                      else "binary128 (software, u32 integer limbs)",
             "data": "synthetic",
-            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, NCCL broadcast(B)+all_gather(C) in the timed region' + (f', all-gather issued per row pass ({args.overlap} passes) from the row-pass hook' if args.overlap > 1 else '') if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
+            "config": {"workload": f"quadblas_qgemm row-major {M}x{n}x{k} alpha=1 beta=0 ({'C row-blocks of ' + str(m_loc) + ' rows per GPU, ' + ('NCCL broadcast(B) + fused gather of C (the reconstruction kernel stores each finished element into every rank over NVLink peer memory; barrier) in the timed region' if getattr(args, 'gather_used', 'nccl') == 'fused' else 'NCCL broadcast(B)+all_gather(C) in the timed region' + (f', all-gather issued per row pass ({args.overlap} passes) from the row-pass hook' if args.overlap > 1 else '')) if world > 1 else 'BASELINE config 3, 1xB200' if not strong else 'BASELINE config 4 shape on 1 GPU'})",
                        "mode": _mode_text(plan) if fast
                                else "reference-order (bit exact, kc=126), integer-limb kernel",
                        "inputs": f"{args.dist}: full 113-bit random mantissas, device resident" if args.dist != "D53" else "D53: doubles U(-1,1) cast to quad (the reference's own benchmark distribution)",
@@ -502,10 +537,30 @@ def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_s
             "parity": {"checked_entries": ns * world, "mismatches": int(mism_t.item()), "against": against},
             "call_ms": call_ms, "extra": extra,
         }
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line (the JSON): everything any library prints to fd 1 (NCCL's version banner, ...) goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + "\n").encode())
 
 
 def main():
@@ -520,6 +575,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary qgemv/qdot/reference-order figures")
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
     ap.add_argument("--overlap", type=int, default=4, help="N > 1: row passes whose all-gathers overlap the next pass (1 = one all-gather after the qgemm)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: C blocks reach the other ranks by peer stores from the kernel that finishes them (fused) or by NCCL all-gather")
     ap.add_argument("--scheme", default=None, choices=["residues", "digits"], help="tensor path: residue planes + CRT (library default) or digit diagonals")
     ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 16)")
     args = ap.parse_args()
@@ -527,6 +583,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        _claim_stdout()
         reference_arm(args, rank, world)
         return
     if world == 1 and args.gpus > 1:
@@ -534,6 +591,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    _claim_stdout()
     own_arm(args, rank, world, local_rank)
 
 

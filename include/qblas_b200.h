@@ -134,6 +134,25 @@ double qb_oz_last_mma_ms(int *launches);
 int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp,
                      int64_t kb_begin, int64_t nkb, void *dD, int64_t Mp, int64_t Np, void *stream);
 
+/* ---- peer memory: fused gather of a row-sharded qgemm (one process per GPU) ----
+ * The reference has no multi-device code; BASELINE config 4 shards C by row blocks and gathers them.  Instead of a separate
+ * all-gather that re-reads and re-sends each block, the reconstruction kernel of the residue-scheme tensor path can store every
+ * finished element straight into the other GPUs' copies of C over NVLink:
+ *   qb_peer_alloc / qb_peer_free      device memory that can be exported to the other processes of the node
+ *   qb_peer_export / qb_peer_open     64-byte CUDA IPC handle of such a buffer / map a peer's buffer here (peer access is enabled)
+ *   qb_set_gemm_peer_outputs(c, ptrs) for the following qb_gemm_dev calls: ptrs[q] is the address, inside peer q's mapped
+ *                                     buffer, that corresponds to the C argument of the call (same strides); count 0 = off
+ *   qb_get_gemm_peer_written()        how many peers the LAST qb_gemm_dev wrote (0 when it ran a path without the fused
+ *                                     stores - digit diagonals, integer-limb kernel - so the caller must gather itself)
+ * Completion: the peers' copies are complete when the call's stream work has finished on EVERY rank (barrier after it). */
+void *qb_peer_alloc(size_t bytes);
+void qb_peer_free(void *p);
+int qb_peer_export(void *p, void *handle64);
+void *qb_peer_open(const void *handle64);
+int qb_peer_close(void *p);
+int qb_set_gemm_peer_outputs(int count, void *const *peer_C);
+int qb_get_gemm_peer_written(void);
+
 /* Quad-typed, host-or-device pointers, synchronous.  alpha/beta/result are HOST pointers to one
  * binary128 each.  Semantics = QuadBLAS::gemm/gemv/dot/axpy (level3.hpp:215, level2.hpp:85,
  * level1.hpp:80,190) and Vector::dot / Vector::norm (cpp_classes.hpp:66-81). */

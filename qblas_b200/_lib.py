@@ -66,6 +66,13 @@ def lib():
         "qb_set_tensor_keep": (None, [ci]),
         "qb_set_gemm_pass_callback": (None, [PASS_CB, vp, ci]),
         "qb_get_tensor_keep": (ci, []),
+        "qb_peer_alloc": (vp, [C.c_size_t]),
+        "qb_peer_free": (None, [vp]),
+        "qb_peer_export": (ci, [vp, vp]),
+        "qb_peer_open": (vp, [vp]),
+        "qb_peer_close": (ci, [vp]),
+        "qb_set_gemm_peer_outputs": (ci, [ci, C.POINTER(vp)]),
+        "qb_get_gemm_peer_written": (ci, []),
         "qb_set_tensor_scheme": (None, [ci]),
         "qb_get_tensor_scheme": (ci, []),
         "qb_set_fast_variant": (None, [ci]),

@@ -15,7 +15,7 @@ import ctypes as C
 import numpy as np
 
 from . import quad
-from ._lib import QbQuad, check, lib
+from ._lib import QbQuad, QblasError, check, lib
 
 MODE_REFERENCE = 0
 MODE_FAST = 1
@@ -259,6 +259,57 @@ def set_tensor_keep(keep):
 
 def get_tensor_keep():
     return lib().qb_get_tensor_keep()
+
+
+def set_gemm_peer_outputs(ptrs):
+    """Fused gather (qb_set_gemm_peer_outputs): ptrs[q] = address inside peer q's mapped buffer that corresponds to the C argument of the
+    following device qgemm calls; None / [] switches it off."""
+    ptrs = list(ptrs or [])
+    arr = (C.c_void_p * max(1, len(ptrs)))(*[C.c_void_p(int(p)) for p in ptrs])
+    check(lib().qb_set_gemm_peer_outputs(len(ptrs), arr), "qb_set_gemm_peer_outputs")
+
+
+def gemm_peer_written():
+    """Peers written by the last device qgemm (0: it ran a path without the fused stores)."""
+    return lib().qb_get_gemm_peer_written()
+
+
+class _CudaArray:
+    """__cuda_array_interface__ carrier so torch can view library-allocated device memory."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def peer_alloc(nbytes):
+    """(ptr, torch uint8 view) of exportable device memory (qb_peer_alloc); free with peer_free(ptr) after the views are gone."""
+    import torch
+    p = lib().qb_peer_alloc(int(nbytes))
+    if not p:
+        raise QblasError(f"qb_peer_alloc({nbytes}): {lib().qb_last_error().decode()}")
+    return int(p), torch.as_tensor(_CudaArray(p, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+
+
+def peer_free(ptr):
+    lib().qb_peer_free(C.c_void_p(int(ptr)))
+
+
+def peer_export(ptr):
+    h = (C.c_ubyte * 64)()
+    check(lib().qb_peer_export(C.c_void_p(int(ptr)), h), "qb_peer_export")
+    return bytes(h)
+
+
+def peer_open(handle):
+    buf = (C.c_ubyte * 64)(*handle)
+    p = lib().qb_peer_open(buf)
+    if not p:
+        raise QblasError(f"qb_peer_open: {lib().qb_last_error().decode()}")
+    return int(p)
+
+
+def peer_close(ptr):
+    check(lib().qb_peer_close(C.c_void_p(int(ptr))), "qb_peer_close")
 
 
 def set_tensor_scheme(scheme):

@@ -36,6 +36,9 @@ static std::atomic<int> g_honor_trans{0};
 static qb_pass_cb g_pass_cb = nullptr;
 static void *g_pass_user = nullptr;
 static int g_pass_min = 1;
+static int g_npeer = 0;                 /* fused gather of the next device qgemm (qb_set_gemm_peer_outputs); guarded by g_s.mu */
+static void *g_peer[QB_MAX_PEERS];
+static int g_peer_written = 0;
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
 int fast_variant() { return g_fastvar.load(); }
@@ -139,7 +142,7 @@ static inline size_t vec_bytes(int64_t n, int64_t inc) { return n <= 0 ? 0 : (si
 static inline size_t mat_bytes(int64_t outer, int64_t inner, int64_t ld) { return (outer <= 0 || inner <= 0) ? 0 : (size_t)((outer - 1) * ld + inner) * 16; }
 
 static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, int64_t k, q128 alpha, const void *dA,
-                         int64_t lda, const void *dB, int64_t ldb, q128 beta, void *dC, int64_t ldc, cudaStream_t st)
+                         int64_t lda, const void *dB, int64_t ldb, q128 beta, void *dC, int64_t ldc, cudaStream_t st, bool peers = false)
 {
   if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
   const bool col = is_col(layout);
@@ -161,10 +164,14 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
     cudaMemGetInfo(&fr, &tot);
     const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
     int used = 0;
+    g.npeer = peers ? g_npeer : 0;   /* only the device entry point (qb_gemm_dev) takes peer outputs */
+    for (int q = 0; q < g.npeer; ++q) g.peerC[q] = (q128 *)g_peer[q];
+    g_peer_written = 0;
     cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget, (oz_pass_cb)g_pass_cb, g_pass_user, g_pass_min);
     if (oe != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm tensor path", oe);
-    if (used) return QB_OK;
+    if (used) { g_peer_written = oz_last_stats().peer_written; return QB_OK; }
   }
+  g_peer_written = 0;
   cudaError_t e = launch_gemm(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm kernel launch", e);
   if (g_pass_cb && m > 0) g_pass_cb(0, m, g_pass_user);   /* the integer-limb kernel produces all rows in one launch */
@@ -217,6 +224,53 @@ void qb_set_tensor_scheme(int scheme)
   oz_set_scheme(scheme);
 }
 int qb_get_tensor_scheme(void) { return oz_get_scheme(); }
+
+/* ---- peer memory (fused gather of the row-sharded qgemm) ---- */
+void *qb_peer_alloc(size_t bytes)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  if (ensure_device()) return nullptr;
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) { fail(QB_ERR_ALLOC, "qb_peer_alloc", e); return nullptr; }
+  return p;
+}
+void qb_peer_free(void *p) { if (p) cudaFree(p); }
+int qb_peer_export(void *p, void *handle64)
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaIpcGetMemHandle", e);
+  memcpy(handle64, &h, 64);
+  return QB_OK;
+}
+void *qb_peer_open(const void *handle64)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  if (ensure_device()) return nullptr;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void *p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { fail(QB_ERR_CUDA, "cudaIpcOpenMemHandle", e); return nullptr; }
+  return p;
+}
+int qb_peer_close(void *p)
+{
+  cudaError_t e = cudaIpcCloseMemHandle(p);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaIpcCloseMemHandle", e);
+  return QB_OK;
+}
+int qb_set_gemm_peer_outputs(int count, void *const *peer_C)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  if (count < 0 || count > QB_MAX_PEERS || (count > 0 && !peer_C)) return fail(QB_ERR_ARG, "qb_set_gemm_peer_outputs: 0 <= count <= 8");
+  g_npeer = count;
+  for (int q = 0; q < count; ++q) g_peer[q] = peer_C[q];
+  return QB_OK;
+}
+int qb_get_gemm_peer_written(void) { return g_peer_written; }
 void qb_oz_last_stats(int64_t *out12)
 {
   const OzStats s = oz_last_stats();
@@ -293,7 +347,7 @@ int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int
                 const void *dA, int64_t lda, const void *dB, int64_t ldb, const qb_quad *beta, void *dC,
                 int64_t ldc, void *stream)
 {
-  return gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), dC, ldc, (cudaStream_t)stream);
+  return gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), dC, ldc, (cudaStream_t)stream, true);
 }
 
 int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,

@@ -14,6 +14,9 @@ struct GemmArgs {
   const q128 *B; int64_t sbl, sbj;   /* op(B)(l,j) = B[l*sbl + j*sbj] */
   q128 *C; int64_t sci, scj;         /* C(i,j)    = C[i*sci + j*scj] */
   int64_t kc;                        /* reference-order k-panel; >= k means a single chain */
+#define QB_MAX_PEERS 8
+  int npeer = 0;                     /* fused gather (residue-scheme tensor path only): C(i,j) is also stored to peerC[q][i*sci + j*scj] */
+  q128 *peerC[QB_MAX_PEERS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 cudaError_t launch_gemm(const GemmArgs &a, int mode, cudaStream_t st);
 
@@ -52,7 +55,7 @@ int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24
-struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; int scheme, WA, WB; };
+struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; int scheme, WA, WB; int peer_written; };
 /* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
 /* row-pass hook: when set, the C rows are produced in at least `min_passes` passes and cb(row0, rows, user) is called on the
  * host after the work of each pass has been ENQUEUED on the stream (so a collective issued from the callback overlaps the

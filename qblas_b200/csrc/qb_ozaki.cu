@@ -694,6 +694,7 @@ struct CrtFoldArgs {
   const int *emaxA, *emaxB; int WA, WB;
   q128 alpha, beta; q128 *C; int64_t sci, scj;
   int simple;                        /* alpha == 1 and beta == +-0 */
+  int npeer; q128 *peer[QB_MAX_PEERS]; /* fused gather: the same C block inside each peer GPU's buffer (NVLink peer stores) */
 };
 /* thread = 4 consecutive columns of one C row: one 32-bit load per residue plane, then per element the reconstruction
  * (crt::reconstruct), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109) */
@@ -724,8 +725,13 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
     const q128 cin = *c;
     /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
      * general line below, without the two software roundings */
-    if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) *c = sum;
-    else *c = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
+    q128 out;
+    if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) out = sum;
+    else out = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
+    *c = out;
+    /* fused all-gather: the finished element goes straight into every peer's copy of C (16-byte NVLink stores; the 4 elements
+     * of a thread are 64 contiguous bytes), so no separate collective has to re-read and re-send the block */
+    for (int q = 0; q < g.npeer; ++q) g.peer[q][i * g.sci + j * g.scj] = out;
   }
 }
 template <int NG>
@@ -1078,6 +1084,8 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
     f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
     f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
     f.simple = (a.alpha.hi == 0x3fff000000000000ULL && a.alpha.lo == 0 && (a.beta.hi & 0x7fffffffffffffffULL) == 0 && a.beta.lo == 0) ? 1 : 0;
+    f.npeer = a.npeer;
+    for (int q = 0; q < QB_MAX_PEERS; ++q) f.peer[q] = q < a.npeer ? a.peerC[q] + r0 * a.sci : nullptr;
     launch_crt_fold(f, pl, cs.sF);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1091,6 +1099,7 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
   g_last_stats.pairs = N; g_last_stats.keep = 0; g_last_stats.flagged = 0; g_last_stats.redo_passes = 0;
   g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
   g_last_stats.scheme = 1; g_last_stats.WA = WA; g_last_stats.WB = WB;
+  g_last_stats.peer_written = a.npeer;
   *used = 1;
   return cudaSuccess;
 }

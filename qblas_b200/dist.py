@@ -36,6 +36,34 @@ def _bytes(t: torch.Tensor) -> torch.Tensor:
     return t.view(torch.uint8)
 
 
+class PeerBuffer:
+    """One equally sized device buffer per rank, each mapped into every other rank's address space (CUDA IPC through the
+    library's qb_peer_* calls; all ranks on one NVLink node).  `tensor` is the local buffer as a torch uint8 tensor,
+    `ptrs[q]` the address of rank q's buffer as seen from this process (ptrs[rank] = the local one).  Collective."""
+
+    def __init__(self, nbytes, group=None):
+        from . import api
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nbytes = int(nbytes)
+        self.local_ptr, self.tensor = api.peer_alloc(self.nbytes)
+        mine = torch.tensor(list(api.peer_export(self.local_ptr)), dtype=torch.uint8, device=self.tensor.device)
+        handles = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(handles, mine, group=group)
+        self.ptrs = [self.local_ptr if q == self.rank else api.peer_open(bytes(handles[q].cpu().tolist())) for q in range(self.world)]
+
+    def close(self):
+        from . import api
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)          # nobody still writes into a buffer that is about to go
+        for q, p in enumerate(self.ptrs):
+            if q != self.rank:
+                api.peer_close(p)
+        self.ptrs = []
+        self.tensor = None
+        api.peer_free(self.local_ptr)
+
+
 class _CudaEngine:
     """Default per-rank engine: libqblas_b200.so on the current CUDA device."""
 
@@ -69,19 +97,51 @@ class _CudaEngine:
         api.fold_partials(count, partials, out, do_sqrt)
 
 
-def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1):
+def _gather_blocks(m, n, world, C_full, C_blk, group):
+    if m % world == 0:
+        dist.all_gather_into_tensor(_bytes(C_full), _bytes(C_blk), group=group)
+    else:  # ragged: one broadcast per owner (grouped broadcasts, SURVEY §8e)
+        for r in range(world):
+            l2, h2 = row_block(m, world, r)
+            if h2 > l2:
+                dist.broadcast(_bytes(C_full[l2 * n:h2 * n]), src=r, group=group)
+
+
+def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1, peers=None):
     """C_full (m x n, row-major, identical buffer shape on every rank) <- alpha*A*B + beta*C.
     A_blk holds this rank's rows [lo, hi) of A (row-major, lda = k); B (k x n) is valid on `src`
     and is overwritten by the broadcast elsewhere.  Returns (lo, hi).
 
     overlap_passes > 1 (even split only): the local block is produced in that many row passes and the all-gather of each
     pass's rows is issued from the library's row-pass hook as soon as that pass is enqueued, so it runs on NCCL's stream
-    while the next pass computes; only the last pass's gather is exposed.  Same bytes, same result."""
+    while the next pass computes; only the last pass's gather is exposed.  Same bytes, same result.
+
+    peers = a PeerBuffer whose local tensor IS C_full's storage (fused gather): the kernel that finishes the C elements stores
+    them into every peer's C_full over NVLink as well, no all-gather is issued, and a barrier makes the step complete.  If the
+    library ran a path without the fused stores (it reports 0 peers written) the NCCL all-gather is issued after all."""
     compute = compute or _CudaEngine()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = row_block(m, world, rank)
     dist.broadcast(_bytes(B), src=src, group=group)
     C_blk = C_full[lo * n:hi * n]
+    if peers is not None and world > 1:
+        from . import api
+        wrote = world - 1                                            # a rank without rows has nothing to deliver
+        if hi > lo:
+            others = [peers.ptrs[q] + lo * n * 16 for q in range(world) if q != rank]
+            api.set_gemm_peer_outputs(others)
+            try:
+                compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
+                wrote = api.gemm_peer_written()
+            finally:
+                api.set_gemm_peer_outputs(None)
+        # every rank must take the same branch: a rank whose planner declined makes all of them gather
+        flag = torch.tensor([1 if wrote == world - 1 else 0], dtype=torch.int32, device=C_full.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also the completion barrier of the peer stores
+        if int(flag.item()) == 1:
+            return lo, hi
+        _gather_blocks(m, n, world, C_full, C_blk, group)            # the blocks are computed; only the exchange is left
+        return lo, hi
     if m % world == 0 and overlap_passes > 1 and hi > lo:
         m_loc = hi - lo
         works = []
@@ -97,13 +157,7 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
         return lo, hi
     if hi > lo:
         compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
-    if m % world == 0:
-        dist.all_gather_into_tensor(_bytes(C_full), _bytes(C_blk), group=group)
-    else:  # ragged: one broadcast per owner (grouped broadcasts, SURVEY §8e)
-        for r in range(world):
-            l2, h2 = row_block(m, world, r)
-            if h2 > l2:
-                dist.broadcast(_bytes(C_full[l2 * n:h2 * n]), src=r, group=group)
+    _gather_blocks(m, n, world, C_full, C_blk, group)
     return lo, hi
 
 

@@ -45,6 +45,21 @@ def main():
             torch.cuda.synchronize()
             if not (to_host(Cf) == to_host(one)).all():
                 fails.append(("gemm overlapped vs 1-GPU", mode, m, n, k))
+        # fused gather: C lives in peer-mapped memory and the kernel that finishes the elements stores them into every rank's copy
+        # (fast-mode residue scheme); in reference order the library reports 0 peers written and the NCCL gather runs after all
+        pb = qd.PeerBuffer(m * n * 16)
+        Cp = pb.tensor.view(torch.int64).reshape(m * n, 2)
+        Cp.copy_(to_dev(C0.copy()))
+        Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize(); dist.barrier()
+        qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cp, peers=pb)
+        torch.cuda.synchronize()
+        if not (to_host(Cp) == to_host(one)).all():
+            fails.append(("gemm fused gather vs 1-GPU", mode, m, n, k, qb.gemm_peer_written()))
+        if mode == qb.MODE_FAST and hi - lo >= 128 and qb.gemm_peer_written() != world - 1:
+            fails.append(("fused gather did not run", mode, m, n, k, qb.gemm_peer_written()))
+        del Cp
+        pb.close()
         if mode == qb.MODE_REFERENCE:
             want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
             if not quad.same_bits(to_host(Cf), want).all():
