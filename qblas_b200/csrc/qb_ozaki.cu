@@ -694,51 +694,76 @@ struct CrtFoldArgs {
   const int *emaxA, *emaxB; int WA, WB;
   q128 alpha, beta; q128 *C; int64_t sci, scj;
   int simple;                        /* alpha == 1 and beta == +-0 */
+  int64_t n4p;                       /* threads per row: ceil(n / 4) rounded up to 32 */
   int npeer; q128 *peer[QB_MAX_PEERS]; /* fused gather: the same C block inside each peer GPU's buffer (NVLink peer stores) */
 };
 /* thread = 4 consecutive columns of one C row: one 32-bit load per residue plane, then per element the reconstruction
- * (crt::reconstruct), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109) */
+ * (crt::reconstruct_dev), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109).
+ * Threads per row are padded to a multiple of 32 (n4p), so a warp never straddles two rows.
+ * Fused gather (npeer > 0): the finished elements also go into every peer GPU's copy of C.  NVLink wants whole 128-byte lines, so
+ * the 4 x 32 elements of a warp are staged in shared memory (2 KB per warp, dynamic: none without peers) and leave as four
+ * 512-byte contiguous warp stores per peer instead of 16-byte pieces 64 bytes apart. */
 template <int NG>
 __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __grid_constant__ crt::Plan pl)
 {
-  const int64_t n4 = (g.n + 3) >> 2;
+  extern __shared__ uint4 fold_sm[];            /* [4 warps][128 elements] when npeer > 0 and C is row-major */
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = idx / n4, j0 = (idx % n4) * 4;
-  if (i >= g.m) return;
-  const int64_t plane = g.Mp * g.Np, off = i * g.Np + j0;
-  uint32_t rw[4 * NG];
+  const int64_t i = idx / g.n4p, jg = idx % g.n4p, j0 = jg * 4;
+  const bool valid = i < g.m && j0 < g.n;
+  const bool stage = g.npeer > 0 && g.scj == 1;
+  if (!valid && !stage) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (valid) {
+    const int64_t plane = g.Mp * g.Np, off = i * g.Np + j0;
+    uint32_t rw[4 * NG];
 #pragma unroll
-  for (int c = 0; c < 4 * NG; ++c) rw[c] = c < pl.N ? *reinterpret_cast<const uint32_t *>(g.R + (int64_t)c * plane + off) : 0u;
-  const int baseA = g.emaxA[g.row0 + i] + 113 - g.WA;
+    for (int c = 0; c < 4 * NG; ++c) rw[c] = c < pl.N ? *reinterpret_cast<const uint32_t *>(g.R + (int64_t)c * plane + off) : 0u;
+    const int baseA = g.emaxA[g.row0 + i] + 113 - g.WA;
 #pragma unroll 1
-  for (int e = 0; e < 4; ++e) {
-    const int64_t j = j0 + e;
-    if (j >= g.n) break;
-    uint32_t r[crt::NMP];
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = j0 + e;
+      if (j >= g.n) break;
+      uint32_t r[crt::NMP];
 #pragma unroll
-    for (int c = 0; c < 4 * NG; ++c) r[c] = (rw[c] >> (8 * e)) & 0xffu;
-    uint32_t Y[NG + 1], neg;
-    crt::reconstruct_dev<NG>(r, pl, Y, neg);
-    const int baseB = g.emaxB[j] + 113 - g.WB;
-    const q128 sum = crt_limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
-    q128 *c = g.C + i * g.sci + j * g.scj;
-    const q128 cin = *c;
-    /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
-     * general line below, without the two software roundings */
-    q128 out;
-    if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) out = sum;
-    else out = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
-    *c = out;
-    /* fused all-gather: the finished element goes straight into every peer's copy of C (16-byte NVLink stores; the 4 elements
-     * of a thread are 64 contiguous bytes), so no separate collective has to re-read and re-send the block */
-    for (int q = 0; q < g.npeer; ++q) g.peer[q][i * g.sci + j * g.scj] = out;
+      for (int c = 0; c < 4 * NG; ++c) r[c] = (rw[c] >> (8 * e)) & 0xffu;
+      uint32_t Y[NG + 1], neg;
+      crt::reconstruct_dev<NG>(r, pl, Y, neg);
+      const int baseB = g.emaxB[j] + 113 - g.WB;
+      const q128 sum = crt_limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
+      q128 *c = g.C + i * g.sci + j * g.scj;
+      const q128 cin = *c;
+      /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
+       * general line below, without the two software roundings */
+      q128 out;
+      if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) out = sum;
+      else out = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
+      *c = out;
+      if (stage) fold_sm[warp * 128 + 4 * lane + e] = make_uint4((uint32_t)out.lo, (uint32_t)(out.lo >> 32), (uint32_t)out.hi, (uint32_t)(out.hi >> 32));
+      else
+        for (int q = 0; q < g.npeer; ++q) g.peer[q][i * g.sci + j * g.scj] = out;   /* col-major C: element-wise peer stores */
+    }
+  }
+  if (stage) {
+    __syncwarp();
+    if (i < g.m) {
+      const int64_t jw = (jg - lane) * 4;       /* first column of the warp's 128 */
+#pragma unroll
+      for (int s4 = 0; s4 < 4; ++s4) {
+        const int64_t col = jw + 32 * s4 + lane;
+        if (col < g.n) {
+          const uint4 v = fold_sm[warp * 128 + 32 * s4 + lane];
+          for (int q = 0; q < g.npeer; ++q) *reinterpret_cast<uint4 *>(g.peer[q] + i * g.sci + col) = v;
+        }
+      }
+    }
   }
 }
 template <int NG>
 static void launch_crt_fold_ng(const CrtFoldArgs &f, const crt::Plan &pl, cudaStream_t st)
 {
-  const int64_t threads = f.m * ((f.n + 3) >> 2);
-  k_crt_fold<NG><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(f, pl);
+  const int64_t threads = f.m * f.n4p;
+  const size_t smem = (f.npeer > 0 && f.scj == 1) ? 4 * 128 * sizeof(uint4) : 0;
+  k_crt_fold<NG><<<(unsigned)((threads + 127) / 128), 128, smem, st>>>(f, pl);
 }
 static void launch_crt_fold(const CrtFoldArgs &f, const crt::Plan &pl, cudaStream_t st)
 {
@@ -1084,6 +1109,7 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
     f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
     f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
     f.simple = (a.alpha.hi == 0x3fff000000000000ULL && a.alpha.lo == 0 && (a.beta.hi & 0x7fffffffffffffffULL) == 0 && a.beta.lo == 0) ? 1 : 0;
+    f.n4p = rup((n + 3) / 4, 32);
     f.npeer = a.npeer;
     for (int q = 0; q < QB_MAX_PEERS; ++q) f.peer[q] = q < a.npeer ? a.peerC[q] + r0 * a.sci : nullptr;
     launch_crt_fold(f, pl, cs.sF);

@@ -25,7 +25,7 @@ def main():
     rng = np.random.default_rng(3)
     fails = []
     # ---- qgemm: reference order (bit exact vs oracle) and fast mode (tensor path; bitwise equal to the 1-GPU call)
-    for mode, (m, n, k) in ((qb.MODE_REFERENCE, (70, 33, 260)), (qb.MODE_REFERENCE, (37, 20, 127)), (qb.MODE_FAST, (512, 384, 640)), (qb.MODE_FAST, (301, 256, 300))):
+    for mode, (m, n, k) in ((qb.MODE_REFERENCE, (70, 33, 260)), (qb.MODE_REFERENCE, (37, 20, 127)), (qb.MODE_FAST, (1024, 384, 640)), (qb.MODE_FAST, (1031, 250, 300))):   # fast: every rank's block keeps >= 128 rows up to world 8 (tensor path)
         A = quad.random_quads(rng, m * k); B = quad.random_quads(rng, k * n); C0 = quad.random_quads(rng, m * n)
         alpha, beta = quad.random_quads(rng, 2)
         qb.set_mode(mode)
