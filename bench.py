@@ -6,10 +6,13 @@
 Own arm (default): one "step" = one quadblas qgemm of the workload, device resident:
     N = 1 : C(SxS) = A(SxS) B(SxS), row-major, alpha=1, beta=0, S=8192 (BASELINE config 3)
     N > 1 : BASELINE config 4 sharding at fixed per-GPU work (weak scaling): C is (N*S x S), rank r owns
-            the row block r; each step = NCCL broadcast of B (bytes) + local qgemm + NCCL all_gather of
-            the C blocks (bytes), all inside the timed region (max over ranks).
-  --mode fast (default): QB_MODE_FAST -> the tensor-core path (csrc/qb_ozaki.cu): exact int8 slicing, tcgen05
-            kind::i8 diagonal GEMMs, exact integer recombination, one rounding.  BASELINE config 3's
+            the row block r; each step = NCCL broadcast of B (bytes) + local qgemm + gather of the C blocks, all
+            inside the timed region (max over ranks).  --gather fused (default): the kernel that finishes the C
+            elements stores them into every rank's copy over NVLink peer memory (no collective; a 4-byte all-reduce
+            is the completion barrier); --gather nccl: NCCL all_gather (per row pass with --overlap P).
+  --mode fast (default): QB_MODE_FAST -> the tensor-core path (csrc/qb_crt.cuh + qb_ozaki.cu): exact int8 residue
+            planes, one tcgen05 kind::i8 GEMM per modulus, exact Chinese-remainder recombination, one rounding
+            (--scheme digits: the digit-diagonal scheme).  BASELINE config 3's
             "integer-limb vs Ozaki" comparison: the integer-limb reference-order kernel is timed in
             extra.qgemm_reference_order (and is the headline with --mode ref).
   `value` = binary128 GFLOP/s (2mnk flops, benchmarks/benchmark.cpp:199-202) of the whole job.
@@ -235,6 +238,29 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
                                                   "frac": 32.0 * nd / ms / 1e6 / hbm, "peak_source": src}}
         qb.quadblas_set_num_threads(0)
         del xd, yd
+        # BASELINE config 1 (the reference README's benchmark, 0.06 GFLOPS there): quadblas_qgemm 1000^3, doubles cast to quad, alpha=1 beta=0,
+        # through the reference-named C entry point with HOST buffers (synchronous, staging included) and device resident
+        import time
+        from gpu_util import to_host
+        Sc = 1000
+        A1 = dev_random((Sc * Sc,), "D53", 31, dev); B1 = dev_random((Sc * Sc,), "D53", 32, dev); C1 = dev_random((Sc * Sc,), "D53", 33, dev)
+        hA1, hB1, hC1 = to_host(A1), to_host(B1), to_host(C1)
+        for md, name in ((qb.MODE_FAST, "fast"), (qb.MODE_REFERENCE, "reference")):
+            qb.set_mode(md)
+            qb.gemm("R", Sc, Sc, Sc, 1.0, A1, Sc, B1, Sc, 0.0, C1, Sc)
+            ms = _time_events(lambda: qb.gemm("R", Sc, Sc, Sc, 1.0, A1, Sc, B1, Sc, 0.0, C1, Sc), reps)
+            qb.quadblas_qgemm("R", "N", "N", Sc, Sc, Sc, 1.0, hA1, Sc, hB1, Sc, 0.0, hC1, Sc)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                qb.quadblas_qgemm("R", "N", "N", Sc, Sc, Sc, 1.0, hA1, Sc, hB1, Sc, 0.0, hC1, Sc)
+            ms_host = (time.perf_counter() - t0) * 1e3 / reps
+            extra[f"qgemm_cfg1_1000_{name}"] = {
+                "workload": f"quadblas_qgemm('R','N','N',1000,1000,1000, 1.0, A,1000, B,1000, 0.0, C,1000), doubles U(-1,1) cast to quad ({name} mode)",
+                "device_resident": {"ms": ms, "gflops": 2.0 * Sc ** 3 / ms / 1e6},
+                "host_buffers_c_abi": {"ms": ms_host, "gflops": 2.0 * Sc ** 3 / ms_host / 1e6, "note": "pageable numpy buffers, staging copies included, wall clock"},
+                "plan": qb.oz_last_stats() if md == qb.MODE_FAST else None,
+                "reference_readme_gflops": 0.06}
+        del A1, B1, C1
     except Exception as e:  # secondary figures must never take the headline down
         extra["error"] = repr(e)
     qb.set_mode(mode)
@@ -367,6 +393,13 @@ def own_arm(args, rank, world, local_rank):
     sync()
     if fused["on"]:
         qb.set_gemm_peer_outputs(None)    # nothing after the timed region may write into the peers
+    # every rank must now hold every rank's block: compare per-block checksums of the local C_full with the owners' own
+    args.gather_bad = 0
+    if world > 1:
+        sums = Cfull.view(torch.int64).reshape(world, -1).sum(dim=1)            # wrapping int64 sums, one per block
+        owners = [torch.empty(1, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(owners, sums[rank:rank + 1].clone())
+        args.gather_bad = int((sums != torch.cat(owners)).sum().item())
     launches = qb.launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     ms_total = ev0.elapsed_time(ev1)
@@ -509,7 +542,7 @@ def _mode_text(plan):
 
 def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_step, M, n, k, m_loc, e2e, launches, clk, roof, cpu, ns, mism, against,
                 call_ms, extra, strong):
-    mism_t = torch.tensor([mism], dtype=torch.int64, device=dev)
+    mism_t = torch.tensor([mism, getattr(args, "gather_bad", 0)], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(mism_t)
 
@@ -534,7 +567,8 @@ def _print_line(args, rank, world, dist, torch, dev, qb, mode, plan, value, ms_s
                        "inputs": f"{args.dist}: full 113-bit random mantissas, device resident" if args.dist != "D53" else "D53: doubles U(-1,1) cast to quad (the reference's own benchmark distribution)",
                        "l2": "inputs (3 x 1 GiB at 8192^3) and the int8 planes (GBs) exceed the 126 MB L2; no flush needed", "parallelism": f"row-block x{world}"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "parity": {"checked_entries": ns * world, "mismatches": int(mism_t.item()), "against": against},
+            "parity": {"checked_entries": ns * world, "mismatches": int(mism_t[0].item()), "against": against,
+                       "gathered_blocks_checked": world * world if world > 1 else 0, "gathered_blocks_wrong": int(mism_t[1].item())},
             "call_ms": call_ms, "extra": extra,
         }
         _emit(json.dumps(line))

@@ -57,6 +57,7 @@ struct Tables {
   uint32_t off[NMP];    /* p*ceil(2^30/p): makes an int32 accumulator (|v| <= 2^30) non-negative, == 0 mod p */
   uint32_t finv[NMP];   /* floor(2^32/p): umulhi(u, finv) in {floor(u/p)-1, floor(u/p)} for u < 2^32 */
   uint32_t pw[NWMAX][NMP]; /* byte b of pw[j][i] = 256^(4j+b) mod p_i  (dp4a against the words of |X|) */
+  uint32_t seedn[NWMAX][NMP]; /* seed of a negative element with NW = index + 1 words: half + ((-2^(32 NW)) mod p) */
 };
 
 /* per-N constants of the reconstruction (kernel parameter) */
@@ -101,19 +102,39 @@ QCRT_HD uint64_t mul64hi_u(uint64_t a, uint64_t b)
 }
 
 /* ------------------------------------------------------------------ residues */
-/* int8 residue (as the low byte) of (-1)^sign * X modulo p_i, X = sum_{j<NW} w[j] 2^(32 j); branch-free.
- * acc <= half + 24*255*255 < 2^21; a negative X turns it into cneg - acc in (0, 2^22); floor division exact (Tables). */
+/* Residue of (-1)^sign * X modulo p_i as r in [0, p) with r - half_i the symmetric int8 residue; X = sum_{j<NW} w[j] 2^(32 j).
+ * The caller passes the words of |X| for sign = 0 and of 2^(32 NW) - |X| (two's complement, once per element) for sign = 1;
+ * the seed then carries c2 = (-2^(32 NW)) mod p_i, so that no per-modulus negation is needed.  Branch-free:
+ * acc <= half + p + 24*255*255 < 2^21, and umulhi(acc, ceil(2^32/p)) is the exact quotient for acc < 2^22 (Tables). */
+template <int NW>
+QCRT_HD uint32_t residue_sym(const uint32_t (&w)[NWMAX], uint32_t sign, int i, const Tables &T)
+{
+  uint32_t acc = sign ? T.seedn[NW - 1][i] : T.half[i];
+QCRT_UNROLL
+  for (int j = 0; j < NW; ++j) acc = dp4a_u(w[j], T.pw[j][i], acc);
+  const uint32_t q = mulhi_u(acc, T.minv[i]);
+  return acc - (q * T.p[i] + T.half[i]);        /* symmetric residue in [-half, p-1-half]; the low byte is the int8 */
+}
+/* in place: the NW words of 2^(32 NW) - X */
+template <int NW>
+QCRT_HD void negate_words(uint32_t (&w)[NWMAX])
+{
+  uint32_t carry = 1;
+QCRT_UNROLL
+  for (int j = 0; j < NW; ++j) { const uint32_t t = ~w[j] + carry; carry = (carry && t == 0) ? 1u : 0u; w[j] = t; }
+}
+/* int8 residue (as the low byte) of (-1)^sign * X from the words of |X| (one element at a time: tests, reference form) */
 template <int NW>
 QCRT_HD uint32_t residue_byte(const uint32_t (&w)[NWMAX], uint32_t sign, int i, const Tables &T)
 {
-  uint32_t acc = T.half[i];
+  uint32_t v[NWMAX];
 QCRT_UNROLL
-  for (int j = 0; j < NW; ++j) acc = dp4a_u(w[j], T.pw[j][i], acc);
-  const uint32_t m = 0u - sign;                 /* all ones for a negative X */
-  acc = acc * (1u + 2u * m) + (T.cneg[i] & m);  /* sign ? cneg - acc : acc */
-  const uint32_t q = mulhi_u(acc, T.minv[i]);
-  const uint32_t r = acc - q * T.p[i];          /* (+-X + half) mod p in [0, p) */
-  return (r - T.half[i]) & 0xffu;               /* symmetric residue in [-half, p-1-half] as int8 */
+  for (int j = 0; j < NWMAX; ++j) v[j] = w[j];
+  bool zero = true;
+QCRT_UNROLL
+  for (int j = 0; j < NW; ++j) zero = zero && v[j] == 0;
+  if (sign && !zero) negate_words<NW>(v);
+  return residue_sym<NW>(v, (sign && !zero) ? 1u : 0u, i, T) & 0xffu;
 }
 
 /* what the tensor kernel's epilogue does with one int32 accumulator v (|v| <= 2^30): v mod p_i in [0, p) */
@@ -328,6 +349,8 @@ static inline void build_tables(Tables &T)
       uint32_t word = 0;
       for (int b = 0; b < 4; ++b) { word |= pw << (8 * b); pw = (pw * 256u) % p; }
       T.pw[j][i] = i < NM ? word : 0u;
+      /* after the loop body above pw == 256^(4(j+1)) mod p == 2^(32 (j+1)) mod p */
+      T.seedn[j][i] = T.half[i] + (p - pw % p) % p;
     }
   }
 }

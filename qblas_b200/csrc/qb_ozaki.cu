@@ -64,6 +64,7 @@ static constexpr int OZ_THREADS = 192;       /* warp 0: TMA producer, warp 1: MM
 static constexpr int OZ_MAX_S = QB_OZ_MAX_SLICES;
 static constexpr int OZ_MAX_DIAG = 2 * OZ_MAX_S - 1;
 static constexpr int OZ_NL = 14;             /* 32-bit limbs of the exact integer (448 bits) */
+static constexpr int OZ_SCAN_CH = 256;       /* k per scan work item: 8192^2 gives 262k warps / threads, enough loads in flight for HBM */
 
 struct OzMmaArgs {
   int32_t *D;                 /* [ndiag][Mp][Np] int32 */
@@ -262,11 +263,11 @@ __device__ __forceinline__ OzElem oz_unpack(q128 a)
 __device__ __forceinline__ int oz_tz(uint64_t lo, uint64_t hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
 
 /* rows x K view: X[r * sr + k * sk].  emax[r] = max ee over non-zero elements (0 if none),
- * lmin[r] = min (ee + tz(M)); flags |= 1 on Inf/NaN.  One warp per (row, 1024-wide k chunk) when k
+ * lmin[r] = min (ee + tz(M)); flags |= 1 on Inf/NaN.  One warp per (row, OZ_SCAN_CH-wide k chunk) when k
  * is the contiguous direction, otherwise one thread per (row, chunk) with lanes along rows. */
 __global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, int *emax, int *lmin, int *flags)
 {
-  constexpr int CH = 1024;
+  constexpr int CH = OZ_SCAN_CH;
   const int64_t nchunk = (K + CH - 1) / CH;
   int em = 0, lm = 0x7fffffff, sp = 0;
   int64_t r;
@@ -567,6 +568,7 @@ __global__ void __launch_bounds__(128) k_oz_fixup(const OzFixArgs g)
 /* ================================================================== residue scheme (qb_crt.cuh) */
 /* The 4 elements (row r, k = 4 g4 .. 4 g4 + 3) as words of |X| and signs, X = x / 2^(base - 16495) an exact integer below 2^W. */
 struct Crt4 { uint32_t w[4][crt::NWMAX]; uint32_t sign[4]; };
+template <int NW>
 __device__ __forceinline__ void crt_load4(const q128 *__restrict__ X, int64_t r, int64_t g4, int64_t K, int64_t sr, int64_t sk, int base, Crt4 &c)
 {
 #pragma unroll
@@ -585,16 +587,17 @@ __device__ __forceinline__ void crt_load4(const q128 *__restrict__ X, int64_t r,
     c.w[q][2] = (uint32_t)v.w1; c.w[q][3] = (uint32_t)(v.w1 >> 32);
     c.w[q][4] = (uint32_t)v.w2; c.w[q][5] = (uint32_t)(v.w2 >> 32);
     c.sign[q] = e.sign;
+    if (e.sign) crt::negate_words<NW>(c.w[q]);   /* non-zero here: 2^(32 NW) - |X|, the seed of residue_sym carries the rest */
   }
 }
 /* residues of the 4 elements modulo p_i packed as 4 int8 (byte q = element q) */
 template <int NW>
 __device__ __forceinline__ uint32_t crt_word(const Crt4 &c, int i)
 {
-  uint32_t word = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) word |= crt::residue_byte<NW>(c.w[q], c.sign[q], i, c_crt) << (8 * q);
-  return word;
+  /* the elements arrive with negative ones already in two's complement (crt_load4<NW>) */
+  const uint32_t r0 = crt::residue_sym<NW>(c.w[0], c.sign[0], i, c_crt), r1 = crt::residue_sym<NW>(c.w[1], c.sign[1], i, c_crt);
+  const uint32_t r2 = crt::residue_sym<NW>(c.w[2], c.sign[2], i, c_crt), r3 = crt::residue_sym<NW>(c.w[3], c.sign[3], i, c_crt);
+  return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);   /* low bytes of r0..r3 */
 }
 
 /* k contiguous (or fully strided): thread = (row, 4 consecutive k); plane i is [rows][Kp] int8 */
@@ -607,7 +610,7 @@ __global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X
   if (tid >= rows * groups) return;
   const int64_t r = tid / groups, g4 = tid % groups;
   Crt4 c;
-  crt_load4(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
+  crt_load4<NW>(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
 #pragma unroll
   for (int g = 0; g < crt::NGMAX; ++g) {
     if (4 * g < N) {
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(256) k_crt_residues_t(const q128 *__restrict__
   const int64_t r = r0 + lane, g4 = g0 + wg;
   if (r < rows) {
     Crt4 c;
-    crt_load4(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
+    crt_load4<NW>(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
 #pragma unroll
     for (int g = 0; g < crt::NGMAX; ++g) {
       if (4 * g < N) {
@@ -1149,7 +1152,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     cudaMemsetAsync(emaxA, 0, (size_t)m * 4, st); cudaMemsetAsync(lminA, 0x7f, (size_t)m * 4, st);
     cudaMemsetAsync(emaxB, 0, (size_t)n * 4, st); cudaMemsetAsync(lminB, 0x7f, (size_t)n * 4, st);
     cudaMemsetAsync(flags, 0, 64, st);
-    const int64_t nch = (k + 1023) / 1024;
+    const int64_t nch = (k + OZ_SCAN_CH - 1) / OZ_SCAN_CH;
     {
       const bool warp_mode = (a.sal == 1 || a.sai != 1);
       const int64_t threads = warp_mode ? m * nch * 32 : m * nch;

@@ -333,3 +333,46 @@ def test_residue_scheme_zero_operand(qb, oracle):
         qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
     assert st["scheme"] == "residues", st
     assert quad.same_bits(to_host(dC), want).all()
+
+
+# ------------------------------------------------------------------ fused gather (qb_set_gemm_peer_outputs): single-GPU check of the store path
+@pytest.mark.parametrize("layout,m,n,k", [("R", 200, 250, 300), ("R", 130, 1024, 257), ("C", 140, 130, 260)])
+def test_residue_scheme_peer_outputs_mirror_C(qb, oracle, layout, m, n, k):
+    """The reconstruction kernel also stores every finished element into the 'peer' copies of C.  On one GPU the peers are simply two
+    more buffers of the same device: they must receive exactly the m x n block (same bits as C, padding untouched), through the
+    staged 512-byte warp stores for row-major C (ragged n % 4 and n % 128 edges) and the element-wise stores for col-major C."""
+    rng = np.random.default_rng(m + n)
+    ar, ac = (m, k) if layout == "R" else (k, m)
+    br, bc = (k, n) if layout == "R" else (n, k)
+    cr, cc = (m, n) if layout == "R" else (n, m)
+    lda, ldb, ldc = ac + 1, bc + 2, cc + 5
+    A = qgen.matrix(rng, ar, ac, "D113", lda); B = qgen.matrix(rng, br, bc, "D113", ldb); C0 = qgen.matrix(rng, cr, cc, "D113", ldc)
+    alpha, beta = quad.random_quads(rng, 2)
+    sentinel = qgen.matrix(rng, cr, cc, "D113", ldc)
+    dC = to_dev(C0); P1 = to_dev(sentinel.copy()); P2 = to_dev(sentinel.copy())
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
+    try:
+        qb.set_gemm_peer_outputs([P1.data_ptr(), P2.data_ptr()])
+        qb.gemm(layout, m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
+        torch.cuda.synchronize()
+        wrote = qb.gemm_peer_written()
+        # reference order has no fused stores: reports 0 and leaves the peers alone
+        qb.set_mode(qb.MODE_REFERENCE)
+        P3 = to_dev(sentinel.copy())
+        qb.set_gemm_peer_outputs([P3.data_ptr()])
+        qb.gemm(layout, 8, 8, 8, alpha, to_dev(A), lda, to_dev(B), ldb, beta, to_dev(C0), ldc)
+        torch.cuda.synchronize()
+        wrote_ref = qb.gemm_peer_written()
+    finally:
+        qb.set_gemm_peer_outputs(None)
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert wrote == 2 and wrote_ref == 0
+    got = to_host(dC)
+    idx = np.array([[(i * ldc + j) if layout == "R" else (j * ldc + i) for j in range(n)] for i in range(m)]).reshape(-1)
+    mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False
+    for P in (P1, P2):
+        p = to_host(P)
+        assert (p[idx] == got[idx]).all(), "peer copy differs from C"
+        assert (p[mask] == sentinel[mask]).all(), "peer padding was touched"
+    assert (to_host(P3) == sentinel).all()
+    assert (got[mask] == C0[mask]).all()
