@@ -310,6 +310,7 @@ def own_arm(args, rank, world, local_rank):
             Cp = peerbuf.tensor.view(torch.int64).reshape(M * n, 2)
             Cp.copy_(Cfull)
             Cfull = Cp
+            torch.cuda.empty_cache()     # hand the first copy back to the driver: the library sizes its workspace from cudaMemGetInfo
         except Exception as e:   # no peer access on this box: NCCL gather
             print(f"[bench] fused gather unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr, flush=True)
             peerbuf = None
