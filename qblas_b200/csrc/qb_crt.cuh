@@ -218,11 +218,14 @@ QCRT_UNROLL
 
 
 /* ------------------------------------------------------------------ reconstruction, device form */
-#if defined(__CUDACC__)
-/* Same result as reconstruct<NG>() (the tested reference form above), written on PTX carry chains: the products t * M_g
+#if defined(__CUDACC__) || defined(QCRT_HOST_EMULATE_PTX)
+/* Same result as reconstruct<NG>() (the reference form above), written on PTX carry chains: the products t * M_g
  * go into an even-column and an odd-column accumulator as mad.lo.cc / madc.hi.cc pairs (ptxas fuses each pair into one
- * IMAD.WIDE with carry), the group digit t_g uses a 32-bit reciprocal of the normalised group modulus. */
+ * IMAD.WIDE with carry), the group digit t_g uses a 32-bit reciprocal of the normalised group modulus.
+ * tests/host/crt_host.cpp defines QCRT_HOST_EMULATE_PTX: the same source then runs on the CPU with the carry flag emulated
+ * (one flag per thread), so every group count NG = 1..13 of this form is checked against Python integers without a GPU. */
 namespace ptx {
+#if defined(__CUDACC__)
 #define QCRT_DI __device__ __forceinline__
 QCRT_DI uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 QCRT_DI uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -234,6 +237,24 @@ QCRT_DI uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u
 QCRT_DI uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 QCRT_DI uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 QCRT_DI uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+#else
+#define QCRT_DI static inline
+static thread_local uint32_t cc_cf = 0;   /* CC.CF: carry out of add / mad, borrow out of sub */
+QCRT_DI uint32_t lo32(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b); }
+QCRT_DI uint32_t hi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+QCRT_DI uint32_t add3(uint32_t a, uint32_t b, uint32_t cin, bool set) { const uint64_t t = (uint64_t)a + b + cin; if (set) cc_cf = (uint32_t)(t >> 32); return (uint32_t)t; }
+QCRT_DI uint32_t sub3(uint32_t a, uint32_t b, uint32_t bin, bool set) { const uint64_t t = (uint64_t)a - b - bin; if (set) cc_cf = (uint32_t)(t >> 63); return (uint32_t)t; }
+QCRT_DI uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(lo32(a, b), c, 0, true); }
+QCRT_DI uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(lo32(a, b), c, cc_cf, true); }
+QCRT_DI uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add3(hi32(a, b), c, cc_cf, true); }
+QCRT_DI uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return add3(hi32(a, b), c, cc_cf, false); }
+QCRT_DI uint32_t add_cc(uint32_t a, uint32_t b) { return add3(a, b, 0, true); }
+QCRT_DI uint32_t addc_cc(uint32_t a, uint32_t b) { return add3(a, b, cc_cf, true); }
+QCRT_DI uint32_t addc(uint32_t a, uint32_t b) { return add3(a, b, cc_cf, false); }
+QCRT_DI uint32_t sub_cc(uint32_t a, uint32_t b) { return sub3(a, b, 0, true); }
+QCRT_DI uint32_t subc_cc(uint32_t a, uint32_t b) { return sub3(a, b, cc_cf, true); }
+QCRT_DI uint32_t subc(uint32_t a, uint32_t b) { return sub3(a, b, cc_cf, false); }
+#endif
 
 /* acc (NL limbs, even or odd columns only) += t * m[l] for l = L0, L0 + 2, ... < NM; carries stay inside NL limbs */
 template <int NL, int NMUL, int L0>
@@ -243,34 +264,34 @@ QCRT_DI void mad_columns(uint32_t (&acc)[NL], uint32_t t, const uint32_t *m)
   acc[L0] = mad_lo_cc(t, m[L0], acc[L0]);
   acc[L0 + 1] = madc_hi_cc(t, m[L0], acc[L0 + 1]);
   int last = L0 + 1;
-#pragma unroll
+QCRT_UNROLL
   for (int l = L0 + 2; l < NMUL; l += 2) {
     acc[l] = madc_lo_cc(t, m[l], acc[l]);
     acc[l + 1] = madc_hi_cc(t, m[l], acc[l + 1]);
     last = l + 1;
   }
-#pragma unroll
+QCRT_UNROLL
   for (int l = 0; l < NL; ++l)
     if (l > last) acc[l] = (l == NL - 1) ? addc(acc[l], 0u) : addc_cc(acc[l], 0u);
 }
 } // namespace ptx
 
 template <int NG>
-__device__ __forceinline__ void reconstruct_dev(const uint32_t (&r)[NMP], const Plan &pl, uint32_t (&Y)[NG + 1], uint32_t &neg)
+QCRT_DI void reconstruct_dev(const uint32_t (&r)[NMP], const Plan &pl, uint32_t (&Y)[NG + 1], uint32_t &neg)
 {
   constexpr int NL = NG + 1;
   uint32_t E[NL], O[NL];
-#pragma unroll
+QCRT_UNROLL
   for (int l = 0; l < NL; ++l) { E[l] = 0; O[l] = 0; }
   uint32_t s0 = 0, s1 = 0, s2 = 0;          /* S = sum t_g f_g (96 bits) */
-#pragma unroll
+QCRT_UNROLL
   for (int g = 0; g < NG; ++g) {
     uint64_t v = 0;
-#pragma unroll
+QCRT_UNROLL
     for (int b = 0; b < 4; ++b) v += (uint64_t)r[4 * g + b] * pl.cp[4 * g + b];   /* cp = 0 beyond N */
     /* t = v mod G: quotient (< 2^10) from the top 31 bits of v 2^sh and a 32-bit reciprocal of G 2^sh in [2^31, 2^32) */
     const uint32_t a = (uint32_t)(v >> pl.gshr[g]) << pl.gshl[g];  /* (v << sh) >> 11 < 2^31 */
-    const uint32_t qh = __umulhi(a, pl.ginv[g]) >> 20;             /* floor(v / G) or one less */
+    const uint32_t qh = mulhi_u(a, pl.ginv[g]) >> 20;               /* floor(v / G) or one less */
     uint64_t t64 = v - (uint64_t)qh * pl.G[g];
     if (t64 >= pl.G[g]) t64 -= pl.G[g];
     const uint32_t t = (uint32_t)t64;
@@ -282,42 +303,42 @@ __device__ __forceinline__ void reconstruct_dev(const uint32_t (&r)[NMP], const 
   /* Y = E + O - qhat P  in [0, 2P) */
   {
     uint32_t QE[NL], QO[NL];
-#pragma unroll
+QCRT_UNROLL
     for (int l = 0; l < NL; ++l) { QE[l] = 0; QO[l] = 0; }
     ptx::mad_columns<NL, NG, 0>(QE, s2, pl.P);
     ptx::mad_columns<NL, NG, 1>(QO, s2, pl.P);
     Y[0] = ptx::add_cc(E[0], O[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::addc(E[l], O[l]) : ptx::addc_cc(E[l], O[l]);
     Y[0] = ptx::sub_cc(Y[0], QE[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::subc(Y[l], QE[l]) : ptx::subc_cc(Y[l], QE[l]);
     Y[0] = ptx::sub_cc(Y[0], QO[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) Y[l] = (l == NL - 1) ? ptx::subc(Y[l], QO[l]) : ptx::subc_cc(Y[l], QO[l]);
   }
   /* Y >= P: subtract P once */
   {
     uint32_t T[NL];
     T[0] = ptx::sub_cc(Y[0], pl.P[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) T[l] = ptx::subc_cc(Y[l], pl.P[l]);
     const uint32_t below = ptx::subc(0u, 0u);   /* all ones when Y < P */
-#pragma unroll
+QCRT_UNROLL
     for (int l = 0; l < NL; ++l) Y[l] = below ? Y[l] : T[l];
   }
   /* |I| = min(Y, P - Y); negative when P - Y is the smaller one (Y = P/2 cannot happen: |I| < P/2) */
   {
     uint32_t U[NL];
     U[0] = ptx::sub_cc(pl.P[0], Y[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) U[l] = (l == NL - 1) ? ptx::subc(pl.P[l], Y[l]) : ptx::subc_cc(pl.P[l], Y[l]);
     (void)ptx::sub_cc(U[0], Y[0]);
-#pragma unroll
+QCRT_UNROLL
     for (int l = 1; l < NL; ++l) (void)ptx::subc_cc(U[l], Y[l]);
     const uint32_t u_below = ptx::subc(0u, 0u); /* all ones when U < Y */
     neg = u_below ? 1u : 0u;
-#pragma unroll
+QCRT_UNROLL
     for (int l = 0; l < NL; ++l) Y[l] = u_below ? U[l] : Y[l];
   }
 }

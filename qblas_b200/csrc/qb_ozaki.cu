@@ -1,6 +1,13 @@
 /*
  * qb_ozaki.cu — fast-mode binary128 GEMM on the 5th-generation tensor cores.
  *
+ * Two schemes share the scan / plan step and the tcgen05 kernel of this file:
+ *   residues (default, qb_set_tensor_scheme(1)): one int8 GEMM per modulus + Chinese-remainder fold, always exact; the
+ *            arithmetic is in qb_crt.cuh, the kernels (k_crt_residues*, k_oz_mma<1>, k_crt_fold) and the stream-pipelined
+ *            driver (launch_gemm_crt) are in the section "residue scheme" below;
+ *   digit diagonals (qb_set_tensor_scheme(0), and the fallback when the moduli cannot cover the operands' bit span):
+ *            described next.
+ *
  * What it replaces: the arithmetic of QuadBLAS::gemm (/root/reference/include/quadblas/algorithms/
  * level3.hpp:215-336; hot loop :77-85 = one Sleef_fmaq2_u05 per two products) when the library is
  * in QB_MODE_FAST.  Fast mode is free to re-associate (last paragraph); this

@@ -1,6 +1,7 @@
 // g++ build of qblas_b200/csrc/qb_crt.cuh (host/device dual source) for tests/test_host_crt.py: the
 // residue, accumulator-reduction and reconstruction arithmetic of the tensor-path qgemm, checked
 // against Python integers.  Test infrastructure only.
+#define QCRT_HOST_EMULATE_PTX 1   // compile the device form of the reconstruction too, carry flag emulated
 #include "../../qblas_b200/csrc/qb_crt.cuh"
 using namespace qb::crt;
 
@@ -8,14 +9,17 @@ static Tables g_T;
 static bool g_have = false;
 static const Tables &tab() { if (!g_have) { host::build_tables(g_T); g_have = true; } return g_T; }
 
+static int g_form = 0;   // 0: reconstruct (reference form), 1: reconstruct_dev (the kernel's carry-chain form)
 template <int NG> static void rec(const uint32_t (&r)[NMP], const Plan &pl, uint32_t *mag, uint32_t *neg)
 {
   uint32_t Y[NG + 1];
-  reconstruct<NG>(r, pl, Y, *neg);
+  if (g_form) reconstruct_dev<NG>(r, pl, Y, *neg);
+  else reconstruct<NG>(r, pl, Y, *neg);
   for (int l = 0; l < NLMAX; ++l) mag[l] = l < NG + 1 ? Y[l] : 0;
 }
 
 extern "C" {
+void crt_set_form(int dev_form) { g_form = dev_form ? 1 : 0; }
 int crt_num_moduli(void) { return NM; }
 int crt_modulus(int i) { return MODULI[i]; }
 int crt_moduli_for_bits(int bits) { return host::moduli_for_bits(bits); }

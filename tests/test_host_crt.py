@@ -23,6 +23,7 @@ def lib(tmp_path_factory):
     L.crt_plan_bits.restype = C.c_double
     L.crt_residues.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.crt_fold.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.crt_set_form.argtypes = [C.c_int]
     return L
 
 
@@ -118,3 +119,46 @@ def test_accumulator_reduction_range(lib):
     for c, v in enumerate(vals):
         got = sum(int(mag[c, l]) << (32 * l) for l in range(14))
         assert (-got if neg[c] else got) == v
+
+
+@pytest.mark.parametrize("form", [0, 1], ids=["reference-form", "kernel-form"])
+def test_reconstruction_every_moduli_count(lib, form):
+    """Every N = 1..49 (group counts 1..13, full and partial last groups): integers spread over (-P/2, P/2), including the
+    extremes, are recovered exactly from their residues - by the reference form and by the kernel's carry-chain form
+    (crt::reconstruct_dev, compiled here with the PTX carry flag emulated)."""
+    rnd = random.Random(1234 + form)
+    m_all = _moduli(lib)
+    lib.crt_set_form(form)
+    try:
+        for N in range(1, len(m_all) + 1):
+            m = m_all[:N]
+            P = 1
+            for p in m:
+                P *= p
+            half = (P - 1) // 2            # |I| < P/2 strictly (P is even: 256 is always among the moduli)
+            vals = [0, 1, -1, half, -half, half - 1, 1 - half] + [rnd.randrange(-half, half + 1) for _ in range(40)] + \
+                   [rnd.randrange(-(2 ** b), 2 ** b) for b in range(1, max(2, half.bit_length() - 1), 7)]
+            # accumulators: any int32 congruent to the value (the tensor kernel hands over sums of products, not residues)
+            acc = np.zeros((len(vals), N), dtype=np.int32)
+            for c, v in enumerate(vals):
+                for i, p in enumerate(m):
+                    r = v % p
+                    kmax = (2 ** 30 - r) // p
+                    acc[c, i] = r + p * rnd.randrange(-kmax, kmax + 1) if c % 2 else r
+            mag = np.zeros((len(vals), 14), dtype=np.uint32); neg = np.zeros(len(vals), dtype=np.uint32)
+            lib.crt_fold(len(vals), acc.ctypes.data, N, mag.ctypes.data, neg.ctypes.data)
+            for c, v in enumerate(vals):
+                got = sum(int(mag[c, l]) << (32 * l) for l in range(14))
+                assert (-got if neg[c] else got) == v, (N, c, v)
+    finally:
+        lib.crt_set_form(0)
+
+
+def test_inner_products_through_kernel_form(lib):
+    """The exact-inner-product check of above, with the kernel's form of the reconstruction."""
+    lib.crt_set_form(1)
+    try:
+        for WA, WB, k in [(139, 139, 64), (54, 54, 128), (24, 24, 40), (80, 11, 300), (7, 5, 1000)]:
+            test_inner_product_reconstruction_exact(lib, WA, WB, k)
+    finally:
+        lib.crt_set_form(0)
