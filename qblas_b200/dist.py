@@ -39,29 +39,71 @@ def _bytes(t: torch.Tensor) -> torch.Tensor:
 class PeerBuffer:
     """One equally sized device buffer per rank, each mapped into every other rank's address space (CUDA IPC through the
     library's qb_peer_* calls; all ranks on one NVLink node).  `tensor` is the local buffer as a torch uint8 tensor,
-    `ptrs[q]` the address of rank q's buffer as seen from this process (ptrs[rank] = the local one).  Collective."""
+    `ptrs[q]` the address of rank q's buffer as seen from this process (ptrs[rank] = the local one).
 
-    def __init__(self, nbytes, group=None):
-        from . import api
-        self.group = group
+    Collective, and failures are collective too: if the allocation, the export or the mapping fails on ANY rank, every
+    rank releases what it holds and raises RuntimeError, so that all of them fall back to the NCCL gather together
+    (a rank that left alone would leave the others waiting in a collective).
+
+    `mem` is the memory backend (default: qblas_b200.api = the CUDA library); the CPU tests inject a shared-memory
+    stand-in with the same five calls (peer_alloc / peer_export / peer_open / peer_close / peer_free)."""
+
+    def __init__(self, nbytes, group=None, mem=None):
+        if mem is None:
+            from . import api as mem
+        self.mem, self.group = mem, group
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.nbytes = int(nbytes)
-        self.local_ptr, self.tensor = api.peer_alloc(self.nbytes)
-        mine = torch.tensor(list(api.peer_export(self.local_ptr)), dtype=torch.uint8, device=self.tensor.device)
-        handles = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(handles, mine, group=group)
-        self.ptrs = [self.local_ptr if q == self.rank else api.peer_open(bytes(handles[q].cpu().tolist())) for q in range(self.world)]
+        self.local_ptr, self.tensor, self.ptrs = None, None, []
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        err, handle = None, bytes(64)
+        try:
+            self.local_ptr, self.tensor = mem.peer_alloc(self.nbytes)
+            handle = bytes(mem.peer_export(self.local_ptr))
+            assert len(handle) == 64
+        except Exception as e:   # reported to every rank below
+            err = e
+        mine = torch.tensor(list(handle) + [0 if err is None else 1], dtype=torch.uint8, device=dev)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=group)
+        gathered = [bytes(h.cpu().tolist()) for h in gathered]
+        bad = [q for q in range(self.world) if gathered[q][64]]
+        if bad:
+            self._release([])
+            raise RuntimeError(f"peer buffer: allocation / export failed on rank(s) {bad}" + (f": {err!r}" if err is not None else ""))
+        opened = []
+        try:
+            for q in range(self.world):
+                if q == self.rank:
+                    self.ptrs.append(self.local_ptr)
+                else:
+                    self.ptrs.append(mem.peer_open(gathered[q][:64]))
+                    opened.append(self.ptrs[-1])
+        except Exception as e:
+            err = e
+        flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+        if int(flag.item()):
+            self._release(opened)
+            raise RuntimeError("peer buffer: mapping a peer's memory failed on some rank" + (f" (here: {err!r})" if err is not None else ""))
 
-    def close(self):
-        from . import api
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)          # nobody still writes into a buffer that is about to go
-        for q, p in enumerate(self.ptrs):
-            if q != self.rank:
-                api.peer_close(p)
+    def _release(self, opened):
+        for p in opened:
+            try:
+                self.mem.peer_close(p)
+            except Exception:
+                pass
         self.ptrs = []
         self.tensor = None
-        api.peer_free(self.local_ptr)
+        if self.local_ptr is not None:
+            self.mem.peer_free(self.local_ptr)
+            self.local_ptr = None
+
+    def close(self):
+        if self.tensor is not None and self.tensor.is_cuda:
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)          # nobody still writes into a buffer that is about to go
+        self._release([p for q, p in enumerate(self.ptrs) if q != self.rank])
 
 
 class _CudaEngine:
@@ -79,6 +121,16 @@ class _CudaEngine:
             api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
         finally:
             api.set_gemm_pass_callback(None)
+
+    def set_peer_outputs(self, ptrs):
+        """fused gather: addresses of the C block inside the peers' buffers for the following gemm calls (None: off)"""
+        from . import api
+        api.set_gemm_peer_outputs(ptrs)
+
+    def peer_written(self):
+        """peers the last gemm stored to (0: it ran a path without the fused stores)"""
+        from . import api
+        return api.gemm_peer_written()
 
     def gemv(self, m, n, alpha, A, lda, x, beta, y):
         from . import api
@@ -125,16 +177,15 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
     dist.broadcast(_bytes(B), src=src, group=group)
     C_blk = C_full[lo * n:hi * n]
     if peers is not None and world > 1:
-        from . import api
         wrote = world - 1                                            # a rank without rows has nothing to deliver
         if hi > lo:
             others = [peers.ptrs[q] + lo * n * 16 for q in range(world) if q != rank]
-            api.set_gemm_peer_outputs(others)
+            compute.set_peer_outputs(others)
             try:
                 compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
-                wrote = api.gemm_peer_written()
+                wrote = compute.peer_written()
             finally:
-                api.set_gemm_peer_outputs(None)
+                compute.set_peer_outputs(None)
         # every rank must take the same branch: a rank whose planner declined makes all of them gather
         flag = torch.tensor([1 if wrote == world - 1 else 0], dtype=torch.int32, device=C_full.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also the completion barrier of the peer stores

@@ -17,9 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class OracleEngine:
     """stand-in engine: same call surface as qblas_b200.dist._CudaEngine, computed by oracle/qoracle.c"""
 
-    def __init__(self):
+    def __init__(self, mem=None, fused_ok=True):
         import oracle_lib
         self.o = oracle_lib.load_oracle()
+        self.mem, self.fused_ok, self.peers, self.wrote = mem, fused_ok, [], 0
+
+    # fused gather (qb_set_gemm_peer_outputs / qb_get_gemm_peer_written): the stand-in copies the finished block into the peers' memory
+    def set_peer_outputs(self, ptrs):
+        self.peers = list(ptrs or [])
+
+    def peer_written(self):
+        return self.wrote
 
     @staticmethod
     def _np(t):
@@ -27,6 +35,11 @@ class OracleEngine:
 
     def gemm(self, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, on_rows=None, min_passes=1):
         self.o.gemm("R", m, n, k, alpha, self._np(A), lda, self._np(B), ldb, beta, self._np(C), ldc)
+        self.wrote = 0
+        if self.peers and self.fused_ok:
+            for p in self.peers:
+                self.mem.view(p, m * n * 16).copy_(C.view(torch.uint8).reshape(-1)[:m * n * 16])
+            self.wrote = len(self.peers)
         if on_rows is not None:   # the library's row-pass hook: every row reported exactly once, in passes
             step = -(-m // max(1, min_passes))
             for r0 in range(0, m, step):
@@ -59,6 +72,102 @@ class OracleEngine:
         if do_sqrt:
             r = self.o.sqrt(r.reshape(1, 2))[0]
         out.copy_(torch.from_numpy(r.view(np.int64)).reshape(out.shape))
+
+
+class ShmMem:
+    """CPU stand-in for the library's qb_peer_* calls: the 'device memory' is a file under /dev/shm mapped MAP_SHARED by every rank,
+    the 64-byte handle is its path, a 'pointer' is (owner rank + 1) << 40 plus a byte offset."""
+
+    def __init__(self, tag, rank, fail_alloc=False, fail_open=False):
+        self.tag, self.rank, self.fail_alloc, self.fail_open = tag, rank, fail_alloc, fail_open
+        self.maps, self.paths = {}, {}
+
+    def peer_alloc(self, nbytes):
+        if self.fail_alloc:
+            raise MemoryError("injected allocation failure")
+        path = f"/dev/shm/qbtest_{self.tag}_{self.rank}"
+        with open(path, "wb") as f:
+            f.truncate(nbytes)
+        t = torch.from_file(path, shared=True, size=nbytes, dtype=torch.uint8)
+        slot = self.rank + 1
+        self.maps[slot], self.paths[slot] = t, path
+        return slot << 40, t
+
+    def peer_export(self, ptr):
+        return self.paths[ptr >> 40].encode().ljust(64, b"\0")
+
+    def peer_open(self, handle):
+        if self.fail_open:
+            raise OSError("injected mapping failure")
+        path = bytes(handle).rstrip(b"\0").decode()
+        t = torch.from_file(path, shared=True, size=os.path.getsize(path), dtype=torch.uint8)
+        slot = int(path.rsplit("_", 1)[1]) + 1
+        self.maps[slot] = t
+        return slot << 40
+
+    def peer_close(self, ptr):
+        self.maps.pop(ptr >> 40, None)
+
+    def peer_free(self, ptr):
+        self.maps.pop(ptr >> 40, None)
+        path = self.paths.pop(ptr >> 40, None)
+        if path and os.path.exists(path):
+            os.unlink(path)
+
+    def view(self, ptr, nbytes):
+        off = ptr & ((1 << 40) - 1)
+        return self.maps[ptr >> 40][off:off + nbytes]
+
+
+def _fused_worker(rank, world, port, q):
+    """dist.PeerBuffer + qgemm_row_sharded(peers=...) on CPU: shared-memory peers, the oracle as the engine."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qblas_b200 import dist as qd, quad
+        import oracle_lib
+        orc = oracle_lib.load_oracle()
+        rng = np.random.default_rng(17)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a).view(np.int64))
+        tag = f"{port}"
+        for (m, n, k), fused_ok_on in (((8, 5, 40), None), ((7, 6, 20), None), ((8, 5, 40), 1), ((2, 3, 9), None)):
+            A = quad.random_quads(rng, m * k); B = quad.random_quads(rng, k * n); C0 = quad.random_quads(rng, m * n)
+            alpha, beta = quad.random_quads(rng, 2)
+            want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
+            mem = ShmMem(tag, rank)
+            # fused_ok_on = r: rank r's engine reports 0 peers written (a declined planner) -> every rank must gather instead
+            eng = OracleEngine(mem=mem, fused_ok=(fused_ok_on is None or fused_ok_on != rank))
+            pb = qd.PeerBuffer(m * n * 16, mem=mem)
+            assert len(pb.ptrs) == world and pb.ptrs[rank] == pb.local_ptr
+            Cp = pb.tensor.view(torch.int64).reshape(m * n, 2)
+            Cp.copy_(t(C0))
+            dist.barrier()
+            lo, hi = qd.row_block(m, world, rank)
+            Bt = t(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64)
+            qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cp, compute=eng, peers=pb)
+            dist.barrier()
+            assert (Cp.numpy().view(np.uint64) == want).all(), ("fused gemm", m, n, k, rank, fused_ok_on)
+            assert eng.peers == []                                   # switched off again after the call
+            del Cp
+            pb.close()
+            assert not os.path.exists(f"/dev/shm/qbtest_{tag}_{rank}")
+        # failures are collective: whichever rank fails, EVERY rank raises (and nobody is left waiting in a collective)
+        for kw in ({"fail_alloc": rank == world - 1}, {"fail_open": rank == 0}):
+            mem = ShmMem(tag, rank, **kw)
+            try:
+                qd.PeerBuffer(64, mem=mem)
+                raise AssertionError(("PeerBuffer did not raise", kw, rank))
+            except RuntimeError:
+                pass
+            dist.barrier()
+            assert not os.path.exists(f"/dev/shm/qbtest_{tag}_{rank}"), "local buffer leaked after a failed setup"
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "".join(traceback.format_exception(e))))
+    finally:
+        dist.destroy_process_group()
 
 
 def _worker(rank, world, port, q):
@@ -118,6 +227,20 @@ def test_sharded_routines_match_single_process_bitwise(world):
     q = ctx.Queue()
     port = 29600 + world + os.getpid() % 200
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_gather_plumbing_and_collective_failures(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + world + os.getpid() % 200
+    procs = [ctx.Process(target=_fused_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in procs]
