@@ -22,6 +22,7 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#include "q128.cuh"
 
 #if defined(__CUDACC__)
 #define QCRT_HD __host__ __device__ __forceinline__
@@ -216,6 +217,58 @@ QCRT_UNROLL
   }
 }
 
+
+/* ------------------------------------------------------------------ the one rounding */
+QCRT_HD int clz32(uint32_t x) /* x != 0 */
+{
+#if defined(__CUDA_ARCH__)
+  return __clz((int)x);
+#else
+  return __builtin_clz(x);
+#endif
+}
+QCRT_HD uint32_t funnel_l(uint32_t lo, uint32_t hi, int n) /* high word of (hi:lo) << n, 0 <= n < 32 */
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, n);
+#else
+  return n ? (hi << n) | (lo >> (32 - n)) : hi;
+#endif
+}
+/* |I| (NL limbs) times 2^Eb -> binary128 with ONE rounding (RNE; gradual underflow and overflow in q_round_pack).
+ * I = 0 gives +0: an exact zero sum is +0 (a +0-seeded chain never yields -0). */
+template <int NL>
+QCRT_HD q128 limbs_to_q(const uint32_t (&L)[NL], uint32_t neg, int Eb)
+{
+  int top = -1;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l) if (L[l]) top = l;
+  if (top < 0) return q_zero(0);
+  uint32_t buf[NL + 8];
+QCRT_UNROLL
+  for (int l = 0; l < 8; ++l) buf[l] = 0;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l) buf[8 + l] = L[l];
+  uint32_t w[9];
+QCRT_UNROLL
+  for (int k = 0; k < 9; ++k) w[k] = buf[top + k];   /* limbs top-8 .. top */
+  uint32_t sticky = 0;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l) if (l < top - 8) sticky |= L[l];
+  const int lz = clz32(w[8]);
+  uint32_t R[8];
+QCRT_UNROLL
+  for (int k = 0; k < 8; ++k) R[k] = funnel_l(w[k], w[k + 1], lz);
+  sticky |= w[0] << lz;
+  if (lz == 0) sticky |= w[0];
+  u256 Rq;
+  Rq.w0 = ((uint64_t)R[1] << 32) | R[0] | (sticky != 0);
+  Rq.w1 = ((uint64_t)R[3] << 32) | R[2];
+  Rq.w2 = ((uint64_t)R[5] << 32) | R[4];
+  Rq.w3 = ((uint64_t)R[7] << 32) | R[6];
+  const int p = 32 * top + 31 - lz;  /* MSB position of |I| */
+  return q_round_pack(neg, p + Eb + QBIAS, Rq);
+}
 
 /* ------------------------------------------------------------------ reconstruction, device form */
 #if defined(__CUDACC__) || defined(QCRT_HOST_EMULATE_PTX)

@@ -664,40 +664,6 @@ __global__ void __launch_bounds__(256) k_crt_residues_t(const q128 *__restrict__
   }
 }
 
-/* |I| (NL limbs, non-zero handled by the caller) times 2^Eb -> binary128, one rounding (RNE) */
-template <int NL>
-__device__ __forceinline__ q128 crt_limbs_to_q(const uint32_t (&L)[NL], uint32_t neg, int Eb)
-{
-  int top = -1;
-#pragma unroll
-  for (int l = 0; l < NL; ++l) if (L[l]) top = l;
-  if (top < 0) return q_zero(0);   /* an exact zero sum is +0 (a +0-seeded chain never yields -0) */
-  uint32_t buf[NL + 8];
-#pragma unroll
-  for (int l = 0; l < 8; ++l) buf[l] = 0;
-#pragma unroll
-  for (int l = 0; l < NL; ++l) buf[8 + l] = L[l];
-  uint32_t w[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) w[k] = buf[top + k];   /* limbs top-8 .. top */
-  uint32_t sticky = 0;
-#pragma unroll
-  for (int l = 0; l < NL; ++l) if (l < top - 8) sticky |= L[l];
-  const int lz = __clz((int)w[8]);
-  uint32_t R[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) R[k] = __funnelshift_l(w[k], w[k + 1], lz);
-  sticky |= w[0] << lz;
-  if (lz == 0) sticky |= w[0];
-  u256 Rq;
-  Rq.w0 = ((uint64_t)R[1] << 32) | R[0] | (sticky != 0);
-  Rq.w1 = ((uint64_t)R[3] << 32) | R[2];
-  Rq.w2 = ((uint64_t)R[5] << 32) | R[4];
-  Rq.w3 = ((uint64_t)R[7] << 32) | R[6];
-  const int p = 32 * top + 31 - lz;  /* MSB position of |I| */
-  return q_round_pack(neg, p + Eb + QBIAS, Rq);
-}
-
 struct CrtFoldArgs {
   const uint8_t *R; int64_t Mp, Np;
   int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
@@ -739,7 +705,7 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
       uint32_t Y[NG + 1], neg;
       crt::reconstruct_dev<NG>(r, pl, Y, neg);
       const int baseB = g.emaxB[j] + 113 - g.WB;
-      const q128 sum = crt_limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
+      const q128 sum = crt::limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
       q128 *c = g.C + i * g.sci + j * g.scj;
       const q128 cin = *c;
       /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the

@@ -44,6 +44,19 @@ void crt_residues(int count, const uint32_t *words, const uint32_t *sign, int nw
     }
   }
 }
+// magnitudes mag[e][14] (nl limbs used), neg[e], Eb[e] -> out[e] = round(+-mag * 2^Eb) as binary128 (lo, hi)
+void crt_round(int count, int nl, const uint32_t *mag, const uint32_t *neg, const int32_t *Eb, uint64_t *out)
+{
+  for (int e = 0; e < count; ++e) {
+    q128 r = {0, 0};
+    switch (nl) {
+#define CASE(n) case n: { uint32_t L[n]; for (int l = 0; l < n; ++l) L[l] = mag[e * NLMAX + l]; r = limbs_to_q<n>(L, neg[e], Eb[e]); } break;
+      CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    out[2 * e] = r.lo; out[2 * e + 1] = r.hi;
+  }
+}
 // int32 accumulators acc[e][N] -> residues in [0,p) -> reconstruction: mag[e][14], neg[e]
 void crt_fold(int count, const int32_t *acc, int N, uint32_t *mag, uint32_t *neg)
 {

@@ -162,3 +162,58 @@ def test_inner_products_through_kernel_form(lib):
             test_inner_product_reconstruction_exact(lib, WA, WB, k)
     finally:
         lib.crt_set_form(0)
+
+
+@pytest.mark.parametrize("nl", [2, 3, 5, 9, 10, 11, 12, 14])
+def test_one_rounding_of_the_wide_integer(lib, nl):
+    """crt::limbs_to_q: +-|I| * 2^Eb -> binary128 with ONE round-to-nearest-even, for magnitudes of every length (short ones,
+    exactly representable ones, ties with even / odd mantissas, sticky bits far below the window, all-ones carries), in the normal
+    range, in gradual underflow and at overflow - against exact rational arithmetic."""
+    from fractions import Fraction
+    from qblas_b200 import quad
+    lib.crt_round.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rnd = random.Random(nl)
+    cases = []
+    maxbits = 32 * nl
+    for _ in range(400):
+        bits = rnd.randrange(1, maxbits + 1)
+        kind = rnd.randrange(6)
+        if kind == 0:
+            v = rnd.getrandbits(bits) | (1 << (bits - 1))
+        elif kind == 1:   # 113 significant bits then a tie pattern: ...1000 / ...0111 / ...1001
+            top = rnd.getrandbits(113) | (1 << 112)
+            low = max(0, bits - 113)
+            tail = [1 << (low - 1), (1 << (low - 1)) - 1, (1 << (low - 1)) + 1][rnd.randrange(3)] if low >= 2 else 0
+            v = (top << low) | tail
+        elif kind == 2:   # all ones: rounding carries into the next binade
+            v = (1 << bits) - 1
+        elif kind == 3:   # a power of two, or one with a single far-away sticky bit
+            v = (1 << (bits - 1)) | (1 if rnd.randrange(2) else 0)
+        elif kind == 4:   # short value
+            v = rnd.getrandbits(min(bits, 40)) or 1
+        else:             # tie exactly at half an ulp with a random (even or odd) mantissa
+            top = rnd.getrandbits(113) | (1 << 112)
+            low = max(1, bits - 113)
+            v = (top << low) | (1 << (low - 1))
+        v &= (1 << maxbits) - 1
+        v = v or 1
+        reg = rnd.randrange(4)
+        Eb = [rnd.randrange(-400, 400), rnd.randrange(-16494 - 120, -16494 + 40) - v.bit_length() + 113,
+              16383 - v.bit_length() + rnd.randrange(-3, 3), rnd.randrange(-16600, -16300)][reg]
+        cases.append((v, rnd.randrange(2), Eb))
+    cases.append((0, 0, 0)); cases.append((0, 1, -50))
+    mag = np.zeros((len(cases), 14), dtype=np.uint32)
+    for c, (v, _, _) in enumerate(cases):
+        for l in range(nl):
+            mag[c, l] = (v >> (32 * l)) & 0xffffffff
+    neg = np.array([c[1] for c in cases], dtype=np.uint32); Eb = np.array([c[2] for c in cases], dtype=np.int32)
+    out = np.zeros((len(cases), 2), dtype=np.uint64)
+    lib.crt_round(len(cases), nl, mag.ctypes.data, neg.ctypes.data, Eb.ctypes.data, out.ctypes.data)
+    for c, (v, s, e) in enumerate(cases):
+        if v == 0:
+            assert (int(out[c, 1]), int(out[c, 0])) == (0, 0)        # +0, whatever the sign flag says
+            continue
+        hi, lo = quad.from_fraction(Fraction(-v if s else v) * Fraction(2) ** e)
+        if hi & 0x7fffffffffffffff == 0 and lo == 0:
+            hi |= s << 63                                            # from_fraction drops the sign of an underflow to zero
+        assert (int(out[c, 1]), int(out[c, 0])) == (hi, lo), (nl, c, hex(v), s, e)
