@@ -138,6 +138,32 @@ QCRT_UNROLL
   return residue_sym<NW>(v, (sign && !zero) ? 1u : 0u, i, T) & 0xffu;
 }
 
+/* ------------------------------------------------------------------ element -> integer words */
+/* The same steps as crt_load4<NW> in qb_ozaki.cu (the kernels keep their own copy until the next GPU validation, so that the
+ * measured binary stays the validated one); used by the CPU end-to-end check of the scheme (tests/host/crt_host.cpp).
+ * x = (-1)^s M 2^(ee - 16495) (M < 2^113, ee = biased exponent, 1 for subnormals).  With base <= the lowest set bit of the row,
+ * X = M 2^(ee - base) is an exact integer; the words come out ready for residue_sym<NW>: |X| for s = 0, 2^(32 NW) - |X| for
+ * s = 1.  Zeros (and Inf/NaN, which the planner has already excluded) give all-zero words and sign 0. */
+template <int NW>
+QCRT_HD void element_words(q128 a, int base, uint32_t (&w)[NWMAX], uint32_t &sign)
+{
+QCRT_UNROLL
+  for (int j = 0; j < NWMAX; ++j) w[j] = 0;
+  sign = 0;
+  const uint32_t ef = (uint32_t)(a.hi >> 48) & 0x7fffu;
+  const uint64_t mhi = (a.hi & Q_MANT_HI_MASK) | (ef ? Q_IMPLICIT : 0);
+  if (!(a.lo | mhi) || ef == 0x7fffu) return;
+  const int ee = ef ? (int)ef : 1;
+  u256 v; v.w0 = a.lo; v.w1 = mhi; v.w2 = 0; v.w3 = 0;
+  const int sh = ee - base;
+  v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact: base <= lowest set bit of the row */
+  w[0] = (uint32_t)v.w0; w[1] = (uint32_t)(v.w0 >> 32);
+  w[2] = (uint32_t)v.w1; w[3] = (uint32_t)(v.w1 >> 32);
+  w[4] = (uint32_t)v.w2; w[5] = (uint32_t)(v.w2 >> 32);
+  sign = (uint32_t)(a.hi >> 63);
+  if (sign) negate_words<NW>(w);
+}
+
 /* what the tensor kernel's epilogue does with one int32 accumulator v (|v| <= 2^30): v mod p_i in [0, p) */
 QCRT_HD uint32_t acc_mod(int32_t v, int i, const Tables &T)
 {

@@ -217,3 +217,44 @@ def test_one_rounding_of_the_wide_integer(lib, nl):
         if hi & 0x7fffffffffffffff == 0 and lo == 0:
             hi |= s << 63                                            # from_fraction drops the sign of an underflow to zero
         assert (int(out[c, 1]), int(out[c, 0])) == (hi, lo), (nl, c, hex(v), s, e)
+
+
+@pytest.mark.parametrize("kind,m,n,k", [("D113", 5, 4, 37), ("D53", 4, 6, 64), ("Dint", 3, 5, 20), ("Dexp8", 4, 3, 33), ("D113", 2, 2, 300),
+                                       ("Dzero", 3, 3, 10), ("Dfloat", 4, 4, 50)])
+def test_whole_scheme_on_the_cpu_is_exactly_rounded(lib, oracle, kind, m, n, k):
+    """The residue-scheme qgemm end to end on the CPU, stitched from the library's own dual-source arithmetic (row / column scan,
+    element -> integer words, int8 residues, int32 accumulation per modulus, reduction, carry-chain reconstruction, the one
+    rounding, the reference epilogue): bit for bit the exact inner products rounded once (tests/exact_ref.py), then
+    C = fma(alpha, s, mul(beta, C)) by the oracle."""
+    from exact_ref import exact_matmul_rounded
+    from qblas_b200 import quad
+    rng = np.random.default_rng(m * 100 + n * 10 + k)
+
+    def mk(r, c):
+        if kind == "Dint":
+            return quad.from_double(rng.integers(-9, 10, size=(r, c)).astype(np.float64)).reshape(r * c, 2)
+        if kind == "Dexp8":
+            return np.ascontiguousarray(quad.random_quads(rng, (r, c), "D113", emin=-8, emax=8).reshape(r * c, 2))
+        if kind == "Dzero":
+            return quad.from_double(np.zeros((r, c))).reshape(r * c, 2)
+        if kind == "Dfloat":   # float32 values: 24-bit spans -> few moduli, two reconstruction groups
+            return quad.from_double(rng.standard_normal((r, c)).astype(np.float32).astype(np.float64)).reshape(r * c, 2)
+        return np.ascontiguousarray(quad.random_quads(rng, (r, c), kind).reshape(r * c, 2))
+    A = mk(m, k); B = mk(k, n) if kind != "Dzero" else np.ascontiguousarray(quad.random_quads(rng, (k, n), "D113").reshape(k * n, 2))
+    C0 = np.ascontiguousarray(quad.random_quads(rng, (m, n), "D113").reshape(m * n, 2))
+    alpha, beta = quad.random_quads(rng, 2)
+    got = C0.copy()
+    info = np.zeros(3, dtype=np.int32)
+    lib.crt_set_form(1)
+    lib.crt_gemm_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    al = np.ascontiguousarray(alpha, dtype=np.uint64); be = np.ascontiguousarray(beta, dtype=np.uint64)
+    rc = lib.crt_gemm_host(m, n, k, A.ctypes.data, B.ctypes.data, got.ctypes.data, al.ctypes.data, be.ctypes.data, info.ctypes.data)
+    assert rc == 0, "scheme declined"
+    s = exact_matmul_rounded(A, k, B, n, m, n, k)
+    alb = np.broadcast_to(al.reshape(1, 2), s.shape).copy(); beb = np.broadcast_to(be.reshape(1, 2), s.shape).copy()
+    want = oracle.fma(alb, s, oracle.mul(beb, C0))
+    assert quad.same_bits(got, want).all(), (kind, info.tolist())
+    if kind == "D53":
+        assert info[1] <= 64 and info[2] <= 64 and info[0] <= 17      # doubles: short spans, few moduli
+    if kind == "Dint":
+        assert info[0] <= 4
