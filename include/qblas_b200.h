@@ -165,7 +165,12 @@ int qb_nrm2(int64_t n, const void *x, int64_t incx, qb_quad *result);
 int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *y, int64_t incy);
 
 /* Device pointers only, asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream).
- * d_result is a DEVICE pointer to 16 bytes.  No host synchronisation inside. */
+ * d_result is a DEVICE pointer to 16 bytes.  No host synchronisation inside, with one exception: the fast-mode tensor path of
+ * qb_gemm_dev waits once for its 3-integer plan (row / column bit spans) before it sizes the residue planes; the bounded
+ * digit-diagonal setting also reads one counter per row pass.  The tensor path runs on internal streams that are ordered
+ * after `stream` at entry and that `stream` waits for before the call returns, so the caller sees plain stream order.
+ * The library owns ONE grow-only workspace per process: calls issued on different streams must be ordered with respect to each
+ * other by the caller (calls on one stream, or from one thread at a time on the default stream, always are). */
 int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int64_t k, const qb_quad *alpha,
                 const void *dA, int64_t lda, const void *dB, int64_t ldb, const qb_quad *beta, void *dC,
                 int64_t ldc, void *stream);
