@@ -1058,8 +1058,9 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
     R[b] = (uint8_t *)(pA[b] + pa_bytes(mb));
   }
   CrtStreams &cs = g_cs;
-  cudaEventRecord(cs.in, st);
-  cudaStreamWaitEvent(cs.sM, cs.in, 0); cudaStreamWaitEvent(cs.sA, cs.in, 0); cudaStreamWaitEvent(cs.sF, cs.in, 0);
+#define QB_CRT_TRY(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+  QB_CRT_TRY(cudaEventRecord(cs.in, st));
+  QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sA, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sF, cs.in, 0));
   launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, cs.sM);
   int pass = 0;
   for (int64_t r0 = 0; r0 < m; r0 += mb, ++pass) {
@@ -1067,19 +1068,19 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
     const int64_t Mp = rup(mr, OZ_BM);
     const int b = pass & 1;
     /* residues of this pass's A rows: its buffer was last read by the tensor kernel of pass - 2 */
-    if (pass >= 2) cudaStreamWaitEvent(cs.sA, cs.mma[b], 0);
+    if (pass >= 2) QB_CRT_TRY(cudaStreamWaitEvent(cs.sA, cs.mma[b], 0));
     launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pA[b], cs.sA);
-    cudaEventRecord(cs.resA[b], cs.sA);
+    QB_CRT_TRY(cudaEventRecord(cs.resA[b], cs.sA));
     /* tensor kernel: needs the residues, and R[b] drained by the reconstruction of pass - 2 */
-    cudaStreamWaitEvent(cs.sM, cs.resA[b], 0);
-    if (pass >= 2) cudaStreamWaitEvent(cs.sM, cs.fold[b], 0);
+    QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.resA[b], 0));
+    if (pass >= 2) QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.fold[b], 0));
     oz_ev_record(0, cs.sM);
     e = launch_crt_mma(pA[b], pB, N, mr, n, Kp, R[b], Mp, Np, cs.sM);
     oz_ev_record(1, cs.sM);
     if (e != cudaSuccess) return e;
-    cudaEventRecord(cs.mma[b], cs.sM);
+    QB_CRT_TRY(cudaEventRecord(cs.mma[b], cs.sM));
     /* reconstruction + epilogue */
-    cudaStreamWaitEvent(cs.sF, cs.mma[b], 0);
+    QB_CRT_TRY(cudaStreamWaitEvent(cs.sF, cs.mma[b], 0));
     CrtFoldArgs f;
     f.R = R[b]; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = n; f.row0 = r0;
     f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
@@ -1091,7 +1092,7 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
     launch_crt_fold(f, pl, cs.sF);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    cudaEventRecord(cs.fold[b], cs.sF);
+    QB_CRT_TRY(cudaEventRecord(cs.fold[b], cs.sF));
     e = cudaStreamWaitEvent(st, cs.fold[b], 0);   /* the caller's stream sees the rows of this pass */
     if (e != cudaSuccess) return e;
     if (cb) cb(r0, mr, cb_user);
@@ -1104,6 +1105,7 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
   g_last_stats.peer_written = a.npeer;
   *used = 1;
   return cudaSuccess;
+#undef QB_CRT_TRY
 }
 
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
