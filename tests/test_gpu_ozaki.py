@@ -376,3 +376,40 @@ def test_residue_scheme_peer_outputs_mirror_C(qb, oracle, layout, m, n, k):
         assert (p[mask] == sentinel[mask]).all(), "peer padding was touched"
     assert (to_host(P3) == sentinel).all()
     assert (got[mask] == C0[mask]).all()
+
+
+# ------------------------------------------------------------------ more template instances of the residue kernels
+def _truncate_mantissa(q, bits):
+    """keep the `bits` leading mantissa bits (incl. the implicit one) of every quad: shorter spans, fewer words / moduli"""
+    q = q.copy()
+    drop = 113 - bits
+    if drop >= 64:
+        q[..., 0] = 0
+        q[..., 1] &= ~np.uint64((1 << (drop - 64)) - 1)
+    elif drop > 0:
+        q[..., 0] &= ~np.uint64((1 << drop) - 1)
+    return q
+
+
+@pytest.mark.parametrize("name,bits,binades,m,n,k", [("float32-like", 24, 3, 40, 50, 100), ("80-bit", 80, 6, 33, 47, 64), ("96-bit", 96, 8, 20, 300, 96),
+                                                    ("wide", 113, 24, 30, 40, 256)])
+def test_residue_scheme_other_word_and_group_counts(qb, oracle, name, bits, binades, m, n, k):
+    """Spans of ~30 / ~90 / ~110 / ~160 bits: 1, 3, 4 and 6 integer words per element and 2 to 12 reconstruction groups (the
+    float32-like case also stands for low-precision data cast to quad).  Exactly rounded, bit for bit."""
+    rng = np.random.default_rng(bits + k)
+    def mk(r, c):
+        return np.ascontiguousarray(_truncate_mantissa(quad.random_quads(rng, (r, c), "D113", emin=-binades, emax=binades), bits).reshape(r * c, 2))
+    A = mk(m, k); B = mk(k, n); C0 = mk(m, n)
+    alpha, beta = quad.random_quads(rng, 2)
+    s = exact_matmul_rounded(A, k, B, n, m, n, k)
+    want = _epilogue(oracle, alpha, s, beta, C0)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
+    try:
+        dC = to_dev(C0)
+        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["scheme"] == "residues", st
+    assert quad.same_bits(to_host(dC), want).all(), st
