@@ -119,6 +119,14 @@ int qb_get_tensor_keep(void);
  * diagonals when its moduli cannot cover the operands' bit span (W_A + W_B + log2 k + 1 > 341) or k > 65536. */
 void qb_set_tensor_scheme(int scheme);
 int qb_get_tensor_scheme(void);
+/* Row passes of the residue scheme (they are software-pipelined: tensor kernel of pass p || residues of pass p+1 || fold of
+ * pass p-1).  0 (default, the measured setting): equal passes.  1 (experimental, not yet measured on hardware): a short first
+ * and a short last pass, whose residues / fold cannot hide behind a tensor pass.  Ignored while a row-pass callback is set.
+ * qb_crt_pass_rows reports the partition the library would use for m rows with at most `cap` rows per pass (returns the
+ * number of passes; out receives up to max_out sizes). */
+void qb_set_tensor_pass_shape(int shape);
+int qb_get_tensor_pass_shape(void);
+int qb_crt_pass_rows(int64_t m, int64_t cap, int shape, int64_t *out, int max_out);
 /* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, digit-plane products
  * per row pass, workspace bytes, padded K, diagonals kept, elements sent to the fix-up, row passes
  * redone with all diagonals, residue-scheme word}.  Residue scheme: S_A / S_B = bytes of the widest row /

@@ -312,6 +312,22 @@ def peer_close(ptr):
     check(lib().qb_peer_close(C.c_void_p(int(ptr))), "qb_peer_close")
 
 
+def set_tensor_pass_shape(shape):
+    """Residue scheme row passes: 0 = equal (default, measured), 1 = short first / last pass (experimental)."""
+    lib().qb_set_tensor_pass_shape(int(shape))
+
+
+def get_tensor_pass_shape():
+    return lib().qb_get_tensor_pass_shape()
+
+
+def crt_pass_rows(m, cap, shape=0):
+    """The row-pass partition the residue scheme uses for m rows with at most cap rows per pass."""
+    out = (C.c_int64 * 4096)()
+    cnt = lib().qb_crt_pass_rows(int(m), int(cap), int(shape), out, 4096)
+    return [int(out[i]) for i in range(min(cnt, 4096))]
+
+
 def set_tensor_scheme(scheme):
     """Tensor-path scheme: 1 = residue planes + Chinese-remainder reconstruction (default), 0 = digit diagonals."""
     lib().qb_set_tensor_scheme(int(scheme))

@@ -224,6 +224,18 @@ void qb_set_tensor_scheme(int scheme)
   oz_set_scheme(scheme);
 }
 int qb_get_tensor_scheme(void) { return oz_get_scheme(); }
+void qb_set_tensor_pass_shape(int shape)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  oz_set_pass_shape(shape);
+}
+int qb_get_tensor_pass_shape(void) { return oz_get_pass_shape(); }
+int qb_crt_pass_rows(int64_t m, int64_t cap, int shape, int64_t *out, int max_out)
+{
+  const std::vector<int64_t> rows = oz_crt_pass_rows(m, cap, shape);
+  for (int i = 0; i < (int)rows.size() && i < max_out; ++i) out[i] = rows[i];
+  return (int)rows.size();
+}
 
 /* ---- peer memory (fused gather of the row-sharded qgemm) ---- */
 void *qb_peer_alloc(size_t bytes)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <vector>
 #include "q128.cuh"
 
 namespace qb {
@@ -66,8 +67,11 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);
 OzStats oz_last_stats();
+std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape);
 void oz_set_keep(int keep);   /* leading diagonals multiplied (bounded setting); 0 = all = exact inner products */
 int oz_get_keep();
+void oz_set_pass_shape(int v); /* residue scheme: 0 = equal row passes (default), 1 = short first and last pass (experimental) */
+int oz_get_pass_shape();
 void oz_set_scheme(int v); /* 1 = residue planes + CRT (qb_crt.cuh, default), 0 = digit diagonals */
 int oz_get_scheme();
 double oz_last_mma_ms(int *launches);

@@ -54,6 +54,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace qb {
 
@@ -986,6 +987,30 @@ static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t 
   count_launch();
 }
 
+/* Rows of each pass of the residue scheme: the sizes sum to m, every size but the last is a multiple of OZ_BM, none exceeds `cap`.
+ * shape 0 (default, the measured one): equal passes of `cap` rows.  shape 1 (experimental, qb_set_tensor_pass_shape): a short
+ * first pass (its A residues cannot overlap a tensor pass) and a short last pass (neither can its fold, nor its peer stores),
+ * equal passes in between. */
+static int g_oz_pass_shape = 0;
+void oz_set_pass_shape(int v) { g_oz_pass_shape = v == 1 ? 1 : 0; }
+int oz_get_pass_shape() { return g_oz_pass_shape; }
+std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape)
+{
+  std::vector<int64_t> rows;
+  if (m <= 0 || cap <= 0) return rows;
+  const int64_t small = std::max<int64_t>(OZ_BM, rup(cap / 4, OZ_BM));
+  const bool shaped = shape == 1 && cap >= 4 * OZ_BM && m >= 2 * small + cap;
+  int64_t left = m, last = 0;
+  if (shaped) {   /* the ragged remainder of m stays in the LAST pass, so every pass starts on a tile boundary */
+    rows.push_back(small);
+    last = small + (m - 2 * small) % OZ_BM;
+    left = m - small - last;
+  }
+  while (left > 0) { const int64_t r = std::min(cap, left); rows.push_back(r); left -= r; }
+  if (shaped) rows.push_back(last);
+  return rows;
+}
+
 /* Internal streams of the residue scheme: the tensor kernel of row pass p (sM, highest priority) runs while the residues of
  * the A rows of pass p+1 (sA) and the reconstruction of pass p-1 (sF) use the integer pipes of the same SMs (the persistent
  * tensor kernel holds one 192-thread CTA per SM; the other two kernels need no shared memory and fit beside it). */
@@ -1062,9 +1087,11 @@ static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used
   QB_CRT_TRY(cudaEventRecord(cs.in, st));
   QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sA, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sF, cs.in, 0));
   launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, cs.sM);
+  const std::vector<int64_t> pass_rows = oz_crt_pass_rows(m, mb, (cb || mb >= m) ? 0 : g_oz_pass_shape);
   int pass = 0;
-  for (int64_t r0 = 0; r0 < m; r0 += mb, ++pass) {
-    const int64_t mr = std::min(mb, m - r0);
+  int64_t r0 = 0;
+  for (; pass < (int)pass_rows.size(); r0 += pass_rows[pass], ++pass) {
+    const int64_t mr = pass_rows[pass];
     const int64_t Mp = rup(mr, OZ_BM);
     const int b = pass & 1;
     /* residues of this pass's A rows: its buffer was last read by the tensor kernel of pass - 2 */

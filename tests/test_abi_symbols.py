@@ -78,3 +78,24 @@ def test_compute_fails_loudly_without_gpu():
     with pytest.raises(qblas_b200.QblasError):
         qblas_b200.quadblas_qgemv("R", "N", 2, 2, 1.0, x, 2, x, 1, 0.0, y, 1)
     assert quad.same_bits(x, y).all()  # outputs untouched on failure
+
+
+def test_residue_scheme_row_pass_partition():
+    """Host logic of the row passes (csrc/qb_ozaki.cu, oz_crt_pass_rows): shape 0 is the equal split the kernels were measured with,
+    shape 1 (experimental) shortens the first and the last pass; every partition covers the rows exactly once in tile multiples."""
+    from qblas_b200 import api
+    assert api.get_tensor_pass_shape() == 0
+    for m in (1, 127, 128, 384, 1000, 4096, 8192, 8200, 32768, 65536 + 5):
+        for cap in (128, 256, 1024, 2048, 8192):
+            for shape in (0, 1):
+                rows = api.crt_pass_rows(m, cap, shape)
+                assert sum(rows) == m and all(0 < r <= cap for r in rows), (m, cap, shape, rows)
+                if shape == 0:      # the old loop: r0 += cap, mr = min(cap, m - r0)
+                    assert rows == [min(cap, m - r0) for r0 in range(0, m, cap)]
+                # a pass that is not the last in ROW ORDER starts the next one on a tile boundary
+                r0 = 0
+                for r in rows[:-1]:
+                    r0 += r
+                    assert r0 % 128 == 0, (m, cap, shape, rows)
+    assert api.crt_pass_rows(8192, 2048, 1) == [512, 2048, 2048, 2048, 1024, 512]
+    assert api.crt_pass_rows(384, 128, 1) == [128, 128, 128]          # too small to shape
