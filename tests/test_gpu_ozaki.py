@@ -413,3 +413,30 @@ def test_residue_scheme_other_word_and_group_counts(qb, oracle, name, bits, bina
         qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
     assert st["scheme"] == "residues", st
     assert quad.same_bits(to_host(dC), want).all(), st
+
+
+def test_residue_scheme_pass_shapes_agree(qb, oracle):
+    """qb_set_tensor_pass_shape(1) (short first and last row pass, experimental) changes only WHEN rows are produced: the result is
+    bit for bit the one of the equal split, and a few rows around the pass boundaries match exact arithmetic."""
+    m, n, k = 4224, 256, 256                      # equal: 1152 x 3 + 768; shaped: 384, 1152 x 3, 384 (api.crt_pass_rows(4224, 1152, s))
+    A = dev_random((m * k,), "D113", seed=21); B = dev_random((k * n,), "D113", seed=22); C0 = dev_random((m * n,), "D113", seed=23)
+    outs, plans = [], []
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_scheme(1)
+    try:
+        for shape in (0, 1):
+            qb.set_tensor_pass_shape(shape)
+            C = C0.clone()
+            qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
+            torch.cuda.synchronize()
+            outs.append(to_host(C)); plans.append(qb.oz_last_stats())
+    finally:
+        qb.set_tensor_pass_shape(0)
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert plans[0]["scheme"] == "residues" and plans[0]["row_passes"] == 4 and plans[1]["row_passes"] == 5, plans
+    assert (outs[0] == outs[1]).all()
+    Ah, Bh = to_host(A), to_host(B)
+    one, zero = quad.from_double(np.array([1.0]))[0], quad.from_double(np.array([0.0]))[0]
+    for i in (0, 383, 384, 1535, 1536, 3839, 3840, m - 1):
+        s = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, Bh, n, 1, n, k)
+        want = _epilogue(oracle, one, s, zero, to_host(C0)[i * n:(i + 1) * n])
+        assert quad.same_bits(outs[1][i * n:(i + 1) * n], want).all(), i
