@@ -99,3 +99,15 @@ def test_residue_scheme_row_pass_partition():
                     assert r0 % 128 == 0, (m, cap, shape, rows)
     assert api.crt_pass_rows(8192, 2048, 1) == [512, 2048, 2048, 2048, 1024, 512]
     assert api.crt_pass_rows(384, 128, 1) == [128, 128, 128]          # too small to shape
+
+
+def test_measured_defaults():
+    """The settings every number under profiles/ was measured with are the library defaults."""
+    L = qblas_b200.lib()
+    assert L.qb_get_mode() == 0                   # reference order (bit exact) unless fast mode is requested
+    assert L.qb_get_tensor_path() == 1            # fast-mode qgemm: tensor path for m, n >= 128, k >= 256
+    assert L.qb_get_tensor_scheme() == 1          # residue planes + Chinese-remainder reconstruction
+    assert L.qb_get_tensor_pass_shape() == 0      # equal row passes
+    assert L.qb_get_tensor_keep() == 16           # digit-diagonal fallback: bounded setting
+    assert L.qb_get_fast_variant() == 1           # qdot / qnrm2 / qgemv: window accumulator
+    assert L.qb_get_gemm_peer_written() == 0
