@@ -287,6 +287,8 @@ def own_arm(args, rank, world, local_rank):
         qb.set_tensor_scheme(1 if args.scheme == "residues" else 0)
     if args.pass_shape:
         qb.set_tensor_pass_shape(args.pass_shape)
+    if args.host_slabs:
+        qb.set_host_slabs(args.host_slabs)
     S = args.size
     m_loc, n, k = S, S, S
     M = S * world
@@ -613,6 +615,7 @@ def main():
     ap.add_argument("--dist", default="D113", choices=["D113", "D53", "Dexp"])
     ap.add_argument("--overlap", type=int, default=4, help="N > 1: row passes whose all-gathers overlap the next pass (1 = one all-gather after the qgemm)")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: C blocks reach the other ranks by peer stores from the kernel that finishes them (fused) or by NCCL all-gather")
+    ap.add_argument("--host-slabs", type=int, default=0, help="e2e: C slabs of the pipelined all-host qgemm (library default 4)")
     ap.add_argument("--pass-shape", type=int, default=0, choices=[0, 1], help="residue scheme row passes: 0 equal (default), 1 short first / last pass (experimental)")
     ap.add_argument("--scheme", default=None, choices=["residues", "digits"], help="tensor path: residue planes + CRT (library default) or digit diagonals")
     ap.add_argument("--keep", type=int, default=None, help="tensor path: leading diagonals multiplied (0 = all = exact inner products; default: library default 16)")

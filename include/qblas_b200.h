@@ -124,6 +124,11 @@ int qb_get_tensor_scheme(void);
  * and a short last pass, whose residues / fold cannot hide behind a tensor pass.  Ignored while a row-pass callback is set.
  * qb_crt_pass_rows reports the partition the library would use for m rows with at most `cap` rows per pass (returns the
  * number of passes; out receives up to max_out sizes). */
+/* Large all-host qgemm calls (quadblas_qgemm / qb_gemm with host pointers) are pipelined: the shared operand is uploaded first,
+ * then C is cut into `slabs` blocks whose uploads, compute and downloads overlap on three streams.  Default 4 (the measured
+ * setting); more slabs shorten the tail after the last upload (1..16). */
+void qb_set_host_slabs(int slabs);
+int qb_get_host_slabs(void);
 void qb_set_tensor_pass_shape(int shape);
 int qb_get_tensor_pass_shape(void);
 int qb_crt_pass_rows(int64_t m, int64_t cap, int shape, int64_t *out, int max_out);

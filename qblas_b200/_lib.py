@@ -73,6 +73,8 @@ def lib():
         "qb_peer_close": (ci, [vp]),
         "qb_set_gemm_peer_outputs": (ci, [ci, C.POINTER(vp)]),
         "qb_get_gemm_peer_written": (ci, []),
+        "qb_set_host_slabs": (None, [ci]),
+        "qb_get_host_slabs": (ci, []),
         "qb_set_tensor_pass_shape": (None, [ci]),
         "qb_get_tensor_pass_shape": (ci, []),
         "qb_crt_pass_rows": (ci, [i64, i64, ci, C.POINTER(i64), ci]),

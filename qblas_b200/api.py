@@ -312,6 +312,15 @@ def peer_close(ptr):
     check(lib().qb_peer_close(C.c_void_p(int(ptr))), "qb_peer_close")
 
 
+def set_host_slabs(slabs):
+    """C slabs of the pipelined all-host qgemm (default 4)."""
+    lib().qb_set_host_slabs(int(slabs))
+
+
+def get_host_slabs():
+    return lib().qb_get_host_slabs()
+
+
 def set_tensor_pass_shape(shape):
     """Residue scheme row passes: 0 = equal (default, measured), 1 = short first / last pass (experimental)."""
     lib().qb_set_tensor_pass_shape(int(shape))

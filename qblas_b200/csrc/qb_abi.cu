@@ -39,6 +39,7 @@ static int g_pass_min = 1;
 static int g_npeer = 0;                 /* fused gather of the next device qgemm (qb_set_gemm_peer_outputs); guarded by g_s.mu */
 static void *g_peer[QB_MAX_PEERS];
 static int g_peer_written = 0;
+static std::atomic<int> g_host_slabs{4}; /* C slabs of the pipelined all-host qgemm */
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
 int fast_variant() { return g_fastvar.load(); }
@@ -224,6 +225,8 @@ void qb_set_tensor_scheme(int scheme)
   oz_set_scheme(scheme);
 }
 int qb_get_tensor_scheme(void) { return oz_get_scheme(); }
+void qb_set_host_slabs(int slabs) { g_host_slabs.store(slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs)); }
+int qb_get_host_slabs(void) { return g_host_slabs.load(); }
 void qb_set_tensor_pass_shape(int shape)
 {
   std::lock_guard<std::recursive_mutex> lk(g_s.mu);
@@ -492,8 +495,9 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
           cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking) != cudaSuccess)
         return fail(QB_ERR_CUDA, "qgemm: stream creation", cudaGetLastError());
     }
-    constexpr int P = 4;
-    cudaEvent_t ev_in[P + 1], ev_done[P];
+    constexpr int PMAX = 16;
+    const int P = std::min(PMAX, std::max(1, g_host_slabs.load()));   /* default 4 (the measured setting), qb_set_host_slabs */
+    cudaEvent_t ev_in[PMAX + 1], ev_done[PMAX];
     for (int i = 0; i <= P; ++i) cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
     for (int i = 0; i < P; ++i) cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
     /* block [c0, c0+cnt) of a matrix X(outer, inner) with leading dimension ld, taken along `along_outer`:

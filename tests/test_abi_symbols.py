@@ -111,3 +111,4 @@ def test_measured_defaults():
     assert L.qb_get_tensor_keep() == 16           # digit-diagonal fallback: bounded setting
     assert L.qb_get_fast_variant() == 1           # qdot / qnrm2 / qgemv: window accumulator
     assert L.qb_get_gemm_peer_written() == 0
+    assert L.qb_get_host_slabs() == 4             # pipelined all-host qgemm: four C slabs
