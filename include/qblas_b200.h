@@ -86,9 +86,10 @@ int qb_get_kc(void);
 void qb_set_honor_trans(int on);         /* extension: honour transa/transb in qgemm (default 0) */
 int qb_get_honor_trans(void);
 
-/* Fast-mode qgemm on the tensor cores (exact int8 slicing + tcgen05 kind::i8, csrc/qb_ozaki.cu):
- * 0 = never (integer-limb kernel only), 1 = automatic (m,n >= 128 and k >= 256; default),
- * 2 = whenever the planner accepts the operands.  Ignored in QB_MODE_REFERENCE. */
+/* Fast-mode qgemm on the tensor cores (exact int8 residue planes + tcgen05 kind::i8 + Chinese-remainder reconstruction,
+ * csrc/qb_ozaki.cu, csrc/qb_crt.cuh): 0 = never (integer-limb kernel only), 1 = automatic (m,n >= 128 and k >= 256; default),
+ * 2 = whenever the planner accepts the operands.  Ignored in QB_MODE_REFERENCE.  Every finite or non-finite input is accepted
+ * (the planner only declines when not even one pipeline unit fits the free device memory); then the integer-limb kernel runs. */
 void qb_set_tensor_path(int v);
 int qb_get_tensor_path(void);
 /* Fast-mode accumulate of qdot / qnrm2 / qgemv: 1 (default) = unrounded 192-bit window accumulator
@@ -96,52 +97,57 @@ int qb_get_tensor_path(void);
  * reference's per-element operation, level1.hpp:24, re-associated).  Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
-/* Row-pass hook of the device qgemm (qb_gemm_dev).  When a callback is installed, the rows of C are produced in at
- * least `min_passes` passes (tensor path; the integer-limb kernel makes one) and cb(row0, rows, user) runs on the
- * calling host thread right after the work of each pass has been enqueued on the stream: a collective issued from the
- * callback (e.g. an all-gather of those rows, ordered after the stream's work so far) overlaps the next pass.  rows are
- * relative to the C passed to the call ("m" direction: rows for row-major, also rows of op(A) for col-major).  Every row
+/* Row-pass hook of the device qgemm (qb_gemm_dev only).  When a callback is installed, the rows of C are produced in
+ * min(min_passes, ceil(m / 128)) or more passes (tensor path; the integer-limb kernel makes one) and cb(row0, rows, user) runs on
+ * the calling host thread right after the work that completes those rows has been enqueued on the stream: a collective issued
+ * from the callback (e.g. an all-gather of those rows, ordered after the stream's work so far) overlaps the remaining work.
+ * rows are relative to the C passed to the call ("m" direction: rows for row-major, also rows of op(A) for col-major).  Every row
  * is reported exactly once.  cb = NULL removes the hook.  Used by qblas_b200/dist.py. */
 typedef void (*qb_pass_cb)(int64_t row0, int64_t rows, void *user);
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes);
-/* Accuracy setting of the tensor path.  keep = 0: every digit-plane product is computed, the inner
- * products are EXACT and rounded once.  keep = d > 0 (default 16): only the d most significant
- * diagonals are multiplied; every element is checked (|J| >= 2^125, csrc/qb_ozaki.cu) and the few that
- * fail are recomputed in the window accumulator, so the result always satisfies the fast-mode
- * contract |c^ - c| <= gamma_k (|A||B|)_ij, but it is no longer the exact sum rounded once. */
-void qb_set_tensor_keep(int keep);
-int qb_get_tensor_keep(void);
-/* How the tensor path forms the exact integer inner products.  1 (default) = residue scheme
- * (csrc/qb_crt.cuh): the block-fixed-point integers are reduced modulo N pairwise coprime moduli <= 256,
- * ONE int8 GEMM per modulus, exact Chinese-remainder reconstruction, one rounding - always exact, so
- * qb_set_tensor_keep does not apply; N = 41 for full 113-bit mantissas at k = 8192 (vs 324 / 136 digit-plane
- * products).  0 = digit diagonals (csrc/qb_ozaki.cu).  The residue scheme hands over to the digit
- * diagonals when its moduli cannot cover the operands' bit span (W_A + W_B + log2 k + 1 > 341) or k > 65536. */
-void qb_set_tensor_scheme(int scheme);
-int qb_get_tensor_scheme(void);
-/* Row passes of the residue scheme (they are software-pipelined: tensor kernel of pass p || residues of pass p+1 || fold of
- * pass p-1).  0 (default, the measured setting): equal passes.  1 (experimental, not yet measured on hardware): a short first
- * and a short last pass, whose residues / fold cannot hide behind a tensor pass.  Ignored while a row-pass callback is set.
- * qb_crt_pass_rows reports the partition the library would use for m rows with at most `cap` rows per pass (returns the
- * number of passes; out receives up to max_out sizes). */
-/* Large all-host qgemm calls (quadblas_qgemm / qb_gemm with host pointers) are pipelined: the shared operand is uploaded first,
- * then C is cut into `slabs` blocks whose uploads, compute and downloads overlap on three streams.  Default 4 (the measured
- * setting); more slabs shorten the tail after the last upload (1..16). */
+/* Streamed B (qb_gemm_dev only, fast-mode tensor path): op(B) reaches the device in column panels of `panel_cols` columns (a multiple
+ * of 256, or >= n) while the call is already computing — BASELINE config 4: the owner of B broadcasts it panel by panel and every rank
+ * multiplies panel j while panel j+1 is still on the wire.  Before the library enqueues the first work that reads columns
+ * [col0, col0 + cols) it calls cb(col0, cols, stream, &panel, &ld, user) on the calling host thread; the callee stores where that
+ * panel lives (*panel: its column col0 is element 0 of each row for row-major B; *ld: leading dimension in elements; same layout
+ * convention as the B argument) and makes `stream` (a cudaStream_t owned by the library) wait for the panel's arrival, e.g. with
+ * cudaStreamWaitEvent.  d_colstats: device array of 3 n ints from qb_gemm_colstats_dev on the COMPLETE op(B) (the owner computes
+ * it once and broadcasts these 12 n bytes first): the windows of all columns must be known before the first panel is reduced.
+ * The B argument of the call is then not dereferenced.  cb = NULL removes the hook.  Non-zero return of cb fails the call. */
+typedef int (*qb_bpanel_cb)(int64_t col0, int64_t cols, void *stream, const void **panel, int64_t *ld, void *user);
+void qb_set_gemm_b_panels(qb_bpanel_cb cb, void *user, int64_t panel_cols, const void *d_colstats);
+int qb_gemm_colstats_dev(char layout, char transb, int64_t k, int64_t n, const void *dB, int64_t ldb, void *d_colstats, void *stream);
+/* Window of the tensor path.  Rows of op(A) / columns of op(B) are block fixed point with W_A / W_B-bit integers; the moduli must
+ * cover W_A + W_B + log2(k) + 1 bits.  When the operands' bit spans fit into 2 x `bits` (every D53 / D113 input: 54 / 140 bits) the
+ * windows are the spans and the inner products are exact.  Wider spans (exponent spreads of tens of binades inside one row) are
+ * cut to the budget: low bits of the small elements of a row are dropped, every C element is tested against the dropped mass
+ * (csrc/qb_crt.cuh: accept_msb) and the few that fail are recomputed in the window accumulator, so the result always satisfies the
+ * fast-mode contract.  Default 144 (42 moduli at k = 8192), range 120..192. */
+void qb_set_tensor_window(int bits);
+int qb_get_tensor_window(void);
+/* Pipeline unit of the tensor path: (rows of an A pass) x (columns of a B panel), default 2048 x 2048; rows / cols <= 0 restore the
+ * default.  The tensor kernel of one unit overlaps the residues of the next pass / panel and the reconstruction of the previous unit. */
+void qb_set_tensor_unit(int64_t rows, int64_t cols);
+void qb_get_tensor_unit(int64_t *rows, int64_t *cols);
+/* Large all-host calls (quadblas_qgemm / quadblas_qgemv with host pointers) are pipelined: qgemm uploads the shared operand first,
+ * then the rows stream in, are multiplied and stream out in `slabs` blocks on three streams; qgemv uploads A in `slabs` row blocks
+ * while the earlier ones are multiplied.  Default 8 (1..16). */
 void qb_set_host_slabs(int slabs);
 int qb_get_host_slabs(void);
+/* the row-pass partition helper: m rows in passes of at most `cap` rows (shape 1: short first and last pass); returns the number
+ * of passes, out receives up to max_out sizes */
 void qb_set_tensor_pass_shape(int shape);
 int qb_get_tensor_pass_shape(void);
 int qb_crt_pass_rows(int64_t m, int64_t cap, int shape, int64_t *out, int max_out);
-/* plan of the last tensor-path qgemm: {S_A, S_B, diagonals, K chunks, row passes, digit-plane products
- * per row pass, workspace bytes, padded K, diagonals kept, elements sent to the fix-up, row passes
- * redone with all diagonals, residue-scheme word}.  Residue scheme: S_A / S_B = bytes of the widest row /
- * column integer, "diagonals" = "products" = N moduli, last word = 1 | W_A << 8 | W_B << 24 (bit spans);
- * digit diagonals: last word = 0. */
-void qb_oz_last_stats(int64_t *out12);
+/* plan of the last tensor-path qgemm (16 words): {moduli N (0: the tensor path did not run), W_A, W_B (window bits), widest span of
+ * an A row, of a B column, truncation word (bit 0 / 1: the window of A / B is narrower than the span, bit 2: Inf / NaN present),
+ * elements recomputed by the fix-up (waits for the call to finish), row passes, column panels, pipeline units, K chunks, padded K,
+ * workspace bytes, peers written, 0, 0} */
+void qb_oz_last_stats(int64_t *out16);
 /* Summed device time (ms, CUDA events on the launching stream) of the tcgen05 kernel launches of
  * the last tensor-path qgemm; waits for them to finish.  *launches (optional) = how many. */
 double qb_oz_last_mma_ms(int *launches);
-/* The tensor-core kernel alone (tests/profiling): D[d] = sum_{s+t=d} A_s B_t^T over k-blocks
+/* The tensor-core kernel alone (tests, the int8 peak microbenchmark): D[d] = sum_{s+t=d} A_s B_t^T over k-blocks
  * [kb_begin, kb_begin+nkb) of 128; planes are int8 [S][rows][Kp] (device), D is int32
  * [S_A+S_B-1][Mp][Np] with Mp % 128 == 0, Np % 256 == 0. */
 int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp,
@@ -156,7 +162,9 @@ int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB,
  *   qb_set_gemm_peer_outputs(c, ptrs) for the following qb_gemm_dev calls: ptrs[q] is the address, inside peer q's mapped
  *                                     buffer, that corresponds to the C argument of the call (same strides); count 0 = off
  *   qb_get_gemm_peer_written()        how many peers the LAST qb_gemm_dev wrote (0 when it ran a path without the fused
- *                                     stores - digit diagonals, integer-limb kernel - so the caller must gather itself)
+ *                                     stores - the integer-limb kernel - so the caller must gather itself)
+ * A peer address may also be an NVSwitch multicast address that maps the same buffer on every GPU of the node (one store then
+ * reaches all of them: qblas_b200/dist.py SymmetricBuffer): pass count = 1.
  * Completion: the peers' copies are complete when the call's stream work has finished on EVERY rank (barrier after it). */
 void *qb_peer_alloc(size_t bytes);
 void qb_peer_free(void *p);
@@ -175,12 +183,14 @@ int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void 
             int64_t incx, const qb_quad *beta, void *y, int64_t incy);
 int qb_dot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, qb_quad *result);
 int qb_nrm2(int64_t n, const void *x, int64_t incx, qb_quad *result);
+/* QuadBLAS::dot_kernel_vectorized (level1.hpp:14-35): the two-lane kernel over contiguous data in reference order, whatever
+ * the mode and the thread count */
+int qb_dot_kernel(int64_t n, const void *x, const void *y, qb_quad *result);
 int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *y, int64_t incy);
 
 /* Device pointers only, asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream).
  * d_result is a DEVICE pointer to 16 bytes.  No host synchronisation inside, with one exception: the fast-mode tensor path of
- * qb_gemm_dev waits once for its 3-integer plan (row / column bit spans) before it sizes the residue planes; the bounded
- * digit-diagonal setting also reads one counter per row pass.  The tensor path runs on internal streams that are ordered
+ * qb_gemm_dev waits once for its 3-integer plan (row / column bit spans) before it sizes the residue planes.  The tensor path runs on internal streams that are ordered
  * after `stream` at entry and that `stream` waits for before the call returns, so the caller sees plain stream order.
  * The library owns ONE grow-only workspace per process: calls issued on different streams must be ordered with respect to each
  * other by the caller (calls on one stream, or from one thread at a time on the default stream, always are). */

@@ -23,6 +23,7 @@
  * Loops are OpenMP-parallel over OUTPUT elements only; the reduction order inside an element is
  * exactly the reference's, so thread count never changes a bit.
  */
+#include <math.h>
 #include <quadmath.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -300,6 +301,181 @@ void orc_absdot_sample(char layout, long k_, const void *A_, long lda_, const vo
       s += fabsq(a) * fabsq(b);
     }
     out[t] = s;
+  }
+}
+
+/* ------------------------------------------------------------------ exact inner products (long accumulator) */
+/* The checker of the FAST mode: fast mode may re-associate, so its reference is not the rounding
+ * order of level3.hpp:77-85 but the exact inner product.  Every product of two binary128 values is added without rounding into a
+ * fixed-point two's-complement accumulator that spans the whole exponent range (66 560 bits, Kulisch style), which gives
+ *   exact[t]  = RNE(sum_l a_l b_l)                      (one rounding; gradual underflow and overflow as IEEE),
+ *   ratio[t]  = |got[t] - sum_l a_l b_l| / (gamma_k sum_l |a_l||b_l|),  gamma_k = k u / (1 - k u), u = 2^-113
+ *               (the fast-mode contract holds iff ratio <= 1; computed from the exact difference, rounded to double at the end),
+ *   klass[t]  = 0 finite data; otherwise the IEEE class of the sum of products: 1 NaN, 2 +Inf, 3 -Inf (ratio is then 0 when
+ *               got[t] is of that class and +Inf otherwise).
+ * Plain C on 64-bit words; test infrastructure like the rest of this file. */
+#define LACC_WORDS 1040
+#define LACC_OFF 33024            /* bit 0 of the accumulator is 2^-33024 <= the smallest product bit 2^-32988 */
+typedef struct { uint64_t w[LACC_WORDS]; } lacc;
+static void lacc_add_shifted(lacc *a, const uint64_t p[5], int word, int negative)
+{
+  if (!negative) {
+    unsigned __int128 c = 0;
+    for (int i = 0; i < 5; ++i) { c += (unsigned __int128)a->w[word + i] + p[i]; a->w[word + i] = (uint64_t)c; c >>= 64; }
+    for (int i = word + 5; c && i < LACC_WORDS; ++i) { c += a->w[i]; a->w[i] = (uint64_t)c; c >>= 64; }
+  } else {
+    uint64_t b = 0;
+    for (int i = 0; i < 5; ++i) {
+      const uint64_t x = a->w[word + i], y = p[i];
+      const uint64_t d = x - y - b;
+      b = (x < y) || (x == y && b) ? 1 : 0;
+      a->w[word + i] = d;
+    }
+    for (int i = word + 5; b && i < LACC_WORDS; ++i) { const uint64_t x = a->w[i]; a->w[i] = x - 1; b = x == 0; }
+  }
+}
+/* acc += (-1)^neg * ma * mb * 2^e with ma, mb < 2^113 given as (hi, lo) */
+static void lacc_add_product(lacc *a, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, int e, int neg)
+{
+  uint64_t p[4] = {0, 0, 0, 0};
+  {
+    unsigned __int128 t = (unsigned __int128)al * bl; p[0] = (uint64_t)t; unsigned __int128 c = t >> 64;
+    t = (unsigned __int128)al * bh; unsigned __int128 t2 = (unsigned __int128)ah * bl;
+    c += (uint64_t)t; c += (uint64_t)t2; p[1] = (uint64_t)c; c >>= 64;
+    c += (t >> 64); c += (t2 >> 64);
+    t = (unsigned __int128)ah * bh; c += (uint64_t)t; p[2] = (uint64_t)c; c >>= 64;
+    c += (t >> 64); p[3] = (uint64_t)c;
+  }
+  const int sh = e + LACC_OFF, word = sh >> 6, bit = sh & 63;
+  uint64_t q[5];
+  if (bit) { q[0] = p[0] << bit; q[1] = (p[1] << bit) | (p[0] >> (64 - bit)); q[2] = (p[2] << bit) | (p[1] >> (64 - bit)); q[3] = (p[3] << bit) | (p[2] >> (64 - bit)); q[4] = p[3] >> (64 - bit); }
+  else { q[0] = p[0]; q[1] = p[1]; q[2] = p[2]; q[3] = p[3]; q[4] = 0; }
+  lacc_add_shifted(a, q, word, neg);
+}
+/* unpack a finite binary128: value = (-1)^s (hi:lo) 2^e; returns 0 finite, 1 NaN, 2 Inf */
+static int q_unpack_bits(const Q *x, uint64_t *hi, uint64_t *lo, int *e, int *s)
+{
+  uint64_t w[2];
+  __builtin_memcpy(w, x, 16);
+  const int ef = (int)((w[1] >> 48) & 0x7fff);
+  *s = (int)(w[1] >> 63);
+  *lo = w[0]; *hi = w[1] & 0x0000ffffffffffffULL;
+  if (ef == 0x7fff) return (*hi | *lo) ? 1 : 2;
+  if (ef) { *hi |= 0x0001000000000000ULL; *e = ef - 16383 - 112; } else *e = 1 - 16383 - 112;
+  return 0;
+}
+static int lacc_negate_if_negative(lacc *a)
+{
+  if (!(a->w[LACC_WORDS - 1] >> 63)) return 0;
+  uint64_t c = 1;
+  for (int i = 0; i < LACC_WORDS; ++i) { const uint64_t v = ~a->w[i] + c; c = (c && v == 0) ? 1 : 0; a->w[i] = v; }
+  return 1;
+}
+static int lacc_top_bit(const lacc *a) /* -1 for zero */
+{
+  for (int i = LACC_WORDS - 1; i >= 0; --i) if (a->w[i]) return 64 * i + 63 - __builtin_clzll(a->w[i]);
+  return -1;
+}
+static int lacc_bit(const lacc *a, int pos) { return pos < 0 ? 0 : (int)((a->w[pos >> 6] >> (pos & 63)) & 1); }
+/* RNE of a non-negative accumulator to binary128 (sign applied by the caller) */
+static Q lacc_round(const lacc *a)
+{
+  const int top = lacc_top_bit(a);
+  if (top < 0) return 0.0Q;
+  int lsb = top - 112;
+  const int sub = -16494 + LACC_OFF;          /* position of the least significant subnormal bit */
+  if (lsb < sub) lsb = sub;
+  unsigned __int128 M = 0;
+  for (int pos = top; pos >= lsb; --pos) M = (M << 1) | (unsigned)lacc_bit(a, pos);
+  const int guard = lacc_bit(a, lsb - 1);
+  int sticky = 0;
+  if (lsb - 2 >= 0) {
+    const int pw = (lsb - 2) >> 6;
+    for (int i = 0; i < pw; ++i) sticky |= a->w[i] != 0;
+    const int nb = ((lsb - 2) & 63) + 1;
+    sticky |= (a->w[pw] & (nb == 64 ? ~0ULL : ((1ULL << nb) - 1))) != 0;
+  }
+  if (guard && (sticky || (M & 1))) M += 1;
+  const Q mq = (Q)(uint64_t)(M >> 64) * 18446744073709551616.0Q + (Q)(uint64_t)M;   /* <= 114 bits, the top one alone when 114: exact */
+  return ldexpq(mq, lsb - LACC_OFF);
+}
+/* non-negative accumulator = m * 2^(*e) with m < 2^64 + 1 rounded UP (relative error < 2^-62); 0 -> returns 0 */
+static double lacc_to_scaled(const lacc *a, int *e)
+{
+  const int top = lacc_top_bit(a);
+  *e = 0;
+  if (top < 0) return 0.0;
+  uint64_t m = 0;
+  for (int pos = top; pos > top - 64 && pos >= 0; --pos) m = (m << 1) | (unsigned)lacc_bit(a, pos);
+  const int used = top >= 63 ? 64 : top + 1;
+  *e = top + 1 - used - LACC_OFF;
+  return (double)m + 1.0;
+}
+void orc_exact_dot_check(char layout, long k_, const void *A_, long lda_, const void *B_, long ldb_, long ns, const int64_t *idx,
+                         const void *got_, void *exact_, double *ratio, int *klass)
+{
+  const Q *A = A_, *B = B_, *got = got_; Q *exact = exact_;
+  const size_t k = (size_t)k_, lda = (size_t)lda_, ldb = (size_t)ldb_;
+  const int col = (layout == 'C' || layout == 'c');
+#pragma omp parallel
+  {
+    lacc *acc = (lacc *)__builtin_malloc(sizeof(lacc)), *ab = (lacc *)__builtin_malloc(sizeof(lacc));
+#pragma omp for schedule(dynamic, 1)
+    for (long t = 0; t < ns; ++t) {
+      const size_t i = (size_t)idx[2 * t], j = (size_t)idx[2 * t + 1];
+      __builtin_memset(acc, 0, sizeof(lacc)); __builtin_memset(ab, 0, sizeof(lacc));
+      int nan = 0, pinf = 0, ninf = 0;
+      for (size_t l = 0; l < k; ++l) {
+        const Q *a = col ? &A[l * lda + i] : &A[i * lda + l];
+        const Q *b = col ? &B[j * ldb + l] : &B[l * ldb + j];
+        uint64_t ah, al, bh, bl; int ea, eb, sa, sb;
+        const int ca = q_unpack_bits(a, &ah, &al, &ea, &sa), cb = q_unpack_bits(b, &bh, &bl, &eb, &sb);
+        if (ca || cb) {
+          const int za = !ca && !(ah | al), zb = !cb && !(bh | bl);
+          if (ca == 1 || cb == 1 || za || zb) nan = 1;          /* NaN operand or Inf * 0 */
+          else if (sa ^ sb) ninf = 1; else pinf = 1;
+          continue;
+        }
+        if (!(ah | al) || !(bh | bl)) continue;
+        lacc_add_product(acc, ah, al, bh, bl, ea + eb, sa ^ sb);
+        lacc_add_product(ab, ah, al, bh, bl, ea + eb, 0);
+      }
+      const Q g = got ? got[t] : 0.0Q;
+      if (nan || pinf || ninf) {
+        const int kl = (nan || (pinf && ninf)) ? 1 : (pinf ? 2 : 3);
+        klass[t] = kl;
+        if (exact) exact[t] = kl == 1 ? nanq("") : (kl == 2 ? HUGE_VALQ : -HUGE_VALQ);
+        if (ratio) ratio[t] = !got ? 0.0 : ((kl == 1 ? isnanq(g) : (isinfq(g) && ((g < 0) == (kl == 3)))) ? 0.0 : HUGE_VAL);
+        continue;
+      }
+      klass[t] = 0;
+      {
+        lacc tmp = *acc;
+        const int neg = lacc_negate_if_negative(&tmp);
+        const Q r = lacc_round(&tmp);
+        if (exact) exact[t] = neg ? -r : r;
+      }
+      if (ratio) {
+        if (!got || isnanq(g) || isinfq(g)) { ratio[t] = got ? HUGE_VAL : 0.0; continue; }
+        uint64_t gh, gl; int ge, gs;
+        q_unpack_bits(&g, &gh, &gl, &ge, &gs);
+        if (gh | gl) lacc_add_product(acc, gh, gl, 0, 1, ge, !gs);      /* acc -= got (exactly) */
+        lacc_negate_if_negative(acc);
+        /* gamma_k >= k u: the bound is k u sum|a||b|; mantissas and exponents are kept apart so that sums far outside the range of
+         * double (2^-32000 .. 2^32000) still compare; the 2^-50 slack covers the two round-ups */
+        int ee, eb;
+        const double me = lacc_to_scaled(acc, &ee), mb = lacc_to_scaled(ab, &eb) * (1.0 - 0x1p-50);
+        if (me == 0.0) ratio[t] = 0.0;
+        else if (mb == 0.0) ratio[t] = HUGE_VAL;
+        else {
+          int d = ee - (eb - 113);
+          if (d > 2000) d = 2000;
+          if (d < -2000) d = -2000;
+          ratio[t] = ldexp(me / (mb * (double)k), d);
+        }
+      }
+    }
+    __builtin_free(acc); __builtin_free(ab);
   }
 }
 

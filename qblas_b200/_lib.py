@@ -10,6 +10,8 @@ import os
 
 # void (*qb_pass_cb)(int64_t row0, int64_t rows, void *user)  (include/qblas_b200.h)
 PASS_CB = C.CFUNCTYPE(None, C.c_int64, C.c_int64, C.c_void_p)
+# int (*qb_bpanel_cb)(int64_t col0, int64_t cols, void *stream, const void **panel, int64_t *ld, void *user)
+BPANEL_CB = C.CFUNCTYPE(C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqblas_b200.so")
@@ -63,9 +65,14 @@ def lib():
         "qb_get_honor_trans": (ci, []),
         "qb_set_tensor_path": (None, [ci]),
         "qb_get_tensor_path": (ci, []),
-        "qb_set_tensor_keep": (None, [ci]),
         "qb_set_gemm_pass_callback": (None, [PASS_CB, vp, ci]),
-        "qb_get_tensor_keep": (ci, []),
+        "qb_set_gemm_b_panels": (None, [BPANEL_CB, vp, i64, vp]),
+        "qb_gemm_colstats_dev": (ci, [cc, cc, i64, i64, vp, i64, vp, vp]),
+        "qb_set_tensor_window": (None, [ci]),
+        "qb_get_tensor_window": (ci, []),
+        "qb_set_tensor_unit": (None, [i64, i64]),
+        "qb_get_tensor_unit": (None, [C.POINTER(i64), C.POINTER(i64)]),
+        "qb_dot_kernel": (ci, [i64, vp, vp, qp]),
         "qb_peer_alloc": (vp, [C.c_size_t]),
         "qb_peer_free": (None, [vp]),
         "qb_peer_export": (ci, [vp, vp]),
@@ -78,8 +85,6 @@ def lib():
         "qb_set_tensor_pass_shape": (None, [ci]),
         "qb_get_tensor_pass_shape": (ci, []),
         "qb_crt_pass_rows": (ci, [i64, i64, ci, C.POINTER(i64), ci]),
-        "qb_set_tensor_scheme": (None, [ci]),
-        "qb_get_tensor_scheme": (ci, []),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),
@@ -117,4 +122,6 @@ def lib():
 def check(rc, what="qblas_b200 call"):
     if rc != 0:
         L = lib()
-        raise QblasError(f"{what} failed (code {rc}): {L.qb_last_error().decode()}")
+        msg = L.qb_last_error().decode()
+        L.qb_clear_error()      # the error is reported here: it must not make a later, successful call look failed
+        raise QblasError(f"{what} failed (code {rc}): {msg}")

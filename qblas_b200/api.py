@@ -252,13 +252,67 @@ def set_gemm_pass_callback(fn, min_passes=1):
     _pass_cb_ref = thunk
 
 
-def set_tensor_keep(keep):
-    """Tensor-path accuracy: 0 = all diagonals (exact inner products), d > 0 = the d leading diagonals + per-element check and fix-up."""
-    lib().qb_set_tensor_keep(int(keep))
+_bpanel_cb_ref = None
 
 
-def get_tensor_keep():
-    return lib().qb_get_tensor_keep()
+def set_gemm_b_panels(fn, panel_cols=0, colstats=None):
+    """Streamed B of the device qgemm (qb_set_gemm_b_panels): fn(col0, cols, stream_ptr) -> (panel_ptr, ld) is called before the library
+    reads columns [col0, col0 + cols) of op(B); it must make the CUDA stream `stream_ptr` wait for the panel's arrival (e.g.
+    torch.cuda.ExternalStream(stream_ptr).wait_event(...)).  colstats: device int32 tensor of 3 n entries from gemm_colstats.
+    fn = None removes the hook.  The ctypes thunk is kept alive here."""
+    global _bpanel_cb_ref
+    from ._lib import BPANEL_CB
+    if fn is None:
+        lib().qb_set_gemm_b_panels(C.cast(None, BPANEL_CB), None, 0, None)
+        _bpanel_cb_ref = None
+        return
+
+    def thunk(col0, cols, stream, panel, ld, user):
+        try:
+            ptr, ldv = fn(int(col0), int(cols), int(stream or 0))
+            panel[0] = int(ptr); ld[0] = int(ldv)
+            return 0
+        except Exception as e:   # never let an exception cross the C ABI
+            import sys
+            print(f"[qblas_b200] B-panel callback failed: {e!r}", file=sys.stderr, flush=True)
+            return 1
+
+    cb = BPANEL_CB(thunk)
+    lib().qb_set_gemm_b_panels(cb, None, int(panel_cols), C.c_void_p(colstats.data_ptr()))
+    _bpanel_cb_ref = (cb, colstats)
+
+
+def gemm_colstats(layout, k, n, B, ldb, out, transb="N"):
+    """Column statistics of op(B) (k x n) for set_gemm_b_panels: `out` = device int32 tensor with 3 n entries."""
+    check(lib().qb_gemm_colstats_dev(_c(layout), _c(transb), k, n, _ptr(B), ldb, C.c_void_p(out.data_ptr()), _stream()), "qb_gemm_colstats_dev")
+    return out
+
+
+def set_tensor_window(bits):
+    """Bits per operand window the tensor-path planner grants when the operands' spans do not fit the moduli (default 144)."""
+    lib().qb_set_tensor_window(int(bits))
+
+
+def get_tensor_window():
+    return lib().qb_get_tensor_window()
+
+
+def set_tensor_unit(rows=0, cols=0):
+    """Pipeline unit of the tensor path: rows of an A pass x columns of a B panel (default 2048 x 2048)."""
+    lib().qb_set_tensor_unit(int(rows), int(cols))
+
+
+def get_tensor_unit():
+    r, c = C.c_int64(0), C.c_int64(0)
+    lib().qb_get_tensor_unit(C.byref(r), C.byref(c))
+    return int(r.value), int(c.value)
+
+
+def dot_kernel(n, x, y):
+    """QuadBLAS::dot_kernel_vectorized (level1.hpp:14-35) on host arrays: the two-lane reference kernel whatever the mode / T."""
+    r = QbQuad()
+    check(lib().qb_dot_kernel(n, _ptr(x), _ptr(y), C.byref(r)), "qb_dot_kernel")
+    return np.array([r.lo, r.hi], dtype=np.uint64)
 
 
 def set_gemm_peer_outputs(ptrs):
@@ -337,15 +391,6 @@ def crt_pass_rows(m, cap, shape=0):
     return [int(out[i]) for i in range(min(cnt, 4096))]
 
 
-def set_tensor_scheme(scheme):
-    """Tensor-path scheme: 1 = residue planes + Chinese-remainder reconstruction (default), 0 = digit diagonals."""
-    lib().qb_set_tensor_scheme(int(scheme))
-
-
-def get_tensor_scheme():
-    return lib().qb_get_tensor_scheme()
-
-
 def set_fast_variant(v):
     """Fast-mode accumulate of dot/nrm2/gemv: 1 = window accumulator (csrc/qwide.cuh), 0 = rounded-FMA chains."""
     lib().qb_set_fast_variant(int(v))
@@ -356,15 +401,14 @@ def get_fast_variant():
 
 
 def oz_last_stats():
-    """Plan of the last tensor-path qgemm."""
-    out = (C.c_int64 * 12)()
+    """Plan of the last tensor-path qgemm (qb_oz_last_stats).  pairs = moduli = int8 GEMMs per product (0: the tensor path did not run)."""
+    out = (C.c_int64 * 16)()
     lib().qb_oz_last_stats(out)
-    keys = ["SA", "SB", "ndiag", "nchunks", "row_passes", "pairs", "ws_bytes", "Kp", "keep", "flagged", "redo_passes"]
+    keys = ["pairs", "WA", "WB", "WA_span", "WB_span", "truncated", "flagged", "row_passes", "panels", "units", "nchunks", "Kp", "ws_bytes", "peer_written"]
     d = {k: int(out[i]) for i, k in enumerate(keys)}
-    w = int(out[11])
-    d["scheme"] = "residues" if w & 1 else "digits"
-    if w & 1:
-        d["WA"] = (w >> 8) & 0xffff; d["WB"] = (w >> 24) & 0xffff; d["moduli"] = d["pairs"]
+    d["moduli"] = d["pairs"]
+    d["scheme"] = "residues"
+    d["exact"] = d["pairs"] > 0 and d["truncated"] == 0     # windows cover the spans, no Inf/NaN: inner products exact, rounded once
     return d
 
 

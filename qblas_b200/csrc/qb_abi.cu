@@ -22,6 +22,7 @@
 #include <thread>
 #include <unordered_set>
 #include <cstdlib>
+#include <strings.h>
 #include <limits>
 
 namespace qb {
@@ -32,18 +33,47 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_mode{QB_MODE_REFERENCE};
 static std::atomic<int> g_kc{126};
 static std::atomic<int> g_honor_trans{0};
-/* row-pass hook of the device qgemm (qb_set_gemm_pass_callback); used under the library mutex */
+/* hooks of the device qgemm (qb_set_gemm_pass_callback / qb_set_gemm_b_panels / qb_set_gemm_peer_outputs); used under the library mutex */
 static qb_pass_cb g_pass_cb = nullptr;
 static void *g_pass_user = nullptr;
 static int g_pass_min = 1;
-static int g_npeer = 0;                 /* fused gather of the next device qgemm (qb_set_gemm_peer_outputs); guarded by g_s.mu */
+static qb_bpanel_cb g_bp_cb = nullptr;
+static void *g_bp_user = nullptr;
+static int64_t g_bp_cols = 0;
+static const int *g_bp_stats = nullptr;
+static int g_npeer = 0;
 static void *g_peer[QB_MAX_PEERS];
 static int g_peer_written = 0;
-static std::atomic<int> g_host_slabs{4}; /* C slabs of the pipelined all-host qgemm */
+static std::atomic<int> g_host_slabs{8}; /* C slabs of the pipelined all-host qgemm / row slabs of the all-host qgemv */
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
 int fast_variant() { return g_fastvar.load(); }
-static std::atomic<int> g_threads{0}; /* 0 = not set -> hardware concurrency (omp_get_max_threads analogue) */
+static std::atomic<int> g_threads{0}; /* 0 = not set -> OMP_NUM_THREADS, then hardware concurrency (omp_get_max_threads) */
+
+/* Environment, read once when the library is loaded, so that an UNMODIFIED caller of the reference API can choose the
+ * numerical mode without a source change:
+ *   QUADBLAS_MODE = reference | fast      (default reference: bit for bit the reference's results)
+ *   QUADBLAS_KC   = k-panel of the reference-order qgemm (default 126, detail/blocking.hpp:46; 256 mimics Apple Silicon)
+ *   OMP_NUM_THREADS is read where the reference reads it: the default of quadblas_get_num_threads()
+ *   (threading/openmp_utils.hpp:10-17: omp_get_max_threads()), which defines the chunking of the reference-order dot. */
+static int env_threads()
+{
+  const char *v = getenv("OMP_NUM_THREADS");
+  if (!v || !*v) return 0;
+  const long t = strtol(v, nullptr, 10);     /* "a,b,c" (nested levels): the first entry is the outermost team size */
+  return t > 0 && t < (1 << 20) ? (int)t : 0;
+}
+struct EnvInit {
+  EnvInit()
+  {
+    if (const char *v = getenv("QUADBLAS_MODE")) {
+      if (!strcasecmp(v, "fast") || !strcmp(v, "1")) g_mode.store(QB_MODE_FAST);
+      else if (!strcasecmp(v, "reference") || !strcasecmp(v, "ref") || !strcmp(v, "0")) g_mode.store(QB_MODE_REFERENCE);
+    }
+    if (const char *v = getenv("QUADBLAS_KC")) { const long kc = strtol(v, nullptr, 10); if (kc > 0 && kc < (1 << 30)) g_kc.store((int)kc); }
+  }
+};
+static EnvInit g_env_init;
 
 static thread_local int t_err_code = 0;
 static thread_local char t_err_msg[512] = "";
@@ -55,54 +85,72 @@ static int fail(int code, const char *what, cudaError_t ce = cudaSuccess)
   else snprintf(t_err_msg, sizeof t_err_msg, "%s", what);
   return code;
 }
+static void clear_error() { t_err_code = 0; t_err_msg[0] = 0; }
 
 static int num_threads()
 {
   int t = g_threads.load();
+  if (t <= 0) t = env_threads();
   if (t <= 0) { t = (int)std::thread::hardware_concurrency(); if (t <= 0) t = 1; }
   return t;
 }
 
-/* ---- per-process device scratch (dot partials, staged scalars), guarded by a mutex ---- */
+/* ---- per-device scratch (dot partials, staged scalars, staging buffers, streams of the pipelined host paths); one mutex
+ * guards all of it.  ensure_device() selects the entry of the current CUDA device: a process that switches devices between
+ * calls gets an independent set per device. ---- */
 struct Scratch {
-  std::recursive_mutex mu;
-  int device = -1;
+  bool ready = false;
   q128 *work = nullptr; int64_t work_elems = 0;
   q128 *result = nullptr;
   void *stage[3] = {nullptr, nullptr, nullptr}; size_t stage_bytes[3] = {0, 0, 0};
+  cudaStream_t cs = nullptr, ks = nullptr, ds = nullptr;   /* copy-in, kernels, copy-out */
 };
-static Scratch g_s;
+static std::recursive_mutex g_mu;
+static Scratch g_scr[QB_MAX_DEVICES];
+static int g_curdev = 0;
+static inline Scratch &S() { return g_scr[g_curdev]; }
 
 static int ensure_device()
 {
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "no usable CUDA device (cudaGetDevice)", e);
-  if (g_s.device != dev) {
-    /* scratch belongs to one device; a different current device gets fresh scratch */
-    if (g_s.device >= 0) {
-      /* best effort release on the old device */
-      int cur = dev; cudaSetDevice(g_s.device);
-      cudaFree(g_s.work); cudaFree(g_s.result);
-      for (int i = 0; i < 3; ++i) { cudaFree(g_s.stage[i]); g_s.stage[i] = nullptr; g_s.stage_bytes[i] = 0; }
-      cudaSetDevice(cur);
-      g_s.work = nullptr; g_s.work_elems = 0; g_s.result = nullptr;
-    }
-    e = cudaMalloc((void **)&g_s.result, 64);
+  if (dev < 0 || dev >= QB_MAX_DEVICES) return fail(QB_ERR_CUDA, "device ordinal out of range");
+  g_curdev = dev;
+  Scratch &s = g_scr[dev];
+  if (!s.ready) {
+    e = cudaMalloc((void **)&s.result, 64);
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMalloc(result)", e);
-    g_s.device = dev;
+    s.ready = true;
   }
+  return QB_OK;
+}
+
+/* the three streams of the pipelined host paths, created together (all or none) */
+static int ensure_streams()
+{
+  Scratch &s = S();
+  if (s.cs) return QB_OK;
+  cudaStream_t t[3] = {nullptr, nullptr, nullptr};
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&t[i], cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    for (int i = 0; i < 3; ++i) if (t[i]) cudaStreamDestroy(t[i]);
+    return fail(QB_ERR_CUDA, "stream creation", e);
+  }
+  s.cs = t[0]; s.ks = t[1]; s.ds = t[2];
   return QB_OK;
 }
 
 static int ensure_work(int64_t elems)
 {
-  if (elems <= g_s.work_elems) return QB_OK;
-  cudaFree(g_s.work);
-  g_s.work = nullptr; g_s.work_elems = 0;
-  cudaError_t e = cudaMalloc((void **)&g_s.work, (size_t)elems * 16);
+  Scratch &s = S();
+  if (elems <= s.work_elems) return QB_OK;
+  cudaFree(s.work);
+  s.work = nullptr; s.work_elems = 0;
+  cudaError_t e = cudaMalloc((void **)&s.work, (size_t)elems * 16);
   if (e != cudaSuccess) return fail(QB_ERR_ALLOC, "cudaMalloc(work)", e);
-  g_s.work_elems = elems;
+  s.work_elems = elems;
   return QB_OK;
 }
 
@@ -119,17 +167,18 @@ static bool is_device_ptr(const void *p)
 static int stage_in(int slot, const void *src, size_t bytes, bool copy, const void **dptr, bool *staged)
 {
   if (bytes == 0 || is_device_ptr(src)) { *dptr = src; *staged = false; return QB_OK; }
-  if (g_s.stage_bytes[slot] < bytes) {
-    cudaFree(g_s.stage[slot]); g_s.stage[slot] = nullptr; g_s.stage_bytes[slot] = 0;
-    cudaError_t e = cudaMalloc(&g_s.stage[slot], bytes);
+  Scratch &s = S();
+  if (s.stage_bytes[slot] < bytes) {
+    cudaFree(s.stage[slot]); s.stage[slot] = nullptr; s.stage_bytes[slot] = 0;
+    cudaError_t e = cudaMalloc(&s.stage[slot], bytes);
     if (e != cudaSuccess) return fail(QB_ERR_ALLOC, "cudaMalloc(staging)", e);
-    g_s.stage_bytes[slot] = bytes;
+    s.stage_bytes[slot] = bytes;
   }
   if (copy) {
-    cudaError_t e = cudaMemcpy(g_s.stage[slot], src, bytes, cudaMemcpyHostToDevice);
+    cudaError_t e = cudaMemcpy(s.stage[slot], src, bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMemcpy H2D", e);
   }
-  *dptr = g_s.stage[slot];
+  *dptr = s.stage[slot];
   *staged = true;
   return QB_OK;
 }
@@ -142,10 +191,25 @@ static inline bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' ||
 static inline size_t vec_bytes(int64_t n, int64_t inc) { return n <= 0 ? 0 : (size_t)((n - 1) * inc + 1) * 16; }
 static inline size_t mat_bytes(int64_t outer, int64_t inner, int64_t ld) { return (outer <= 0 || inner <= 0) ? 0 : (size_t)((outer - 1) * ld + inner) * 16; }
 
-static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, int64_t k, q128 alpha, const void *dA,
-                         int64_t lda, const void *dB, int64_t ldb, q128 beta, void *dC, int64_t ldc, cudaStream_t st, bool peers = false)
+/* a handful of ordering events for one pipelined host call; destroyed on scope exit */
+struct EventSet {
+  std::vector<cudaEvent_t> ev;
+  bool make(int count)
+  {
+    while ((int)ev.size() < count) {
+      cudaEvent_t e;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+      ev.push_back(e);
+    }
+    return true;
+  }
+  ~EventSet() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+};
+
+/* (layout, transposes, leading dimensions) -> the stride form the kernels take */
+static GemmArgs make_gemm_args(char layout, char ta, char tb, int64_t m, int64_t n, int64_t k, q128 alpha, const void *dA, int64_t lda, const void *dB,
+                               int64_t ldb, q128 beta, void *dC, int64_t ldc)
 {
-  if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
   const bool col = is_col(layout);
   const bool honor = g_honor_trans.load() != 0;
   const bool tA = honor && is_trans(ta), tB = honor && is_trans(tb);
@@ -157,25 +221,84 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
   if (col != tB) { g.sbl = 1; g.sbj = ldb; } else { g.sbl = ldb; g.sbj = 1; }
   if (col) { g.sci = 1; g.scj = ldc; } else { g.sci = ldc; g.scj = 1; }
   g.kc = g_kc.load();
+  return g;
+}
+/* C^T = op(B)^T op(A)^T: the same product with the roles of the operands exchanged (rows of the new problem = columns of C) */
+static void swap_roles(GemmArgs &g)
+{
+  std::swap(g.m, g.n);
+  const q128 *A0 = g.A; const int64_t sai0 = g.sai, sal0 = g.sal;
+  g.A = g.B; g.sai = g.sbj; g.sal = g.sbl;
+  g.B = A0; g.sbl = sal0; g.sbj = sai0;
+  std::swap(g.sci, g.scj);
+}
+
+/* hooks of the all-host tensor-path qgemm: slabs of rows arrive on the copy-in stream (events ev_in[p]), finished passes leave on
+ * the copy-out stream */
+struct HostPipe {
+  cudaEvent_t *ev_in; int P; int64_t blk;
+  cudaStream_t ks, ds;
+  EventSet *out_ev; int out_used;
+  void *dC; void *hC; int64_t outer, inner, ldc;   /* C as (outer x inner) storage: slabs along `outer` are contiguous */
+  cudaError_t err;
+};
+static int host_rows_in(int64_t r0, int64_t rows, void *sA, void *sF, void *user)
+{
+  HostPipe *hp = (HostPipe *)user;
+  int idx = (int)((r0 + rows - 1) / hp->blk);
+  if (idx >= hp->P) idx = hp->P - 1;
+  cudaError_t e = cudaStreamWaitEvent((cudaStream_t)sA, hp->ev_in[idx], 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)sF, hp->ev_in[idx], 0);
+  if (e != cudaSuccess) { hp->err = e; return 1; }
+  return 0;
+}
+static void host_rows_out(int64_t r0, int64_t rows, void *user)
+{
+  HostPipe *hp = (HostPipe *)user;
+  if (hp->err != cudaSuccess || rows <= 0) return;
+  if (!hp->out_ev->make(hp->out_used + 1)) { hp->err = cudaErrorMemoryAllocation; return; }
+  cudaEvent_t ev = hp->out_ev->ev[hp->out_used++];
+  cudaError_t e = cudaEventRecord(ev, hp->ks);            /* ks already waits for the reconstruction of these rows */
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->ds, ev, 0);
+  const size_t off = (size_t)r0 * hp->ldc * 16, bytes = ((size_t)(rows - 1) * hp->ldc + hp->inner) * 16;
+  if (e == cudaSuccess) e = cudaMemcpyAsync((char *)hp->hC + off, (char *)hp->dC + off, bytes, cudaMemcpyDeviceToHost, hp->ds);
+  if (e != cudaSuccess) hp->err = e;
+}
+
+/* `hooks`: the call comes from qb_gemm_dev, the only entry point that takes the row-pass callback, the streamed-B panels and
+ * the peer outputs (the host paths below call this function per slab and must not fire them) */
+static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, int64_t k, q128 alpha, const void *dA,
+                         int64_t lda, const void *dB, int64_t ldb, q128 beta, void *dC, int64_t ldc, cudaStream_t st, bool hooks = false)
+{
+  if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
+  GemmArgs g = make_gemm_args(layout, ta, tb, m, n, k, alpha, dA, lda, dB, ldb, beta, dC, ldc);
   const int mode = g_mode.load(), tp = g_tensor.load();
-  if (mode == QB_MODE_FAST && m > 0 && n > 0 && k > 0 && (tp == 2 || (tp == 1 && m >= 128 && n >= 128 && k >= 256))) {
-    /* tensor-core path (exact int8 slicing, qb_ozaki.cu); declines -> integer-limb kernel below */
-    std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  const bool streamed = hooks && g_bp_cb != nullptr;
+  if (streamed && !(mode == QB_MODE_FAST && tp != 0)) return fail(QB_ERR_ARG, "qgemm: streamed B panels need the fast-mode tensor path");
+  if (mode == QB_MODE_FAST && m > 0 && n > 0 && k > 0 && (tp == 2 || streamed || (tp == 1 && m >= 128 && n >= 128 && k >= 256))) {
+    /* tensor-core path (exact int8 residues, qb_ozaki.cu); declines -> integer-limb kernel below */
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
     const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
     int used = 0;
-    g.npeer = peers ? g_npeer : 0;   /* only the device entry point (qb_gemm_dev) takes peer outputs */
-    for (int q = 0; q < g.npeer; ++q) g.peerC[q] = (q128 *)g_peer[q];
+    OzHooks h;
+    if (hooks) {
+      h.cb = (oz_pass_cb)g_pass_cb; h.cb_user = g_pass_user; h.min_passes = g_pass_min;
+      h.bp = (oz_bpanel_cb)g_bp_cb; h.bp_user = g_bp_user; h.bp_cols = g_bp_cols; h.bstats = g_bp_stats;
+      g.npeer = g_npeer;
+      for (int q = 0; q < g.npeer; ++q) g.peerC[q] = (q128 *)g_peer[q];
+    }
     g_peer_written = 0;
-    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget, (oz_pass_cb)g_pass_cb, g_pass_user, g_pass_min);
+    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget, h);
     if (oe != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm tensor path", oe);
     if (used) { g_peer_written = oz_last_stats().peer_written; return QB_OK; }
+    if (streamed) return fail(QB_ERR_ALLOC, "qgemm: the tensor path declined a streamed-B call (workspace)");
   }
   g_peer_written = 0;
   cudaError_t e = launch_gemm(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm kernel launch", e);
-  if (g_pass_cb && m > 0) g_pass_cb(0, m, g_pass_user);   /* the integer-limb kernel produces all rows in one launch */
+  if (hooks && g_pass_cb && m > 0) g_pass_cb(0, m, g_pass_user);   /* the integer-limb kernel produces all rows in one launch */
   return QB_OK;
 }
 
@@ -188,18 +311,18 @@ extern "C" {
 /* ------------------------------------------------------------------ housekeeping */
 int qb_init(void)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   cudaDeviceProp pr;
-  cudaError_t e = cudaGetDeviceProperties(&pr, g_s.device);
+  cudaError_t e = cudaGetDeviceProperties(&pr, g_curdev);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaGetDeviceProperties", e);
   if (pr.major < 10) return fail(QB_ERR_CUDA, "qblas_b200 is built for sm_100a only; this device is older");
   return QB_OK;
 }
 const char *qb_last_error(void) { return t_err_msg; }
 int qb_last_error_code(void) { return t_err_code; }
-void qb_clear_error(void) { t_err_code = 0; t_err_msg[0] = 0; }
+void qb_clear_error(void) { clear_error(); }
 const char *qb_build_info(void) { return "qblas_b200 1.0.0 (sm_100a, integer-limb binary128; modes: reference-order, fast)"; }
 
 void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : QB_MODE_REFERENCE); }
@@ -210,26 +333,41 @@ void qb_set_fast_variant(int v) { g_fastvar.store(v ? 1 : 0); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   g_pass_cb = cb; g_pass_user = user; g_pass_min = min_passes < 1 ? 1 : min_passes;
 }
-void qb_set_tensor_keep(int keep)
+void qb_set_gemm_b_panels(qb_bpanel_cb cb, void *user, int64_t panel_cols, const void *d_colstats)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
-  oz_set_keep(keep);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  g_bp_cb = cb; g_bp_user = user; g_bp_cols = cb ? panel_cols : 0; g_bp_stats = cb ? (const int *)d_colstats : nullptr;
 }
-int qb_get_tensor_keep(void) { return oz_get_keep(); }
-void qb_set_tensor_scheme(int scheme)
+int qb_gemm_colstats_dev(char layout, char transb, int64_t k, int64_t n, const void *dB, int64_t ldb, void *d_colstats, void *stream)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
-  oz_set_scheme(scheme);
+  if (k < 0 || n < 0) return fail(QB_ERR_ARG, "qb_gemm_colstats_dev: negative dimension");
+  if (k == 0 || n == 0) return QB_OK;
+  const bool col = is_col(layout), tB = g_honor_trans.load() != 0 && is_trans(transb);
+  const int64_t sbl = (col != tB) ? 1 : ldb, sbj = (col != tB) ? ldb : 1;
+  cudaError_t e = launch_colstats((const q128 *)dB, n, k, sbj, sbl, (int *)d_colstats, (cudaStream_t)stream);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "column statistics launch", e);
+  return QB_OK;
 }
-int qb_get_tensor_scheme(void) { return oz_get_scheme(); }
+void qb_set_tensor_window(int bits)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  oz_set_window(bits);
+}
+int qb_get_tensor_window(void) { return oz_get_window(); }
+void qb_set_tensor_unit(int64_t rows, int64_t cols)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  oz_set_unit(rows, cols);
+}
+void qb_get_tensor_unit(int64_t *rows, int64_t *cols) { oz_get_unit(rows, cols); }
 void qb_set_host_slabs(int slabs) { g_host_slabs.store(slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs)); }
 int qb_get_host_slabs(void) { return g_host_slabs.load(); }
 void qb_set_tensor_pass_shape(int shape)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   oz_set_pass_shape(shape);
 }
 int qb_get_tensor_pass_shape(void) { return oz_get_pass_shape(); }
@@ -243,7 +381,7 @@ int qb_crt_pass_rows(int64_t m, int64_t cap, int shape, int64_t *out, int max_ou
 /* ---- peer memory (fused gather of the row-sharded qgemm) ---- */
 void *qb_peer_alloc(size_t bytes)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (ensure_device()) return nullptr;
   void *p = nullptr;
   cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
@@ -262,7 +400,7 @@ int qb_peer_export(void *p, void *handle64)
 }
 void *qb_peer_open(const void *handle64)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (ensure_device()) return nullptr;
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
@@ -279,23 +417,24 @@ int qb_peer_close(void *p)
 }
 int qb_set_gemm_peer_outputs(int count, void *const *peer_C)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   if (count < 0 || count > QB_MAX_PEERS || (count > 0 && !peer_C)) return fail(QB_ERR_ARG, "qb_set_gemm_peer_outputs: 0 <= count <= 8");
   g_npeer = count;
   for (int q = 0; q < count; ++q) g_peer[q] = peer_C[q];
   return QB_OK;
 }
 int qb_get_gemm_peer_written(void) { return g_peer_written; }
-void qb_oz_last_stats(int64_t *out12)
+void qb_oz_last_stats(int64_t *out16)
 {
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   const OzStats s = oz_last_stats();
-  out12[0] = s.SA; out12[1] = s.SB; out12[2] = s.ndiag; out12[3] = s.nchunks; out12[4] = s.row_passes; out12[5] = s.pairs; out12[6] = s.ws_bytes;
-  out12[7] = s.Kp; out12[8] = s.keep; out12[9] = s.flagged; out12[10] = s.redo_passes;
-  out12[11] = s.scheme ? (int64_t)1 | ((int64_t)s.WA << 8) | ((int64_t)s.WB << 24) : 0;
+  out16[0] = s.pairs; out16[1] = s.WA; out16[2] = s.WB; out16[3] = s.WA_nat; out16[4] = s.WB_nat; out16[5] = s.truncated; out16[6] = s.flagged;
+  out16[7] = s.row_passes; out16[8] = s.panels; out16[9] = s.units; out16[10] = s.nchunks; out16[11] = s.Kp; out16[12] = s.ws_bytes;
+  out16[13] = s.peer_written; out16[14] = 0; out16[15] = 0;
 }
 double qb_oz_last_mma_ms(int *launches)
 {
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   return oz_last_mma_ms(launches);
 }
 int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int64_t kb_begin,
@@ -376,34 +515,35 @@ int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const v
   g.work = nullptr; g.work_elems = 0;
   const int mode = g_mode.load();
   const int64_t need = gemv_work_elems(m, n, g.col_major, mode);
-  std::unique_lock<std::recursive_mutex> lk(g_s.mu, std::defer_lock);
+  std::unique_lock<std::recursive_mutex> lk(g_mu, std::defer_lock);
   if (need > 0) { /* the shared scratch is held until the launch is queued (stream order protects its reuse) */
     lk.lock();
     int rc = ensure_device();
     if (rc) return rc;
     rc = ensure_work(need);
     if (rc) return rc;
-    g.work = g_s.work; g.work_elems = g_s.work_elems;
+    g.work = S().work; g.work_elems = S().work_elems;
   }
   cudaError_t e = launch_gemv(g, mode, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv kernel launch", e);
   return QB_OK;
 }
 
+/* force_T > 0: reference order with that many chunks whatever the mode (qb_dot_kernel: T = 1 is dot_kernel_vectorized) */
 static int dot_dev_impl(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t incy, int do_sqrt,
-                        void *d_result, cudaStream_t st)
+                        void *d_result, cudaStream_t st, int force_T = 0)
 {
   if (n < 0) return fail(QB_ERR_ARG, "qdot: negative n");
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
-  const int mode = g_mode.load();
-  const int T = num_threads();
+  const int mode = force_T > 0 ? (int)QB_MODE_REFERENCE : g_mode.load();
+  const int T = force_T > 0 ? force_T : num_threads();
   rc = ensure_work(dot_work_elems(n, T, mode));
   if (rc) return rc;
   DotArgs g;
   g.n = n; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
-  g.T = T; g.do_sqrt = do_sqrt; g.result = (q128 *)d_result; g.work = g_s.work; g.work_elems = g_s.work_elems;
+  g.T = T; g.do_sqrt = do_sqrt; g.result = (q128 *)d_result; g.work = S().work; g.work_elems = S().work_elems;
   cudaError_t e = launch_dot(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot kernel launch", e);
   return QB_OK;
@@ -425,14 +565,14 @@ int qb_dot_partials_dev(int64_t n_local, const void *dx, int64_t incx, const voi
                         int64_t nchunks, void *d_partials, void *stream)
 {
   if (n_local < 0 || nchunks < 0 || chunk < 0) return fail(QB_ERR_ARG, "qdot partials: negative argument");
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   rc = ensure_work(3 * nchunks + 4);
   if (rc) return rc;
   DotArgs g;
   g.n = n_local; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
-  g.T = (int)nchunks; g.do_sqrt = 0; g.result = nullptr; g.work = g_s.work; g.work_elems = g_s.work_elems;
+  g.T = (int)nchunks; g.do_sqrt = 0; g.result = nullptr; g.work = S().work; g.work_elems = S().work_elems;
   cudaError_t e = launch_dot_partials(g, chunk, (int)nchunks, (q128 *)d_partials, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot partials launch", e);
   return QB_OK;
@@ -465,7 +605,7 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
 {
   if (m < 0 || n < 0 || k < 0) return fail(QB_ERR_ARG, "qgemm: negative dimension");
   if (m == 0 || n == 0 || k == 0) return QB_OK; /* level3.hpp:221 */
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   const bool col = is_col(layout);
@@ -489,17 +629,13 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
     if ((rc = stage_in(0, A, a_bytes, false, &dA, &sa))) return rc;
     if ((rc = stage_in(1, B, b_bytes, false, &dB, &sb))) return rc;
     if ((rc = stage_in(2, C, c_bytes, false, &dC, &sc))) return rc;
-    static cudaStream_t cs = nullptr, ks = nullptr, ds = nullptr;
-    if (!cs) {
-      if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ks, cudaStreamNonBlocking) != cudaSuccess ||
-          cudaStreamCreateWithFlags(&ds, cudaStreamNonBlocking) != cudaSuccess)
-        return fail(QB_ERR_CUDA, "qgemm: stream creation", cudaGetLastError());
-    }
+    if ((rc = ensure_streams())) return rc;
+    const cudaStream_t cs = S().cs, ks = S().ks, ds = S().ds;
     constexpr int PMAX = 16;
-    const int P = std::min(PMAX, std::max(1, g_host_slabs.load()));   /* default 4 (the measured setting), qb_set_host_slabs */
-    cudaEvent_t ev_in[PMAX + 1], ev_done[PMAX];
-    for (int i = 0; i <= P; ++i) cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming);
-    for (int i = 0; i < P; ++i) cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming);
+    const int P = std::min(PMAX, std::max(1, g_host_slabs.load()));   /* qb_set_host_slabs */
+    EventSet evs;
+    if (!evs.make(2 * P + 1)) return fail(QB_ERR_CUDA, "qgemm: event creation", cudaGetLastError());
+    cudaEvent_t *ev_in = evs.ev.data(), *ev_done = evs.ev.data() + P + 1;
     /* block [c0, c0+cnt) of a matrix X(outer, inner) with leading dimension ld, taken along `along_outer`:
      * a contiguous slab when taken along the strided direction, a 2-D copy otherwise */
     auto xfer = [&](void *dev, void *host, bool to_dev, bool along_outer, int64_t outer, int64_t inner, int64_t ld, int64_t c0, int64_t cnt,
@@ -530,7 +666,33 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       if (e == cudaSuccess) e = cudaEventRecord(ev_in[p], cs);
     }
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, ev_in[P], 0);
-    for (int p = 0; p < P && e == cudaSuccess && rc == QB_OK; ++p) {
+    /* fast mode: ONE tensor-path call whose row passes wait for their slabs (passes outer: the residue planes of the shared
+     * operand are computed once and stay resident) and whose finished passes are downloaded while the next ones compute */
+    bool streamed = false;
+    const int mode = g_mode.load(), tp = g_tensor.load();
+    if (e == cudaSuccess && mode == QB_MODE_FAST && (tp == 2 || (tp == 1 && m >= 128 && n >= 128 && k >= 256))) {
+      GemmArgs g = make_gemm_args(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), (void *)dC, ldc);
+      if (col) swap_roles(g);
+      EventSet out_ev;
+      HostPipe hp;
+      hp.ev_in = ev_in; hp.P = P; hp.blk = blk; hp.ks = ks; hp.ds = ds; hp.out_ev = &out_ev; hp.out_used = 0;
+      hp.dC = (void *)dC; hp.hC = C; hp.outer = col ? n : m; hp.inner = col ? m : n; hp.ldc = ldc; hp.err = cudaSuccess;
+      OzHooks h;
+      h.order = 1; h.rows_in = host_rows_in; h.rows_user = &hp; h.cb = host_rows_out; h.cb_user = &hp;
+      h.min_passes = (int)std::min<int64_t>(4096, (split + 1023) / 1024);     /* passes of <= 1024 rows: a short tail after the last upload */
+      size_t fr = 0, tot = 0;
+      cudaMemGetInfo(&fr, &tot);
+      const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
+      int used = 0;
+      const cudaError_t oe = launch_gemm_ozaki(g, ks, &used, budget, h);
+      if (oe != cudaSuccess || hp.err != cudaSuccess) {
+        cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds);
+        return fail(QB_ERR_CUDA, "qgemm pipelined host path (tensor)", oe != cudaSuccess ? oe : hp.err);
+      }
+      streamed = used != 0;
+      if (streamed) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds); }   /* out_ev is destroyed with this scope */
+    }
+    for (int p = 0; p < P && e == cudaSuccess && rc == QB_OK && !streamed; ++p) {
       const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
       if (cnt <= 0) break;
       e = cudaStreamWaitEvent(ks, ev_in[p], 0);
@@ -547,8 +709,6 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       if (e == cudaSuccess) e = xfer((void *)dC, C, false, true, col ? n : m, col ? m : n, ldc, c0, cnt, ds);
     }
     cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ks), e4 = cudaStreamSynchronize(ds);
-    for (int i = 0; i <= P; ++i) cudaEventDestroy(ev_in[i]);
-    for (int i = 0; i < P; ++i) cudaEventDestroy(ev_done[i]);
     if (rc) return rc;
     if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm pipelined host path", e);
@@ -570,13 +730,52 @@ int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void 
 {
   if (m < 0 || n < 0) return fail(QB_ERR_ARG, "qgemv: negative dimension");
   if (m == 0 || n == 0) return QB_OK;
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   const bool col = is_col(layout);
   const size_t a_bytes = col ? mat_bytes(n, m, lda) : mat_bytes(m, n, lda);
   const size_t x_bytes = vec_bytes(n, incx), y_bytes = vec_bytes(m, incy);
   const void *dA, *dx, *dy; bool sa, sx, sy;
+  /* Large host A (16 GiB at 32768^2): the upload is the whole cost, so A goes up in row slabs (rows of y) on a copy stream
+   * while the kernels of the earlier slabs run: contiguous blocks for row-major, 2-D copies of a row range of every column
+   * for col-major.  Each slab is an ordinary qgemv on its rows: every y_i sees exactly the arithmetic of the unsplit call. */
+  if (!is_device_ptr(A) && m >= 1024 && a_bytes >= ((size_t)64 << 20)) {
+    if ((rc = stage_in(0, A, a_bytes, false, &dA, &sa))) return rc;
+    if ((rc = stage_in(1, x, x_bytes, true, &dx, &sx))) return rc;
+    if ((rc = stage_in(2, y, y_bytes, true, &dy, &sy))) return rc;
+    if ((rc = ensure_streams())) return rc;
+    const cudaStream_t cs = S().cs, ks = S().ks;
+    constexpr int PMAX = 16;
+    const int P = std::min(PMAX, std::max(1, g_host_slabs.load()));
+    EventSet evs;
+    if (!evs.make(P)) return fail(QB_ERR_CUDA, "qgemv: event creation", cudaGetLastError());
+    const int64_t blk = ((m + P - 1) / P + 31) / 32 * 32;
+    cudaError_t e = cudaSuccess;
+    for (int p = 0; p < P && e == cudaSuccess; ++p) {
+      const int64_t r0 = (int64_t)p * blk, cnt = std::min(blk, m - r0);
+      if (cnt <= 0) break;
+      if (!col) {
+        const size_t off = (size_t)r0 * lda * 16, bytes = ((size_t)(cnt - 1) * lda + n) * 16;
+        e = cudaMemcpyAsync((char *)dA + off, (const char *)A + off, bytes, cudaMemcpyHostToDevice, cs);
+      } else {
+        const size_t off = (size_t)r0 * 16;
+        e = cudaMemcpy2DAsync((char *)dA + off, (size_t)lda * 16, (const char *)A + off, (size_t)lda * 16, (size_t)cnt * 16, (size_t)n, cudaMemcpyHostToDevice, cs);
+      }
+      if (e == cudaSuccess) e = cudaEventRecord(evs.ev[p], cs);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, evs.ev[p], 0);
+      if (e != cudaSuccess) break;
+      const q128 *As = (const q128 *)dA + (col ? r0 : r0 * lda);
+      rc = qb_gemv_dev(layout, cnt, n, alpha, As, lda, dx, incx, beta, (q128 *)dy + r0 * incy, incy, ks);
+      if (rc) break;
+    }
+    const cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ks);
+    if (rc) return rc;
+    if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : e3;
+    if (e == cudaSuccess && sy) e = cudaMemcpy(y, dy, y_bytes, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv pipelined host path", e);
+    return QB_OK;
+  }
   if ((rc = stage_in(0, A, a_bytes, true, &dA, &sa))) return rc;
   if ((rc = stage_in(1, x, x_bytes, true, &dx, &sx))) return rc;
   if ((rc = stage_in(2, y, y_bytes, true, &dy, &sy))) return rc;
@@ -588,20 +787,20 @@ int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void 
   return QB_OK;
 }
 
-static int dot_host_impl(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, int do_sqrt, qb_quad *result)
+static int dot_host_impl(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, int do_sqrt, qb_quad *result, int force_T = 0)
 {
   if (n < 0) return fail(QB_ERR_ARG, "qdot: negative n");
   const void *dx, *dy; bool sx = false, sy = false;
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   if ((rc = stage_in(0, x, vec_bytes(n, incx), true, &dx, &sx))) return rc;
-  if (y == x) { dy = dx; }
+  if (y == x && incy == incx) { dy = dx; }   /* same vector: one staged copy serves both (different strides read different extents) */
   else if ((rc = stage_in(1, y, vec_bytes(n, incy), true, &dy, &sy))) return rc;
-  rc = dot_dev_impl(n, dx, incx, dy, incy, do_sqrt, g_s.result, 0);
+  rc = dot_dev_impl(n, dx, incx, dy, incy, do_sqrt, S().result, 0, force_T);
   if (rc) return rc;
   q128 r;
-  cudaError_t e = cudaMemcpy(&r, g_s.result, 16, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(&r, S().result, 16, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot result copy", e);
   result->lo = r.lo; result->hi = r.hi;
   return QB_OK;
@@ -611,11 +810,16 @@ int qb_dot(int64_t n, const void *x, int64_t incx, const void *y, int64_t incy, 
 { return dot_host_impl(n, x, incx, y, incy, 0, result); }
 int qb_nrm2(int64_t n, const void *x, int64_t incx, qb_quad *result)
 { return dot_host_impl(n, x, incx, x, incx, 1, result); }
+/* QuadBLAS::dot_kernel_vectorized (level1.hpp:14-35): the two-lane kernel over contiguous data, whatever the mode and the thread
+ * count: even / odd chains from +0, add(lane0, lane1), odd tail.  (dot with ONE chunk is that kernel followed by add(+0, r),
+ * and r is never -0, so the bits are the kernel's.) */
+int qb_dot_kernel(int64_t n, const void *x, const void *y, qb_quad *result)
+{ return dot_host_impl(n, x, 1, y, 1, 0, result, 1); }
 
 int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *y, int64_t incy)
 {
   if (n <= 0) return QB_OK; /* c_interface.hpp:49 */
-  std::lock_guard<std::recursive_mutex> lk(g_s.mu);
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
   int rc = ensure_device();
   if (rc) return rc;
   const void *dx, *dy; bool sx, sy;
@@ -632,6 +836,7 @@ int qb_axpy(int64_t n, const qb_quad *alpha, const void *x, int64_t incx, void *
 /* ------------------------------------------------------------------ reference C ABI */
 double quadblas_qdot(int n, void *x, int incx, void *y, int incy)
 {
+  clear_error();
   qb_quad r;
   if (qb_dot(n, x, incx, y, incy, &r)) return std::numeric_limits<double>::quiet_NaN();
   return qb_to_double(r); /* c_interface.hpp:30 */
@@ -639,6 +844,7 @@ double quadblas_qdot(int n, void *x, int incx, void *y, int incy)
 
 double quadblas_qnrm2(int n, void *x, int incx)
 {
+  clear_error();
   qb_quad r;
   if (qb_nrm2(n, x, incx, &r)) return std::numeric_limits<double>::quiet_NaN();
   return qb_to_double(r); /* c_interface.hpp:42-43 */
@@ -646,6 +852,7 @@ double quadblas_qnrm2(int n, void *x, int incx)
 
 void quadblas_qaxpy(int n, double alpha, void *x, int incx, void *y, int incy)
 {
+  clear_error();
   if (n <= 0) return; /* c_interface.hpp:49 */
   qb_quad a = qb_from_double(alpha);
   qb_axpy(n, &a, x, incx, y, incy);
@@ -654,6 +861,7 @@ void quadblas_qaxpy(int n, double alpha, void *x, int incx, void *y, int incy)
 void quadblas_qgemv(char layout, char trans, int m, int n, double alpha, void *A, int lda, void *x, int incx, double beta,
                     void *y, int incy)
 {
+  clear_error();
   qb_quad a = qb_from_double(alpha), b = qb_from_double(beta);
   bool col = is_col(layout);
   if (is_trans(trans)) { int t = m; m = n; n = t; col = !col; } /* c_interface.hpp:79-85 */
@@ -663,6 +871,7 @@ void quadblas_qgemv(char layout, char trans, int m, int n, double alpha, void *A
 void quadblas_qgemm(char layout, char transa, char transb, int m, int n, int k, double alpha, void *A, int lda, void *B,
                     int ldb, double beta, void *C, int ldc)
 {
+  clear_error();
   qb_quad a = qb_from_double(alpha), b = qb_from_double(beta);
   qb_gemm(layout, transa, transb, m, n, k, &a, A, lda, B, ldb, &b, C, ldc);
 }

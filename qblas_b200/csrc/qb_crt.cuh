@@ -139,11 +139,27 @@ QCRT_UNROLL
 }
 
 /* ------------------------------------------------------------------ element -> integer words */
-/* The same steps as crt_load4<NW> in qb_ozaki.cu (the kernels keep their own copy until the next GPU validation, so that the
- * measured binary stays the validated one); used by the CPU end-to-end check of the scheme (tests/host/crt_host.cpp).
- * x = (-1)^s M 2^(ee - 16495) (M < 2^113, ee = biased exponent, 1 for subnormals).  With base <= the lowest set bit of the row,
- * X = M 2^(ee - base) is an exact integer; the words come out ready for residue_sym<NW>: |X| for s = 0, 2^(32 NW) - |X| for
- * s = 1.  Zeros (and Inf/NaN, which the planner has already excluded) give all-zero words and sign 0. */
+/* logical right shift without the sticky jam of u256_shr_jam: truncation toward zero of the magnitude */
+QCRT_HD u256 u256_shr_trunc(u256 a, uint32_t s)
+{
+  if (s >= 256) { a.w0 = a.w1 = a.w2 = a.w3 = 0; return a; }
+  if (s >= 128) { a.w0 = a.w2; a.w1 = a.w3; a.w2 = 0; a.w3 = 0; s -= 128; }
+  if (s >= 64)  { a.w0 = a.w1; a.w1 = a.w2; a.w2 = a.w3; a.w3 = 0; s -= 64; }
+  if (s) {
+    a.w0 = (a.w0 >> s) | (a.w1 << (64 - s));
+    a.w1 = (a.w1 >> s) | (a.w2 << (64 - s));
+    a.w2 = (a.w2 >> s) | (a.w3 << (64 - s));
+    a.w3 = a.w3 >> s;
+  }
+  return a;
+}
+/* The element as the words the residue kernels consume (crt_load4 in qb_ozaki.cu calls this; tests/host/crt_host.cpp runs the
+ * same source on the CPU).  x = (-1)^s M 2^(ee - 16495) (M < 2^113, ee = biased exponent, 1 for subnormals) and
+ * base = emax(row) + 113 - W, so X = trunc(M 2^(ee - base)) < 2^W.  When W covers the row's whole bit span (base <= the lowest set
+ * bit of the row) X is exact; when the planner capped W, the bits of small elements below 2^base are dropped (truncation toward
+ * zero, |x / 2^(base-16495) - X| < 1) and the reconstruction kernel checks every C element against the dropped mass (k_crt_fold).
+ * Words: |X| for s = 0, 2^(32 NW) - |X| for s = 1 and X != 0 (residue_sym<NW>).  Zeros, elements truncated to zero and Inf/NaN
+ * (their rows go to the fix-up kernel) give all-zero words and sign 0. */
 template <int NW>
 QCRT_HD void element_words(q128 a, int base, uint32_t (&w)[NWMAX], uint32_t &sign)
 {
@@ -156,7 +172,8 @@ QCRT_UNROLL
   const int ee = ef ? (int)ef : 1;
   u256 v; v.w0 = a.lo; v.w1 = mhi; v.w2 = 0; v.w3 = 0;
   const int sh = ee - base;
-  v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact: base <= lowest set bit of the row */
+  v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_trunc(v, (uint32_t)(-sh));
+  if (!(v.w0 | v.w1 | v.w2)) return;            /* truncated to zero: a plain zero (sign 0) */
   w[0] = (uint32_t)v.w0; w[1] = (uint32_t)(v.w0 >> 32);
   w[2] = (uint32_t)v.w1; w[3] = (uint32_t)(v.w1 >> 32);
   w[4] = (uint32_t)v.w2; w[5] = (uint32_t)(v.w2 >> 32);
@@ -171,6 +188,39 @@ QCRT_HD uint32_t acc_mod(int32_t v, int i, const Tables &T)
   uint32_t r = u - mulhi_u(u, T.finv[i]) * T.p[i];
   if (r >= T.p[i]) r -= T.p[i];
   return r;
+}
+
+/* ------------------------------------------------------------------ capped windows: the per-element acceptance test */
+/* When the planner caps a window below a row's bit span (element_words above), every dropped tail is < 1 unit of the row's
+ * scale, so the integer I^ the moduli reconstruct differs from the exact scaled inner product I by
+ *     |I - I^| < E = tA sum_l |XB_lj| + tB sum_l |XA_il| + tA tB k  <=  k (tA 2^WB + tB 2^WA + tA tB)
+ * (tA / tB = 1 when row i of A / column j of B lost bits).  The rounded result c^ = RNE(I^) scale then has
+ * |c^ - c| <= (u |I^| + E) scale while (|A||B|)_ij >= |c| >= (|I^| - E) scale, so the fast-mode contract
+ * |c^ - c| <= k u (|A||B|)_ij holds as soon as |I^| >= E (1 + k u) / ((k - 1) u); with k / (k - 1) <= 2 that is implied by
+ * |I^| >= 2^T, T = WB + 115 (only A truncated), WA + 115 (only B), max(WA, WB) + 116 (both).  Returns T (the lowest
+ * acceptable position of the leading bit of |I^|), -1 (every value passes, zero included) when nothing was truncated, and an
+ * unreachable value for k < 2
+ * (a single product must be correctly rounded: every truncated element goes to the fix-up). */
+QCRT_HD int accept_msb(bool tA, bool tB, int WA, int WB, long long k)
+{
+  if (!tA && !tB) return -1;
+  if (k < 2) return 1 << 20;
+  if (tA && tB) return (WA > WB ? WA : WB) + 116;
+  return tA ? WB + 115 : WA + 115;
+}
+/* position of the leading bit of an NL-limb magnitude, -1 for zero */
+template <int NL>
+QCRT_HD int limbs_msb(const uint32_t (&L)[NL])
+{
+  int top = -1; uint32_t tv = 1;
+QCRT_UNROLL
+  for (int l = 0; l < NL; ++l) if (L[l]) { top = l; tv = L[l]; }
+  if (top < 0) return -1;
+#if defined(__CUDA_ARCH__)
+  return 32 * top + 31 - __clz((int)tv);
+#else
+  return 32 * top + 31 - __builtin_clz(tv);
+#endif
 }
 
 /* ------------------------------------------------------------------ reconstruction */
@@ -526,6 +576,33 @@ static inline int moduli_for_bits(int need_bits)
     if (bits > need_bits + 1e-6) return i + 1;
   }
   return 0;
+}
+
+/* Windows and moduli count of one qgemm.  WA_nat / WB_nat = widest bit span of a row of op(A) / column of op(B) (scan).  The
+ * windows are the spans themselves when the moduli can cover them inside the `wcap` budget (WA + WB <= 2 wcap): then every
+ * element is represented exactly and so is every inner product.  Otherwise the wider window is cut (both to wcap when both
+ * exceed it) and the low bits of small elements are dropped (element_words); accept_msb() is the per-element test that keeps
+ * the result inside the fast-mode contract.  false: even all the moduli cannot cover 2 x 117 bits at this k. */
+struct Windows { int WA, WB, N, truncA, truncB; };
+static inline bool plan_windows(int WA_nat, int WB_nat, long long k, int wcap, Windows &w)
+{
+  int lk = 0;
+  while (((long long)1 << lk) < k) ++lk;
+  double all = 0;
+  for (int i = 0; i < NM; ++i) all += __builtin_log2((double)MODULI[i]);
+  int maxsum = (int)(all - 1e-6) - lk - 1;              /* P > 2 k 2^(WA + WB) */
+  if (2 * wcap < maxsum) maxsum = 2 * wcap;
+  int WA = WA_nat < 1 ? 1 : (WA_nat > WMAX ? WMAX : WA_nat), WB = WB_nat < 1 ? 1 : (WB_nat > WMAX ? WMAX : WB_nat);
+  if (WA + WB > maxsum) {
+    const int half = maxsum / 2;
+    if (WA <= half) WB = maxsum - WA;
+    else if (WB <= half) WA = maxsum - WB;
+    else { WA = half; WB = maxsum - half; }
+  }
+  if ((WA < WA_nat && WA < 117) || (WB < WB_nat && WB < 117)) return false;   /* a cut window must still hold the largest element */
+  w.WA = WA; w.WB = WB; w.truncA = WA < WA_nat; w.truncB = WB < WB_nat;
+  w.N = moduli_for_bits(WA + WB + lk + 1);
+  return w.N != 0;
 }
 
 } // namespace host

@@ -56,24 +56,42 @@ int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */
 #define QB_OZ_MAX_SLICES 24
-struct OzStats { int SA, SB, ndiag, nchunks, row_passes; int64_t pairs, ws_bytes, Kp; int keep; int64_t flagged; int redo_passes; int scheme, WA, WB; int peer_written; };
-/* *used = 0: the planner declined (Inf/NaN, exponent span too wide, no workspace) and nothing was written */
+#define QB_MAX_DEVICES 64
+struct OzStats {
+  int SA = 0, SB = 0, ndiag = 0, nchunks = 0, row_passes = 0; int64_t pairs = 0, ws_bytes = 0, Kp = 0; int keep = 0; int64_t flagged = 0; int redo_passes = 0;
+  int scheme = 0, WA = 0, WB = 0; int peer_written = 0;
+  int panels = 0; int64_t units = 0; int WA_nat = 0, WB_nat = 0; int truncated = 0;   /* bit 0 / 1: the window of A / B is narrower than the span; bit 2: Inf / NaN present */
+};
 /* row-pass hook: when set, the C rows are produced in at least `min_passes` passes and cb(row0, rows, user) is called on the
- * host after the work of each pass has been ENQUEUED on the stream (so a collective issued from the callback overlaps the
- * next pass) */
+ * host after the work that completes those rows has been ENQUEUED on the stream (so a collective issued from the callback
+ * overlaps the remaining work) */
 typedef void (*oz_pass_cb)(int64_t row0, int64_t rows, void *user);
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb = nullptr, void *cb_user = nullptr,
-                              int min_passes = 1);
+/* streamed B: called on the host before the library enqueues the first work that reads columns [col0, col0 + cols) of op(B);
+ * the callee returns where that panel lives (*panel, leading dimension *ld in elements, same layout as the B argument) and makes
+ * `stream` (a cudaStream_t of the library) wait for the panel's arrival.  non-zero return = failure. */
+typedef int (*oz_bpanel_cb)(int64_t col0, int64_t cols, void *stream, const void **panel, int64_t *ld, void *user);
+struct OzHooks {
+  oz_pass_cb cb = nullptr; void *cb_user = nullptr; int min_passes = 1;
+  oz_bpanel_cb bp = nullptr; void *bp_user = nullptr; int64_t bp_cols = 0;
+  const int *bstats = nullptr;       /* device: column statistics of op(B) from launch_colstats (3 n ints); skips the scan of B */
+  /* streamed rows (the all-host path): called once per row pass before its first use; the callee makes sA wait for the rows of A
+   * and sF for the rows of C_in.  non-zero return = failure. */
+  int (*rows_in)(int64_t row0, int64_t rows, void *sA, void *sF, void *user) = nullptr; void *rows_user = nullptr;
+  int order = 0;                     /* 0: panels outer (A planes resident), 1: passes outer (B planes resident, rows complete pass by pass) */
+};
+/* *used = 0: the planner declined (no TMA entry point, no workspace) and nothing was written */
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, const OzHooks &h);
+cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, int64_t sbl, int *stats, cudaStream_t st);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);
 OzStats oz_last_stats();
 std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape);
-void oz_set_keep(int keep);   /* leading diagonals multiplied (bounded setting); 0 = all = exact inner products */
-int oz_get_keep();
-void oz_set_pass_shape(int v); /* residue scheme: 0 = equal row passes (default), 1 = short first and last pass (experimental) */
+void oz_set_pass_shape(int v);
 int oz_get_pass_shape();
-void oz_set_scheme(int v); /* 1 = residue planes + CRT (qb_crt.cuh, default), 0 = digit diagonals */
-int oz_get_scheme();
+void oz_set_window(int bits);  /* bits per operand window the planner grants when the spans do not fit the moduli (default 144) */
+int oz_get_window();
+void oz_set_unit(int64_t rows, int64_t cols);   /* pipeline unit: rows of an A pass x columns of a B panel (default 2048 x 2048) */
+void oz_get_unit(int64_t *rows, int64_t *cols);
 double oz_last_mma_ms(int *launches);
 void oz_release();
 

@@ -1,49 +1,33 @@
 /*
- * qb_ozaki.cu — fast-mode binary128 GEMM on the 5th-generation tensor cores.
- *
- * Two schemes share the scan / plan step and the tcgen05 kernel of this file:
- *   residues (default, qb_set_tensor_scheme(1)): one int8 GEMM per modulus + Chinese-remainder fold, always exact; the
- *            arithmetic is in qb_crt.cuh, the kernels (k_crt_residues*, k_oz_mma<1>, k_crt_fold) and the stream-pipelined
- *            driver (launch_gemm_crt) are in the section "residue scheme" below;
- *   digit diagonals (qb_set_tensor_scheme(0), and the fallback when the moduli cannot cover the operands' bit span):
- *            described next.
+ * qb_ozaki.cu — fast-mode binary128 GEMM on the 5th-generation tensor cores (residue scheme).
  *
  * What it replaces: the arithmetic of QuadBLAS::gemm (/root/reference/include/quadblas/algorithms/
- * level3.hpp:215-336; hot loop :77-85 = one Sleef_fmaq2_u05 per two products) when the library is
- * in QB_MODE_FAST.  Fast mode is free to re-associate (last paragraph); this
- * path goes further and computes every dot product EXACTLY, then rounds once:
+ * level3.hpp:215-336; hot loop :77-85 = one Sleef_fmaq2_u05 per two products) when the library is in
+ * QB_MODE_FAST.  Fast mode is free to re-associate (last paragraph); this path
+ * computes every inner product as an exact integer and rounds once:
  *
- *   scan   : per row of op(A) / column of op(B): largest exponent and lowest set mantissa bit
- *   plan   : W = widest row span in bits  ->  S = ceil((W + 2) / 8) signed 8-bit slices, so that
- *            every element is represented EXACTLY as  x = 2^base(row) * sum_s d_s 256^(S-1-s),
- *            d_s in [-128, 127]  (row-wise block fixed point, no truncation at all)
- *   slice  : write the S int8 digit planes, K-major, for A ([S_A][m][Kp]) and B ([S_B][n][Kp])
- *   mma    : for every diagonal d = s + t:  D_d = sum_{s+t=d} A_s * B_t^T  as ONE K-concatenated
- *            int8 x int8 -> int32 GEMM on tcgen05 (kind::i8), operands staged by TMA into 128-byte
- *            swizzled shared memory, accumulators in TMEM, warp-specialised persistent kernel.
- *            Exact: |d| <= 128 and Kc * min(S_A, S_B) * 2^14 < 2^31 (K is cut into chunks of Kc).
- *   fold   : I = sum_d D_d 256^(ndiag-1-d) as a 448-bit two's complement integer per C element
- *            (accumulated across K chunks in a workspace), one correctly rounded conversion to
- *            binary128, then the reference epilogue  C = fma(alpha, s, mul(beta, C))
- *            (level3.hpp:102-109).
+ *   scan     : per row of op(A) / column of op(B): largest exponent, lowest set mantissa bit, Inf/NaN flag   (k_oz_scan)
+ *   plan     : widest bit spans -> windows W_A, W_B and the number of moduli N (crt::host::plan_windows).  Rows / columns
+ *              become block fixed point, x = X 2^(base - 16495), |X| < 2^W; the windows normally cover the spans (X exact);
+ *              spans wider than the moduli can cover (exponent spreads of +-40 binades and more) are cut: the low bits of the
+ *              small elements of a row are dropped and every C element is tested against the dropped mass (below)
+ *   residues : a_i = X mod p_i as symmetric int8, one byte plane per modulus, K-major                      (k_crt_residues*)
+ *   mma      : R_i = (A_i B_i^T) mod p_i — ONE int8 x int8 -> int32 GEMM per modulus on tcgen05 (kind::i8), operands staged
+ *              by TMA into 128-byte swizzled shared memory, accumulators in TMEM, warp-specialised persistent kernel,
+ *              the accumulator reduced mod p_i in the epilogue and stored as one byte                      (k_oz_mma<1>)
+ *   fold     : Chinese-remainder reconstruction of the exact integer (crt::reconstruct_dev), ONE correctly rounded conversion
+ *              to binary128, then the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109) (k_crt_fold)
+ *   fix-up   : C elements the fold does not accept — the reconstructed integer is too small against what a capped window
+ *              dropped (crt::accept_msb; cancellation), or the row / column holds Inf / NaN — are recomputed from the
+ *              original operands in the unrounded window accumulator of qwide.cuh, one warp per element      (k_crt_fixup)
  *
- * Accuracy, exact setting (qb_set_tensor_keep(0)): the inner product is exact, so |c^ - c| <= u |A B|_ij
- * (+ the two epilogue roundings), far inside the fast-mode contract  gamma_k (|A||B|)_ij.
+ * The work is cut into units (row pass of A) x (column panel of B) and software-pipelined over four internal streams:
+ * tensor kernel of unit u || residues of the next A pass / B panel || reconstruction of unit u-1 (launch_gemm_crt).
  *
- * Bounded setting (default, qb_set_tensor_keep(16)): only the `keep` most significant diagonals
- * d = 0 .. keep-1 are multiplied (136 digit-plane products instead of 18 x 18 = 324 for full 113-bit
- * mantissas).  With J = sum_{d<keep} D_d 256^(keep-1-d), the dropped diagonals amount to less than
- * min(S_A,S_B) * k * 64.3 units of J, so whenever |J| >= 2^125 the truncation is below
- * (k-1) u |c_ij| and the rounded J meets  |c^ - c| <= k u |c| <= gamma_k (|A||B|)_ij  (k >= 2,
- * S <= 24; derivation in DESIGN.md §4.1).  The fold checks that per element; an element that fails
- * it (cancellation: |c_ij| more than ~2^10 below the typical size; 0.02 % of the entries of a random
- * 8192^3 product with 16 diagonals, 1e-6 with 17) is NOT written by the fold
- * and is recomputed by k_oz_fixup, one warp per element, in the unrounded window accumulator of
- * qwide.cuh (error < k 2^-133 max|a b|, also inside the contract).  If more than 1/64 of a row pass
- * fails (structured cancellation), the pass is redone with all diagonals for the failed elements.  Inputs this cannot represent (Inf/NaN,
- * or a row whose exponent span needs more than QB_OZ_MAX_SLICES digits) make the planner decline
- * and the caller runs the integer-limb kernel (qb_level3.cu) instead; that is a different CUDA
- * kernel of this library, not a CPU fallback.
+ * Accuracy: windows that cover the spans (every D53 / D113 input of BASELINE configs 1-4): the inner product is exact and
+ * rounded once, |c^ - c| <= u |A B|_ij (+ the two epilogue roundings).  Capped windows: every accepted element satisfies
+ * |c^ - c| <= k u (|A||B|)_ij by the test in crt::accept_msb, every other element comes from the window accumulator
+ * (error < k 2^-133 max|a b| + one rounding); both are inside the fast-mode contract gamma_k (|A||B|)_ij.
  */
 #include "qb_internal.h"
 #include "qb_tc.cuh"
@@ -71,26 +55,26 @@ static constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE_BYTES + 1024 /* alignment sl
 static constexpr int OZ_THREADS = 192;       /* warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue */
 static constexpr int OZ_MAX_S = QB_OZ_MAX_SLICES;
 static constexpr int OZ_MAX_DIAG = 2 * OZ_MAX_S - 1;
-static constexpr int OZ_NL = 14;             /* 32-bit limbs of the exact integer (448 bits) */
 static constexpr int OZ_SCAN_CH = 256;       /* k per scan work item: 8192^2 gives 262k warps / threads, enough loads in flight for HBM */
+static constexpr int OZ_KCHUNK = 65536;      /* K per int32 accumulation: 128 * 128 * 65536 = 2^30 */
 
 struct OzMmaArgs {
-  int32_t *D;                 /* [ndiag][Mp][Np] int32 */
+  int32_t *D;                 /* plain mode (CRT = 0): [ndiag][Mp][Np] int32 */
   int64_t Mp, Np;             /* padded to tile multiples */
   int SA, SB, ndiag;
   int m_tiles, n_tiles;
-  int kb_begin, nkb;          /* k-blocks of OZ_BK for this K chunk */
-  uint8_t order[OZ_MAX_DIAG + 1]; /* diagonals, heaviest first */
-  uint8_t *R;                 /* residue scheme: [N][Mp][Np] bytes, R_i = (A_i B_i^T) mod p_i in [0, p_i); ndiag = N */
+  int kb_begin, nkb;          /* k-blocks of OZ_BK of this launch */
+  uint8_t order[OZ_MAX_DIAG + 1];
+  uint8_t *R;                 /* residue mode (CRT = 1): [N][Mp][Np] bytes, R_i = (A_i B_i^T) mod p_i in [0, p_i); ndiag = N */
+  int accum;                  /* residue mode: add to the residues already in R (K chunks beyond OZ_KCHUNK) */
 };
 
-/* per-modulus constants of the residue scheme (qb_crt.cuh); uploaded once per device by crt_upload_tables() */
+/* per-modulus constants of the residue scheme (qb_crt.cuh); uploaded once per device */
 __constant__ crt::Tables c_crt;
 
-/* Tile order inside one diagonal: bands of OZ_GM m-tiles, n-tile outer / m-tile inner inside a band, so
- * that the ~148 tiles in flight form a compact 16 x 9 block of C: every A row panel is shared by ~9
- * CTAs and every B column panel by 16 through L2 (profiles/r1c: the n-fastest order re-read the
- * planes from HBM 3.4x more often than this needs at 8192^3). */
+/* Tile order inside one modulus: bands of OZ_GM m-tiles, n-tile outer / m-tile inner inside a band, so that the ~148 tiles
+ * in flight form a compact block of C: every A row panel is shared by ~9 CTAs and every B column panel by 16 through L2
+ * (profiles/r1c: the n-fastest order re-read the planes from HBM 3.4x more often than this needs at 8192^3). */
 static constexpr int OZ_GM = 16;
 __device__ __forceinline__ void oz_tile_decode(int rem, int m_tiles, int n_tiles, int &mt, int &nt)
 {
@@ -102,8 +86,9 @@ __device__ __forceinline__ void oz_tile_decode(int rem, int m_tiles, int n_tiles
 }
 
 /* ------------------------------------------------------------------ the tensor-core kernel */
-/* CRT = 0: digit diagonals, D_d = sum_{s+t=d} A_s B_t^T as int32.  CRT = 1: residue planes, one product A_i B_i^T per
- * modulus, reduced mod p_i in the epilogue and stored as bytes. */
+/* CRT = 1: residue planes, one product A_i B_i^T per modulus, reduced mod p_i in the epilogue and stored as bytes.
+ * CRT = 0: the same pipeline with int32 output, D_d = sum_{s+t=d} A_s B_t^T over plane pairs (qb_oz_i8gemm_dev: the int8 peak
+ * microbenchmark and the standalone test of the tcgen05 path). */
 template <int CRT>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzMmaArgs g)
@@ -191,7 +176,7 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       }
     }
   } else {
-    /* ===================== epilogue: TMEM -> registers -> D (int32) ===================== */
+    /* ===================== epilogue: TMEM -> registers -> global ===================== */
     const int quarter = warp & 3;       /* TMEM lanes 32*quarter .. +31 are the ones this warp may read */
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -224,20 +209,35 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             }
             w[q] = word;
           }
+          if (g.accum) { /* a later K chunk: (old + new) mod p, byte by byte */
+            const uint4 o0 = *reinterpret_cast<const uint4 *>(dst + c * 32), o1 = *reinterpret_cast<const uint4 *>(dst + c * 32 + 16);
+            const uint32_t o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int b = 0; b < 4; ++b) {
+                uint32_t r = ((w[q] >> (8 * b)) & 0xffu) + ((o[q] >> (8 * b)) & 0xffu);
+                r = r >= p ? r - p : r;
+                word |= r << (8 * b);
+              }
+              w[q] = word;
+            }
+          }
           *reinterpret_cast<uint4 *>(dst + c * 32) = make_uint4(w[0], w[1], w[2], w[3]);
           *reinterpret_cast<uint4 *>(dst + c * 32 + 16) = make_uint4(w[4], w[5], w[6], w[7]);
         }
       } else {
-      int32_t *dst = g.D + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
+        int32_t *dst = g.D + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
 #pragma unroll 1
-      for (int c = 0; c < OZ_BN / 32; ++c) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(taddr + c * 32, v);
-        tc::tmem_ld_wait();
+        for (int c = 0; c < OZ_BN / 32; ++c) {
+          uint32_t v[32];
+          tc::tmem_ld_32x32(taddr + c * 32, v);
+          tc::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4 *>(dst + c * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      }
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4 *>(dst + c * 32 + q * 4) = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
       }
       tc::tc_fence_before();
       __syncwarp();
@@ -270,14 +270,15 @@ __device__ __forceinline__ OzElem oz_unpack(q128 a)
 }
 __device__ __forceinline__ int oz_tz(uint64_t lo, uint64_t hi) { return lo ? __ffsll((long long)lo) - 1 : 64 + __ffsll((long long)hi) - 1; }
 
-/* rows x K view: X[r * sr + k * sk].  emax[r] = max ee over non-zero elements (0 if none),
- * lmin[r] = min (ee + tz(M)); flags |= 1 on Inf/NaN.  One warp per (row, OZ_SCAN_CH-wide k chunk) when k
- * is the contiguous direction, otherwise one thread per (row, chunk) with lanes along rows. */
-__global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, int *emax, int *lmin, int *flags)
+/* rows x K view: X[r * sr + k * sk].  Over the finite non-zero elements of row r: emax[r] = max ee (0 if none),
+ * lmin[r] = min (ee + tz(M)); sp[r] = 1 when the row holds an Inf or NaN (those elements count as zero for the tensor kernel,
+ * every C element of the row goes to the fix-up).  One warp per (row, OZ_SCAN_CH-wide k chunk) when k is the contiguous
+ * direction, otherwise one thread per (row, chunk) with lanes along rows.  emax / sp start at 0, lmin at a large value. */
+__global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, int *emax, int *lmin, int *sp)
 {
   constexpr int CH = OZ_SCAN_CH;
   const int64_t nchunk = (K + CH - 1) / CH;
-  int em = 0, lm = 0x7fffffff, sp = 0;
+  int em = 0, lm = 0x7fffffff, spc = 0;
   int64_t r;
   if (sk == 1 || sr != 1) { /* warp per (row, chunk), lanes along k */
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -287,14 +288,14 @@ __global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, i
     const int64_t k0 = (w % nchunk) * CH, k1 = k0 + CH < K ? k0 + CH : K;
     for (int64_t k = k0 + lane; k < k1; k += 32) {
       const OzElem e = oz_unpack(X[r * sr + k * sk]);
-      sp |= e.special;
-      if (e.lo | e.hi) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
+      spc |= e.special;
+      if (!e.special && (e.lo | e.hi)) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
       em = max(em, __shfl_xor_sync(0xffffffffu, em, o));
       lm = min(lm, __shfl_xor_sync(0xffffffffu, lm, o));
-      sp |= __shfl_xor_sync(0xffffffffu, sp, o);
+      spc |= __shfl_xor_sync(0xffffffffu, spc, o);
     }
     if (lane != 0) return;
   } else { /* rows contiguous: thread per (row, chunk), lanes along rows */
@@ -304,305 +305,53 @@ __global__ void k_oz_scan(const q128 *__restrict__ X, int64_t rows, int64_t K, i
     const int64_t k0 = (t / rows) * CH, k1 = k0 + CH < K ? k0 + CH : K;
     for (int64_t k = k0; k < k1; ++k) {
       const OzElem e = oz_unpack(X[r * sr + k * sk]);
-      sp |= e.special;
-      if (e.lo | e.hi) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
+      spc |= e.special;
+      if (!e.special && (e.lo | e.hi)) { em = max(em, e.ee); lm = min(lm, e.ee + oz_tz(e.lo, e.hi)); }
     }
   }
   if (em) { atomicMax(&emax[r], em); atomicMin(&lmin[r], lm); }
-  if (sp) atomicOr(flags, 1);
+  if (spc) sp[r] = 1;
 }
 
-/* out[0] = widest span of A rows, out[1] = widest span of B columns, out[2] = flags */
-__global__ void k_oz_plan(const int *emaxA, const int *lminA, int64_t m, const int *emaxB, const int *lminB, int64_t n, const int *flags, int *out)
+/* out[0] = widest span of A rows, out[1] = widest span of B columns, out[2] = 1 when any row / column holds Inf or NaN */
+__global__ void k_oz_plan(const int *emaxA, const int *lminA, const int *spA, int64_t m, const int *emaxB, const int *lminB, const int *spB, int64_t n, int *out)
 {
-  __shared__ int sw[2];
-  if (threadIdx.x == 0) { sw[0] = 0; sw[1] = 0; }
+  __shared__ int sw[3];
+  if (threadIdx.x == 0) { sw[0] = 0; sw[1] = 0; sw[2] = 0; }
   __syncthreads();
-  int wa = 0, wb = 0;
-  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) if (emaxA[i]) wa = max(wa, emaxA[i] + 113 - lminA[i]);
-  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) if (emaxB[j]) wb = max(wb, emaxB[j] + 113 - lminB[j]);
+  int wa = 0, wb = 0, fl = 0;
+  for (int64_t i = threadIdx.x; i < m; i += blockDim.x) { if (emaxA[i]) wa = max(wa, emaxA[i] + 113 - lminA[i]); fl |= spA[i]; }
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) { if (emaxB[j]) wb = max(wb, emaxB[j] + 113 - lminB[j]); fl |= spB[j]; }
   atomicMax(&sw[0], wa);
   atomicMax(&sw[1], wb);
+  if (fl) atomicOr(&sw[2], 1);
   __syncthreads();
-  if (threadIdx.x == 0) { out[0] = sw[0]; out[1] = sw[1]; out[2] = *flags; }
+  if (threadIdx.x == 0) { out[0] = sw[0]; out[1] = sw[1]; out[2] = sw[2]; }
 }
 
-/* ------------------------------------------------------------------ slice: exact signed 8-bit digits */
-/* thread = (row r, 4 consecutive k); plane s (0 = most significant digit) is [rows][Kp] int8.
- * x = X_int * 2^(base - 16495), base = emax[r] + 115 - 8 S, |X_int| < 2^(8S-2); digits are the
- * balanced base-256 expansion of X_int (so the sign needs no separate plane). */
-/* digits of the 4 elements (row r, k = 4 g4 .. 4 g4 + 3): word[j] = byte q is digit j (0 = least significant) of element q */
-template <int MAXS>
-__device__ __forceinline__ void oz_slice4(const q128 *__restrict__ X, int64_t r, int64_t g4, int64_t K, int64_t sr, int64_t sk, int base, int S,
-                                          uint32_t (&word)[MAXS])
-{
-#pragma unroll
-  for (int s = 0; s < MAXS; ++s) word[s] = 0;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t k = g4 * 4 + q;
-    if (k >= K) continue;
-    const OzElem e = oz_unpack(X[r * sr + k * sk]);
-    if (!(e.lo | e.hi) || e.special) continue;
-    u256 v; v.w0 = e.lo; v.w1 = e.hi; v.w2 = 0; v.w3 = 0;
-    const int sh = e.ee - base;
-    v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact by construction of S */
-    const uint64_t w[4] = {v.w0, v.w1, v.w2, v.w3};
-    /* balanced digits, least significant first; a negative number takes digits of its magnitude
-     * in [-127, 128] and negates them, so both signs land in [-128, 127] */
-    uint32_t carry = 0;
-    const uint32_t thr = 128u + e.sign;
-#pragma unroll
-    for (int j = 0; j < MAXS; ++j) {
-      if (j < S) {
-        uint32_t t = (uint32_t)((w[j >> 3] >> (8 * (j & 7))) & 0xffu) + carry;
-        carry = t >= thr ? 1u : 0u;                 /* digit = t - 256 */
-        const uint32_t dig = e.sign ? (0u - t) : t; /* low 8 bits are the int8 digit either way */
-        word[j] |= (dig & 0xffu) << (8 * q);
-      }
-    }
-  }
-}
-
-/* k contiguous in memory (or fully strided): thread = (row, 4 consecutive k), lanes along k; every thread
- * stores one 32-bit word per plane and a warp's stores are 128 contiguous bytes of one plane row. */
-template <int MAXS>
-__global__ void k_oz_slice(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax, int S, int64_t Kp,
-                           int8_t *__restrict__ planes)
-{
-  const int64_t groups = Kp >> 2;
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= rows * groups) return;
-  const int64_t r = tid / groups, g4 = tid % groups;
-  uint32_t word[MAXS];
-  oz_slice4<MAXS>(X, r, g4, K, sr, sk, emax[r] + 115 - 8 * S, S, word);
-#pragma unroll
-  for (int j = 0; j < MAXS; ++j)
-    if (j < S) *reinterpret_cast<uint32_t *>(planes + ((int64_t)(S - 1 - j) * rows + r) * Kp + g4 * 4) = word[j];
-}
-
-/* rows contiguous in memory (B of a row-major product, A of a col-major one): a CTA of 32 x 8 threads takes a tile of
- * 32 rows x 32 k with lanes along the rows, so the 16-byte loads coalesce; the plane words are transposed through
- * shared memory and leave as 32-byte runs along K (the direct store would scatter 4-byte words Kp bytes apart). */
-template <int MAXS>
-__global__ void __launch_bounds__(256) k_oz_slice_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
-                                                   int S, int64_t Kp, int8_t *__restrict__ planes)
-{
-  __shared__ uint32_t sm[MAXS][32][9];            /* [digit][row][k-group], padded against bank conflicts */
-  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32, g0 = (int64_t)blockIdx.y * 8;
-  const int64_t r = r0 + lane, g4 = g0 + wg;
-  if (r < rows) {
-    uint32_t word[MAXS];
-    oz_slice4<MAXS>(X, r, g4, K, sr, sk, emax[r] + 115 - 8 * S, S, word);
-#pragma unroll
-    for (int j = 0; j < MAXS; ++j)
-      if (j < S) sm[j][lane][wg] = word[j];
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < S * 64; q += 256) {
-    const int j = q >> 6, row = (q & 63) >> 1, half = q & 1;
-    if (r0 + row >= rows) continue;
-    const uint32_t *src = &sm[j][row][half * 4];
-    *reinterpret_cast<uint4 *>(planes + ((int64_t)(S - 1 - j) * rows + r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
-  }
-}
-
-/* ------------------------------------------------------------------ fold: diagonals -> binary128 */
-struct OzFoldArgs {
-  const int32_t *D; int64_t Mp, Np; int ndiag;
-  int nsets; int64_t set_stride;     /* K chunks kept as separate int32 diagonal sets (summed here in 64 bits) */
-  int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
-  const int *emaxA, *emaxB; int SA, SB;
-  uint32_t *W; int w_in, w_out;      /* 448-bit running sums across K chunks: [OZ_NL][Mp*Np] */
-  q128 alpha, beta; q128 *C; int64_t sci, scj;
-  /* bounded setting: ndiag = kept diagonals, the integer is J (units of 256^exp8 above the full one) */
-  int exp8;                          /* dropped diagonals (0 in the exact setting) */
-  int check;                         /* 1: elements with |J| < 2^OZ_JMIN_BIT are flagged and left unwritten */
-  int only_flagged;                  /* 1: (exact redo) write only the elements flagged earlier */
-  uint8_t *flag;                     /* [Mp*Np] */
-  int2 *list; int list_cap; int *counter;
-};
-static constexpr int OZ_JMIN_BIT = 125;
-
-/* NSETS > 0: that many diagonal sets, unrolled; NSETS = 0: g.nsets of them (any count) */
-template <int NSETS>
-__global__ void __launch_bounds__(256) k_oz_fold(const OzFoldArgs g)
-{
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = idx / g.n, j = idx % g.n;
-  if (i >= g.m) return;
-  const int64_t plane = g.Mp * g.Np, off = i * g.Np + j;
-  uint32_t L[OZ_NL];
-  long long carry = 0;
-#pragma unroll
-  for (int l = 0; l < OZ_NL; ++l) {
-    long long acc = carry;
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int d = g.ndiag - 1 - (4 * l + b);
-      if (d >= 0) {
-        const int32_t *dp = g.D + (int64_t)d * plane + off;
-        long long v = dp[0];
-        if (NSETS > 0) {
-#pragma unroll
-          for (int c = 1; c < NSETS; ++c) v += dp[c * g.set_stride];
-        } else {
-          for (int c = 1; c < g.nsets; ++c) v += dp[c * g.set_stride];
-        }
-        acc += v << (8 * b);
-      }
-    }
-    L[l] = (uint32_t)acc;
-    carry = acc >> 32;
-  }
-  if (g.w_in) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int l = 0; l < OZ_NL; ++l) {
-      const uint64_t t = (uint64_t)L[l] + g.W[(int64_t)l * plane + off] + c;
-      L[l] = (uint32_t)t; c = (uint32_t)(t >> 32);
-    }
-  }
-  if (g.w_out) {
-#pragma unroll
-    for (int l = 0; l < OZ_NL; ++l) g.W[(int64_t)l * plane + off] = L[l];
-    return;
-  }
-  if (g.only_flagged && !g.flag[off]) return;
-  /* ---- sign / magnitude ---- */
-  const uint32_t neg = L[OZ_NL - 1] >> 31;
-  if (neg) {
-    uint32_t c = 1;
-#pragma unroll
-    for (int l = 0; l < OZ_NL; ++l) { const uint64_t t = (uint64_t)(~L[l]) + c; L[l] = (uint32_t)t; c = (uint32_t)(t >> 32); }
-  }
-  int top = -1;
-  uint32_t topv = 0;
-#pragma unroll
-  for (int l = 0; l < OZ_NL; ++l) if (L[l]) { top = l; topv = L[l]; }
-  if (g.check) { /* |J| >= 2^125 or the element goes to the fix-up (header comment) */
-    const int msb = top < 0 ? -1 : 32 * top + 31 - __clz((int)topv);
-    const bool weak = msb < OZ_JMIN_BIT;
-    g.flag[off] = weak ? 1 : 0;
-    if (weak) {
-      const int slot = atomicAdd(g.counter, 1);
-      if (slot < g.list_cap) g.list[slot] = make_int2((int)(g.row0 + i), (int)j);
-      return;
-    }
-  }
-  q128 sum;
-  if (top < 0) {
-    sum = q_zero(0); /* an exact zero sum is +0 (a +0-seeded chain never yields -0) */
-  } else {
-    /* 9-limb window ending at the top limb, through a local buffer (dynamic index) */
-    uint32_t buf[OZ_NL + 8];
-#pragma unroll
-    for (int l = 0; l < 8; ++l) buf[l] = 0;
-#pragma unroll
-    for (int l = 0; l < OZ_NL; ++l) buf[8 + l] = L[l];
-    uint32_t w[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) w[k] = buf[top + k];
-    uint32_t sticky = 0;
-#pragma unroll
-    for (int l = 0; l < OZ_NL; ++l) if (l < top - 8) sticky |= L[l];
-    const int lz = __clz((int)w[8]);
-    uint32_t R[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) R[k] = __funnelshift_l(w[k], w[k + 1], lz);
-    sticky |= w[0] << lz; /* lz == 0: w[0] is entirely below the window */
-    if (lz == 0) sticky |= w[0];
-    u256 Rq;
-    Rq.w0 = ((uint64_t)R[1] << 32) | R[0] | (sticky != 0);
-    Rq.w1 = ((uint64_t)R[3] << 32) | R[2];
-    Rq.w2 = ((uint64_t)R[5] << 32) | R[4];
-    Rq.w3 = ((uint64_t)R[7] << 32) | R[6];
-    /* I * 2^Eb, Eb = baseA + baseB - 2 * 16495; MSB of I at bit p = 32 top + 31 - lz  ->  er = p + Eb + QBIAS */
-    const int baseA = g.emaxA[g.row0 + i] + 115 - 8 * g.SA, baseB = g.emaxB[j] + 115 - 8 * g.SB;
-    const int p = 32 * top + 31 - lz;
-    const int er = p + 8 * g.exp8 + baseA + baseB - 2 * 16495 + QBIAS;
-    sum = q_round_pack(neg, er, Rq);
-  }
-  q128 *c = g.C + i * g.sci + j * g.scj;
-  *c = q_fma(g.alpha, sum, q_mul(g.beta, *c)); /* level3.hpp:102-109: beta*C is always evaluated */
-}
-
-/* ------------------------------------------------------------------ fix-up of the flagged elements (bounded setting) */
-struct OzFixArgs {
-  const int2 *list; const int *counter; int list_cap;
-  const q128 *A; int64_t sai, sal; const q128 *B; int64_t sbl, sbj; int64_t k;
-  q128 alpha, beta; q128 *C; int64_t sci, scj;
-};
-__device__ __noinline__ qwide oz_merge(qwide a, qwide b) { qw_merge(a, b); return a; }
-/* one warp per flagged C element: the k products go into the unrounded window accumulator (lanes
- * stride over k), a shuffle tree merges the 32 windows, lane 0 rounds once and applies the epilogue */
-__global__ void __launch_bounds__(128) k_oz_fixup(const OzFixArgs g)
-{
-  __shared__ uint32_t scr[QWA_COL_WORDS * 128];
-  const int lane = threadIdx.x & 31;
-  uint32_t *col = scr + threadIdx.x;
-  qwa_col_init(col, 128);
-  int count = *g.counter;
-  if (count > g.list_cap) count = g.list_cap;
-  const int nwarps = gridDim.x * 4;
-  for (int e = blockIdx.x * 4 + (threadIdx.x >> 5); e < count; e += nwarps) {
-    const int2 ij = g.list[e];
-    const q128 *ap = g.A + (int64_t)ij.x * g.sai, *bp = g.B + (int64_t)ij.y * g.sbj;
-    qwacc acc = qwa_zero();
-    uint32_t bad = 0;
-    for (int64_t l = lane; l < g.k; l += 32) {
-      const q128 a = ap[l * g.sal], b = bp[l * g.sbl];
-      if (qwa_fma(acc, qop_load_n(a), qop_load_n(b), col, 128)) qwa_fma_rare(acc, a, b, bad);
-    }
-    qwide v = qwa_fold(acc);
-#pragma unroll 1
-    for (int o = 16; o > 0; o >>= 1) {
-      qwide t;
-      t.w0 = __shfl_down_sync(0xffffffffu, v.w0, o); t.w1 = __shfl_down_sync(0xffffffffu, v.w1, o);
-      t.w2 = __shfl_down_sync(0xffffffffu, v.w2, o); t.w3 = __shfl_down_sync(0xffffffffu, v.w3, o);
-      t.w4 = __shfl_down_sync(0xffffffffu, v.w4, o); t.w5 = __shfl_down_sync(0xffffffffu, v.w5, o);
-      t.E = __shfl_down_sync(0xffffffffu, v.E, o);
-      v = oz_merge(v, t);
-    }
-    if (lane == 0) {
-      q128 *c = g.C + (int64_t)ij.x * g.sci + (int64_t)ij.y * g.scj;
-      *c = q_fma(g.alpha, qw_finish(v, bad), q_mul(g.beta, *c));
-    }
-  }
-}
-
-
-/* ================================================================== residue scheme (qb_crt.cuh) */
-/* The 4 elements (row r, k = 4 g4 .. 4 g4 + 3) as words of |X| and signs, X = x / 2^(base - 16495) an exact integer below 2^W. */
+/* ------------------------------------------------------------------ residues */
+/* The 4 elements (row r, k = 4 g4 .. 4 g4 + 3) as the words residue_sym consumes (crt::element_words: |X| or its two's
+ * complement, X = trunc(x / 2^(base - 16495)) < 2^W). */
 struct Crt4 { uint32_t w[4][crt::NWMAX]; uint32_t sign[4]; };
 template <int NW>
 __device__ __forceinline__ void crt_load4(const q128 *__restrict__ X, int64_t r, int64_t g4, int64_t K, int64_t sr, int64_t sk, int base, Crt4 &c)
 {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-#pragma unroll
-    for (int j = 0; j < crt::NWMAX; ++j) c.w[q][j] = 0;
-    c.sign[q] = 0;
     const int64_t k = g4 * 4 + q;
-    if (k >= K) continue;
-    const OzElem e = oz_unpack(X[r * sr + k * sk]);
-    if (!(e.lo | e.hi) || e.special) continue;
-    u256 v; v.w0 = e.lo; v.w1 = e.hi; v.w2 = 0; v.w3 = 0;
-    const int sh = e.ee - base;
-    v = sh >= 0 ? u256_shl(v, (uint32_t)sh) : u256_shr_jam(v, (uint32_t)(-sh)); /* exact: base <= lowest set bit of the row */
-    c.w[q][0] = (uint32_t)v.w0; c.w[q][1] = (uint32_t)(v.w0 >> 32);
-    c.w[q][2] = (uint32_t)v.w1; c.w[q][3] = (uint32_t)(v.w1 >> 32);
-    c.w[q][4] = (uint32_t)v.w2; c.w[q][5] = (uint32_t)(v.w2 >> 32);
-    c.sign[q] = e.sign;
-    if (e.sign) crt::negate_words<NW>(c.w[q]);   /* non-zero here: 2^(32 NW) - |X|, the seed of residue_sym carries the rest */
+    if (k >= K) {
+#pragma unroll
+      for (int j = 0; j < crt::NWMAX; ++j) c.w[q][j] = 0;
+      c.sign[q] = 0;
+      continue;
+    }
+    crt::element_words<NW>(X[r * sr + k * sk], base, c.w[q], c.sign[q]);
   }
 }
 /* residues of the 4 elements modulo p_i packed as 4 int8 (byte q = element q) */
 template <int NW>
 __device__ __forceinline__ uint32_t crt_word(const Crt4 &c, int i)
 {
-  /* the elements arrive with negative ones already in two's complement (crt_load4<NW>) */
   const uint32_t r0 = crt::residue_sym<NW>(c.w[0], c.sign[0], i, c_crt), r1 = crt::residue_sym<NW>(c.w[1], c.sign[1], i, c_crt);
   const uint32_t r2 = crt::residue_sym<NW>(c.w[2], c.sign[2], i, c_crt), r3 = crt::residue_sym<NW>(c.w[3], c.sign[3], i, c_crt);
   return __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);   /* low bytes of r0..r3 */
@@ -631,17 +380,20 @@ __global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X
   }
 }
 
-/* rows contiguous in memory: CTA = 32 rows x 32 k with lanes along the rows (coalesced 16-byte loads); the plane words are
- * transposed through shared memory and leave as 32-byte runs along K (cf. k_oz_slice_t) */
-static constexpr int CRT_T_SMEM = crt::NMP * 32 * 9 * 4;
+/* rows contiguous in memory (B of a row-major product, A of a col-major one): CTA = 16 rows x 32 k, 128 threads with the 16 lanes of
+ * a half-warp along the rows (256-byte contiguous loads); the plane words are transposed through shared memory and leave as
+ * 32-byte runs along K (the direct store would scatter 4-byte words Kp bytes apart).  The tile is this small on purpose:
+ * N * 16 * 9 words (23.6 KB at 41 moduli, 28.2 KB at 49) fit NEXT TO the persistent tensor kernel's 193 KB of shared memory, so
+ * the residues of the next B panel are computed on the integer pipes while the tensor kernel of the current panel runs. */
+static inline int crt_t_smem(int N) { return N * 16 * 9 * 4; }
 template <int NW>
-__global__ void __launch_bounds__(256) k_crt_residues_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
+__global__ void __launch_bounds__(128) k_crt_residues_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
                                                         int W, int N, int64_t Kp, int8_t *__restrict__ planes)
 {
   extern __shared__ uint32_t crt_sm[];            /* [plane][row][k-group], padded: 9 words per row */
-  const int lane = threadIdx.x & 31, wg = threadIdx.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * 32, g0 = (int64_t)blockIdx.y * 8;
-  const int64_t r = r0 + lane, g4 = g0 + wg;
+  const int row_l = threadIdx.x & 15, kg = threadIdx.x >> 4;
+  const int64_t r0 = (int64_t)blockIdx.x * 16, g0 = (int64_t)blockIdx.y * 8;
+  const int64_t r = r0 + row_l, g4 = g0 + kg;
   if (r < rows) {
     Crt4 c;
     crt_load4<NW>(X, r, g4, K, sr, sk, emax[r] + 113 - W, c);
@@ -651,28 +403,32 @@ __global__ void __launch_bounds__(256) k_crt_residues_t(const q128 *__restrict__
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int i = 4 * g + b;
-          if (i < N) crt_sm[(i * 32 + lane) * 9 + wg] = crt_word<NW>(c, i);
+          if (i < N) crt_sm[(i * 16 + row_l) * 9 + kg] = crt_word<NW>(c, i);
         }
       }
     }
   }
   __syncthreads();
-  for (int q = threadIdx.x; q < N * 64; q += 256) {
-    const int i = q >> 6, row = (q & 63) >> 1, half = q & 1;
+  for (int q = threadIdx.x; q < N * 32; q += 128) {
+    const int i = q >> 5, row = (q & 31) >> 1, half = q & 1;
     if (r0 + row >= rows) continue;
-    const uint32_t *src = &crt_sm[(i * 32 + row) * 9 + half * 4];
+    const uint32_t *src = &crt_sm[(i * 16 + row) * 9 + half * 4];
     *reinterpret_cast<uint4 *>(planes + ((int64_t)i * rows + r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
   }
 }
 
+/* ------------------------------------------------------------------ fold: residues -> binary128 */
 struct CrtFoldArgs {
-  const uint8_t *R; int64_t Mp, Np;
-  int64_t m, n, row0;                /* C rows [row0, row0 + m) of the full problem are this pass */
-  const int *emaxA, *emaxB; int WA, WB;
+  const uint8_t *R; int64_t Mp, Np;  /* residues of this unit: [N][Mp][Np] */
+  int64_t m, n, row0, col0;          /* the unit is C rows [row0, row0 + m) x columns [col0, col0 + n) of the call's C */
+  const int *emaxA, *lminA, *spA, *emaxB, *lminB, *spB; int WA, WB;   /* per row / column of the whole call */
+  int64_t k;
   q128 alpha, beta; q128 *C; int64_t sci, scj;
   int simple;                        /* alpha == 1 and beta == +-0 */
   int64_t n4p;                       /* threads per row: ceil(n / 4) rounded up to 32 */
-  int npeer; q128 *peer[QB_MAX_PEERS]; /* fused gather: the same C block inside each peer GPU's buffer (NVLink peer stores) */
+  int check;                         /* capped windows or Inf / NaN present: test every element (crt::accept_msb), rejected ones are listed */
+  int2 *list; int list_cap; int *counter; uint8_t *flag;   /* rejected elements: (row, column) of the call's C; beyond list_cap: flag[i * Np + j] = 1 */
+  int npeer; q128 *peer[QB_MAX_PEERS]; /* fused gather: the call's C inside each peer GPU's buffer (or one NVSwitch multicast address) */
 };
 /* thread = 4 consecutive columns of one C row: one 32-bit load per residue plane, then per element the reconstruction
  * (crt::reconstruct_dev), ONE rounding to binary128 and the reference epilogue C = fma(alpha, s, mul(beta, C)) (level3.hpp:102-109).
@@ -695,29 +451,47 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
     uint32_t rw[4 * NG];
 #pragma unroll
     for (int c = 0; c < 4 * NG; ++c) rw[c] = c < pl.N ? *reinterpret_cast<const uint32_t *>(g.R + (int64_t)c * plane + off) : 0u;
-    const int baseA = g.emaxA[g.row0 + i] + 113 - g.WA;
+    const int64_t gi = g.row0 + i;
+    const int eA = g.emaxA[gi];
+    const int baseA = eA + 113 - g.WA;
+    bool tA = false, sA = false;
+    if (g.check) { tA = eA != 0 && g.lminA[gi] < baseA; sA = g.spA[gi] != 0; }
 #pragma unroll 1
     for (int e = 0; e < 4; ++e) {
       const int64_t j = j0 + e;
       if (j >= g.n) break;
+      const int64_t gj = g.col0 + j;
       uint32_t r[crt::NMP];
 #pragma unroll
       for (int c = 0; c < 4 * NG; ++c) r[c] = (rw[c] >> (8 * e)) & 0xffu;
       uint32_t Y[NG + 1], neg;
       crt::reconstruct_dev<NG>(r, pl, Y, neg);
-      const int baseB = g.emaxB[j] + 113 - g.WB;
-      const q128 sum = crt::limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
-      q128 *c = g.C + i * g.sci + j * g.scj;
+      const int eB = g.emaxB[gj];
+      const int baseB = eB + 113 - g.WB;
+      q128 *c = g.C + gi * g.sci + gj * g.scj;
       const q128 cin = *c;
-      /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
-       * general line below, without the two software roundings */
       q128 out;
-      if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) out = sum;
-      else out = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
-      *c = out;
+      bool reject = false;
+      if (g.check) {
+        const bool tB = eB != 0 && g.lminB[gj] < baseB;
+        reject = sA || g.spB[gj] != 0 || crt::limbs_msb<NG + 1>(Y) < crt::accept_msb(tA, tB, g.WA, g.WB, g.k);
+      }
+      if (reject) { /* left to k_crt_fixup (C_in stays in place for its epilogue) */
+        const int slot = atomicAdd(g.counter, 1);
+        if (slot < g.list_cap) g.list[slot] = make_int2((int)gi, (int)gj);
+        else g.flag[i * g.Np + j] = 1;
+        out = cin;
+      } else {
+        const q128 sum = crt::limbs_to_q<NG + 1>(Y, neg, baseA + baseB - 2 * 16495);
+        /* alpha = 1, beta = +-0, finite C: mul(beta, C) = +-0 and fma(1, s, +-0) = s (s is never -0) - the same bits as the
+         * general line below, without the two software roundings */
+        if (g.simple && ((cin.hi >> 48) & 0x7fffu) != 0x7fffu) out = sum;
+        else out = q_fma(g.alpha, sum, q_mul(g.beta, cin)); /* beta*C is always evaluated */
+        *c = out;
+      }
       if (stage) fold_sm[warp * 128 + 4 * lane + e] = make_uint4((uint32_t)out.lo, (uint32_t)(out.lo >> 32), (uint32_t)out.hi, (uint32_t)(out.hi >> 32));
-      else
-        for (int q = 0; q < g.npeer; ++q) g.peer[q][i * g.sci + j * g.scj] = out;   /* col-major C: element-wise peer stores */
+      else if (!reject)
+        for (int q = 0; q < g.npeer; ++q) g.peer[q][gi * g.sci + gj * g.scj] = out;   /* col-major C: element-wise peer stores */
     }
   }
   if (stage) {
@@ -729,7 +503,7 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
         const int64_t col = jw + 32 * s4 + lane;
         if (col < g.n) {
           const uint4 v = fold_sm[warp * 128 + 32 * s4 + lane];
-          for (int q = 0; q < g.npeer; ++q) *reinterpret_cast<uint4 *>(g.peer[q] + i * g.sci + col) = v;
+          for (int q = 0; q < g.npeer; ++q) *reinterpret_cast<uint4 *>(g.peer[q] + (g.row0 + i) * g.sci + g.col0 + col) = v;
         }
       }
     }
@@ -751,6 +525,66 @@ static void launch_crt_fold(const CrtFoldArgs &f, const crt::Plan &pl, cudaStrea
 #undef QB_CRT_CASE
   }
   count_launch();
+}
+
+/* ------------------------------------------------------------------ fix-up of the rejected elements */
+struct CrtFixArgs {
+  const int2 *list; const int *counter; int list_cap; const uint8_t *flag;
+  int64_t um, un, uNp, row0, col0;   /* the unit (for the flag scan when the list overflowed) */
+  const q128 *A; int64_t sai, sal; const q128 *B; int64_t sbl, sbj; int64_t k;
+  q128 alpha, beta; q128 *C; int64_t sci, scj;
+  int *total;                        /* running count of fixed elements of the call (stats) */
+  int npeer; q128 *peer[QB_MAX_PEERS];
+};
+__device__ __noinline__ qwide crt_merge(qwide a, qwide b) { qw_merge(a, b); return a; }
+/* One warp per rejected C element: the k products go into the unrounded window accumulator of qwide.cuh (lanes stride over k),
+ * a shuffle tree merges the 32 windows and the Inf / NaN classes, lane 0 rounds once and applies the reference epilogue.
+ * Elements come from the list; when more were rejected than it holds, the rest is found by scanning the unit's flag bytes. */
+__global__ void __launch_bounds__(128) k_crt_fixup(const CrtFixArgs g)
+{
+  __shared__ uint32_t scr[QWA_COL_WORDS * 128];
+  const int lane = threadIdx.x & 31;
+  uint32_t *col = scr + threadIdx.x;
+  qwa_col_init(col, 128);
+  const int count = *g.counter;
+  if (count == 0) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(g.total, count);
+  const int64_t nwarps = (int64_t)gridDim.x * 4, wid = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int64_t listed = count < g.list_cap ? count : g.list_cap;
+  const int64_t scan = count > g.list_cap ? g.um * g.uNp : 0;
+  for (int64_t e = wid; e < listed + scan; e += nwarps) {
+    int64_t gi, gj;
+    if (e < listed) { const int2 ij = g.list[e]; gi = ij.x; gj = ij.y; }
+    else {
+      const int64_t f = e - listed;
+      if (!g.flag[f]) continue;
+      gi = g.row0 + f / g.uNp; gj = g.col0 + f % g.uNp;
+    }
+    const q128 *ap = g.A + gi * g.sai, *bp = g.B + gj * g.sbj;
+    qwacc acc = qwa_zero();
+    uint32_t bad = 0;
+    for (int64_t l = lane; l < g.k; l += 32) {
+      const q128 a = ap[l * g.sal], b = bp[l * g.sbl];
+      if (qwa_fma(acc, qop_load_n(a), qop_load_n(b), col, 128)) qwa_fma_rare(acc, a, b, bad);
+    }
+    qwide v = qwa_fold(acc);
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+      qwide t;
+      t.w0 = __shfl_down_sync(0xffffffffu, v.w0, o); t.w1 = __shfl_down_sync(0xffffffffu, v.w1, o);
+      t.w2 = __shfl_down_sync(0xffffffffu, v.w2, o); t.w3 = __shfl_down_sync(0xffffffffu, v.w3, o);
+      t.w4 = __shfl_down_sync(0xffffffffu, v.w4, o); t.w5 = __shfl_down_sync(0xffffffffu, v.w5, o);
+      t.E = __shfl_down_sync(0xffffffffu, v.E, o);
+      bad |= __shfl_down_sync(0xffffffffu, bad, o);
+      v = crt_merge(v, t);
+    }
+    if (lane == 0) {
+      const int64_t off = gi * g.sci + gj * g.scj;
+      const q128 out = q_fma(g.alpha, qw_finish(v, bad), q_mul(g.beta, g.C[off]));
+      g.C[off] = out;
+      for (int q = 0; q < g.npeer; ++q) g.peer[q][off] = out;
+    }
+  }
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -784,84 +618,64 @@ static bool make_plane_map(CUtensorMap *tm, const int8_t *planes, int S, int64_t
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static int g_sm_count = 0;
-static int sm_count()
-{
-  if (!g_sm_count) {
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  return g_sm_count;
-}
-
-/* D[d] = sum_{s+t=d} A_s B_t^T over k-blocks [kb_begin, kb_begin + nkb) */
-cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
-                          int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep)
-{
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_oz_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_oz_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  CUtensorMap tmA, tmB;
-  if (!make_plane_map(&tmA, pA, SA, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, SB, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
-  OzMmaArgs g;
-  g.D = D; g.R = nullptr; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
-  if (keep > 0 && keep < g.ndiag) g.ndiag = keep;   /* diagonals 0 .. keep-1 only */
-  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
-  g.kb_begin = kb_begin; g.nkb = nkb;
-  /* heaviest diagonals first so the static round-robin over CTAs stays balanced */
-  int idx[OZ_MAX_DIAG + 1];
-  for (int d = 0; d < g.ndiag; ++d) idx[d] = d;
-  auto pairs = [&](int d) { return std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; };
-  std::stable_sort(idx, idx + g.ndiag, [&](int a, int b) { return pairs(a) > pairs(b); });
-  for (int d = 0; d < g.ndiag; ++d) g.order[d] = (uint8_t)idx[d];
-  const int total = g.ndiag * g.m_tiles * g.n_tiles;
-  const int grid = std::min(total, sm_count());
-  k_oz_mma<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
-  count_launch();
-  return cudaGetLastError();
-}
-
-/* residue scheme: R_i = (A_i B_i^T) mod p_i for the N residue planes, all k-blocks [0, nkb) in one accumulation
- * (|acc| <= 128*128*Kp <= 2^30: Kp <= 65536) */
-static cudaError_t launch_crt_mma(const int8_t *pA, const int8_t *pB, int N, int64_t m, int64_t n, int64_t Kp, uint8_t *R, int64_t Mp, int64_t Np,
-                                  cudaStream_t st)
-{
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_oz_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  CUtensorMap tmA, tmB;
-  if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
-  OzMmaArgs g;
-  memset(&g, 0, sizeof(g));
-  g.R = R; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
-  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
-  g.kb_begin = 0; g.nkb = (int)(Kp / OZ_BK);
-  const int64_t total = (int64_t)N * g.m_tiles * g.n_tiles;
-  const int grid = (int)std::min<int64_t>(total, sm_count());
-  k_oz_mma<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
-  count_launch();
-  return cudaGetLastError();
-}
-
-/* ---- workspaces (grow-only, per process; callers hold the library mutex) ----
- * meta: per-row exponent data + plan (small, survives a regrowth of the big buffer)
- * buf : digit planes, diagonals, wide accumulators */
-struct OzWork {
-  void *buf = nullptr; size_t bytes = 0;
-  void *meta = nullptr; size_t meta_bytes = 0;
-  int device = -1;
-  int *h_plan = nullptr; /* pinned, 16 ints */
+/* ---- per-device state (callers hold the library mutex): streams, events, workspaces, one-time kernel attributes.
+ * A process that switches the current device gets an independent set for each device. ---- */
+static constexpr int OZ_MAX_EV = 1024;       /* timed tensor-kernel launches per qgemm */
+enum { EV_IN = 0, EV_SCAN_A, EV_SCAN_B, EV_DONE, EV_MMA0, EV_MMA1, EV_FOLD0, EV_FOLD1, EV_SLOT0 };
+struct OzDev {
+  bool ready = false;
+  int sm_count = 148;
+  void *buf = nullptr; size_t bytes = 0;          /* grow-only: residue planes, residues, flags, list */
+  void *meta = nullptr; size_t meta_bytes = 0;    /* per-row exponent data + plan words (small, survives a regrowth of buf) */
+  int *h_plan = nullptr;                          /* pinned, 16 ints */
+  cudaStream_t sM = nullptr, sA = nullptr, sB = nullptr, sF = nullptr;
+  std::vector<cudaEvent_t> ev;                    /* ordering events (no timing) */
+  std::vector<cudaEvent_t> tev;                   /* timing events around the tensor kernel */
+  int tev_used = 0;
+  bool stats_pending = false;
 };
-static OzWork g_oz;
+static OzDev g_dev[QB_MAX_DEVICES];
+
+static cudaError_t oz_dev(OzDev **out)
+{
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= QB_MAX_DEVICES) return cudaErrorInvalidDevice;
+  OzDev &D = g_dev[dev];
+  *out = &D;
+  if (D.ready) return cudaSuccess;
+  cudaDeviceGetAttribute(&D.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (D.sm_count <= 0) D.sm_count = 148;
+  e = cudaFuncSetAttribute(k_oz_mma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_oz_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM);
+  if (e != cudaSuccess) return e;
+  static crt::Tables T;
+  crt::host::build_tables(T);
+  e = cudaMemcpyToSymbol(c_crt, &T, sizeof(T));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();   /* once per device: the copy from pageable memory must have landed before any stream reads it */
+  if (e != cudaSuccess) return e;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, i == 0 ? hi : lo);
+  if (e == cudaSuccess) e = cudaMallocHost((void **)&D.h_plan, 64);
+  if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) if (s[i]) cudaStreamDestroy(s[i]); return e; }
+  D.sM = s[0]; D.sA = s[1]; D.sB = s[2]; D.sF = s[3];
+  D.ready = true;
+  return cudaSuccess;
+}
+static cudaError_t oz_event(OzDev &D, int idx, cudaEvent_t *out)
+{
+  while ((int)D.ev.size() <= idx) {
+    cudaEvent_t e;
+    const cudaError_t r = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (r != cudaSuccess) return r;
+    D.ev.push_back(e);
+  }
+  *out = D.ev[idx];
+  return cudaSuccess;
+}
 static cudaError_t oz_grow(void **p, size_t *have, size_t want)
 {
   if (want <= *have) return cudaSuccess;
@@ -872,94 +686,100 @@ static cudaError_t oz_grow(void **p, size_t *have, size_t want)
   *have = want;
   return cudaSuccess;
 }
-static cudaError_t oz_reserve(size_t meta_bytes, size_t bytes)
-{
-  int dev = 0; cudaGetDevice(&dev);
-  if (g_oz.device != dev) { /* buffers of another device are left to that context */
-    g_oz.buf = nullptr; g_oz.bytes = 0; g_oz.meta = nullptr; g_oz.meta_bytes = 0; g_oz.device = dev;
-  }
-  if (!g_oz.h_plan) { cudaError_t e = cudaMallocHost((void **)&g_oz.h_plan, 64); if (e != cudaSuccess) return e; }
-  cudaError_t e = oz_grow(&g_oz.meta, &g_oz.meta_bytes, meta_bytes);
-  if (e != cudaSuccess) return e;
-  return oz_grow(&g_oz.buf, &g_oz.bytes, bytes);
-}
 void oz_release()
 {
-  if (g_oz.buf) cudaFree(g_oz.buf);
-  if (g_oz.meta) cudaFree(g_oz.meta);
-  g_oz.buf = nullptr; g_oz.bytes = 0; g_oz.meta = nullptr; g_oz.meta_bytes = 0;
+  OzDev *D;
+  if (oz_dev(&D) != cudaSuccess) return;
+  if (D->buf) cudaFree(D->buf);
+  if (D->meta) cudaFree(D->meta);
+  D->buf = nullptr; D->bytes = 0; D->meta = nullptr; D->meta_bytes = 0;
 }
 
 static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 static OzStats g_last_stats;
-OzStats oz_last_stats() { return g_last_stats; }
-static int g_oz_keep = 16;      /* leading diagonals multiplied in the bounded setting; 0 = all (exact) */
-void oz_set_keep(int keep) { g_oz_keep = keep < 0 ? 0 : keep; }
-int oz_get_keep() { return g_oz_keep; }
+OzStats oz_last_stats()
+{
+  OzDev *D;
+  if (g_last_stats.pairs > 0 && oz_dev(&D) == cudaSuccess && D->stats_pending) { /* the fix-up count arrives with the call's last work */
+    cudaEvent_t done;
+    if (oz_event(*D, EV_DONE, &done) == cudaSuccess && cudaEventSynchronize(done) == cudaSuccess) g_last_stats.flagged = D->h_plan[8];
+    D->stats_pending = false;
+  }
+  return g_last_stats;
+}
 
 /* CUDA events around every k_oz_mma launch of the last qgemm, on the launching stream (bench.py's
  * roofline needs the kernel's own duration, not the whole call's) */
-static constexpr int OZ_MAX_EV = 64;
-static cudaEvent_t g_ev[2 * OZ_MAX_EV];
-static int g_ev_made = 0, g_ev_used = 0;
-static void oz_ev_record(int which, cudaStream_t st)
+static void oz_ev_record(OzDev &D, int which, cudaStream_t st)
 {
-  if (g_ev_used >= OZ_MAX_EV) return;
-  if (!g_ev_made) { for (int i = 0; i < 2 * OZ_MAX_EV; ++i) cudaEventCreate(&g_ev[i]); g_ev_made = 1; }
-  cudaEventRecord(g_ev[2 * g_ev_used + which], st);
-  if (which == 1) ++g_ev_used;
+  if (D.tev_used >= OZ_MAX_EV) return;
+  while ((int)D.tev.size() < 2 * (D.tev_used + 1)) { cudaEvent_t e; if (cudaEventCreate(&e) != cudaSuccess) return; D.tev.push_back(e); }
+  cudaEventRecord(D.tev[2 * D.tev_used + which], st);
+  if (which == 1) ++D.tev_used;
 }
 /* blocks until the last recorded launch has finished; returns the summed duration in ms */
 double oz_last_mma_ms(int *launches)
 {
+  OzDev *D;
   double tot = 0;
-  for (int i = 0; i < g_ev_used; ++i) {
+  if (launches) *launches = 0;
+  if (oz_dev(&D) != cudaSuccess) return 0;
+  for (int i = 0; i < D->tev_used; ++i) {
     float ms = 0;
-    if (cudaEventSynchronize(g_ev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, g_ev[2 * i], g_ev[2 * i + 1]) == cudaSuccess) tot += ms;
+    if (cudaEventSynchronize(D->tev[2 * i + 1]) == cudaSuccess && cudaEventElapsedTime(&ms, D->tev[2 * i], D->tev[2 * i + 1]) == cudaSuccess) tot += ms;
   }
-  if (launches) *launches = g_ev_used;
+  if (launches) *launches = D->tev_used;
   return tot;
 }
 
-static void launch_oz_slice(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int S, int64_t Kp, int8_t *planes, cudaStream_t st)
+/* plain int8 GEMM on the tcgen05 pipeline: D[d] = sum_{s+t=d} A_s B_t^T over k-blocks [kb_begin, kb_begin + nkb) */
+cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
+                          int32_t *Dout, int64_t Mp, int64_t Np, cudaStream_t st, int keep)
 {
-  if (sk == 1 || sr != 1) {
-    const int64_t threads = rows * (Kp / 4);
-    k_oz_slice<OZ_MAX_S><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, rows, K, sr, sk, emax, S, Kp, planes);
-  } else {
-    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)(Kp / 32));
-    k_oz_slice_t<OZ_MAX_S><<<grid, 256, 0, st>>>(X, rows, K, sr, sk, emax, S, Kp, planes);
-  }
+  OzDev *D;
+  cudaError_t e = oz_dev(&D);
+  if (e != cudaSuccess) return e;
+  CUtensorMap tmA, tmB;
+  if (!make_plane_map(&tmA, pA, SA, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, SB, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
+  OzMmaArgs g;
+  memset(&g, 0, sizeof(g));
+  g.D = Dout; g.R = nullptr; g.Mp = Mp; g.Np = Np; g.SA = SA; g.SB = SB; g.ndiag = SA + SB - 1;
+  if (keep > 0 && keep < g.ndiag) g.ndiag = keep;   /* diagonals 0 .. keep-1 only */
+  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
+  g.kb_begin = kb_begin; g.nkb = nkb;
+  /* heaviest diagonals first so the static round-robin over CTAs stays balanced */
+  int idx[OZ_MAX_DIAG + 1];
+  for (int d = 0; d < g.ndiag; ++d) idx[d] = d;
+  auto pairs = [&](int d) { return std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; };
+  std::stable_sort(idx, idx + g.ndiag, [&](int a, int b) { return pairs(a) > pairs(b); });
+  for (int d = 0; d < g.ndiag; ++d) g.order[d] = (uint8_t)idx[d];
+  const int total = g.ndiag * g.m_tiles * g.n_tiles;
+  const int grid = std::min(total, D->sm_count);
+  k_oz_mma<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
   count_launch();
+  return cudaGetLastError();
 }
 
-/* capacity of the fix-up list of one row pass: above 1/64 of the pass the exact redo is cheaper */
-static inline int64_t oz_list_cap(int64_t mb, int64_t n) { return std::max<int64_t>(1024, std::min<int64_t>((mb * n) / 64, (int64_t)1 << 22)); }
-
-
-/* ---- residue scheme, host side ---- */
-static int g_oz_scheme = 1;     /* 1 = residues (qb_crt.cuh), 0 = digit diagonals */
-void oz_set_scheme(int v) { g_oz_scheme = v ? 1 : 0; }
-int oz_get_scheme() { return g_oz_scheme; }
-
-static cudaError_t crt_upload_tables()
+/* residue scheme: R_i (+)= (A_i B_i^T) mod p_i for the N residue planes over k-blocks [kb_begin, kb_begin + nkb)
+ * (|acc| <= 128 * 128 * OZ_KCHUNK = 2^30) */
+static cudaError_t launch_crt_mma(OzDev &D, const int8_t *pA, const int8_t *pB, int N, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb, int accum,
+                                  uint8_t *R, int64_t Mp, int64_t Np, cudaStream_t st)
 {
-  static int uploaded_dev = -1;
-  int dev = 0; cudaGetDevice(&dev);
-  if (uploaded_dev == dev) return cudaSuccess;
-  static crt::Tables T;
-  crt::host::build_tables(T);
-  cudaError_t e = cudaMemcpyToSymbol(c_crt, &T, sizeof(T));
-  if (e != cudaSuccess) return e;
-  e = cudaDeviceSynchronize();   /* once per device: the copy from pageable memory must have landed before any stream reads it */
-  if (e != cudaSuccess) return e;
-#define QB_CRT_ATTR(NW) e = cudaFuncSetAttribute(k_crt_residues_t<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CRT_T_SMEM); if (e != cudaSuccess) return e;
-  QB_CRT_ATTR(1) QB_CRT_ATTR(2) QB_CRT_ATTR(3) QB_CRT_ATTR(4) QB_CRT_ATTR(5) QB_CRT_ATTR(6)
-#undef QB_CRT_ATTR
-  uploaded_dev = dev;
-  return cudaSuccess;
+  CUtensorMap tmA, tmB;
+  if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
+  OzMmaArgs g;
+  memset(&g, 0, sizeof(g));
+  g.R = R; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
+  g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
+  g.kb_begin = kb_begin; g.nkb = nkb; g.accum = accum;
+  const int64_t total = (int64_t)N * g.m_tiles * g.n_tiles;
+  const int grid = (int)std::min<int64_t>(total, D.sm_count);
+  k_oz_mma<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(tmA, tmB, g);
+  count_launch();
+  return cudaGetLastError();
 }
+
 static const crt::Plan &crt_plan(int N)
 {
   static crt::Plan plans[crt::NM + 1];
@@ -974,12 +794,12 @@ static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t 
   const bool direct = (sk == 1 || sr != 1);
   const int64_t threads = rows * (Kp / 4);
   const unsigned g1 = (unsigned)((threads + 255) / 256);
-  const dim3 g2((unsigned)((rows + 31) / 32), (unsigned)(Kp / 32));
+  const dim3 g2((unsigned)((rows + 15) / 16), (unsigned)(Kp / 32));
   switch (nw) {
 #define QB_CRT_CASE(NW)                                                                                     \
   case NW:                                                                                                  \
     if (direct) k_crt_residues<NW><<<g1, 256, 0, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);          \
-    else k_crt_residues_t<NW><<<g2, 256, CRT_T_SMEM, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);      \
+    else k_crt_residues_t<NW><<<g2, 128, crt_t_smem(N), st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);   \
     break;
     QB_CRT_CASE(1) QB_CRT_CASE(2) QB_CRT_CASE(3) QB_CRT_CASE(4) QB_CRT_CASE(5) QB_CRT_CASE(6)
 #undef QB_CRT_CASE
@@ -987,13 +807,41 @@ static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t 
   count_launch();
 }
 
-/* Rows of each pass of the residue scheme: the sizes sum to m, every size but the last is a multiple of OZ_BM, none exceeds `cap`.
- * shape 0 (default, the measured one): equal passes of `cap` rows.  shape 1 (experimental, qb_set_tensor_pass_shape): a short
- * first pass (its A residues cannot overlap a tensor pass) and a short last pass (neither can its fold, nor its peer stores),
- * equal passes in between. */
+/* scan of `rows` rows of one operand on `st`: per-row statistics into emax / lmin / sp */
+static void launch_scan(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, int *emax, int *lmin, int *sp, cudaStream_t st)
+{
+  cudaMemsetAsync(emax, 0, (size_t)rows * 4, st); cudaMemsetAsync(lmin, 0x7f, (size_t)rows * 4, st); cudaMemsetAsync(sp, 0, (size_t)rows * 4, st);
+  const int64_t nch = (K + OZ_SCAN_CH - 1) / OZ_SCAN_CH;
+  const bool warp_mode = (sk == 1 || sr != 1);
+  const int64_t threads = warp_mode ? rows * nch * 32 : rows * nch;
+  k_oz_scan<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(X, rows, K, sr, sk, emax, lmin, sp);
+  count_launch();
+}
+/* column statistics of op(B) for a caller that streams B in panels (qb_gemm_colstats_dev): stats = [emax[n] | lmin[n] | sp[n]] */
+cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, int64_t sbl, int *stats, cudaStream_t st)
+{
+  launch_scan(B, n, k, sbj, sbl, stats, stats + n, stats + 2 * n, st);
+  return cudaGetLastError();
+}
+
+/* ---- tuning knobs (qb_set_tensor_window / qb_set_tensor_unit) ---- */
+static int g_window = 144;            /* bits per window the planner grants when the spans do not fit (2 x 144 + log2 k + 1 -> 42 moduli at k = 8192) */
+static int64_t g_unit_rows = 2048, g_unit_cols = 2048;
+void oz_set_window(int bits) { g_window = bits < 120 ? 120 : (bits > crt::WMAX ? crt::WMAX : bits); }
+int oz_get_window() { return g_window; }
+void oz_set_unit(int64_t rows, int64_t cols)
+{
+  g_unit_rows = rows <= 0 ? 2048 : std::max<int64_t>(OZ_BM, rup(rows, OZ_BM));
+  g_unit_cols = cols <= 0 ? 2048 : std::max<int64_t>(OZ_BN, rup(cols, OZ_BN));
+}
+void oz_get_unit(int64_t *rows, int64_t *cols) { *rows = g_unit_rows; *cols = g_unit_cols; }
+/* legacy knobs of the row-pass partition (kept for the tests of the partition helper) */
 static int g_oz_pass_shape = 0;
 void oz_set_pass_shape(int v) { g_oz_pass_shape = v == 1 ? 1 : 0; }
 int oz_get_pass_shape() { return g_oz_pass_shape; }
+/* Rows of each pass: the sizes sum to m, every size but the last is a multiple of OZ_BM, none exceeds `cap`.  shape 0: equal
+ * passes of `cap` rows.  shape 1: a short first pass (its residues cannot overlap a tensor pass) and a short last pass (neither
+ * can its fold, nor its peer stores), equal passes in between. */
 std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape)
 {
   std::vector<int64_t> rows;
@@ -1011,301 +859,205 @@ std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape)
   return rows;
 }
 
-/* Internal streams of the residue scheme: the tensor kernel of row pass p (sM, highest priority) runs while the residues of
- * the A rows of pass p+1 (sA) and the reconstruction of pass p-1 (sF) use the integer pipes of the same SMs (the persistent
- * tensor kernel holds one 192-thread CTA per SM; the other two kernels need no shared memory and fit beside it). */
-struct CrtStreams {
-  cudaStream_t sM = nullptr, sA = nullptr, sF = nullptr;
-  cudaEvent_t in = nullptr, resA[2] = {nullptr, nullptr}, mma[2] = {nullptr, nullptr}, fold[2] = {nullptr, nullptr};
-  int device = -1;
-};
-static CrtStreams g_cs;
-static cudaError_t crt_streams()
+/* The whole fast-mode GEMM.  *used = 0 means the planner declined (no TMA entry point, or not even one unit fits the
+ * workspace budget) and nothing was written: the caller runs the integer-limb kernel. */
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, const OzHooks &h)
 {
-  int dev = 0; cudaGetDevice(&dev);
-  if (g_cs.device == dev) return cudaSuccess;
-  int lo = 0, hi = 0;
-  cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  cudaError_t e = cudaStreamCreateWithPriority(&g_cs.sM, cudaStreamNonBlocking, hi);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g_cs.sA, cudaStreamNonBlocking, lo);
-  if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&g_cs.sF, cudaStreamNonBlocking, lo);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.in, cudaEventDisableTiming);
-  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-    e = cudaEventCreateWithFlags(&g_cs.resA[b], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.mma[b], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g_cs.fold[b], cudaEventDisableTiming);
-  }
-  if (e == cudaSuccess) g_cs.device = dev;
-  return e;
-}
-
-/* The residue-scheme GEMM after scan + plan (WA, WB = widest row / column span in bits, no Inf/NaN).  *used = 0: declined.
- * The C rows are produced in row passes, software-pipelined over three internal streams (CrtStreams); `st` waits for the
- * reconstruction of every pass before the pass callback runs and before this function returns, so for the caller all the
- * work is ordered on `st` as usual. */
-static cudaError_t launch_gemm_crt(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes,
-                                   int WA, int WB, size_t meta_ints)
-{
+  *used = 0;
+  { const int64_t keep = g_last_stats.ws_bytes; g_last_stats = OzStats(); g_last_stats.ws_bytes = keep; }
+  if (!get_encode()) return cudaSuccess;
+  OzDev *Dp;
+  cudaError_t e = oz_dev(&Dp);
+  if (e != cudaSuccess) return e;
+  OzDev &D = *Dp;
+  D.tev_used = 0;
+  D.stats_pending = false;
   const int64_t m = a.m, n = a.n, k = a.k;
   const int64_t Kp = rup(k, OZ_BK);
-  WA = std::max(WA, 1); WB = std::max(WB, 1);
-  if (WA > crt::WMAX || WB > crt::WMAX || Kp > 65536) return cudaSuccess;
-  int lk = 0;
-  while (((int64_t)1 << lk) < k) ++lk;
-  const int need_bits = WA + WB + lk + 1;             /* P > 2 * k * 2^(WA + WB) >= 2 |I| */
-  const int N = crt::host::moduli_for_bits(need_bits);
-  if (N == 0) return cudaSuccess;
-  cudaError_t e = crt_upload_tables();
-  if (e != cudaSuccess) return e;
-  e = crt_streams();
-  if (e != cudaSuccess) return e;
+#define QB_TRY(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+  cudaEvent_t evIn, evScanA, evScanB, evDone;
+  QB_TRY(oz_event(D, EV_IN, &evIn)); QB_TRY(oz_event(D, EV_SCAN_A, &evScanA)); QB_TRY(oz_event(D, EV_SCAN_B, &evScanB)); QB_TRY(oz_event(D, EV_DONE, &evDone));
+  /* ---- scan (A on one stream, B on another) + plan; ONE host sync, for the 3-int plan ---- */
+  const size_t meta_ints = (size_t)(3 * m + 3 * n + 32);
+  QB_TRY(oz_grow(&D.meta, &D.meta_bytes, meta_ints * 4));
+  int *meta = (int *)D.meta;
+  int *statA = meta, *statB = meta + 3 * m, *misc = meta + 3 * m + 3 * n;
+  const int *emaxA = statA, *lminA = statA + m, *spA = statA + 2 * m, *emaxB = statB, *lminB = statB + n, *spB = statB + 2 * n;
+  int *plan = misc, *total = misc + 8, *counter = misc + 9;
+  QB_TRY(cudaMemsetAsync(misc, 0, 32 * 4, st));
+  QB_TRY(cudaEventRecord(evIn, st));
+  QB_TRY(cudaStreamWaitEvent(D.sA, evIn, 0)); QB_TRY(cudaStreamWaitEvent(D.sB, evIn, 0));
+  /* streamed rows (h.rows_in): A is not on the device yet; its rows are scanned pass by pass right before their residues, the
+   * window of A is the planner's budget and every element is tested (check) */
+  if (h.rows_in) { QB_TRY(cudaMemsetAsync(statA, 0, (size_t)m * 4, D.sA)); QB_TRY(cudaMemsetAsync(statA + m, 0x7f, (size_t)m * 4, D.sA)); QB_TRY(cudaMemsetAsync(statA + 2 * m, 0, (size_t)m * 4, D.sA)); }
+  else launch_scan(a.A, m, k, a.sai, a.sal, statA, statA + m, statA + 2 * m, D.sA);
+  QB_TRY(cudaEventRecord(evScanA, D.sA));
+  if (h.bstats) QB_TRY(cudaMemcpyAsync(statB, h.bstats, (size_t)n * 12, cudaMemcpyDeviceToDevice, D.sB));
+  else launch_scan(a.B, n, k, a.sbj, a.sbl, statB, statB + n, statB + 2 * n, D.sB);
+  QB_TRY(cudaEventRecord(evScanB, D.sB));
+  QB_TRY(cudaStreamWaitEvent(st, evScanA, 0)); QB_TRY(cudaStreamWaitEvent(st, evScanB, 0));
+  k_oz_plan<<<1, 1024, 0, st>>>(emaxA, lminA, spA, m, emaxB, lminB, spB, n, plan);
+  count_launch();
+  QB_TRY(cudaMemcpyAsync(D.h_plan, plan, 16, cudaMemcpyDeviceToHost, st));
+  QB_TRY(cudaStreamSynchronize(st));
+  const int WA_nat = h.rows_in ? g_window : D.h_plan[0], WB_nat = D.h_plan[1], fl = D.h_plan[2];
+  crt::host::Windows win;
+  if (!crt::host::plan_windows(WA_nat, WB_nat, k, g_window, win)) return cudaSuccess;
+  const int WA = win.WA, WB = win.WB, N = win.N;
+  const int check = (win.truncA || win.truncB || fl || h.rows_in) ? 1 : 0;
   const crt::Plan &pl = crt_plan(N);
-  /* ---- workspace: residue planes of B | 2 x (residue planes of the A rows of a pass | R of the pass) ---- */
-  const int64_t Np = rup(n, OZ_BN);
-  const size_t pb_b = rup((int64_t)N * n * Kp, 1024);
-  auto pa_bytes = [&](int64_t mb) -> size_t { return (size_t)rup((int64_t)N * mb * Kp, 1024); };
-  auto pass_bytes = [&](int64_t mb) -> size_t { return pa_bytes(mb) + (size_t)rup((int64_t)N * rup(mb, OZ_BM) * Np, 1024); };
-  int want_passes = m >= 4096 ? 4 : (m >= 2048 ? 2 : 1);
-  if (cb && min_passes > want_passes) want_passes = min_passes;
-  int64_t mb = std::max<int64_t>(OZ_BM, rup((m + want_passes - 1) / want_passes, OZ_BM));
-  auto bufs = [&](int64_t mb_) -> int { return mb_ < m ? 2 : 1; };
-  while (mb > OZ_BM && pb_b + bufs(mb) * pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
-  if (pb_b + bufs(mb) * pass_bytes(mb) > ws_budget) return cudaSuccess;
-  const int nb = bufs(mb);
-  e = oz_reserve(meta_ints * 4, pb_b + nb * pass_bytes(mb));
-  if (e != cudaSuccess) return e;
-  int *meta = (int *)g_oz.meta;
-  const int *emaxA = meta, *emaxB = meta + 2 * m;
-  int8_t *pB = (int8_t *)g_oz.buf;
-  int8_t *pA[2]; uint8_t *R[2];
-  for (int b = 0; b < 2; ++b) {
-    pA[b] = pB + pb_b + (size_t)(b % nb) * pass_bytes(mb);
-    R[b] = (uint8_t *)(pA[b] + pa_bytes(mb));
+  /* ---- units: row passes of `ur` rows x column panels of `uc` columns ----
+   * Loop order 0 (default): panels outer, passes inner — the residue planes of the A rows stay resident, the B panels are double
+   * buffered (what a device-resident or a panel-streamed B wants).  Order 1: passes outer — the B planes stay resident and the A
+   * passes are double buffered, so the rows of C complete pass by pass (what the all-host path wants: rows stream in and out). */
+  int64_t ur = std::min(rup(m, OZ_BM), g_unit_rows), uc = std::min(rup(n, OZ_BN), h.bp ? rup(h.bp_cols, OZ_BN) : g_unit_cols);
+  if (h.cb && h.min_passes > 1) ur = std::min(ur, std::max<int64_t>(OZ_BM, rup((m + h.min_passes - 1) / h.min_passes, OZ_BM)));
+  auto planes_bytes = [&](int64_t rows) -> size_t { return (size_t)rup((int64_t)N * rows * Kp, 1024); };
+  auto rest_bytes = [&](int64_t ur_, int64_t uc_) -> size_t {   /* 2 residue buffers, flags + list */
+    size_t b = 2 * (size_t)rup((int64_t)N * rup(ur_, OZ_BM) * rup(uc_, OZ_BN), 1024);
+    if (check) b += (size_t)rup(rup(ur_, OZ_BM) * rup(uc_, OZ_BN), 1024) + (size_t)std::max<int64_t>(4096, ur_ * uc_ / 64) * sizeof(int2);
+    return b;
+  };
+  auto need_bytes = [&](int64_t ur_, int64_t uc_, int64_t nA_, int64_t nB_) -> size_t { return nA_ * planes_bytes(ur_) + nB_ * planes_bytes(uc_) + rest_bytes(ur_, uc_); };
+  auto npass_of = [&](int64_t ur_) { return (m + ur_ - 1) / ur_; };
+  auto npanel_of = [&](int64_t uc_) { return (n + uc_ - 1) / uc_; };
+  auto min_need = [&](int64_t ur_, int64_t uc_) { return need_bytes(ur_, uc_, std::min<int64_t>(npass_of(ur_), 2), std::min<int64_t>(npanel_of(uc_), 2)); };
+  while (min_need(ur, uc) > ws_budget && !h.bp && uc > OZ_BN) uc = rup(uc / 2, OZ_BN);
+  while (min_need(ur, uc) > ws_budget && ur > OZ_BM) ur = rup(ur / 2, OZ_BM);
+  if (min_need(ur, uc) > ws_budget) return cudaSuccess;
+  const int64_t nP = npass_of(ur), nJ = npanel_of(uc);
+  const int order = h.order == 1 ? 1 : 0;
+  int64_t nA = std::min<int64_t>(nP, 2), nB = std::min<int64_t>(nJ, 2);
+  if (order == 0) { while (nA < nP && need_bytes(ur, uc, nA + 1, nB) <= ws_budget) ++nA; }
+  else { while (nB < nJ && need_bytes(ur, uc, nA, nB + 1) <= ws_budget) ++nB; }
+  if (h.bp && nA < nP) return cudaSuccess;                   /* a streamed B passes once */
+  const int64_t Mu = rup(ur, OZ_BM), Nu = rup(uc, OZ_BN);
+  const size_t pa_bytes = planes_bytes(ur), pb_bytes = planes_bytes(uc), r_bytes = (size_t)rup((int64_t)N * Mu * Nu, 1024);
+  const int list_cap = (int)std::max<int64_t>(4096, ur * uc / 64);
+  const size_t flag_bytes = check ? (size_t)rup(Mu * Nu, 1024) : 0, list_bytes = check ? (size_t)list_cap * sizeof(int2) : 0;
+  QB_TRY(oz_grow(&D.buf, &D.bytes, nA * pa_bytes + nB * pb_bytes + 2 * r_bytes + flag_bytes + list_bytes));
+  int8_t *pA0 = (int8_t *)D.buf, *pB0 = pA0 + nA * pa_bytes;
+  uint8_t *R[2] = {(uint8_t *)(pB0 + nB * pb_bytes), (uint8_t *)(pB0 + nB * pb_bytes + r_bytes)};
+  uint8_t *flagp = R[1] + r_bytes;
+  int2 *list = (int2 *)(flagp + flag_bytes);
+  /* K chunks of the int32 accumulation */
+  const int64_t nkb_total = Kp / OZ_BK;
+  const int nkc = (int)((Kp + OZ_KCHUNK - 1) / OZ_KCHUNK);
+  const int64_t kcb = (nkb_total + nkc - 1) / nkc;
+  const int simple = (a.alpha.hi == 0x3fff000000000000ULL && a.alpha.lo == 0 && (a.beta.hi & 0x7fffffffffffffffULL) == 0 && a.beta.lo == 0) ? 1 : 0;
+  /* ---- the pipeline: tensor kernel of unit u (sM) || residues for the coming units (sA, sB) || reconstruction of unit u-1 (sF) ---- */
+  cudaEvent_t evMma[2], evFold[2];
+  for (int b = 0; b < 2; ++b) { QB_TRY(oz_event(D, EV_MMA0 + b, &evMma[b])); QB_TRY(oz_event(D, EV_FOLD0 + b, &evFold[b])); }
+  struct Slot { int64_t who = -1; cudaEvent_t ready = nullptr, read = nullptr; bool read_rec = false; const q128 *panel = nullptr; int64_t ld = 0; };
+  std::vector<Slot> slotA((size_t)nA), slotB((size_t)nB);
+  for (int64_t i = 0; i < nA + nB; ++i) {
+    Slot &sl = i < nA ? slotA[(size_t)i] : slotB[(size_t)(i - nA)];
+    QB_TRY(oz_event(D, EV_SLOT0 + 2 * (int)i, &sl.ready)); QB_TRY(oz_event(D, EV_SLOT0 + 2 * (int)i + 1, &sl.read));
   }
-  CrtStreams &cs = g_cs;
-#define QB_CRT_TRY(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
-  QB_CRT_TRY(cudaEventRecord(cs.in, st));
-  QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sA, cs.in, 0)); QB_CRT_TRY(cudaStreamWaitEvent(cs.sF, cs.in, 0));
-  launch_crt_residues(a.B, n, k, a.sbj, a.sbl, emaxB, WB, N, Kp, pB, cs.sM);
-  const std::vector<int64_t> pass_rows = oz_crt_pass_rows(m, mb, (cb || mb >= m) ? 0 : g_oz_pass_shape);
-  int pass = 0;
-  int64_t r0 = 0;
-  for (; pass < (int)pass_rows.size(); r0 += pass_rows[pass], ++pass) {
-    const int64_t mr = pass_rows[pass];
-    const int64_t Mp = rup(mr, OZ_BM);
-    const int b = pass & 1;
-    /* residues of this pass's A rows: its buffer was last read by the tensor kernel of pass - 2 */
-    if (pass >= 2) QB_CRT_TRY(cudaStreamWaitEvent(cs.sA, cs.mma[b], 0));
-    launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pA[b], cs.sA);
-    QB_CRT_TRY(cudaEventRecord(cs.resA[b], cs.sA));
-    /* tensor kernel: needs the residues, and R[b] drained by the reconstruction of pass - 2 */
-    QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.resA[b], 0));
-    if (pass >= 2) QB_CRT_TRY(cudaStreamWaitEvent(cs.sM, cs.fold[b], 0));
-    oz_ev_record(0, cs.sM);
-    e = launch_crt_mma(pA[b], pB, N, mr, n, Kp, R[b], Mp, Np, cs.sM);
-    oz_ev_record(1, cs.sM);
-    if (e != cudaSuccess) return e;
-    QB_CRT_TRY(cudaEventRecord(cs.mma[b], cs.sM));
-    /* reconstruction + epilogue */
-    QB_CRT_TRY(cudaStreamWaitEvent(cs.sF, cs.mma[b], 0));
+  std::vector<int> rows_in_done((size_t)nP, 0), panels_left((size_t)nP, (int)nJ);
+  int64_t unit = 0;
+  int passes_done = 0;
+  auto run_unit = [&](int64_t p, int64_t j) -> cudaError_t {
+    const int64_t r0 = p * ur, mr = std::min(ur, m - r0), c0 = j * uc, w = std::min(uc, n - c0);
+    const int64_t Mp = rup(mr, OZ_BM), Np = rup(w, OZ_BN);
+    Slot &sa = slotA[(size_t)(p % nA)], &sb = slotB[(size_t)(j % nB)];
+    int8_t *pAp = pA0 + (size_t)(p % nA) * pa_bytes, *pBj = pB0 + (size_t)(j % nB) * pb_bytes;
+    if (h.rows_in && !rows_in_done[(size_t)p]) {   /* streamed rows: the caller orders the arrival of A's rows on sA, of C's on sF */
+      if (h.rows_in(r0, mr, (void *)D.sA, (void *)D.sF, h.rows_user) != 0) return cudaErrorInvalidValue;
+      rows_in_done[(size_t)p] = 1;
+    }
+    if (sa.who != p) {   /* residues of this pass's A rows; the slot was last read by the tensor kernel that recorded sa.read */
+      if (sa.read_rec) QB_TRY(cudaStreamWaitEvent(D.sA, sa.read, 0));
+      if (h.rows_in && rows_in_done[(size_t)p] == 1) { launch_scan(a.A + r0 * a.sai, mr, k, a.sai, a.sal, statA + r0, statA + m + r0, statA + 2 * m + r0, D.sA); rows_in_done[(size_t)p] = 2; }
+      launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pAp, D.sA);
+      QB_TRY(cudaEventRecord(sa.ready, D.sA));
+      QB_TRY(cudaStreamWaitEvent(D.sM, sa.ready, 0));
+      sa.who = p;
+    }
+    const q128 *Bp = a.B + c0 * a.sbj;
+    int64_t sbl = a.sbl, sbj = a.sbj;
+    if (sb.who != j) {
+      if (sb.read_rec) QB_TRY(cudaStreamWaitEvent(D.sB, sb.read, 0));
+      if (h.bp) {   /* streamed B: the caller hands over the panel and orders its arrival on sB */
+        const void *ptr = nullptr; int64_t ldp = 0;
+        if (h.bp(c0, w, (void *)D.sB, &ptr, &ldp, h.bp_user) != 0 || !ptr) return cudaErrorInvalidValue;
+        sb.panel = (const q128 *)ptr; sb.ld = ldp;
+      }
+      if (h.bp) { Bp = sb.panel; if (a.sbj == 1) sbl = sb.ld; else sbj = sb.ld; }
+      launch_crt_residues(Bp, w, k, sbj, sbl, emaxB + c0, WB, N, Kp, pBj, D.sB);
+      QB_TRY(cudaEventRecord(sb.ready, D.sB));
+      QB_TRY(cudaStreamWaitEvent(D.sM, sb.ready, 0));
+      sb.who = j;
+    } else if (h.bp) { Bp = sb.panel; if (a.sbj == 1) sbl = sb.ld; else sbj = sb.ld; }
+    const int rb = (int)(unit & 1);
+    if (unit >= 2) QB_TRY(cudaStreamWaitEvent(D.sM, evFold[rb], 0));   /* R[rb] drained by the reconstruction of unit - 2 */
+    for (int c = 0; c < nkc; ++c) {
+      const int kb0 = (int)(c * kcb), nkb = (int)std::min<int64_t>(kcb, nkb_total - kb0);
+      oz_ev_record(D, 0, D.sM);
+      const cudaError_t e2 = launch_crt_mma(D, pAp, pBj, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, D.sM);
+      oz_ev_record(D, 1, D.sM);
+      if (e2 != cudaSuccess) return e2;
+    }
+    QB_TRY(cudaEventRecord(evMma[rb], D.sM));
+    if (nA < nP) { QB_TRY(cudaEventRecord(sa.read, D.sM)); sa.read_rec = true; }
+    if (nB < nJ) { QB_TRY(cudaEventRecord(sb.read, D.sM)); sb.read_rec = true; }
+    /* reconstruction + epilogue (+ fix-up of the elements it rejects) */
+    QB_TRY(cudaStreamWaitEvent(D.sF, evMma[rb], 0));
     CrtFoldArgs f;
-    f.R = R[b]; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = n; f.row0 = r0;
-    f.emaxA = emaxA; f.emaxB = emaxB; f.WA = WA; f.WB = WB;
-    f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
-    f.simple = (a.alpha.hi == 0x3fff000000000000ULL && a.alpha.lo == 0 && (a.beta.hi & 0x7fffffffffffffffULL) == 0 && a.beta.lo == 0) ? 1 : 0;
-    f.n4p = rup((n + 3) / 4, 32);
+    f.R = R[rb]; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = w; f.row0 = r0; f.col0 = c0;
+    f.emaxA = emaxA; f.lminA = lminA; f.spA = spA; f.emaxB = emaxB; f.lminB = lminB; f.spB = spB; f.WA = WA; f.WB = WB; f.k = k;
+    f.alpha = a.alpha; f.beta = a.beta; f.C = a.C; f.sci = a.sci; f.scj = a.scj;
+    f.simple = simple;
+    f.n4p = rup((w + 3) / 4, 32);
+    f.check = check; f.list = list; f.list_cap = list_cap; f.counter = counter; f.flag = flagp;
     f.npeer = a.npeer;
-    for (int q = 0; q < QB_MAX_PEERS; ++q) f.peer[q] = q < a.npeer ? a.peerC[q] + r0 * a.sci : nullptr;
-    launch_crt_fold(f, pl, cs.sF);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    QB_CRT_TRY(cudaEventRecord(cs.fold[b], cs.sF));
-    e = cudaStreamWaitEvent(st, cs.fold[b], 0);   /* the caller's stream sees the rows of this pass */
-    if (e != cudaSuccess) return e;
-    if (cb) cb(r0, mr, cb_user);
+    for (int q = 0; q < QB_MAX_PEERS; ++q) f.peer[q] = q < a.npeer ? a.peerC[q] : nullptr;
+    if (check) { QB_TRY(cudaMemsetAsync(counter, 0, 4, D.sF)); QB_TRY(cudaMemsetAsync(flagp, 0, (size_t)(Mp * Np), D.sF)); }
+    launch_crt_fold(f, pl, D.sF);
+    QB_TRY(cudaGetLastError());
+    if (check) {
+      CrtFixArgs x;
+      x.list = list; x.counter = counter; x.list_cap = list_cap; x.flag = flagp;
+      x.um = mr; x.un = w; x.uNp = Np; x.row0 = r0; x.col0 = c0;
+      x.A = a.A; x.sai = a.sai; x.sal = a.sal; x.k = k;
+      x.B = Bp - c0 * sbj; x.sbl = sbl; x.sbj = sbj;   /* column gj of op(B) lives at Bp + (gj - c0) * sbj (the panel as handed over, or B itself) */
+      x.alpha = a.alpha; x.beta = a.beta; x.C = a.C; x.sci = a.sci; x.scj = a.scj; x.total = total;
+      x.npeer = a.npeer;
+      for (int q = 0; q < QB_MAX_PEERS; ++q) x.peer[q] = q < a.npeer ? a.peerC[q] : nullptr;
+      k_crt_fixup<<<D.sm_count * 4, 128, 0, D.sF>>>(x);
+      count_launch();
+      QB_TRY(cudaGetLastError());
+    }
+    QB_TRY(cudaEventRecord(evFold[rb], D.sF));
+    if (--panels_left[(size_t)p] == 0) {   /* the rows of this pass are complete */
+      ++passes_done;
+      if (h.cb) { QB_TRY(cudaStreamWaitEvent(st, evFold[rb], 0)); h.cb(r0, mr, h.cb_user); }
+    }
+    ++unit;
+    return cudaSuccess;
+  };
+  if (order == 0) {
+    for (int64_t pb = 0; pb < nP; pb += nA)                 /* blocks of resident A passes (one block unless the workspace is short) */
+      for (int64_t j = 0; j < nJ; ++j)
+        for (int64_t p = pb; p < std::min(nP, pb + nA); ++p) QB_TRY(run_unit(p, j));
+  } else {
+    for (int64_t jb = 0; jb < nJ; jb += nB)
+      for (int64_t p = 0; p < nP; ++p)
+        for (int64_t j = jb; j < std::min(nJ, jb + nB); ++j) QB_TRY(run_unit(p, j));
   }
-  g_last_stats.SA = (WA + 7) / 8; g_last_stats.SB = (WB + 7) / 8; g_last_stats.ndiag = N; g_last_stats.nchunks = 1;
-  g_last_stats.row_passes = pass;
+  if (check) { QB_TRY(cudaMemcpyAsync(D.h_plan + 8, total, 4, cudaMemcpyDeviceToHost, D.sF)); D.stats_pending = true; }
+  QB_TRY(cudaEventRecord(evDone, D.sF));
+  QB_TRY(cudaStreamWaitEvent(st, evDone, 0));   /* sF is the last stage of every unit: the caller's stream sees all of C */
+  g_last_stats.SA = (WA + 7) / 8; g_last_stats.SB = (WB + 7) / 8; g_last_stats.ndiag = N; g_last_stats.nchunks = nkc;
+  g_last_stats.row_passes = passes_done; g_last_stats.panels = (int)nJ; g_last_stats.units = unit;
   g_last_stats.pairs = N; g_last_stats.keep = 0; g_last_stats.flagged = 0; g_last_stats.redo_passes = 0;
-  g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
-  g_last_stats.scheme = 1; g_last_stats.WA = WA; g_last_stats.WB = WB;
+  g_last_stats.ws_bytes = (int64_t)D.bytes; g_last_stats.Kp = Kp;
+  g_last_stats.scheme = 1; g_last_stats.WA = WA; g_last_stats.WB = WB; g_last_stats.WA_nat = WA_nat; g_last_stats.WB_nat = WB_nat;
+  g_last_stats.truncated = (win.truncA ? 1 : 0) | (win.truncB ? 2 : 0) | (fl ? 4 : 0);
   g_last_stats.peer_written = a.npeer;
   *used = 1;
   return cudaSuccess;
-#undef QB_CRT_TRY
-}
-
-/* The whole fast-mode GEMM.  *used = 0 means the planner declined (caller runs the integer kernel). */
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, oz_pass_cb cb, void *cb_user, int min_passes)
-{
-  *used = 0;
-  g_ev_used = 0;
-  { const int64_t keep = g_last_stats.ws_bytes; g_last_stats = OzStats(); g_last_stats.ws_bytes = keep; }
-  if (!get_encode()) return cudaSuccess;
-  const int64_t m = a.m, n = a.n, k = a.k;
-  const int64_t Kp = rup(k, OZ_BK);
-  /* ---- scan + plan ---- */
-  const size_t meta_ints = (size_t)(2 * m + 2 * n + 16);
-  cudaError_t e = oz_reserve(meta_ints * 4, 0);
-  if (e != cudaSuccess) return e;
-  int *meta = (int *)g_oz.meta;
-  int *emaxA = meta, *lminA = meta + m, *emaxB = meta + 2 * m, *lminB = meta + 2 * m + n, *flags = meta + 2 * m + 2 * n, *plan = flags + 4;
-  {
-    cudaMemsetAsync(emaxA, 0, (size_t)m * 4, st); cudaMemsetAsync(lminA, 0x7f, (size_t)m * 4, st);
-    cudaMemsetAsync(emaxB, 0, (size_t)n * 4, st); cudaMemsetAsync(lminB, 0x7f, (size_t)n * 4, st);
-    cudaMemsetAsync(flags, 0, 64, st);
-    const int64_t nch = (k + OZ_SCAN_CH - 1) / OZ_SCAN_CH;
-    {
-      const bool warp_mode = (a.sal == 1 || a.sai != 1);
-      const int64_t threads = warp_mode ? m * nch * 32 : m * nch;
-      k_oz_scan<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.A, m, k, a.sai, a.sal, emaxA, lminA, flags);
-    }
-    {
-      const bool warp_mode = (a.sbl == 1 || a.sbj != 1);
-      const int64_t threads = warp_mode ? n * nch * 32 : n * nch;
-      k_oz_scan<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(a.B, n, k, a.sbj, a.sbl, emaxB, lminB, flags);
-    }
-    k_oz_plan<<<1, 1024, 0, st>>>(emaxA, lminA, m, emaxB, lminB, n, flags, plan);
-    count_launch(3);
-    e = cudaMemcpyAsync(g_oz.h_plan, plan, 16, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-  }
-  const int WA = g_oz.h_plan[0], WB = g_oz.h_plan[1], fl = g_oz.h_plan[2];
-  if (g_oz_scheme == 1 && fl == 0) { /* residue scheme: one int8 GEMM per modulus; declines (-> digit diagonals) when the moduli cannot cover the span */
-    e = launch_gemm_crt(a, st, used, ws_budget, cb, cb_user, min_passes, WA, WB, meta_ints);
-    if (e != cudaSuccess || *used) return e;
-  }
-  const int SA = std::max(1, (WA + 2 + 7) / 8), SB = std::max(1, (WB + 2 + 7) / 8);
-  if (fl != 0 || SA > OZ_MAX_S || SB > OZ_MAX_S) return cudaSuccess; /* decline: Inf/NaN or span too wide */
-  const int ndiag = SA + SB - 1;
-  /* bounded setting: multiply only the leading diagonals (needs k >= 2 for the error budget, header comment) */
-  const int keep = (g_oz_keep > 0 && g_oz_keep < ndiag && k >= 2) ? g_oz_keep : ndiag;
-  const bool bounded = keep < ndiag;
-  /* int32 exactness: Kc * min(SA, SB) * 2^14 <= 2^31 - 1 */
-  int64_t kc_blocks = ((((int64_t)1 << 17) - 1) / std::min(SA, SB)) / OZ_BK;
-  if (kc_blocks < 1) return cudaSuccess;
-  const int64_t nkb_total = Kp / OZ_BK;
-  const int nchunks = (int)((nkb_total + kc_blocks - 1) / kc_blocks);
-  kc_blocks = (nkb_total + nchunks - 1) / nchunks;   /* equal chunks: a short last chunk runs the tensor kernel at a worse duty cycle */
-  /* ---- workspace: planes B | planes A (per row pass) | D | W ---- */
-  const int64_t Np = rup(n, OZ_BN);
-  const size_t pb_b = rup((int64_t)SB * n * Kp, 1024);
-  /* K chunks: either every chunk keeps its own int32 diagonal set and ONE fold sums them (`sets` = nchunks, no wide
-   * workspace, least traffic), or - when that does not fit next to the full-diagonal redo buffer - one set is
-   * folded after every chunk into the 448-bit running sums W */
-  const int nd_main = keep;                      /* diagonals of the main sweep (== ndiag in the exact setting) */
-  auto d_planes = [&](bool multi) -> int64_t { return multi ? std::max<int64_t>((int64_t)nchunks * nd_main, ndiag) : ndiag; };
-  auto pass_bytes_v = [&](int64_t mb, bool multi) -> size_t {
-    const int64_t Mp = rup(mb, OZ_BM);
-    size_t b = rup((int64_t)SA * mb * Kp, 1024) + (size_t)d_planes(multi) * Mp * Np * 4;
-    if (nchunks > 1) b += (size_t)OZ_NL * Mp * Np * 4;      /* W: always reserved (the redo sweep folds per chunk) */
-    if (bounded) b += (size_t)rup(Mp * Np, 1024) + (size_t)oz_list_cap(mb, n) * sizeof(int2);
-    return b;
-  };
-  const int64_t mb_hint = (cb && min_passes > 1) ? std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM)) : m;
-  const bool multi = nchunks > 1 && pb_b + pass_bytes_v(mb_hint, true) <= ws_budget;
-  auto pass_bytes = [&](int64_t mb) -> size_t { return pass_bytes_v(mb, multi); };
-  int64_t mb = m;
-  if (cb && min_passes > 1) mb = std::max<int64_t>(OZ_BM, rup((m + min_passes - 1) / min_passes, OZ_BM));
-  while (mb > OZ_BM && pb_b + pass_bytes(mb) > ws_budget) mb = rup((mb + 1) / 2, OZ_BM);
-  if (pb_b + pass_bytes(mb) > ws_budget) return cudaSuccess; /* does not fit: decline */
-  e = oz_reserve(meta_ints * 4, pb_b + pass_bytes(mb));
-  if (e != cudaSuccess) return e;
-  int8_t *pB = (int8_t *)g_oz.buf;
-  int8_t *pA = pB + pb_b;
-  /* ---- slice B once ---- */
-  launch_oz_slice(a.B, n, k, a.sbj, a.sbl, emaxB, SB, Kp, pB, st);
-  int64_t flagged_total = 0, pairs_done = 0;
-  int redo_passes = 0;
-  auto npairs = [&](int nd) { int64_t p = 0; for (int d = 0; d < nd; ++d) p += std::min(d, SA - 1) - std::max(0, d - (SB - 1)) + 1; return p; };
-  int *counter = flags + 8;   /* meta: one int, zeroed per row pass */
-  for (int64_t r0 = 0; r0 < m; r0 += mb) {
-    const int64_t mr = std::min(mb, m - r0);
-    const int64_t Mp = rup(mr, OZ_BM);
-    int32_t *D = (int32_t *)(pA + rup((int64_t)SA * mb * Kp, 1024));
-    uint32_t *W = (uint32_t *)(D + (size_t)d_planes(multi) * rup(mb, OZ_BM) * Np);
-    uint8_t *flagp = (uint8_t *)(W + (nchunks > 1 ? (size_t)OZ_NL * rup(mb, OZ_BM) * Np : 0));
-    int2 *list = (int2 *)(flagp + rup(rup(mb, OZ_BM) * Np, 1024));
-    const int list_cap = (int)oz_list_cap(mb, n);
-    launch_oz_slice(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, SA, Kp, pA, st);
-    /* one sweep over the K chunks with `nd` leading diagonals; `redo` = exact redo of the flagged elements */
-    auto sweep = [&](int nd, bool check, bool redo) -> cudaError_t {
-      const bool sets = multi && !redo;          /* every chunk into its own diagonal set, one fold at the end */
-      const int64_t set_stride = (int64_t)nd * Mp * Np;
-      for (int c = 0; c < nchunks; ++c) {
-        const int kb0 = (int)(c * kc_blocks), nkb = (int)std::min<int64_t>(kc_blocks, nkb_total - kb0);
-        oz_ev_record(0, st);
-        cudaError_t e2 = launch_oz_mma(pA, pB, SA, SB, mr, n, Kp, kb0, nkb, D + (sets ? c * set_stride : 0), Mp, Np, st, nd);
-        oz_ev_record(1, st);
-        if (e2 != cudaSuccess) return e2;
-        if (sets && c + 1 < nchunks) continue;
-        OzFoldArgs f;
-        f.D = D; f.Mp = Mp; f.Np = Np; f.ndiag = nd; f.m = mr; f.n = n; f.row0 = r0;
-        f.nsets = sets ? nchunks : 1; f.set_stride = set_stride;
-        f.emaxA = emaxA; f.emaxB = emaxB; f.SA = SA; f.SB = SB;
-        f.W = W; f.w_in = !sets && c > 0; f.w_out = !sets && c + 1 < nchunks;
-        f.alpha = a.alpha; f.beta = a.beta; f.C = a.C + r0 * a.sci; f.sci = a.sci; f.scj = a.scj;
-        f.exp8 = ndiag - nd; f.check = check ? 1 : 0; f.only_flagged = redo ? 1 : 0;
-        f.flag = flagp; f.list = list; f.list_cap = list_cap; f.counter = counter;
-        const int64_t elems = mr * n;
-        const unsigned fg = (unsigned)((elems + 255) / 256);
-        switch (f.nsets) {
-        case 1: k_oz_fold<1><<<fg, 256, 0, st>>>(f); break;
-        case 2: k_oz_fold<2><<<fg, 256, 0, st>>>(f); break;
-        case 3: k_oz_fold<3><<<fg, 256, 0, st>>>(f); break;
-        case 4: k_oz_fold<4><<<fg, 256, 0, st>>>(f); break;
-        case 5: k_oz_fold<5><<<fg, 256, 0, st>>>(f); break;
-        default: k_oz_fold<0><<<fg, 256, 0, st>>>(f); break;
-        }
-        count_launch();
-        e2 = cudaGetLastError();
-        if (e2 != cudaSuccess) return e2;
-      }
-      pairs_done += npairs(nd);
-      return cudaSuccess;
-    };
-    if (!bounded) {
-      e = sweep(ndiag, false, false);
-      if (e != cudaSuccess) return e;
-      if (cb) cb(r0, mr, cb_user);
-      continue;
-    }
-    cudaMemsetAsync(counter, 0, 4, st);
-    e = sweep(keep, true, false);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(g_oz.h_plan + 8, counter, 4, cudaMemcpyDeviceToHost, st);
-    if (e != cudaSuccess) return e;
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    const int nflag = g_oz.h_plan[8];
-    flagged_total += nflag;
-    if (nflag == 0) { if (cb) cb(r0, mr, cb_user); continue; }
-    if (nflag <= list_cap) {
-      OzFixArgs x;
-      x.list = list; x.counter = counter; x.list_cap = list_cap;
-      x.A = a.A; x.sai = a.sai; x.sal = a.sal; x.B = a.B; x.sbl = a.sbl; x.sbj = a.sbj; x.k = k;
-      x.alpha = a.alpha; x.beta = a.beta; x.C = a.C; x.sci = a.sci; x.scj = a.scj;
-      const int blocks = (int)std::min<int64_t>((nflag + 3) / 4, (int64_t)sm_count() * 8);
-      k_oz_fixup<<<blocks, 128, 0, st>>>(x);
-      count_launch();
-      e = cudaGetLastError();
-      if (e != cudaSuccess) return e;
-    } else { /* structured cancellation: all diagonals, written for the flagged elements only */
-      ++redo_passes;
-      e = sweep(ndiag, false, true);
-      if (e != cudaSuccess) return e;
-    }
-    if (cb) cb(r0, mr, cb_user);
-  }
-  g_last_stats.SA = SA; g_last_stats.SB = SB; g_last_stats.ndiag = ndiag; g_last_stats.nchunks = nchunks;
-  g_last_stats.row_passes = (int)((m + mb - 1) / mb);
-  g_last_stats.pairs = pairs_done / g_last_stats.row_passes;   /* digit-plane products per row pass (bounded + any redo) */
-  g_last_stats.keep = keep; g_last_stats.flagged = flagged_total; g_last_stats.redo_passes = redo_passes;
-  g_last_stats.ws_bytes = (int64_t)g_oz.bytes; g_last_stats.Kp = Kp;
-  *used = 1;
-  return cudaSuccess;
+#undef QB_TRY
 }
 
 } // namespace qb

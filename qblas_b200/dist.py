@@ -106,6 +106,45 @@ class PeerBuffer:
         self._release([p for q, p in enumerate(self.ptrs) if q != self.rank])
 
 
+class SymmetricBuffer:
+    """Same role as PeerBuffer, on torch's symmetric memory (torch.distributed._symmetric_memory: the allocation, the handle exchange
+    and the NVSwitch multicast mapping are torch plumbing).  `ptrs[q]` = rank q's buffer as seen from this process, and `mc_ptr` = ONE
+    address that the NVSwitch replicates to every rank's buffer (0 when the fabric has no multicast): a kernel that stores a finished
+    C element there once reaches all the copies, so the egress of the fused gather is 1x the block instead of (world - 1)x.
+    Raises RuntimeError where symmetric memory is unavailable (gloo groups, old drivers): callers fall back to PeerBuffer / NCCL."""
+
+    def __init__(self, nbytes, group=None):
+        if dist.get_backend(group) != "nccl":
+            raise RuntimeError("symmetric memory needs CUDA devices (nccl group)")
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.group = group if group is not None else dist.group.WORLD
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self.nbytes = int(nbytes)
+            self.tensor = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+            self.handle = symm_mem.rendezvous(self.tensor, self.group)
+            self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+            self.mc_ptr = int(self.handle.multicast_ptr or 0)
+            self.local_ptr = self.ptrs[self.rank]
+        except Exception as e:
+            raise RuntimeError(f"symmetric memory unavailable: {e!r}")
+
+    def close(self):
+        if self.tensor is not None:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)
+        self.tensor = None
+        self.handle = None
+
+
+def fused_outputs(buf, rank, byte_offset, multicast=True):
+    """Addresses for qb_set_gemm_peer_outputs: the multicast address when the buffer has one (one store reaches every rank), else the
+    other ranks' mapped buffers."""
+    if multicast and getattr(buf, "mc_ptr", 0):
+        return [buf.mc_ptr + byte_offset]
+    return [buf.ptrs[q] + byte_offset for q in range(len(buf.ptrs)) if q != rank]
+
+
 class _CudaEngine:
     """Default per-rank engine: libqblas_b200.so on the current CUDA device."""
 
@@ -121,6 +160,24 @@ class _CudaEngine:
             api.gemm("R", m, n, k, alpha, A, lda, B, ldb, beta, C, ldc)
         finally:
             api.set_gemm_pass_callback(None)
+
+    def gemm_streamed(self, m, n, k, alpha, A, lda, panel_fn, panel_cols, colstats, beta, C, ldc):
+        """qgemm whose B arrives in column panels: panel_fn(col0, cols, stream_ptr) -> (ptr, ld) (qb_set_gemm_b_panels)."""
+        from . import api
+        api.set_gemm_b_panels(panel_fn, panel_cols, colstats)
+        try:
+            api.gemm("R", m, n, k, alpha, A, lda, A, n, beta, C, ldc)      # the B argument is not dereferenced
+        finally:
+            api.set_gemm_b_panels(None)
+
+    def colstats(self, k, n, B, ldb, out):
+        from . import api
+        return api.gemm_colstats("R", k, n, B, ldb, out)
+
+    def wait_on_stream(self, work, stream_ptr):
+        """make the library's CUDA stream wait for an async collective"""
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream_ptr)):
+            work.wait()
 
     def set_peer_outputs(self, ptrs):
         """fused gather: addresses of the C block inside the peers' buffers for the following gemm calls (None: off)"""
@@ -159,7 +216,8 @@ def _gather_blocks(m, n, world, C_full, C_blk, group):
                 dist.broadcast(_bytes(C_full[l2 * n:h2 * n]), src=r, group=group)
 
 
-def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1, peers=None):
+def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1, peers=None, b_panels=0,
+                      b_packed=None):
     """C_full (m x n, row-major, identical buffer shape on every rank) <- alpha*A*B + beta*C.
     A_blk holds this rank's rows [lo, hi) of A (row-major, lda = k); B (k x n) is valid on `src`
     and is overwritten by the broadcast elsewhere.  Returns (lo, hi).
@@ -168,46 +226,89 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
     pass's rows is issued from the library's row-pass hook as soon as that pass is enqueued, so it runs on NCCL's stream
     while the next pass computes; only the last pass's gather is exposed.  Same bytes, same result.
 
-    peers = a PeerBuffer whose local tensor IS C_full's storage (fused gather): the kernel that finishes the C elements stores
-    them into every peer's C_full over NVLink as well, no all-gather is issued, and a barrier makes the step complete.  If the
-    library ran a path without the fused stores (it reports 0 peers written) the NCCL all-gather is issued after all."""
+    peers = a PeerBuffer / SymmetricBuffer whose local tensor IS C_full's storage (fused gather): the kernel that finishes the C elements
+    stores them into every rank's C_full over NVLink as well (through the NVSwitch multicast address when the buffer has one), no
+    all-gather is issued, and a barrier makes the step complete.  If the library ran a path without the fused stores (it reports 0
+    outputs written) the NCCL all-gather is issued after all.
+
+    b_panels = w > 0 (fast mode, every rank owns >= 1 row): B is not broadcast before the product but DURING it, in column panels of w
+    columns (a multiple of 256): the owner computes the column statistics of B (12 n bytes, broadcast first), packs panel j into a
+    contiguous k x w buffer and broadcasts it while the ranks multiply panel j-1 (qb_set_gemm_b_panels).  b_packed: optional
+    preallocated (k * n, 2) buffer for the packed panels (panel j occupies rows [j*k*w, ...)); B itself is only read on `src`."""
     compute = compute or _CudaEngine()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = row_block(m, world, rank)
-    dist.broadcast(_bytes(B), src=src, group=group)
     C_blk = C_full[lo * n:hi * n]
+    streamed = b_panels > 0 and world > 1 and m >= world
+    panel_fn = stats = None
+    if streamed:
+        w = int(b_panels)
+        dev, dt = C_full.device, B.dtype
+        stats = torch.zeros(3 * n, dtype=torch.int32, device=dev)
+        if rank == src:
+            compute.colstats(k, n, B, n, stats)
+        dist.broadcast(stats, src=src, group=group)
+        packed = b_packed if b_packed is not None else torch.empty((k * n, 2), dtype=dt, device=dev)
+        B3 = B.reshape(k, n, 2) if rank == src else None
+        works, views = [], []
+        for c0 in range(0, n, w):
+            cols = min(w, n - c0)
+            pv = packed[c0 * k:(c0 + cols) * k]                      # panel j: k x cols, contiguous, ld = cols
+            if rank == src:
+                pv.reshape(k, cols, 2).copy_(B3[:, c0:c0 + cols])
+            works.append(dist.broadcast(_bytes(pv), src=src, group=group, async_op=True))
+            views.append(pv)
+
+        def panel_fn(col0, cols, stream_ptr):
+            j = col0 // w
+            compute.wait_on_stream(works[j], stream_ptr)
+            return views[j].data_ptr(), cols
+    else:
+        dist.broadcast(_bytes(B), src=src, group=group)
+
+    def run_gemm(rows, A_, C_, **kw):
+        if streamed:
+            compute.gemm_streamed(rows, n, k, alpha, A_, k, panel_fn, int(b_panels), stats, beta, C_, n)
+        else:
+            compute.gemm(rows, n, k, alpha, A_, k, B, n, beta, C_, n, **kw)
+
     if peers is not None and world > 1:
-        wrote = world - 1                                            # a rank without rows has nothing to deliver
+        expect = -1                                                  # a rank without rows has nothing to deliver
+        wrote = -1
         if hi > lo:
-            others = [peers.ptrs[q] + lo * n * 16 for q in range(world) if q != rank]
-            compute.set_peer_outputs(others)
+            outs = fused_outputs(peers, rank, lo * n * 16)
+            expect = len(outs)
+            compute.set_peer_outputs(outs)
             try:
-                compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
+                run_gemm(hi - lo, A_blk, C_blk)
                 wrote = compute.peer_written()
             finally:
                 compute.set_peer_outputs(None)
         # every rank must take the same branch: a rank whose planner declined makes all of them gather
-        flag = torch.tensor([1 if wrote == world - 1 else 0], dtype=torch.int32, device=C_full.device)
+        flag = torch.tensor([1 if wrote == expect else 0], dtype=torch.int32, device=C_full.device)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)     # also the completion barrier of the peer stores
         if int(flag.item()) == 1:
             return lo, hi
         _gather_blocks(m, n, world, C_full, C_blk, group)            # the blocks are computed; only the exchange is left
         return lo, hi
-    if m % world == 0 and overlap_passes > 1 and hi > lo:
+    if m % world == 0 and overlap_passes > 1 and hi > lo and not streamed:
         m_loc = hi - lo
-        works = []
+        works2 = []
 
         def on_rows(r0, rows):
             # rows [r0, r0 + rows) of EVERY rank's block: rank q's copy lands at rows q * m_loc + r0 of C_full
             outs = [_bytes(C_full[(q * m_loc + r0) * n:(q * m_loc + r0 + rows) * n]) for q in range(world)]
-            works.append(dist.all_gather(outs, _bytes(C_blk[r0 * n:(r0 + rows) * n]), group=group, async_op=True))
+            works2.append(dist.all_gather(outs, _bytes(C_blk[r0 * n:(r0 + rows) * n]), group=group, async_op=True))
 
         compute.gemm(m_loc, n, k, alpha, A_blk, k, B, n, beta, C_blk, n, on_rows=on_rows, min_passes=overlap_passes)
-        for w in works:
-            w.wait()
+        for wk in works2:
+            wk.wait()
         return lo, hi
     if hi > lo:
-        compute.gemm(hi - lo, n, k, alpha, A_blk, k, B, n, beta, C_blk, n)
+        run_gemm(hi - lo, A_blk, C_blk)
+    elif streamed:
+        for wk in works:                                             # a rank without rows still takes part in the broadcasts
+            wk.wait()
     _gather_blocks(m, n, world, C_full, C_blk, group)
     return lo, hi
 

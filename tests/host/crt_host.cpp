@@ -54,28 +54,31 @@ static void scan_line(const q128 *x, int count, int stride, int &emax, int &lmin
     if (ee + tz < lmin) lmin = ee + tz;
   }
 }
-template <int NG> static q128 fold_one(const uint32_t (&r)[NMP], const Plan &pl, int Eb)
+template <int NG> static q128 fold_one(const uint32_t (&r)[NMP], const Plan &pl, int Eb, int *msb)
 {
   uint32_t Y[NG + 1], neg;
   reconstruct_dev<NG>(r, pl, Y, neg);
+  *msb = limbs_msb<NG + 1>(Y);
   return limbs_to_q<NG + 1>(Y, neg, Eb);
 }
 
 extern "C" {
-// C (m x n) = alpha * A (m x k) * B (k x n) + beta * C, row-major, dense.  returns 0, or 1 if the scheme declines (Inf/NaN, span).
-int crt_gemm_host(int m, int n, int k, const q128 *A, const q128 *B, q128 *Cm, const q128 *alpha, const q128 *beta, int *info /* N, WA, WB */)
+// C (m x n) = alpha * A (m x k) * B (k x n) + beta * C, row-major, dense, as the GPU path computes it: scan, windows from
+// crt::host::plan_windows (wcap = the planner's budget per operand), truncating element_words, residues, int32 accumulation,
+// acc_mod, reconstruct_dev, and the acceptance test crt::accept_msb of k_crt_fold: rejected[i*n+j] = 1 marks the elements the GPU
+// hands to the fix-up kernel (C is left untouched there).  returns 0, or 1 if the scheme declines (Inf/NaN are not mirrored here).
+int crt_gemm_host(int m, int n, int k, const q128 *A, const q128 *B, q128 *Cm, const q128 *alpha, const q128 *beta, int wcap, int *info /* N, WA, WB, truncated */,
+                  unsigned char *rejected)
 {
   std::vector<int> emaxA(m), lminA(m), emaxB(n), lminB(n);
-  int special = 0, WA = 0, WB = 0;
-  for (int i = 0; i < m; ++i) { scan_line(A + (size_t)i * k, k, 1, emaxA[i], lminA[i], special); if (emaxA[i]) WA = std::max(WA, emaxA[i] + 113 - lminA[i]); }
-  for (int j = 0; j < n; ++j) { scan_line(B + j, k, n, emaxB[j], lminB[j], special); if (emaxB[j]) WB = std::max(WB, emaxB[j] + 113 - lminB[j]); }
-  WA = std::max(WA, 1); WB = std::max(WB, 1);
-  if (special || WA > WMAX || WB > WMAX) return 1;
-  int lk = 0;
-  while ((1 << lk) < k) ++lk;
-  const int N = host::moduli_for_bits(WA + WB + lk + 1);
-  if (N == 0) return 1;
-  info[0] = N; info[1] = WA; info[2] = WB;
+  int special = 0, WA_nat = 0, WB_nat = 0;
+  for (int i = 0; i < m; ++i) { scan_line(A + (size_t)i * k, k, 1, emaxA[i], lminA[i], special); if (emaxA[i]) WA_nat = std::max(WA_nat, emaxA[i] + 113 - lminA[i]); }
+  for (int j = 0; j < n; ++j) { scan_line(B + j, k, n, emaxB[j], lminB[j], special); if (emaxB[j]) WB_nat = std::max(WB_nat, emaxB[j] + 113 - lminB[j]); }
+  if (special) return 1;
+  host::Windows win;
+  if (!host::plan_windows(WA_nat, WB_nat, k, wcap, win)) return 1;
+  const int WA = win.WA, WB = win.WB, N = win.N;
+  info[0] = N; info[1] = WA; info[2] = WB; info[3] = (win.truncA ? 1 : 0) | (win.truncB ? 2 : 0);
   Plan pl; host::build_plan(N, pl);
   const int nwA = std::min(NWMAX, std::max(1, (WA + 31) / 32)), nwB = std::min(NWMAX, std::max(1, (WB + 31) / 32));
   std::vector<int8_t> pA((size_t)N * m * k), pB((size_t)N * n * k);     // planes [N][rows][k]
@@ -92,13 +95,19 @@ int crt_gemm_host(int m, int n, int k, const q128 *A, const q128 *B, q128 *Cm, c
         for (int l = 0; l < k; ++l) acc += (int32_t)a[l] * (int32_t)b[l];
         r[c] = acc_mod(acc, c, tab());
       }
-      const int Eb = (emaxA[i] + 113 - WA) + (emaxB[j] + 113 - WB) - 2 * 16495;
+      const int baseA = emaxA[i] + 113 - WA, baseB = emaxB[j] + 113 - WB;
+      const int Eb = baseA + baseB - 2 * 16495;
       q128 s = {0, 0};
+      int msb = -1;
       switch (pl.NG) {
-#define CASE(g) case g: s = fold_one<g>(r, pl, Eb); break;
+#define CASE(g) case g: s = fold_one<g>(r, pl, Eb, &msb); break;
         CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13)
 #undef CASE
       }
+      const bool tA = emaxA[i] != 0 && lminA[i] < baseA, tB = emaxB[j] != 0 && lminB[j] < baseB;
+      const bool reject = msb < accept_msb(tA, tB, WA, WB, k);
+      if (rejected) rejected[(size_t)i * n + j] = reject ? 1 : 0;
+      if (reject) continue;
       q128 &c = Cm[(size_t)i * n + j];
       c = qb::q_fma(*alpha, s, qb::q_mul(*beta, c));
     }

@@ -25,7 +25,7 @@ def main():
     rng = np.random.default_rng(3)
     fails = []
     # ---- qgemm: reference order (bit exact vs oracle) and fast mode (tensor path; bitwise equal to the 1-GPU call)
-    for mode, (m, n, k) in ((qb.MODE_REFERENCE, (70, 33, 260)), (qb.MODE_REFERENCE, (37, 20, 127)), (qb.MODE_FAST, (1024, 384, 640)), (qb.MODE_FAST, (1031, 250, 300))):   # fast: every rank's block keeps >= 128 rows up to world 8 (tensor path)
+    for mode, (m, n, k) in ((qb.MODE_REFERENCE, (70, 33, 260)), (qb.MODE_REFERENCE, (37, 20, 127)), (qb.MODE_FAST, (1024, 640, 640)), (qb.MODE_FAST, (1031, 250, 300))):   # fast: every rank's block keeps >= 128 rows up to world 8 (tensor path)
         A = quad.random_quads(rng, m * k); B = quad.random_quads(rng, k * n); C0 = quad.random_quads(rng, m * n)
         alpha, beta = quad.random_quads(rng, 2)
         qb.set_mode(mode)
@@ -60,6 +60,34 @@ def main():
             fails.append(("fused gather did not run", mode, m, n, k, qb.gemm_peer_written()))
         del Cp
         pb.close()
+        # the same through torch symmetric memory: ONE store per element to the NVSwitch multicast address reaches every rank's copy
+        try:
+            sb = qd.SymmetricBuffer(m * n * 16)
+        except RuntimeError as e:
+            sb = None
+            if rank == 0:
+                print(f"mgpu_worker: symmetric memory unavailable, multicast gather not tested: {e}", flush=True)
+        if sb is not None:
+            Cs = sb.tensor.view(torch.int64).reshape(m * n, 2)
+            Cs.copy_(to_dev(C0.copy()))
+            Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+            torch.cuda.synchronize(); dist.barrier()
+            qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cs, peers=sb)
+            torch.cuda.synchronize()
+            if not (to_host(Cs) == to_host(one)).all():
+                fails.append(("gemm multicast gather vs 1-GPU", mode, m, n, k, sb.mc_ptr != 0, qb.gemm_peer_written()))
+            if rank == 0 and mode == qb.MODE_FAST:
+                print(f"mgpu_worker: symmetric buffer multicast={'yes' if sb.mc_ptr else 'no'} outputs written={qb.gemm_peer_written()}", flush=True)
+            del Cs
+            sb.close()
+        # B broadcast during the product in packed column panels (fast mode, tensor path)
+        if mode == qb.MODE_FAST and n >= 256:
+            Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+            Cf2 = to_dev(C0.copy())
+            qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cf2, b_panels=256)
+            torch.cuda.synchronize()
+            if not (to_host(Cf2) == to_host(one)).all():
+                fails.append(("gemm streamed B vs 1-GPU", mode, m, n, k))
         if mode == qb.MODE_REFERENCE:
             want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
             if not quad.same_bits(to_host(Cf), want).all():
@@ -87,6 +115,22 @@ def main():
         torch.cuda.synchronize()
         if not (to_host(out).reshape(2) == want).all():
             fails.append(("dot", nn, T))
+    # ---- qdot / qnrm2, fast mode: contiguous ranges, all-gather of the 16-byte partials, fixed-order fold on every rank
+    qb.set_mode(qb.MODE_FAST)
+    nn = 300001
+    x = quad.random_quads(rng, nn); y = quad.random_quads(rng, nn)
+    lo, hi = qd.dot_shard_range(nn, 1, world, rank, False)
+    out = torch.zeros((1, 2), dtype=torch.int64, device="cuda")
+    qd.qdot_sharded(nn, to_dev(x[lo:hi]), to_dev(y[lo:hi]), 1, out, reference_order=False)
+    torch.cuda.synchronize()
+    exact, ratio, klass = orc.exact_dot_check("R", nn, x, nn, y, 1, np.array([[0, 0]]), to_host(out).reshape(1, 2))
+    if not (ratio[0] <= 1.0 and klass[0] == 0):
+        fails.append(("fast dot contract", float(ratio[0])))
+    gathered = [torch.zeros_like(out) for _ in range(world)]
+    dist.all_gather(gathered, out)
+    if not all((g == out).all() for g in gathered):
+        fails.append(("fast dot differs between ranks",))
+    qb.set_mode(qb.MODE_REFERENCE)
     t = torch.tensor([len(fails)], device="cuda")
     dist.all_reduce(t)
     if fails:

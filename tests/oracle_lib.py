@@ -49,6 +49,7 @@ class Oracle:
         L.orc_c_qgemm.argtypes = [cc, cc, cc, ci, ci, ci, cd, vp, ci, vp, ci, cd, vp, ci]
         L.orc_gemm_sample.argtypes = [cc, cl, cl, cl, vp, vp, cl, vp, cl, vp, vp, cl, cl, cl, vp, vp]
         L.orc_absdot_sample.argtypes = [cc, cl, vp, cl, vp, cl, cl, vp, vp]
+        L.orc_exact_dot_check.argtypes = [cc, cl, vp, cl, vp, cl, cl, vp, vp, vp, vp, vp]
         L.orc_to_double.argtypes = [vp]
         L.orc_to_double.restype = cd
         L.orc_from_double.argtypes = [cd, vp]
@@ -130,6 +131,23 @@ class Oracle:
         out = np.zeros((idx.shape[0], 2), dtype=np.uint64)
         self.L.orc_absdot_sample(layout.encode(), k, _p(A), lda, _p(B), ldb, idx.shape[0], C.c_void_p(idx.ctypes.data), _p(out))
         return out
+
+
+    def exact_dot_check(self, layout, k, A, lda, B, ldb, idx, got=None):
+        """Exact inner products of the sampled (i, j) through a long accumulator (oracle/qoracle.c): returns
+        (exact sums rounded once (ns, 2), err / (k u sum|a||b|) per entry as float64 (<= 1 <=> fast-mode contract), IEEE class per entry:
+        0 finite data, 1 NaN, 2 +Inf, 3 -Inf).  `got`: the (ns, 2) results to check (None: only the exact sums)."""
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        ns = idx.shape[0]
+        exact = np.zeros((ns, 2), dtype=np.uint64)
+        ratio = np.zeros(ns, dtype=np.float64)
+        klass = np.zeros(ns, dtype=np.int32)
+        if got is not None:
+            got = np.ascontiguousarray(got, dtype=np.uint64)
+            assert got.shape == (ns, 2)
+        self.L.orc_exact_dot_check(layout.encode(), k, _p(A), lda, _p(B), ldb, ns, C.c_void_p(idx.ctypes.data),
+                                   _p(got) if got is not None else None, _p(exact), C.c_void_p(ratio.ctypes.data), C.c_void_p(klass.ctypes.data))
+        return exact, ratio, klass
 
 
 class Ref:

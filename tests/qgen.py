@@ -101,3 +101,14 @@ def matrix(rng, rows, cols, kind="D113", ld=None):
     ld = cols if ld is None else ld
     buf = quad.random_quads(rng, (rows, ld), "D113" if kind == "pad" else kind)
     return np.ascontiguousarray(buf.reshape(rows * ld, 2))
+
+
+def reference_benchmark_doubles(count, seed=42):
+    """The value stream of the reference's benchmark programs (benchmarks/benchmark.cpp:8-29: std::mt19937(seed) +
+    std::uniform_real_distribution<double>(-1, 1), i.e. libstdc++'s generate_canonical<double, 53>: two 32-bit draws, low word first),
+    reproduced with numpy's MT19937 (same init_genrand seeding).  Checked against a g++ build of the same three lines."""
+    rs = np.random.RandomState(seed)
+    raw = rs.randint(0, 2 ** 32, size=2 * count, dtype=np.uint64).astype(np.float64)
+    s = (raw[0::2] + raw[1::2] * 4294967296.0) / 18446744073709551616.0
+    s = np.where(s >= 1.0, np.nextafter(1.0, 0.0), s)
+    return s * 2.0 - 1.0

@@ -31,7 +31,9 @@ def test_exports_every_declared_symbol():
 
 def test_version_threads_alignment():
     assert qblas_b200.quadblas_get_version() == "QuadBLAS 1.0.0 - High Performance Quad Precision BLAS"  # c_interface.hpp:136
-    assert qblas_b200.quadblas_get_num_threads() == (os.cpu_count() or 1)
+    # default = omp_get_max_threads() as the reference reads it (threading/openmp_utils.hpp:10-17): OMP_NUM_THREADS, else the hardware
+    env_t = os.environ.get("OMP_NUM_THREADS", "").split(",")[0].strip()
+    assert qblas_b200.quadblas_get_num_threads() == (int(env_t) if env_t.isdigit() and int(env_t) > 0 else (os.cpu_count() or 1))
     qblas_b200.quadblas_set_num_threads(5)
     assert qblas_b200.quadblas_get_num_threads() == 5
     qblas_b200.quadblas_set_num_threads(0)
@@ -80,6 +82,41 @@ def test_compute_fails_loudly_without_gpu():
     assert quad.same_bits(x, y).all()  # outputs untouched on failure
 
 
+def test_environment_selects_mode_kc_and_threads():
+    """An UNMODIFIED caller of the reference API picks the numerical mode through the environment (QUADBLAS_MODE, QUADBLAS_KC), and
+    the default thread count follows OMP_NUM_THREADS like omp_get_max_threads() does in the reference."""
+    import subprocess
+    import sys
+    code = ("import qblas_b200 as q; L = q.lib(); print(L.qb_get_mode(), L.qb_get_kc(), L.quadblas_get_num_threads()); "
+            "L.quadblas_set_num_threads(3); print(L.quadblas_get_num_threads())")
+    def run(env):
+        e = dict(os.environ, PYTHONPATH=ROOT); e.pop("OMP_NUM_THREADS", None); e.pop("QUADBLAS_MODE", None); e.pop("QUADBLAS_KC", None)
+        e.update(env)
+        out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, check=True).stdout.split()
+        return [int(v) for v in out]
+    assert run({}) == [0, 126, os.cpu_count() or 1, 3]
+    assert run({"QUADBLAS_MODE": "fast", "QUADBLAS_KC": "256", "OMP_NUM_THREADS": "7"}) == [1, 256, 7, 3]
+    assert run({"QUADBLAS_MODE": "REFERENCE", "OMP_NUM_THREADS": "4,2"}) == [0, 126, 4, 3]
+    assert run({"QUADBLAS_MODE": "bogus", "QUADBLAS_KC": "-5", "OMP_NUM_THREADS": "zero"}) == [0, 126, os.cpu_count() or 1, 3]
+
+
+def test_a_reported_error_does_not_stick():
+    """A failed call raises once; the thread-local error is cleared with the report, and the reference-named entry points clear it at
+    entry, so qb_last_error_code() always describes the LAST call only."""
+    import torch
+    L = qblas_b200.lib()
+    x = quad.from_double(np.ones(4))
+    with pytest.raises(qblas_b200.QblasError):
+        qblas_b200.gemv("R", -1, 2, 1.0, x, 2, x, 1, 0.0, x.copy(), 1)        # QB_ERR_ARG, no GPU needed
+    assert L.qb_last_error_code() == 0 and L.qb_last_error() == b""
+    L.qb_gemv(b"R", -1, 2, None, None, 2, None, 1, None, None, 1)              # a C caller that ignores the return code
+    assert L.qb_last_error_code() == 2
+    if not torch.cuda.is_available():
+        L.quadblas_qaxpy(0, 1.0, None, 1, None, 1)                             # n <= 0: returns at once (c_interface.hpp:49) ...
+        assert L.qb_last_error_code() == 0                                     # ... after clearing the stale code
+    L.qb_clear_error()
+
+
 def test_residue_scheme_row_pass_partition():
     """Host logic of the row passes (csrc/qb_ozaki.cu, oz_crt_pass_rows): shape 0 is the equal split the kernels were measured with,
     shape 1 (experimental) shortens the first and the last pass; every partition covers the rows exactly once in tile multiples."""
@@ -106,9 +143,8 @@ def test_measured_defaults():
     L = qblas_b200.lib()
     assert L.qb_get_mode() == 0                   # reference order (bit exact) unless fast mode is requested
     assert L.qb_get_tensor_path() == 1            # fast-mode qgemm: tensor path for m, n >= 128, k >= 256
-    assert L.qb_get_tensor_scheme() == 1          # residue planes + Chinese-remainder reconstruction
+    assert L.qb_get_tensor_window() == 144        # bits per operand window when the spans do not fit the moduli
     assert L.qb_get_tensor_pass_shape() == 0      # equal row passes
-    assert L.qb_get_tensor_keep() == 16           # digit-diagonal fallback: bounded setting
     assert L.qb_get_fast_variant() == 1           # qdot / qnrm2 / qgemv: window accumulator
     assert L.qb_get_gemm_peer_written() == 0
-    assert L.qb_get_host_slabs() == 4             # pipelined all-host qgemm: four C slabs
+    assert L.qb_get_host_slabs() == 8             # pipelined all-host qgemm / qgemv: eight slabs

@@ -45,6 +45,32 @@ class OracleEngine:
             for r0 in range(0, m, step):
                 on_rows(r0, min(step, m - r0))
 
+    # streamed B (qb_set_gemm_b_panels): the stand-in asks for every panel in order, as the library does, and multiplies panel by panel
+    def colstats(self, k, n, B, ldb, out):
+        out.fill_(7)            # opaque to the host logic: it is only broadcast and handed back
+        return out
+
+    def wait_on_stream(self, work, stream_ptr):
+        work.wait()
+
+    def gemm_streamed(self, m, n, k, alpha, A, lda, panel_fn, panel_cols, colstats, beta, C, ldc):
+        import ctypes
+        assert (colstats.numpy() == 7).all() and colstats.numel() == 3 * n       # the owner's statistics arrived on every rank
+        Cn = self._np(C)
+        for c0 in range(0, n, panel_cols):
+            cols = min(panel_cols, n - c0)
+            ptr, ld = panel_fn(c0, cols, 0)
+            assert ld == cols
+            Bp = np.ctypeslib.as_array((ctypes.c_uint64 * (k * cols * 2)).from_address(ptr)).reshape(k * cols, 2)
+            Cp = np.ascontiguousarray(Cn.reshape(m, ldc, 2)[:, c0:c0 + cols]).reshape(m * cols, 2)
+            self.o.gemm("R", m, cols, k, alpha, self._np(A), lda, np.ascontiguousarray(Bp), cols, beta, Cp, cols)
+            Cn.reshape(m, ldc, 2)[:, c0:c0 + cols] = Cp.reshape(m, cols, 2)
+        self.wrote = 0
+        if self.peers and self.fused_ok:
+            for p in self.peers:
+                self.mem.view(p, m * n * 16).copy_(C.view(torch.uint8).reshape(-1)[:m * n * 16])
+            self.wrote = len(self.peers)
+
     def gemv(self, m, n, alpha, A, lda, x, beta, y):
         self.o.gemv("R", m, n, alpha, self._np(A), lda, self._np(x), 1, beta, self._np(y), 1)
 
@@ -145,7 +171,7 @@ def _fused_worker(rank, world, port, q):
             dist.barrier()
             lo, hi = qd.row_block(m, world, rank)
             Bt = t(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64)
-            qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cp, compute=eng, peers=pb)
+            qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cp, compute=eng, peers=pb, b_panels=(3 if m >= world and k == 40 else 0))
             dist.barrier()
             assert (Cp.numpy().view(np.uint64) == want).all(), ("fused gemm", m, n, k, rank, fused_ok_on)
             assert eng.peers == []                                   # switched off again after the call
@@ -196,6 +222,13 @@ def _worker(rank, world, port, q):
             Cf = t(C0.copy())
             qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cf, compute=eng, overlap_passes=2)
             assert (Cf.numpy().view(np.uint64) == want).all(), ("gemm overlapped", m, n, k, rank)
+            # B broadcast DURING the product, in packed column panels (here 2 columns wide, ragged last panel), statistics first
+            Bt = t(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64)
+            Cf = t(C0.copy())
+            qd.qgemm_row_sharded(m, n, k, alpha, t(A[lo * k:hi * k]), Bt, beta, Cf, compute=eng, b_panels=2)
+            assert (Cf.numpy().view(np.uint64) == want).all(), ("gemm streamed B", m, n, k, rank)
+            if rank != 0:
+                assert (Bt == 0).all()                                   # B itself is only read on its owner
         # ---- qgemv
         m, n = 9, 33
         A = quad.random_quads(rng, m * n); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)

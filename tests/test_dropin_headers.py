@@ -36,6 +36,16 @@ def test_reference_test_program_compiles_unmodified(tmp_path):
                         "-L" + os.path.join(ROOT, "qblas_b200"), "-lqblas_b200"], stdin=src, check=True, cwd=ROOT)
 
 
+@pytest.mark.parametrize("prog", ["tests/debug_test.cpp", "tests/test_sleef_simd.cpp"])
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "tests", "debug_test.cpp")), reason="reference sources not present")
+def test_reference_debug_programs_compile_unmodified(tmp_path, prog):
+    """QuadVector + QuadBLAS::dot_kernel_vectorized (level1.hpp:14-35) are part of the surface the reference's debug programs use."""
+    exe = tmp_path / "dbg"
+    with open(os.path.join(REF, prog), "rb") as src:
+        subprocess.run(["/usr/bin/g++", "-std=gnu++17", "-O0", "-x", "c++", "-", "-I" + ROOT, "-I" + INC, "-I" + os.path.join(INC, "quadblas"), "-o", str(exe),
+                        "-L" + os.path.join(ROOT, "qblas_b200"), "-lqblas_b200"], stdin=src, check=True, cwd=ROOT)
+
+
 def test_compat_scalar_ops_are_correctly_rounded(tmp_path):
     """Sleef_*q1_u05 of include/quadblas/b200/sleefquad_compat.h (caller-side only) vs libquadmath, bitwise."""
     src = tmp_path / "c.cpp"

@@ -38,3 +38,17 @@ def test_reference_own_test_program_passes_unmodified(qb):
     tail = r.stdout[-2500:]
     assert r.returncode == 0, tail + r.stderr[-1000:]
     assert "FAIL" not in r.stdout.upper().replace("FAILED: 0", ""), tail
+
+
+@pytest.mark.parametrize("prog,expect", [("debug_test_b200", ["a*b + 1 = 7", "15"]), ("test_sleef_simd_b200", ["14"])])
+def test_reference_debug_programs_run_unmodified(qb, prog, expect):
+    """/root/reference/tests/debug_test.cpp and tests/test_sleef_simd.cpp (QuadVector, QuadBLAS::dot_kernel_vectorized of
+    level1.hpp:14-35, dot 1..5 = 15, the 2 x 2 gemv), compiled unmodified against the drop-in headers (oracle/Makefile)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", prog)
+    if not os.path.exists(exe):
+        pytest.skip(f"oracle/_ref/{prog} not built (reference sources absent when build() ran)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1000:]
+    for e in expect:
+        assert e in r.stdout, (e, r.stdout[-2500:])
+    assert "FAIL" not in r.stdout and "ERROR" not in r.stdout.upper().replace("ERROR = 0", ""), r.stdout[-2500:]

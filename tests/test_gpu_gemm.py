@@ -165,3 +165,34 @@ def test_gemm_full_size_sampled(qb, oracle):
     exp = oracle.gemm_sample("R", n, n, n, 1.0, Ah, n, Bh, n, 0.0, Cinh, n, idx)
     got = to_host(C).reshape(n, n, 2)[idx[:, 0], idx[:, 1]]
     assert quad.same_bits(got, exp).all()
+
+
+@pytest.mark.parametrize("mode", ["fast", "reference"])
+def test_baseline_config1_1000_cubed_full_matrix(qb, oracle, mode):
+    """BASELINE config 1 = the reference README's benchmark: quadblas_qgemm('R','N','N',1000,1000,1000, 1.0, A,1000, B,1000, 0.0, C,1000)
+    with A, then B, then C drawn from ONE mt19937(42) + uniform_real_distribution<double>(-1,1) stream and cast to quad
+    (benchmarks/benchmark.cpp:8-29,181-189), through the reference-named C entry point with host buffers.
+    fast mode: EVERY entry is the exact inner product rounded once (long accumulator, oracle/qoracle.c) - and so inside the contract;
+    reference mode: bit for bit the reference order (kc = 126) on every 4th row, all columns (a full CPU recomputation is ~25 core-minutes)."""
+    import qgen
+    S = 1000
+    d = qgen.reference_benchmark_doubles(3 * S * S)
+    A = quad.from_double(d[:S * S]).reshape(-1, 2); B = quad.from_double(d[S * S:2 * S * S]).reshape(-1, 2); C0 = quad.from_double(d[2 * S * S:]).reshape(-1, 2)
+    assert abs(d[0] - 0.59308596857569196) < 1e-16 and abs(d[5] + 0.80005015891231857) < 1e-16      # the g++ build's first draws
+    C = C0.copy()
+    qb.set_mode(qb.MODE_FAST if mode == "fast" else qb.MODE_REFERENCE)
+    try:
+        qb.quadblas_qgemm("R", "N", "N", S, S, S, 1.0, A, S, B, S, 0.0, C, S)
+        st = qb.oz_last_stats() if mode == "fast" else None
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    if mode == "fast":
+        assert st["pairs"] > 0 and st["exact"] and st["WA"] <= 64 and st["WB"] <= 64, st          # doubles: 53-bit mantissas, short windows, ~16 moduli
+        idx = np.stack(np.meshgrid(np.arange(S), np.arange(S), indexing="ij"), axis=-1).reshape(-1, 2)
+        exact, ratio, klass = oracle.exact_dot_check("R", S, A, S, B, S, idx, C)
+        assert (klass == 0).all() and quad.same_bits(C, exact).all() and (ratio <= 1.0).all()
+    else:
+        rows = np.arange(0, S, 4)
+        idx = np.stack(np.meshgrid(rows, np.arange(S), indexing="ij"), axis=-1).reshape(-1, 2)
+        want = oracle.gemm_sample("R", S, S, S, 1.0, A, S, B, S, 0.0, C0, S, idx)
+        assert quad.same_bits(C.reshape(S, S, 2)[rows].reshape(-1, 2), want).all()

@@ -1,7 +1,9 @@
-"""GPU tests of the pipelined all-host qgemm path (csrc/qb_abi.cu qb_gemm: shared operand first, then C cut into four
-slabs whose uploads / compute / downloads overlap on three streams).  Each slab is an ordinary qgemm on device pointers,
-so the host-buffer result must equal the device-buffer result of the SAME call bit for bit — in reference-order mode
-(where every bit is defined by /root/reference/include/quadblas/algorithms/level3.hpp:215-336) and in fast mode."""
+"""GPU tests of the pipelined all-host paths (csrc/qb_abi.cu).  qb_gemm: the shared operand is uploaded first, then the rows
+stream in, are multiplied and stream out on three streams — in reference-order mode as slabs that are ordinary qgemms on device
+pointers, in fast mode as ONE tensor-path call whose row passes wait for their slabs (passes outer, streamed rows).  qb_gemv: A is
+uploaded in row slabs while the earlier slabs are multiplied.  The host-buffer result must equal the device-buffer result of the
+SAME call bit for bit — in reference-order mode (where every bit is defined by
+/root/reference/include/quadblas/algorithms/level3.hpp:215-336, level2.hpp:15-82) and in fast mode."""
 import numpy as np
 import pytest
 import torch
@@ -59,3 +61,52 @@ def test_pipelined_host_path_fast_mode(qb):
         qb.set_mode(qb.MODE_REFERENCE)
     assert st["pairs"] > 0                                        # the slabs went through the tensor path
     assert quad.same_bits(dev, host).all(), f"{(~quad.same_bits(dev, host)).sum()} entries differ"
+
+
+@pytest.mark.parametrize("layout,m,n,k", [("R", 2300, 1100, 900), ("C", 1100, 2300, 900), ("R", 4200, 520, 640)])
+def test_streamed_host_path_fast_mode_layouts_and_ragged_passes(qb, layout, m, n, k):
+    """The fast-mode all-host call is one tensor-path qgemm with streamed rows: ragged slabs / passes, padded leading dimensions, and
+    col-major through the exchanged roles (C^T = B^T A^T: the columns of C are the streamed 'rows')."""
+    rng = np.random.default_rng(m + n)
+    col = layout == "C"
+    a_shape = (k, m) if col else (m, k); b_shape = (n, k) if col else (k, n); c_shape = (n, m) if col else (m, n)
+    lda, ldb, ldc = a_shape[1] + 3, b_shape[1] + 1, c_shape[1] + 2
+    A = qgen.matrix(rng, a_shape[0], a_shape[1], "D113", lda); B = qgen.matrix(rng, b_shape[0], b_shape[1], "D113", ldb)
+    C0 = qgen.matrix(rng, c_shape[0], c_shape[1], "D113", ldc)
+    alpha, beta = quad.random_quads(rng, 2)
+    assert A.nbytes + B.nbytes + C0.nbytes >= 64 << 20
+    qb.set_mode(qb.MODE_FAST)
+    try:
+        dev, host = _run_both(qb, layout, "N", "N", m, n, k, lda, ldb, ldc, A, B, C0, alpha, beta)
+        st = qb.oz_last_stats()
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert st["pairs"] > 0 and st["row_passes"] >= 3, st
+    assert quad.same_bits(dev, host).all(), f"{(~quad.same_bits(dev, host)).sum()} entries differ"
+    idx = np.array([[(i * ldc + j) if not col else (j * ldc + i) for j in range(n)] for i in range(m)]).reshape(-1)
+    mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False
+    assert (host[mask] == C0[mask]).all()                           # padding between the rows is not touched
+
+
+@pytest.mark.parametrize("layout,mode", [("R", "ref"), ("C", "ref"), ("R", "fast"), ("C", "fast")])
+def test_pipelined_host_gemv_equals_device_path(qb, layout, mode):
+    """qb_gemv with a large host A: uploaded in row slabs (contiguous for row-major, 2-D copies of a row range for col-major), each
+    slab an ordinary qgemv on its rows: same bits as the device-resident call."""
+    rng = np.random.default_rng(ord(layout) + len(mode))
+    m, n = 2100, 2060
+    lda = (n if layout == "R" else m) + 5
+    A = qgen.matrix(rng, m if layout == "R" else n, n if layout == "R" else m, "D113", lda)
+    x = quad.random_quads(rng, n * 2); y0 = quad.random_quads(rng, m * 3)
+    alpha, beta = quad.random_quads(rng, 2)
+    assert A.nbytes >= 64 << 20
+    qb.set_mode(qb.MODE_FAST if mode == "fast" else qb.MODE_REFERENCE)
+    try:
+        dy = to_dev(y0)
+        qb.gemv(layout, m, n, alpha, to_dev(A), lda, to_dev(x), 2, beta, dy, 3)
+        torch.cuda.synchronize()
+        hy = y0.copy()
+        qb.gemv(layout, m, n, alpha, A, lda, x, 2, beta, hy, 3)
+    finally:
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert quad.same_bits(to_host(dy), hy).all()
+    assert not quad.same_bits(hy, y0).all()

@@ -1,7 +1,9 @@
-"""GPU tests of the fast-mode tensor-core qgemm (csrc/qb_ozaki.cu): the int8 tcgen05 kernel alone
-against integer matmul, and the whole path (scan -> slice -> mma -> fold) against EXACT inner
-products rounded once (tests/exact_ref.py) followed by the reference epilogue
-C = fma(alpha, s, mul(beta, C)) (/root/reference/include/quadblas/algorithms/level3.hpp:102-109)."""
+"""GPU tests of the fast-mode tensor-core qgemm (csrc/qb_ozaki.cu + csrc/qb_crt.cuh): the int8 tcgen05 kernel alone against
+integer matmul, and the whole path (scan -> residues -> mma -> reconstruction [-> fix-up]) against EXACT inner products rounded once
+(tests/exact_ref.py in Python integers for small cases, the long accumulator of oracle/qoracle.c for large ones) followed by the
+reference epilogue C = fma(alpha, s, mul(beta, C)) (/root/reference/include/quadblas/algorithms/level3.hpp:102-109).  Inputs whose
+exponent spread the moduli cannot cover (SURVEY.md §8d cfg3 'Dexp') are checked against the fast-mode contract
+|c^ - c| <= gamma_k (|A||B|)_ij entry by entry."""
 import numpy as np
 import pytest
 import torch
@@ -14,18 +16,12 @@ from qblas_b200 import quad
 pytestmark = pytest.mark.gpu
 
 
+
 @pytest.fixture(autouse=True)
-def _exact_setting(qb):
-    """The tests of this file that compare bit for bit run the digit-diagonal scheme with ALL diagonals
-    (qb_set_tensor_keep(0)); the bounded setting is covered by the test_bounded_* tests, which select it themselves.
-    The residue scheme (qb_set_tensor_scheme(1), the default) is always exact."""
-    old, old_scheme = qb.get_tensor_keep(), qb.get_tensor_scheme()
-    qb.set_tensor_keep(0)
+def _defaults(qb):
     yield
-    qb.set_tensor_keep(old); qb.set_tensor_scheme(old_scheme)
-
-
-SCHEMES = [pytest.param(1, id="residues"), pytest.param(0, id="digits")]
+    qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO); qb.set_tensor_unit(0, 0); qb.set_tensor_window(144)
+    qb.set_gemm_pass_callback(None); qb.set_gemm_peer_outputs(None); qb.set_gemm_b_panels(None)
 
 
 def _diag_ref(pa, pb, m, n):
@@ -76,263 +72,259 @@ def _epilogue(oracle, alpha, s, beta, C0):
     return oracle.fma(al, s, oracle.mul(be, np.ascontiguousarray(C0)))
 
 
-@pytest.mark.parametrize("scheme", SCHEMES)
-@pytest.mark.parametrize("m,n,k,kind,layout", [(40, 33, 300, "D113", "R"), (17, 50, 129, "Dexp", "R"), (33, 20, 257, "D53", "C"),
-                                               (130, 260, 64, "D113", "R"), (5, 7, 1000, "D113", "C"), (24, 30, 140, "Dexp8", "R"),
-                                               (9, 300, 70, "Dint", "C"), (140, 12, 33, "D113", "C")])
-def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, layout, scheme):
-    qb.set_tensor_scheme(scheme)
+
+def _mk(rng, r, c, ld, kind):
+    if kind.startswith("Dexp"):  # full mantissas times 2^U{-s..s}
+        s_ = int(kind[4:])
+        return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-s_, emax=s_).reshape(r * ld, 2))
+    if kind == "Dint":   # small integers (a few moduli, one reconstruction group), with zeros
+        return quad.from_double(rng.integers(-9, 10, size=(r, ld)).astype(np.float64)).reshape(r * ld, 2)
+    return qgen.matrix(rng, r, c, kind, ld)
+
+
+def _fast_gemm(qb, layout, m, n, k, alpha, A, lda, B, ldb, beta, C0, ldc):
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
+    dC = to_dev(C0)
+    qb.gemm(layout, m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
+    torch.cuda.synchronize()
+    st = qb.oz_last_stats()
+    qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert st["pairs"] > 0, "tensor path declined"
+    return to_host(dC), st
+
+
+@pytest.mark.parametrize("m,n,k,kind,layout", [(40, 33, 300, "D113", "R"), (33, 20, 257, "D53", "C"), (130, 260, 64, "D113", "R"), (5, 7, 1000, "D113", "C"),
+                                               (24, 30, 140, "Dexp8", "R"), (17, 50, 129, "Dexp12", "C"), (9, 300, 70, "Dint", "C"), (140, 12, 33, "D113", "C")])
+def test_fast_gemm_tensor_path_is_exactly_rounded(qb, oracle, m, n, k, kind, layout):
+    """Spans the moduli cover (everything up to +-12 binades inside a row): exact inner products, one rounding, bit for bit."""
     rng = np.random.default_rng(m + n + k)
     ar, ac = (m, k) if layout == "R" else (k, m)
     br, bc = (k, n) if layout == "R" else (n, k)
     cr, cc = (m, n) if layout == "R" else (n, m)
     lda, ldb, ldc = ac + 1, bc + 2, cc + 3
-    def mk(r, c, ld):
-        if kind == "Dexp":  # +-28 binades: 113 + 56 + 2 bits -> 22 digits (the full +-40 of qgen needs 25 > 24 and is declined);
-            # 2 x 171 bits + log2 k is also more than the residue scheme's 49 moduli cover: it hands over to the digit diagonals
-            return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-28, emax=28).reshape(r * ld, 2))
-        if kind == "Dexp8":  # +-8 binades: spans of ~130 bits, inside the residue scheme
-            return np.ascontiguousarray(quad.random_quads(rng, (r, ld), "D113", emin=-8, emax=8).reshape(r * ld, 2))
-        if kind == "Dint":   # small integers (a few moduli, one reconstruction group), with zeros
-            return quad.from_double(rng.integers(-9, 10, size=(r, ld)).astype(np.float64)).reshape(r * ld, 2)
-        return qgen.matrix(rng, r, c, kind, ld)
-    A = mk(ar, ac, lda); B = mk(br, bc, ldb); C0 = mk(cr, cc, ldc)
+    A = _mk(rng, ar, ac, lda, kind); B = _mk(rng, br, bc, ldb, kind); C0 = _mk(rng, cr, cc, ldc, kind)
     alpha, beta = quad.random_quads(rng, 2)
     s = exact_matmul_rounded(A, lda, B, ldb, m, n, k, layout)          # (m*n, 2) in (i, j) order
     idx = np.array([[(i * ldc + j) if layout == "R" else (j * ldc + i) for j in range(n)] for i in range(m)]).reshape(-1)
     want = _epilogue(oracle, alpha, s, beta, C0[idx])
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
-    try:
-        dC = to_dev(C0)
-        qb.gemm(layout, m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    got = to_host(dC)
-    assert st["pairs"] > 0, "tensor path declined"
-    assert st["scheme"] == ("residues" if scheme == 1 and kind != "Dexp" else "digits"), st
+    got, st = _fast_gemm(qb, layout, m, n, k, alpha, A, lda, B, ldb, beta, C0, ldc)
+    assert st["exact"] and st["flagged"] == 0, st
     assert quad.same_bits(got[idx], want).all(), f"{(~quad.same_bits(got[idx], want)).sum()} mismatches, plan {st}"
-    # untouched padding
-    mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False
+    mask = np.ones(C0.shape[0], dtype=bool); mask[idx] = False       # untouched padding
     assert (got[mask] == C0[mask]).all()
 
 
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle, scheme):
+def test_fast_gemm_cancellation_pattern_is_exact(qb, oracle):
     """README:141-158 / test_quadblas.cpp:715-739: rows (1e20, 1, -1e20, 0...) times ones -> exactly 1."""
-    qb.set_tensor_scheme(scheme)
     m, n, k = 128, 128, 256
     A = np.zeros((m, k)); A[:, 0] = 1e20; A[:, 1] = 1.0; A[:, 2] = -1e20
     Aq = quad.from_double(A).reshape(-1, 2); Bq = quad.from_double(np.ones((k, n))).reshape(-1, 2)
     C0 = quad.from_double(np.zeros((m, n))).reshape(-1, 2)
     qb.set_mode(qb.MODE_FAST)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, 1.0, to_dev(Aq), k, to_dev(Bq), n, 0.0, dC, n)
-        torch.cuda.synchronize()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE)
-    one = quad.from_double(np.ones(m * n))
-    assert quad.same_bits(to_host(dC), one).all()
+    dC = to_dev(C0)
+    qb.gemm("R", m, n, k, 1.0, to_dev(Aq), k, to_dev(Bq), n, 0.0, dC, n)
+    torch.cuda.synchronize()
+    st = qb.oz_last_stats()
+    assert st["pairs"] > 0 and st["exact"], st
+    assert quad.same_bits(to_host(dC), quad.from_double(np.ones(m * n))).all()
 
 
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_fast_gemm_declines_specials_and_wide_spans(qb, oracle, scheme):
-    """Inf/NaN or a row spanning more than 24 digits: the planner declines, the integer kernel runs (fast mode = single chain)."""
-    qb.set_tensor_scheme(scheme)
+def _check_contract(oracle, layout, m, n, k, A, lda, B, ldb, got_ij, idx=None):
+    """every (sampled) entry against the exact inner product: returns (exact sums rounded once, err / (k u |A||B|), IEEE class)"""
+    if idx is None:
+        idx = np.stack(np.meshgrid(np.arange(m), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
+    return oracle.exact_dot_check(layout, k, A, lda, B, ldb, idx, got_ij)
+
+
+@pytest.mark.parametrize("m,n,k,kind,window", [(256, 256, 1024, "Dexp40", 144), (130, 260, 300, "Dexp40", 144), (128, 256, 512, "Dexp40", 128),
+                                               (140, 132, 260, "Dexp100", 144)])
+def test_wide_exponent_ranges_stay_on_the_tensor_path_and_meet_the_contract(qb, oracle, m, n, k, kind, window):
+    """SURVEY.md §8d cfg3 'Dexp' = D113 x 2^U{-40..40} (and wider): row spans of ~190+ bits, more than the moduli cover.  The planner
+    caps the windows instead of declining, the reconstruction kernel tests every element against the dropped mass and the fix-up
+    kernel recomputes the rejected ones.  EVERY entry of C is inside |c^ - c| <= k u (|A||B|)_ij against exact arithmetic."""
+    rng = np.random.default_rng(m * 3 + k)
+    A = _mk(rng, m, k, k, kind); B = _mk(rng, k, n, n, kind); C0 = _mk(rng, m, n, n, "D113")
+    qb.set_tensor_window(window)
+    got, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    assert st["truncated"] & 3 and not st["exact"] and st["WA"] + st["WB"] <= 2 * window, st
+    exact, ratio, klass = _check_contract(oracle, "R", m, n, k, A, k, B, n, got)
+    assert (klass == 0).all() and (ratio <= 1.0).all(), (st, float(ratio.max()), int((ratio > 1).sum()))
+    if kind == "Dexp40" and window == 144 and k >= 1024:
+        assert st["flagged"] <= m * n // 1000, st          # a handful of cancelling entries at most
+    # deterministic
+    got2, _ = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    assert (got == got2).all()
+
+
+def test_cancelling_entries_under_a_capped_window_go_to_the_fixup(qb, oracle):
+    """Rows whose large terms cancel exactly (+2^60 b, -2^60 b): what is left comes from small elements a capped window truncates; those
+    entries fail the acceptance test, are left to k_crt_fixup (window accumulator) and come out correctly rounded; alpha / beta epilogue
+    included (C_in of a rejected entry must still be intact when the fix-up reads it)."""
+    rng = np.random.default_rng(77)
+    m, n, k = 128, 256, 512
+    A = _mk(rng, m, k, k, "Dexp40").reshape(m, k, 2); B = _mk(rng, k, n, n, "Dexp40").reshape(k, n, 2)
+    big = quad.from_double(np.array([2.0 ** 60]))[0]
+    A[:8, 0] = big; A[:8, 1] = big; A[:8, 1, 1] ^= np.uint64(1 << 63)
+    A[:8, 2:, 1] = (A[:8, 2:, 1] & np.uint64(0x8000ffffffffffff)) | (np.uint64(16383 - 30) << np.uint64(48))    # the rest of those rows is small
+    B[1, :] = B[0, :]
+    A = np.ascontiguousarray(A.reshape(m * k, 2)); B = np.ascontiguousarray(B.reshape(k * n, 2)); C0 = _mk(rng, m, n, n, "D113")
+    alpha, beta = quad.random_quads(rng, 2)
+    got, st = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
+    assert st["truncated"] & 3 and st["flagged"] >= 8 * n, st
+    idx = np.stack(np.meshgrid(np.arange(8), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
+    exact, _, klass = oracle.exact_dot_check("R", k, A, k, B, n, idx)
+    want = _epilogue(oracle, alpha, exact, beta, C0[:8 * n])
+    # the window accumulator drops less than k 2^-133 of the largest product: here the exact sum rounded once, bit for bit
+    assert (klass == 0).all() and quad.same_bits(got[:8 * n], want).all()
+    # and the whole matrix meets the contract through the epilogue-free path
+    got0, _ = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    _, ratio, _ = _check_contract(oracle, "R", m, n, k, A, k, B, n, got0)
+    assert (ratio <= 1.0).all()
+
+
+def test_inf_nan_and_huge_spans_run_on_the_tensor_path(qb, oracle):
+    """Inf / NaN operands and a row that spans 2000 binades: nothing is declined any more.  The rows / columns that hold Inf or NaN get
+    the IEEE result of the sum of products (NaN for NaN, Inf - Inf, Inf * 0; else +-Inf) from the fix-up kernel, every finite entry
+    meets the contract, and the rest of the matrix is not slowed down to the integer kernel."""
     rng = np.random.default_rng(3)
     m, n, k = 130, 140, 260
     A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
-    A[5] = quad.from_double(np.array([np.inf]))[0]
-    A[700] = quad.from_double(np.array([1e-300]))[0] ; A[701] = quad.from_double(np.array([1e300]))[0]
-    Co = C0.copy()
-    oracle.gemm("R", m, n, k, 1.0, A, k, B, n, 1.0, Co, n, kc=k)       # single chain = fast-mode integer kernel
-    qb.set_mode(qb.MODE_FAST)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 1.0, dC, n)
-        torch.cuda.synchronize()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE)
-    assert quad.same_bits(to_host(dC), Co).all()
+    inf, nan = quad.from_double(np.array([np.inf]))[0], quad.from_double(np.array([np.nan]))[0]
+    A[5] = inf                                   # row 0: +Inf (times finite non-zero)
+    A[2 * k + 7] = inf; A[2 * k + 8] = inf; A[2 * k + 8, 1] ^= np.uint64(1 << 63)     # row 2: +Inf and -Inf
+    A[4 * k + 1] = nan                           # row 4: NaN
+    B[9 * n + 3] = inf                           # column 3: Inf
+    B[11 * n + 6] = quad.from_double(np.array([0.0]))[0]; A[7 * k + 11] = inf          # row 7, column 6: Inf * 0
+    A[9 * k + 0] = quad.from_double(np.array([1e-300]))[0]; A[9 * k + 1] = quad.from_double(np.array([1e300]))[0]   # row 9: 2000 binades
+    got, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    assert st["truncated"] & 4 and st["flagged"] >= 4 * n + m - 4, st
+    exact, ratio, klass = _check_contract(oracle, "R", m, n, k, A, k, B, n, got)
+    assert (ratio <= 1.0).all(), (st, np.argwhere(ratio > 1)[:5])
+    kl = klass.reshape(m, n)
+    assert (kl[4] == 1).all() and (kl[2] == 1).all() and kl[7, 6] == 1 and (kl[:, 3] != 0).all() and (kl[0] != 0).all()
+    assert (kl[[1, 3, 5, 6, 8, 9] + list(range(10, m))][:, [0, 1, 2] + list(range(4, n))] == 0).all()
+    fin = (klass == 0).reshape(m, n).copy(); fin[9] = False     # row 9 lost bits to its window: contract only; all others are exact sums
+    assert quad.same_bits(got.reshape(m, n, 2)[fin], exact.reshape(m, n, 2)[fin]).all()
 
 
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_fast_gemm_large_matches_sampled_exact(qb, oracle, scheme):
-    """1024 x 768 x 2304 (two K chunks at 18 slices would need k > 7281; force chunks via D113 + k): sampled entries vs exact."""
-    qb.set_tensor_scheme(scheme)
-    m, n, k = 1024, 768, 2304
-    A = dev_random((m * k,), "D113", seed=1); B = dev_random((k * n,), "D113", seed=2); C = dev_random((m * n,), "D113", seed=3)
-    C0 = to_host(C).copy()
-    qb.set_mode(qb.MODE_FAST)
-    try:
-        qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE)
-    assert st["pairs"] > 0 and st["scheme"] == ("residues" if scheme else "digits"), st
-    Ah, Bh, got = to_host(A), to_host(B), to_host(C)
-    rng = np.random.default_rng(0)
-    for _ in range(12):
-        i, j = int(rng.integers(m)), int(rng.integers(n))
-        s = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, np.ascontiguousarray(Bh[j::n][:k]), 1, 1, 1, k)
-        want = _epilogue(oracle, quad.from_double(np.array([1.0]))[0], s, quad.from_double(np.array([0.0]))[0], C0[i * n + j:i * n + j + 1])
-        assert quad.same_bits(got[i * n + j:i * n + j + 1], want).all(), (i, j, st)
-
-
-# ------------------------------------------------------------------ bounded setting (qb_set_tensor_keep(d), default d = 17)
-def _contract_check(qb, oracle, m, n, k, A, B, got, C0=None, beta0=True):
-    """|c^ - c| <= gamma_k (|A||B|)_ij for every entry, c = exact inner product (alpha = 1, beta = 0)."""
-    from fractions import Fraction
-    s = exact_matmul_rounded(A, k, B, n, m, n, k, "R")                 # exact, rounded once: within u|c| of c
-    idx = np.stack(np.meshgrid(np.arange(m), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
-    ab = oracle.absdot_sample("R", k, A, k, B, n, idx)
-    u = Fraction(1, 2 ** 113); gam = k * u / (1 - k * u)
-    f = lambda v: quad.to_fraction(int(v[1]), int(v[0]))
-    worst = Fraction(0)
-    for q in range(m * n):
-        err = abs(f(got[q]) - f(s[q]))
-        bound = gam * f(ab[q])
-        assert err <= bound + u * abs(f(s[q])), (q, float(err), float(bound))
-        if bound: worst = max(worst, err / bound)
-    return float(worst)
-
-
-@pytest.mark.parametrize("m,n,k,kind", [(130, 257, 300, "D113"), (128, 256, 1024, "D113"), (140, 260, 520, "Dexp")])
-def test_bounded_tensor_path_meets_contract(qb, oracle, m, n, k, kind):
-    rng = np.random.default_rng(m * 7 + k)
-    mk = (lambda r, c: np.ascontiguousarray(quad.random_quads(rng, (r, c), "D113", emin=-28, emax=28).reshape(r * c, 2))) if kind == "Dexp" \
-        else (lambda r, c: qgen.matrix(rng, r, c, kind, c))
-    A = mk(m, k); B = mk(k, n); C0 = qgen.matrix(rng, m, n, "D113", n)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 0.0, dC, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-        dC2 = to_dev(C0)
-        qb.gemm("R", m, n, k, 1.0, to_dev(A), k, to_dev(B), n, 0.0, dC2, n)
-        torch.cuda.synchronize()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert st["pairs"] > 0 and st["keep"] == 17 and st["keep"] < st["ndiag"], st
-    want_pairs = sum(min(d, st["SA"] - 1) - max(0, d - (st["SB"] - 1)) + 1 for d in range(17))
-    assert st["pairs"] == want_pairs < st["SA"] * st["SB"], st        # e.g. 153 digit-plane products instead of 18 * 18
-    got = to_host(dC)
-    assert quad.same_bits(got, to_host(dC2)).all()                    # deterministic
-    worst = _contract_check(qb, oracle, m, n, k, A, B, got)
-    assert worst < 0.5                                                # typically ~1/k: far inside the bound
-
-
-def test_bounded_fixup_on_cancelling_entries(qb, oracle):
-    """Columns of B built so that some inner products cancel to ~2^-60 of their terms: those entries fail the
-    |J| >= 2^125 check, are left to k_oz_fixup and must still meet the contract."""
-    rng = np.random.default_rng(77)
-    m, n, k = 128, 256, 512
-    A = qgen.matrix(rng, m, k, "D113", k)
-    Bm = quad.random_quads(rng, (k, n), "D113")
-    # column j (odd) = -(column j-1) in the first half of k, + the same in the second half, applied to rows of A
-    # that repeat their first half: A[i, k/2 + l] = A[i, l] for i < 4  ->  c[i, j] cancels to ~2^-107 for those (i, j odd)
-    Am = A.reshape(m, k, 2).copy()
-    Am[:4, k // 2:] = Am[:4, :k // 2]
-    Bm[k // 2:, 1::2] = Bm[:k // 2, 1::2] ^ np.array([0, 1 << 63], dtype=np.uint64)   # negated copy
-    Bm[k // 2:, 1::2, 0] ^= np.uint64(1) << np.uint64(5)                               # ... up to one low mantissa bit
-    A2 = np.ascontiguousarray(Am.reshape(m * k, 2)); B2 = np.ascontiguousarray(Bm.reshape(k * n, 2))
-    C0 = qgen.matrix(rng, m, n, "D113", n)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, 1.0, to_dev(A2), k, to_dev(B2), n, 0.0, dC, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert 4 * (n // 2) <= st["flagged"] <= 1024 and st["redo_passes"] == 0, st   # 512 entries <= list capacity: k_oz_fixup, no redo
-    _contract_check(qb, oracle, m, n, k, A2, B2, to_host(dC))
-
-
-def test_bounded_redo_when_many_entries_vanish(qb, oracle):
-    """A quarter of the rows of A are zero: every entry of those C rows is an exact 0, far more than 1/64 of the pass, so the
-    pass is redone with all diagonals for them; alpha/beta epilogue included (C_in of the flagged entries must be intact)."""
-    rng = np.random.default_rng(78)
-    m, n, k = 256, 256, 384
-    A = qgen.matrix(rng, m, k, "D113", k).reshape(m, k, 2)
-    A[::4] = 0
-    A = np.ascontiguousarray(A.reshape(m * k, 2)); B = qgen.matrix(rng, k, n, "D113", n); C0 = qgen.matrix(rng, m, n, "D113", n)
-    alpha, beta = quad.random_quads(rng, 2)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_keep(17); qb.set_tensor_scheme(0)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert st["redo_passes"] == 1 and st["flagged"] >= (m // 4) * n, st
-    got = to_host(dC).reshape(m, n, 2)
-    # the vanished rows: exact sum 0 -> C = fma(alpha, +0, mul(beta, C_in)), bit for bit
-    z = np.zeros(((m // 4) * n, 2), dtype=np.uint64)
-    want = _epilogue(oracle, alpha, z, beta, np.ascontiguousarray(C0.reshape(m, n, 2)[::4].reshape(-1, 2)))
-    assert quad.same_bits(got[::4].reshape(-1, 2), want).all()
-    # the other rows went through the bounded path: exact-rounded sums agree to within the contract (sampled)
-    s = exact_matmul_rounded(A, k, B, n, m, n, k, "R").reshape(m, n, 2)
-    rows = [1, 2, 3, 129, 255]
-    for i in rows:
-        w = _epilogue(oracle, alpha, np.ascontiguousarray(s[i]), beta, np.ascontiguousarray(C0.reshape(m, n, 2)[i]))
-        for j in (0, 100, 255):
-            fg, fw = quad.to_fraction(int(got[i, j, 1]), int(got[i, j, 0])), quad.to_fraction(int(w[j, 1]), int(w[j, 0]))
-            assert abs(fg - fw) <= abs(fw) / 2 ** 90
-
-
-# ------------------------------------------------------------------ residue scheme specifics (csrc/qb_crt.cuh)
-def test_residue_scheme_row_passes_and_epilogue(qb, oracle):
-    """Row passes (pass hook with min_passes = 3) + alpha/beta epilogue + padded leading dimensions: every pass slices its own A
-    rows, reuses the residue planes of B, and the result is the exact product rounded once, bit for bit."""
-    m, n, k = 384, 264, 200
+@pytest.mark.parametrize("unit", [(128, 256), (256, 512), (384, 256)])
+def test_units_passes_panels_and_epilogue(qb, oracle, unit):
+    """The pipeline units (row passes x column panels): small units force many passes and panels, ragged last ones included; the pass
+    hook reports every row once; alpha/beta epilogue and padded leading dimensions; sampled rows against exact arithmetic, and the
+    whole result bit for bit the one of a single unit."""
+    m, n, k = 520, 700, 200
     rng = np.random.default_rng(11)
     lda, ldb, ldc = k + 3, n + 1, n + 2
     A = qgen.matrix(rng, m, k, "D113", lda); B = qgen.matrix(rng, k, n, "D113", ldb); C0 = qgen.matrix(rng, m, n, "D113", ldc)
     alpha, beta = quad.random_quads(rng, 2)
-    rows_idx = rng.choice(m, 6, replace=False)
+    got1, st1 = _fast_gemm(qb, "R", m, n, k, alpha, A, lda, B, ldb, beta, C0, ldc)
+    assert st1["units"] == 1
     seen = []
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
-    try:
-        qb.set_gemm_pass_callback(lambda r0, rows: seen.append((r0, rows)), 3)
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_gemm_pass_callback(None)
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert st["scheme"] == "residues" and st["row_passes"] == 3 and seen == [(0, 128), (128, 128), (256, 128)], (st, seen)
-    got = to_host(dC)
-    for i in rows_idx:
+    qb.set_tensor_unit(*unit)
+    qb.set_gemm_pass_callback(lambda r0, rows: seen.append((r0, rows)), 1)
+    got, st = _fast_gemm(qb, "R", m, n, k, alpha, A, lda, B, ldb, beta, C0, ldc)
+    qb.set_gemm_pass_callback(None)
+    np_, nj = -(-m // unit[0]), -(-n // unit[1])
+    assert st["row_passes"] == np_ and st["panels"] == nj and st["units"] == np_ * nj, st
+    assert sorted(seen) == [(p * unit[0], min(unit[0], m - p * unit[0])) for p in range(np_)], seen
+    assert (got == got1).all()
+    for i in rng.choice(m, 5, replace=False):
         s = exact_matmul_rounded(A[i * lda:(i + 1) * lda], lda, B, ldb, 1, n, k, "R")
         want = _epilogue(oracle, alpha, s, beta, C0[i * ldc:i * ldc + n])
         assert quad.same_bits(got[i * ldc:i * ldc + n], want).all(), (i, st)
 
 
-def test_residue_scheme_zero_operand(qb, oracle):
+def test_pass_callback_min_passes(qb, oracle):
+    m, n, k = 384, 264, 200
+    rng = np.random.default_rng(12)
+    A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    seen = []
+    qb.set_gemm_pass_callback(lambda r0, rows: seen.append((r0, rows)), 3)
+    got, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    qb.set_gemm_pass_callback(None)
+    assert st["row_passes"] == 3 and seen == [(0, 128), (128, 128), (256, 128)], (st, seen)
+    # min_passes larger than ceil(m / 128): passes of one tile row each (include/qblas_b200.h)
+    seen.clear()
+    qb.set_gemm_pass_callback(lambda r0, rows: seen.append((r0, rows)), 16)
+    got2, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    qb.set_gemm_pass_callback(None)
+    assert len(seen) == 3 and (got == got2).all()
+
+
+def test_zero_operand(qb, oracle):
     """An all-zero A (no span at all): the sums are +0 and C = fma(alpha, +0, mul(beta, C))."""
     m, n, k = 130, 258, 130
     rng = np.random.default_rng(12)
     A = quad.from_double(np.zeros((m, k))).reshape(-1, 2); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
     alpha, beta = quad.random_quads(rng, 2)
-    zero = quad.from_double(np.zeros(m * n))
-    want = _epilogue(oracle, alpha, zero, beta, C0)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert st["scheme"] == "residues", st
-    assert quad.same_bits(to_host(dC), want).all()
+    want = _epilogue(oracle, alpha, quad.from_double(np.zeros(m * n)), beta, C0)
+    got, st = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
+    assert st["exact"] and quad.same_bits(got, want).all(), st
+
+
+def test_fast_gemm_large_matches_sampled_exact(qb, oracle):
+    """1024 x 768 x 2304 with the default units, device resident: sampled entries against the long accumulator, bit for bit."""
+    m, n, k = 1024, 768, 2304
+    A = dev_random((m * k,), "D113", seed=1); B = dev_random((k * n,), "D113", seed=2); C = dev_random((m * n,), "D113", seed=3)
+    qb.set_mode(qb.MODE_FAST)
+    qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
+    torch.cuda.synchronize()
+    st = qb.oz_last_stats()
+    assert st["pairs"] > 0 and st["exact"], st
+    rng = np.random.default_rng(0)
+    idx = np.stack([rng.integers(0, m, 256), rng.integers(0, n, 256)], axis=1)
+    got = to_host(C).reshape(m, n, 2)[idx[:, 0], idx[:, 1]]
+    exact, ratio, klass = oracle.exact_dot_check("R", k, to_host(A), k, to_host(B), n, idx, got)
+    assert quad.same_bits(got, exact).all() and (klass == 0).all()
+
+
+def test_k_beyond_one_int32_accumulation(qb, oracle):
+    """k > 65536: the int32 accumulators of the tensor kernel hold 2^30 at most, so K is cut into chunks whose residues are added
+    mod p in the kernel's epilogue.  Sampled entries against the long accumulator, bit for bit."""
+    m, n, k = 128, 256, 65536 + 4096 + 100
+    A = dev_random((m * k,), "D113", seed=31); B = dev_random((k * n,), "D113", seed=32); C = dev_random((m * n,), "D113", seed=33)
+    qb.set_mode(qb.MODE_FAST)
+    qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
+    torch.cuda.synchronize()
+    st = qb.oz_last_stats()
+    assert st["pairs"] > 0 and st["nchunks"] == 2 and st["exact"], st
+    rng = np.random.default_rng(1)
+    idx = np.stack([rng.integers(0, m, 48), rng.integers(0, n, 48)], axis=1)
+    got = to_host(C).reshape(m, n, 2)[idx[:, 0], idx[:, 1]]
+    exact, _, klass = oracle.exact_dot_check("R", k, to_host(A), k, to_host(B), n, idx, got)
+    assert quad.same_bits(got, exact).all() and (klass == 0).all()
+
+
+def test_streamed_b_panels(qb, oracle):
+    """qb_set_gemm_b_panels: B is handed over in column panels that live in their own packed buffers (what a rank that receives B panel
+    by panel holds), with the column statistics computed up front; same bits as the resident-B call."""
+    m, n, k, pw = 300, 1024, 260, 256
+    rng = np.random.default_rng(21)
+    A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    alpha, beta = quad.random_quads(rng, 2)
+    want, st0 = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
+    dB = to_dev(B)
+    stats = torch.zeros(3 * n, dtype=torch.int32, device="cuda")
+    qb.gemm_colstats("R", k, n, dB, n, stats)
+    panels = [dB.reshape(k, n, 2)[:, c0:c0 + pw].contiguous() for c0 in range(0, n, pw)]     # packed k x pw panels, ld = pw
+    calls = []
+
+    def provide(col0, cols, stream_ptr):
+        calls.append((col0, cols))
+        ev = torch.cuda.Event(); ev.record()                       # "arrival": ordered after the packing copies on torch's stream
+        torch.cuda.ExternalStream(stream_ptr).wait_event(ev)
+        return panels[col0 // pw].data_ptr(), pw
+
+    qb.set_gemm_b_panels(provide, pw, stats)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
+    dC = to_dev(C0)
+    bogus = torch.zeros(16, dtype=torch.int64, device="cuda")     # the B argument is not dereferenced
+    qb.gemm("R", m, n, k, alpha, to_dev(A), k, bogus.reshape(-1, 2), n, beta, dC, n)
+    torch.cuda.synchronize()
+    st = qb.oz_last_stats()
+    qb.set_gemm_b_panels(None)
+    assert calls == [(c0, pw) for c0 in range(0, n, pw)] and st["panels"] == n // pw, (calls, st)
+    assert (to_host(dC) == want).all()
 
 
 # ------------------------------------------------------------------ fused gather (qb_set_gemm_peer_outputs): single-GPU check of the store path
@@ -350,7 +342,7 @@ def test_residue_scheme_peer_outputs_mirror_C(qb, oracle, layout, m, n, k):
     alpha, beta = quad.random_quads(rng, 2)
     sentinel = qgen.matrix(rng, cr, cc, "D113", ldc)
     dC = to_dev(C0); P1 = to_dev(sentinel.copy()); P2 = to_dev(sentinel.copy())
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
     try:
         qb.set_gemm_peer_outputs([P1.data_ptr(), P2.data_ptr()])
         qb.gemm(layout, m, n, k, alpha, to_dev(A), lda, to_dev(B), ldb, beta, dC, ldc)
@@ -392,9 +384,9 @@ def _truncate_mantissa(q, bits):
 
 
 @pytest.mark.parametrize("name,bits,binades,m,n,k", [("float32-like", 24, 3, 40, 50, 100), ("80-bit", 80, 6, 33, 47, 64), ("96-bit", 96, 8, 20, 300, 96),
-                                                    ("wide", 113, 24, 30, 40, 256)])
-def test_residue_scheme_other_word_and_group_counts(qb, oracle, name, bits, binades, m, n, k):
-    """Spans of ~30 / ~90 / ~110 / ~160 bits: 1, 3, 4 and 6 integer words per element and 2 to 12 reconstruction groups (the
+                                                    ("wide", 113, 14, 30, 40, 256)])
+def test_other_word_and_group_counts(qb, oracle, name, bits, binades, m, n, k):
+    """Spans of ~30 / ~90 / ~110 / ~140 bits: 1, 3, 4 and 5 integer words per element and 2 to 11 reconstruction groups (the
     float32-like case also stands for low-precision data cast to quad).  Exactly rounded, bit for bit."""
     rng = np.random.default_rng(bits + k)
     def mk(r, c):
@@ -403,40 +395,23 @@ def test_residue_scheme_other_word_and_group_counts(qb, oracle, name, bits, bina
     alpha, beta = quad.random_quads(rng, 2)
     s = exact_matmul_rounded(A, k, B, n, m, n, k)
     want = _epilogue(oracle, alpha, s, beta, C0)
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS); qb.set_tensor_scheme(1)
-    try:
-        dC = to_dev(C0)
-        qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
-        torch.cuda.synchronize()
-        st = qb.oz_last_stats()
-    finally:
-        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
-    assert st["scheme"] == "residues", st
-    assert quad.same_bits(to_host(dC), want).all(), st
+    got, st = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
+    assert st["exact"], st
+    assert quad.same_bits(got, want).all(), st
 
 
-def test_residue_scheme_pass_shapes_agree(qb, oracle):
-    """qb_set_tensor_pass_shape(1) (short first and last row pass, experimental) changes only WHEN rows are produced: the result is
-    bit for bit the one of the equal split, and a few rows around the pass boundaries match exact arithmetic."""
-    m, n, k = 4224, 256, 256                      # equal: 1152 x 3 + 768; shaped: 384, 1152 x 3, 384 (api.crt_pass_rows(4224, 1152, s))
-    A = dev_random((m * k,), "D113", seed=21); B = dev_random((k * n,), "D113", seed=22); C0 = dev_random((m * n,), "D113", seed=23)
-    outs, plans = [], []
-    qb.set_mode(qb.MODE_FAST); qb.set_tensor_scheme(1)
-    try:
-        for shape in (0, 1):
-            qb.set_tensor_pass_shape(shape)
-            C = C0.clone()
-            qb.gemm("R", m, n, k, 1.0, A, k, B, n, 0.0, C, n)
-            torch.cuda.synchronize()
-            outs.append(to_host(C)); plans.append(qb.oz_last_stats())
-    finally:
-        qb.set_tensor_pass_shape(0)
-        qb.set_mode(qb.MODE_REFERENCE)
-    assert plans[0]["scheme"] == "residues" and plans[0]["row_passes"] == 4 and plans[1]["row_passes"] == 5, plans
-    assert (outs[0] == outs[1]).all()
-    Ah, Bh = to_host(A), to_host(B)
-    one, zero = quad.from_double(np.array([1.0]))[0], quad.from_double(np.array([0.0]))[0]
-    for i in (0, 383, 384, 1535, 1536, 3839, 3840, m - 1):
-        s = exact_matmul_rounded(Ah[i * k:(i + 1) * k], k, Bh, n, 1, n, k)
-        want = _epilogue(oracle, one, s, zero, to_host(C0)[i * n:(i + 1) * n])
-        assert quad.same_bits(outs[1][i * n:(i + 1) * n], want).all(), i
+def test_widest_windows_six_words_thirteen_groups(qb, oracle):
+    """A wide A (+-36 binades: 185-bit rows) against double-valued B (54 bits): the narrow operand leaves its share of the moduli to
+    the wide one, which takes all 6 words; with qb_set_tensor_window(170) both operands at +-24 binades use 161-bit windows and 13
+    reconstruction groups.  Exact in both cases."""
+    rng = np.random.default_rng(5)
+    m, n, k = 30, 40, 128
+    A = _mk(rng, m, k, k, "Dexp36"); B = qgen.matrix(rng, k, n, "D53"); C0 = _mk(rng, m, n, n, "D113")
+    got, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    assert st["exact"] and st["WA"] > 160, st
+    assert quad.same_bits(got, exact_matmul_rounded(A, k, B, n, m, n, k)).all()
+    qb.set_tensor_window(170)
+    A = _mk(rng, m, k, k, "Dexp24"); B = _mk(rng, k, n, n, "Dexp24")
+    got, st = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    assert st["exact"] and st["pairs"] >= 45, st
+    assert quad.same_bits(got, exact_matmul_rounded(A, k, B, n, m, n, k)).all()

@@ -244,12 +244,14 @@ def test_whole_scheme_on_the_cpu_is_exactly_rounded(lib, oracle, kind, m, n, k):
     C0 = np.ascontiguousarray(quad.random_quads(rng, (m, n), "D113").reshape(m * n, 2))
     alpha, beta = quad.random_quads(rng, 2)
     got = C0.copy()
-    info = np.zeros(3, dtype=np.int32)
+    info = np.zeros(4, dtype=np.int32)
+    rej = np.zeros(m * n, dtype=np.uint8)
     lib.crt_set_form(1)
-    lib.crt_gemm_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.crt_gemm_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     al = np.ascontiguousarray(alpha, dtype=np.uint64); be = np.ascontiguousarray(beta, dtype=np.uint64)
-    rc = lib.crt_gemm_host(m, n, k, A.ctypes.data, B.ctypes.data, got.ctypes.data, al.ctypes.data, be.ctypes.data, info.ctypes.data)
+    rc = lib.crt_gemm_host(m, n, k, A.ctypes.data, B.ctypes.data, got.ctypes.data, al.ctypes.data, be.ctypes.data, 144, info.ctypes.data, rej.ctypes.data)
     assert rc == 0, "scheme declined"
+    assert info[3] == 0 and not rej.any()          # windows cover the spans: nothing truncated, nothing rejected
     s = exact_matmul_rounded(A, k, B, n, m, n, k)
     alb = np.broadcast_to(al.reshape(1, 2), s.shape).copy(); beb = np.broadcast_to(be.reshape(1, 2), s.shape).copy()
     want = oracle.fma(alb, s, oracle.mul(beb, C0))
@@ -258,3 +260,58 @@ def test_whole_scheme_on_the_cpu_is_exactly_rounded(lib, oracle, kind, m, n, k):
         assert info[1] <= 64 and info[2] <= 64 and info[0] <= 17      # doubles: short spans, few moduli
     if kind == "Dint":
         assert info[0] <= 4
+
+
+@pytest.mark.parametrize("kind,m,n,k,wcap", [("Dexp40", 6, 5, 64, 144), ("Dexp40", 4, 4, 200, 128), ("Dexp40xD53", 5, 5, 80, 144), ("Dexp70xD53", 5, 5, 80, 144), ("Dexp200", 4, 6, 48, 144),
+                                            ("cancel", 4, 4, 64, 144), ("Dexp40", 3, 3, 2, 144)])
+def test_capped_windows_meet_the_contract_or_are_rejected(lib, oracle, kind, m, n, k, wcap):
+    """Exponent spreads the moduli cannot cover (SURVEY.md §8d cfg3 'Dexp' = D113 x 2^U{-40..40}, and far wider): the planner caps the
+    windows, element_words drops the low bits of the small elements, and k_crt_fold's acceptance test (crt::accept_msb) decides per
+    element.  Here the same source runs on the CPU: every ACCEPTED element is inside |c^ - c| <= k u (|A||B|)_ij against exact
+    long-accumulator arithmetic (oracle/qoracle.c), every other one is reported for the fix-up; engineered cancellations are caught."""
+    from qblas_b200 import quad
+    rng = np.random.default_rng(m * 1000 + n * 100 + k + wcap)
+
+    def mk(r, c, spread):
+        return np.ascontiguousarray(quad.random_quads(rng, (r, c), "D113", emin=-spread, emax=spread).reshape(r * c, 2))
+    if kind == "Dexp40":
+        A, B = mk(m, k, 40), mk(k, n, 40)
+    elif kind in ("Dexp40xD53", "Dexp70xD53"):
+        A = mk(m, k, 40 if kind == "Dexp40xD53" else 70); B = np.ascontiguousarray(quad.random_quads(rng, (k, n), "D53").reshape(k * n, 2))
+    elif kind == "Dexp200":
+        A, B = mk(m, k, 200), mk(k, n, 200)
+    else:   # rows whose large terms cancel exactly: what is left comes from the small elements the cap truncates
+        A, B = mk(m, k, 40), mk(k, n, 40)
+        Am = A.reshape(m, k, 2); Bm = B.reshape(k, n, 2)
+        big = quad.from_double(np.array([2.0 ** 60]))[0]
+        Am[:, 0] = big; Am[:, 1] = big; Am[:, 1, 1] ^= np.uint64(1 << 63)      # +2^60, -2^60
+        Bm[1, :] = Bm[0, :]                                                    # times equal entries: the pair cancels exactly
+    C0 = np.ascontiguousarray(quad.random_quads(rng, (m, n), "D113").reshape(m * n, 2))
+    got = C0.copy()
+    info = np.zeros(4, dtype=np.int32)
+    rej = np.zeros(m * n, dtype=np.uint8)
+    one = quad.from_double(np.array([1.0])); zero = quad.from_double(np.array([0.0]))
+    lib.crt_set_form(1)
+    lib.crt_gemm_host.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = lib.crt_gemm_host(m, n, k, A.ctypes.data, B.ctypes.data, got.ctypes.data, one.ctypes.data, zero.ctypes.data, wcap, info.ctypes.data, rej.ctypes.data)
+    assert rc == 0
+    N, WA, WB, trunc = info.tolist()
+    assert WA + WB <= 2 * wcap and max(WA, WB) <= 192, info.tolist()
+    idx = np.stack(np.meshgrid(np.arange(m), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
+    exact, ratio, klass = oracle.exact_dot_check("R", k, A, k, B, n, idx, got)
+    if kind == "Dexp40xD53":                     # the narrow operand leaves its share of the budget to the wide one: still exact
+        assert trunc == 0 and WB <= 60 and WA > wcap and not rej.any() and quad.same_bits(got, exact).all(), info.tolist()
+        return
+    assert trunc != 0, info.tolist()
+    if kind == "Dexp70xD53":
+        assert trunc == 1 and WA == 192 and WB <= 60, info.tolist()
+    acc = rej == 0
+    assert (klass == 0).all()
+    assert (ratio[acc] <= 1.0).all(), (info.tolist(), ratio[acc].max())
+    assert (got[~acc] == C0[~acc]).all()                                       # rejected elements are left to the fix-up
+    if kind == "cancel":
+        assert rej.sum() >= 1, "the engineered cancellations must be rejected"
+    elif k > 1 and wcap >= 144 and kind != "Dexp200":
+        # (a 128-bit window leaves ~10 bits of margin over the test, and with +-200 binades the largest element of a row rarely meets
+        # the largest of a column, so the sums sit far below the windows' product: many rejections, all legitimate)
+        assert rej.mean() < 0.25, rej.mean()
