@@ -147,6 +147,8 @@ void qb_oz_last_stats(int64_t *out16);
 /* Summed device time (ms, CUDA events on the launching stream) of the tcgen05 kernel launches of
  * the last tensor-path qgemm; waits for them to finish.  *launches (optional) = how many. */
 double qb_oz_last_mma_ms(int *launches);
+/* profiling aid: (start relative to the first launch, duration) in ms of each of those launches, up to max_pairs; returns how many */
+int qb_oz_last_mma_timeline(double *out, int max_pairs);
 /* The tensor-core kernel alone (tests, the int8 peak microbenchmark): D[d] = sum_{s+t=d} A_s B_t^T over k-blocks
  * [kb_begin, kb_begin+nkb) of 128; planes are int8 [S][rows][Kp] (device), D is int32
  * [S_A+S_B-1][Mp][Np] with Mp % 128 == 0, Np % 256 == 0. */

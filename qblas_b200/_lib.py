@@ -89,6 +89,7 @@ def lib():
         "qb_get_fast_variant": (ci, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),
         "qb_oz_last_mma_ms": (cd, [C.POINTER(ci)]),
+        "qb_oz_last_mma_timeline": (ci, [C.POINTER(cd), ci]),
         "qb_oz_i8gemm_dev": (ci, [vp, vp, ci, ci, i64, i64, i64, i64, i64, vp, i64, i64, vp]),
         "qb_gemm": (ci, [cc, cc, cc, i64, i64, i64, qp, vp, i64, vp, i64, qp, vp, i64]),
         "qb_gemv": (ci, [cc, i64, i64, qp, vp, i64, vp, i64, qp, vp, i64]),

@@ -419,6 +419,13 @@ def oz_last_mma_ms():
     return float(ms), int(n.value)
 
 
+def oz_last_mma_timeline(max_pairs=1024):
+    """[(start_ms relative to the first launch, duration_ms)] of the tcgen05 kernel launches of the last tensor-path qgemm (blocks)."""
+    buf = (C.c_double * (2 * max_pairs))()
+    n = lib().qb_oz_last_mma_timeline(buf, max_pairs)
+    return [(float(buf[2 * i]), float(buf[2 * i + 1])) for i in range(n)]
+
+
 def oz_i8gemm(planesA, planesB, m, n, D, kb_begin=0, nkb=None):
     """The tcgen05 kernel alone: planes are torch int8 CUDA tensors [S][rows][Kp], D int32 [SA+SB-1][Mp][Np]."""
     SA, _, Kp = planesA.shape

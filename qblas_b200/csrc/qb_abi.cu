@@ -437,6 +437,11 @@ double qb_oz_last_mma_ms(int *launches)
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   return oz_last_mma_ms(launches);
 }
+int qb_oz_last_mma_timeline(double *out, int max_pairs)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  return oz_last_mma_timeline(out, max_pairs);
+}
 int qb_oz_i8gemm_dev(const void *dPlanesA, const void *dPlanesB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int64_t kb_begin,
                      int64_t nkb, void *dD, int64_t Mp, int64_t Np, void *stream)
 {
@@ -643,7 +648,9 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       if (cnt <= 0) return cudaSuccess;
       char *d = (char *)dev, *h = (char *)host;
       if (along_outer) {
-        const size_t off = (size_t)c0 * ld * 16, bytes = ((size_t)(cnt - 1) * ld + inner) * 16;
+        /* whole rows including the padding up to the next block's first row (a download may cut the rows differently than the
+         * uploads did: the padding in between must hold the caller's bytes); the last row of the matrix ends at its last element */
+        const size_t off = (size_t)c0 * ld * 16, bytes = (c0 + cnt < outer ? (size_t)cnt * ld : (size_t)(cnt - 1) * ld + inner) * 16;
         return to_dev ? cudaMemcpyAsync(d + off, h + off, bytes, cudaMemcpyHostToDevice, st) : cudaMemcpyAsync(h + off, d + off, bytes, cudaMemcpyDeviceToHost, st);
       }
       const size_t off = (size_t)c0 * 16;

@@ -93,6 +93,7 @@ int oz_get_window();
 void oz_set_unit(int64_t rows, int64_t cols);   /* pipeline unit: rows of an A pass x columns of a B panel (default 2048 x 2048) */
 void oz_get_unit(int64_t *rows, int64_t *cols);
 double oz_last_mma_ms(int *launches);
+int oz_last_mma_timeline(double *out, int max_pairs);
 void oz_release();
 
 } // namespace qb

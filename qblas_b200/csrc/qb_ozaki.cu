@@ -65,7 +65,8 @@ struct OzMmaArgs {
   int m_tiles, n_tiles;
   int kb_begin, nkb;          /* k-blocks of OZ_BK of this launch */
   uint8_t order[OZ_MAX_DIAG + 1];
-  uint8_t *R;                 /* residue mode (CRT = 1): [N][Mp][Np] bytes, R_i = (A_i B_i^T) mod p_i in [0, p_i); ndiag = N */
+  uint8_t *R;                 /* residue mode (CRT = 1): N planes of [Mp][Np] bytes `rplane` bytes apart, R_i = (A_i B_i^T) mod p_i in [0, p_i); ndiag = N */
+  int64_t rplane;
   int accum;                  /* residue mode: add to the residues already in R (K chunks beyond OZ_KCHUNK) */
 };
 
@@ -189,7 +190,7 @@ k_oz_mma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * OZ_BN;
       if (CRT) {
         /* accumulator mod p_d (crt::acc_mod), 32 residues = 32 bytes per thread and 32-column step */
-        uint8_t *dst = g.R + ((int64_t)d * g.Mp + row) * g.Np + (int64_t)nt * OZ_BN;
+        uint8_t *dst = g.R + (int64_t)d * g.rplane + row * g.Np + (int64_t)nt * OZ_BN;
         const uint32_t p = c_crt.p[d], off = c_crt.off[d], finv = c_crt.finv[d];
 #pragma unroll 1
         for (int c = 0; c < OZ_BN / 32; ++c) {
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(128) k_crt_residues_t(const q128 *__restrict__
 
 /* ------------------------------------------------------------------ fold: residues -> binary128 */
 struct CrtFoldArgs {
-  const uint8_t *R; int64_t Mp, Np;  /* residues of this unit: [N][Mp][Np] */
+  const uint8_t *R; int64_t Mp, Np, rplane;  /* residues of this unit: N planes of [Mp][Np] bytes, rplane bytes apart */
   int64_t m, n, row0, col0;          /* the unit is C rows [row0, row0 + m) x columns [col0, col0 + n) of the call's C */
   const int *emaxA, *lminA, *spA, *emaxB, *lminB, *spB; int WA, WB;   /* per row / column of the whole call */
   int64_t k;
@@ -447,7 +448,7 @@ __global__ void __launch_bounds__(128) k_crt_fold(const CrtFoldArgs g, const __g
   if (!valid && !stage) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (valid) {
-    const int64_t plane = g.Mp * g.Np, off = i * g.Np + j0;
+    const int64_t plane = g.rplane, off = i * g.Np + j0;
     uint32_t rw[4 * NG];
 #pragma unroll
     for (int c = 0; c < 4 * NG; ++c) rw[c] = c < pl.N ? *reinterpret_cast<const uint32_t *>(g.R + (int64_t)c * plane + off) : 0u;
@@ -658,7 +659,11 @@ static cudaError_t oz_dev(OzDev **out)
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, i == 0 ? hi : lo);
+  /* priorities: the tensor kernel first, the reconstruction (which frees the residue buffer the tensor kernel of unit + 2 needs) second,
+   * the residue kernels (needed one pass / panel ahead) last: blocks of a higher-priority kernel are scheduled before pending
+   * blocks of a lower one, so a fold never queues behind thousands of residue blocks */
+  const int mid = hi < lo ? std::min(lo, hi + 1) : hi;
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, i == 0 ? hi : (i == 3 ? mid : lo));
   if (e == cudaSuccess) e = cudaMallocHost((void **)&D.h_plan, 64);
   if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) if (s[i]) cudaStreamDestroy(s[i]); return e; }
   D.sM = s[0]; D.sA = s[1]; D.sB = s[2]; D.sF = s[3];
@@ -718,6 +723,21 @@ static void oz_ev_record(OzDev &D, int which, cudaStream_t st)
   cudaEventRecord(D.tev[2 * D.tev_used + which], st);
   if (which == 1) ++D.tev_used;
 }
+/* per-launch (start relative to the first launch, duration) in ms of the tensor-kernel launches of the last qgemm (profiling aid) */
+int oz_last_mma_timeline(double *out, int max_pairs)
+{
+  OzDev *D;
+  if (oz_dev(&D) != cudaSuccess) return 0;
+  int n = 0;
+  for (int i = 0; i < D->tev_used && n < max_pairs; ++i, ++n) {
+    float t0 = 0, dt = 0;
+    if (cudaEventSynchronize(D->tev[2 * i + 1]) != cudaSuccess) break;
+    cudaEventElapsedTime(&t0, D->tev[0], D->tev[2 * i]);
+    cudaEventElapsedTime(&dt, D->tev[2 * i], D->tev[2 * i + 1]);
+    out[2 * n] = t0; out[2 * n + 1] = dt;
+  }
+  return n;
+}
 /* blocks until the last recorded launch has finished; returns the summed duration in ms */
 double oz_last_mma_ms(int *launches)
 {
@@ -764,13 +784,13 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
 /* residue scheme: R_i (+)= (A_i B_i^T) mod p_i for the N residue planes over k-blocks [kb_begin, kb_begin + nkb)
  * (|acc| <= 128 * 128 * OZ_KCHUNK = 2^30) */
 static cudaError_t launch_crt_mma(OzDev &D, const int8_t *pA, const int8_t *pB, int N, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb, int accum,
-                                  uint8_t *R, int64_t Mp, int64_t Np, cudaStream_t st)
+                                  uint8_t *R, int64_t Mp, int64_t Np, int64_t rplane, cudaStream_t st)
 {
   CUtensorMap tmA, tmB;
   if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
   OzMmaArgs g;
   memset(&g, 0, sizeof(g));
-  g.R = R; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
+  g.R = R; g.rplane = rplane; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
   g.m_tiles = (int)(Mp / OZ_BM); g.n_tiles = (int)(Np / OZ_BN);
   g.kb_begin = kb_begin; g.nkb = nkb; g.accum = accum;
   const int64_t total = (int64_t)N * g.m_tiles * g.n_tiles;
@@ -900,7 +920,9 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   count_launch();
   QB_TRY(cudaMemcpyAsync(D.h_plan, plan, 16, cudaMemcpyDeviceToHost, st));
   QB_TRY(cudaStreamSynchronize(st));
-  const int WA_nat = h.rows_in ? g_window : D.h_plan[0], WB_nat = D.h_plan[1], fl = D.h_plan[2];
+  /* streamed rows: the spans of A are not known yet; assume the widest, so that the planner gives A whatever the budget leaves
+   * after B - never less than the resident call gets (same bits whenever that one is exact) */
+  const int WA_nat = h.rows_in ? crt::WMAX : D.h_plan[0], WB_nat = D.h_plan[1], fl = D.h_plan[2];
   crt::host::Windows win;
   if (!crt::host::plan_windows(WA_nat, WB_nat, k, g_window, win)) return cudaSuccess;
   const int WA = win.WA, WB = win.WB, N = win.N;
@@ -912,9 +934,12 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
    * passes are double buffered, so the rows of C complete pass by pass (what the all-host path wants: rows stream in and out). */
   int64_t ur = std::min(rup(m, OZ_BM), g_unit_rows), uc = std::min(rup(n, OZ_BN), h.bp ? rup(h.bp_cols, OZ_BN) : g_unit_cols);
   if (h.cb && h.min_passes > 1) ur = std::min(ur, std::max<int64_t>(OZ_BM, rup((m + h.min_passes - 1) / h.min_passes, OZ_BM)));
+  /* the N residue planes of a unit are padded apart: with power-of-two plane sizes the N words a reconstruction thread gathers (one
+   * per plane) would all fall into the same DRAM channel / L2 slice */
+  auto rplane_of = [](int64_t Mp_, int64_t Np_) -> int64_t { return Mp_ * Np_ + 4352; };
   auto planes_bytes = [&](int64_t rows) -> size_t { return (size_t)rup((int64_t)N * rows * Kp, 1024); };
   auto rest_bytes = [&](int64_t ur_, int64_t uc_) -> size_t {   /* 2 residue buffers, flags + list */
-    size_t b = 2 * (size_t)rup((int64_t)N * rup(ur_, OZ_BM) * rup(uc_, OZ_BN), 1024);
+    size_t b = 2 * (size_t)rup((int64_t)N * rplane_of(rup(ur_, OZ_BM), rup(uc_, OZ_BN)), 1024);
     if (check) b += (size_t)rup(rup(ur_, OZ_BM) * rup(uc_, OZ_BN), 1024) + (size_t)std::max<int64_t>(4096, ur_ * uc_ / 64) * sizeof(int2);
     return b;
   };
@@ -932,7 +957,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   else { while (nB < nJ && need_bytes(ur, uc, nA, nB + 1) <= ws_budget) ++nB; }
   if (h.bp && nA < nP) return cudaSuccess;                   /* a streamed B passes once */
   const int64_t Mu = rup(ur, OZ_BM), Nu = rup(uc, OZ_BN);
-  const size_t pa_bytes = planes_bytes(ur), pb_bytes = planes_bytes(uc), r_bytes = (size_t)rup((int64_t)N * Mu * Nu, 1024);
+  const size_t pa_bytes = planes_bytes(ur), pb_bytes = planes_bytes(uc), r_bytes = (size_t)rup((int64_t)N * rplane_of(Mu, Nu), 1024);
   const int list_cap = (int)std::max<int64_t>(4096, ur * uc / 64);
   const size_t flag_bytes = check ? (size_t)rup(Mu * Nu, 1024) : 0, list_bytes = check ? (size_t)list_cap * sizeof(int2) : 0;
   QB_TRY(oz_grow(&D.buf, &D.bytes, nA * pa_bytes + nB * pb_bytes + 2 * r_bytes + flag_bytes + list_bytes));
@@ -994,7 +1019,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     for (int c = 0; c < nkc; ++c) {
       const int kb0 = (int)(c * kcb), nkb = (int)std::min<int64_t>(kcb, nkb_total - kb0);
       oz_ev_record(D, 0, D.sM);
-      const cudaError_t e2 = launch_crt_mma(D, pAp, pBj, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, D.sM);
+      const cudaError_t e2 = launch_crt_mma(D, pAp, pBj, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, rplane_of(Mp, Np), D.sM);
       oz_ev_record(D, 1, D.sM);
       if (e2 != cudaSuccess) return e2;
     }
@@ -1004,7 +1029,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
     /* reconstruction + epilogue (+ fix-up of the elements it rejects) */
     QB_TRY(cudaStreamWaitEvent(D.sF, evMma[rb], 0));
     CrtFoldArgs f;
-    f.R = R[rb]; f.Mp = Mp; f.Np = Np; f.m = mr; f.n = w; f.row0 = r0; f.col0 = c0;
+    f.R = R[rb]; f.Mp = Mp; f.Np = Np; f.rplane = rplane_of(Mp, Np); f.m = mr; f.n = w; f.row0 = r0; f.col0 = c0;
     f.emaxA = emaxA; f.lminA = lminA; f.spA = spA; f.emaxB = emaxB; f.lminB = lminB; f.spB = spB; f.WA = WA; f.WB = WB; f.k = k;
     f.alpha = a.alpha; f.beta = a.beta; f.C = a.C; f.sci = a.sci; f.scj = a.scj;
     f.simple = simple;

@@ -158,7 +158,7 @@ def test_wide_exponent_ranges_stay_on_the_tensor_path_and_meet_the_contract(qb, 
 
 def test_cancelling_entries_under_a_capped_window_go_to_the_fixup(qb, oracle):
     """Rows whose large terms cancel exactly (+2^60 b, -2^60 b): what is left comes from small elements a capped window truncates; those
-    entries fail the acceptance test, are left to k_crt_fixup (window accumulator) and come out correctly rounded; alpha / beta epilogue
+    entries fail the acceptance test and are left to k_crt_fixup (window accumulator): inside the contract; alpha / beta epilogue
     included (C_in of a rejected entry must still be intact when the fix-up reads it)."""
     rng = np.random.default_rng(77)
     m, n, k = 128, 256, 512
@@ -171,15 +171,14 @@ def test_cancelling_entries_under_a_capped_window_go_to_the_fixup(qb, oracle):
     alpha, beta = quad.random_quads(rng, 2)
     got, st = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
     assert st["truncated"] & 3 and st["flagged"] >= 8 * n, st
-    idx = np.stack(np.meshgrid(np.arange(8), np.arange(n), indexing="ij"), axis=-1).reshape(-1, 2)
-    exact, _, klass = oracle.exact_dot_check("R", k, A, k, B, n, idx)
-    want = _epilogue(oracle, alpha, exact, beta, C0[:8 * n])
-    # the window accumulator drops less than k 2^-133 of the largest product: here the exact sum rounded once, bit for bit
-    assert (klass == 0).all() and quad.same_bits(got[:8 * n], want).all()
-    # and the whole matrix meets the contract through the epilogue-free path
-    got0, _ = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
-    _, ratio, _ = _check_contract(oracle, "R", m, n, k, A, k, B, n, got0)
-    assert (ratio <= 1.0).all()
+    # the fix-up's window accumulator keeps 192 bits below the largest product of the row (the cancelled +-2^60 b pair here), which leaves
+    # ~80 correct bits for sums 2^-90 of it: inside the contract, not bit-exact.  alpha / beta epilogue: applied to the same sums.
+    got0, st0 = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n)
+    exact, ratio, klass = _check_contract(oracle, "R", m, n, k, A, k, B, n, got0)
+    assert (klass == 0).all() and (ratio <= 1.0).all(), float(ratio.max())
+    assert ratio[:8 * n].max() < 1e-3                       # the fixed-up rows are far inside the bound
+    want = _epilogue(oracle, alpha, got0, beta, C0)          # same sums through the reference epilogue, bit for bit
+    assert quad.same_bits(got, want).all()
 
 
 def test_inf_nan_and_huge_spans_run_on_the_tensor_path(qb, oracle):
@@ -191,7 +190,7 @@ def test_inf_nan_and_huge_spans_run_on_the_tensor_path(qb, oracle):
     A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
     inf, nan = quad.from_double(np.array([np.inf]))[0], quad.from_double(np.array([np.nan]))[0]
     A[5] = inf                                   # row 0: +Inf (times finite non-zero)
-    A[2 * k + 7] = inf; A[2 * k + 8] = inf; A[2 * k + 8, 1] ^= np.uint64(1 << 63)     # row 2: +Inf and -Inf
+    A[2 * k + 7] = inf; A[2 * k + 8] = inf; A[2 * k + 8, 1] ^= np.uint64(1 << 63)     # row 2: +Inf and -Inf (NaN where the signs of b make them oppose)
     A[4 * k + 1] = nan                           # row 4: NaN
     B[9 * n + 3] = inf                           # column 3: Inf
     B[11 * n + 6] = quad.from_double(np.array([0.0]))[0]; A[7 * k + 11] = inf          # row 7, column 6: Inf * 0
@@ -201,7 +200,7 @@ def test_inf_nan_and_huge_spans_run_on_the_tensor_path(qb, oracle):
     exact, ratio, klass = _check_contract(oracle, "R", m, n, k, A, k, B, n, got)
     assert (ratio <= 1.0).all(), (st, np.argwhere(ratio > 1)[:5])
     kl = klass.reshape(m, n)
-    assert (kl[4] == 1).all() and (kl[2] == 1).all() and kl[7, 6] == 1 and (kl[:, 3] != 0).all() and (kl[0] != 0).all()
+    assert (kl[4] == 1).all() and (kl[2] != 0).all() and (kl[2] == 1).any() and kl[7, 6] == 1 and (kl[:, 3] != 0).all() and (kl[0] != 0).all()
     assert (kl[[1, 3, 5, 6, 8, 9] + list(range(10, m))][:, [0, 1, 2] + list(range(4, n))] == 0).all()
     fin = (klass == 0).reshape(m, n).copy(); fin[9] = False     # row 9 lost bits to its window: contract only; all others are exact sums
     assert quad.same_bits(got.reshape(m, n, 2)[fin], exact.reshape(m, n, 2)[fin]).all()
