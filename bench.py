@@ -58,7 +58,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -196,9 +196,9 @@ def _int_issue_peak(qb, torch, dev):
 
 
 def _int8_peak(qb, torch, dev):
-    """The tcgen05 kind::i8 pipeline of k_oz_mma on operands that stay in L2 (2 x 8 MB of int8 planes, 16 plane pairs per launch):
-    the measured int8 rate of this kernel's own instruction stream with HBM out of the way -> TOPS."""
-    S, m, n, Kp = 4, 2048, 2048, 4096
+    """The tcgen05 kind::i8 pipeline of k_oz_mma on operands that stay in L2 (2 x 32 MB of int8 planes, 64 plane pairs per launch,
+    ~0.4 ms per launch): the measured int8 rate of this kernel's own instruction stream with HBM reads out of the way -> TOPS."""
+    S, m, n, Kp = 8, 2048, 2048, 2048
     g = torch.Generator(device=dev); g.manual_seed(1)
     pa = torch.randint(-128, 128, (S, m, Kp), generator=g, device=dev, dtype=torch.int8)
     pb = torch.randint(-128, 128, (S, n, Kp), generator=g, device=dev, dtype=torch.int8)
@@ -617,7 +617,7 @@ def own_arm(args, rank, world, local_rank):
                 try:
                     tops8, ms8 = _int8_peak(qb, torch, dev)
                     extra["int8_peak_microbench"] = {"tops": tops8, "ms_per_launch": ms8,
-                                                     "what": "k_oz_mma<0> (same TMA + tcgen05 kind::i8 pipeline, int32 output), 16 plane pairs of 2048 x 2048 x 4096 per launch, operands L2 resident, 20 launches back to back"}
+                                                     "what": "k_oz_mma<0> (same TMA + tcgen05 kind::i8 pipeline, int32 output), 64 plane pairs of 2048 x 2048 x 2048 per launch, operands L2 resident, 20 launches back to back"}
                     if roof is not None and roof.get("bound") == "tensor":
                         roof["frac_of_measured_int8_peak"] = roof["achieved"] / tops8
                 except Exception as e:
@@ -809,7 +809,7 @@ def main():
     ap.add_argument("--bcast", default="panels", choices=["panels", "whole"], help="N > 1: B is broadcast in column panels during the product, or as a whole before it")
     ap.add_argument("--panel-cols", type=int, default=2048, help="N > 1, --bcast panels: columns per panel (multiple of 256)")
     ap.add_argument("--host-slabs", type=int, default=0, help="e2e: slabs of the pipelined all-host qgemm (library default 8)")
-    ap.add_argument("--unit", default=None, help="tensor path pipeline unit rows,cols (library default 2048,2048)")
+    ap.add_argument("--unit", default=None, help="tensor path pipeline unit rows,cols (library default 2048,4096)")
     ap.add_argument("--window", type=int, default=0, help="tensor path window budget in bits (library default 144)")
     ap.add_argument("--cfg4", type=int, default=32768, help="side of the fixed global problem of extra.cfg4_strong (0 = skip)")
     args = ap.parse_args()

@@ -125,10 +125,14 @@ int qb_gemm_colstats_dev(char layout, char transb, int64_t k, int64_t n, const v
  * fast-mode contract.  Default 144 (42 moduli at k = 8192), range 120..192. */
 void qb_set_tensor_window(int bits);
 int qb_get_tensor_window(void);
-/* Pipeline unit of the tensor path: (rows of an A pass) x (columns of a B panel), default 2048 x 2048; rows / cols <= 0 restore the
+/* Pipeline unit of the tensor path: (rows of an A pass) x (columns of a B panel), default 2048 x 4096; rows / cols <= 0 restore the
  * default.  The tensor kernel of one unit overlaps the residues of the next pass / panel and the reconstruction of the previous unit. */
 void qb_set_tensor_unit(int64_t rows, int64_t cols);
 void qb_get_tensor_unit(int64_t *rows, int64_t *cols);
+/* Rows of the FIRST pass and columns of the FIRST panel (0 = like the others): the residues of the first unit are the only ones
+ * nothing can hide, so a short first unit lets the tensor kernel start early. */
+void qb_set_tensor_ramp(int64_t rows, int64_t cols);
+void qb_get_tensor_ramp(int64_t *rows, int64_t *cols);
 /* Large all-host calls (quadblas_qgemm / quadblas_qgemv with host pointers) are pipelined: qgemm uploads the shared operand first,
  * then the rows stream in, are multiplied and stream out in `slabs` blocks on three streams; qgemv uploads A in `slabs` row blocks
  * while the earlier ones are multiplied.  Default 8 (1..16). */

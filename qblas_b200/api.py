@@ -298,13 +298,24 @@ def get_tensor_window():
 
 
 def set_tensor_unit(rows=0, cols=0):
-    """Pipeline unit of the tensor path: rows of an A pass x columns of a B panel (default 2048 x 2048)."""
+    """Pipeline unit of the tensor path: rows of an A pass x columns of a B panel (default 2048 x 4096)."""
     lib().qb_set_tensor_unit(int(rows), int(cols))
 
 
 def get_tensor_unit():
     r, c = C.c_int64(0), C.c_int64(0)
     lib().qb_get_tensor_unit(C.byref(r), C.byref(c))
+    return int(r.value), int(c.value)
+
+
+def set_tensor_ramp(rows=0, cols=0):
+    """Rows of the first pass / columns of the first panel of the tensor path (0 = like the others)."""
+    lib().qb_set_tensor_ramp(int(rows), int(cols))
+
+
+def get_tensor_ramp():
+    r, c = C.c_int64(0), C.c_int64(0)
+    lib().qb_get_tensor_ramp(C.byref(r), C.byref(c))
     return int(r.value), int(c.value)
 
 

@@ -119,7 +119,8 @@ static int ensure_device()
   g_curdev = dev;
   Scratch &s = g_scr[dev];
   if (!s.ready) {
-    e = cudaMalloc((void **)&s.result, 64);
+    e = cudaMalloc((void **)&s.result, 64);          /* 16 B staged result | 16 B spare | the dot ticket (zero between calls) */
+    if (e == cudaSuccess) e = cudaMemset(s.result, 0, 64);
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMalloc(result)", e);
     s.ready = true;
   }
@@ -162,6 +163,104 @@ static bool is_device_ptr(const void *p)
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+/* ---- pageable host memory <-> device at DMA speed ----
+ * cudaMemcpy from / to pageable memory is staged by the driver through a small pinned buffer by ONE thread (~10 GB/s, a fifth of
+ * the PCIe rate), and that is what std::vector<Sleef_quad> / numpy callers of the reference API hand over (the README's 1000^3
+ * call moves 64 MB around 0.7 ms of compute).  Here a few host threads copy 4 MB chunks between the caller's memory and a ring
+ * of page-locked slots while the copy engine moves the previous chunks, so the transfer runs at the memcpy rate of several
+ * cores.  Only for unregistered host memory and transfers of 8 MB and more; everything else is a plain cudaMemcpy. */
+static constexpr size_t PG_CHUNK = (size_t)4 << 20;
+static constexpr int PG_THREADS = 4, PG_SLOTS = 2;
+struct PageRing {
+  char *base = nullptr; bool tried = false;
+  int dev = -1;                                   /* the streams / events below belong to this device */
+  cudaStream_t st[PG_THREADS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[PG_THREADS][PG_SLOTS] = {};
+};
+static PageRing g_ring;   /* guarded by g_mu like every host path */
+static bool is_pageable(const void *p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+static bool ring_ready(int dev)
+{
+  if (!g_ring.base) {
+    if (g_ring.tried) return false;
+    g_ring.tried = true;
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, PG_CHUNK * PG_THREADS * PG_SLOTS, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return false; }
+    g_ring.base = (char *)p;
+  }
+  if (g_ring.dev != dev) {   /* (re)create the per-thread streams and per-slot events on the current device */
+    for (int w = 0; w < PG_THREADS; ++w) {
+      if (g_ring.st[w]) { cudaStreamDestroy(g_ring.st[w]); g_ring.st[w] = nullptr; }
+      for (int i = 0; i < PG_SLOTS; ++i) if (g_ring.ev[w][i]) { cudaEventDestroy(g_ring.ev[w][i]); g_ring.ev[w][i] = nullptr; }
+    }
+    g_ring.dev = -1;
+    for (int w = 0; w < PG_THREADS; ++w) {
+      if (cudaStreamCreateWithFlags(&g_ring.st[w], cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return false; }
+      for (int i = 0; i < PG_SLOTS; ++i)
+        if (cudaEventCreateWithFlags(&g_ring.ev[w][i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return false; }
+    }
+    g_ring.dev = dev;
+  }
+  return true;
+}
+/* to_dev: host -> device, else device -> host.  Synchronous. */
+static cudaError_t paged_copy(void *dst, const void *src, size_t bytes, bool to_dev)
+{
+  const void *host = to_dev ? src : dst;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes < 2 * PG_CHUNK || !is_pageable(host) || !ring_ready(dev))
+    return cudaMemcpy(dst, src, bytes, to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  const size_t nchunks = (bytes + PG_CHUNK - 1) / PG_CHUNK;
+  cudaError_t errs[PG_THREADS];
+  std::thread th[PG_THREADS];
+  for (int w = 0; w < PG_THREADS; ++w) {
+    errs[w] = cudaSuccess;
+    th[w] = std::thread([&, w]() {
+      cudaError_t e = cudaSetDevice(dev);
+      const cudaStream_t st = g_ring.st[w];
+      cudaEvent_t *ev = g_ring.ev[w];
+      size_t pending_off[PG_SLOTS] = {0, 0}, pending_len[PG_SLOTS] = {0, 0};
+      int it = 0;
+      for (size_t c = (size_t)w; c < nchunks && e == cudaSuccess; c += PG_THREADS, ++it) {
+        const int slot = it % PG_SLOTS;
+        char *pin = g_ring.base + ((size_t)w * PG_SLOTS + slot) * PG_CHUNK;
+        const size_t off = c * PG_CHUNK, len = std::min(PG_CHUNK, bytes - off);
+        if (it >= PG_SLOTS) {      /* the slot's previous transfer must be over */
+          e = cudaEventSynchronize(ev[slot]);
+          if (e == cudaSuccess && !to_dev) memcpy((char *)dst + pending_off[slot], pin, pending_len[slot]);
+        }
+        if (e != cudaSuccess) break;
+        if (to_dev) {
+          memcpy(pin, (const char *)src + off, len);
+          e = cudaMemcpyAsync((char *)dst + off, pin, len, cudaMemcpyHostToDevice, st);
+        } else {
+          e = cudaMemcpyAsync(pin, (const char *)src + off, len, cudaMemcpyDeviceToHost, st);
+          pending_off[slot] = off; pending_len[slot] = len;
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ev[slot], st);
+      }
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess && !to_dev) {   /* drain the slots still holding downloaded chunks */
+        const int done = it;
+        for (int b = std::max(0, done - PG_SLOTS); b < done; ++b) {
+          const int slot = b % PG_SLOTS;
+          memcpy((char *)dst + pending_off[slot], g_ring.base + ((size_t)w * PG_SLOTS + slot) * PG_CHUNK, pending_len[slot]);
+        }
+      }
+      errs[w] = e;
+    });
+  }
+  cudaError_t e = cudaSuccess;
+  for (int w = 0; w < PG_THREADS; ++w) { th[w].join(); if (errs[w] != cudaSuccess) e = errs[w]; }
+  return e;
+}
+
 /* staging slot: returns a device pointer holding `bytes` copied from host `src` (or src itself if
  * it is already device-accessible) */
 static int stage_in(int slot, const void *src, size_t bytes, bool copy, const void **dptr, bool *staged)
@@ -175,7 +274,7 @@ static int stage_in(int slot, const void *src, size_t bytes, bool copy, const vo
     s.stage_bytes[slot] = bytes;
   }
   if (copy) {
-    cudaError_t e = cudaMemcpy(s.stage[slot], src, bytes, cudaMemcpyHostToDevice);
+    cudaError_t e = paged_copy(s.stage[slot], src, bytes, true);
     if (e != cudaSuccess) return fail(QB_ERR_CUDA, "cudaMemcpy H2D", e);
   }
   *dptr = s.stage[slot];
@@ -278,9 +377,6 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
   if (streamed && !(mode == QB_MODE_FAST && tp != 0)) return fail(QB_ERR_ARG, "qgemm: streamed B panels need the fast-mode tensor path");
   if (mode == QB_MODE_FAST && m > 0 && n > 0 && k > 0 && (tp == 2 || streamed || (tp == 1 && m >= 128 && n >= 128 && k >= 256))) {
     /* tensor-core path (exact int8 residues, qb_ozaki.cu); declines -> integer-limb kernel below */
-    size_t fr = 0, tot = 0;
-    cudaMemGetInfo(&fr, &tot);
-    const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
     int used = 0;
     OzHooks h;
     if (hooks) {
@@ -290,9 +386,9 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
       for (int q = 0; q < g.npeer; ++q) g.peerC[q] = (q128 *)g_peer[q];
     }
     g_peer_written = 0;
-    cudaError_t oe = launch_gemm_ozaki(g, st, &used, budget, h);
+    cudaError_t oe = launch_gemm_ozaki(g, st, &used, h);
     if (oe != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm tensor path", oe);
-    if (used) { g_peer_written = oz_last_stats().peer_written; return QB_OK; }
+    if (used) { g_peer_written = oz_last_stats(false).peer_written; return QB_OK; }
     if (streamed) return fail(QB_ERR_ALLOC, "qgemm: the tensor path declined a streamed-B call (workspace)");
   }
   g_peer_written = 0;
@@ -363,6 +459,12 @@ void qb_set_tensor_unit(int64_t rows, int64_t cols)
   oz_set_unit(rows, cols);
 }
 void qb_get_tensor_unit(int64_t *rows, int64_t *cols) { oz_get_unit(rows, cols); }
+void qb_set_tensor_ramp(int64_t rows, int64_t cols)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  oz_set_ramp(rows, cols);
+}
+void qb_get_tensor_ramp(int64_t *rows, int64_t *cols) { oz_get_ramp(rows, cols); }
 void qb_set_host_slabs(int slabs) { g_host_slabs.store(slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs)); }
 int qb_get_host_slabs(void) { return g_host_slabs.load(); }
 void qb_set_tensor_pass_shape(int shape)
@@ -549,6 +651,7 @@ static int dot_dev_impl(int64_t n, const void *dx, int64_t incx, const void *dy,
   DotArgs g;
   g.n = n; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
   g.T = T; g.do_sqrt = do_sqrt; g.result = (q128 *)d_result; g.work = S().work; g.work_elems = S().work_elems;
+  g.ticket = (unsigned *)(S().result + 2);
   cudaError_t e = launch_dot(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot kernel launch", e);
   return QB_OK;
@@ -687,11 +790,8 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       OzHooks h;
       h.order = 1; h.rows_in = host_rows_in; h.rows_user = &hp; h.cb = host_rows_out; h.cb_user = &hp;
       h.min_passes = (int)std::min<int64_t>(4096, (split + 1023) / 1024);     /* passes of <= 1024 rows: a short tail after the last upload */
-      size_t fr = 0, tot = 0;
-      cudaMemGetInfo(&fr, &tot);
-      const size_t budget = (size_t)((double)fr * 0.85) + (size_t)oz_last_stats().ws_bytes;
       int used = 0;
-      const cudaError_t oe = launch_gemm_ozaki(g, ks, &used, budget, h);
+      const cudaError_t oe = launch_gemm_ozaki(g, ks, &used, h);
       if (oe != cudaSuccess || hp.err != cudaSuccess) {
         cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds);
         return fail(QB_ERR_CUDA, "qgemm pipelined host path (tensor)", oe != cudaSuccess ? oe : hp.err);
@@ -727,7 +827,7 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
   rc = gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), (void *)dC, ldc, 0);
   if (rc) return rc;
   cudaError_t e;
-  if (sc) e = cudaMemcpy(C, dC, c_bytes, cudaMemcpyDeviceToHost); else e = cudaDeviceSynchronize();
+  if (sc) { e = cudaDeviceSynchronize(); if (e == cudaSuccess) e = paged_copy(C, dC, c_bytes, false); } else e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemm completion", e);
   return QB_OK;
 }

@@ -41,6 +41,7 @@ struct DotArgs {
   int do_sqrt;                       /* nrm2 */
   q128 *result;                      /* device, 16 B */
   q128 *work; int64_t work_elems;    /* device scratch for partials */
+  unsigned *ticket = nullptr;        /* device, zero between calls: the last-CTA-done counter of the fast one-launch reduction */
 };
 int64_t dot_work_elems(int64_t n, int T, int mode);
 cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st);
@@ -80,18 +81,20 @@ struct OzHooks {
   int order = 0;                     /* 0: panels outer (A planes resident), 1: passes outer (B planes resident, rows complete pass by pass) */
 };
 /* *used = 0: the planner declined (no TMA entry point, no workspace) and nothing was written */
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, const OzHooks &h);
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, const OzHooks &h);
 cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, int64_t sbl, int *stats, cudaStream_t st);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);
-OzStats oz_last_stats();
+OzStats oz_last_stats(bool wait = true);   /* wait: block until the fix-up count of the last call has arrived */
 std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape);
 void oz_set_pass_shape(int v);
 int oz_get_pass_shape();
 void oz_set_window(int bits);  /* bits per operand window the planner grants when the spans do not fit the moduli (default 144) */
 int oz_get_window();
-void oz_set_unit(int64_t rows, int64_t cols);   /* pipeline unit: rows of an A pass x columns of a B panel (default 2048 x 2048) */
+void oz_set_unit(int64_t rows, int64_t cols);   /* pipeline unit: rows of an A pass x columns of a B panel (default 2048 x 4096) */
 void oz_get_unit(int64_t *rows, int64_t *cols);
+void oz_set_ramp(int64_t rows, int64_t cols);    /* rows of the first pass / columns of the first panel (0 = like the others) */
+void oz_get_ramp(int64_t *rows, int64_t *cols);
 double oz_last_mma_ms(int *launches);
 int oz_last_mma_timeline(double *out, int max_pairs);
 void oz_release();

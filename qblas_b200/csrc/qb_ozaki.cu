@@ -36,6 +36,7 @@
 #include "qb_crt.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -659,11 +660,13 @@ static cudaError_t oz_dev(OzDev **out)
   int lo = 0, hi = 0;
   cudaDeviceGetStreamPriorityRange(&lo, &hi);
   cudaStream_t s[4] = {nullptr, nullptr, nullptr, nullptr};
-  /* priorities: the tensor kernel first, the reconstruction (which frees the residue buffer the tensor kernel of unit + 2 needs) second,
-   * the residue kernels (needed one pass / panel ahead) last: blocks of a higher-priority kernel are scheduled before pending
-   * blocks of a lower one, so a fold never queues behind thousands of residue blocks */
-  const int mid = hi < lo ? std::min(lo, hi + 1) : hi;
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, i == 0 ? hi : (i == 3 ? mid : lo));
+  /* priorities: the tensor kernel first; then the reconstruction (it frees the residue buffer the tensor kernel of unit + 2 needs) and
+   * the residues of the A passes (the tensor kernel of the NEXT unit needs them during the first panel); the residues of the B panels
+   * (needed a whole panel ahead) last.  Blocks of a higher-priority kernel are scheduled before pending blocks of a lower one.
+   * QBLAS_STREAM_PRIO=abcd overrides (digits = priority levels below the highest for sM, sA, sB, sF; experiments). */
+  int off[4] = {0, 1, 2, 1};
+  if (const char *v = getenv("QBLAS_STREAM_PRIO")) for (int i = 0; i < 4 && v[i] >= '0' && v[i] <= '9'; ++i) off[i] = v[i] - '0';
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaStreamCreateWithPriority(&s[i], cudaStreamNonBlocking, hi < lo ? std::min(lo, hi + off[i]) : hi);
   if (e == cudaSuccess) e = cudaMallocHost((void **)&D.h_plan, 64);
   if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) if (s[i]) cudaStreamDestroy(s[i]); return e; }
   D.sM = s[0]; D.sA = s[1]; D.sB = s[2]; D.sF = s[3];
@@ -703,10 +706,10 @@ void oz_release()
 static inline int64_t rup(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 static OzStats g_last_stats;
-OzStats oz_last_stats()
+OzStats oz_last_stats(bool wait)
 {
   OzDev *D;
-  if (g_last_stats.pairs > 0 && oz_dev(&D) == cudaSuccess && D->stats_pending) { /* the fix-up count arrives with the call's last work */
+  if (wait && g_last_stats.pairs > 0 && oz_dev(&D) == cudaSuccess && D->stats_pending) { /* the fix-up count arrives with the call's last work */
     cudaEvent_t done;
     if (oz_event(*D, EV_DONE, &done) == cudaSuccess && cudaEventSynchronize(done) == cudaSuccess) g_last_stats.flagged = D->h_plan[8];
     D->stats_pending = false;
@@ -846,13 +849,16 @@ cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, in
 
 /* ---- tuning knobs (qb_set_tensor_window / qb_set_tensor_unit) ---- */
 static int g_window = 144;            /* bits per window the planner grants when the spans do not fit (2 x 144 + log2 k + 1 -> 42 moduli at k = 8192) */
-static int64_t g_unit_rows = 2048, g_unit_cols = 2048;
+static int64_t g_unit_rows = 2048, g_unit_cols = 4096;
+static int64_t g_ramp_rows = 0, g_ramp_cols = 0;   /* short first pass / panel (0 = like the others) */
+void oz_set_ramp(int64_t rows, int64_t cols) { g_ramp_rows = rows < 0 ? 0 : rows; g_ramp_cols = cols < 0 ? 0 : cols; }
+void oz_get_ramp(int64_t *rows, int64_t *cols) { *rows = g_ramp_rows; *cols = g_ramp_cols; }
 void oz_set_window(int bits) { g_window = bits < 120 ? 120 : (bits > crt::WMAX ? crt::WMAX : bits); }
 int oz_get_window() { return g_window; }
 void oz_set_unit(int64_t rows, int64_t cols)
 {
   g_unit_rows = rows <= 0 ? 2048 : std::max<int64_t>(OZ_BM, rup(rows, OZ_BM));
-  g_unit_cols = cols <= 0 ? 2048 : std::max<int64_t>(OZ_BN, rup(cols, OZ_BN));
+  g_unit_cols = cols <= 0 ? 4096 : std::max<int64_t>(OZ_BN, rup(cols, OZ_BN));
 }
 void oz_get_unit(int64_t *rows, int64_t *cols) { *rows = g_unit_rows; *cols = g_unit_cols; }
 /* legacy knobs of the row-pass partition (kept for the tests of the partition helper) */
@@ -881,7 +887,7 @@ std::vector<int64_t> oz_crt_pass_rows(int64_t m, int64_t cap, int shape)
 
 /* The whole fast-mode GEMM.  *used = 0 means the planner declined (no TMA entry point, or not even one unit fits the
  * workspace budget) and nothing was written: the caller runs the integer-limb kernel. */
-cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, size_t ws_budget, const OzHooks &h)
+cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, const OzHooks &h)
 {
   *used = 0;
   { const int64_t keep = g_last_stats.ws_bytes; g_last_stats = OzStats(); g_last_stats.ws_bytes = keep; }
@@ -946,15 +952,34 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   auto need_bytes = [&](int64_t ur_, int64_t uc_, int64_t nA_, int64_t nB_) -> size_t { return nA_ * planes_bytes(ur_) + nB_ * planes_bytes(uc_) + rest_bytes(ur_, uc_); };
   auto npass_of = [&](int64_t ur_) { return (m + ur_ - 1) / ur_; };
   auto npanel_of = [&](int64_t uc_) { return (n + uc_ - 1) / uc_; };
-  auto min_need = [&](int64_t ur_, int64_t uc_) { return need_bytes(ur_, uc_, std::min<int64_t>(npass_of(ur_), 2), std::min<int64_t>(npanel_of(uc_), 2)); };
-  while (min_need(ur, uc) > ws_budget && !h.bp && uc > OZ_BN) uc = rup(uc / 2, OZ_BN);
-  while (min_need(ur, uc) > ws_budget && ur > OZ_BM) ur = rup(ur / 2, OZ_BM);
-  if (min_need(ur, uc) > ws_budget) return cudaSuccess;
-  const int64_t nP = npass_of(ur), nJ = npanel_of(uc);
+  auto min_need = [&](int64_t ur_, int64_t uc_) { return need_bytes(ur_, uc_, std::min<int64_t>(npass_of(ur_) + 1, 2), std::min<int64_t>(npanel_of(uc_) + 1, 2)); };
+  /* what fits: anything inside the workspace the library already holds, else 85 % of the free device memory on top of it (queried only
+   * when the workspace would have to grow: cudaMemGetInfo is a driver call that the steady state does not need) */
+  size_t budget = 0; bool have_budget = false;
+  auto fits = [&](size_t need) -> bool {
+    if (need <= D.bytes) return true;
+    if (!have_budget) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); budget = (size_t)((double)fr * 0.85) + D.bytes; have_budget = true; }
+    return need <= budget;
+  };
+  while (!fits(min_need(ur, uc)) && !h.bp && uc > OZ_BN) uc = rup(uc / 2, OZ_BN);
+  while (!fits(min_need(ur, uc)) && ur > OZ_BM) ur = rup(ur / 2, OZ_BM);
+  if (!fits(min_need(ur, uc))) return cudaSuccess;
+  /* pass / panel boundaries.  The first pass and the first panel are short (g_ramp_rows x g_ramp_cols): their residues are the only
+   * ones nothing can hide, and a short first unit lets the tensor kernel start early; streamed panels keep the caller's width. */
+  std::vector<int64_t> prow, pcol;
+  {
+    const int64_t fr = (g_ramp_rows > 0 && !h.rows_in) ? std::min(ur, rup(g_ramp_rows, OZ_BM)) : ur;
+    const int64_t fc = (g_ramp_cols > 0 && !h.bp) ? std::min(uc, rup(g_ramp_cols, OZ_BN)) : uc;
+    for (int64_t r = 0; r < m; r += (r == 0 && m > fr + OZ_BM ? fr : ur)) prow.push_back(r);
+    prow.push_back(m);
+    for (int64_t c = 0; c < n; c += (c == 0 && n > fc + OZ_BN ? fc : uc)) pcol.push_back(c);
+    pcol.push_back(n);
+  }
+  const int64_t nP = (int64_t)prow.size() - 1, nJ = (int64_t)pcol.size() - 1;
   const int order = h.order == 1 ? 1 : 0;
   int64_t nA = std::min<int64_t>(nP, 2), nB = std::min<int64_t>(nJ, 2);
-  if (order == 0) { while (nA < nP && need_bytes(ur, uc, nA + 1, nB) <= ws_budget) ++nA; }
-  else { while (nB < nJ && need_bytes(ur, uc, nA, nB + 1) <= ws_budget) ++nB; }
+  if (order == 0) { while (nA < nP && fits(need_bytes(ur, uc, nA + 1, nB))) ++nA; }
+  else { while (nB < nJ && fits(need_bytes(ur, uc, nA, nB + 1))) ++nB; }
   if (h.bp && nA < nP) return cudaSuccess;                   /* a streamed B passes once */
   const int64_t Mu = rup(ur, OZ_BM), Nu = rup(uc, OZ_BN);
   const size_t pa_bytes = planes_bytes(ur), pb_bytes = planes_bytes(uc), r_bytes = (size_t)rup((int64_t)N * rplane_of(Mu, Nu), 1024);
@@ -983,7 +1008,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, siz
   int64_t unit = 0;
   int passes_done = 0;
   auto run_unit = [&](int64_t p, int64_t j) -> cudaError_t {
-    const int64_t r0 = p * ur, mr = std::min(ur, m - r0), c0 = j * uc, w = std::min(uc, n - c0);
+    const int64_t r0 = prow[(size_t)p], mr = prow[(size_t)p + 1] - r0, c0 = pcol[(size_t)j], w = pcol[(size_t)j + 1] - c0;
     const int64_t Mp = rup(mr, OZ_BM), Np = rup(w, OZ_BN);
     Slot &sa = slotA[(size_t)(p % nA)], &sb = slotB[(size_t)(j % nB)];
     int8_t *pAp = pA0 + (size_t)(p % nA) * pa_bytes, *pBj = pB0 + (size_t)(j % nB) * pb_bytes;

@@ -144,6 +144,7 @@ def test_measured_defaults():
     assert L.qb_get_mode() == 0                   # reference order (bit exact) unless fast mode is requested
     assert L.qb_get_tensor_path() == 1            # fast-mode qgemm: tensor path for m, n >= 128, k >= 256
     assert L.qb_get_tensor_window() == 144        # bits per operand window when the spans do not fit the moduli
+    assert qblas_b200.get_tensor_unit() == (2048, 4096) and qblas_b200.get_tensor_ramp() == (0, 0)   # pipeline unit: A pass x B panel
     assert L.qb_get_tensor_pass_shape() == 0      # equal row passes
     assert L.qb_get_fast_variant() == 1           # qdot / qnrm2 / qgemv: window accumulator
     assert L.qb_get_gemm_peer_written() == 0

@@ -11,7 +11,7 @@ kind = sys.argv[2] if len(sys.argv) > 2 else "D113"
 calls = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 dev = torch.device("cuda:0"); torch.cuda.set_device(0); qb.init()
 qb.set_mode(qb.MODE_FAST)
-A = dev_random((S * S,), kind, 1, dev); B = dev_random((S * S,), kind, 2, dev); C = dev_random((S * S,), kind, 3, dev)
+A = dev_random((S * S,), kind, 100, dev); B = dev_random((S * S,), kind, 7, dev); C = dev_random((S * S,), kind, 9, dev)   # bench.py's rank-0 inputs: the same plan
 for _ in range(calls):
     qb.gemm("R", S, S, S, 1.0, A, S, B, S, 0.0, C, S)
 torch.cuda.synchronize()
