@@ -133,6 +133,11 @@ void qb_get_tensor_unit(int64_t *rows, int64_t *cols);
  * nothing can hide, so a short first unit lets the tensor kernel start early. */
 void qb_set_tensor_ramp(int64_t rows, int64_t cols);
 void qb_get_tensor_ramp(int64_t *rows, int64_t *cols);
+/* Workspace of the tensor path (residue planes of the resident operand + double-buffered panels and residues): by default up to 85 % of
+ * the free device memory, grow-only.  A limit > 0 caps it: the planner then keeps fewer passes / panels resident and sweeps the product
+ * in blocks (the residues of the non-resident operand are recomputed per block), or shrinks the units; 0 restores the default. */
+void qb_set_tensor_workspace_limit(size_t bytes);
+size_t qb_get_tensor_workspace_limit(void);
 /* Large all-host calls (quadblas_qgemm / quadblas_qgemv with host pointers) are pipelined: qgemm uploads the shared operand first,
  * then the rows stream in, are multiplied and stream out in `slabs` blocks on three streams; qgemv uploads A in `slabs` row blocks
  * while the earlier ones are multiplied.  Default 8 (1..16). */

@@ -74,6 +74,8 @@ def lib():
         "qb_get_tensor_unit": (None, [C.POINTER(i64), C.POINTER(i64)]),
         "qb_set_tensor_ramp": (None, [i64, i64]),
         "qb_get_tensor_ramp": (None, [C.POINTER(i64), C.POINTER(i64)]),
+        "qb_set_tensor_workspace_limit": (None, [C.c_size_t]),
+        "qb_get_tensor_workspace_limit": (C.c_size_t, []),
         "qb_dot_kernel": (ci, [i64, vp, vp, qp]),
         "qb_peer_alloc": (vp, [C.c_size_t]),
         "qb_peer_free": (None, [vp]),

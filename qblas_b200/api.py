@@ -319,6 +319,11 @@ def get_tensor_ramp():
     return int(r.value), int(c.value)
 
 
+def set_tensor_workspace_limit(nbytes=0):
+    """Cap of the tensor path's workspace in bytes (0 = 85 % of the free device memory)."""
+    lib().qb_set_tensor_workspace_limit(int(nbytes))
+
+
 def dot_kernel(n, x, y):
     """QuadBLAS::dot_kernel_vectorized (level1.hpp:14-35) on host arrays: the two-lane reference kernel whatever the mode / T."""
     r = QbQuad()

@@ -465,6 +465,12 @@ void qb_set_tensor_ramp(int64_t rows, int64_t cols)
   oz_set_ramp(rows, cols);
 }
 void qb_get_tensor_ramp(int64_t *rows, int64_t *cols) { oz_get_ramp(rows, cols); }
+void qb_set_tensor_workspace_limit(size_t bytes)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  oz_set_ws_limit(bytes);
+}
+size_t qb_get_tensor_workspace_limit(void) { return oz_get_ws_limit(); }
 void qb_set_host_slabs(int slabs) { g_host_slabs.store(slabs < 1 ? 1 : (slabs > 16 ? 16 : slabs)); }
 int qb_get_host_slabs(void) { return g_host_slabs.load(); }
 void qb_set_tensor_pass_shape(int shape)

@@ -95,6 +95,8 @@ void oz_set_unit(int64_t rows, int64_t cols);   /* pipeline unit: rows of an A p
 void oz_get_unit(int64_t *rows, int64_t *cols);
 void oz_set_ramp(int64_t rows, int64_t cols);    /* rows of the first pass / columns of the first panel (0 = like the others) */
 void oz_get_ramp(int64_t *rows, int64_t *cols);
+void oz_set_ws_limit(size_t bytes);              /* cap of the tensor path's workspace (0 = 85 % of the free device memory) */
+size_t oz_get_ws_limit();
 double oz_last_mma_ms(int *launches);
 int oz_last_mma_timeline(double *out, int max_pairs);
 void oz_release();

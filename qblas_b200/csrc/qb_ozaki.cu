@@ -851,6 +851,9 @@ cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, in
 static int g_window = 144;            /* bits per window the planner grants when the spans do not fit (2 x 144 + log2 k + 1 -> 42 moduli at k = 8192) */
 static int64_t g_unit_rows = 2048, g_unit_cols = 4096;
 static int64_t g_ramp_rows = 0, g_ramp_cols = 0;   /* short first pass / panel (0 = like the others) */
+static size_t g_ws_limit = 0;                       /* bytes the workspace may take (0 = 85 % of the free device memory) */
+void oz_set_ws_limit(size_t bytes) { g_ws_limit = bytes; }
+size_t oz_get_ws_limit() { return g_ws_limit; }
 void oz_set_ramp(int64_t rows, int64_t cols) { g_ramp_rows = rows < 0 ? 0 : rows; g_ramp_cols = cols < 0 ? 0 : cols; }
 void oz_get_ramp(int64_t *rows, int64_t *cols) { *rows = g_ramp_rows; *cols = g_ramp_cols; }
 void oz_set_window(int bits) { g_window = bits < 120 ? 120 : (bits > crt::WMAX ? crt::WMAX : bits); }
@@ -957,6 +960,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, con
    * when the workspace would have to grow: cudaMemGetInfo is a driver call that the steady state does not need) */
   size_t budget = 0; bool have_budget = false;
   auto fits = [&](size_t need) -> bool {
+    if (g_ws_limit) return need <= g_ws_limit;     /* qb_set_tensor_workspace_limit: an explicit cap (tests of the block loops, shared GPUs) */
     if (need <= D.bytes) return true;
     if (!have_budget) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); budget = (size_t)((double)fr * 0.85) + D.bytes; have_budget = true; }
     return need <= budget;

@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 def _defaults(qb):
     yield
     qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO); qb.set_tensor_unit(0, 0); qb.set_tensor_window(144)
+    qb.set_tensor_workspace_limit(0); qb.set_tensor_ramp(0, 0)
     qb.set_gemm_pass_callback(None); qb.set_gemm_peer_outputs(None); qb.set_gemm_b_panels(None)
 
 
@@ -231,6 +232,54 @@ def test_units_passes_panels_and_epilogue(qb, oracle, unit):
         s = exact_matmul_rounded(A[i * lda:(i + 1) * lda], lda, B, ldb, 1, n, k, "R")
         want = _epilogue(oracle, alpha, s, beta, C0[i * ldc:i * ldc + n])
         assert quad.same_bits(got[i * ldc:i * ldc + n], want).all(), (i, st)
+
+
+@pytest.mark.parametrize("host", [False, True])
+def test_workspace_limit_sweeps_in_blocks(qb, oracle, host):
+    """A capped workspace (qb_set_tensor_workspace_limit): only some passes (device path: panels outer) or some panels (all-host path:
+    passes outer) stay resident, the product is swept in blocks, the slots of the other operand are reused under their events.  Same bits
+    as the unconstrained call; a cap too small for a single unit makes the planner decline (integer-limb kernel, contract only)."""
+    m, n, k = (1664, 1536, 4608) if host else (1100, 1300, 512)         # host: >= 64 MB in total for the pipelined path
+    rng = np.random.default_rng(31 + host)
+    A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    alpha, beta = quad.random_quads(rng, 2)
+
+    def run():
+        qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
+        l0 = qb.launch_count()
+        if host:
+            C = C0.copy()
+            qb.gemm("R", m, n, k, alpha, A, k, B, n, beta, C, n)
+        else:
+            dC = to_dev(C0)
+            qb.gemm("R", m, n, k, alpha, to_dev(A), k, to_dev(B), n, beta, dC, n)
+            torch.cuda.synchronize()
+            C = to_host(dC)
+        st = qb.oz_last_stats()
+        st["launches"] = qb.launch_count() - l0
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+        return C, st
+
+    want, st0 = run()
+    assert st0["pairs"] > 0
+    qb.set_tensor_unit(256, 256)
+    full, st1 = run()
+    assert st1["units"] == st1["row_passes"] * st1["panels"] and (full == want).all()
+    N, Kp = st1["pairs"], st1["Kp"]
+    # room for 2 + 2 slots of 256 rows and the two residue buffers, far less than all passes / panels resident
+    qb.set_tensor_workspace_limit(5 * N * 256 * Kp + 2 * N * (256 * 256 + 4352) + (64 << 10))
+    got, st2 = run()
+    assert st2["pairs"] > 0 and st2["units"] == st1["units"] and st2["launches"] > st1["launches"], (st1, st2)   # blocks: the residues of the non-resident operand are recomputed
+    assert (got == want).all()
+    qb.set_tensor_workspace_limit(1 << 20)
+    low, st3 = run()
+    assert st3["pairs"] == 0                                                 # declined -> integer-limb kernel
+    idx = np.stack([rng.integers(0, m, 64), rng.integers(0, n, 64)], axis=1)
+    qb.set_tensor_workspace_limit(0)
+    pure, _ = _fast_gemm(qb, "R", m, n, k, 1.0, A, k, B, n, 0.0, C0, n) if not host else (None, None)
+    if not host:
+        _, ratio, _ = oracle.exact_dot_check("R", k, A, k, B, n, idx, pure.reshape(m, n, 2)[idx[:, 0], idx[:, 1]])
+        assert (ratio <= 1.0).all()
 
 
 def test_pass_callback_min_passes(qb, oracle):
