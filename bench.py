@@ -358,7 +358,7 @@ class ShardedGemm:
         self.A = dev_random((m_loc * k,), kind, 100 + rank, dev)
         self.B = dev_random((k * n,), kind, 7, dev) if rank == 0 or world == 1 else torch.empty((k * n, 2), dtype=torch.int64, device=dev)
         Cinit = dev_random((m_loc * n,), kind, 9 + rank, dev)          # C_in of the local block (beta = 0 still reads it, level3.hpp:107)
-        self.buf, self.gather, self.packed, self.panels = None, "none", None, 0
+        self.buf, self.gather, self.packed, self.panels, self.shared = None, "none", None, 0, None
         if world == 1:
             self.Cfull = Cinit
         else:
@@ -384,8 +384,11 @@ class ShardedGemm:
             self.Cfull[rank * m_loc * n:(rank + 1) * m_loc * n].copy_(Cinit)
             del Cinit
             self.panels = args.panel_cols if (args.bcast == "panels" and fast and n >= 2 * args.panel_cols) else 0
+            self.shared = None
             if self.panels:
                 self.packed = torch.empty((k * n, 2), dtype=torch.int64, device=dev)
+                if args.share_planes:
+                    self.shared = qd.SharedPlanes()
         torch.cuda.empty_cache()     # hand freed blocks back to the driver: the library sizes its workspace from cudaMemGetInfo
         self.Cblk = self.Cfull[rank * m_loc * n:(rank + 1) * m_loc * n]
 
@@ -395,13 +398,15 @@ class ShardedGemm:
             qb.gemm("R", self.m_loc, self.n, self.k, 1.0, self.A, self.k, self.B, self.n, 0.0, self.Cblk, self.n)
             return
         self.qd.qgemm_row_sharded(self.M, self.n, self.k, 1.0, self.A, self.B, 0.0, self.Cfull, peers=self.buf, b_panels=self.panels, b_packed=self.packed,
-                                  overlap_passes=(self.args.overlap if self.buf is None else 1))
+                                  overlap_passes=(self.args.overlap if self.buf is None else 1), share_planes=self.shared)
 
     def describe(self):
         if self.world == 1:
             return "1 GPU, device resident"
         b = (f"B broadcast from rank 0 in packed column panels of {self.panels} columns DURING the product (qb_set_gemm_b_panels), column statistics first"
              if self.panels else "one NCCL broadcast of B before the product")
+        if self.panels and self.shared is not None and self.shared.buf is not None:
+            b += "; the residue planes of B are computed cooperatively (one column slice per rank) and exchanged through the NVSwitch multicast address of a symmetric buffer (dist.SharedPlanes)"
         g = {"nccl": "NCCL all_gather of the C blocks", "fused-peer": "fused gather: the reconstruction kernel stores each finished element into every peer's copy over NVLink (one store per peer)",
              "fused-multicast": "fused gather: the reconstruction kernel stores each finished element ONCE to the NVSwitch multicast address of torch symmetric memory"}.get(self.gather, self.gather)
         return f"C row-blocks of {self.m_loc} rows per GPU; {b}; {g}; completion barrier; all inside the timed region"
@@ -420,7 +425,9 @@ class ShardedGemm:
         self.Cblk = self.Cfull = None
         if self.buf is not None:
             self.buf.close()
-        self.buf = self.packed = self.A = self.B = None
+        if getattr(self, "shared", None) is not None:
+            self.shared.close()
+        self.buf = self.packed = self.A = self.B = self.shared = None
         self.torch.cuda.empty_cache()
 
 
@@ -807,6 +814,7 @@ def main():
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="N > 1: C blocks reach the other ranks by stores from the kernel that finishes them (fused) or by NCCL all-gather")
     ap.add_argument("--no-multicast", action="store_true", help="N > 1, --gather fused: CUDA IPC peer buffers (one store per peer) instead of torch symmetric memory + NVSwitch multicast")
     ap.add_argument("--bcast", default="panels", choices=["panels", "whole"], help="N > 1: B is broadcast in column panels during the product, or as a whole before it")
+    ap.add_argument("--share-planes", action="store_true", help="N > 1, --bcast panels: the ranks reduce one column slice of B each and exchange the residue planes over the multicast fabric (dist.SharedPlanes; measured slower than every rank reducing all of B: profiles/r2_shared_planes_probe_n8.log)")
     ap.add_argument("--panel-cols", type=int, default=2048, help="N > 1, --bcast panels: columns per panel (multiple of 256)")
     ap.add_argument("--host-slabs", type=int, default=0, help="e2e: slabs of the pipelined all-host qgemm (library default 8)")
     ap.add_argument("--unit", default=None, help="tensor path pipeline unit rows,cols (library default 2048,4096)")

@@ -117,6 +117,23 @@ void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes);
 typedef int (*qb_bpanel_cb)(int64_t col0, int64_t cols, void *stream, const void **panel, int64_t *ld, void *user);
 void qb_set_gemm_b_panels(qb_bpanel_cb cb, void *user, int64_t panel_cols, const void *d_colstats);
 int qb_gemm_colstats_dev(char layout, char transb, int64_t k, int64_t n, const void *dB, int64_t ldb, void *d_colstats, void *stream);
+/* B handed over as RESIDUE PLANES (row-sharded qgemm on N GPUs: every rank needs the residue planes of all of B, so the ranks compute
+ * one column slice each and exchange the int8 planes over the NVSwitch multicast fabric instead of every rank reducing all of B;
+ * qblas_b200/dist.py: qgemm_row_sharded(share_planes=...)).
+ *   qb_crt_plan          the planner: spans of op(A) rows / op(B) columns (bits; from the statistics: max over non-empty lines of
+ *                        emax + 113 - lmin) and k -> moduli count and windows.  Returns 0 when the windows cover the spans (exact),
+ *                        a bit mask (1: A cut, 2: B cut) when they had to be capped, -1 when no plan exists.
+ *   qb_crt_residues_dev  residue planes of the n columns of op(B) (k x n; same layout convention as qb_gemm_colstats_dev): plane i is
+ *                        n x Kp int8 at d_planes + i * plane_stride (Kp = k rounded up to 128; plane_stride = 0: packed).  d_emax =
+ *                        the first array of those columns' statistics.
+ *   qb_set_gemm_b_planes the panels that the qb_set_gemm_b_panels callback hands over are such planes (`*panel` = plane 0 of the
+ *                        panel's first column, `*ld` = bytes between planes), computed with `window` and at least the `moduli` the
+ *                        call needs; moduli = 0 switches back to element panels.  The call fails (QB_ERR_CUDA, not supported) when
+ *                        its own plan needs another window, more moduli, or the fix-up kernel (capped windows, Inf/NaN). */
+int qb_crt_plan(int span_a, int span_b, int64_t k, int *moduli, int *window_a, int *window_b);
+int qb_crt_residues_dev(char layout, char transb, int64_t k, int64_t n, const void *dB, int64_t ldb, const void *d_emax, int window, int moduli,
+                        void *d_planes, int64_t plane_stride, void *stream);
+void qb_set_gemm_b_planes(int moduli, int window);
 /* Window of the tensor path.  Rows of op(A) / columns of op(B) are block fixed point with W_A / W_B-bit integers; the moduli must
  * cover W_A + W_B + log2(k) + 1 bits.  When the operands' bit spans fit into 2 x `bits` (every D53 / D113 input: 54 / 140 bits) the
  * windows are the spans and the inner products are exact.  Wider spans (exponent spreads of tens of binades inside one row) are

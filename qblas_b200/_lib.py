@@ -68,6 +68,9 @@ def lib():
         "qb_set_gemm_pass_callback": (None, [PASS_CB, vp, ci]),
         "qb_set_gemm_b_panels": (None, [BPANEL_CB, vp, i64, vp]),
         "qb_gemm_colstats_dev": (ci, [cc, cc, i64, i64, vp, i64, vp, vp]),
+        "qb_crt_plan": (ci, [ci, ci, i64, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci)]),
+        "qb_crt_residues_dev": (ci, [cc, cc, i64, i64, vp, i64, vp, ci, ci, vp, i64, vp]),
+        "qb_set_gemm_b_planes": (None, [ci, ci]),
         "qb_set_tensor_window": (None, [ci]),
         "qb_get_tensor_window": (ci, []),
         "qb_set_tensor_unit": (None, [i64, i64]),

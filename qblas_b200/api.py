@@ -288,6 +288,27 @@ def gemm_colstats(layout, k, n, B, ldb, out, transb="N"):
     return out
 
 
+def crt_plan(span_a, span_b, k):
+    """(moduli, window_a, window_b, truncated mask) the tensor path's planner gives for these bit spans (qb_crt_plan); None: no plan."""
+    n, wa, wb = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().qb_crt_plan(int(span_a), int(span_b), int(k), C.byref(n), C.byref(wa), C.byref(wb))
+    return None if rc < 0 else (int(n.value), int(wa.value), int(wb.value), int(rc))
+
+
+def crt_residues(layout, k, n, B, ldb, emax, window, moduli, planes, plane_stride=0, transb="N", data_ptr=None):
+    """Residue planes of the n columns of op(B) (qb_crt_residues_dev).  B: device quads (or data_ptr = a raw device address);
+    emax: int32 device tensor (first array of the columns' statistics); planes: int8 device tensor or raw address."""
+    bp = C.c_void_p(int(data_ptr)) if data_ptr is not None else _ptr(B)
+    pp = C.c_void_p(int(planes)) if isinstance(planes, int) else C.c_void_p(planes.data_ptr())
+    check(lib().qb_crt_residues_dev(_c(layout), _c(transb), k, n, bp, ldb, C.c_void_p(emax.data_ptr()), int(window), int(moduli), pp, int(plane_stride), _stream()),
+          "qb_crt_residues_dev")
+
+
+def set_gemm_b_planes(moduli=0, window=0):
+    """The panels of set_gemm_b_panels are residue planes computed with `window` and `moduli` moduli (0: element panels)."""
+    lib().qb_set_gemm_b_planes(int(moduli), int(window))
+
+
 def set_tensor_window(bits):
     """Bits per operand window the tensor-path planner grants when the operands' spans do not fit the moduli (default 144)."""
     lib().qb_set_tensor_window(int(bits))
@@ -349,6 +370,12 @@ class _CudaArray:
 
     def __init__(self, ptr, nbytes):
         self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def tensor_from_ptr(ptr, nbytes):
+    """torch uint8 view of `nbytes` of device memory at a raw address (e.g. a multicast mapping); the caller keeps the memory alive."""
+    import torch
+    return torch.as_tensor(_CudaArray(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
 
 
 def peer_alloc(nbytes):

@@ -12,6 +12,7 @@
  */
 #include "../../include/qblas_b200.h"
 #include "qb_internal.h"
+#include "qb_crt.cuh"
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -41,6 +42,7 @@ static qb_bpanel_cb g_bp_cb = nullptr;
 static void *g_bp_user = nullptr;
 static int64_t g_bp_cols = 0;
 static const int *g_bp_stats = nullptr;
+static int g_bp_planes_N = 0, g_bp_planes_W = 0;   /* the panels are residue planes (qb_set_gemm_b_planes) */
 static int g_npeer = 0;
 static void *g_peer[QB_MAX_PEERS];
 static int g_peer_written = 0;
@@ -382,6 +384,7 @@ static int gemm_dev_impl(char layout, char ta, char tb, int64_t m, int64_t n, in
     if (hooks) {
       h.cb = (oz_pass_cb)g_pass_cb; h.cb_user = g_pass_user; h.min_passes = g_pass_min;
       h.bp = (oz_bpanel_cb)g_bp_cb; h.bp_user = g_bp_user; h.bp_cols = g_bp_cols; h.bstats = g_bp_stats;
+      if (g_bp_cb) { h.bplanes_N = g_bp_planes_N; h.bplanes_W = g_bp_planes_W; }
       g.npeer = g_npeer;
       for (int q = 0; q < g.npeer; ++q) g.peerC[q] = (q128 *)g_peer[q];
     }
@@ -445,6 +448,37 @@ int qb_gemm_colstats_dev(char layout, char transb, int64_t k, int64_t n, const v
   const int64_t sbl = (col != tB) ? 1 : ldb, sbj = (col != tB) ? ldb : 1;
   cudaError_t e = launch_colstats((const q128 *)dB, n, k, sbj, sbl, (int *)d_colstats, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "column statistics launch", e);
+  return QB_OK;
+}
+void qb_set_gemm_b_planes(int moduli, int window)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  g_bp_planes_N = moduli > 0 ? moduli : 0; g_bp_planes_W = moduli > 0 ? window : 0;
+}
+int qb_crt_plan(int span_a, int span_b, int64_t k, int *moduli, int *window_a, int *window_b)
+{
+  crt::host::Windows w;
+  if (k <= 0 || !crt::host::plan_windows(span_a, span_b, k, oz_get_window(), w)) return -1;
+  if (moduli) *moduli = w.N;
+  if (window_a) *window_a = w.WA;
+  if (window_b) *window_b = w.WB;
+  return (w.truncA ? 1 : 0) | (w.truncB ? 2 : 0);
+}
+int qb_crt_residues_dev(char layout, char transb, int64_t k, int64_t n, const void *dB, int64_t ldb, const void *d_emax, int window, int moduli,
+                        void *d_planes, int64_t plane_stride, void *stream)
+{
+  if (k <= 0 || n <= 0 || moduli < 1 || moduli > crt::NM || window < 1 || window > crt::WMAX) return fail(QB_ERR_ARG, "qb_crt_residues_dev: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  int rc = ensure_device();
+  if (rc) return rc;
+  cudaError_t e = oz_prepare_device();
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qb_crt_residues_dev", e);
+  const bool col = is_col(layout), tB = g_honor_trans.load() != 0 && is_trans(transb);
+  const int64_t sbl = (col != tB) ? 1 : ldb, sbj = (col != tB) ? ldb : 1;
+  const int64_t Kp = (k + 127) / 128 * 128;
+  launch_crt_residues((const q128 *)dB, n, k, sbj, sbl, (const int *)d_emax, window, moduli, Kp, (int8_t *)d_planes, (cudaStream_t)stream, plane_stride);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "residue kernel launch", e);
   return QB_OK;
 }
 void qb_set_tensor_window(int bits)

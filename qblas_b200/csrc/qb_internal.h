@@ -75,6 +75,9 @@ struct OzHooks {
   oz_pass_cb cb = nullptr; void *cb_user = nullptr; int min_passes = 1;
   oz_bpanel_cb bp = nullptr; void *bp_user = nullptr; int64_t bp_cols = 0;
   const int *bstats = nullptr;       /* device: column statistics of op(B) from launch_colstats (3 n ints); skips the scan of B */
+  /* the panels bp hands over are RESIDUE PLANES of op(B) (N planes of cols x Kp int8, `ld` returned by bp = bytes between planes),
+   * computed with window bplanes_W and bplanes_N moduli: no residues of B are computed here */
+  int bplanes_N = 0, bplanes_W = 0;
   /* streamed rows (the all-host path): called once per row pass before its first use; the callee makes sA wait for the rows of A
    * and sF for the rows of C_in.  non-zero return = failure. */
   int (*rows_in)(int64_t row0, int64_t rows, void *sA, void *sF, void *user) = nullptr; void *rows_user = nullptr;
@@ -82,6 +85,9 @@ struct OzHooks {
 };
 /* *used = 0: the planner declined (no TMA entry point, no workspace) and nothing was written */
 cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, const OzHooks &h);
+void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int W, int N, int64_t Kp, int8_t *planes,
+                         cudaStream_t st, int64_t pstride);
+cudaError_t oz_prepare_device();
 cudaError_t launch_colstats(const q128 *B, int64_t n, int64_t k, int64_t sbj, int64_t sbl, int *stats, cudaStream_t st);
 cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb,
                           int32_t *D, int64_t Mp, int64_t Np, cudaStream_t st, int keep = 0);

@@ -362,7 +362,7 @@ __device__ __forceinline__ uint32_t crt_word(const Crt4 &c, int i)
 /* k contiguous (or fully strided): thread = (row, 4 consecutive k); plane i is [rows][Kp] int8 */
 template <int NW>
 __global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
-                                                      int W, int N, int64_t Kp, int8_t *__restrict__ planes)
+                                                      int W, int N, int64_t Kp, int8_t *__restrict__ planes, int64_t pstride)
 {
   const int64_t groups = Kp >> 2;
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = 4 * g + b;
-        if (i < N) *reinterpret_cast<uint32_t *>(planes + ((int64_t)i * rows + r) * Kp + g4 * 4) = crt_word<NW>(c, i);
+        if (i < N) *reinterpret_cast<uint32_t *>(planes + (int64_t)i * pstride + r * Kp + g4 * 4) = crt_word<NW>(c, i);
       }
     }
   }
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) k_crt_residues(const q128 *__restrict__ X
 static inline int crt_t_smem(int N) { return N * 16 * 9 * 4; }
 template <int NW>
 __global__ void __launch_bounds__(128) k_crt_residues_t(const q128 *__restrict__ X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *__restrict__ emax,
-                                                        int W, int N, int64_t Kp, int8_t *__restrict__ planes)
+                                                        int W, int N, int64_t Kp, int8_t *__restrict__ planes, int64_t pstride)
 {
   extern __shared__ uint32_t crt_sm[];            /* [plane][row][k-group], padded: 9 words per row */
   const int row_l = threadIdx.x & 15, kg = threadIdx.x >> 4;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(128) k_crt_residues_t(const q128 *__restrict__
     const int i = q >> 5, row = (q & 31) >> 1, half = q & 1;
     if (r0 + row >= rows) continue;
     const uint32_t *src = &crt_sm[(i * 16 + row) * 9 + half * 4];
-    *reinterpret_cast<uint4 *>(planes + ((int64_t)i * rows + r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
+    *reinterpret_cast<uint4 *>(planes + (int64_t)i * pstride + (r0 + row) * Kp + (g0 + half * 4) * 4) = make_uint4(src[0], src[1], src[2], src[3]);
   }
 }
 
@@ -608,12 +608,12 @@ static PFN_encodeTiled get_encode()
 
 /* planes [S][rows][Kp] int8 -> 3-D map {Kp, rows, S}, box {128, box_rows, 1}, 128-byte swizzle; rows
  * beyond `rows` are zero-filled by the TMA unit */
-static bool make_plane_map(CUtensorMap *tm, const int8_t *planes, int S, int64_t rows, int64_t Kp, int box_rows)
+static bool make_plane_map(CUtensorMap *tm, const int8_t *planes, int S, int64_t rows, int64_t Kp, int box_rows, int64_t pstride = 0)
 {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)S};
-  cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * (cuuint64_t)rows};
+  cuuint64_t strides[2] = {(cuuint64_t)Kp, pstride > 0 ? (cuuint64_t)pstride : (cuuint64_t)Kp * (cuuint64_t)rows};
   cuuint32_t box[3] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void *)planes, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -673,6 +673,8 @@ static cudaError_t oz_dev(OzDev **out)
   D.ready = true;
   return cudaSuccess;
 }
+/* one-time setup of the current device (constant tables, kernel attributes, streams) for entry points that launch kernels directly */
+cudaError_t oz_prepare_device() { OzDev *D; return oz_dev(&D); }
 static cudaError_t oz_event(OzDev &D, int idx, cudaEvent_t *out)
 {
   while ((int)D.ev.size() <= idx) {
@@ -787,10 +789,10 @@ cudaError_t launch_oz_mma(const int8_t *pA, const int8_t *pB, int SA, int SB, in
 /* residue scheme: R_i (+)= (A_i B_i^T) mod p_i for the N residue planes over k-blocks [kb_begin, kb_begin + nkb)
  * (|acc| <= 128 * 128 * OZ_KCHUNK = 2^30) */
 static cudaError_t launch_crt_mma(OzDev &D, const int8_t *pA, const int8_t *pB, int N, int64_t m, int64_t n, int64_t Kp, int kb_begin, int nkb, int accum,
-                                  uint8_t *R, int64_t Mp, int64_t Np, int64_t rplane, cudaStream_t st)
+                                  uint8_t *R, int64_t Mp, int64_t Np, int64_t rplane, cudaStream_t st, int64_t pstrideB = 0)
 {
   CUtensorMap tmA, tmB;
-  if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN)) return cudaErrorInvalidValue;
+  if (!make_plane_map(&tmA, pA, N, m, Kp, OZ_BM) || !make_plane_map(&tmB, pB, N, n, Kp, OZ_BN, pstrideB)) return cudaErrorInvalidValue;
   OzMmaArgs g;
   memset(&g, 0, sizeof(g));
   g.R = R; g.rplane = rplane; g.Mp = Mp; g.Np = Np; g.SA = N; g.SB = N; g.ndiag = N;
@@ -810,9 +812,11 @@ static const crt::Plan &crt_plan(int N)
   if (!have[N]) { crt::host::build_plan(N, plans[N]); have[N] = true; }
   return plans[N];
 }
-static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int W, int N, int64_t Kp, int8_t *planes,
-                                cudaStream_t st)
+/* planes: plane i holds rows x Kp bytes at planes + i * pstride (pstride = 0: packed, rows * Kp) */
+void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t sr, int64_t sk, const int *emax, int W, int N, int64_t Kp, int8_t *planes,
+                         cudaStream_t st, int64_t pstride)
 {
+  if (pstride <= 0) pstride = rows * Kp;
   const int nw = std::min(crt::NWMAX, std::max(1, (W + 31) / 32));
   const bool direct = (sk == 1 || sr != 1);
   const int64_t threads = rows * (Kp / 4);
@@ -821,8 +825,8 @@ static void launch_crt_residues(const q128 *X, int64_t rows, int64_t K, int64_t 
   switch (nw) {
 #define QB_CRT_CASE(NW)                                                                                     \
   case NW:                                                                                                  \
-    if (direct) k_crt_residues<NW><<<g1, 256, 0, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);          \
-    else k_crt_residues_t<NW><<<g2, 128, crt_t_smem(N), st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes);   \
+    if (direct) k_crt_residues<NW><<<g1, 256, 0, st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes, pstride);  \
+    else k_crt_residues_t<NW><<<g2, 128, crt_t_smem(N), st>>>(X, rows, K, sr, sk, emax, W, N, Kp, planes, pstride); \
     break;
     QB_CRT_CASE(1) QB_CRT_CASE(2) QB_CRT_CASE(3) QB_CRT_CASE(4) QB_CRT_CASE(5) QB_CRT_CASE(6)
 #undef QB_CRT_CASE
@@ -931,11 +935,15 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, con
   QB_TRY(cudaStreamSynchronize(st));
   /* streamed rows: the spans of A are not known yet; assume the widest, so that the planner gives A whatever the budget leaves
    * after B - never less than the resident call gets (same bits whenever that one is exact) */
-  const int WA_nat = h.rows_in ? crt::WMAX : D.h_plan[0], WB_nat = D.h_plan[1], fl = D.h_plan[2];
+  const int WA_nat = h.rows_in ? crt::WMAX : D.h_plan[0], WB_nat = h.bplanes_N ? h.bplanes_W : D.h_plan[1], fl = D.h_plan[2];
   crt::host::Windows win;
   if (!crt::host::plan_windows(WA_nat, WB_nat, k, g_window, win)) return cudaSuccess;
   const int WA = win.WA, WB = win.WB, N = win.N;
   const int check = (win.truncA || win.truncB || fl || h.rows_in) ? 1 : 0;
+  /* B handed over as residue planes (computed elsewhere with window bplanes_W and bplanes_N moduli, e.g. cooperatively by the ranks of
+   * a row-sharded product): this call must arrive at the same window, need no more moduli, and have no element to fix up (the fix-up
+   * reads the original B) */
+  if (h.bplanes_N && (!h.bp || WB != h.bplanes_W || N > h.bplanes_N || check)) return cudaErrorNotSupported;
   const crt::Plan &pl = crt_plan(N);
   /* ---- units: row passes of `ur` rows x column panels of `uc` columns ----
    * Loop order 0 (default): panels outer, passes inner — the residue planes of the A rows stay resident, the B panels are double
@@ -1023,7 +1031,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, con
     if (sa.who != p) {   /* residues of this pass's A rows; the slot was last read by the tensor kernel that recorded sa.read */
       if (sa.read_rec) QB_TRY(cudaStreamWaitEvent(D.sA, sa.read, 0));
       if (h.rows_in && rows_in_done[(size_t)p] == 1) { launch_scan(a.A + r0 * a.sai, mr, k, a.sai, a.sal, statA + r0, statA + m + r0, statA + 2 * m + r0, D.sA); rows_in_done[(size_t)p] = 2; }
-      launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pAp, D.sA);
+      launch_crt_residues(a.A + r0 * a.sai, mr, k, a.sai, a.sal, emaxA + r0, WA, N, Kp, pAp, D.sA, 0);
       QB_TRY(cudaEventRecord(sa.ready, D.sA));
       QB_TRY(cudaStreamWaitEvent(D.sM, sa.ready, 0));
       sa.who = p;
@@ -1038,7 +1046,7 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, con
         sb.panel = (const q128 *)ptr; sb.ld = ldp;
       }
       if (h.bp) { Bp = sb.panel; if (a.sbj == 1) sbl = sb.ld; else sbj = sb.ld; }
-      launch_crt_residues(Bp, w, k, sbj, sbl, emaxB + c0, WB, N, Kp, pBj, D.sB);
+      if (!h.bplanes_N) launch_crt_residues(Bp, w, k, sbj, sbl, emaxB + c0, WB, N, Kp, pBj, D.sB, 0);
       QB_TRY(cudaEventRecord(sb.ready, D.sB));
       QB_TRY(cudaStreamWaitEvent(D.sM, sb.ready, 0));
       sb.who = j;
@@ -1048,7 +1056,8 @@ cudaError_t launch_gemm_ozaki(const GemmArgs &a, cudaStream_t st, int *used, con
     for (int c = 0; c < nkc; ++c) {
       const int kb0 = (int)(c * kcb), nkb = (int)std::min<int64_t>(kcb, nkb_total - kb0);
       oz_ev_record(D, 0, D.sM);
-      const cudaError_t e2 = launch_crt_mma(D, pAp, pBj, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, rplane_of(Mp, Np), D.sM);
+      const cudaError_t e2 = h.bplanes_N ? launch_crt_mma(D, pAp, (const int8_t *)sb.panel, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, rplane_of(Mp, Np), D.sM, sb.ld)
+                                         : launch_crt_mma(D, pAp, pBj, N, mr, w, Kp, kb0, nkb, c > 0, R[rb], Mp, Np, rplane_of(Mp, Np), D.sM);
       oz_ev_record(D, 1, D.sM);
       if (e2 != cudaSuccess) return e2;
     }

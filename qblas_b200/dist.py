@@ -145,6 +145,45 @@ def fused_outputs(buf, rank, byte_offset, multicast=True):
     return [buf.ptrs[q] + byte_offset for q in range(len(buf.ptrs)) if q != rank]
 
 
+class SharedPlanes:
+    """Residue planes of B shared between the ranks of a row-sharded qgemm (fast mode).  Every rank of such a product needs the int8
+    residue planes of ALL of B; instead of every rank reducing the whole of B (the one part of the work that does not shrink with the
+    number of GPUs), rank r reduces one column slice of each panel and stores it ONCE to the NVSwitch multicast address of a symmetric
+    [N][n][Kp] buffer, which puts it into every rank's copy; a symmetric-memory barrier per panel tells the ranks that the panel is
+    complete.  Needs torch symmetric memory with multicast; holds its buffers across calls (grow-only)."""
+
+    def __init__(self, group=None):
+        self.group, self.buf, self.stage, self.stream, self.key = group, None, None, None, None
+
+    def ensure(self, N, n, Kp, slice_cols):
+        key = (N, n, Kp)
+        if self.buf is None or self.key != key:
+            if self.buf is not None:
+                self.buf.close()
+            self.buf = SymmetricBuffer(N * n * Kp, group=self.group)
+            if not self.buf.mc_ptr:
+                raise RuntimeError("no multicast address")
+            self.key = key
+        need = N * slice_cols * Kp
+        if self.stage is None or self.stage.numel() < need:
+            self.stage = torch.empty(need, dtype=torch.int8, device=self.buf.tensor.device)
+        if self.stream is None:
+            self.stream = torch.cuda.Stream(priority=0)
+        return self.buf
+
+    def close(self):
+        if self.buf is not None:
+            self.buf.close()
+        self.buf = self.stage = None
+
+
+def _lines_span(stats, count):
+    """widest bit span of the `count` lines described by a statistics block [emax | lmin | sp]; any Inf/NaN"""
+    emax, lmin, sp = stats[:count], stats[count:2 * count], stats[2 * count:3 * count]
+    span = torch.where(emax != 0, emax + 113 - lmin, torch.zeros_like(emax)).max()
+    return span, sp.max()
+
+
 class _CudaEngine:
     """Default per-rank engine: libqblas_b200.so on the current CUDA device."""
 
@@ -161,13 +200,17 @@ class _CudaEngine:
         finally:
             api.set_gemm_pass_callback(None)
 
-    def gemm_streamed(self, m, n, k, alpha, A, lda, panel_fn, panel_cols, colstats, beta, C, ldc):
-        """qgemm whose B arrives in column panels: panel_fn(col0, cols, stream_ptr) -> (ptr, ld) (qb_set_gemm_b_panels)."""
+    def gemm_streamed(self, m, n, k, alpha, A, lda, panel_fn, panel_cols, colstats, beta, C, ldc, planes=None):
+        """qgemm whose B arrives in column panels: panel_fn(col0, cols, stream_ptr) -> (ptr, ld) (qb_set_gemm_b_panels).
+        planes = (moduli, window): the panels are residue planes (qb_set_gemm_b_planes)."""
         from . import api
         api.set_gemm_b_panels(panel_fn, panel_cols, colstats)
+        if planes:
+            api.set_gemm_b_planes(*planes)
         try:
             api.gemm("R", m, n, k, alpha, A, lda, A, n, beta, C, ldc)      # the B argument is not dereferenced
         finally:
+            api.set_gemm_b_planes(0)
             api.set_gemm_b_panels(None)
 
     def colstats(self, k, n, B, ldb, out):
@@ -217,7 +260,7 @@ def _gather_blocks(m, n, world, C_full, C_blk, group):
 
 
 def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=None, group=None, overlap_passes=1, peers=None, b_panels=0,
-                      b_packed=None):
+                      b_packed=None, share_planes=None):
     """C_full (m x n, row-major, identical buffer shape on every rank) <- alpha*A*B + beta*C.
     A_blk holds this rank's rows [lo, hi) of A (row-major, lda = k); B (k x n) is valid on `src`
     and is overwritten by the broadcast elsewhere.  Returns (lo, hi).
@@ -234,7 +277,12 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
     b_panels = w > 0 (fast mode, every rank owns >= 1 row): B is not broadcast before the product but DURING it, in column panels of w
     columns (a multiple of 256): the owner computes the column statistics of B (12 n bytes, broadcast first), packs panel j into a
     contiguous k x w buffer and broadcasts it while the ranks multiply panel j-1 (qb_set_gemm_b_panels).  b_packed: optional
-    preallocated (k * n, 2) buffer for the packed panels (panel j occupies rows [j*k*w, ...)); B itself is only read on `src`."""
+    preallocated (k * n, 2) buffer for the packed panels (panel j occupies rows [j*k*w, ...)); B itself is only read on `src`.
+
+    share_planes = a SharedPlanes object (with b_panels, NCCL, multicast fabric): the ranks do not each reduce all of B to residue
+    planes; rank r reduces one column slice of every panel and multicasts the planes (see SharedPlanes).  Used only when the windows
+    cover the spans on every rank (exact case: nothing for the fix-up kernel, which would need B's elements); otherwise, and whenever
+    the set-up fails on any rank, the call proceeds with element panels."""
     compute = compute or _CudaEngine()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     lo, hi = row_block(m, world, rank)
@@ -263,11 +311,20 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
             j = col0 // w
             compute.wait_on_stream(works[j], stream_ptr)
             return views[j].data_ptr(), cols
+
+        if share_planes is not None and isinstance(compute, _CudaEngine) and hi > lo:
+            planes_mode = _share_planes_setup(share_planes, m, n, k, w, lo, hi, A_blk, stats, works, views, world, rank, group)
+            if planes_mode is not None:
+                panel_fn, planes_mode = planes_mode
     else:
         dist.broadcast(_bytes(B), src=src, group=group)
+    if not streamed or share_planes is None or not isinstance(compute, _CudaEngine) or hi <= lo:
+        planes_mode = None
 
     def run_gemm(rows, A_, C_, **kw):
-        if streamed:
+        if streamed and planes_mode is not None:
+            compute.gemm_streamed(rows, n, k, alpha, A_, k, panel_fn, int(b_panels), stats, beta, C_, n, planes=planes_mode)
+        elif streamed:
             compute.gemm_streamed(rows, n, k, alpha, A_, k, panel_fn, int(b_panels), stats, beta, C_, n)
         else:
             compute.gemm(rows, n, k, alpha, A_, k, B, n, beta, C_, n, **kw)
@@ -311,6 +368,65 @@ def qgemm_row_sharded(m, n, k, alpha, A_blk, B, beta, C_full, *, src=0, compute=
             wk.wait()
     _gather_blocks(m, n, world, C_full, C_blk, group)
     return lo, hi
+
+
+def _share_planes_setup(sp, m, n, k, w, lo, hi, A_blk, stats, works, views, world, rank, group):
+    """Shared residue planes of B (see SharedPlanes): returns (panel_fn, (moduli, window_B)) or None when the ranks must fall back to
+    element panels (every rank takes the same branch: the decision is all-reduced)."""
+    from . import api
+    dev = stats.device
+    ok, N, WA, WB = 1, 0, 0, 0
+    try:
+        statsA = torch.zeros(3 * (hi - lo), dtype=torch.int32, device=dev)
+        api.gemm_colstats("C", k, hi - lo, A_blk, k, statsA)          # rows of the row-major A block = columns of its col-major view
+        spanA, flA = _lines_span(statsA, hi - lo)
+        spanB, flB = _lines_span(stats, n)
+        red = torch.stack([spanA, spanB, flA, flB]).to(torch.int64)
+    except Exception:
+        ok, red = 0, torch.zeros(4, dtype=torch.int64, device=dev)
+    dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)            # every rank plans with the widest A rows of all ranks
+    sa, sb_, fa, fb = (int(v) for v in red.tolist())
+    plan = api.crt_plan(sa, sb_, k) if ok else None
+    if plan is None or plan[3] != 0 or fa or fb:
+        ok = 0
+    else:
+        N, WA, WB, _ = plan
+    Kp = (k + 127) // 128 * 128
+    sw = -(-w // world)
+    if ok:
+        try:
+            buf = sp.ensure(N, n, Kp, sw)
+        except Exception:
+            ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        return None
+    mc = api.tensor_from_ptr(buf.mc_ptr, N * n * Kp).view(torch.int64).reshape(N, n, Kp // 8)
+    emaxB = stats[:n]
+    events = []
+    cur = torch.cuda.current_stream()
+    sp.stream.wait_stream(cur)
+    with torch.cuda.stream(sp.stream):
+        for j, c0 in enumerate(range(0, n, w)):
+            cols = min(w, n - c0)
+            s0 = min(cols, rank * sw); cnt = max(0, min(cols, (rank + 1) * sw) - s0)
+            works[j].wait()                                            # the packed k x cols panel has arrived (side stream waits)
+            if cnt > 0:
+                st = sp.stage[:N * cnt * Kp]
+                # my slice of the panel: columns s0 .. s0 + cnt of the packed panel (ld = cols)
+                api.crt_residues("R", k, cnt, None, cols, emaxB[c0 + s0:], WB, N, st, 0, data_ptr=views[j].data_ptr() + s0 * 16)
+                mc[:, c0 + s0:c0 + s0 + cnt].copy_(st.view(torch.int64).reshape(N, cnt, Kp // 8))
+            buf.handle.barrier(channel=0)                              # every rank's slice of this panel has landed everywhere
+            ev = torch.cuda.Event(); ev.record(sp.stream)
+            events.append(ev)
+    base = buf.local_ptr
+
+    def panel_fn(col0, cols, stream_ptr):
+        torch.cuda.ExternalStream(stream_ptr).wait_event(events[col0 // w])
+        return base + col0 * Kp, n * Kp
+
+    return panel_fn, (N, WB)
 
 
 def qgemv_row_sharded(m, n, alpha, A_blk, x, beta, y_full, *, src=0, compute=None, group=None):

@@ -88,6 +88,19 @@ def main():
             torch.cuda.synchronize()
             if not (to_host(Cf2) == to_host(one)).all():
                 fails.append(("gemm streamed B vs 1-GPU", mode, m, n, k))
+        # ... and with the residue planes of B computed cooperatively (one column slice per rank) and exchanged over the multicast fabric
+        if mode == qb.MODE_FAST and n >= 256:
+            shp = qd.SharedPlanes()
+            for rep in range(2):                                     # twice: the second call reuses the symmetric buffers
+                Bt = to_dev(B) if rank == 0 else torch.zeros((k * n, 2), dtype=torch.int64, device="cuda")
+                Cf3 = to_dev(C0.copy())
+                qd.qgemm_row_sharded(m, n, k, alpha, to_dev(A[lo * k:hi * k]), Bt, beta, Cf3, b_panels=256, share_planes=shp)
+                torch.cuda.synchronize()
+                if not (to_host(Cf3) == to_host(one)).all():
+                    fails.append(("gemm shared residue planes vs 1-GPU", mode, m, n, k, rep))
+            if rank == 0:
+                print(f"mgpu_worker: shared residue planes {'used' if shp.buf is not None else 'NOT used (fallback)'}", flush=True)
+            shp.close()
         if mode == qb.MODE_REFERENCE:
             want = C0.copy(); orc.gemm("R", m, n, k, alpha, A, k, B, n, beta, want, n)
             if not quad.same_bits(to_host(Cf), want).all():

@@ -22,7 +22,7 @@ def _defaults(qb):
     yield
     qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO); qb.set_tensor_unit(0, 0); qb.set_tensor_window(144)
     qb.set_tensor_workspace_limit(0); qb.set_tensor_ramp(0, 0)
-    qb.set_gemm_pass_callback(None); qb.set_gemm_peer_outputs(None); qb.set_gemm_b_panels(None)
+    qb.set_gemm_pass_callback(None); qb.set_gemm_peer_outputs(None); qb.set_gemm_b_panels(None); qb.set_gemm_b_planes(0)
 
 
 def _diag_ref(pa, pb, m, n):
@@ -372,6 +372,59 @@ def test_streamed_b_panels(qb, oracle):
     st = qb.oz_last_stats()
     qb.set_gemm_b_panels(None)
     assert calls == [(c0, pw) for c0 in range(0, n, pw)] and st["panels"] == n // pw, (calls, st)
+    assert (to_host(dC) == want).all()
+
+
+def test_b_handed_over_as_residue_planes(qb, oracle):
+    """qb_crt_plan + qb_crt_residues_dev + qb_set_gemm_b_planes: the residue planes of B are computed OUTSIDE the call (column slice by
+    column slice into one [N][n][Kp] buffer, as the ranks of a row-sharded product do before exchanging them) and handed over panel by
+    panel; the call computes no residues of B.  Same bits as the ordinary call; more planes than the call needs are fine; a call that
+    would need the fix-up (B's original elements) is refused."""
+    m, n, k, pw = 300, 1280, 260, 256
+    rng = np.random.default_rng(23)
+    A = qgen.matrix(rng, m, k, "D113"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n, "D113")
+    alpha, beta = quad.random_quads(rng, 2)
+    want, st0 = _fast_gemm(qb, "R", m, n, k, alpha, A, k, B, n, beta, C0, n)
+    dA, dB = to_dev(A), to_dev(B)
+    statsB = torch.zeros(3 * n, dtype=torch.int32, device="cuda"); statsA = torch.zeros(3 * m, dtype=torch.int32, device="cuda")
+    qb.gemm_colstats("R", k, n, dB, n, statsB)
+    qb.gemm_colstats("C", k, m, dA, k, statsA)            # the rows of a row-major A are the columns of the col-major view
+    span = lambda st, cnt: int(torch.where(st[:cnt] != 0, st[:cnt] + 113 - st[cnt:2 * cnt], torch.zeros_like(st[:cnt])).max().item())
+    WAs, WBs = span(statsA, m), span(statsB, n)
+    assert (WAs, WBs) == (st0["WA_span"], st0["WB_span"])
+    N, WA, WB, trunc = qb.crt_plan(WAs, WBs, k)
+    assert trunc == 0 and (N, WA, WB) == (st0["pairs"], st0["WA"], st0["WB"])
+    Kp = (k + 127) // 128 * 128
+    NB = N + 2                                            # two planes more than this call needs
+    planes = torch.zeros((NB, n, Kp), dtype=torch.int8, device="cuda")
+    for c0 in range(0, n, 320):                           # slices of 320 columns, written straight into the shared layout
+        qb.crt_residues("R", k, 320, None, n, statsB[c0:], WB, NB, planes.data_ptr() + c0 * Kp, n * Kp, data_ptr=dB.data_ptr() + c0 * 16)
+    calls = []
+
+    def provide(col0, cols, stream_ptr):
+        calls.append(col0)
+        ev = torch.cuda.Event(); ev.record()
+        torch.cuda.ExternalStream(stream_ptr).wait_event(ev)
+        return planes.data_ptr() + col0 * Kp, n * Kp
+
+    qb.set_gemm_b_panels(provide, pw, statsB); qb.set_gemm_b_planes(NB, WB)
+    qb.set_mode(qb.MODE_FAST); qb.set_tensor_path(qb.TENSOR_ALWAYS)
+    l0 = qb.launch_count()
+    try:
+        dC = to_dev(C0)
+        bogus = torch.zeros(16, dtype=torch.int64, device="cuda")
+        qb.gemm("R", m, n, k, alpha, dA, k, bogus.reshape(-1, 2), n, beta, dC, n)
+        torch.cuda.synchronize()
+        st = qb.oz_last_stats()
+        launches = qb.launch_count() - l0
+        # Dexp rows need the fix-up: refused in this mode
+        Ax = to_dev(_mk(rng, m, k, k, "Dexp40"))
+        with pytest.raises(qb.QblasError):
+            qb.gemm("R", m, n, k, alpha, Ax, k, bogus.reshape(-1, 2), n, beta, to_dev(C0), n)
+    finally:
+        qb.set_gemm_b_planes(0); qb.set_gemm_b_panels(None)
+        qb.set_mode(qb.MODE_REFERENCE); qb.set_tensor_path(qb.TENSOR_AUTO)
+    assert calls == list(range(0, n, pw)) and st["pairs"] == N
     assert (to_host(dC) == want).all()
 
 
