@@ -30,6 +30,10 @@
  * There is no CPU fallback: every compute entry point fails with QB_ERR_CUDA when no sm_100 device
  * is usable.
  *
+ * Environment (read when the library is loaded, so that an UNMODIFIED caller of the reference API can choose): QUADBLAS_MODE =
+ * reference | fast, QUADBLAS_KC = k-panel of the reference-order qgemm (126), and OMP_NUM_THREADS = the default of
+ * quadblas_get_num_threads() as in the reference (threading/openmp_utils.hpp:10-17: omp_get_max_threads()).
+ *
  * Errors: the reference has no error channel (void/double returns, c_interface.hpp).  Here the
  * reference-named functions keep their signatures and record failures in a thread-local sticky
  * error (qb_last_error / qb_last_error_code); outputs are left untouched on failure, qdot/qnrm2

@@ -221,9 +221,8 @@ static cudaError_t paged_copy(void *dst, const void *src, size_t bytes, bool to_
   const size_t nchunks = (bytes + PG_CHUNK - 1) / PG_CHUNK;
   cudaError_t errs[PG_THREADS];
   std::thread th[PG_THREADS];
-  for (int w = 0; w < PG_THREADS; ++w) {
-    errs[w] = cudaSuccess;
-    th[w] = std::thread([&, w]() {
+  int started = 0;
+  auto worker = [&](int w) {
       cudaError_t e = cudaSetDevice(dev);
       const cudaStream_t st = g_ring.st[w];
       cudaEvent_t *ev = g_ring.ev[w];
@@ -256,10 +255,17 @@ static cudaError_t paged_copy(void *dst, const void *src, size_t bytes, bool to_
         }
       }
       errs[w] = e;
-    });
+  };
+  for (int w = 0; w < PG_THREADS; ++w) errs[w] = cudaSuccess;
+  for (int w = 1; w < PG_THREADS; ++w) {
+    try { th[w] = std::thread(worker, w); ++started; }
+    catch (...) { break; }             /* no thread to be had: nothing may throw across the C ABI; the caller's thread does that share too */
   }
+  worker(0);
+  for (int w = started + 1; w < PG_THREADS; ++w) worker(w);
   cudaError_t e = cudaSuccess;
-  for (int w = 0; w < PG_THREADS; ++w) { th[w].join(); if (errs[w] != cudaSuccess) e = errs[w]; }
+  for (int w = 1; w <= started; ++w) th[w].join();
+  for (int w = 0; w < PG_THREADS; ++w) if (errs[w] != cudaSuccess) e = errs[w];
   return e;
 }
 
