@@ -40,6 +40,19 @@ def test_reference_own_test_program_passes_unmodified(qb):
     assert "FAIL" not in r.stdout.upper().replace("FAILED: 0", ""), tail
 
 
+@pytest.mark.parametrize("env", [{"QUADBLAS_MODE": "fast"}, {"QUADBLAS_MODE": "fast", "OMP_NUM_THREADS": "3"}, {"OMP_NUM_THREADS": "5", "QUADBLAS_KC": "256"}])
+def test_reference_own_test_program_with_environment_selected_modes(qb, env):
+    """The same unmodified binary with the numerical mode chosen through the environment (no source change): fast mode (tensor path for
+    the large cases, window accumulator for dot / gemv), other thread counts (dot chunking), the Apple-Silicon k-panel: 20/20 each."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "quadblas_test_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/quadblas_test_b200 not built (reference sources absent when build() ran)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
+    tail = r.stdout[-2500:]
+    assert r.returncode == 0, tail + r.stderr[-1000:]
+    assert "FAIL" not in r.stdout.upper().replace("FAILED: 0", ""), tail
+
+
 @pytest.mark.parametrize("prog,expect", [("debug_test_b200", ["a*b + 1 = 7", "15"]), ("test_sleef_simd_b200", ["14"])])
 def test_reference_debug_programs_run_unmodified(qb, prog, expect):
     """/root/reference/tests/debug_test.cpp and tests/test_sleef_simd.cpp (QuadVector, QuadBLAS::dot_kernel_vectorized of
