@@ -96,11 +96,16 @@ int qb_get_honor_trans(void);
  * (the planner only declines when not even one pipeline unit fits the free device memory); then the integer-limb kernel runs. */
 void qb_set_tensor_path(int v);
 int qb_get_tensor_path(void);
-/* Fast-mode accumulate of qdot / qnrm2 / qgemv: 1 (default) = unrounded 192-bit window accumulator
- * (csrc/qwide.cuh, one rounding per result), 0 = chains of correctly rounded FMAs (the
- * reference's per-element operation, level1.hpp:24, re-associated).  Ignored in QB_MODE_REFERENCE. */
+/* Fast-mode accumulate of qdot / qnrm2 / qgemv: 2 (default) = large row-major qgemv on the FP64 pipe (csrc/qslice.cuh: 22-bit
+ * slices as exact doubles, one rounding per result, rows it cannot guarantee recomputed by the window kernel) and the window
+ * accumulator everywhere else; 1 = unrounded 192-bit window accumulator everywhere (csrc/qwide.cuh, one rounding per result);
+ * 0 = chains of correctly rounded FMAs (the reference's per-element operation, level1.hpp:24, re-associated).
+ * Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
+/* Rows of the last qb_gemv_dev that the sliced FP64 kernel declined and the window kernel recomputed (-1: that call did not take
+ * the sliced path).  Synchronises the device: diagnostics and tests. */
+int64_t qb_gemv_last_declined(void);
 /* Row-pass hook of the device qgemm (qb_gemm_dev only).  When a callback is installed, the rows of C are produced in
  * min(min_passes, ceil(m / 128)) or more passes (tensor path; the integer-limb kernel makes one) and cb(row0, rows, user) runs on
  * the calling host thread right after the work that completes those rows has been enqueued on the stream: a collective issued
@@ -231,6 +236,10 @@ int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int
                 int64_t ldc, void *stream);
 int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda,
                 const void *dx, int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream);
+/* The m rows are a block of a qgemv that has m_total rows in all (row blocks of a multi-GPU qgemv, slabs of a host matrix): the
+ * fast-mode kernel choice and column splits follow m_total, so that every y_i carries the bits of the unsplit call. */
+int qb_gemv_rows_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda,
+                     const void *dx, int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream, int64_t m_total);
 int qb_dot_dev(int64_t n, const void *dx, int64_t incx, const void *dy, int64_t incy, void *d_result,
                void *stream);
 int qb_nrm2_dev(int64_t n, const void *dx, int64_t incx, void *d_result, void *stream);

@@ -94,6 +94,7 @@ def lib():
         "qb_crt_pass_rows": (ci, [i64, i64, ci, C.POINTER(i64), ci]),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
+        "qb_gemv_last_declined": (C.c_int64, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),
         "qb_oz_last_mma_ms": (cd, [C.POINTER(ci)]),
         "qb_oz_last_mma_timeline": (ci, [C.POINTER(cd), ci]),
@@ -105,6 +106,7 @@ def lib():
         "qb_axpy": (ci, [i64, qp, vp, i64, vp, i64]),
         "qb_gemm_dev": (ci, [cc, cc, cc, i64, i64, i64, qp, vp, i64, vp, i64, qp, vp, i64, vp]),
         "qb_gemv_dev": (ci, [cc, i64, i64, qp, vp, i64, vp, i64, qp, vp, i64, vp]),
+        "qb_gemv_rows_dev": (ci, [cc, i64, i64, qp, vp, i64, vp, i64, qp, vp, i64, vp, i64]),
         "qb_dot_dev": (ci, [i64, vp, i64, vp, i64, vp, vp]),
         "qb_nrm2_dev": (ci, [i64, vp, i64, vp, vp]),
         "qb_axpy_dev": (ci, [i64, qp, vp, i64, vp, i64, vp]),

@@ -152,11 +152,16 @@ def gemm(layout, m, n, k, alpha, A, lda, B, ldb, beta, C_, ldc, transa="N", tran
                         C.byref(b), _ptr(C_), ldc), "qb_gemm")
 
 
-def gemv(layout, m, n, alpha, A, lda, x, incx, beta, y, incy):
-    """QuadBLAS::gemv (level2.hpp:85) — AFTER any transpose relabelling."""
+def gemv(layout, m, n, alpha, A, lda, x, incx, beta, y, incy, m_total=0):
+    """QuadBLAS::gemv (level2.hpp:85) — AFTER any transpose relabelling.  m_total (device tensors): these m rows are a block of a
+    qgemv with m_total rows; the fast-mode kernel is planned for the whole, so the block carries the bits of the unsplit call."""
     L = lib()
     a, b = _q(alpha), _q(beta)
     if _is_torch(y):
+        if m_total:
+            check(L.qb_gemv_rows_dev(_c(layout), m, n, C.byref(a), _ptr(A), lda, _ptr(x), incx, C.byref(b), _ptr(y), incy,
+                                     _stream(), int(m_total)), "qb_gemv_rows_dev")
+            return
         check(L.qb_gemv_dev(_c(layout), m, n, C.byref(a), _ptr(A), lda, _ptr(x), incx, C.byref(b), _ptr(y), incy,
                             _stream()), "qb_gemv_dev")
     else:
@@ -435,12 +440,19 @@ def crt_pass_rows(m, cap, shape=0):
 
 
 def set_fast_variant(v):
-    """Fast-mode accumulate of dot/nrm2/gemv: 1 = window accumulator (csrc/qwide.cuh), 0 = rounded-FMA chains."""
+    """Fast-mode accumulate of dot/nrm2/gemv: 2 (default) = sliced FP64 accumulate for large row-major gemv (csrc/qslice.cuh), window
+    accumulator elsewhere; 1 = window accumulator everywhere (csrc/qwide.cuh); 0 = rounded-FMA chains."""
     lib().qb_set_fast_variant(int(v))
 
 
 def get_fast_variant():
     return lib().qb_get_fast_variant()
+
+
+def gemv_last_declined():
+    """Rows of the last device qgemv that the sliced FP64 kernel declined (recomputed by the window kernel); -1 if that call did not
+    take the sliced path.  Synchronises the device."""
+    return int(lib().qb_gemv_last_declined())
 
 
 def oz_last_stats():

@@ -48,7 +48,8 @@ static void *g_peer[QB_MAX_PEERS];
 static int g_peer_written = 0;
 static std::atomic<int> g_host_slabs{8}; /* C slabs of the pipelined all-host qgemm / row slabs of the all-host qgemv */
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
-static std::atomic<int> g_fastvar{1}; /* fast-mode level-1/2 accumulate: 1 window accumulator, 0 rounded-FMA chains */
+static std::atomic<int> g_fastvar{2}; /* fast-mode level-1/2 accumulate: 2 = sliced FP64 accumulate where it applies (large row-major qgemv), window
+                                         accumulator elsewhere; 1 = window accumulator everywhere; 0 = rounded-FMA chains */
 int fast_variant() { return g_fastvar.load(); }
 static std::atomic<int> g_threads{0}; /* 0 = not set -> OMP_NUM_THREADS, then hardware concurrency (omp_get_max_threads) */
 
@@ -111,6 +112,7 @@ static std::recursive_mutex g_mu;
 static Scratch g_scr[QB_MAX_DEVICES];
 static int g_curdev = 0;
 static inline Scratch &S() { return g_scr[g_curdev]; }
+static struct { const uint8_t *flags = nullptr; int64_t m = 0; int dev = 0; } g_last_sliced;   /* qb_gemv_last_declined */
 
 static int ensure_device()
 {
@@ -434,7 +436,7 @@ void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : 
 int qb_get_mode(void) { return g_mode.load(); }
 void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
-void qb_set_fast_variant(int v) { g_fastvar.store(v ? 1 : 0); }
+void qb_set_fast_variant(int v) { g_fastvar.store(v <= 0 ? 0 : (v >= 2 ? 2 : 1)); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)
 {
@@ -657,17 +659,17 @@ int qb_gemm_dev(char layout, char transa, char transb, int64_t m, int64_t n, int
   return gemm_dev_impl(layout, transa, transb, m, n, k, toq(alpha), dA, lda, dB, ldb, toq(beta), dC, ldc, (cudaStream_t)stream, true);
 }
 
-int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,
-                int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream)
+static int gemv_dev_impl(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,
+                         int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream, int64_t m_plan)
 {
   if (m < 0 || n < 0) return fail(QB_ERR_ARG, "qgemv: negative dimension");
   GemvArgs g;
   g.m = m; g.n = n; g.alpha = toq(alpha); g.beta = toq(beta);
   g.A = (const q128 *)dA; g.lda = lda; g.col_major = is_col(layout);
   g.x = (const q128 *)dx; g.incx = incx; g.y = (q128 *)dy; g.incy = incy;
-  g.work = nullptr; g.work_elems = 0;
+  g.work = nullptr; g.work_elems = 0; g.m_plan = m_plan;
   const int mode = g_mode.load();
-  const int64_t need = gemv_work_elems(m, n, g.col_major, mode);
+  const int64_t need = gemv_work_elems(m, n, g.col_major, mode, m_plan);
   std::unique_lock<std::recursive_mutex> lk(g_mu, std::defer_lock);
   if (need > 0) { /* the shared scratch is held until the launch is queued (stream order protects its reuse) */
     lk.lock();
@@ -679,7 +681,35 @@ int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const v
   }
   cudaError_t e = launch_gemv(g, mode, (cudaStream_t)stream);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qgemv kernel launch", e);
+  g_last_sliced.flags = need > 0 && mode != 0 ? gemv_sliced_rowflags(g.work, m, n, g.col_major, m_plan) : nullptr;
+  g_last_sliced.m = m; g_last_sliced.dev = g_curdev;
   return QB_OK;
+}
+
+int qb_gemv_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,
+                int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream)
+{
+  return gemv_dev_impl(layout, m, n, alpha, dA, lda, dx, incx, beta, dy, incy, stream, 0);
+}
+
+int qb_gemv_rows_dev(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void *dA, int64_t lda, const void *dx,
+                     int64_t incx, const qb_quad *beta, void *dy, int64_t incy, void *stream, int64_t m_total)
+{
+  if (m_total < m) return fail(QB_ERR_ARG, "qgemv: m_total smaller than the block");
+  return gemv_dev_impl(layout, m, n, alpha, dA, lda, dx, incx, beta, dy, incy, stream, m_total);
+}
+
+/* rows of the last qb_gemv_dev on this thread's device that the sliced FP64 kernel declined and the window kernel recomputed
+ * (-1: that call did not take the sliced path).  Synchronises the device: diagnostics / tests only. */
+int64_t qb_gemv_last_declined(void)
+{
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  if (g_last_sliced.flags == nullptr) return -1;
+  std::vector<uint8_t> h((size_t)g_last_sliced.m);
+  if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(h.data(), g_last_sliced.flags, h.size(), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  int64_t c = 0;
+  for (uint8_t f : h) c += f != 0;
+  return c;
 }
 
 /* force_T > 0: reference order with that many chunks whatever the mode (qb_dot_kernel: T = 1 is dot_kernel_vectorized) */
@@ -919,7 +949,7 @@ int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void 
       if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, evs.ev[p], 0);
       if (e != cudaSuccess) break;
       const q128 *As = (const q128 *)dA + (col ? r0 : r0 * lda);
-      rc = qb_gemv_dev(layout, cnt, n, alpha, As, lda, dx, incx, beta, (q128 *)dy + r0 * incy, incy, ks);
+      rc = gemv_dev_impl(layout, cnt, n, alpha, As, lda, dx, incx, beta, (q128 *)dy + r0 * incy, incy, ks, m);   /* planned as the whole call: same bits */
       if (rc) break;
     }
     const cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ks);

@@ -21,9 +21,13 @@
  * Contract: |y^_i - y_i| <= gamma_n (|alpha| |A||x| + |beta y|)_i; for fixed shapes
  * the merge tree is fixed, so results are reproducible.
  */
+#include <algorithm>
+#include <cstdlib>
 #include "qb_internal.h"
 #include "q128_chain.cuh"
 #include "qwide.cuh"
+#include "qslice.cuh"
+#include "qb_tc.cuh"
 
 namespace qb {
 
@@ -169,16 +173,13 @@ __device__ __forceinline__ void gv_row_step(qwacc (&acc)[R], uint32_t (&bad)[R],
   }
 }
 
-template <int R, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-k_gemv_row_wide(GemvArgs g)
+template <int R, int NT>
+__device__ __forceinline__ void gv_row_wide_body(const GemvArgs &g, const int64_t row0, uint32_t *scr)
 {
   constexpr int NW = NT / 32;
   static_assert(R * NW * 8 <= R * QWA_COL_WORDS * NT, "the reduction records reuse the scratch columns");
-  __shared__ __align__(16) uint32_t scr[R * QWA_COL_WORDS * NT];
   uint32_t *sh = scr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
   qwacc acc[R];
   uint32_t bad[R];
   const q128 *ap[R];                     /* running pointers: element (row r, column tid + k * NT) */
@@ -239,13 +240,225 @@ k_gemv_row_wide(GemvArgs g)
   }
 }
 
+template <int R, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+k_gemv_row_wide(GemvArgs g)
+{
+  __shared__ __align__(16) uint32_t scr[R * QWA_COL_WORDS * NT];
+  gv_row_wide_body<R, NT>(g, (int64_t)blockIdx.x * R, scr);
+}
+
+/* the rows the sliced kernel below declined (rowflag != 0), one row per CTA pass */
+template <int NT>
+__global__ void __launch_bounds__(NT, 8)
+k_gemv_row_wide_sel(GemvArgs g, const uint8_t *rowflag)
+{
+  __shared__ __align__(16) uint32_t scr[QWA_COL_WORDS * NT];
+  for (int64_t row = blockIdx.x; row < g.m; row += gridDim.x) {
+    if (rowflag[row] == 0) continue;                /* uniform over the CTA */
+    __syncthreads();                                /* the scratch of the previous row is free */
+    gv_row_wide_body<1, NT>(g, row, scr);
+  }
+}
+
+/* ------------------------------------------------------------------ fast mode on the FP64 pipe (qslice.cuh), both layouts
+ * k_gv_xscan: EX = largest exponent field of x, and whether x holds an Inf / NaN / nonzero subnormal (then every row goes to
+ * the window kernel).  k_gv_xtab: per x_j a 200-byte table {6 zeros, +X_0..5, 6 zeros, -X_0..5, e(x_j)} — what qs_step reads at the
+ * dynamic slice offset, ready to be copied.  k_gemv_f64: ONE THREAD PER ROW (no cross-thread merge, no per-thread staging of x):
+ * a CTA owns 128 rows and a range of columns (gridDim.y splits); tiles of 128 rows x 8 columns of A arrive by TMA into a
+ * two-stage ring (row-major: box {128 B, 128 rows} with the 128-byte swizzle, so that 32 threads reading the same column of 32
+ * consecutive rows hit 32 different bank groups; col-major: box {128 rows, 8 columns}, consecutive threads read consecutive
+ * quads), the x tables of the 8 columns by one bulk copy on the same mbarrier; elements past m or n read as zero (TMA fill, zero
+ * tables), so there is no edge code.  Each thread runs qs_step on its row (about 70 instructions per element, 64 registers, 6
+ * CTAs per SM), keeps its 256-bit window in shared memory, and ends with a record {window as qwide, anchor, Dmax, flags}.
+ * k_gemv_f64_fin folds the records of the column splits in order, applies qs_accept and either stores
+ * y_i = fma(alpha, S_i, mul(beta, y_i)) or flags the row for the window kernel (k_gemv_row_wide_sel / k_gemv_col_wide). */
+__global__ void k_gv_xscan(GemvArgs g, int32_t *hdr)
+{
+  int32_t emax = 0;
+  uint32_t special = 0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < g.n; j += (int64_t)gridDim.x * blockDim.x) {
+    const qop o = qop_load(g.x[j * g.incx]);
+    if (o.e == 0x7fff || (o.e == 0 && (o.m0 | o.m1 | o.m2 | o.m3) != 0u)) special = 1u;
+    else emax = max(emax, o.e);
+  }
+  emax = __reduce_max_sync(0xffffffffu, emax);
+  special = __reduce_or_sync(0xffffffffu, special);
+  if ((threadIdx.x & 31) == 0) {
+    if (emax) atomicMax(hdr, emax);
+    if (special) atomicOr(reinterpret_cast<unsigned *>(hdr) + 1, 1u);
+  }
+}
+
+constexpr int GVT_ROWS = 128;            /* rows per CTA = threads per CTA */
+constexpr int GVT_COLS = 8;              /* columns per tile: 8 x 16 B = the 128-byte swizzle span */
+constexpr int GVT_XDBL = QS_XCOL + 1;    /* doubles per column of the x table */
+constexpr int GVT_GRP = 4;               /* elements stepped between two looks at the rare flags */
+constexpr int GVT_TILE_BYTES = GVT_ROWS * GVT_COLS * 16;
+constexpr int GVT_XT_BYTES = GVT_COLS * GVT_XDBL * 8;
+constexpr int GVT_SMEM = 2 * GVT_TILE_BYTES + 2 * GVT_XT_BYTES + 4 * GVT_ROWS * 8 + 64;
+
+__global__ void k_gv_xtab(GemvArgs g, const int32_t *hdr, double *tab, int64_t npad)
+{
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= npad) return;
+  qs_xrec r;
+  if (j < g.n) qs_xrec_make(g.x[j * g.incx], hdr[0], r);
+  else { for (int l = 0; l < QS_NS; ++l) r.X[l] = 0.0; r.ex = QS_EXNONE; }
+  double *dst = tab + j * GVT_XDBL;
+#pragma unroll
+  for (int l = 0; l < QS_NS; ++l) { dst[l] = 0.0; dst[QS_NS + l] = r.X[l]; dst[2 * QS_NS + l] = 0.0; dst[3 * QS_NS + l] = -r.X[l]; }
+  dst[QS_XCOL] = __hiloint2double(0, r.ex);
+}
+
+template <int NT>
+__device__ __noinline__ void gv_flush(double c0, double c1, double c2, double c3, double c4, double c5, uint64_t *w)
+{
+  qs_flush(c0, c1, c2, c3, c4, c5, w, NT);
+}
+
+/* the element the hot form left out (it met only zeros there): qs_rare moves the anchor or flags the row, then the element is
+ * stepped.  Through memory (t = the six columns, st = {anchor, flags}) so that the call does not pin the hot loop's registers. */
+template <int NT>
+__device__ __noinline__ void gv_rare_mem(double *t, int32_t *st, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint64_t *w, const double *col)
+{
+  qs_cols C; C.c0 = t[0]; C.c1 = t[1]; C.c2 = t[2]; C.c3 = t[3]; C.c4 = t[4]; C.c5 = t[5];
+  qs_row S; S.anc = st[0]; S.dmax = 0;
+  uint32_t flags = (uint32_t)st[1];
+  const uint32_t e = (w3 >> 16) & 0x7fffu;
+  /* an earlier element of the same group may have moved the anchor above this one */
+  const uint32_t sh = ((uint32_t)(e - 1u) >= (uint32_t)S.anc) ? qs_rare(C, S, flags, e, w0, w1, w2, w3, w, NT) : min((uint32_t)S.anc - e, QS_SHMAX);
+  if (sh < QS_SHMAX) qs_step(C, w0, w1, w2, w3, sh, col, 1);
+  t[0] = C.c0; t[1] = C.c1; t[2] = C.c2; t[3] = C.c3; t[4] = C.c4; t[5] = C.c5;
+  st[0] = S.anc; st[1] = (int32_t)flags;
+}
+
+/* record of one (row, column split): the window as a qwide + flags (gv_store), then anchor and Dmax */
+constexpr int GVT_REC = 12;
+
+template <bool COL>
+__global__ void __launch_bounds__(GVT_ROWS, 6)
+k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *hdr, const double *tab, int64_t jsplit, uint32_t *part)
+{
+  /* the kernel has no static shared memory, so the dynamic array starts the CTA's window and the 1024-byte alignment the swizzled
+   * tiles need is the declared one (checked below); used directly so that every access stays an LDS / STS */
+  extern __shared__ __align__(1024) unsigned char gvt_sm[];
+  uint64_t *win = reinterpret_cast<uint64_t *>(gvt_sm + 2 * GVT_TILE_BYTES + 2 * GVT_XT_BYTES);
+  uint64_t *full = win + 4 * GVT_ROWS;
+  const int tid = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * GVT_ROWS, row = row0 + tid;
+  const int64_t j0 = (int64_t)blockIdx.y * jsplit, j1 = min(g.n, j0 + jsplit);
+  const int ntiles = hdr[1] != 0 ? 0 : (int)((j1 - j0 + GVT_COLS - 1) / GVT_COLS);   /* Inf / NaN / subnormal in x: nothing here, every row flagged */
+  const int32_t EX = hdr[0];
+  auto issue = [&](int t, int s) {
+    const int64_t j = j0 + (int64_t)t * GVT_COLS;
+    tc::mbar_expect_tx(&full[s], GVT_TILE_BYTES + GVT_XT_BYTES);
+    if (COL) tc::tma_load_2d(gvt_sm + s * GVT_TILE_BYTES, &tmA, &full[s], (int)(row0 * 2), (int)j);
+    else tc::tma_load_2d(gvt_sm + s * GVT_TILE_BYTES, &tmA, &full[s], (int)(j * 4), (int)row0);
+    tc::bulk_load_1d(gvt_sm + 2 * GVT_TILE_BYTES + s * GVT_XT_BYTES, tab + j * GVT_XDBL, GVT_XT_BYTES, &full[s]);
+  };
+  if (tid == 0) {
+    if ((tc::smem_u32(gvt_sm) & 1023u) != 0u) __trap();
+    tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
+    tc::fence_barrier_init();
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) win[k * GVT_ROWS + tid] = 0ull;
+  __syncthreads();
+  if (tid == 0) {
+    if (ntiles > 0) issue(0, 0);
+    if (ntiles > 1) issue(1, 1);
+  }
+  qs_cols C = qs_cols_zero();
+  int32_t anc = QS_ANCMIN, dmax = QS_EXNONE;
+  uint32_t flags = hdr[1] != 0 ? QS_FALLBACK : 0u;
+  uint64_t *wn = win + tid;
+  const uint32_t aoff = COL ? (uint32_t)tid * 16u : (uint32_t)tid * 128u;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t & 1;
+    tc::mbar_wait(&full[s], (uint32_t)(t >> 1) & 1u);
+    const unsigned char *at = gvt_sm + s * GVT_TILE_BYTES + aoff;
+    const double *xs = reinterpret_cast<const double *>(gvt_sm + 2 * GVT_TILE_BYTES + s * GVT_XT_BYTES);
+    /* groups of GVT_GRP elements: the hot steps are branch-free so that their decode / convert / multiply chains interleave in one
+     * instruction stream; an element the hot form cannot take (zero / subnormal / Inf / NaN, or larger than everything before it
+     * in this row) meets only the six zeros there and is redone after its group, in order */
+#pragma unroll
+    for (int c0 = 0; c0 < GVT_COLS; c0 += GVT_GRP) {
+      uint4 v[GVT_GRP];
+      bool rare[GVT_GRP], any = false;
+#pragma unroll
+      for (int u = 0; u < GVT_GRP; ++u) {
+        const int c = c0 + u;
+        v[u] = *reinterpret_cast<const uint4 *>(COL ? at + c * (GVT_ROWS * 16) : at + ((c ^ (tid & 7)) << 4));
+      }
+#pragma unroll
+      for (int u = 0; u < GVT_GRP; ++u) {
+        const double *col = xs + (c0 + u) * GVT_XDBL;
+        const uint32_t e = (v[u].w >> 16) & 0x7fffu;
+        rare[u] = (uint32_t)(e - 1u) >= (uint32_t)anc;
+        any |= rare[u];
+        const uint32_t sh = min((uint32_t)anc - e, QS_SHMAX);   /* an element above the anchor wraps to a huge shift, a zero gives anc >= QS_ANCMIN: both meet only zeros */
+        qs_step(C, v[u].x, v[u].y, v[u].z, v[u].w, sh, col, 1);
+        dmax = max(dmax, (int32_t)e + __double2loint(col[QS_XCOL]));
+      }
+      if (any) {
+#pragma unroll
+        for (int u = 0; u < GVT_GRP; ++u) {
+          if (!rare[u]) continue;
+          double tt[6] = {C.c0, C.c1, C.c2, C.c3, C.c4, C.c5};
+          int32_t st[2] = {anc, (int32_t)flags};
+          gv_rare_mem<GVT_ROWS>(tt, st, v[u].x, v[u].y, v[u].z, v[u].w, wn, xs + (c0 + u) * GVT_XDBL);
+          C.c0 = tt[0]; C.c1 = tt[1]; C.c2 = tt[2]; C.c3 = tt[3]; C.c4 = tt[4]; C.c5 = tt[5];
+          anc = st[0]; flags = (uint32_t)st[1];
+        }
+      }
+    }
+    if ((t & 7) == 7) {                   /* 64 elements: the columns are still exact */
+      gv_flush<GVT_ROWS>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
+      C = qs_cols_zero();
+    }
+    __syncthreads();                      /* every thread is done with stage s */
+    if (tid == 0 && t + 2 < ntiles) issue(t + 2, s);
+  }
+  gv_flush<GVT_ROWS>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
+  if (row < g.m) {
+    const qwide v = qs_to_qwide(wn, GVT_ROWS, anc, EX);
+    uint32_t *dst = part + ((int64_t)blockIdx.y * g.m + row) * GVT_REC;
+    gv_store(dst, v, flags);
+    dst[8] = (uint32_t)anc; dst[9] = (uint32_t)dmax;
+  }
+}
+
+/* fold the column splits of a row in order; store the row or flag it */
+__global__ void k_gemv_f64_fin(GemvArgs g, const int32_t *hdr, int splits, const uint32_t *part, uint8_t *rowflag)
+{
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.m) return;
+  uint32_t b = 0;
+  const uint32_t *src = part + i * GVT_REC;
+  qwide v = gv_load(src, b);
+  int32_t am = (int32_t)src[8], dm = (int32_t)src[9];
+#pragma unroll 1
+  for (int s = 1; s < splits; ++s) {
+    src = part + ((int64_t)s * g.m + i) * GVT_REC;
+    v = gv_merge(v, gv_load(src, b));
+    am = max(am, (int32_t)src[8]); dm = max(dm, (int32_t)src[9]);
+  }
+  const bool ok = qs_accept(am, hdr[0], dm, b);
+  rowflag[i] = ok ? 0 : 1;
+  if (ok) {
+    q128 *yp = g.y + i * g.incy;
+    *yp = gemv_epilogue(g.alpha, qw_finish(v, 0u), g.beta, *yp);
+  }
+}
+
 /* Col-major (and row-major transposed): thread per row, consecutive threads read consecutive quads
  * of a column; the column range is split over gridDim.y CTAs so that the grid fills the chip, each
  * writing its window to part[split][row]; k_gemv_col_fin folds the splits in order and applies the
  * epilogue. */
 template <int ROWS, int TW>
 __global__ void __launch_bounds__(ROWS)
-k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
+k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part, const uint8_t *only)
 {
   constexpr int U = 4;                  /* columns in flight per thread, one scratch column each */
   static_assert(TW % U == 0, "tile width");
@@ -254,6 +467,7 @@ k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
   const int tid = threadIdx.x;
   const int64_t i = (int64_t)blockIdx.x * ROWS + tid;
   const bool live = i < g.m;
+  if (only != nullptr && !__syncthreads_or(live && only[i] != 0)) return;   /* none of this CTA's rows was declined by the sliced kernel */
   const int64_t jb = (int64_t)blockIdx.y * jchunk;
   const int64_t je = (jb + jchunk < g.n) ? jb + jchunk : g.n;
   qwacc acc = qwa_zero();
@@ -294,10 +508,10 @@ k_gemv_col_wide(GemvArgs g, int64_t jchunk, uint32_t *part)
   if (live) gv_store(part + ((int64_t)blockIdx.y * g.m + i) * 8, qwa_fold(acc), bad);
 }
 
-__global__ void k_gemv_col_fin(GemvArgs g, int splits, const uint32_t *part)
+__global__ void k_gemv_col_fin(GemvArgs g, int splits, const uint32_t *part, const uint8_t *only)
 {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= g.m) return;
+  if (i >= g.m || (only != nullptr && only[i] == 0)) return;
   uint32_t b = 0;
   qwide v = gv_load(part + i * 8, b);
 #pragma unroll 1
@@ -319,17 +533,101 @@ static int gemv_col_splits(int64_t m, int64_t n)
   return (int)s;
 }
 
-/* 16-byte elements of device scratch the fast col-major path needs (32-byte window per split x row) */
-int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode)
+/* the sliced FP64 kernel pays four small launches around the product: worth it from about a million elements, and the acceptance
+ * bound of qslice.cuh is stated for n >= 128 */
+static bool gemv_sliced(int64_t m, int64_t n) { return fast_variant() == 2 && n >= 512 && m >= 148 * 4 && m * n >= (1 << 20); }
+static int64_t gemv_sliced_npad(int64_t n) { return (n + GVT_COLS - 1) / GVT_COLS * GVT_COLS; }
+/* column splits of the sliced kernel: about 12 CTAs per SM in all (two waves of 6), at least 256 columns per split */
+static int gemv_sliced_splits(int64_t m, int64_t n)
 {
-  if (mode == 0 || !col_major || fast_variant() == 0 || m <= 0 || n <= 0) return 0;
-  return 2 * (int64_t)gemv_col_splits(m, n) * m;
+  const int64_t rb = (m + GVT_ROWS - 1) / GVT_ROWS;
+  int64_t s = (148 * 12 + rb - 1) / rb;
+  s = std::min<int64_t>(s, n / 256);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+}
+struct GvSlicedLayout { int64_t tab, flags, part, colwork, total; };   /* offsets in 16-byte elements */
+static GvSlicedLayout gemv_sliced_layout(int64_t m, int64_t n, int col_major, int64_t mp)
+{
+  GvSlicedLayout L;
+  L.tab = 4;
+  L.flags = L.tab + (GVT_XDBL * gemv_sliced_npad(n) + 1) / 2;
+  L.part = L.flags + (m + 15) / 16;
+  L.colwork = L.part + (int64_t)gemv_sliced_splits(mp, n) * m * GVT_REC / 4;
+  L.total = L.colwork + (col_major ? 2 * (int64_t)gemv_col_splits(m, n) * m : 0);
+  return L;
+}
+
+/* 16-byte elements of device scratch: fast col-major = a 32-byte window per split x row; the sliced kernel adds a 64-byte header,
+ * the 200-byte table of every (padded) element of x, one flag byte per row and a 48-byte record per (split, row) */
+int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode, int64_t m_plan)
+{
+  if (mode == 0 || fast_variant() == 0 || m <= 0 || n <= 0) return 0;
+  const int64_t mp = m_plan > 0 ? m_plan : m;
+  if (gemv_sliced(mp, n)) return gemv_sliced_layout(m, n, col_major, mp).total;
+  return col_major ? 2 * (int64_t)gemv_col_splits(m, n) * m : 0;
+}
+
+const uint8_t *gemv_sliced_rowflags(const q128 *work, int64_t m, int64_t n, int col_major, int64_t m_plan)
+{
+  const int64_t mp = m_plan > 0 ? m_plan : m;
+  return gemv_sliced(mp, n) ? reinterpret_cast<const uint8_t *>(work + gemv_sliced_layout(m, n, col_major, mp).flags) : nullptr;
+}
+
+bool make_quad_map(CUtensorMap *tm, const void *base, int64_t inner, int64_t outer, int64_t stride_bytes, int box_inner, int box_outer, bool swizzle128);
+
+static cudaError_t launch_gemv_col_window(const GemvArgs &a, q128 *work, const uint8_t *only, cudaStream_t st)
+{
+  const int splits = gemv_col_splits(a.m, a.n);
+  const int64_t jchunk = (((a.n + splits - 1) / splits) + 31) / 32 * 32;
+  const int gy = (int)((a.n + jchunk - 1) / jchunk);
+  dim3 grid((unsigned)((a.m + GV_COL_ROWS - 1) / GV_COL_ROWS), (unsigned)gy);
+  k_gemv_col_wide<GV_COL_ROWS, 32><<<grid, GV_COL_ROWS, 0, st>>>(a, jchunk, reinterpret_cast<uint32_t *>(work), only);
+  k_gemv_col_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, gy, reinterpret_cast<const uint32_t *>(work), only);
+  count_launch(2);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_gemv_sliced(const GemvArgs &a, cudaStream_t st)
+{
+  const int64_t mp = a.m_plan > 0 ? a.m_plan : a.m;
+  const GvSlicedLayout L = gemv_sliced_layout(a.m, a.n, a.col_major, mp);
+  if (a.work == nullptr || a.work_elems < L.total) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a.A) & 15u) != 0) return cudaErrorMisalignedAddress;
+  CUtensorMap tm;
+  const bool ok = a.col_major ? make_quad_map(&tm, a.A, a.m, a.n, a.lda * 16, GVT_ROWS, GVT_COLS, false)
+                              : make_quad_map(&tm, a.A, a.n, a.m, a.lda * 16, GVT_COLS, GVT_ROWS, true);
+  if (!ok) return cudaErrorNotSupported;
+  const int64_t npad = gemv_sliced_npad(a.n);
+  int32_t *hdr = reinterpret_cast<int32_t *>(a.work);
+  double *tab = reinterpret_cast<double *>(a.work + L.tab);
+  uint8_t *rowflag = reinterpret_cast<uint8_t *>(a.work + L.flags);
+  uint32_t *part = reinterpret_cast<uint32_t *>(a.work + L.part);
+  cudaError_t e = cudaMemsetAsync(hdr, 0, 64, st);
+  if (e != cudaSuccess) return e;
+  k_gv_xscan<<<(unsigned)std::min<int64_t>((a.n + 255) / 256, 148 * 8), 256, 0, st>>>(a, hdr);
+  k_gv_xtab<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(a, hdr, tab, npad);
+  const int splits = gemv_sliced_splits(mp, a.n);
+  const int64_t jsplit = (((a.n + splits - 1) / splits) + GVT_COLS - 1) / GVT_COLS * GVT_COLS;
+  const int gy = (int)((a.n + jsplit - 1) / jsplit);
+  dim3 grid((unsigned)((a.m + GVT_ROWS - 1) / GVT_ROWS), (unsigned)gy);
+  if (a.col_major) k_gemv_f64<true><<<grid, GVT_ROWS, GVT_SMEM, st>>>(tm, a, hdr, tab, jsplit, part);
+  else k_gemv_f64<false><<<grid, GVT_ROWS, GVT_SMEM, st>>>(tm, a, hdr, tab, jsplit, part);
+  k_gemv_f64_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, hdr, gy, part, rowflag);
+  count_launch(4);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  /* the rows the sliced kernel declined: the window kernel of the same layout, other rows untouched */
+  if (a.col_major) return launch_gemv_col_window(a, a.work + L.colwork, rowflag, st);
+  k_gemv_row_wide_sel<128><<<(unsigned)std::min<int64_t>(a.m, 148 * 8), 128, 0, st>>>(a, rowflag);
+  count_launch();
+  return cudaGetLastError();
 }
 
 cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st)
 {
   if (a.m == 0 || a.n == 0) return cudaSuccess; /* level2.hpp:21,59: y untouched */
   if (mode != 0 && fast_variant() != 0) {
+    if (gemv_sliced(a.m_plan > 0 ? a.m_plan : a.m, a.n)) return launch_gemv_sliced(a, st);
     if (!a.col_major) {
       /* R rows per CTA: 4 when that still gives >= 2 CTAs per SM, else fewer rows for more CTAs */
       /* R rows per CTA share the unpacked x_j; 2 x 128 measured best at m = 32768 (96 registers, 5 CTAs per SM);
@@ -341,14 +639,8 @@ cudaError_t launch_gemv(const GemvArgs &a, int mode, cudaStream_t st)
 #undef GV_LAUNCH
       count_launch();
     } else {
-      const int splits = gemv_col_splits(a.m, a.n);
-      if (a.work == nullptr || a.work_elems < 2 * (int64_t)splits * a.m) return cudaErrorInvalidValue;
-      const int64_t jchunk = (((a.n + splits - 1) / splits) + 31) / 32 * 32;
-      const int gy = (int)((a.n + jchunk - 1) / jchunk);
-      dim3 grid((unsigned)((a.m + GV_COL_ROWS - 1) / GV_COL_ROWS), (unsigned)gy);
-      k_gemv_col_wide<GV_COL_ROWS, 32><<<grid, GV_COL_ROWS, 0, st>>>(a, jchunk, reinterpret_cast<uint32_t *>(a.work));
-      k_gemv_col_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, gy, reinterpret_cast<const uint32_t *>(a.work));
-      count_launch(2);
+      if (a.work == nullptr || a.work_elems < 2 * (int64_t)gemv_col_splits(a.m, a.n) * a.m) return cudaErrorInvalidValue;
+      return launch_gemv_col_window(a, a.work, nullptr, st);
     }
     return cudaGetLastError();
   }

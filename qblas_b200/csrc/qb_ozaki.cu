@@ -606,6 +606,23 @@ static PFN_encodeTiled get_encode()
   return fn;
 }
 
+/* 2-D map over a matrix of 16-byte elements (qb_level2.cu: tiles of A for the sliced qgemv).  swizzle128: dims {inner * 4 uint32,
+ * outer}, box {box_inner * 4, box_outer} with box_inner * 16 = 128 bytes; else dims {inner * 2 uint64, outer}, box {box_inner * 2,
+ * box_outer}.  stride = bytes between consecutive outer indices.  Out-of-range elements read as zero. */
+bool make_quad_map(CUtensorMap *tm, const void *base, int64_t inner, int64_t outer, int64_t stride_bytes, int box_inner, int box_outer, bool swizzle128)
+{
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const int per = swizzle128 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)inner * per, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(box_inner * per), (cuuint32_t)box_outer};
+  cuuint32_t es[2] = {1, 1};
+  return enc(tm, swizzle128 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<void *>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 /* planes [S][rows][Kp] int8 -> 3-D map {Kp, rows, S}, box {128, box_rows, 1}, 128-byte swizzle; rows
  * beyond `rows` are zero-filled by the TMA unit */
 static bool make_plane_map(CUtensorMap *tm, const int8_t *planes, int S, int64_t rows, int64_t Kp, int box_rows, int64_t pstride = 0)

@@ -1,7 +1,7 @@
 /*
  * qb_tc.cuh — thin inline-PTX layer for the Blackwell (sm_100a) tensor path: mbarrier, TMA
  * (cp.async.bulk.tensor), tcgen05 alloc / mma kind::i8 / commit / ld, shared-memory matrix and
- * instruction descriptors.  Used only by qb_ozaki.cu.  No reference counterpart: the reference
+ * instruction descriptors.  Used by qb_ozaki.cu (tensor path) and qb_level2.cu (TMA tiles of the sliced qgemv).  No reference counterpart: the reference
  * (/root/reference) has no accelerator code at all.
  */
 #pragma once
@@ -60,6 +60,21 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, ui
 {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+/* 2-D tiled load global -> shared, completion on an mbarrier */
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1)
+{
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+/* contiguous bulk copy global -> shared (bytes a multiple of 16, both addresses 16-byte aligned), completion on an mbarrier */
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
 

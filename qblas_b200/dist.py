@@ -232,9 +232,9 @@ class _CudaEngine:
         from . import api
         return api.gemm_peer_written()
 
-    def gemv(self, m, n, alpha, A, lda, x, beta, y):
+    def gemv(self, m, n, alpha, A, lda, x, beta, y, m_total=0):
         from . import api
-        api.gemv("R", m, n, alpha, A, lda, x, 1, beta, y, 1)
+        api.gemv("R", m, n, alpha, A, lda, x, 1, beta, y, 1, m_total=m_total)
 
     def dot_partials(self, n_local, x, y, chunk, nchunks, out):
         from . import api
@@ -435,7 +435,7 @@ def qgemv_row_sharded(m, n, alpha, A_blk, x, beta, y_full, *, src=0, compute=Non
     lo, hi = row_block(m, world, rank)
     dist.broadcast(_bytes(x), src=src, group=group)
     if hi > lo:
-        compute.gemv(hi - lo, n, alpha, A_blk, n, x, beta, y_full[lo:hi])
+        compute.gemv(hi - lo, n, alpha, A_blk, n, x, beta, y_full[lo:hi], m_total=m)   # planned as the whole qgemv: same bits as one GPU
     for r in range(world):
         l2, h2 = row_block(m, world, r)
         if h2 > l2:

@@ -10,6 +10,7 @@
 #include "../../qblas_b200/csrc/q128.cuh"
 #include "../../qblas_b200/csrc/q128_chain.cuh"
 #include "../../qblas_b200/csrc/qwide.cuh"
+#include "../../qblas_b200/csrc/qslice.cuh"
 
 using namespace qb;
 
@@ -60,5 +61,57 @@ void qwide_tree(int64_t n, const q128 *x, const q128 *y, q128 *out)
     for (int64_t i = 0; i + s < n; i += 2 * s) qw_merge(acc[i], acc[i + s]);
   *out = n > 0 ? qw_finish(acc[0], bad) : q_zero(0);
   delete[] acc;
+}
+
+/* the sliced FP64 accumulate (qslice.cuh) as k_gemv_row_f64 runs it on one row: thread t of `lanes` takes the elements t, t + lanes, ...
+ * of the row a against x, flushes its columns every QS_TILE steps, the windows are merged in lane order and rounded once.
+ * Returns 1 when the row passes the acceptance test (the kernel then stores this result), 0 when it would be recomputed by the
+ * window kernel, -1 when x itself sends the whole call there (Inf / NaN / subnormal in x).  info = {anchor, EX, dmax, flags}. */
+int qslice_dot(int64_t n, const q128 *a, const q128 *x, int lanes, q128 *out, int32_t *info)
+{
+  int32_t EX = 0;
+  for (int64_t j = 0; j < n; ++j) {
+    const qop o = qop_load(x[j]);
+    if (o.e == 0x7fff || (o.e == 0 && (o.m0 | o.m1 | o.m2 | o.m3))) return -1;
+    if (o.e > EX) EX = o.e;
+  }
+  qs_xrec *rec = new qs_xrec[n > 0 ? n : 1];
+  for (int64_t j = 0; j < n; ++j) qs_xrec_make(x[j], EX, rec[j]);
+  qwide v = qw_zero();
+  int32_t anc = QS_ANCMIN, dmax = QS_EXNONE;
+  uint32_t flags = 0;
+  for (int t = 0; t < lanes; ++t) {
+    qs_cols C = qs_cols_zero();
+    qs_row S; S.anc = QS_ANCMIN; S.dmax = QS_EXNONE;
+    uint64_t w[4] = {0, 0, 0, 0};
+    double col[QS_XCOL];
+    qs_col_init(col, 1);
+    int steps = 0;
+    for (int64_t j = t; j < n; j += lanes) {
+      qs_col_set(col, 1, rec[j].X);
+      const uint32_t w0 = (uint32_t)a[j].lo, w1 = (uint32_t)(a[j].lo >> 32), w2 = (uint32_t)a[j].hi, w3 = (uint32_t)(a[j].hi >> 32);
+      const uint32_t e = (w3 >> 16) & 0x7fffu;
+      /* as the kernel does it: the hot step for every element (an element above the anchor or a zero meets only zeros there),
+       * then the rare ones again after qs_rare */
+      uint32_t sh = (uint32_t)S.anc - e;
+      sh = sh > QS_SHMAX ? QS_SHMAX : sh;
+      qs_step(C, w0, w1, w2, w3, sh, col, 1);
+      if ((uint32_t)(e - 1u) >= (uint32_t)S.anc) {
+        sh = qs_rare(C, S, flags, e, w0, w1, w2, w3, w, 1);
+        if (sh < QS_SHMAX) qs_step(C, w0, w1, w2, w3, sh, col, 1);
+      }
+      const int32_t d = (int32_t)e + rec[j].ex;
+      S.dmax = d > S.dmax ? d : S.dmax;
+      if (++steps == QS_TILE) { qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1); C = qs_cols_zero(); steps = 0; }
+    }
+    qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1);
+    qw_merge(v, qs_to_qwide(w, 1, S.anc, EX));
+    anc = S.anc > anc ? S.anc : anc;
+    dmax = S.dmax > dmax ? S.dmax : dmax;
+  }
+  delete[] rec;
+  *out = qw_finish(v, 0);
+  info[0] = anc; info[1] = EX; info[2] = dmax; info[3] = (int32_t)flags;
+  return qs_accept(anc, EX, dmax, flags) ? 1 : 0;
 }
 }

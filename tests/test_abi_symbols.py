@@ -146,6 +146,6 @@ def test_measured_defaults():
     assert L.qb_get_tensor_window() == 144        # bits per operand window when the spans do not fit the moduli
     assert qblas_b200.get_tensor_unit() == (2048, 4096) and qblas_b200.get_tensor_ramp() == (0, 0)   # pipeline unit: A pass x B panel
     assert L.qb_get_tensor_pass_shape() == 0      # equal row passes
-    assert L.qb_get_fast_variant() == 1           # qdot / qnrm2 / qgemv: window accumulator
+    assert L.qb_get_fast_variant() == 2           # large row-major qgemv: sliced FP64 accumulate; qdot / qnrm2 / the rest: window accumulator
     assert L.qb_get_gemm_peer_written() == 0
     assert L.qb_get_host_slabs() == 8             # pipelined all-host qgemm / qgemv: eight slabs

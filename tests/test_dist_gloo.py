@@ -71,7 +71,7 @@ class OracleEngine:
                 self.mem.view(p, m * n * 16).copy_(C.view(torch.uint8).reshape(-1)[:m * n * 16])
             self.wrote = len(self.peers)
 
-    def gemv(self, m, n, alpha, A, lda, x, beta, y):
+    def gemv(self, m, n, alpha, A, lda, x, beta, y, m_total=0):
         self.o.gemv("R", m, n, alpha, self._np(A), lda, self._np(x), 1, beta, self._np(y), 1)
 
     def dot_partials(self, n_local, x, y, chunk, nchunks, out):

@@ -34,8 +34,9 @@ def _round(fr):
 @pytest.fixture()
 def fast(qb):
     qb.set_mode(qb.MODE_FAST)
-    qb.set_fast_variant(1)
+    qb.set_fast_variant(1)                          # the window accumulator everywhere (tests/test_gpu_gemv_sliced.py covers variant 2)
     yield qb
+    qb.set_fast_variant(2)
     qb.set_mode(qb.MODE_REFERENCE)
 
 
@@ -179,7 +180,7 @@ def test_fast_variant_zero_still_available(qb, oracle):
         qb.set_fast_variant(1)
         r1 = qb.dot(n, x, 1, y, 1)
     finally:
-        qb.set_fast_variant(1); qb.set_mode(qb.MODE_REFERENCE)
+        qb.set_fast_variant(2); qb.set_mode(qb.MODE_REFERENCE)
     fx, fy = _fr_vec(x), _fr_vec(y)
     tot = sum(a * b for a, b in zip(fx, fy)); sab = sum(abs(a * b) for a, b in zip(fx, fy))
     u = Fraction(1, 2 ** 113)

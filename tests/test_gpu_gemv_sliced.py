@@ -1,0 +1,151 @@
+"""GPU checks of the fast-mode qgemv on the FP64 pipe (k_gemv_f64, csrc/qslice.cuh; both layouts) through the C ABI.
+
+The checker is the oracle's long accumulator (oracle/qoracle.c: exact sums rounded once, and err / (n u sum|a||x|) per row): every
+row must keep the fast-mode contract (ratio <= 1) — accepted rows in fact the tighter bound of the qslice.cuh header, under which
+the result is the exact sum rounded once except when that sum lies within 2^-14 ulp-ish of a rounding boundary — and the rows the
+kernel declines must carry exactly the bits of the window kernel (fast variant 1), which recomputes them."""
+import numpy as np
+import pytest
+import torch
+
+import qgen
+from gpu_util import dev_random, to_dev, to_host
+from qblas_b200 import quad
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def fast(qb):
+    qb.set_mode(qb.MODE_FAST)
+    qb.set_fast_variant(2)
+    yield qb
+    qb.set_fast_variant(2)
+    qb.set_mode(qb.MODE_REFERENCE)
+
+
+def _gemv(qb, m, n, A, lda, x, y0, alpha=1.0, beta=0.0, incx=1, incy=1, variant=2, layout="R"):
+    qb.set_fast_variant(variant)
+    try:
+        dy = to_dev(y0)
+        qb.gemv(layout, m, n, alpha, to_dev(A), lda, to_dev(x), incx, beta, dy, incy)
+        declined = qb.gemv_last_declined()
+        return to_host(dy), declined
+    finally:
+        qb.set_fast_variant(2)
+
+
+def _rows_check(oracle, m, n, A, lda, x, got, layout="R"):
+    idx = np.stack([np.arange(m), np.zeros(m, dtype=np.int64)], axis=1)
+    exact, ratio, klass = oracle.exact_dot_check(layout, n, A, lda, x, 1 if layout == "R" else n, idx, got)
+    return exact, ratio, klass
+
+
+@pytest.mark.parametrize("layout", ["R", "C"])
+@pytest.mark.parametrize("kind,m,n,pad", [("D113", 1500, 1100, 3), ("D53", 1501, 1027, 0), ("Dexp", 2000, 700, 5), ("D113", 640, 4096, 0)])
+def test_sliced_gemv_every_row_against_the_long_accumulator(fast, oracle, layout, kind, m, n, pad):
+    rng = np.random.default_rng(m + n)
+    lda = (n if layout == "R" else m) + pad
+    A = qgen.matrix(rng, m if layout == "R" else n, n if layout == "R" else m, kind, lda)
+    x = quad.random_quads(rng, n, "D53" if kind == "D53" else "D113"); y0 = quad.random_quads(rng, m)
+    got, declined = _gemv(fast, m, n, A, lda, x, y0, layout=layout)
+    assert declined >= 0, "the call did not take the sliced path"
+    exact, ratio, klass = _rows_check(oracle, m, n, A, lda, x, got, layout)
+    assert (klass == 0).all()
+    assert ratio.max() <= 1.0, ratio.max()                       # the contract, every row
+    same = quad.same_bits(got, exact)
+    assert same.mean() > 0.995, same.mean()                      # ... and nearly always the exact sum rounded once
+    assert ratio.max() <= 2.0 / n + 1e-6                         # one rounding of a sum is at most ~1/n of n u sum|a||x|
+    if kind != "Dexp":
+        assert declined == 0
+    got2, _ = _gemv(fast, m, n, A, lda, x, y0, layout=layout)
+    assert quad.same_bits(got, got2).all()                       # deterministic
+
+
+@pytest.mark.parametrize("layout", ["R", "C"])
+def test_sliced_gemv_declined_rows_are_the_window_kernels(fast, oracle, layout):
+    """exponents spread over 2^+-100 on both sides: the kernel declines the rows where no product comes within 2^-12 of
+    (largest |a_ij|) x (largest |x_j|) — predicted here from the data — and those rows carry the window kernel's bits"""
+    rng = np.random.default_rng(3)
+    m, n = 1200, 1024
+    A = quad.random_quads(rng, m * n, emin=-100, emax=100); x = quad.random_quads(rng, n, emin=-100, emax=100); y0 = quad.random_quads(rng, m)
+    lda = n if layout == "R" else m
+    got, declined = _gemv(fast, m, n, A, lda, x, y0, layout=layout)
+    ref, none = _gemv(fast, m, n, A, lda, x, y0, variant=1, layout=layout)
+    assert none == -1
+    ea = ((A[:, 1] >> np.uint64(48)).astype(np.int64) & 0x7fff).reshape((m, n) if layout == "R" else (n, m)); ex = (x[:, 1] >> np.uint64(48)).astype(np.int64) & 0x7fff
+    ea = ea if layout == "R" else ea.T
+    want_declined = (ea + ex[None, :]).max(axis=1) < ea.max(axis=1) + ex.max() - 12
+    assert declined == int(want_declined.sum()) and 0 < declined < m, (declined, int(want_declined.sum()))
+    assert quad.same_bits(got[want_declined], ref[want_declined]).all()
+    exact, ratio, klass = _rows_check(oracle, m, n, A, lda, x, got, layout)
+    assert ratio.max() <= 1.0
+
+
+def test_sliced_gemv_zeros_subnormals_specials(fast, oracle):
+    rng = np.random.default_rng(4)
+    m, n = 800, 1400
+    A = qgen.matrix(rng, m, n, "D113", n); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)
+    inf = np.array([0, 0x7FFF << 48], dtype=np.uint64); nan = np.array([1, 0x7FFF << 48], dtype=np.uint64); sub = np.array([5, 0], dtype=np.uint64)
+    A[::5] = 0; x[::11] = 0                       # zeros are skipped
+    A[3 * n: 4 * n] = 0                           # an all-zero row: exactly +0
+    A[7 * n + 100] = inf; A[9 * n + 1] = nan; A[13 * n + 700] = sub; A[15 * n + 5] = inf; A[15 * n + 6] = inf ^ np.array([0, 1 << 63], dtype=np.uint64)
+    got, declined = _gemv(fast, m, n, A, n, x, y0)
+    ref, _ = _gemv(fast, m, n, A, n, x, y0, variant=1)
+    assert declined == 5                          # the four rows with an Inf / NaN / subnormal and the all-zero row
+    for i in (3, 7, 9, 13, 15):
+        assert quad.same_bits(got[i], ref[i]).all()
+    assert (got[3] == 0).all()
+    exact, ratio, klass = _rows_check(oracle, m, n, A, n, x, got)
+    fin = klass == 0
+    assert ratio[fin].max() <= 1.0 and fin.sum() == m - 3
+    nonfin = ~fin
+    assert ((got[nonfin, 1] >> np.uint64(48)) & np.uint64(0x7fff) == np.uint64(0x7fff)).all()
+    # an Inf in x: every row goes to the window kernel, bit for bit
+    x2 = x.copy(); x2[17] = inf
+    got2, declined2 = _gemv(fast, m, n, A, n, x2, y0)
+    ref2, _ = _gemv(fast, m, n, A, n, x2, y0, variant=1)
+    assert declined2 == m and quad.same_bits(got2, ref2).all()
+    # all of x zero: the same
+    x3 = np.zeros_like(x)
+    got3, declined3 = _gemv(fast, m, n, A, n, x3, y0)
+    ref3, _ = _gemv(fast, m, n, A, n, x3, y0, variant=1)
+    assert quad.same_bits(got3, ref3).all()
+
+
+def test_sliced_gemv_strides_and_epilogue(fast, oracle):
+    """incx / incy / lda and y = fma(alpha, S, mul(beta, y)) (level2.hpp:48): S from the long accumulator through the oracle's scalar ops"""
+    rng = np.random.default_rng(5)
+    m, n, lda, incx, incy = 1300, 900, 911, 2, 3
+    A = qgen.matrix(rng, m, n, "D113", lda); x = quad.random_quads(rng, n * incx); y0 = quad.random_quads(rng, m * incy)
+    alpha, beta = quad.random_quads(rng, 2)
+    got, declined = _gemv(fast, m, n, A, lda, x, y0, alpha, beta, incx, incy)
+    assert declined == 0
+    xs = np.ascontiguousarray(x[::incx][:n])
+    idx = np.stack([np.arange(m), np.zeros(m, dtype=np.int64)], axis=1)
+    exact, _, _ = oracle.exact_dot_check("R", n, A, lda, xs, 1, idx)
+    want = np.stack([oracle.fma(alpha, exact[i], oracle.mul(beta, y0[i * incy])) for i in range(m)])
+    same = quad.same_bits(got[::incy][:m], want)
+    assert same.mean() > 0.995
+    mask = np.ones(len(y0), dtype=bool); mask[::incy] = False
+    assert quad.same_bits(got[mask], y0[mask]).all()             # the gaps of a strided y are untouched
+
+
+@pytest.mark.parametrize("layout", ["R", "C"])
+def test_sliced_gemv_full_size(fast, oracle, layout):
+    """BASELINE config 2 scale (8192^2) on device: sampled rows against the long accumulator, deterministic"""
+    n = 8192
+    A = dev_random((n * n,), "D113", 5); x = dev_random((n,), "D113", 6); y = dev_random((n,), "D113", 7)
+    y1 = y.clone(); y2 = y.clone()
+    fast.gemv(layout, n, n, 1.0, A, n, x, 1, 0.0, y1, 1)
+    assert fast.gemv_last_declined() == 0
+    fast.gemv(layout, n, n, 1.0, A, n, x, 1, 0.0, y2, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y2)
+    got = to_host(y1); xh = to_host(x)
+    rows = np.random.default_rng(2).integers(0, n, 64)
+    Ar = np.concatenate([to_host(A[r * n:(r + 1) * n]) if layout == "R" else to_host(A.view(n, n, 2)[:, r].contiguous()) for r in rows])
+    idx = np.stack([np.arange(len(rows)), np.zeros(len(rows), dtype=np.int64)], axis=1)
+    exact, ratio, klass = oracle.exact_dot_check("R", n, Ar, n, xh, 1, idx, got[rows])
+    assert ratio.max() <= 2.0 / n + 1e-6
+    assert quad.same_bits(got[rows], exact).mean() > 0.98
