@@ -728,6 +728,7 @@ static int dot_dev_impl(int64_t n, const void *dx, int64_t incx, const void *dy,
   g.n = n; g.x = (const q128 *)dx; g.incx = incx; g.y = (const q128 *)dy; g.incy = incy;
   g.T = T; g.do_sqrt = do_sqrt; g.result = (q128 *)d_result; g.work = S().work; g.work_elems = S().work_elems;
   g.ticket = (unsigned *)(S().result + 2);
+  g.only_if = (unsigned *)(S().result + 3);
   cudaError_t e = launch_dot(g, mode, st);
   if (e != cudaSuccess) return fail(QB_ERR_CUDA, "qdot kernel launch", e);
   return QB_OK;

@@ -45,6 +45,7 @@ struct DotArgs {
   q128 *result;                      /* device, 16 B */
   q128 *work; int64_t work_elems;    /* device scratch for partials */
   unsigned *ticket = nullptr;        /* device, zero between calls: the last-CTA-done counter of the fast one-launch reduction */
+  unsigned *only_if = nullptr;       /* device word: the sliced qnrm2 kernel sets it when it declines; the window kernel queued behind it runs only then */
 };
 int64_t dot_work_elems(int64_t n, int T, int mode);
 cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st);

@@ -24,6 +24,7 @@
 #include "qb_internal.h"
 #include "q128_chain.cuh"
 #include "qwide.cuh"
+#include "qslice.cuh"
 
 namespace qb {
 
@@ -221,6 +222,7 @@ k_dot_wide_l1(DotArgs g)
   static_assert(8 * (B / 32) <= U * QWA_COL_WORDS * B, "the reduction records reuse the scratch columns");
   __shared__ __align__(16) uint32_t scr[U * QWA_COL_WORDS * B];
   uint32_t *sh = scr;
+  if (g.only_if != nullptr && *g.only_if == 0u) return;   /* queued behind k_sumsq_f64: runs only when that kernel declined */
   const int64_t nthreads = (int64_t)gridDim.x * B;
   const int64_t t = (int64_t)blockIdx.x * B + threadIdx.x;
   qwacc acc = qwa_zero();
@@ -284,15 +286,135 @@ k_dot_wide_l1(DotArgs g)
   }
 }
 
+/* qnrm2 on the FP64 pipe (qslice.cuh, qs_square_step): every thread strides over the vector with U loads in flight, keeps six exact
+ * column sums and a 256-bit window (shared memory), and ends as a qwide that takes the same block tree / last-ticket fold as the
+ * window kernel.  All terms are positive, so the truncation (< 2^-125 of the sum per element) needs no acceptance test; an Inf, NaN
+ * or nonzero subnormal element sets *g.only_if instead of a result, and the window kernel queued behind this one then runs. */
+template <int B>
+__device__ __noinline__ void sq_flush(double c0, double c1, double c2, double c3, double c4, double c5, uint64_t *w)
+{
+  qs_flush(c0, c1, c2, c3, c4, c5, w, B);
+}
+/* the element the hot form left out: its accumulators go to the window first (t: in = the six columns, out = the eight fresh
+ * accumulators), qs_rare moves the anchor or flags the call, then the element is stepped.  Through memory so that the call does
+ * not pin the hot loop's registers. */
+template <int B>
+__device__ __noinline__ void sq_rare_mem(double *t, int32_t *st, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint64_t *w)
+{
+  qs_cols C; C.c0 = t[0]; C.c1 = t[1]; C.c2 = t[2]; C.c3 = t[3]; C.c4 = t[4]; C.c5 = t[5];
+  qs_row S; S.anc = st[0]; S.dmax = 0;
+  uint32_t flags = (uint32_t)st[1];
+  const uint32_t e = (w3 >> 16) & 0x7fffu;
+  const uint32_t sh = ((uint32_t)(e - 1u) >= (uint32_t)S.anc) ? qs_rare(C, S, flags, e, w0, w1, w2, w3, w, B, 2u) : min((uint32_t)S.anc - e, QS_SHMAX);
+  qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, B);
+  qs_sq_cols Q = qs_sq_zero();
+  qs_square_step(Q, w0, w1, w2, w3, sh);
+  t[0] = Q.d0; t[1] = Q.o1; t[2] = Q.o2; t[3] = Q.d2; t[4] = Q.o3; t[5] = Q.o4; t[6] = Q.d4; t[7] = Q.o5;
+  st[0] = S.anc; st[1] = (int32_t)flags;
+}
+
+template <int B, int U, int MINB>
+__global__ void __launch_bounds__(B, MINB)
+k_sumsq_f64(DotArgs g)
+{
+  __shared__ uint64_t win[4 * B];
+  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * B;
+  const int64_t t = (int64_t)blockIdx.x * B + tid;
+  qs_sq_cols Q = qs_sq_zero();
+  int32_t anc = QS_ANCMIN;
+  uint32_t flags = 0;
+  uint64_t *wn = win + tid;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wn[k * B] = 0ull;
+  const q128 *xp = g.x + t * g.incx;
+  const int64_t xs = nthreads * g.incx;
+  int64_t left = (g.n > t) ? (g.n - t + nthreads - 1) / nthreads : 0;
+  int tile = 0;
+  auto one = [&](const q128 &xv) {
+    const uint32_t w0 = (uint32_t)xv.lo, w1 = (uint32_t)(xv.lo >> 32), w2 = (uint32_t)xv.hi, w3 = (uint32_t)(xv.hi >> 32);
+    const uint32_t e = (w3 >> 16) & 0x7fffu;
+    qs_square_step(Q, w0, w1, w2, w3, min((uint32_t)anc - e, QS_SHMAX));   /* a zero or an element above the anchor adds nothing here */
+    if ((uint32_t)(e - 1u) >= (uint32_t)anc) {
+      const qs_cols C = qs_sq_columns(Q);
+      double tt[8] = {C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, 0.0, 0.0};
+      int32_t st[2] = {anc, (int32_t)flags};
+      sq_rare_mem<B>(tt, st, w0, w1, w2, w3, wn);
+      Q.d0 = tt[0]; Q.o1 = tt[1]; Q.o2 = tt[2]; Q.d2 = tt[3]; Q.o3 = tt[4]; Q.o4 = tt[5]; Q.d4 = tt[6]; Q.o5 = tt[7];
+      anc = st[0]; flags = (uint32_t)st[1];
+    }
+  };
+  auto flush = [&]() {
+    const qs_cols C = qs_sq_columns(Q);
+    sq_flush<B>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
+    Q = qs_sq_zero();
+  };
+  /* two register sets of U elements: the loads of the next batch are issued before the arithmetic of this one */
+  q128 xa[U], xb[U];
+  if (left >= U) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) { xa[u] = ldg128_l1(xp); xp += xs; }
+  }
+  while (left >= U) {
+    if (left >= 2 * U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { xb[u] = ldg128_l1(xp); xp += xs; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(xa[u]);
+    left -= U;
+    if (left < U) break;
+    if (left >= 2 * U) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { xa[u] = ldg128_l1(xp); xp += xs; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one(xb[u]);
+    left -= U;
+    tile += 2 * U;
+    if (tile >= QS_TILE - 2 * U) { tile = 0; flush(); }
+  }
+  flush();                                /* (the ragged tail below adds fewer than U elements) */
+  for (; left > 0; --left) { const q128 xv = ldg128_l1(xp); xp += xs; one(xv); }
+  flush();
+  qwide v = qw_block_tree<B>(qs_to_qwide(wn, B, anc, anc), flags, sh);
+  uint32_t *rec = reinterpret_cast<uint32_t *>(g.work);
+  if (tid == 0) {
+    qw_store(rec + 8 * (int64_t)blockIdx.x, v, flags);
+    __threadfence();
+    is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  v = qw_zero();
+  flags = 0;
+  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, flags));
+  __syncthreads();
+  v = qw_block_tree<B>(v, flags, sh);
+  if (tid == 0) {
+    if (flags & QS_FALLBACK) *g.only_if = 1u;
+    else {
+      *g.only_if = 0u;
+      const q128 r = qw_finish(v, 0u);
+      *g.result = g.do_sqrt ? q_sqrt(r) : r;
+    }
+    *g.ticket = 0u;
+  }
+}
+
 static constexpr int FAST_B = 256;       /* rounded-chain variant and the second-level CTA */
 static constexpr int FAST_GRID = 148 * 4;
 static constexpr int WIDE_B = 128;       /* window variant: 4 scratch columns per thread = 24 KB per CTA */
 static constexpr int WIDE_GRID = 148 * 6;
+static constexpr int SUMSQ_B = 128, SUMSQ_CTAS = 6, SUMSQ_GRID = 148 * SUMSQ_CTAS;
 
 int64_t dot_work_elems(int64_t n, int T, int mode)
 {
   (void)n;
-  if (mode != 0) return 2 * WIDE_GRID;   /* 32-byte window records */
+  if (mode != 0) return 2 * SUMSQ_GRID;   /* 32-byte window records */
   return 3 * (int64_t)(T < 1 ? 1 : T) + 4;
 }
 
@@ -316,6 +438,15 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
        * the grid is exactly one wave, every thread strides over the whole vector; the CTA that finishes last folds the
        * per-CTA records (one launch) */
       if (g.ticket == nullptr) return cudaErrorInvalidValue;
+      if (same && fast_variant() == 2 && g.only_if != nullptr && g.n >= (1 << 18)) {
+        /* sum of squares on the FP64 pipe; the window kernel is queued behind it and runs only if an Inf / NaN / subnormal made
+         * the sliced kernel decline */
+        k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
+        k_dot_wide_l1<WIDE_B, 4, true, WIDE_GRID / 148><<<WIDE_GRID, WIDE_B, 0, st>>>(g);
+        count_launch(2);
+        return cudaGetLastError();
+      }
+      g.only_if = nullptr;
       int grid = WIDE_GRID;
       const int64_t need = (g.n + WIDE_B - 1) / WIDE_B;
       if (need < grid) grid = (int)need;

@@ -110,6 +110,51 @@ QB_HD void qs_step(qs_cols &C, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w
   C.c5 = fma(d0, x5, fma(d1, x4, fma(d2, x3, fma(d3, x2, fma(d4, x1, fma(d5, x0, C.c5))))));
 }
 
+/* one element of a sum of squares: C_c += sum_{i + l + 2q = c} A_i A_l with q = sh / 22 and the significand shifted by sh % 22.
+ * Both factors are the same slices, so the column offset 2q is static per case and nothing goes through shared memory; the
+ * symmetric pairs i < l are formed once and kept in accumulators of their own (o1..o5) that count twice when the columns are read
+ * (qs_sq_columns): 12 DFMAs for q = 0, 6 for q = 1, 2 for q = 2, none beyond — such an element is below 2^-66 of the largest
+ * one, its square below 2^-130 of the sum.  Per element a column takes at most 3 products < 2^44: QS_TILE elements stay exact. */
+struct qs_sq_cols { double d0, o1, o2, d2, o3, o4, d4, o5; };
+
+QB_HD qs_sq_cols qs_sq_zero() { qs_sq_cols z; z.d0 = z.o1 = z.o2 = z.d2 = z.o3 = z.o4 = z.d4 = z.o5 = 0.0; return z; }
+
+QB_HD qs_cols qs_sq_columns(const qs_sq_cols &Q)
+{
+  qs_cols C;
+  C.c0 = Q.d0; C.c1 = Q.o1 + Q.o1; C.c2 = Q.o2 + Q.o2 + Q.d2; C.c3 = Q.o3 + Q.o3; C.c4 = Q.o4 + Q.o4 + Q.d4; C.c5 = Q.o5 + Q.o5;
+  return C;
+}
+
+QB_HD void qs_square_step(qs_sq_cols &Q, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t sh)
+{
+  if (sh >= 3u * QS_SL) return;
+  const uint32_t q = (sh * 2979u) >> 16;
+  const uint32_t s = 21u - (sh - q * 22u);
+  const uint32_t m3 = (w3 & 0xffffu) | 0x10000u;
+  const uint32_t v0 = w0 << s, v1 = fshl(w0, w1, s), v2 = fshl(w1, w2, s), v3 = fshl(w2, m3, s), v4 = fshl(m3, 0u, s);
+  const double d0 = (double)fshr(v3, v4, 16), d1 = (double)(fshr(v2, v3, 26) & QS_MK);
+  if (q == 0u) {
+    const double d2 = (double)((v2 >> 4) & QS_MK), d3 = (double)(fshr(v1, v2, 14) & QS_MK), d4 = (double)(fshr(v0, v1, 24) & QS_MK),
+                 d5 = (double)((v0 >> 2) & QS_MK);
+    Q.d0 = fma(d0, d0, Q.d0);
+    Q.o1 = fma(d0, d1, Q.o1);
+    Q.o2 = fma(d0, d2, Q.o2); Q.d2 = fma(d1, d1, Q.d2);
+    Q.o3 = fma(d0, d3, fma(d1, d2, Q.o3));
+    Q.o4 = fma(d0, d4, fma(d1, d3, Q.o4)); Q.d4 = fma(d2, d2, Q.d4);
+    Q.o5 = fma(d0, d5, fma(d1, d4, fma(d2, d3, Q.o5)));
+  } else if (q == 1u) {
+    const double d2 = (double)((v2 >> 4) & QS_MK), d3 = (double)(fshr(v1, v2, 14) & QS_MK);
+    Q.d2 = fma(d0, d0, Q.d2);
+    Q.o3 = fma(d0, d1, Q.o3);
+    Q.o4 = fma(d0, d2, Q.o4); Q.d4 = fma(d1, d1, Q.d4);
+    Q.o5 = fma(d0, d3, fma(d1, d2, Q.o5));
+  } else {
+    Q.d4 = fma(d0, d0, Q.d4);
+    Q.o5 = fma(d0, d1, Q.o5);
+  }
+}
+
 /* the thread column: zeros in front of both copies (once), then the slices of the current x_j */
 QB_HD void qs_col_init(double *col, int stride)
 {
@@ -183,13 +228,13 @@ struct qs_row {
  * e = 0x7fff (Inf / NaN: falls back) or a new largest element (the columns go to the window at the old anchor, the window is
  * shifted to the new one).  Returns the shift for qs_step. */
 QB_HD uint32_t qs_rare(qs_cols &C, qs_row &S, uint32_t &flags, uint32_t e, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint64_t *w,
-                       int stride)
+                       int stride, uint32_t anchors = 1u /* 2 for a sum of squares: both factors follow the anchor */)
 {
   if (e == 0x7fffu) { flags |= QS_FALLBACK; return QS_SHMAX; }
   if (e == 0u) { if ((w0 | w1 | w2 | (w3 & 0xffffu)) != 0u) flags |= QS_FALLBACK; return QS_SHMAX; }
   qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, stride);
   C = qs_cols_zero();
-  qs_win_shr(w, stride, e - (uint32_t)S.anc);
+  qs_win_shr(w, stride, anchors * (e - (uint32_t)S.anc));
   S.anc = (int32_t)e;
   return 0u;
 }

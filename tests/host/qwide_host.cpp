@@ -114,4 +114,38 @@ int qslice_dot(int64_t n, const q128 *a, const q128 *x, int lanes, q128 *out, in
   info[0] = anc; info[1] = EX; info[2] = dmax; info[3] = (int32_t)flags;
   return qs_accept(anc, EX, dmax, flags) ? 1 : 0;
 }
+
+/* the sliced sum of squares (qs_square_step) as k_nrm2_f64 runs it: thread t of `lanes` takes the elements t, t + lanes, ...;
+ * returns 0 when an Inf / NaN / nonzero subnormal sends the call to the window kernel, else 1 with *out = the rounded sum of squares */
+int qslice_sumsq(int64_t n, const q128 *x, int lanes, q128 *out)
+{
+  qwide v = qw_zero();
+  uint32_t flags = 0;
+  for (int t = 0; t < lanes; ++t) {
+    qs_sq_cols Q = qs_sq_zero();
+    qs_row S; S.anc = QS_ANCMIN; S.dmax = 0;
+    uint64_t w[4] = {0, 0, 0, 0};
+    int steps = 0;
+    for (int64_t j = t; j < n; j += lanes) {
+      const uint32_t w0 = (uint32_t)x[j].lo, w1 = (uint32_t)(x[j].lo >> 32), w2 = (uint32_t)x[j].hi, w3 = (uint32_t)(x[j].hi >> 32);
+      const uint32_t e = (w3 >> 16) & 0x7fffu;
+      uint32_t sh = (uint32_t)S.anc - e;
+      sh = sh > QS_SHMAX ? QS_SHMAX : sh;
+      qs_square_step(Q, w0, w1, w2, w3, sh);
+      if ((uint32_t)(e - 1u) >= (uint32_t)S.anc) {
+        qs_cols C = qs_sq_columns(Q);
+        Q = qs_sq_zero();
+        sh = qs_rare(C, S, flags, e, w0, w1, w2, w3, w, 1, 2u);      /* flushes C when it moves the anchor */
+        qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1);
+        if (sh < QS_SHMAX) qs_square_step(Q, w0, w1, w2, w3, sh);
+      }
+      if (++steps == QS_TILE) { const qs_cols C = qs_sq_columns(Q); qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1); Q = qs_sq_zero(); steps = 0; }
+    }
+    const qs_cols C = qs_sq_columns(Q);
+    qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1);
+    qw_merge(v, qs_to_qwide(w, 1, S.anc, S.anc));
+  }
+  *out = qw_finish(v, 0);
+  return (flags & QS_FALLBACK) ? 0 : 1;
+}
 }

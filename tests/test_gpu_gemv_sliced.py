@@ -149,3 +149,49 @@ def test_sliced_gemv_full_size(fast, oracle, layout):
     exact, ratio, klass = oracle.exact_dot_check("R", n, Ar, n, xh, 1, idx, got[rows])
     assert ratio.max() <= 2.0 / n + 1e-6
     assert quad.same_bits(got[rows], exact).mean() > 0.98
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# qnrm2 / qdot(x, x): the sum of squares on the FP64 pipe (k_sumsq_f64)
+
+@pytest.mark.parametrize("kind,n,incx", [("D113", 300000, 1), ("D53", 1 << 20, 1), ("Dexp", 400001, 1), ("wide", 300000, 2)])
+def test_sliced_sum_of_squares(fast, oracle, kind, n, incx):
+    rng = np.random.default_rng(n)
+    x = quad.random_quads(rng, (n - 1) * incx + 1, emin=-150, emax=150) if kind == "wide" else quad.random_quads(rng, (n - 1) * incx + 1, kind)
+    xs = np.ascontiguousarray(x[::incx][:n])
+    exact, _, _ = oracle.exact_dot_check("R", n, xs, n, xs, 1, np.array([[0, 0]], dtype=np.int64))
+    got = fast.dot(n, x, incx, x, incx)
+    assert quad.same_bits(got, fast.dot(n, x, incx, x, incx)).all()           # deterministic
+    _, ratio, _ = oracle.exact_dot_check("R", n, xs, n, xs, 1, np.array([[0, 0]], dtype=np.int64), got.reshape(1, 2))
+    assert ratio[0] <= 2.0 / n + 1e-9                                            # one rounding (1 / n of the contract) plus n 2^-125
+    if kind != "wide":
+        assert quad.same_bits(got, exact[0]).all()
+    nr = fast.nrm2(n, x, incx)
+    fast.set_fast_variant(1)
+    try:
+        nr1 = fast.nrm2(n, x, incx)                                              # the window kernel: sqrt of the same rounded sum
+    finally:
+        fast.set_fast_variant(2)
+    if kind != "wide":
+        assert quad.same_bits(nr, nr1).all()
+
+
+def test_sliced_sum_of_squares_declines_specials(fast):
+    rng = np.random.default_rng(11)
+    n = 300000
+    x = quad.random_quads(rng, n)
+    x[::7] = 0
+    inf = np.array([0, 0x7FFF << 48], dtype=np.uint64); sub = np.array([77, 0], dtype=np.uint64)
+    for special in (inf, sub):
+        y = x.copy(); y[123457] = special
+        got = fast.nrm2(n, y, 1)
+        fast.set_fast_variant(1)
+        try:
+            want = fast.nrm2(n, y, 1)
+        finally:
+            fast.set_fast_variant(2)
+        assert quad.same_bits(got, want).all()
+    assert ((int(fast.nrm2(n, np.concatenate([x[:5], inf[None, :], x[6:]]), 1)[1]) >> 48) & 0x7fff) == 0x7fff
+    z = np.zeros_like(x)
+    r = fast.nrm2(n, z, 1)
+    assert int(r[0]) == 0 and int(r[1]) == 0

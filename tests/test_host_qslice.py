@@ -24,6 +24,8 @@ def qs(tmp_path_factory):
     lib = C.CDLL(str(so))
     lib.qslice_dot.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.qslice_dot.restype = C.c_int
+    lib.qslice_sumsq.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qslice_sumsq.restype = C.c_int
     return lib
 
 
@@ -151,3 +153,44 @@ def test_sliced_dot_exact_cancellation(qs):
     rc, r, info = _dot(qs, a3, x3, 4)
     assert rc == 1
     _check_contract(r, a3, x3, info)
+
+
+def _sumsq(lib, x, lanes):
+    x = np.ascontiguousarray(x)
+    out = np.zeros((1, 2), dtype=np.uint64)
+    rc = lib.qslice_sumsq(len(x), x.ctypes.data, lanes, out.ctypes.data)
+    return rc, out[0]
+
+
+@pytest.mark.parametrize("kind", ["D113", "D53", "Dexp", "wide"])
+@pytest.mark.parametrize("lanes", [1, 5, 32])
+def test_sliced_sum_of_squares_vs_exact(qs, kind, lanes):
+    """qnrm2's sum of squares: the exact sum rounded once up to n 2^-125 of it (every term is positive: no acceptance test needed)"""
+    rng = np.random.default_rng(len(kind) + lanes)
+    n = 900
+    x = quad.random_quads(rng, n, emin=-150, emax=150) if kind == "wide" else quad.random_quads(rng, n, kind)
+    rc, r = _sumsq(qs, x, lanes)
+    assert rc == 1
+    tot = sum(_frac(q) ** 2 for q in x)
+    err = abs(_frac(r) - tot)
+    assert err <= tot / 2 ** 113 + n * tot / 2 ** 124
+    if kind != "wide":
+        hi, lo = quad.from_fraction(tot)
+        assert (int(r[1]), int(r[0])) == (hi, lo)           # in fact the exact sum rounded once
+
+
+def test_sliced_sum_of_squares_specials(qs):
+    rng = np.random.default_rng(3)
+    x = quad.random_quads(rng, 200)
+    x[::4] = 0
+    rc, r = _sumsq(qs, x, 3)
+    assert rc == 1
+    tot = sum(_frac(q) ** 2 for q in x)
+    hi, lo = quad.from_fraction(tot)
+    assert (int(r[1]), int(r[0])) == (hi, lo)
+    y = x.copy(); y[7, 1] = np.uint64(0x7fff) << np.uint64(48)
+    assert _sumsq(qs, y, 3)[0] == 0
+    y = x.copy(); y[7, 1] = np.uint64(0); y[7, 0] = np.uint64(9)
+    assert _sumsq(qs, y, 3)[0] == 0
+    rc, r = _sumsq(qs, np.zeros_like(x), 3)
+    assert rc == 1 and int(r[0]) == 0 and int(r[1]) == 0
