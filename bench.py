@@ -241,6 +241,26 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
             byt = 16.0 * (mv * mv + mv + 2 * mv)
             extra[f"qgemv_{name}"] = {"workload": f"quadblas_qgemv R/N {mv}x{mv} alpha=1 beta=0 ({name} mode)", "ms": ms, "gflops": 2.0 * mv * mv / ms / 1e6,
                                       "roofline": {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": byt / ms / 1e6 / hbm, "peak_source": src}}
+            if md == qb.MODE_FAST:
+                # the sliced FP64 kernel (default) declines rows it cannot guarantee; col-major takes the same kernel; variant 1 = the
+                # window accumulator of round 1 on both layouts, for comparison
+                extra["qgemv_fast"]["kernel"] = "k_gemv_f64 (sliced FP64 accumulate, csrc/qslice.cuh)"
+                extra["qgemv_fast"]["rows_declined"] = qb.gemv_last_declined()
+                qb.gemv("C", mv, mv, 1.0, Av, mv, xv, 1, 0.0, yv, 1)
+                msc = _time_events(lambda: qb.gemv("C", mv, mv, 1.0, Av, mv, xv, 1, 0.0, yv, 1), reps)
+                extra["qgemv_fast_colmajor"] = {"workload": f"quadblas_qgemv C/N {mv}x{mv} alpha=1 beta=0 (fast mode)", "ms": msc,
+                                                "roofline": {"bound": "hbm", "achieved": byt / msc / 1e6, "peak": hbm, "unit": "GB/s", "frac": byt / msc / 1e6 / hbm, "peak_source": src}}
+                qb.set_fast_variant(1)
+                try:
+                    w = {}
+                    for lay in "RC":
+                        qb.gemv(lay, mv, mv, 1.0, Av, mv, xv, 1, 0.0, yv, 1)
+                        w[lay] = _time_events(lambda: qb.gemv(lay, mv, mv, 1.0, Av, mv, xv, 1, 0.0, yv, 1), reps)
+                    extra["qgemv_fast_window_variant"] = {"what": "qb_set_fast_variant(1): the 192-bit window accumulate (integer multiplier) on the same call",
+                                                          "ms_row_major": w["R"], "frac_row_major": byt / w["R"] / 1e6 / hbm,
+                                                          "ms_col_major": w["C"], "frac_col_major": byt / w["C"] / 1e6 / hbm}
+                finally:
+                    qb.set_fast_variant(2)
         del Av
         nd = 100_000_000 if S >= 8192 else 10_000_000
         xd = dev_random((nd,), args.dist, 14, dev); yd = dev_random((nd,), args.dist, 15, dev); res = torch.zeros((1, 2), dtype=torch.int64, device=dev)
@@ -259,8 +279,16 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
                     extra[f"qdot_fast_n{n2}"] = {"ms": ms2, "gbs": 32.0 * n2 / ms2 / 1e6, "frac": 32.0 * n2 / ms2 / 1e6 / hbm}
                 qb.nrm2(nd, xd, 1, res)
                 ms3 = _time_events(lambda: qb.nrm2(nd, xd, 1, res), reps)
-                extra["qnrm2_fast"] = {"workload": f"qnrm2 n={nd} unit stride (fast mode)", "ms": ms3,
+                extra["qnrm2_fast"] = {"workload": f"qnrm2 n={nd} unit stride (fast mode)", "ms": ms3, "kernel": "k_sumsq_f64 (sliced FP64 sum of squares, csrc/qslice.cuh)",
                                        "roofline": {"bound": "hbm", "achieved": 16.0 * nd / ms3 / 1e6, "peak": hbm, "unit": "GB/s", "frac": 16.0 * nd / ms3 / 1e6 / hbm, "peak_source": src}}
+                qb.set_fast_variant(1)
+                try:
+                    qb.nrm2(nd, xd, 1, res)
+                    ms4 = _time_events(lambda: qb.nrm2(nd, xd, 1, res), reps)
+                    extra["qnrm2_fast"]["window_variant_ms"] = ms4
+                    extra["qnrm2_fast"]["window_variant_frac"] = 16.0 * nd / ms4 / 1e6 / hbm
+                finally:
+                    qb.set_fast_variant(2)
         qb.quadblas_set_num_threads(0)
         del xd, yd
         # BASELINE config 1 (the reference README's benchmark, 0.06 GFLOPS there): quadblas_qgemm 1000^3, doubles cast to quad, alpha=1 beta=0,
@@ -700,7 +728,7 @@ def _mgpu_level12(qb, torch, dist, rank, world, dev):
     t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
     # parity: the owner's rows recomputed by ONE GPU call on the same rows must give the same bits (and every rank holds them)
     y1 = torch.zeros((hi - lo, 2), dtype=torch.int64, device=dev)
-    qb.gemv("R", hi - lo, n, 1.0, Ablk, n, x, 1, 0.0, y1, 1)
+    qb.gemv("R", hi - lo, n, 1.0, Ablk, n, x, 1, 0.0, y1, 1, m_total=m)    # these rows as ONE GPU computing the whole m x n qgemv produces them
     same = int((y[lo:hi] == y1).all().item())
     chk = y.view(torch.int64).sum().reshape(1); allc = [torch.empty_like(chk) for _ in range(world)]; dist.all_gather(allc, chk)
     same_all = int(all(int(c.item()) == int(chk.item()) for c in allc))

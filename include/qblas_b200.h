@@ -96,10 +96,11 @@ int qb_get_honor_trans(void);
  * (the planner only declines when not even one pipeline unit fits the free device memory); then the integer-limb kernel runs. */
 void qb_set_tensor_path(int v);
 int qb_get_tensor_path(void);
-/* Fast-mode accumulate of qdot / qnrm2 / qgemv: 2 (default) = large row-major qgemv on the FP64 pipe (csrc/qslice.cuh: 22-bit
- * slices as exact doubles, one rounding per result, rows it cannot guarantee recomputed by the window kernel) and the window
- * accumulator everywhere else; 1 = unrounded 192-bit window accumulator everywhere (csrc/qwide.cuh, one rounding per result);
- * 0 = chains of correctly rounded FMAs (the reference's per-element operation, level1.hpp:24, re-associated).
+/* Fast-mode accumulate of qdot / qnrm2 / qgemv: 2 (default) = large qgemv (both layouts) and large qnrm2 / qdot(x, x) on the FP64 pipe
+ * (csrc/qslice.cuh: 22-bit slices as exact doubles, one rounding per result, rows it cannot guarantee recomputed by the window
+ * kernel) and the window accumulator everywhere else; 1 = unrounded 192-bit window accumulator everywhere (csrc/qwide.cuh, one rounding per result);
+ * 0 = chains of correctly rounded FMAs (the reference's per-element operation, level1.hpp:24, re-associated);
+ * 3 = as 2 but the sliced kernels also take the sizes where they do not pay (any qgemv with n >= 128, any qnrm2): for tests.
  * Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);

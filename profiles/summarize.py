@@ -10,7 +10,7 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum",
         "sm__issue_active.avg.pct", "smsp__issue_active.avg.pct", "sm__inst_executed_pipe_alu.avg.pct", "sm__inst_executed_pipe_fma.avg.pct",
         "sm__pipe_alu_cycles_active.avg.pct", "sm__pipe_fma_cycles_active.avg.pct", "sm__pipe_fmaheavy_cycles_active.avg.pct", "sm__inst_executed_pipe_lsu.avg.pct",
-        "sm__pipe_tensor_cycles_active.avg.pct", "sm__throughput.avg.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct", "sm__inst_executed_pipe_fp64.avg.pct", "sm__inst_executed_pipe_xu.avg.pct", "sm__throughput.avg.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct", "dram__cycles_active.avg.pct", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu.sum",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__sass_average_branch_targets_threads_uniform.pct",
         "sm__cycles_elapsed.max", "smsp__average_warp", "smsp__warp_issue_stalled", "launch__shared_mem_per_block"]

@@ -49,7 +49,7 @@ static int g_peer_written = 0;
 static std::atomic<int> g_host_slabs{8}; /* C slabs of the pipelined all-host qgemm / row slabs of the all-host qgemv */
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
 static std::atomic<int> g_fastvar{2}; /* fast-mode level-1/2 accumulate: 2 = sliced FP64 accumulate where it applies (large row-major qgemv), window
-                                         accumulator elsewhere; 1 = window accumulator everywhere; 0 = rounded-FMA chains */
+                                         accumulator elsewhere; 1 = window accumulator everywhere; 0 = rounded-FMA chains; 3 = 2 without the size thresholds (tests) */
 int fast_variant() { return g_fastvar.load(); }
 static std::atomic<int> g_threads{0}; /* 0 = not set -> OMP_NUM_THREADS, then hardware concurrency (omp_get_max_threads) */
 
@@ -436,7 +436,7 @@ void qb_set_mode(int mode) { g_mode.store(mode == QB_MODE_FAST ? QB_MODE_FAST : 
 int qb_get_mode(void) { return g_mode.load(); }
 void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
-void qb_set_fast_variant(int v) { g_fastvar.store(v <= 0 ? 0 : (v >= 2 ? 2 : 1)); }
+void qb_set_fast_variant(int v) { g_fastvar.store(v <= 0 ? 0 : (v >= 3 ? 3 : v)); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)
 {

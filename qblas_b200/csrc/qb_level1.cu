@@ -438,7 +438,8 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
        * the grid is exactly one wave, every thread strides over the whole vector; the CTA that finishes last folds the
        * per-CTA records (one launch) */
       if (g.ticket == nullptr) return cudaErrorInvalidValue;
-      if (same && fast_variant() == 2 && g.only_if != nullptr && g.n >= (1 << 18)) {
+      /* from 2^24 elements (measured: at 10^7 the window kernel's single launch still wins, 79 vs 89 us); variant 3 = test hook, any size */
+      if (same && g.only_if != nullptr && ((fast_variant() == 2 && g.n >= (1 << 24)) || fast_variant() == 3)) {
         /* sum of squares on the FP64 pipe; the window kernel is queued behind it and runs only if an Inf / NaN / subnormal made
          * the sliced kernel decline */
         k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);

@@ -397,8 +397,10 @@ k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *h
         const uint32_t e = (v[u].w >> 16) & 0x7fffu;
         rare[u] = (uint32_t)(e - 1u) >= (uint32_t)anc;
         any |= rare[u];
-        const uint32_t sh = min((uint32_t)anc - e, QS_SHMAX);   /* an element above the anchor wraps to a huge shift, a zero gives anc >= QS_ANCMIN: both meet only zeros */
-        qs_step(C, v[u].x, v[u].y, v[u].z, v[u].w, sh, col, 1);
+        /* nsh = 21 - min(anc - e, QS_SHMAX) in one add-max; an element above the anchor (the difference wraps) and a zero
+         * (anc >= QS_ANCMIN) both get QS_SHMAX and meet only zeros */
+        const int32_t nsh = 21 - (int32_t)min((uint32_t)anc - e, QS_SHMAX);
+        qs_step_n(C, v[u].x, v[u].y, v[u].z, v[u].w, nsh, col, 1);
         dmax = max(dmax, (int32_t)e + __double2loint(col[QS_XCOL]));
       }
       if (any) {
@@ -417,7 +419,7 @@ k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *h
       gv_flush<GVT_ROWS>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
       C = qs_cols_zero();
     }
-    __syncthreads();                      /* every thread is done with stage s */
+    __syncthreads();                      /* every thread is done with stage s (an mbarrier handshake that lets the warps drift was measured slower) */
     if (tid == 0 && t + 2 < ntiles) issue(t + 2, s);
   }
   gv_flush<GVT_ROWS>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
@@ -535,7 +537,11 @@ static int gemv_col_splits(int64_t m, int64_t n)
 
 /* the sliced FP64 kernel pays four small launches around the product: worth it from about a million elements, and the acceptance
  * bound of qslice.cuh is stated for n >= 128 */
-static bool gemv_sliced(int64_t m, int64_t n) { return fast_variant() == 2 && n >= 512 && m >= 148 * 4 && m * n >= (1 << 20); }
+static bool gemv_sliced(int64_t m, int64_t n)
+{
+  if (fast_variant() == 3) return n >= 128 && m >= 1;            /* test hook: the sliced kernel at every size its bound covers */
+  return fast_variant() == 2 && n >= 512 && m >= 148 * 4 && m * n >= (1 << 20);
+}
 static int64_t gemv_sliced_npad(int64_t n) { return (n + GVT_COLS - 1) / GVT_COLS * GVT_COLS; }
 /* column splits of the sliced kernel: about 12 CTAs per SM in all (two waves of 6), at least 256 columns per split */
 static int gemv_sliced_splits(int64_t m, int64_t n)
@@ -592,11 +598,17 @@ static cudaError_t launch_gemv_sliced(const GemvArgs &a, cudaStream_t st)
   const int64_t mp = a.m_plan > 0 ? a.m_plan : a.m;
   const GvSlicedLayout L = gemv_sliced_layout(a.m, a.n, a.col_major, mp);
   if (a.work == nullptr || a.work_elems < L.total) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(a.A) & 15u) != 0) return cudaErrorMisalignedAddress;
   CUtensorMap tm;
-  const bool ok = a.col_major ? make_quad_map(&tm, a.A, a.m, a.n, a.lda * 16, GVT_ROWS, GVT_COLS, false)
-                              : make_quad_map(&tm, a.A, a.n, a.m, a.lda * 16, GVT_COLS, GVT_ROWS, true);
-  if (!ok) return cudaErrorNotSupported;
+  const bool ok = (reinterpret_cast<uintptr_t>(a.A) & 15u) == 0 &&
+                  (a.col_major ? make_quad_map(&tm, a.A, a.m, a.n, a.lda * 16, GVT_ROWS, GVT_COLS, false)
+                               : make_quad_map(&tm, a.A, a.n, a.m, a.lda * 16, GVT_COLS, GVT_ROWS, true));
+  if (!ok) {   /* no tensor map for this matrix (alignment, extents): the window kernel takes the whole call */
+    cudaMemsetAsync(a.work + L.flags, 1, (size_t)a.m, st);   /* (qb_gemv_last_declined then reports every row) */
+    if (a.col_major) return launch_gemv_col_window(a, a.work + L.colwork, nullptr, st);
+    k_gemv_row_wide<2, 128, 5><<<(unsigned)((a.m + 1) / 2), 128, 0, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+  }
   const int64_t npad = gemv_sliced_npad(a.n);
   int32_t *hdr = reinterpret_cast<int32_t *>(a.work);
   double *tab = reinterpret_cast<double *>(a.work + L.tab);

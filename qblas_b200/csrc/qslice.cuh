@@ -90,13 +90,24 @@ QB_HD void qs_xrec_make(q128 x, int32_t EX, qs_xrec &r)
   }
 }
 
-/* one element: C_c += sum_i A_i X'_(c-i).  w0..w3 = the packed element, sh = anc - e clamped to QS_SHMAX (QS_SHMAX itself for
- * an element that must not count), col = this thread's column of QS_XCOL doubles at `stride`. */
-QB_HD void qs_step(qs_cols &C, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t sh, const double *col, int stride)
+/* (w3 & 0xffff) | 0x10000: the top word of the significand with the implicit bit (one PRMT on the device) */
+QB_HD uint32_t qs_top_word(uint32_t w3)
 {
-  const uint32_t q = (sh * 2979u) >> 16;                      /* sh / 22 for sh <= 153 */
-  const uint32_t s = 21u - (sh - q * 22u);
-  const uint32_t m3 = (w3 & 0xffffu) | 0x10000u;
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(w3, 0x00010000u, 0x7610);
+#else
+  return (w3 & 0xffffu) | 0x10000u;
+#endif
+}
+
+/* one element: C_c += sum_i A_i X'_(c-i).  w0..w3 = the packed element, nsh = 21 - sh with sh = anc - e clamped to QS_SHMAX
+ * (QS_SHMAX itself for an element that must not count) — the kernels get nsh from one fused add-max —, col = this thread's column
+ * of QS_XCOL doubles at `stride`. */
+QB_HD void qs_step_n(qs_cols &C, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int32_t nsh, const double *col, int stride)
+{
+  const uint32_t q = (uint32_t)(nsh * -2979 + 21 * 2979) >> 16;   /* sh / 22 for sh <= 153 */
+  const uint32_t s = q * 22u + (uint32_t)nsh;                     /* 21 - sh % 22 */
+  const uint32_t m3 = qs_top_word(w3);
   const uint32_t v0 = w0 << s, v1 = fshl(w0, w1, s), v2 = fshl(w1, w2, s), v3 = fshl(w2, m3, s), v4 = fshl(m3, 0u, s);
   const double d0 = (double)fshr(v3, v4, 16), d1 = (double)(fshr(v2, v3, 26) & QS_MK), d2 = (double)((v2 >> 4) & QS_MK),
                d3 = (double)(fshr(v1, v2, 14) & QS_MK), d4 = (double)(fshr(v0, v1, 24) & QS_MK), d5 = (double)((v0 >> 2) & QS_MK);
@@ -108,6 +119,10 @@ QB_HD void qs_step(qs_cols &C, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w
   C.c3 = fma(d0, x3, fma(d1, x2, fma(d2, x1, fma(d3, x0, C.c3))));
   C.c4 = fma(d0, x4, fma(d1, x3, fma(d2, x2, fma(d3, x1, fma(d4, x0, C.c4)))));
   C.c5 = fma(d0, x5, fma(d1, x4, fma(d2, x3, fma(d3, x2, fma(d4, x1, fma(d5, x0, C.c5))))));
+}
+QB_HD void qs_step(qs_cols &C, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t sh, const double *col, int stride)
+{
+  qs_step_n(C, w0, w1, w2, w3, 21 - (int32_t)sh, col, stride);
 }
 
 /* one element of a sum of squares: C_c += sum_{i + l + 2q = c} A_i A_l with q = sh / 22 and the significand shifted by sh % 22.
@@ -131,7 +146,7 @@ QB_HD void qs_square_step(qs_sq_cols &Q, uint32_t w0, uint32_t w1, uint32_t w2, 
   if (sh >= 3u * QS_SL) return;
   const uint32_t q = (sh * 2979u) >> 16;
   const uint32_t s = 21u - (sh - q * 22u);
-  const uint32_t m3 = (w3 & 0xffffu) | 0x10000u;
+  const uint32_t m3 = qs_top_word(w3);
   const uint32_t v0 = w0 << s, v1 = fshl(w0, w1, s), v2 = fshl(w1, w2, s), v3 = fshl(w2, m3, s), v4 = fshl(m3, 0u, s);
   const double d0 = (double)fshr(v3, v4, 16), d1 = (double)(fshr(v2, v3, 26) & QS_MK);
   if (q == 0u) {

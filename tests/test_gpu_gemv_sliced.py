@@ -154,8 +154,19 @@ def test_sliced_gemv_full_size(fast, oracle, layout):
 # ---------------------------------------------------------------------------------------------------------------------------
 # qnrm2 / qdot(x, x): the sum of squares on the FP64 pipe (k_sumsq_f64)
 
-@pytest.mark.parametrize("kind,n,incx", [("D113", 300000, 1), ("D53", 1 << 20, 1), ("Dexp", 400001, 1), ("wide", 300000, 2)])
-def test_sliced_sum_of_squares(fast, oracle, kind, n, incx):
+@pytest.fixture()
+def fast3(qb):
+    """the sliced kernels without their size thresholds"""
+    qb.set_mode(qb.MODE_FAST)
+    qb.set_fast_variant(3)
+    yield qb
+    qb.set_fast_variant(2)
+    qb.set_mode(qb.MODE_REFERENCE)
+
+
+@pytest.mark.parametrize("kind,n,incx", [("D113", 300000, 1), ("D53", 1 << 20, 1), ("Dexp", 400001, 1), ("wide", 300000, 2), ("D113", 1000, 1), ("D113", 7, 3)])
+def test_sliced_sum_of_squares(fast3, oracle, kind, n, incx):
+    fast = fast3
     rng = np.random.default_rng(n)
     x = quad.random_quads(rng, (n - 1) * incx + 1, emin=-150, emax=150) if kind == "wide" else quad.random_quads(rng, (n - 1) * incx + 1, kind)
     xs = np.ascontiguousarray(x[::incx][:n])
@@ -171,12 +182,13 @@ def test_sliced_sum_of_squares(fast, oracle, kind, n, incx):
     try:
         nr1 = fast.nrm2(n, x, incx)                                              # the window kernel: sqrt of the same rounded sum
     finally:
-        fast.set_fast_variant(2)
+        fast.set_fast_variant(3)
     if kind != "wide":
         assert quad.same_bits(nr, nr1).all()
 
 
-def test_sliced_sum_of_squares_declines_specials(fast):
+def test_sliced_sum_of_squares_declines_specials(fast3):
+    fast = fast3
     rng = np.random.default_rng(11)
     n = 300000
     x = quad.random_quads(rng, n)
@@ -189,9 +201,55 @@ def test_sliced_sum_of_squares_declines_specials(fast):
         try:
             want = fast.nrm2(n, y, 1)
         finally:
-            fast.set_fast_variant(2)
+            fast.set_fast_variant(3)
         assert quad.same_bits(got, want).all()
     assert ((int(fast.nrm2(n, np.concatenate([x[:5], inf[None, :], x[6:]]), 1)[1]) >> 48) & 0x7fff) == 0x7fff
     z = np.zeros_like(x)
     r = fast.nrm2(n, z, 1)
     assert int(r[0]) == 0 and int(r[1]) == 0
+
+
+@pytest.mark.parametrize("layout", ["R", "C"])
+def test_row_blocks_planned_as_the_whole_call_keep_its_bits(fast, layout):
+    """qb_gemv_rows_dev: a block of rows computed with m_total = the whole qgemv (slabs of the pipelined host path, row blocks of the
+    multi-GPU qgemv) takes the same kernel and column splits, so every y_i is bit-identical to the unsplit call"""
+    rng = np.random.default_rng(21)
+    m, n = 4100, 2048
+    lda = n if layout == "R" else m
+    A = qgen.matrix(rng, m if layout == "R" else n, n if layout == "R" else m, "D113", lda); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)
+    alpha, beta = quad.random_quads(rng, 2)
+    dA, dx = to_dev(A), to_dev(x)
+    dy = to_dev(y0)
+    fast.gemv(layout, m, n, alpha, dA, lda, dx, 1, beta, dy, 1)
+    whole = to_host(dy)
+    dy2 = to_dev(y0)
+    for lo, hi in ((0, 700), (700, 1900), (1900, 4100)):          # the first block alone would not even take the sliced kernel
+        blk = dA[lo * lda:] if layout == "R" else dA[lo:]
+        fast.gemv(layout, hi - lo, n, alpha, blk, lda, dx, 1, beta, dy2[lo:hi], 1, m_total=m)
+    assert quad.same_bits(to_host(dy2), whole).all()
+
+
+def test_sliced_sum_of_squares_default_threshold(fast, oracle):
+    """the default (variant 2) takes the sliced kernel from 2^24 elements: one such call against the long accumulator"""
+    n = (1 << 24) + 5
+    x = dev_random((n,), "D113", 9)
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    fast.dot(n, x, 1, x, 1, out)
+    got = to_host(out.view(1, 2))
+    xh = to_host(x)
+    _, ratio, _ = oracle.exact_dot_check("R", n, xh, n, xh, 1, np.array([[0, 0]], dtype=np.int64), got.reshape(1, 2))
+    assert ratio[0] <= 2.0 / n + 1e-9
+
+
+@pytest.mark.parametrize("layout,m,n", [("R", 37, 200), ("C", 300, 128), ("R", 129, 1031)])
+def test_sliced_gemv_small_shapes(fast3, oracle, layout, m, n):
+    """variant 3: the sliced kernel on shapes below its size threshold (ragged tiles, fewer rows than a CTA, a single column split)"""
+    rng = np.random.default_rng(m * n)
+    lda = (n if layout == "R" else m) + 2
+    A = qgen.matrix(rng, m if layout == "R" else n, n if layout == "R" else m, "D113", lda); x = quad.random_quads(rng, n); y0 = quad.random_quads(rng, m)
+    dy = to_dev(y0)
+    fast3.gemv(layout, m, n, 1.0, to_dev(A), lda, to_dev(x), 1, 0.0, dy, 1)
+    assert fast3.gemv_last_declined() == 0
+    got = to_host(dy)
+    exact, ratio, klass = _rows_check(oracle, m, n, A, lda, x, got, layout)
+    assert ratio.max() <= 2.0 / n + 1e-6 and quad.same_bits(got, exact).mean() > 0.99
