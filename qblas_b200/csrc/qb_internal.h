@@ -29,8 +29,8 @@ struct GemvArgs {
   const q128 *x; int64_t incx;
   q128 *y; int64_t incy;
   q128 *work; int64_t work_elems;    /* device scratch (fast col-major split windows, the sliced kernel's tables and records), gemv_work_elems() */
-  int64_t m_plan = 0;                /* > 0: these m rows are a slab of a qgemv with m_plan rows; kernel choice and column splits follow m_plan,
-                                        so that a row gets the same bits whether the call is made in one piece or in slabs */
+  int64_t m_plan = 0;                /* > 0: these m rows are a slab of a qgemv with m_plan rows; the kernel choice follows m_plan (the column
+                                        splits depend on n alone), so that a row gets the same bits whether the call is made in one piece or in slabs */
 };
 int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode, int64_t m_plan = 0);
 const uint8_t *gemv_sliced_rowflags(const q128 *work, int64_t m, int64_t n, int col_major, int64_t m_plan = 0);   /* the declined-row flags of the sliced row-major kernel inside its scratch */

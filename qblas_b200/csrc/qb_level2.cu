@@ -265,14 +265,14 @@ k_gemv_row_wide_sel(GemvArgs g, const uint8_t *rowflag)
  * k_gv_xscan: EX = largest exponent field of x, and whether x holds an Inf / NaN / nonzero subnormal (then every row goes to
  * the window kernel).  k_gv_xtab: per x_j a 200-byte table {6 zeros, +X_0..5, 6 zeros, -X_0..5, e(x_j)} — what qs_step reads at the
  * dynamic slice offset, ready to be copied.  k_gemv_f64: ONE THREAD PER ROW (no cross-thread merge, no per-thread staging of x):
- * a CTA owns 128 rows and a range of columns (gridDim.y splits); tiles of 128 rows x 8 columns of A arrive by TMA into a
- * two-stage ring (row-major: box {128 B, 128 rows} with the 128-byte swizzle, so that 32 threads reading the same column of 32
- * consecutive rows hit 32 different bank groups; col-major: box {128 rows, 8 columns}, consecutive threads read consecutive
- * quads), the x tables of the 8 columns by one bulk copy on the same mbarrier; elements past m or n read as zero (TMA fill, zero
- * tables), so there is no edge code.  Each thread runs qs_step on its row (about 70 instructions per element, 64 registers, 6
- * CTAs per SM), keeps its 256-bit window in shared memory, and ends with a record {window as qwide, anchor, Dmax, flags}.
- * k_gemv_f64_fin folds the records of the column splits in order, applies qs_accept and either stores
- * y_i = fma(alpha, S_i, mul(beta, y_i)) or flags the row for the window kernel (k_gemv_row_wide_sel / k_gemv_col_wide). */
+ * a CTA owns a block of rows and a range of columns (gridDim.y splits); tiles of A arrive by TMA into a two-stage ring (col-major:
+ * box {128 rows, 8 columns}, consecutive threads read consecutive quads; row-major: boxes {128 B, rows} with the 128-byte swizzle,
+ * so that 32 threads reading the same column of 32 consecutive rows hit 32 different bank groups), the x tables of the tile's
+ * columns by one bulk copy on the same mbarrier; elements past m or n read as zero (TMA fill, zero tables), so there is no edge
+ * code.  Each thread runs qs_step on its row (about 72 instructions per element), keeps its 256-bit window in shared memory, and
+ * ends with a record {window as qwide, anchor, Dmax, flags}.  k_gemv_f64_fin folds the records of a row in order, applies
+ * qs_accept and either stores y_i = fma(alpha, S_i, mul(beta, y_i)) or flags the row for the window kernel
+ * (k_gemv_row_wide_sel / k_gemv_col_wide). */
 __global__ void k_gv_xscan(GemvArgs g, int32_t *hdr)
 {
   int32_t emax = 0;
@@ -295,8 +295,8 @@ constexpr int GVT_COLS = 8;              /* columns per tile: 8 x 16 B = the 128
 constexpr int GVT_XDBL = QS_XCOL + 1;    /* doubles per column of the x table */
 constexpr int GVT_GRP = 4;               /* elements stepped between two looks at the rare flags */
 constexpr int GVT_TILE_BYTES = GVT_ROWS * GVT_COLS * 16;
-constexpr int GVT_XT_BYTES = GVT_COLS * GVT_XDBL * 8;
-constexpr int GVT_SMEM = 2 * GVT_TILE_BYTES + 2 * GVT_XT_BYTES + 4 * GVT_ROWS * 8 + 64;
+constexpr int GVT_NB_ROW = 2;           /* column boxes per tile of the row-major kernel (see k_gemv_f64) */
+constexpr int gvt_smem(int nb) { return 2 * GVT_TILE_BYTES + 2 * ((GVT_COLS * nb * GVT_XDBL * 8 + 127) / 128 * 128) + 4 * GVT_ROWS * 8 + 64; }
 
 __global__ void k_gv_xtab(GemvArgs g, const int32_t *hdr, double *tab, int64_t npad)
 {
@@ -336,26 +336,40 @@ __device__ __noinline__ void gv_rare_mem(double *t, int32_t *st, uint32_t w0, ui
 /* record of one (row, column split): the window as a qwide + flags (gv_store), then anchor and Dmax */
 constexpr int GVT_REC = 12;
 
-template <bool COL>
-__global__ void __launch_bounds__(GVT_ROWS, 6)
+/* NB = column boxes of 8 columns per tile: the CTA's 128 threads are RB = 128 / NB rows x NB boxes (a warp = 32 consecutive rows of
+ * one box), a tile is RB rows x 8 NB columns.  Row-major uses NB = 2 or 4: a row then contributes 256 / 512 contiguous bytes per
+ * tile instead of 128, which is what the DRAM pages want (measured: NB = 1 leaves row-major 10 % behind col-major, whose tile is a
+ * run of 2 KB per column); every (row, box) is a partial of its own.  Col-major: NB = 1. */
+template <bool COL, int NB>
+__global__ void __launch_bounds__(GVT_ROWS, 5)
 k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *hdr, const double *tab, int64_t jsplit, uint32_t *part)
 {
+  constexpr int RB = GVT_ROWS / NB;                  /* rows per CTA */
+  constexpr int TC = GVT_COLS * NB;                  /* columns per tile */
+  constexpr int XT_BYTES = TC * GVT_XDBL * 8;
+  constexpr int XT_STRIDE = (XT_BYTES + 127) / 128 * 128;
+  static_assert(!COL || NB == 1, "col-major tiles are one box");
   /* the kernel has no static shared memory, so the dynamic array starts the CTA's window and the 1024-byte alignment the swizzled
    * tiles need is the declared one (checked below); used directly so that every access stays an LDS / STS */
   extern __shared__ __align__(1024) unsigned char gvt_sm[];
-  uint64_t *win = reinterpret_cast<uint64_t *>(gvt_sm + 2 * GVT_TILE_BYTES + 2 * GVT_XT_BYTES);
+  uint64_t *win = reinterpret_cast<uint64_t *>(gvt_sm + 2 * GVT_TILE_BYTES + 2 * XT_STRIDE);
   uint64_t *full = win + 4 * GVT_ROWS;
   const int tid = threadIdx.x;
-  const int64_t row0 = (int64_t)blockIdx.x * GVT_ROWS, row = row0 + tid;
+  const int box = tid / RB, rr = tid % RB;
+  const int64_t row0 = (int64_t)blockIdx.x * RB, row = row0 + rr;
   const int64_t j0 = (int64_t)blockIdx.y * jsplit, j1 = min(g.n, j0 + jsplit);
-  const int ntiles = hdr[1] != 0 ? 0 : (int)((j1 - j0 + GVT_COLS - 1) / GVT_COLS);   /* Inf / NaN / subnormal in x: nothing here, every row flagged */
+  const int ntiles = hdr[1] != 0 ? 0 : (int)((j1 - j0 + TC - 1) / TC);   /* Inf / NaN / subnormal in x: nothing here, every row flagged */
   const int32_t EX = hdr[0];
   auto issue = [&](int t, int s) {
-    const int64_t j = j0 + (int64_t)t * GVT_COLS;
-    tc::mbar_expect_tx(&full[s], GVT_TILE_BYTES + GVT_XT_BYTES);
+    const int64_t j = j0 + (int64_t)t * TC;
+    tc::mbar_expect_tx(&full[s], GVT_TILE_BYTES + XT_BYTES);
     if (COL) tc::tma_load_2d(gvt_sm + s * GVT_TILE_BYTES, &tmA, &full[s], (int)(row0 * 2), (int)j);
-    else tc::tma_load_2d(gvt_sm + s * GVT_TILE_BYTES, &tmA, &full[s], (int)(j * 4), (int)row0);
-    tc::bulk_load_1d(gvt_sm + 2 * GVT_TILE_BYTES + s * GVT_XT_BYTES, tab + j * GVT_XDBL, GVT_XT_BYTES, &full[s]);
+    else {
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb)
+        tc::tma_load_2d(gvt_sm + s * GVT_TILE_BYTES + bb * (RB * 128), &tmA, &full[s], (int)((j + bb * GVT_COLS) * 4), (int)row0);
+    }
+    tc::bulk_load_1d(gvt_sm + 2 * GVT_TILE_BYTES + s * XT_STRIDE, tab + j * GVT_XDBL, XT_BYTES, &full[s]);
   };
   if (tid == 0) {
     if ((tc::smem_u32(gvt_sm) & 1023u) != 0u) __trap();
@@ -373,12 +387,12 @@ k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *h
   int32_t anc = QS_ANCMIN, dmax = QS_EXNONE;
   uint32_t flags = hdr[1] != 0 ? QS_FALLBACK : 0u;
   uint64_t *wn = win + tid;
-  const uint32_t aoff = COL ? (uint32_t)tid * 16u : (uint32_t)tid * 128u;
+  const uint32_t aoff = COL ? (uint32_t)tid * 16u : (uint32_t)(box * (RB * 128) + rr * 128);
   for (int t = 0; t < ntiles; ++t) {
     const int s = t & 1;
     tc::mbar_wait(&full[s], (uint32_t)(t >> 1) & 1u);
     const unsigned char *at = gvt_sm + s * GVT_TILE_BYTES + aoff;
-    const double *xs = reinterpret_cast<const double *>(gvt_sm + 2 * GVT_TILE_BYTES + s * GVT_XT_BYTES);
+    const double *xs = reinterpret_cast<const double *>(gvt_sm + 2 * GVT_TILE_BYTES + s * XT_STRIDE) + box * (GVT_COLS * GVT_XDBL);
     /* groups of GVT_GRP elements: the hot steps are branch-free so that their decode / convert / multiply chains interleave in one
      * instruction stream; an element the hot form cannot take (zero / subnormal / Inf / NaN, or larger than everything before it
      * in this row) meets only the six zeros there and is redone after its group, in order */
@@ -389,7 +403,7 @@ k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *h
 #pragma unroll
       for (int u = 0; u < GVT_GRP; ++u) {
         const int c = c0 + u;
-        v[u] = *reinterpret_cast<const uint4 *>(COL ? at + c * (GVT_ROWS * 16) : at + ((c ^ (tid & 7)) << 4));
+        v[u] = *reinterpret_cast<const uint4 *>(COL ? at + c * (GVT_ROWS * 16) : at + ((c ^ (rr & 7)) << 4));
       }
 #pragma unroll
       for (int u = 0; u < GVT_GRP; ++u) {
@@ -425,7 +439,7 @@ k_gemv_f64(const __grid_constant__ CUtensorMap tmA, GemvArgs g, const int32_t *h
   gv_flush<GVT_ROWS>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
   if (row < g.m) {
     const qwide v = qs_to_qwide(wn, GVT_ROWS, anc, EX);
-    uint32_t *dst = part + ((int64_t)blockIdx.y * g.m + row) * GVT_REC;
+    uint32_t *dst = part + (((int64_t)blockIdx.y * NB + box) * g.m + row) * GVT_REC;
     gv_store(dst, v, flags);
     dst[8] = (uint32_t)anc; dst[9] = (uint32_t)dmax;
   }
@@ -542,23 +556,26 @@ static bool gemv_sliced(int64_t m, int64_t n)
   if (fast_variant() == 3) return n >= 128 && m >= 1;            /* test hook: the sliced kernel at every size its bound covers */
   return fast_variant() == 2 && n >= 512 && m >= 148 * 4 && m * n >= (1 << 20);
 }
-static int64_t gemv_sliced_npad(int64_t n) { return (n + GVT_COLS - 1) / GVT_COLS * GVT_COLS; }
-/* column splits of the sliced kernel: about 12 CTAs per SM in all (two waves of 6), at least 256 columns per split */
-static int gemv_sliced_splits(int64_t m, int64_t n)
+static int64_t gemv_sliced_npad(int64_t n) { return (n + 4 * GVT_COLS - 1) / (4 * GVT_COLS) * (4 * GVT_COLS) + 4 * GVT_COLS; }   /* whole tiles of any box count, read past the last one */
+/* column splits of the sliced kernel: a function of n ALONE (1024 columns per split, 512 for narrower matrices), so that the bits of
+ * a row do not depend on how many rows the call has — a slab of a host matrix or the row block of one GPU gives what the whole call
+ * gives — and a block of a few thousand rows still fills the chip (32768 columns: 32 splits x 32 row blocks of 4096 rows) */
+static int64_t gemv_sliced_jsplit(int64_t n, int col_major)
 {
-  const int64_t rb = (m + GVT_ROWS - 1) / GVT_ROWS;
-  int64_t s = (148 * 12 + rb - 1) / rb;
-  s = std::min<int64_t>(s, n / 256);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+  int64_t j = (n >= 16384 ? 1024 : 512) * (col_major ? 1 : GVT_NB_ROW);   /* row-major: NB partials per split, the same number of records */
+  while ((n + j - 1) / j > 16384) j *= 2;                        /* gridDim.y */
+  return j;
 }
+static int gemv_sliced_splits(int64_t n, int col_major) { return (int)((n + gemv_sliced_jsplit(n, col_major) - 1) / gemv_sliced_jsplit(n, col_major)); }
+static int gemv_sliced_records(int64_t n, int col_major) { return gemv_sliced_splits(n, col_major) * (col_major ? 1 : GVT_NB_ROW); }
 struct GvSlicedLayout { int64_t tab, flags, part, colwork, total; };   /* offsets in 16-byte elements */
-static GvSlicedLayout gemv_sliced_layout(int64_t m, int64_t n, int col_major, int64_t mp)
+static GvSlicedLayout gemv_sliced_layout(int64_t m, int64_t n, int col_major)
 {
   GvSlicedLayout L;
   L.tab = 4;
   L.flags = L.tab + (GVT_XDBL * gemv_sliced_npad(n) + 1) / 2;
   L.part = L.flags + (m + 15) / 16;
-  L.colwork = L.part + (int64_t)gemv_sliced_splits(mp, n) * m * GVT_REC / 4;
+  L.colwork = L.part + (int64_t)gemv_sliced_records(n, col_major) * m * GVT_REC / 4;
   L.total = L.colwork + (col_major ? 2 * (int64_t)gemv_col_splits(m, n) * m : 0);
   return L;
 }
@@ -569,14 +586,14 @@ int64_t gemv_work_elems(int64_t m, int64_t n, int col_major, int mode, int64_t m
 {
   if (mode == 0 || fast_variant() == 0 || m <= 0 || n <= 0) return 0;
   const int64_t mp = m_plan > 0 ? m_plan : m;
-  if (gemv_sliced(mp, n)) return gemv_sliced_layout(m, n, col_major, mp).total;
+  if (gemv_sliced(mp, n)) return gemv_sliced_layout(m, n, col_major).total;
   return col_major ? 2 * (int64_t)gemv_col_splits(m, n) * m : 0;
 }
 
 const uint8_t *gemv_sliced_rowflags(const q128 *work, int64_t m, int64_t n, int col_major, int64_t m_plan)
 {
   const int64_t mp = m_plan > 0 ? m_plan : m;
-  return gemv_sliced(mp, n) ? reinterpret_cast<const uint8_t *>(work + gemv_sliced_layout(m, n, col_major, mp).flags) : nullptr;
+  return gemv_sliced(mp, n) ? reinterpret_cast<const uint8_t *>(work + gemv_sliced_layout(m, n, col_major).flags) : nullptr;
 }
 
 bool make_quad_map(CUtensorMap *tm, const void *base, int64_t inner, int64_t outer, int64_t stride_bytes, int box_inner, int box_outer, bool swizzle128);
@@ -595,13 +612,12 @@ static cudaError_t launch_gemv_col_window(const GemvArgs &a, q128 *work, const u
 
 static cudaError_t launch_gemv_sliced(const GemvArgs &a, cudaStream_t st)
 {
-  const int64_t mp = a.m_plan > 0 ? a.m_plan : a.m;
-  const GvSlicedLayout L = gemv_sliced_layout(a.m, a.n, a.col_major, mp);
+  const GvSlicedLayout L = gemv_sliced_layout(a.m, a.n, a.col_major);
   if (a.work == nullptr || a.work_elems < L.total) return cudaErrorInvalidValue;
   CUtensorMap tm;
   const bool ok = (reinterpret_cast<uintptr_t>(a.A) & 15u) == 0 &&
                   (a.col_major ? make_quad_map(&tm, a.A, a.m, a.n, a.lda * 16, GVT_ROWS, GVT_COLS, false)
-                               : make_quad_map(&tm, a.A, a.n, a.m, a.lda * 16, GVT_COLS, GVT_ROWS, true));
+                               : make_quad_map(&tm, a.A, a.n, a.m, a.lda * 16, GVT_COLS, GVT_ROWS / GVT_NB_ROW, true));
   if (!ok) {   /* no tensor map for this matrix (alignment, extents): the window kernel takes the whole call */
     cudaMemsetAsync(a.work + L.flags, 1, (size_t)a.m, st);   /* (qb_gemv_last_declined then reports every row) */
     if (a.col_major) return launch_gemv_col_window(a, a.work + L.colwork, nullptr, st);
@@ -618,13 +634,27 @@ static cudaError_t launch_gemv_sliced(const GemvArgs &a, cudaStream_t st)
   if (e != cudaSuccess) return e;
   k_gv_xscan<<<(unsigned)std::min<int64_t>((a.n + 255) / 256, 148 * 8), 256, 0, st>>>(a, hdr);
   k_gv_xtab<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(a, hdr, tab, npad);
-  const int splits = gemv_sliced_splits(mp, a.n);
-  const int64_t jsplit = (((a.n + splits - 1) / splits) + GVT_COLS - 1) / GVT_COLS * GVT_COLS;
-  const int gy = (int)((a.n + jsplit - 1) / jsplit);
-  dim3 grid((unsigned)((a.m + GVT_ROWS - 1) / GVT_ROWS), (unsigned)gy);
-  if (a.col_major) k_gemv_f64<true><<<grid, GVT_ROWS, GVT_SMEM, st>>>(tm, a, hdr, tab, jsplit, part);
-  else k_gemv_f64<false><<<grid, GVT_ROWS, GVT_SMEM, st>>>(tm, a, hdr, tab, jsplit, part);
-  k_gemv_f64_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, hdr, gy, part, rowflag);
+  const int64_t jsplit = gemv_sliced_jsplit(a.n, a.col_major);
+  const int gy = gemv_sliced_splits(a.n, a.col_major);
+  if (a.col_major) {
+    dim3 grid((unsigned)((a.m + GVT_ROWS - 1) / GVT_ROWS), (unsigned)gy);
+    k_gemv_f64<true, 1><<<grid, GVT_ROWS, gvt_smem(1), st>>>(tm, a, hdr, tab, jsplit, part);
+  } else {
+    constexpr int RB = GVT_ROWS / GVT_NB_ROW;
+    dim3 grid((unsigned)((a.m + RB - 1) / RB), (unsigned)gy);
+    if (gvt_smem(GVT_NB_ROW) > 48 * 1024) {
+      static bool attr_set[QB_MAX_DEVICES] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev >= 0 && dev < QB_MAX_DEVICES && !attr_set[dev]) {
+        e = cudaFuncSetAttribute(k_gemv_f64<false, GVT_NB_ROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, gvt_smem(GVT_NB_ROW));
+        if (e != cudaSuccess) return e;
+        attr_set[dev] = true;
+      }
+    }
+    k_gemv_f64<false, GVT_NB_ROW><<<grid, GVT_ROWS, gvt_smem(GVT_NB_ROW), st>>>(tm, a, hdr, tab, jsplit, part);
+  }
+  k_gemv_f64_fin<<<(unsigned)((a.m + 127) / 128), 128, 0, st>>>(a, hdr, gemv_sliced_records(a.n, a.col_major), part, rowflag);
   count_launch(4);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
