@@ -25,6 +25,7 @@
 #include "q128_chain.cuh"
 #include "qwide.cuh"
 #include "qslice.cuh"
+#include "qb_tc.cuh"
 
 namespace qb {
 
@@ -405,6 +406,104 @@ k_sumsq_f64(DotArgs g)
   }
 }
 
+/* the same for a contiguous vector, fed by the copy engine: tiles of B x SQ_PER elements (16 KB) arrive by cp.async.bulk into a
+ * two-stage ring — 32 KB in flight per CTA and six CTAs per SM, without a register spent on it (k_sumsq_f64 above waits on its own
+ * loads: long-scoreboard stalls 3.9 per issue at 24 warps per SM).  CTA b takes the tiles b, b + gridDim.x, ...; the last, partial
+ * tile of the vector is read with plain loads by the CTA it falls to. */
+constexpr int SQ_PER = 8;
+template <int B, int MINB>
+__global__ void __launch_bounds__(B, MINB)
+k_sumsq_tma(DotArgs g)
+{
+  constexpr int TE = B * SQ_PER;                       /* elements per tile */
+  __shared__ __align__(128) uint4 tile[2][TE];
+  __shared__ uint64_t win[4 * B];
+  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  __shared__ uint64_t full[2];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  qs_sq_cols Q = qs_sq_zero();
+  int32_t anc = QS_ANCMIN;
+  uint32_t flags = 0;
+  uint64_t *wn = win + tid;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wn[k * B] = 0ull;
+  const int64_t nfull = g.n / TE;                      /* whole tiles of the vector */
+  const int64_t mine = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](int64_t i, int s) {
+    tc::mbar_expect_tx(&full[s], TE * 16);
+    tc::bulk_load_1d(&tile[s][0], g.x + (blockIdx.x + i * gridDim.x) * TE, TE * 16, &full[s]);
+  };
+  if (tid == 0) {
+    tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (mine > 0) issue(0, 0);
+    if (mine > 1) issue(1, 1);
+  }
+  auto one = [&](const uint4 &v) {
+    const uint32_t e = (v.w >> 16) & 0x7fffu;
+    qs_square_step(Q, v.x, v.y, v.z, v.w, min((uint32_t)anc - e, QS_SHMAX));   /* a zero or an element above the anchor adds nothing here */
+    if ((uint32_t)(e - 1u) >= (uint32_t)anc) {
+      const qs_cols C = qs_sq_columns(Q);
+      double tt[8] = {C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, 0.0, 0.0};
+      int32_t st[2] = {anc, (int32_t)flags};
+      sq_rare_mem<B>(tt, st, v.x, v.y, v.z, v.w, wn);
+      Q.d0 = tt[0]; Q.o1 = tt[1]; Q.o2 = tt[2]; Q.d2 = tt[3]; Q.o3 = tt[4]; Q.o4 = tt[5]; Q.d4 = tt[6]; Q.o5 = tt[7];
+      anc = st[0]; flags = (uint32_t)st[1];
+    }
+  };
+  auto flush = [&]() {
+    const qs_cols C = qs_sq_columns(Q);
+    sq_flush<B>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn);
+    Q = qs_sq_zero();
+  };
+  for (int64_t i = 0; i < mine; ++i) {
+    const int s = (int)(i & 1);
+    tc::mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
+    const uint4 *tp = &tile[s][tid];
+#pragma unroll
+    for (int k = 0; k < SQ_PER; ++k) one(tp[k * B]);
+    if ((i % 7) == 6) flush();                        /* 56 elements: the accumulators are still exact */
+    __syncthreads();                                   /* every thread is done with stage s */
+    if (tid == 0 && i + 2 < mine) issue(i + 2, s);
+  }
+  flush();
+  if (blockIdx.x == (unsigned)(nfull % gridDim.x)) {   /* the partial tile */
+    for (int64_t j = nfull * TE + tid; j < g.n; j += B) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(g.x + j));
+      one(v);
+    }
+    flush();
+  }
+  qwide v = qw_block_tree<B>(qs_to_qwide(wn, B, anc, anc), flags, sh);
+  uint32_t *rec = reinterpret_cast<uint32_t *>(g.work);
+  if (tid == 0) {
+    qw_store(rec + 8 * (int64_t)blockIdx.x, v, flags);
+    __threadfence();
+    is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  v = qw_zero();
+  flags = 0;
+  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, flags));
+  __syncthreads();
+  v = qw_block_tree<B>(v, flags, sh);
+  if (tid == 0) {
+    if (flags & QS_FALLBACK) *g.only_if = 1u;
+    else {
+      *g.only_if = 0u;
+      const q128 r = qw_finish(v, 0u);
+      *g.result = g.do_sqrt ? q_sqrt(r) : r;
+    }
+    *g.ticket = 0u;
+  }
+}
+
 static constexpr int FAST_B = 256;       /* rounded-chain variant and the second-level CTA */
 static constexpr int FAST_GRID = 148 * 4;
 static constexpr int WIDE_B = 128;       /* window variant: 4 scratch columns per thread = 24 KB per CTA */
@@ -442,7 +541,8 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
       if (same && g.only_if != nullptr && ((fast_variant() == 2 && g.n >= (1 << 24)) || fast_variant() == 3)) {
         /* sum of squares on the FP64 pipe; the window kernel is queued behind it and runs only if an Inf / NaN / subnormal made
          * the sliced kernel decline */
-        k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
+        if (g.incx == 1 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0) k_sumsq_tma<SUMSQ_B, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
+        else k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
         k_dot_wide_l1<WIDE_B, 4, true, WIDE_GRID / 148><<<WIDE_GRID, WIDE_B, 0, st>>>(g);
         count_launch(2);
         return cudaGetLastError();
