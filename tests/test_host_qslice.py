@@ -194,3 +194,20 @@ def test_sliced_sum_of_squares_specials(qs):
     assert _sumsq(qs, y, 3)[0] == 0
     rc, r = _sumsq(qs, np.zeros_like(x), 3)
     assert rc == 1 and int(r[0]) == 0 and int(r[1]) == 0
+
+
+def test_sliced_dot_extreme_exponents_match_the_window_accumulator(qs):
+    """overflow to Inf, gradual underflow and the smallest normal results go through the same final rounding (qw_round) as the
+    window accumulator: same bits on data without cancellation"""
+    lib = qs
+    lib.qwide_dot.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(12)
+    n = 300
+    for ea, ex in ((16000, 383), (16000, 300), (-8000, -8300), (-8000, -8382), (-8191, -8191), (0, 16383), (16383, 0)):
+        a = quad.random_quads(rng, n, emin=ea - 3, emax=ea); x = quad.random_quads(rng, n, emin=ex - 3, emax=ex)
+        a[:, 1] &= np.uint64((1 << 63) - 1); x[:, 1] &= np.uint64((1 << 63) - 1)        # positive: nothing cancels
+        rc, r, info = _dot(qs, a, x, 4)
+        assert rc == 1, (ea, ex, info)
+        out = np.zeros((1, 2), dtype=np.uint64); bad = np.zeros(1, dtype=np.uint32)
+        lib.qwide_dot(n, a.ctypes.data, 1, x.ctypes.data, 1, 4, 0, out.ctypes.data, bad.ctypes.data)
+        assert (int(r[0]), int(r[1])) == (int(out[0][0]), int(out[0][1])), (ea, ex)
