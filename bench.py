@@ -290,6 +290,11 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
                 finally:
                     qb.set_fast_variant(2)
         qb.quadblas_set_num_threads(0)
+        # qaxpy (order-free: one kernel for both modes, every y_i = one correctly rounded FMA): 48 bytes per element
+        qb.axpy(nd, 1.5, xd, 1, yd, 1)
+        msa = _time_events(lambda: qb.axpy(nd, 1.5, xd, 1, yd, 1), reps)
+        extra["qaxpy"] = {"workload": f"qaxpy n={nd} unit stride (bit exact in both modes)", "ms": msa, "gqfma_per_s": nd / msa / 1e6,
+                          "roofline": {"bound": "hbm", "achieved": 48.0 * nd / msa / 1e6, "peak": hbm, "unit": "GB/s", "frac": 48.0 * nd / msa / 1e6 / hbm, "peak_source": src}}
         del xd, yd
         # BASELINE config 1 (the reference README's benchmark, 0.06 GFLOPS there): quadblas_qgemm 1000^3, doubles cast to quad, alpha=1 beta=0,
         # through the reference-named C entry point with HOST buffers (synchronous, staging included) and device resident

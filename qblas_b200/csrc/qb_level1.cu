@@ -611,13 +611,23 @@ cudaError_t launch_fold(int64_t count, const q128 *partials, int do_sqrt, q128 *
 
 /* ------------------------------------------------------------------ axpy */
 /* y_i = fma(alpha, x_i, y_i) (level1.hpp:140-223); order-free, so one kernel serves every mode */
-__global__ void k_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy)
+/* the loads of the next element are issued before the FMA of this one (the FMA is ~280 dependent instructions: without the
+ * prefetch every warp waits out a full memory round trip per element) */
+__global__ void __launch_bounds__(256, 4) k_axpy(int64_t n, q128 alpha, const q128 *x, int64_t incx, q128 *y, int64_t incy)
 {
   const qop al = qop_load(alpha);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    qacc acc = qacc_from(y[i * incy]);
-    qacc_fma(acc, al, qop_load(ldg128_l1(x + i * incx)));
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  q128 xv = ldg128_l1(x + i * incx), yv = y[i * incy];
+  for (; i < n; i += step) {
+    const int64_t in = i + step;
+    q128 xn = xv, yn = yv;
+    if (in < n) { xn = ldg128_l1(x + in * incx); yn = y[in * incy]; }
+    qacc acc = qacc_from(yv);
+    qacc_fma(acc, al, qop_load(xv));
     y[i * incy] = qacc_pack(acc);
+    xv = xn; yv = yn;
   }
 }
 
