@@ -279,7 +279,7 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
                     extra[f"qdot_fast_n{n2}"] = {"ms": ms2, "gbs": 32.0 * n2 / ms2 / 1e6, "frac": 32.0 * n2 / ms2 / 1e6 / hbm}
                 qb.nrm2(nd, xd, 1, res)
                 ms3 = _time_events(lambda: qb.nrm2(nd, xd, 1, res), reps)
-                extra["qnrm2_fast"] = {"workload": f"qnrm2 n={nd} unit stride (fast mode)", "ms": ms3, "kernel": "k_sumsq_f64 (sliced FP64 sum of squares, csrc/qslice.cuh)",
+                extra["qnrm2_fast"] = {"workload": f"qnrm2 n={nd} unit stride (fast mode)", "ms": ms3, "kernel": "k_sumsq_tma (sliced FP64 sum of squares fed by cp.async.bulk, csrc/qslice.cuh)",
                                        "roofline": {"bound": "hbm", "achieved": 16.0 * nd / ms3 / 1e6, "peak": hbm, "unit": "GB/s", "frac": 16.0 * nd / ms3 / 1e6 / hbm, "peak_source": src}}
                 qb.set_fast_variant(1)
                 try:
