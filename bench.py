@@ -642,7 +642,11 @@ def own_arm(args, rank, world, local_rank):
         te = torch.tensor([(t1 - t0) / e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": 2.0 * M * n * k / float(te.item()) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * (m_loc * k + k * n + m_loc * n),
+        # beta = 0 and contiguous rows of C: the library classifies C_in on the host and uploads one class byte per element instead of 16
+        # (qb_set_beta0_classes; beta * C_in keeps the reference's bits), so that is what crosses PCIe
+        cls = bool(qb.get_beta0_classes())
+        e2e = {"value": 2.0 * M * n * k / float(te.item()) / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": 16 * (m_loc * k + k * n) + (1 if cls else 16) * m_loc * n,
+               "c_in": "one class byte per element (beta = 0: finite sign / Inf-NaN), read in full by host threads" if cls else "16 bytes per element",
                "d2h_bytes_per_step": 16 * m_loc * n, "ms_per_step": float(te.item()) * 1e3, "steps": e2e_steps,
                "api": "quadblas_qgemm (reference C ABI), pinned host buffers, synchronous" +
                       ("" if world == 1 else "; N > 1: every rank multiplies ITS row block from its own host buffers at the same time (no broadcast / gather: "

@@ -104,6 +104,12 @@ int qb_get_tensor_path(void);
  * Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
+/* Pipelined all-host qgemm with beta = +-0 and contiguous rows of C: 1 (default) = C_in travels as one class byte per element
+ * (finite >= +0 / finite with the sign bit / Inf-or-NaN) classified by host threads, and a kernel writes the stand-in +1 / -1 / NaN
+ * on the device — beta * stand-in has exactly the bits of the reference's beta * C (level3.hpp:107), and 15/16 of the upload of C
+ * is saved; 0 = upload C_in itself. */
+void qb_set_beta0_classes(int v);
+int qb_get_beta0_classes(void);
 /* Rows of the last qb_gemv_dev that the sliced FP64 kernel declined and the window kernel recomputed (-1: that call did not take
  * the sliced path).  Synchronises the device: diagnostics and tests. */
 int64_t qb_gemv_last_declined(void);

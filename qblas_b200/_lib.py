@@ -95,6 +95,8 @@ def lib():
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
         "qb_gemv_last_declined": (C.c_int64, []),
+        "qb_set_beta0_classes": (None, [ci]),
+        "qb_get_beta0_classes": (ci, []),
         "qb_oz_last_stats": (None, [C.POINTER(i64)]),
         "qb_oz_last_mma_ms": (cd, [C.POINTER(ci)]),
         "qb_oz_last_mma_timeline": (ci, [C.POINTER(cd), ci]),

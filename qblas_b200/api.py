@@ -449,6 +449,15 @@ def get_fast_variant():
     return lib().qb_get_fast_variant()
 
 
+def set_beta0_classes(v):
+    """Pipelined all-host qgemm with beta = 0: 1 (default) = C_in goes up as one class byte per element, 0 = as its 16 bytes."""
+    lib().qb_set_beta0_classes(int(v))
+
+
+def get_beta0_classes():
+    return lib().qb_get_beta0_classes()
+
+
 def gemv_last_declined():
     """Rows of the last device qgemv that the sliced FP64 kernel declined (recomputed by the window kernel); -1 if that call did not
     take the sliced path.  Synchronises the device."""

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -48,6 +49,7 @@ static void *g_peer[QB_MAX_PEERS];
 static int g_peer_written = 0;
 static std::atomic<int> g_host_slabs{8}; /* C slabs of the pipelined all-host qgemm / row slabs of the all-host qgemv */
 static std::atomic<int> g_tensor{1};  /* fast-mode tensor path: 0 off, 1 auto (size threshold), 2 always */
+static std::atomic<int> g_beta0_classes{1};   /* qb_set_beta0_classes: the pipelined host qgemm sends C_in as class bytes when beta = 0 */
 static std::atomic<int> g_fastvar{2}; /* fast-mode level-1/2 accumulate: 2 = sliced FP64 accumulate where it applies (large row-major qgemv), window
                                          accumulator elsewhere; 1 = window accumulator everywhere; 0 = rounded-FMA chains; 3 = 2 without the size thresholds (tests) */
 int fast_variant() { return g_fastvar.load(); }
@@ -107,6 +109,7 @@ struct Scratch {
   q128 *result = nullptr;
   void *stage[3] = {nullptr, nullptr, nullptr}; size_t stage_bytes[3] = {0, 0, 0};
   cudaStream_t cs = nullptr, ks = nullptr, ds = nullptr;   /* copy-in, kernels, copy-out */
+  uint8_t *codes_h = nullptr, *codes_d = nullptr; size_t codes_bytes = 0;   /* one class byte per element of C_in (beta = 0 host path) */
 };
 static std::recursive_mutex g_mu;
 static Scratch g_scr[QB_MAX_DEVICES];
@@ -300,6 +303,53 @@ static inline bool is_trans(char t) { return t == 'T' || t == 't' || t == 'C' ||
 static inline size_t vec_bytes(int64_t n, int64_t inc) { return n <= 0 ? 0 : (size_t)((n - 1) * inc + 1) * 16; }
 static inline size_t mat_bytes(int64_t outer, int64_t inner, int64_t ld) { return (outer <= 0 || inner <= 0) ? 0 : (size_t)((outer - 1) * ld + inner) * 16; }
 
+/* ---- beta = 0 on the pipelined host path: C_in by its class, not by its bytes ----------------------------------------------------
+ * The reference evaluates beta * C even for beta = 0 (level3.hpp:107), so C_in cannot simply be ignored: 0 * C is +-0 with the sign
+ * of beta XOR the sign of C for a finite C, and NaN for an Inf or NaN.  But nothing else of C_in reaches the result.  So instead of
+ * uploading 16 bytes per element, host threads classify C_in (one byte per element: 0 = finite >= +0, 1 = finite with the sign bit,
+ * 2 = Inf / NaN) while the shared operand is on the wire, the class bytes are uploaded, and a kernel writes the stand-in +1, -1 or
+ * NaN into the device copy of C: beta * stand-in has exactly the bits of beta * C_in, whatever the mode.  An 8192 x 8192 C: 64 MB
+ * instead of 1 GiB over PCIe.  Used when the rows of C are contiguous (ldc = row length: the download then restores no padding). */
+struct CodeScan {
+  const q128 *C = nullptr;
+  uint8_t *codes = nullptr;
+  int64_t count = 0, chunk = 1 << 16, nchunks = 0;
+  std::atomic<int64_t> next{0};
+  std::vector<std::atomic<uint8_t>> done;
+  std::vector<std::thread> th;
+  explicit CodeScan(int64_t nch) : done((size_t)nch) { for (auto &d : done) d.store(0, std::memory_order_relaxed); }
+  void work()
+  {
+    for (;;) {
+      const int64_t c = next.fetch_add(1, std::memory_order_relaxed);
+      if (c >= nchunks) return;
+      const int64_t lo = c * chunk, hi = std::min(count, lo + chunk);
+      for (int64_t i = lo; i < hi; ++i) {
+        const uint64_t h = C[i].hi;
+        codes[i] = ((h >> 48) & 0x7fffu) == 0x7fffu ? (uint8_t)2 : (uint8_t)(h >> 63);
+      }
+      done[(size_t)c].store(1, std::memory_order_release);
+    }
+  }
+  void wait_elems(int64_t lo, int64_t hi)   /* until the classes of [lo, hi) are written */
+  {
+    for (int64_t c = lo / chunk; c <= (hi - 1) / chunk && c < nchunks; ++c)
+      while (!done[(size_t)c].load(std::memory_order_acquire)) std::this_thread::yield();
+  }
+  ~CodeScan() { for (auto &t : th) if (t.joinable()) t.join(); }
+};
+
+__global__ void k_c_standin(const uint8_t *codes, q128 *C, int64_t count)
+{
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t c = codes[i];
+    q128 v;
+    v.lo = 0;
+    v.hi = c == 2 ? 0x7fff800000000000ull : (0x3fff000000000000ull | ((uint64_t)(c & 1) << 63));
+    C[i] = v;
+  }
+}
+
 /* a handful of ordering events for one pipelined host call; destroyed on scope exit */
 struct EventSet {
   std::vector<cudaEvent_t> ev;
@@ -438,6 +488,8 @@ void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
 void qb_set_fast_variant(int v) { g_fastvar.store(v <= 0 ? 0 : (v >= 3 ? 3 : v)); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
+void qb_set_beta0_classes(int v) { g_beta0_classes.store(v ? 1 : 0); }
+int qb_get_beta0_classes(void) { return g_beta0_classes.load(); }
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)
 {
   std::lock_guard<std::recursive_mutex> lk(g_mu);
@@ -838,6 +890,35 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
                     : cudaMemcpy2DAsync(h + off, (size_t)ld * 16, d + off, (size_t)ld * 16, (size_t)cnt * 16, (size_t)outer, cudaMemcpyDeviceToHost, st);
     };
     cudaError_t e = cudaSuccess;
+    /* beta = +-0 and contiguous rows of C: classify C_in on the host instead of uploading it (see CodeScan) */
+    const q128 bq = toq(beta);
+    const int64_t c_outer = col ? n : m, c_inner = col ? m : n;
+    std::unique_ptr<CodeScan> scan;
+    if ((bq.hi & 0x7fffffffffffffffull) == 0 && bq.lo == 0 && ldc == c_inner && g_beta0_classes.load() != 0) {
+      const size_t need = (size_t)c_outer * (size_t)c_inner;
+      Scratch &sc_ = S();
+      bool ok = true;
+      if (sc_.codes_bytes < need) {
+        if (sc_.codes_h) cudaFreeHost(sc_.codes_h);
+        if (sc_.codes_d) cudaFree(sc_.codes_d);
+        sc_.codes_h = nullptr; sc_.codes_d = nullptr; sc_.codes_bytes = 0;
+        ok = cudaHostAlloc((void **)&sc_.codes_h, need, cudaHostAllocDefault) == cudaSuccess && cudaMalloc((void **)&sc_.codes_d, need) == cudaSuccess;
+        if (ok) sc_.codes_bytes = need;
+        else { if (sc_.codes_h) cudaFreeHost(sc_.codes_h); if (sc_.codes_d) cudaFree(sc_.codes_d); sc_.codes_h = nullptr; sc_.codes_d = nullptr; cudaGetLastError(); }
+      }
+      if (ok) {
+        try {
+          const int64_t chunk = 1 << 16, nch = ((int64_t)need + chunk - 1) / chunk;
+          scan.reset(new CodeScan(nch));
+          scan->C = (const q128 *)C; scan->codes = sc_.codes_h; scan->count = (int64_t)need; scan->chunk = chunk; scan->nchunks = nch;
+          const unsigned hw = std::thread::hardware_concurrency();
+          const int T = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+          for (int t = 0; t < T; ++t) scan->th.emplace_back([sp = scan.get()] { sp->work(); });
+        } catch (...) {
+          if (scan && scan->th.empty()) scan.reset();            /* no thread at all: upload C as before; some threads: they finish the scan */
+        }
+      }
+    }
     /* storage shapes (outer x inner): A is k x m when (col != tA) else m x k; B is n x k when (col != tB) else k x n */
     const bool a_m_outer = !(col != tA), b_n_outer = (col != tB);
     if (!col) e = cudaMemcpyAsync((void *)dB, B, b_bytes, cudaMemcpyHostToDevice, cs);   /* shared operand first */
@@ -849,7 +930,17 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       if (cnt <= 0) { e = cudaEventRecord(ev_in[p], cs); continue; }
       if (!col) e = xfer((void *)dA, (void *)A, true, a_m_outer, a_m_outer ? m : k, a_m_outer ? k : m, lda, c0, cnt, cs);
       else e = xfer((void *)dB, (void *)B, true, b_n_outer, b_n_outer ? n : k, b_n_outer ? k : n, ldb, c0, cnt, cs);
-      if (e == cudaSuccess) e = xfer((void *)dC, C, true, true, col ? n : m, col ? m : n, ldc, c0, cnt, cs);   /* beta*C is always read */
+      if (e == cudaSuccess && !scan) e = xfer((void *)dC, C, true, true, col ? n : m, col ? m : n, ldc, c0, cnt, cs);   /* beta*C is always read */
+      if (e == cudaSuccess && scan) {   /* ... through its classes: one byte per element, expanded to +1 / -1 / NaN on the device */
+        const int64_t lo = c0 * c_inner, cntel = cnt * c_inner;
+        scan->wait_elems(lo, lo + cntel);
+        e = cudaMemcpyAsync(S().codes_d + lo, S().codes_h + lo, (size_t)cntel, cudaMemcpyHostToDevice, cs);
+        if (e == cudaSuccess) {
+          k_c_standin<<<(unsigned)std::min<int64_t>((cntel + 255) / 256, 148 * 8), 256, 0, cs>>>(S().codes_d + lo, (q128 *)dC + lo, cntel);
+          count_launch();
+          e = cudaGetLastError();
+        }
+      }
       if (e == cudaSuccess) e = cudaEventRecord(ev_in[p], cs);
     }
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, ev_in[P], 0);

@@ -110,3 +110,39 @@ def test_pipelined_host_gemv_equals_device_path(qb, layout, mode):
         qb.set_mode(qb.MODE_REFERENCE)
     assert quad.same_bits(to_host(dy), hy).all()
     assert not quad.same_bits(hy, y0).all()
+
+
+@pytest.mark.parametrize("layout,mode", [("R", "fast"), ("C", "fast"), ("R", "ref")])
+@pytest.mark.parametrize("beta_bits", [0, 1 << 63])
+def test_pipelined_host_path_beta_zero_sends_classes_of_c(qb, layout, mode, beta_bits):
+    """beta = +-0 with contiguous rows of C: the host path classifies C_in (finite sign / Inf-NaN) instead of uploading it and the
+    device multiplies beta by a stand-in of the same class — the result must carry the bits of the device-resident call, which
+    evaluates beta * C_in itself (level3.hpp:107: 0 * NaN and 0 * Inf are NaN, 0 * negative is -0), and of the same call with the
+    class path switched off."""
+    rng = np.random.default_rng(31 + (beta_bits >> 63))
+    m, n, k = (2048, 1024, 1024) if layout == "R" else (1024, 2048, 1024)
+    col = layout == "C"
+    a_shape = (k, m) if col else (m, k); b_shape = (n, k) if col else (k, n); c_shape = (n, m) if col else (m, n)
+    A = qgen.matrix(rng, a_shape[0], a_shape[1], "D113"); B = qgen.matrix(rng, b_shape[0], b_shape[1], "D113")
+    C0 = qgen.matrix(rng, c_shape[0], c_shape[1], "D113")
+    inf = np.array([0, 0x7FFF << 48], dtype=np.uint64); nan = np.array([1, 0x7FFF << 48], dtype=np.uint64)
+    C0[5] = inf; C0[6] = inf ^ np.array([0, 1 << 63], dtype=np.uint64); C0[7] = nan; C0[8] = 0; C0[9] = np.array([0, 1 << 63], dtype=np.uint64)
+    C0[10] = np.array([3, 0], dtype=np.uint64); C0[c_shape[1] * 700 + 3] = nan; C0[-1] = inf
+    # a zero row of A: alpha * S = 0 there, so the sign of 0 * C decides the sign of the result
+    if not col:
+        A[3 * k: 4 * k] = 0
+    alpha = quad.random_quads(rng, 1)[0]
+    beta = np.array([0, beta_bits], dtype=np.uint64)
+    assert A.nbytes + B.nbytes + C0.nbytes >= 64 << 20
+    qb.set_mode(qb.MODE_FAST if mode == "fast" else qb.MODE_REFERENCE)
+    try:
+        dev, host = _run_both(qb, layout, "N", "N", m, n, k, a_shape[1], b_shape[1], c_shape[1], A, B, C0, alpha, beta)
+        qb.set_beta0_classes(0)
+        hC = C0.copy()
+        qb.gemm(layout, m, n, k, alpha, A, a_shape[1], B, b_shape[1], beta, hC, c_shape[1])
+    finally:
+        qb.set_beta0_classes(1)
+        qb.set_mode(qb.MODE_REFERENCE)
+    assert quad.same_bits(dev, host).all(), f"{(~quad.same_bits(dev, host)).sum()} entries differ"
+    assert quad.same_bits(hC, host).all()
+    assert quad.is_nan(host[[5, 6, 7]]).all() and not quad.is_nan(host[[8, 9, 10]]).any()
