@@ -15,6 +15,8 @@
 #include "qb_crt.cuh"
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <cstdio>
 #include <cstring>
 #include <cmath>
@@ -184,15 +186,16 @@ struct PageRing {
   cudaStream_t st[PG_THREADS] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev[PG_THREADS][PG_SLOTS] = {};
 };
-static PageRing g_ring;   /* guarded by g_mu like every host path */
+static PageRing g_rings[2];   /* guarded by g_mu like every host path; [0] uploads (and every synchronous path), [1] the download thread of the pipelined qgemm */
 static bool is_pageable(const void *p)
 {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
   return at.type == cudaMemoryTypeUnregistered;
 }
-static bool ring_ready(int dev)
+static bool ring_ready(int dev, int ring)
 {
+  PageRing &g_ring = g_rings[ring];
   if (!g_ring.base) {
     if (g_ring.tried) return false;
     g_ring.tried = true;
@@ -216,12 +219,13 @@ static bool ring_ready(int dev)
   return true;
 }
 /* to_dev: host -> device, else device -> host.  Synchronous. */
-static cudaError_t paged_copy(void *dst, const void *src, size_t bytes, bool to_dev)
+static cudaError_t paged_copy(void *dst, const void *src, size_t bytes, bool to_dev, int ring = 0)
 {
+  PageRing &g_ring = g_rings[ring];
   const void *host = to_dev ? src : dst;
   int dev = 0;
   cudaGetDevice(&dev);
-  if (bytes < 2 * PG_CHUNK || !is_pageable(host) || !ring_ready(dev))
+  if (bytes < 2 * PG_CHUNK || !is_pageable(host) || !ring_ready(dev, ring))
     return cudaMemcpy(dst, src, bytes, to_dev ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
   const size_t nchunks = (bytes + PG_CHUNK - 1) / PG_CHUNK;
   cudaError_t errs[PG_THREADS];
@@ -394,18 +398,66 @@ static void swap_roles(GemmArgs &g)
 
 /* hooks of the all-host tensor-path qgemm: slabs of rows arrive on the copy-in stream (events ev_in[p]), finished passes leave on
  * the copy-out stream */
+/* Pageable host buffers (std::vector<Sleef_quad>, numpy: what callers of the reference API pass): a cudaMemcpyAsync from / to such
+ * memory is staged by the driver at a fraction of the PCIe rate AND blocks the calling thread, which here is the thread that
+ * enqueues the kernels.  So the pipelined qgemm hands the transfers to two feeder threads: the uploader runs the whole upload
+ * sequence (paged_copy through ring 0 for pageable sources: four threads copy into page-locked slots while the copy engine moves
+ * the previous ones), records the slab events and publishes a flag per slab, which the enqueueing thread waits for before it makes
+ * a stream wait for that event (an event must be recorded before it is waited on); the downloader takes (event, range) jobs,
+ * waits for the event and brings the rows home through ring 1.  8192^3 from numpy arrays: 275 ms -> see DESIGN.md §7. */
+struct HostFeeder {
+  std::vector<std::atomic<int>> up_done;          /* [P + 1]: slab p (P = the shared operand) is uploaded and its event recorded */
+  std::atomic<int> err{(int)cudaSuccess};
+  std::thread up, dn;
+  struct Job { cudaEvent_t ev; char *host; const char *dev; size_t bytes; };
+  std::mutex mu; std::condition_variable cv; std::deque<Job> jobs; bool closing = false;
+  bool threaded_up = false, threaded_dn = false;
+  explicit HostFeeder(int n) : up_done((size_t)n) { for (auto &f : up_done) f.store(0, std::memory_order_relaxed); }
+  void wait_up(int idx) { while (!up_done[(size_t)idx].load(std::memory_order_acquire)) std::this_thread::yield(); }
+  void fail_all(cudaError_t e) { err.store((int)e); for (auto &f : up_done) f.store(1, std::memory_order_release); }
+  void push(cudaEvent_t ev, void *host, const void *dev, size_t bytes)
+  {
+    { std::lock_guard<std::mutex> lk(mu); jobs.push_back(Job{ev, (char *)host, (const char *)dev, bytes}); }
+    cv.notify_one();
+  }
+  void download_loop(int device)
+  {
+    cudaSetDevice(device);
+    for (;;) {
+      Job j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return closing || !jobs.empty(); });
+        if (jobs.empty()) return;
+        j = jobs.front(); jobs.pop_front();
+      }
+      cudaError_t e = cudaEventSynchronize(j.ev);
+      if (e == cudaSuccess) e = paged_copy(j.host, j.dev, j.bytes, false, 1);
+      if (e != cudaSuccess) err.store((int)e);
+    }
+  }
+  void finish()   /* every job handed over has been carried out, both threads are gone */
+  {
+    if (up.joinable()) up.join();
+    if (dn.joinable()) { { std::lock_guard<std::mutex> lk(mu); closing = true; } cv.notify_all(); dn.join(); }
+  }
+  ~HostFeeder() { finish(); }
+};
+
 struct HostPipe {
   cudaEvent_t *ev_in; int P; int64_t blk;
   cudaStream_t ks, ds;
   EventSet *out_ev; int out_used;
   void *dC; void *hC; int64_t outer, inner, ldc;   /* C as (outer x inner) storage: slabs along `outer` are contiguous */
   cudaError_t err;
+  HostFeeder *feed = nullptr;
 };
 static int host_rows_in(int64_t r0, int64_t rows, void *sA, void *sF, void *user)
 {
   HostPipe *hp = (HostPipe *)user;
   int idx = (int)((r0 + rows - 1) / hp->blk);
   if (idx >= hp->P) idx = hp->P - 1;
+  if (hp->feed) hp->feed->wait_up(idx);            /* the event is recorded by the uploader thread: not before this */
   cudaError_t e = cudaStreamWaitEvent((cudaStream_t)sA, hp->ev_in[idx], 0);
   if (e == cudaSuccess) e = cudaStreamWaitEvent((cudaStream_t)sF, hp->ev_in[idx], 0);
   if (e != cudaSuccess) { hp->err = e; return 1; }
@@ -418,8 +470,9 @@ static void host_rows_out(int64_t r0, int64_t rows, void *user)
   if (!hp->out_ev->make(hp->out_used + 1)) { hp->err = cudaErrorMemoryAllocation; return; }
   cudaEvent_t ev = hp->out_ev->ev[hp->out_used++];
   cudaError_t e = cudaEventRecord(ev, hp->ks);            /* ks already waits for the reconstruction of these rows */
-  if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->ds, ev, 0);
   const size_t off = (size_t)r0 * hp->ldc * 16, bytes = ((size_t)(rows - 1) * hp->ldc + hp->inner) * 16;
+  if (e == cudaSuccess && hp->feed && hp->feed->threaded_dn) { hp->feed->push(ev, (char *)hp->hC + off, (char *)hp->dC + off, bytes); return; }
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(hp->ds, ev, 0);
   if (e == cudaSuccess) e = cudaMemcpyAsync((char *)hp->hC + off, (char *)hp->dC + off, bytes, cudaMemcpyDeviceToHost, hp->ds);
   if (e != cudaSuccess) hp->err = e;
 }
@@ -921,28 +974,62 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
     }
     /* storage shapes (outer x inner): A is k x m when (col != tA) else m x k; B is n x k when (col != tB) else k x n */
     const bool a_m_outer = !(col != tA), b_n_outer = (col != tB);
-    if (!col) e = cudaMemcpyAsync((void *)dB, B, b_bytes, cudaMemcpyHostToDevice, cs);   /* shared operand first */
-    else e = cudaMemcpyAsync((void *)dA, A, a_bytes, cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess) e = cudaEventRecord(ev_in[P], cs);
     const int64_t blk = ((split + P - 1) / P + 127) / 128 * 128;
-    for (int p = 0; p < P && e == cudaSuccess; ++p) {
-      const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
-      if (cnt <= 0) { e = cudaEventRecord(ev_in[p], cs); continue; }
-      if (!col) e = xfer((void *)dA, (void *)A, true, a_m_outer, a_m_outer ? m : k, a_m_outer ? k : m, lda, c0, cnt, cs);
-      else e = xfer((void *)dB, (void *)B, true, b_n_outer, b_n_outer ? n : k, b_n_outer ? k : n, ldb, c0, cnt, cs);
-      if (e == cudaSuccess && !scan) e = xfer((void *)dC, C, true, true, col ? n : m, col ? m : n, ldc, c0, cnt, cs);   /* beta*C is always read */
-      if (e == cudaSuccess && scan) {   /* ... through its classes: one byte per element, expanded to +1 / -1 / NaN on the device */
-        const int64_t lo = c0 * c_inner, cntel = cnt * c_inner;
-        scan->wait_elems(lo, lo + cntel);
-        e = cudaMemcpyAsync(S().codes_d + lo, S().codes_h + lo, (size_t)cntel, cudaMemcpyHostToDevice, cs);
-        if (e == cudaSuccess) {
-          k_c_standin<<<(unsigned)std::min<int64_t>((cntel + 255) / 256, 148 * 8), 256, 0, cs>>>(S().codes_d + lo, (q128 *)dC + lo, cntel);
-          count_launch();
-          e = cudaGetLastError();
-        }
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    HostFeeder feed(P + 1);
+    const bool page_in = is_pageable(A) || is_pageable(B) || (!scan && is_pageable(C));
+    const bool page_out = is_pageable(C);
+    /* an upload of a slab taken along the strided direction of a pageable matrix goes through the page-locked ring (synchronous:
+     * that is why it runs on the uploader thread); everything else is an asynchronous copy as before */
+    auto up_xfer = [&](void *dev, const void *host, bool along_outer, int64_t outer, int64_t inner, int64_t ld, int64_t c0, int64_t cnt) -> cudaError_t {
+      if (cnt > 0 && along_outer && page_in && is_pageable(host)) {
+        const size_t off = (size_t)c0 * ld * 16, bytes = (c0 + cnt < outer ? (size_t)cnt * ld : (size_t)(cnt - 1) * ld + inner) * 16;
+        return paged_copy((char *)dev + off, (const char *)host + off, bytes, true, 0);
       }
-      if (e == cudaSuccess) e = cudaEventRecord(ev_in[p], cs);
+      return xfer(dev, const_cast<void *>(host), true, along_outer, outer, inner, ld, c0, cnt, cs);
+    };
+    auto upload_all = [&]() {
+      cudaError_t ue = cudaSuccess;
+      if (page_in) ue = cudaSetDevice(cur_dev);
+      if (ue == cudaSuccess) {                                   /* shared operand first */
+        const void *src = !col ? B : A; void *dst = !col ? (void *)dB : (void *)dA; const size_t bytes = !col ? b_bytes : a_bytes;
+        ue = (page_in && is_pageable(src)) ? paged_copy(dst, src, bytes, true, 0) : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs);
+      }
+      if (ue == cudaSuccess) ue = cudaEventRecord(ev_in[P], cs);
+      if (ue != cudaSuccess) { feed.fail_all(ue); return; }
+      feed.up_done[(size_t)P].store(1, std::memory_order_release);
+      for (int p = 0; p < P; ++p) {
+        const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
+        if (cnt > 0) {
+          if (!col) ue = up_xfer((void *)dA, A, a_m_outer, a_m_outer ? m : k, a_m_outer ? k : m, lda, c0, cnt);
+          else ue = up_xfer((void *)dB, B, b_n_outer, b_n_outer ? n : k, b_n_outer ? k : n, ldb, c0, cnt);
+          if (ue == cudaSuccess && !scan) ue = up_xfer((void *)dC, C, true, col ? n : m, col ? m : n, ldc, c0, cnt);   /* beta*C is always read */
+          if (ue == cudaSuccess && scan) {   /* ... through its classes: one byte per element, expanded to +1 / -1 / NaN on the device */
+            const int64_t lo = c0 * c_inner, cntel = cnt * c_inner;
+            scan->wait_elems(lo, lo + cntel);
+            ue = cudaMemcpyAsync(S().codes_d + lo, S().codes_h + lo, (size_t)cntel, cudaMemcpyHostToDevice, cs);
+            if (ue == cudaSuccess) {
+              k_c_standin<<<(unsigned)std::min<int64_t>((cntel + 255) / 256, 148 * 8), 256, 0, cs>>>(S().codes_d + lo, (q128 *)dC + lo, cntel);
+              count_launch();
+              ue = cudaGetLastError();
+            }
+          }
+        }
+        if (ue == cudaSuccess) ue = cudaEventRecord(ev_in[p], cs);
+        if (ue != cudaSuccess) { feed.fail_all(ue); return; }
+        feed.up_done[(size_t)p].store(1, std::memory_order_release);
+      }
+    };
+    if (page_in) {
+      try { feed.up = std::thread(upload_all); feed.threaded_up = true; } catch (...) { feed.threaded_up = false; }
     }
+    if (!feed.threaded_up) upload_all();
+    if (page_out) {
+      try { feed.dn = std::thread([&feed, cur_dev] { feed.download_loop(cur_dev); }); feed.threaded_dn = true; } catch (...) { feed.threaded_dn = false; }
+    }
+    feed.wait_up(P);
+    e = (cudaError_t)feed.err.load();
     if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, ev_in[P], 0);
     /* fast mode: ONE tensor-path call whose row passes wait for their slabs (passes outer: the residue planes of the shared
      * operand are computed once and stay resident) and whose finished passes are downloaded while the next ones compute */
@@ -954,22 +1041,24 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
       EventSet out_ev;
       HostPipe hp;
       hp.ev_in = ev_in; hp.P = P; hp.blk = blk; hp.ks = ks; hp.ds = ds; hp.out_ev = &out_ev; hp.out_used = 0;
-      hp.dC = (void *)dC; hp.hC = C; hp.outer = col ? n : m; hp.inner = col ? m : n; hp.ldc = ldc; hp.err = cudaSuccess;
+      hp.dC = (void *)dC; hp.hC = C; hp.outer = col ? n : m; hp.inner = col ? m : n; hp.ldc = ldc; hp.err = cudaSuccess; hp.feed = &feed;
       OzHooks h;
       h.order = 1; h.rows_in = host_rows_in; h.rows_user = &hp; h.cb = host_rows_out; h.cb_user = &hp;
       h.min_passes = (int)std::min<int64_t>(4096, (split + 1023) / 1024);     /* passes of <= 1024 rows: a short tail after the last upload */
       int used = 0;
       const cudaError_t oe = launch_gemm_ozaki(g, ks, &used, h);
       if (oe != cudaSuccess || hp.err != cudaSuccess) {
+        feed.finish();
         cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds);
         return fail(QB_ERR_CUDA, "qgemm pipelined host path (tensor)", oe != cudaSuccess ? oe : hp.err);
       }
       streamed = used != 0;
-      if (streamed) { cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds); }   /* out_ev is destroyed with this scope */
+      if (streamed) { feed.finish(); cudaStreamSynchronize(cs); cudaStreamSynchronize(ks); cudaStreamSynchronize(ds); }   /* out_ev is destroyed with this scope */
     }
     for (int p = 0; p < P && e == cudaSuccess && rc == QB_OK && !streamed; ++p) {
       const int64_t c0 = (int64_t)p * blk, cnt = std::min(blk, split - c0);
       if (cnt <= 0) break;
+      feed.wait_up(p);
       e = cudaStreamWaitEvent(ks, ev_in[p], 0);
       if (e != cudaSuccess) break;
       /* element offsets of the block inside A / B / C (same strides as gemm_dev_impl derives) */
@@ -980,9 +1069,17 @@ int qb_gemm(char layout, char transa, char transb, int64_t m, int64_t n, int64_t
                          toq(beta), (q128 *)dC + c_off, ldc, ks);
       if (rc) break;
       e = cudaEventRecord(ev_done[p], ks);
+      if (e == cudaSuccess && feed.threaded_dn) {
+        const int64_t c_out = col ? n : m, c_in = col ? m : n;
+        const size_t off = (size_t)c0 * ldc * 16, bytes = (c0 + cnt < c_out ? (size_t)cnt * ldc : (size_t)(cnt - 1) * ldc + c_in) * 16;
+        feed.push(ev_done[p], (char *)C + off, (const char *)dC + off, bytes);
+        continue;
+      }
       if (e == cudaSuccess) e = cudaStreamWaitEvent(ds, ev_done[p], 0);
       if (e == cudaSuccess) e = xfer((void *)dC, C, false, true, col ? n : m, col ? m : n, ldc, c0, cnt, ds);
     }
+    feed.finish();
+    if (e == cudaSuccess) e = (cudaError_t)feed.err.load();
     cudaError_t e2 = cudaStreamSynchronize(cs), e3 = cudaStreamSynchronize(ks), e4 = cudaStreamSynchronize(ds);
     if (rc) return rc;
     if (e == cudaSuccess) e = e2 != cudaSuccess ? e2 : (e3 != cudaSuccess ? e3 : e4);
