@@ -1123,13 +1123,17 @@ int qb_gemv(char layout, int64_t m, int64_t n, const qb_quad *alpha, const void 
     EventSet evs;
     if (!evs.make(P)) return fail(QB_ERR_CUDA, "qgemv: event creation", cudaGetLastError());
     const int64_t blk = ((m + P - 1) / P + 31) / 32 * 32;
+    const bool a_pageable = is_pageable(A);
     cudaError_t e = cudaSuccess;
     for (int p = 0; p < P && e == cudaSuccess; ++p) {
       const int64_t r0 = (int64_t)p * blk, cnt = std::min(blk, m - r0);
       if (cnt <= 0) break;
       if (!col) {
         const size_t off = (size_t)r0 * lda * 16, bytes = ((size_t)(cnt - 1) * lda + n) * 16;
-        e = cudaMemcpyAsync((char *)dA + off, (const char *)A + off, bytes, cudaMemcpyHostToDevice, cs);
+        /* pageable A: through the page-locked ring (four copy threads; synchronous, but the kernels of the earlier slabs are already
+         * queued, so the device multiplies slab p - 1 while this thread copies slab p) */
+        if (a_pageable) e = paged_copy((char *)dA + off, (const char *)A + off, bytes, true, 0);
+        else e = cudaMemcpyAsync((char *)dA + off, (const char *)A + off, bytes, cudaMemcpyHostToDevice, cs);
       } else {
         const size_t off = (size_t)r0 * 16;
         e = cudaMemcpy2DAsync((char *)dA + off, (size_t)lda * 16, (const char *)A + off, (size_t)lda * 16, (size_t)cnt * 16, (size_t)n, cudaMemcpyHostToDevice, cs);
