@@ -253,3 +253,32 @@ def test_sliced_gemv_small_shapes(fast3, oracle, layout, m, n):
     got = to_host(dy)
     exact, ratio, klass = _rows_check(oracle, m, n, A, lda, x, got, layout)
     assert ratio.max() <= 2.0 / n + 1e-6 and quad.same_bits(got, exact).mean() > 0.99
+
+
+def test_sliced_gemv_random_shapes(fast3, oracle):
+    """a sweep of random shapes, paddings, strides and layouts through the sliced kernel (variant 3: no size threshold): ragged tiles and
+    splits, fewer rows than a CTA, sprinkled zeros; every row against the long accumulator"""
+    rng = np.random.default_rng(2024)
+    for trial in range(28):
+        layout = "RC"[trial % 2]
+        m = int(rng.integers(1, 700)); n = int(rng.integers(128, 3000))
+        pad = int(rng.integers(0, 4)); incx = int(rng.integers(1, 3)); incy = int(rng.integers(1, 4))
+        kind = ["D113", "D53", "Dexp"][trial % 3]
+        lda = (n if layout == "R" else m) + pad
+        A = qgen.matrix(rng, m if layout == "R" else n, n if layout == "R" else m, kind, lda)
+        x = quad.random_quads(rng, (n - 1) * incx + 1, "D53" if kind == "D53" else "D113"); y0 = quad.random_quads(rng, (m - 1) * incy + 1)
+        if trial % 4 == 0:
+            A[rng.integers(0, len(A), len(A) // 7)] = 0; x[rng.integers(0, len(x), len(x) // 9)] = 0
+        dy = to_dev(y0)
+        fast3.gemv(layout, m, n, 1.0, to_dev(A), lda, to_dev(x), incx, 0.0, dy, incy)
+        declined = fast3.gemv_last_declined()
+        got = to_host(dy)
+        xs = np.ascontiguousarray(x[::incx][:n])
+        idx = np.stack([np.arange(m), np.zeros(m, dtype=np.int64)], axis=1)
+        exact, ratio, klass = oracle.exact_dot_check(layout, n, A, lda, xs, 1 if layout == "R" else n, idx, np.ascontiguousarray(got[::incy][:m]))
+        assert (klass == 0).all() and ratio.max() <= 1.0, (trial, layout, m, n, lda, incx, incy, kind, float(ratio.max()))
+        assert quad.same_bits(got[::incy][:m], exact).mean() > 0.98, (trial, layout, m, n)
+        assert declined >= 0 and (kind == "Dexp" or trial % 4 == 0 or declined == 0), (trial, declined)
+        if incy > 1:
+            mask = np.ones(len(y0), dtype=bool); mask[::incy] = False
+            assert quad.same_bits(got[mask], y0[mask]).all()
