@@ -504,6 +504,146 @@ k_sumsq_tma(DotArgs g)
   }
 }
 
+/* qdot of two contiguous vectors on the FP64 pipe: both factors are sliced on the fly (qs_dot_step), each thread keeps an anchor
+ * per vector, tiles of B x DQ_PER elements of x and of y arrive by cp.async.bulk into a two-stage ring.  The truncation is
+ * relative to (largest |x| so far) x (largest |y| so far) of the thread, so the call is accepted when some product comes within
+ * 2^-12 of the largest anchor pair (qs_accept's test on max e(x_j) + e(y_j)); otherwise — or with an Inf / NaN / subnormal — the
+ * kernel sets *g.only_if and the window kernel queued behind it computes the result. */
+constexpr int DQ_PER = 4;
+template <int B>
+__device__ __noinline__ void dq_rare_mem(double *t, int32_t *st, const uint4 *xy, uint64_t *w)
+{
+  qs_cols C; C.c0 = t[0]; C.c1 = t[1]; C.c2 = t[2]; C.c3 = t[3]; C.c4 = t[4]; C.c5 = t[5];
+  qs_row SX, SY; SX.anc = st[0]; SY.anc = st[1]; SX.dmax = SY.dmax = 0;
+  uint32_t flags = (uint32_t)st[2];
+  const uint4 x = xy[0], y = xy[1];
+  const uint32_t ex = (x.w >> 16) & 0x7fffu, ey = (y.w >> 16) & 0x7fffu;
+  uint32_t shx = min((uint32_t)SX.anc - ex, QS_SHMAX), shy = min((uint32_t)SY.anc - ey, QS_SHMAX);
+  if ((uint32_t)(ex - 1u) >= (uint32_t)SX.anc) shx = qs_rare(C, SX, flags, ex, x.x, x.y, x.z, x.w, w, B);
+  if ((uint32_t)(ey - 1u) >= (uint32_t)SY.anc) shy = qs_rare(C, SY, flags, ey, y.x, y.y, y.z, y.w, w, B);
+  if (shx < QS_SHMAX && shy < QS_SHMAX) qs_dot_step(C, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, shx, shy);
+  t[0] = C.c0; t[1] = C.c1; t[2] = C.c2; t[3] = C.c3; t[4] = C.c4; t[5] = C.c5;
+  st[0] = SX.anc; st[1] = SY.anc; st[2] = (int32_t)flags;
+}
+
+template <int B>
+__device__ __forceinline__ int block_max(int v, int *shm /* B / 32 ints */)
+{
+  v = __reduce_max_sync(0xffffffffu, v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = shm[0];
+#pragma unroll
+  for (int w = 1; w < B / 32; ++w) r = max(r, shm[w]);
+  return r;
+}
+
+template <int B, int MINB>
+__global__ void __launch_bounds__(B, MINB)
+k_dot_f64_tma(DotArgs g)
+{
+  constexpr int TE = B * DQ_PER;
+  __shared__ __align__(128) uint4 tx[2][TE];
+  __shared__ __align__(128) uint4 ty[2][TE];
+  __shared__ uint64_t win[4 * B];
+  __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
+  __shared__ int shm[B / 32];
+  __shared__ uint64_t full[2];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  qs_cols C = qs_cols_zero();
+  int32_t ancx = QS_ANCMIN, ancy = QS_ANCMIN, dmax = QS_EXNONE;
+  uint32_t flags = 0;
+  uint64_t *wn = win + tid;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) wn[k * B] = 0ull;
+  const int64_t nfull = g.n / TE;
+  const int64_t mine = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](int64_t i, int s) {
+    const int64_t off = (blockIdx.x + i * gridDim.x) * TE;
+    tc::mbar_expect_tx(&full[s], 2 * TE * 16);
+    tc::bulk_load_1d(&tx[s][0], g.x + off, TE * 16, &full[s]);
+    tc::bulk_load_1d(&ty[s][0], g.y + off, TE * 16, &full[s]);
+  };
+  if (tid == 0) {
+    tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (mine > 0) issue(0, 0);
+    if (mine > 1) issue(1, 1);
+  }
+  auto one = [&](const uint4 &x, const uint4 &y) {
+    const uint32_t ex = (x.w >> 16) & 0x7fffu, ey = (y.w >> 16) & 0x7fffu;
+    /* a zero factor or one above its anchor gets QS_SHMAX: the hot step adds nothing then */
+    qs_dot_step(C, x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w, min((uint32_t)ancx - ex, QS_SHMAX), min((uint32_t)ancy - ey, QS_SHMAX));
+    if (((uint32_t)(ex - 1u) >= (uint32_t)ancx) | ((uint32_t)(ey - 1u) >= (uint32_t)ancy)) {
+      double tt[6] = {C.c0, C.c1, C.c2, C.c3, C.c4, C.c5};
+      int32_t st[3] = {ancx, ancy, (int32_t)flags};
+      uint4 xy[2] = {x, y};
+      dq_rare_mem<B>(tt, st, xy, wn);
+      C.c0 = tt[0]; C.c1 = tt[1]; C.c2 = tt[2]; C.c3 = tt[3]; C.c4 = tt[4]; C.c5 = tt[5];
+      ancx = st[0]; ancy = st[1]; flags = (uint32_t)st[2];
+      if (ex != 0u && ey != 0u) dmax = max(dmax, (int32_t)(ex + ey));   /* a zero factor is no product */
+    } else {
+      dmax = max(dmax, (int32_t)(ex + ey));
+    }
+  };
+  auto flush = [&]() { sq_flush<B>(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, wn); C = qs_cols_zero(); };
+  for (int64_t i = 0; i < mine; ++i) {
+    const int s = (int)(i & 1);
+    tc::mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
+#pragma unroll
+    for (int k = 0; k < DQ_PER; ++k) one(tx[s][k * B + tid], ty[s][k * B + tid]);
+    if ((i & 15) == 15) flush();                      /* 64 pairs: the columns are still exact */
+    __syncthreads();
+    if (tid == 0 && i + 2 < mine) issue(i + 2, s);
+  }
+  flush();
+  if (blockIdx.x == (unsigned)(nfull % gridDim.x)) {   /* the partial tile */
+    for (int64_t j = nfull * TE + tid; j < g.n; j += B)
+      one(__ldg(reinterpret_cast<const uint4 *>(g.x + j)), __ldg(reinterpret_cast<const uint4 *>(g.y + j)));
+    flush();
+  }
+  int asum = block_max<B>(ancx + ancy, shm);
+  int dm = block_max<B>(dmax, shm);
+  qwide v = qw_block_tree<B>(qs_to_qwide(wn, B, ancx, ancy), flags, sh);
+  uint32_t *rec = reinterpret_cast<uint32_t *>(g.work);
+  if (tid == 0) {
+    uint32_t *dst = rec + 12 * (int64_t)blockIdx.x;
+    qw_store(dst, v, flags);
+    dst[8] = (uint32_t)asum; dst[9] = (uint32_t)dm;
+    __threadfence();
+    is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  v = qw_zero();
+  flags = 0;
+  asum = 0; dm = QS_EXNONE;
+  for (int i = tid; i < (int)gridDim.x; i += B) {
+    const uint32_t *src = rec + 12 * (int64_t)i;
+    v = qw_merge_ni(v, qw_load_cg(src, flags));
+    asum = max(asum, (int)__ldcg(src + 8)); dm = max(dm, (int)__ldcg(src + 9));
+  }
+  asum = block_max<B>(asum, shm);
+  dm = block_max<B>(dm, shm);
+  __syncthreads();
+  v = qw_block_tree<B>(v, flags, sh);
+  if (tid == 0) {
+    if ((flags & QS_FALLBACK) || dm < asum - QS_ACCEPT) *g.only_if = 1u;
+    else {
+      *g.only_if = 0u;
+      const q128 r = qw_finish(v, 0u);
+      *g.result = g.do_sqrt ? q_sqrt(r) : r;
+    }
+    *g.ticket = 0u;
+  }
+}
+
 static constexpr int FAST_B = 256;       /* rounded-chain variant and the second-level CTA */
 static constexpr int FAST_GRID = 148 * 4;
 static constexpr int WIDE_B = 128;       /* window variant: 4 scratch columns per thread = 24 KB per CTA */
@@ -513,7 +653,7 @@ static constexpr int SUMSQ_B = 128, SUMSQ_CTAS = 6, SUMSQ_GRID = 148 * SUMSQ_CTA
 int64_t dot_work_elems(int64_t n, int T, int mode)
 {
   (void)n;
-  if (mode != 0) return 2 * SUMSQ_GRID;   /* 32-byte window records */
+  if (mode != 0) return 3 * SUMSQ_GRID;   /* 32-byte window records (48 bytes with the anchors of the sliced dot) */
   return 3 * (int64_t)(T < 1 ? 1 : T) + 4;
 }
 
@@ -544,6 +684,16 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
         if (g.incx == 1 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0) k_sumsq_tma<SUMSQ_B, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
         else k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
         k_dot_wide_l1<WIDE_B, 4, true, WIDE_GRID / 148><<<WIDE_GRID, WIDE_B, 0, st>>>(g);
+        count_launch(2);
+        return cudaGetLastError();
+      }
+      /* two different contiguous vectors with both factors sliced on the fly: measured SLOWER than the window kernel (n = 10^8:
+       * 0.675 vs 0.607 ms — two slicings per product cost more than the integer multiplier saves, and 32 bytes per product leave
+       * the window kernel at 0.82 of HBM anyway), so it is not part of the default; fast variant 3 keeps it reachable for the tests */
+      if (!same && g.only_if != nullptr && g.incx == 1 && g.incy == 1 && ((reinterpret_cast<uintptr_t>(g.x) | reinterpret_cast<uintptr_t>(g.y)) & 15u) == 0 &&
+          fast_variant() == 3) {
+        k_dot_f64_tma<SUMSQ_B, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
+        k_dot_wide_l1<WIDE_B, 4, false, WIDE_GRID / 148><<<WIDE_GRID, WIDE_B, 0, st>>>(g);
         count_launch(2);
         return cudaGetLastError();
       }

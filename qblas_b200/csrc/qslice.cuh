@@ -170,6 +170,66 @@ QB_HD void qs_square_step(qs_sq_cols &Q, uint32_t w0, uint32_t w1, uint32_t w2, 
   }
 }
 
+/* one product x * y of a dot product with BOTH factors sliced on the fly (no table): shx = ancx - e(x), shy = ancy - e(y), each
+ * clamped to QS_SHMAX.  With sh = 22 q + r the significand is shifted by r and the slice offset q is static per case:
+ * C_c += sum_{i + l + Q = c} X_i Y_l, Q = qx + qy = 0..5 (21, 15, 10, 6, 3, 1 DFMAs; nothing beyond).  The sign of the product is
+ * put into the Y slices (one XOR on the high word of each double). */
+QB_HD void qs_slices(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t r, double (&d)[QS_NS])
+{
+  const uint32_t s = 21u - r;
+  const uint32_t m3 = qs_top_word(w3);
+  const uint32_t v0 = w0 << s, v1 = fshl(w0, w1, s), v2 = fshl(w1, w2, s), v3 = fshl(w2, m3, s), v4 = fshl(m3, 0u, s);
+  d[0] = (double)fshr(v3, v4, 16); d[1] = (double)(fshr(v2, v3, 26) & QS_MK); d[2] = (double)((v2 >> 4) & QS_MK);
+  d[3] = (double)(fshr(v1, v2, 14) & QS_MK); d[4] = (double)(fshr(v0, v1, 24) & QS_MK); d[5] = (double)((v0 >> 2) & QS_MK);
+}
+QB_HD double qs_flip(double v, uint32_t signbit31)   /* v with its sign XORed by bit 31 of signbit31 */
+{
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(v) ^ (int)(signbit31 & 0x80000000u), __double2loint(v));
+#else
+  return (signbit31 & 0x80000000u) ? -v : v;
+#endif
+}
+QB_HD void qs_dot_step(qs_cols &C, uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t y0, uint32_t y1, uint32_t y2, uint32_t y3,
+                       uint32_t shx, uint32_t shy)
+{
+  const uint32_t qx = (shx * 2979u) >> 16, qy = (shy * 2979u) >> 16, Q = qx + qy;
+  if (Q >= (uint32_t)QS_NS) return;
+  double a[QS_NS], b[QS_NS];
+  qs_slices(x0, x1, x2, x3, shx - qx * 22u, a);
+  qs_slices(y0, y1, y2, y3, shy - qy * 22u, b);
+  const uint32_t sg = x3 ^ y3;
+  for (int l = 0; l < QS_NS; ++l) b[l] = qs_flip(b[l], sg);
+  if (Q == 0u) {
+    C.c0 = fma(a[0], b[0], C.c0);
+    C.c1 = fma(a[0], b[1], fma(a[1], b[0], C.c1));
+    C.c2 = fma(a[0], b[2], fma(a[1], b[1], fma(a[2], b[0], C.c2)));
+    C.c3 = fma(a[0], b[3], fma(a[1], b[2], fma(a[2], b[1], fma(a[3], b[0], C.c3))));
+    C.c4 = fma(a[0], b[4], fma(a[1], b[3], fma(a[2], b[2], fma(a[3], b[1], fma(a[4], b[0], C.c4)))));
+    C.c5 = fma(a[0], b[5], fma(a[1], b[4], fma(a[2], b[3], fma(a[3], b[2], fma(a[4], b[1], fma(a[5], b[0], C.c5))))));
+  } else if (Q == 1u) {
+    C.c1 = fma(a[0], b[0], C.c1);
+    C.c2 = fma(a[0], b[1], fma(a[1], b[0], C.c2));
+    C.c3 = fma(a[0], b[2], fma(a[1], b[1], fma(a[2], b[0], C.c3)));
+    C.c4 = fma(a[0], b[3], fma(a[1], b[2], fma(a[2], b[1], fma(a[3], b[0], C.c4))));
+    C.c5 = fma(a[0], b[4], fma(a[1], b[3], fma(a[2], b[2], fma(a[3], b[1], fma(a[4], b[0], C.c5)))));
+  } else if (Q == 2u) {
+    C.c2 = fma(a[0], b[0], C.c2);
+    C.c3 = fma(a[0], b[1], fma(a[1], b[0], C.c3));
+    C.c4 = fma(a[0], b[2], fma(a[1], b[1], fma(a[2], b[0], C.c4)));
+    C.c5 = fma(a[0], b[3], fma(a[1], b[2], fma(a[2], b[1], fma(a[3], b[0], C.c5))));
+  } else if (Q == 3u) {
+    C.c3 = fma(a[0], b[0], C.c3);
+    C.c4 = fma(a[0], b[1], fma(a[1], b[0], C.c4));
+    C.c5 = fma(a[0], b[2], fma(a[1], b[1], fma(a[2], b[0], C.c5)));
+  } else if (Q == 4u) {
+    C.c4 = fma(a[0], b[0], C.c4);
+    C.c5 = fma(a[0], b[1], fma(a[1], b[0], C.c5));
+  } else {
+    C.c5 = fma(a[0], b[0], C.c5);
+  }
+}
+
 /* the thread column: zeros in front of both copies (once), then the slices of the current x_j */
 QB_HD void qs_col_init(double *col, int stride)
 {

@@ -148,4 +148,43 @@ int qslice_sumsq(int64_t n, const q128 *x, int lanes, q128 *out)
   *out = qw_finish(v, 0);
   return (flags & QS_FALLBACK) ? 0 : 1;
 }
+
+/* the sliced dot product of two vectors (qs_dot_step) as k_dot_f64 runs it: thread t of `lanes` takes the pairs t, t + lanes, ... with
+ * its own anchors for x and y; returns 1 when the acceptance test passes, 0 when the call goes to the window kernel */
+int qslice_dot2(int64_t n, const q128 *x, const q128 *y, int lanes, q128 *out)
+{
+  qwide v = qw_zero();
+  uint32_t flags = 0;
+  int32_t ancsum = 0, dmax = QS_EXNONE;
+  for (int t = 0; t < lanes; ++t) {
+    qs_cols C = qs_cols_zero();
+    qs_row SX, SY; SX.anc = SY.anc = QS_ANCMIN; SX.dmax = SY.dmax = 0;
+    int32_t dm = QS_EXNONE;
+    uint64_t w[4] = {0, 0, 0, 0};
+    int steps = 0;
+    for (int64_t j = t; j < n; j += lanes) {
+      const uint32_t x0 = (uint32_t)x[j].lo, x1 = (uint32_t)(x[j].lo >> 32), x2 = (uint32_t)x[j].hi, x3 = (uint32_t)(x[j].hi >> 32);
+      const uint32_t y0 = (uint32_t)y[j].lo, y1 = (uint32_t)(y[j].lo >> 32), y2 = (uint32_t)y[j].hi, y3 = (uint32_t)(y[j].hi >> 32);
+      const uint32_t ex = (x3 >> 16) & 0x7fffu, ey = (y3 >> 16) & 0x7fffu;
+      const bool rx = (uint32_t)(ex - 1u) >= (uint32_t)SX.anc, ry = (uint32_t)(ey - 1u) >= (uint32_t)SY.anc;
+      uint32_t shx = (uint32_t)SX.anc - ex, shy = (uint32_t)SY.anc - ey;
+      shx = shx > QS_SHMAX ? QS_SHMAX : shx; shy = shy > QS_SHMAX ? QS_SHMAX : shy;
+      if (!rx && !ry) qs_dot_step(C, x0, x1, x2, x3, y0, y1, y2, y3, shx, shy);
+      else {   /* a zero / subnormal / Inf / NaN factor or a new largest one: anchors first (each moves the window), then the product */
+        if (rx) shx = qs_rare(C, SX, flags, ex, x0, x1, x2, x3, w, 1);
+        if (ry) shy = qs_rare(C, SY, flags, ey, y0, y1, y2, y3, w, 1);
+        if (shx < QS_SHMAX && shy < QS_SHMAX) qs_dot_step(C, x0, x1, x2, x3, y0, y1, y2, y3, shx, shy);
+      }
+      if (ex != 0 && ey != 0) { const int32_t d = (int32_t)ex + (int32_t)ey; dm = d > dm ? d : dm; }
+      if (++steps == QS_TILE) { qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1); C = qs_cols_zero(); steps = 0; }
+    }
+    qs_flush(C.c0, C.c1, C.c2, C.c3, C.c4, C.c5, w, 1);
+    qw_merge(v, qs_to_qwide(w, 1, SX.anc, SY.anc));
+    ancsum = SX.anc + SY.anc > ancsum ? SX.anc + SY.anc : ancsum;
+    dmax = dm > dmax ? dm : dmax;
+  }
+  *out = qw_finish(v, 0);
+  if (flags & QS_FALLBACK) return 0;
+  return dmax >= ancsum - QS_ACCEPT ? 1 : 0;
+}
 }

@@ -282,3 +282,51 @@ def test_sliced_gemv_random_shapes(fast3, oracle):
         if incy > 1:
             mask = np.ones(len(y0), dtype=bool); mask[::incy] = False
             assert quad.same_bits(got[mask], y0[mask]).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# qdot of two vectors: both factors sliced on the fly (k_dot_f64_tma)
+
+@pytest.mark.parametrize("kind,n", [("D113", 300000), ("D53", 1 << 20), ("Dexp", 400001), ("D113", 2000), ("D113", 5)])
+def test_sliced_dot_of_two_vectors(fast3, oracle, kind, n):
+    fast = fast3
+    rng = np.random.default_rng(n + 1)
+    x = quad.random_quads(rng, n, kind); y = quad.random_quads(rng, n, "D53" if kind == "D53" else "D113")
+    x[::13] = 0; y[::17] = 0
+    got = fast.dot(n, x, 1, y, 1)
+    assert quad.same_bits(got, fast.dot(n, x, 1, y, 1)).all()                 # deterministic
+    exact, ratio, _ = oracle.exact_dot_check("R", n, x, n, y, 1, np.array([[0, 0]], dtype=np.int64), got.reshape(1, 2))
+    assert ratio[0] <= 1.0
+    fast.set_fast_variant(1)
+    try:
+        ref = fast.dot(n, x, 1, y, 1)                                          # the window kernel
+    finally:
+        fast.set_fast_variant(3)
+    _, ratio_ref, _ = oracle.exact_dot_check("R", n, x, n, y, 1, np.array([[0, 0]], dtype=np.int64), ref.reshape(1, 2))
+    assert ratio[0] <= max(4.0 * ratio_ref[0], 4.0 / n)                        # as tight as the window accumulator up to its own rounding
+
+
+def test_sliced_dot_of_two_vectors_declines(fast3):
+    """an Inf / subnormal factor, or products that all lie far below (largest |x|) x (largest |y|): the window kernel's bits"""
+    fast = fast3
+    rng = np.random.default_rng(5)
+    n = 300000
+    x = quad.random_quads(rng, n); y = quad.random_quads(rng, n)
+    inf = np.array([0, 0x7FFF << 48], dtype=np.uint64); sub = np.array([77, 0], dtype=np.uint64)
+    cases = []
+    for special in (inf, sub):
+        a = x.copy(); a[1234] = special; cases.append((a, y))
+        b = y.copy(); b[4321] = special; cases.append((x, b))
+    # the largest x meets a zero y and vice versa, everything else 2^-40 smaller: no product near the anchor pair
+    a = x.copy(); b = y.copy()
+    a[:, 1] = (a[:, 1] & np.uint64(0x8000FFFFFFFFFFFF)) | (np.uint64(16383 - 40) << np.uint64(48)); b[:, 1] = (b[:, 1] & np.uint64(0x8000FFFFFFFFFFFF)) | (np.uint64(16383 - 40) << np.uint64(48))
+    a[7, 1] = np.uint64(16383 + 5) << np.uint64(48); b[7] = 0; b[9, 1] = np.uint64(16383 + 5) << np.uint64(48); a[9] = 0
+    cases.append((a, b))
+    for u, v in cases:
+        got = fast.dot(n, u, 1, v, 1)
+        fast.set_fast_variant(1)
+        try:
+            want = fast.dot(n, u, 1, v, 1)
+        finally:
+            fast.set_fast_variant(3)
+        assert quad.same_bits(got, want).all()

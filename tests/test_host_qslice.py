@@ -26,6 +26,8 @@ def qs(tmp_path_factory):
     lib.qslice_dot.restype = C.c_int
     lib.qslice_sumsq.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
     lib.qslice_sumsq.restype = C.c_int
+    lib.qslice_dot2.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.qslice_dot2.restype = C.c_int
     return lib
 
 
@@ -211,3 +213,58 @@ def test_sliced_dot_extreme_exponents_match_the_window_accumulator(qs):
         out = np.zeros((1, 2), dtype=np.uint64); bad = np.zeros(1, dtype=np.uint32)
         lib.qwide_dot(n, a.ctypes.data, 1, x.ctypes.data, 1, 4, 0, out.ctypes.data, bad.ctypes.data)
         assert (int(r[0]), int(r[1])) == (int(out[0][0]), int(out[0][1])), (ea, ex)
+
+
+def _dot2(lib, x, y, lanes):
+    x = np.ascontiguousarray(x); y = np.ascontiguousarray(y)
+    out = np.zeros((1, 2), dtype=np.uint64)
+    rc = lib.qslice_dot2(len(x), x.ctypes.data, y.ctypes.data, lanes, out.ctypes.data)
+    return rc, out[0]
+
+
+@pytest.mark.parametrize("kind", ["D113", "D53", "Dexp"])
+@pytest.mark.parametrize("lanes", [1, 5, 32])
+def test_sliced_dot_of_two_vectors_vs_exact(qs, kind, lanes):
+    """qdot with both factors sliced on the fly: accepted results inside the contract (and the exact sum rounded once when nothing
+    cancels badly); growing elements move both anchors"""
+    rng = np.random.default_rng(len(kind) * 7 + lanes)
+    n = 800
+    x = quad.random_quads(rng, n, kind); y = quad.random_quads(rng, n, "D113" if kind != "D53" else "D53")
+    rc, r = _dot2(qs, x, y, lanes)
+    tot, sab = _exact(x, y)
+    u = Fraction(1, 2 ** 113)
+    if rc == 1:
+        assert abs(_frac(r) - tot) <= n * u / (1 - n * u) * sab
+        assert abs(_frac(r) - tot) <= abs(tot) * u + n * sab / 2 ** 120
+    assert rc == 1 or kind == "Dexp"
+    # positive data: the exact sum rounded once
+    xp = x.copy(); yp = y.copy(); xp[:, 1] &= np.uint64((1 << 63) - 1); yp[:, 1] &= np.uint64((1 << 63) - 1)
+    rc, r = _dot2(qs, xp, yp, lanes)
+    if rc == 1 and kind != "Dexp":
+        tot, _ = _exact(xp, yp)
+        hi, lo = quad.from_fraction(tot)
+        assert (int(r[1]), int(r[0])) == (hi, lo)
+
+
+def test_sliced_dot_of_two_vectors_anchors_and_specials(qs):
+    rng = np.random.default_rng(77)
+    n = 300
+    x = quad.random_quads(rng, n); y = quad.random_quads(rng, n)
+    ex = (QBIAS - 2000 + np.cumsum(rng.integers(0, 25, n))).astype(np.uint64); ey = (QBIAS + 1500 - np.cumsum(rng.integers(0, 25, n))).astype(np.uint64)
+    x[:, 1] = (x[:, 1] & np.uint64(0x8000FFFFFFFFFFFF)) | (ex << np.uint64(48)); y[:, 1] = (y[:, 1] & np.uint64(0x8000FFFFFFFFFFFF)) | (ey << np.uint64(48))
+    for lanes in (1, 6):
+        rc, r = _dot2(qs, x, y, lanes)
+        tot, sab = _exact(x, y)
+        u = Fraction(1, 2 ** 113)
+        if rc == 1:
+            assert abs(_frac(r) - tot) <= n * u / (1 - n * u) * sab
+    x = quad.random_quads(rng, n); y = quad.random_quads(rng, n)
+    x[::5] = 0; y[::7] = 0
+    rc, r = _dot2(qs, x, y, 3)
+    assert rc == 1
+    tot, sab = _exact(x, y)
+    assert abs(_frac(r) - tot) <= abs(tot) / 2 ** 113 + n * sab / 2 ** 120
+    z = x.copy(); z[9, 1] = np.uint64(0x7fff) << np.uint64(48)
+    assert _dot2(qs, z, y, 3)[0] == 0 and _dot2(qs, y, z, 3)[0] == 0
+    z = x.copy(); z[9, 1] = np.uint64(0); z[9, 0] = np.uint64(5)
+    assert _dot2(qs, z, y, 3)[0] == 0
