@@ -21,6 +21,7 @@
  * generation of this path (rounded FMA chains, k_dot_fast_l1) is kept as `fast variant 0` for the
  * bench's side-by-side (qb_set_fast_variant).
  */
+#include <cstdlib>
 #include "qb_internal.h"
 #include "q128_chain.cuh"
 #include "qwide.cuh"
@@ -284,6 +285,95 @@ k_dot_wide_l1(DotArgs g)
     const q128 r = qw_finish(v, bad);
     *g.result = g.do_sqrt ? q_sqrt(r) : r;
     *g.ticket = 0u;                      /* ready for the next call (stream order) */
+  }
+}
+
+/* k_dot_wide_l1 for two contiguous vectors, fed by the copy engine: the kernel above waits on its own loads (long-scoreboard stalls
+ * 3.9 per issue, issue slots 49 % busy at 24 warps per SM, profiles/r2_dot_wide_ncu_full.txt); here tiles of B x U pairs arrive by
+ * cp.async.bulk into a two-stage ring and a tile is exactly one interleaved group of U branch-free accumulate steps per thread. */
+template <int B, int U, bool SAME, int MINB>
+__global__ void __launch_bounds__(B, MINB)
+k_dot_wide_tma(DotArgs g)
+{
+  constexpr int TE = B * U;
+  extern __shared__ __align__(128) unsigned char dw_sm[];
+  uint4 *tx = reinterpret_cast<uint4 *>(dw_sm);                      /* [2][TE] */
+  uint4 *ty = SAME ? tx : tx + 2 * TE;                               /* [2][TE] (x * x: the same tiles) */
+  uint32_t *scr = reinterpret_cast<uint32_t *>(tx + (SAME ? 2 : 4) * TE);   /* [U * QWA_COL_WORDS * B] */
+  uint64_t *full = reinterpret_cast<uint64_t *>(scr + U * QWA_COL_WORDS * B);
+  uint32_t *sh = scr;
+  __shared__ int is_last;
+  if (g.only_if != nullptr && *g.only_if == 0u) return;
+  const int tid = threadIdx.x;
+  qwacc acc = qwa_zero();
+  uint32_t bad = 0;
+#pragma unroll
+  for (int u = 0; u < U; ++u) qwa_col_init(scr + u * QWA_COL_WORDS * B + tid, B);
+  const int64_t nfull = g.n / TE;
+  const int64_t mine = nfull > blockIdx.x ? (nfull - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto issue = [&](int64_t i, int s) {
+    const int64_t off = (blockIdx.x + i * gridDim.x) * TE;
+    tc::mbar_expect_tx(&full[s], (SAME ? 1 : 2) * TE * 16);
+    tc::bulk_load_1d(tx + s * TE, g.x + off, TE * 16, &full[s]);
+    if (!SAME) tc::bulk_load_1d(ty + s * TE, g.y + off, TE * 16, &full[s]);
+  };
+  if (tid == 0) {
+    tc::mbar_init(&full[0], 1); tc::mbar_init(&full[1], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (mine > 0) issue(0, 0);
+    if (mine > 1) issue(1, 1);
+  }
+  auto ld = [](const uint4 &v) { q128 r; r.lo = ((uint64_t)v.y << 32) | v.x; r.hi = ((uint64_t)v.w << 32) | v.z; return r; };
+  for (int64_t i = 0; i < mine; ++i) {
+    const int s = (int)(i & 1);
+    tc::mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
+    q128 xv[U], yv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { xv[u] = ld(tx[s * TE + u * B + tid]); yv[u] = SAME ? xv[u] : ld(ty[s * TE + u * B + tid]); }
+    bool rare = false, rr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const qop a = qop_load_n(xv[u]);
+      rr[u] = qwa_fma(acc, a, SAME ? a : qop_load_n(yv[u]), scr + u * QWA_COL_WORDS * B + tid, B);
+      rare |= rr[u];
+    }
+    if (rare) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rr[u]) qwa_fma_rare(acc, xv[u], yv[u], bad);
+    }
+    __syncthreads();
+    if (tid == 0 && i + 2 < mine) issue(i + 2, s);
+  }
+  if (blockIdx.x == (unsigned)(nfull % gridDim.x)) {   /* the partial tile */
+    for (int64_t j = nfull * TE + tid; j < g.n; j += B) {
+      const q128 xv = ldg128_l1(g.x + j), yv = SAME ? xv : ldg128_l1(g.y + j);
+      if (qwa_fma(acc, qop_load_n(xv), qop_load_n(yv), scr + tid, B)) qwa_fma_rare(acc, xv, yv, bad);
+    }
+  }
+  __syncthreads();                       /* the scratch columns become the reduction records */
+  qwide v = qw_block_tree<B>(qwa_fold(acc), bad, sh);
+  uint32_t *rec = reinterpret_cast<uint32_t *>(g.work);
+  if (tid == 0) {
+    qw_store(rec + 8 * (int64_t)blockIdx.x, v, bad);
+    __threadfence();
+    is_last = atomicAdd(g.ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  v = qw_zero();
+  bad = 0;
+  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, bad));
+  __syncthreads();
+  v = qw_block_tree<B>(v, bad, sh);
+  if (tid == 0) {
+    const q128 r = qw_finish(v, bad);
+    *g.result = g.do_sqrt ? q_sqrt(r) : r;
+    *g.ticket = 0u;
   }
 }
 
@@ -698,6 +788,20 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
         return cudaGetLastError();
       }
       g.only_if = nullptr;
+      /* contiguous vectors, large enough for tiles: the copy-engine-fed form of the window kernel (U = 4 pairs per thread and tile,
+       * 3 CTAs per SM: 56 KB of tiles and scratch columns each; measured against U = 2 x 6 CTAs and U = 3 x 4 CTAs) */
+      if (g.incx == 1 && g.incy == 1 && ((reinterpret_cast<uintptr_t>(g.x) | reinterpret_cast<uintptr_t>(g.y)) & 15u) == 0 && g.n >= (1 << 19)) {
+        constexpr int U = 4, CT = 3;
+        auto go = [&](auto kern, int smem) -> cudaError_t {
+          cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+          if (ae != cudaSuccess) return ae;
+          kern<<<148 * CT, WIDE_B, smem, st>>>(g);
+          count_launch(1);
+          return cudaGetLastError();
+        };
+        if (same) return go(k_dot_wide_tma<WIDE_B, U, true, CT>, 2 * WIDE_B * U * 16 + U * QWA_COL_WORDS * WIDE_B * 4 + 64);
+        return go(k_dot_wide_tma<WIDE_B, U, false, CT>, 4 * WIDE_B * U * 16 + U * QWA_COL_WORDS * WIDE_B * 4 + 64);
+      }
       int grid = WIDE_GRID;
       const int64_t need = (g.n + WIDE_B - 1) / WIDE_B;
       if (need < grid) grid = (int)need;

@@ -185,3 +185,60 @@ def test_fast_variant_zero_still_available(qb, oracle):
     tot = sum(a * b for a, b in zip(fx, fy)); sab = sum(abs(a * b) for a, b in zip(fx, fy))
     u = Fraction(1, 2 ** 113)
     assert abs(_frac(r0) - tot) <= n * u * sab and abs(_frac(r1) - tot) <= abs(tot) * u + n * sab / 2 ** 133
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the copy-engine-fed window kernel (k_dot_wide_tma): contiguous vectors from 2^19 elements
+
+@pytest.mark.parametrize("kind,n", [("D113", (1 << 19) + 3), ("Dexp", 700001), ("D53", 1 << 21), ("D113", 2 * 512 * 444 + 511)])
+def test_fast_dot_tiles_against_the_long_accumulator(fast, oracle, kind, n):
+    """tiles of 512 pairs by cp.async.bulk, the ragged tail by plain loads: the exact sum rounded once (up to the window truncation,
+    2^-133 of sum|x||y| per term), deterministic, and x . x (one set of tiles) as well"""
+    rng = np.random.default_rng(n)
+    x = quad.random_quads(rng, n, kind); y = quad.random_quads(rng, n, "D53" if kind == "D53" else "D113")
+    x[::13] = 0; y[5::17] = 0
+    none = np.array([[0, 0]], dtype=np.int64)
+    got = fast.dot(n, x, 1, y, 1)
+    assert quad.same_bits(got, fast.dot(n, x, 1, y, 1)).all()
+    exact, ratio, _ = oracle.exact_dot_check("R", n, x, n, y, 1, none, got.reshape(1, 2))
+    assert ratio[0] <= 1.0 / n + 2.0 ** -20 + 1e-12
+    if kind != "Dexp":
+        assert quad.same_bits(got, exact[0]).all()
+    got2 = fast.dot(n, x, 1, x, 1)
+    exact2, ratio2, _ = oracle.exact_dot_check("R", n, x, n, x, 1, none, got2.reshape(1, 2))
+    assert ratio2[0] <= 1.0 / n + 2.0 ** -20 + 1e-12
+    if kind != "Dexp":
+        assert quad.same_bits(got2, exact2[0]).all()
+    # device vectors that start 16 bytes into their allocations
+    dx, dy = to_dev(x), to_dev(y)
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    fast.dot(n - 1, dx[1:], 1, dy[1:], 1, out)
+    got3 = to_host(out.view(1, 2))
+    _, ratio3, _ = oracle.exact_dot_check("R", n - 1, x[1:], n - 1, y[1:], 1, none, got3.reshape(1, 2))
+    assert ratio3[0] <= 1.0 / n + 2.0 ** -20 + 1e-12
+
+
+def test_fast_dot_tiles_specials_and_cancellation(fast):
+    rng = np.random.default_rng(3)
+    n = (1 << 20) + 77
+    x = quad.random_quads(rng, n); y = quad.random_quads(rng, n)
+    inf = np.array([0, 0x7FFF << 48], dtype=np.uint64); ninf = np.array([0, 0xFFFF << 48], dtype=np.uint64)
+    nan = np.array([1, 0x7FFF << 48], dtype=np.uint64); one = quad.from_double(np.array([1.0]))[0]
+    xs, ys = x.copy(), y.copy(); xs[777777] = inf; ys[777777] = one
+    assert quad.same_bits(fast.dot(n, xs, 1, ys, 1), inf).all()
+    xs[400] = ninf; ys[400] = one
+    assert quad.is_nan(fast.dot(n, xs, 1, ys, 1).reshape(1, 2)).all()
+    xs, ys = x.copy(), y.copy(); xs[n - 2] = nan                                   # in the ragged tail
+    assert quad.is_nan(fast.dot(n, xs, 1, ys, 1).reshape(1, 2)).all()
+    xs, ys = x.copy(), y.copy(); xs[12] = inf; ys[12] = 0
+    assert quad.is_nan(fast.dot(n, xs, 1, ys, 1).reshape(1, 2)).all()
+    assert ((int(fast.nrm2(n, np.concatenate([x[:5], inf[None, :], x[6:]]), 1)[1]) >> 48) & 0x7fff) == 0x7fff
+    # subnormals and a product far above everything seen so far (the out-of-line exact path) inside a tile
+    xs = np.zeros((n, 2), dtype=np.uint64); ys = quad.from_double(np.ones(n))
+    xs[:] = quad.from_double(np.array([2.0 ** -60]))[0]
+    xs[1000] = quad.from_double(np.array([1e20]))[0]; xs[900000] = quad.from_double(np.array([-1e20]))[0]
+    xs[5] = (np.uint64(99), np.uint64(0))                                           # 99 * 2^-16494
+    tot = Fraction(n - 3, 2 ** 60) + Fraction(99, 2 ** 16494)
+    assert quad.same_bits(fast.dot(n, xs, 1, ys, 1), _round(tot)).all()
+    xv = np.zeros(n); xv[[3, 500000, n - 1]] = [1e20, 1.0, -1e20]
+    assert _frac(fast.dot(n, quad.from_double(xv), 1, quad.from_double(np.ones(n)), 1)) == 1
