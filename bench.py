@@ -223,13 +223,24 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
             qb.set_mode(qb.MODE_REFERENCE)
             qb.gemm("R", 256, 256, 256, 1.0, Ar, Sr, Br, Sr, 0.0, Cr, Sr)
             ms = _time_events(lambda: qb.gemm("R", Sr, Sr, Sr, 1.0, Ar, Sr, Br, Sr, 0.0, Cr, Sr), 1)
+            qb.set_ref_gemm_kernel(0)                      # the first version of the kernel, same bits (side by side)
+            try:
+                qb.gemm("R", 256, 256, 256, 1.0, Ar, Sr, Br, Sr, 0.0, Cr, Sr)
+                ms_old = _time_events(lambda: qb.gemm("R", Sr, Sr, Sr, 1.0, Ar, Sr, Br, Sr, 0.0, Cr, Sr), 1)
+            finally:
+                qb.set_ref_gemm_kernel(1)
             pk = _int_issue_peak(qb, torch, dev)
             gf = 2.0 * Sr ** 3 / ms / 1e6
+            sm_ghz = 1.965
+            clk = ms * 1e-3 * sm_ghz * 1e9 * 148 * 4 / (Sr ** 3 / 32.0)     # dispatch clocks per warp-qFMA and SM sub-partition at the boost clock
             extra["qgemm_reference_order"] = {
-                "workload": f"quadblas_qgemm row-major {Sr}^3 alpha=1 beta=0, reference-order mode (bit exact vs the reference, kc=126), integer-limb kernel k_gemm",
+                "workload": f"quadblas_qgemm row-major {Sr}^3 alpha=1 beta=0, reference-order mode (bit exact vs the reference, kc=126), integer-limb kernel k_gemm_nb (branch-free step, staged decoded operands)",
                 "ms": ms, "gflops": gf,
+                "first_version_k_gemm": {"ms": ms_old, "gflops": 2.0 * Sr ** 3 / ms_old / 1e6},
+                "clk_per_warp_qfma_per_subpartition": clk,
+                "clk_model": "sum of dispatch clocks over the SASS of the hot block (tools/sass_cost.py, calibrated by tools/exp/mb_pipes.cu): 261 for k_gemm_nb, 273 for k_gemm; the 16 IMAD.WIDE of the 113x113-bit product alone are 69",
                 "roofline": {"bound": "int-issue (IMAD/ALU pipes)", "achieved": gf, "peak": pk, "unit": "GFLOP/s (binary128)", "frac": gf / pk,
-                             "peak_source": "live register-resident qFMA microbenchmark (same primitive, no memory); pipe utilisation from ncu is in profiles/"}}
+                             "peak_source": "live register-resident qFMA microbenchmark (first-version primitive, no memory); pipe utilisation from ncu is in profiles/"}}
             qb.set_mode(mode)
             del Ar, Br, Cr
         mv = 32768 if S >= 8192 else 4096

@@ -104,6 +104,11 @@ int qb_get_tensor_path(void);
  * Ignored in QB_MODE_REFERENCE. */
 void qb_set_fast_variant(int v);
 int qb_get_fast_variant(void);
+/* Kernel of the reference-order qgemm (QuadBLAS::gemm, level3.hpp:215-336; same bits either way): 1 (default) = k_gemm_nb, staged
+ * decoded operands and a branch-free step whose rare declined steps are redone out of line; 0 = k_gemm, the first version (side-by-side
+ * in bench.py).  Also QBLAS_GEMM_KERNEL=0|1 in the environment when the library is loaded. */
+void qb_set_ref_gemm_kernel(int v);
+int qb_get_ref_gemm_kernel(void);
 /* Pipelined all-host qgemm with beta = +-0 and contiguous rows of C: 1 (default) = C_in travels as one class byte per element
  * (finite >= +0 / finite with the sign bit / Inf-or-NaN) classified by host threads, and a kernel writes the stand-in +1 / -1 / NaN
  * on the device — beta * stand-in has exactly the bits of the reference's beta * C (level3.hpp:107), and 15/16 of the upload of C

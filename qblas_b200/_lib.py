@@ -94,6 +94,8 @@ def lib():
         "qb_crt_pass_rows": (ci, [i64, i64, ci, C.POINTER(i64), ci]),
         "qb_set_fast_variant": (None, [ci]),
         "qb_get_fast_variant": (ci, []),
+        "qb_set_ref_gemm_kernel": (None, [ci]),
+        "qb_get_ref_gemm_kernel": (ci, []),
         "qb_gemv_last_declined": (C.c_int64, []),
         "qb_set_beta0_classes": (None, [ci]),
         "qb_get_beta0_classes": (ci, []),

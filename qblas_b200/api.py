@@ -449,6 +449,15 @@ def get_fast_variant():
     return lib().qb_get_fast_variant()
 
 
+def set_ref_gemm_kernel(v):
+    """Kernel of the reference-order qgemm (same bits): 1 (default) = k_gemm_nb (branch-free step), 0 = k_gemm (first version)."""
+    lib().qb_set_ref_gemm_kernel(int(v))
+
+
+def get_ref_gemm_kernel():
+    return lib().qb_get_ref_gemm_kernel()
+
+
 def set_beta0_classes(v):
     """Pipelined all-host qgemm with beta = 0: 1 (default) = C_in goes up as one class byte per element, 0 = as its 16 bytes."""
     lib().qb_set_beta0_classes(int(v))

@@ -513,6 +513,289 @@ QB_HD void qacc_fma_sc(qacc &S, const qop &A, const qop &B, const qscratch &scr,
   qacc_fma_t<true>(S, A, B, scr, tzsum);
 }
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * The branch-free step of the reference-order qgemm (k_gemm_nb, qb_level3.cu).
+ *
+ * tools/exp/mb_pipes.cu measured what a warp instruction costs one SM sub-partition of sm_100a in dispatch clocks — IMAD.WIDE 4-5,
+ * IMAD / LOP3 / SHF / LDS / STS 2, IADD3 / ISETP / SEL 1 — and the sum of these over the hot path of qacc_fma_t reproduces the
+ * measured 277 clocks per qFMA: the kernel is bound by that sum, not by one pipe.  This step is the same arithmetic with fewer and
+ * cheaper instructions:
+ *   - the operands arrive STAGED (qstaged: implicit bit set, and one meta word e | sign << 16 | zero << 18 | abnormal << 20 |
+ *     tz << 23 made once per element when the tile is staged): ONE add of the two meta words gives the exponent sum, the sign of
+ *     the product, tz(a) + tz(b) and the operand classes at once;
+ *   - the product is added or subtracted in two's complement by predicated carry chains (IADD3, 1 clock each) and a predicated
+ *     negation replaces the XOR masks, the end-around increment and the conditional complement;
+ *   - normalisation is one 5-word select (the sum has its leading one in word 4 or in word 3) and ONE funnel-shift pass;
+ *   - no branch and no call: a step that needs the generic routine (cancellation of more than 13 bits, a product far above the
+ *     accumulator, an abnormal operand or result) leaves S untouched and returns 1; the caller redoes those steps out of line after
+ *     the independent steps of one k index, so the hot loop is one basic block.
+ * A zero operand is not abnormal: the product is an exact zero, tz = 255 keeps the sticky bit clear, and S comes out unchanged
+ * (a zero accumulator is always +0 here — -0 is kept in the packed form — and (+0) + (+-0) = +0).
+ * Same bits as q_fma for every step that returns 0 (tests/host/q128_host_test.cpp). */
+struct qacc2 {
+  uint32_t m0, m1, m2, m3;   /* normal: mantissa << 15; e in [1, 0x7ffe].  +0: all zero, e = 0.  Anything else: e = QACC2_PACKED, m = the packed words */
+  int32_t e;
+  uint32_t sw;               /* sign in bit 16 (the other bits are don't-care) */
+};
+struct qstaged { uint32_t m0, m1, m2, m3, meta; };
+
+constexpr uint32_t QM_SIGN = 1u << 16, QM_ZERO = 1u << 18, QM_ABN = 1u << 20, QM_FLAGS = 0xfu << 18;
+constexpr int QM_TZ = 23;
+constexpr int32_t QACC2_PACKED = -0x10000;   /* so far below every exponent sum that the shift test of the step declines it */
+struct qnbctx {              /* per-thread constants of the step */
+  uint32_t *col;             /* scratch column (12 words at `stride`, words 6..11 zero) */
+  uint32_t stride;
+  uint32_t zero;             /* 0 that the compiler cannot see through (keeps the negation on IADD3.X with an inverted operand) */
+};
+
+QB_HD qstaged qstage(q128 v)
+{
+  const qop o = qop_load(v);
+  qstaged r;
+  r.m0 = o.m0; r.m1 = o.m1; r.m2 = o.m2; r.m3 = o.m3;
+  r.meta = (uint32_t)o.e | (o.s << 16);
+  if ((uint32_t)o.e - 1u < 0x7ffeu) r.meta |= qop_tz(o) << QM_TZ;
+  else if (o.e == 0 && (o.m0 | o.m1 | o.m2 | o.m3) == 0u) r.meta |= QM_ZERO | (255u << QM_TZ);
+  else r.meta |= QM_ABN;
+  return r;
+}
+QB_HD q128 qstaged_pack(const qstaged &a)
+{
+  q128 r;
+  r.lo = ((uint64_t)a.m1 << 32) | a.m0;
+  const uint32_t h = ((a.meta & QM_SIGN) << 15) | ((a.meta & 0x7fffu) << 16) | (a.m3 & 0xffffu);
+  r.hi = ((uint64_t)h << 32) | a.m2;
+  return r;
+}
+QB_HD qacc2 qacc2_zero()
+{
+  qacc2 z;
+  z.m0 = z.m1 = z.m2 = z.m3 = 0; z.e = 0; z.sw = 0;
+  return z;
+}
+QB_HD qacc2 qacc2_from(q128 a)
+{
+  qacc2 r;
+  const uint32_t h = (uint32_t)(a.hi >> 32);
+  const uint32_t ef = (h >> 16) & 0x7fff;
+  r.sw = h >> 15;                          /* bit 31 -> bit 16 */
+  if (ef - 1u < 0x7ffeu) {
+    const uint32_t w0 = (uint32_t)a.lo, w1 = (uint32_t)(a.lo >> 32), w2 = (uint32_t)a.hi, w3 = (h & 0xffffu) | 0x10000u;
+    r.m3 = (w3 << 15) | (w2 >> 17);
+    r.m2 = (w2 << 15) | (w1 >> 17);
+    r.m1 = (w1 << 15) | (w0 >> 17);
+    r.m0 = w0 << 15;
+    r.e = (int32_t)ef;
+  } else if ((a.hi | a.lo) == 0) {
+    r.m0 = r.m1 = r.m2 = r.m3 = 0;
+    r.e = 0;
+  } else {
+    r.m0 = (uint32_t)a.lo; r.m1 = (uint32_t)(a.lo >> 32); r.m2 = (uint32_t)a.hi; r.m3 = h;
+    r.e = QACC2_PACKED;
+  }
+  return r;
+}
+QB_HD q128 qacc2_pack(const qacc2 &a)
+{
+  q128 r;
+  if (a.e > 0) {
+    const uint32_t w0 = (a.m0 >> 15) | (a.m1 << 17);
+    const uint32_t w1 = (a.m1 >> 15) | (a.m2 << 17);
+    const uint32_t w2 = (a.m2 >> 15) | (a.m3 << 17);
+    const uint32_t w3 = ((a.m3 >> 15) & 0xffffu) | ((uint32_t)a.e << 16) | ((a.sw & QM_SIGN) << 15);
+    r.lo = ((uint64_t)w1 << 32) | w0;
+    r.hi = ((uint64_t)w3 << 32) | w2;
+  } else if (a.e == 0) {
+    r.lo = 0;
+    r.hi = 0;
+  } else {
+    r.lo = ((uint64_t)a.m1 << 32) | a.m0;
+    r.hi = ((uint64_t)a.m3 << 32) | a.m2;
+  }
+  return r;
+}
+
+/* (g0..g4) = (s0..s3, 0) +- (f0..f4) in two's complement (minus iff subw != 0); bo = 0xffffffff iff the difference is negative */
+QB_HD void addsub5(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, uint32_t f4,
+                   uint32_t subw, uint32_t &g0, uint32_t &g1, uint32_t &g2, uint32_t &g3, uint32_t &g4, uint32_t &bo)
+{
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %15, 0;\n\t"
+      "@!p add.cc.u32 %0, %6, %10;\n\t"
+      "@!p addc.cc.u32 %1, %7, %11;\n\t"
+      "@!p addc.cc.u32 %2, %8, %12;\n\t"
+      "@!p addc.cc.u32 %3, %9, %13;\n\t"
+      "@!p addc.u32 %4, %14, 0;\n\t"
+      "@!p mov.u32 %5, 0;\n\t"
+      "@p sub.cc.u32 %0, %6, %10;\n\t"
+      "@p subc.cc.u32 %1, %7, %11;\n\t"
+      "@p subc.cc.u32 %2, %8, %12;\n\t"
+      "@p subc.cc.u32 %3, %9, %13;\n\t"
+      "@p subc.cc.u32 %4, 0, %14;\n\t"
+      "@p subc.u32 %5, 0, 0;\n\t"
+      "}"
+      : "=&r"(g0), "=&r"(g1), "=&r"(g2), "=&r"(g3), "=&r"(g4), "=&r"(bo)
+      : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(f0), "r"(f1), "r"(f2), "r"(f3), "r"(f4), "r"(subw));
+#else
+  const uint32_t s[5] = {s0, s1, s2, s3, 0u}, f[5] = {f0, f1, f2, f3, f4};
+  uint32_t g[5];
+  if (subw == 0u) {
+    uint64_t c = 0;
+    for (int i = 0; i < 5; ++i) { c += (uint64_t)s[i] + f[i]; g[i] = (uint32_t)c; c >>= 32; }
+    bo = 0u;
+  } else {
+    int64_t c = 0;
+    for (int i = 0; i < 5; ++i) { c += (int64_t)s[i] - (int64_t)f[i]; g[i] = (uint32_t)c; c >>= 32; }
+    bo = c < 0 ? 0xffffffffu : 0u;
+  }
+  g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3]; g4 = g[4];
+#endif
+}
+/* (g0..g4) = -(g0..g4) iff bo != 0 (z = 0 in a register) */
+QB_HD void condneg5(uint32_t &g0, uint32_t &g1, uint32_t &g2, uint32_t &g3, uint32_t &g4, uint32_t bo, uint32_t z)
+{
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %5, 0;\n\t"
+      "@p sub.cc.u32 %0, %6, %0;\n\t"
+      "@p subc.cc.u32 %1, %6, %1;\n\t"
+      "@p subc.cc.u32 %2, %6, %2;\n\t"
+      "@p subc.cc.u32 %3, %6, %3;\n\t"
+      "@p subc.u32 %4, %6, %4;\n\t"
+      "}"
+      : "+r"(g0), "+r"(g1), "+r"(g2), "+r"(g3), "+r"(g4)
+      : "r"(bo), "r"(z));
+#else
+  (void)z;
+  if (bo) {
+    uint32_t g[5] = {g0, g1, g2, g3, g4};
+    int64_t c = 0;
+    for (int i = 0; i < 5; ++i) { c -= (int64_t)g[i]; g[i] = (uint32_t)c; c >>= 32; }
+    g0 = g[0]; g1 = g[1]; g2 = g[2]; g3 = g[3]; g4 = g[4];
+  }
+#endif
+}
+/* the leading one of (g4..g0) is in g4 or, if g4 = 0, in g3: move it to w4 (predicated moves: the copies may go to either pipe) */
+QB_HD void lead5(uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3, uint32_t g4, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
+                 uint32_t &w4)
+{
+#if defined(__CUDA_ARCH__)
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.eq.u32 p, %9, 0;\n\t"
+      "mov.u32 %0, %5;\n\t" "mov.u32 %1, %6;\n\t" "mov.u32 %2, %7;\n\t" "mov.u32 %3, %8;\n\t" "mov.u32 %4, %9;\n\t"
+      "@p mov.u32 %4, %8;\n\t" "@p mov.u32 %3, %7;\n\t" "@p mov.u32 %2, %6;\n\t" "@p mov.u32 %1, %5;\n\t" "@p mov.u32 %0, 0;\n\t"
+      "}"
+      : "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3), "=&r"(w4)
+      : "r"(g0), "r"(g1), "r"(g2), "r"(g3), "r"(g4));
+#else
+  const bool top = (g4 != 0u);
+  w4 = top ? g4 : g3; w3 = top ? g3 : g2; w2 = top ? g2 : g1; w1 = top ? g1 : g0; w0 = top ? g0 : 0u;
+#endif
+}
+
+/* The last stage of the step: the rounding increment, the carry into the exponent and the new sign are written into S by
+ * PREDICATED instructions, so a declined step leaves S untouched without a select per word.  Declined (returns true) when
+ *   sh_raw < 67 | lz > 45 | en outside [1, 0x7ffd] (one short of the largest exponent: the carry of the rounding is not known yet) |
+ *   an abnormal operand — unless S = +0 meets an exact zero product (fl: a zero operand and no abnormal one), which leaves S = +0. */
+QB_HD bool round_commit(qacc2 &S, uint32_t n0, uint32_t n1, uint32_t n2, uint32_t n3, uint32_t rc, int32_t en, uint32_t wsum, uint32_t subw,
+                        uint32_t bo, int32_t sh_raw, uint32_t lz, uint32_t fl)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t ret;
+  asm("{\n\t.reg .pred p, z;\n\t.reg .u32 t, t3, c;\n\t"
+      "setp.eq.s32 z, %4, 0;\n\t"                          /* S = +0 ... */
+      "setp.lt.and.u32 z, %17, 0xfffff, z;\n\t"                /* ... and (fl - 1) < ABN - 1 */
+      "setp.lt.s32 p, %14, 67;\n\t"
+      "setp.gt.or.u32 p, %15, 45, p;\n\t"
+      "setp.ge.or.u32 p, %16, 0x7ffd, p;\n\t"              /* en - 1 */
+      "setp.ge.or.u32 p, %18, 0x100000, p;\n\t"                 /* fl >= ABN */
+      "@!p add.cc.u32 t, %7, %11;\n\t"
+      "@!p addc.cc.u32 %1, %8, 0;\n\t"
+      "@!p addc.cc.u32 %2, %9, 0;\n\t"
+      "@!p addc.cc.u32 t3, %10, 0;\n\t"
+      "@!p addc.u32 c, 0, 0;\n\t"
+      "@!p and.b32 %0, t, 0xffff8000;\n\t"
+      "@!p mad.lo.u32 %3, c, 0x80000000, t3;\n\t"          /* a mantissa that rounded up to 2^113 left 0 */
+      "@!p add.s32 %4, %12, c;\n\t"
+      "@!p lop3.b32 %5, %13, %19, %20, 0xb4;\n\t"          /* wsum ^ (subw & ~bo): sign(S) unless the magnitudes swapped */
+      "and.pred p, p, !z;\n\t"
+      "selp.u32 %6, 1, 0, p;\n\t"
+      "}"
+      : "+r"(S.m0), "+r"(S.m1), "+r"(S.m2), "+r"(S.m3), "+r"(S.e), "+r"(S.sw), "=r"(ret)
+      : "r"(n0), "r"(n1), "r"(n2), "r"(n3), "r"(rc), "r"(en), "r"(wsum), "r"(sh_raw), "r"(lz), "r"((uint32_t)en - 1u), "r"(fl - 1u),
+        "r"(fl), "r"(subw), "r"(bo));
+  static_assert(QM_ABN == 0x100000u, "the literals of the asm block");
+  return ret != 0u;
+#else
+  const bool zz = (S.e == 0) && (fl - 1u < QM_ABN - 1u);
+  const bool bad = (sh_raw < 67) || (lz > 45u) || ((uint32_t)en - 1u >= 0x7ffdu) || (fl >= QM_ABN);
+  if (!bad) {
+    const uint32_t rco = inc4c(n0, n1, n2, n3, rc);
+    S.m0 = n0 & 0xffff8000u; S.m1 = n1; S.m2 = n2; S.m3 = n3 + (rco << 31); S.e = en + (int32_t)rco; S.sw = wsum ^ (subw & ~bo);
+  }
+  return bad && !zz;
+#endif
+}
+
+/* S <- RNE(A*B + S) for staged operands (wsum = A.meta + B.meta); returns false and updates S, or returns true and leaves S as it was */
+QB_HD bool qacc_fma_nb(qacc2 &S, const uint32_t a0, const uint32_t a1, const uint32_t a2, const uint32_t a3, const uint32_t b0,
+                       const uint32_t b1, const uint32_t b2, const uint32_t b3, const uint32_t wsum, const qnbctx &cx)
+{
+  uint32_t p[8];
+  mul4x4(a0, a1, a2, a3, b0, b1, b2, b3, p);
+
+  const int32_t esum = (int32_t)(wsum & 0xffffu);
+  const bool s_zero = (S.e == 0);
+  int32_t sh = S.e - esum + (QBIAS + 97);     /* es - ep + 97: P >> sh puts the product into the frame */
+  sh = s_zero ? 97 : sh;
+  const int32_t sh_raw = sh;                  /* < 67: product more than 2^30 above S, or S in the packed form */
+  sh = sh > 255 ? 255 : sh;
+  sh = sh < 67 ? 67 : sh;
+  /* whole words of the shift through the scratch column (words 6..11 are zero), the bit part by funnel shifts (sh mod 32) */
+  uint32_t *c = cx.col;
+  const uint32_t st = cx.stride;
+  c[0] = p[2]; c[st] = p[3]; c[2 * st] = p[4]; c[3 * st] = p[5]; c[4 * st] = p[6]; c[5 * st] = p[7];
+  const uint32_t *q = c + (((uint32_t)sh >> 5) - 2u) * st;
+  const uint32_t t0 = q[0], t1 = q[st], t2 = q[2 * st], t3 = q[3 * st], t4 = q[4 * st], t5 = q[5 * st];
+  const uint32_t jam = ((wsum >> QM_TZ) < (uint32_t)sh) ? 1u : 0u;   /* bits of P below the frame: tz(a b) = tz(a) + tz(b) */
+  const uint32_t r = (uint32_t)sh;
+  const uint32_t f0 = fshr(t0, t1, r) | jam, f1 = fshr(t1, t2, r), f2 = fshr(t2, t3, r), f3 = fshr(t3, t4, r), f4 = fshr(t4, t5, r);
+
+  /* S +- P, magnitude and sign */
+  uint32_t subw = (S.sw ^ wsum) & QM_SIGN;
+  subw = s_zero ? 0u : subw;
+  uint32_t g0, g1, g2, g3, g4, bo;
+  addsub5(S.m0, S.m1, S.m2, S.m3, f0, f1, f2, f3, f4, subw, g0, g1, g2, g3, g4, bo);
+  condneg5(g0, g1, g2, g3, g4, bo, cx.zero);
+
+  /* normalise: the leading one is in word 4 or, after a cancellation of up to 13 bits, in word 3 */
+  const bool top = (g4 != 0u);
+  uint32_t w0, w1, w2, w3, w4;
+  lead5(g0, g1, g2, g3, g4, w0, w1, w2, w3, w4);
+  const uint32_t lzq = (uint32_t)clz32(w4);
+  const uint32_t lz = lzq + (top ? 0u : 32u);            /* > 45: more than 13 bits cancelled */
+  const uint32_t n3 = fshl(w3, w4, lzq), n2 = fshl(w2, w3, lzq), n1 = fshl(w1, w2, lzq);
+  uint32_t n0 = fshl(w0, w1, lzq);
+  const uint32_t rest = w0 << (lzq & 31u);
+  const int32_t es = s_zero ? esum - QBIAS : S.e;
+  const int32_t en = es + 32 - (int32_t)lz;              /* before the carry of the rounding */
+  const uint32_t rc = 0x3fffu + ((n0 >> 15) & 1u);       /* round to nearest even at bit 15 of n0 */
+  n0 |= (rest < 1u ? rest : 1u);
+  const uint32_t fl = wsum & QM_FLAGS;
+  return round_commit(S, n0, n1, n2, n3, rc, en, wsum, subw, bo, sh_raw, lz, fl);
+}
+
+/* test wrapper: *bad = 1 means "not handled" and the return value is c itself */
+QB_HD q128 q_fma_fast_nb(q128 a, q128 b, q128 c, uint32_t *col, uint32_t stride, uint32_t *bad)
+{
+  qacc2 s = qacc2_from(c);
+  const qstaged A = qstage(a), B = qstage(b);
+  qnbctx cx; cx.col = col; cx.stride = stride; cx.zero = 0u;
+  *bad = qacc_fma_nb(s, A.m0, A.m1, A.m2, A.m3, B.m0, B.m1, B.m2, B.m3, A.meta + B.meta, cx) ? 1u : 0u;
+  return qacc2_pack(s);
+}
+
 /* packed convenience wrappers (tests, epilogues) */
 QB_HD q128 q_fma_fast(q128 a, q128 b, q128 c)
 {

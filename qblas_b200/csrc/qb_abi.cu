@@ -55,6 +55,8 @@ static std::atomic<int> g_beta0_classes{1};   /* qb_set_beta0_classes: the pipel
 static std::atomic<int> g_fastvar{2}; /* fast-mode level-1/2 accumulate: 2 = sliced FP64 accumulate where it applies (large row-major qgemv), window
                                          accumulator elsewhere; 1 = window accumulator everywhere; 0 = rounded-FMA chains; 3 = 2 without the size thresholds (tests) */
 int fast_variant() { return g_fastvar.load(); }
+static std::atomic<int> g_gemm_kernel{1}; /* reference-order qgemm: 1 = k_gemm_nb, 0 = k_gemm (qb_set_ref_gemm_kernel / QBLAS_GEMM_KERNEL) */
+int ref_gemm_kernel() { return g_gemm_kernel.load(); }
 static std::atomic<int> g_threads{0}; /* 0 = not set -> OMP_NUM_THREADS, then hardware concurrency (omp_get_max_threads) */
 
 /* Environment, read once when the library is loaded, so that an UNMODIFIED caller of the reference API can choose the
@@ -77,6 +79,7 @@ struct EnvInit {
       if (!strcasecmp(v, "fast") || !strcmp(v, "1")) g_mode.store(QB_MODE_FAST);
       else if (!strcasecmp(v, "reference") || !strcasecmp(v, "ref") || !strcmp(v, "0")) g_mode.store(QB_MODE_REFERENCE);
     }
+    if (const char *v = getenv("QBLAS_GEMM_KERNEL")) g_gemm_kernel.store(v[0] == '0' ? 0 : 1);
     if (const char *v = getenv("QUADBLAS_KC")) { const long kc = strtol(v, nullptr, 10); if (kc > 0 && kc < (1 << 30)) g_kc.store((int)kc); }
   }
 };
@@ -541,6 +544,8 @@ void qb_set_tensor_path(int v) { g_tensor.store(v < 0 ? 0 : (v > 2 ? 2 : v)); }
 int qb_get_tensor_path(void) { return g_tensor.load(); }
 void qb_set_fast_variant(int v) { g_fastvar.store(v <= 0 ? 0 : (v >= 3 ? 3 : v)); }
 int qb_get_fast_variant(void) { return g_fastvar.load(); }
+void qb_set_ref_gemm_kernel(int v) { g_gemm_kernel.store(v != 0 ? 1 : 0); }
+int qb_get_ref_gemm_kernel(void) { return g_gemm_kernel.load(); }
 void qb_set_beta0_classes(int v) { g_beta0_classes.store(v ? 1 : 0); }
 int qb_get_beta0_classes(void) { return g_beta0_classes.load(); }
 void qb_set_gemm_pass_callback(qb_pass_cb cb, void *user, int min_passes)

@@ -57,6 +57,7 @@ cudaError_t launch_elementwise(int op, int64_t n, const q128 *a, const q128 *b, 
 cudaError_t launch_fma_microbench(int variant, int blocks, int threads, int iters, q128 *sink, int64_t *n_fma, cudaStream_t st);
 
 void count_launch(int n = 1);
+int ref_gemm_kernel(); /* qb_set_ref_gemm_kernel: 1 = k_gemm_nb (branch-free step, default), 0 = k_gemm (first version) */
 int fast_variant();   /* qb_set_fast_variant: 1 = window accumulator (default), 0 = rounded-FMA chains */
 
 /* ---- fast-mode tensor-core GEMM (qb_ozaki.cu) ---- */

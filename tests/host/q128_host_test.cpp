@@ -184,8 +184,8 @@ int main(int argc, char **argv)
   int nreg = 12, failed = 0;
   long total = 0;
   for (int reg = 0; reg < nreg; ++reg) {
-    long bad_fma = 0, bad_mul = 0, bad_add = 0, bad_sqrt = 0, bad_cast = 0, bad_chain = 0;
-#pragma omp parallel reduction(+ : bad_fma, bad_mul, bad_add, bad_sqrt, bad_cast, bad_chain)
+    long bad_fma = 0, bad_mul = 0, bad_add = 0, bad_sqrt = 0, bad_cast = 0, bad_chain = 0, bad_nb = 0, nb_total = 0, nb_declined = 0;
+#pragma omp parallel reduction(+ : bad_fma, bad_mul, bad_add, bad_sqrt, bad_cast, bad_chain, bad_nb, nb_total, nb_declined)
     {
       uint64_t s = seed0 * 1000003ULL + (uint64_t)reg * 7919ULL + (uint64_t)omp_get_thread_num() * 104729ULL;
       bool printed = false;
@@ -225,6 +225,26 @@ int main(int argc, char **argv)
             }
           }
         }
+        /* branch-free step of the reference-order qgemm: either the same bits, or "not handled" with the accumulator untouched */
+        {
+          uint32_t col[24] = {0}, nb_bad = 0;
+          q128 rn = qb::q_fma_fast_nb(a, b, c, col, 2, &nb_bad);
+          bool negzero = (c.hi == 0x8000000000000000ULL && c.lo == 0);
+          ++nb_total;
+          if (nb_bad) { ++nb_declined; if (!same(rn, c)) ++bad_nb; }
+          else if (!same(rn, e)) {
+            ++bad_nb;
+            if (!printed) {
+              printed = true;
+#pragma omp critical
+              printf("  NB mismatch [%s] a=%016llx%016llx b=%016llx%016llx c=%016llx%016llx got=%016llx%016llx exp=%016llx%016llx\n",
+                     names[reg], (unsigned long long)a.hi, (unsigned long long)a.lo, (unsigned long long)b.hi, (unsigned long long)b.lo,
+                     (unsigned long long)c.hi, (unsigned long long)c.lo, (unsigned long long)rn.hi, (unsigned long long)rn.lo,
+                     (unsigned long long)e.hi, (unsigned long long)e.lo);
+            }
+          }
+          (void)negzero;
+        }
         if ((i & 3) == 0) {
           q128 rm = qb::q_mul(a, b), em = fromQ(toQ(a) * toQ(b));
           if (!same(rm, em)) ++bad_mul;
@@ -262,9 +282,9 @@ int main(int argc, char **argv)
     total += n;
     double fastfrac = (double)qb_chain_fast_hits / (double)(qb_chain_fast_hits + qb_chain_slow_hits + 1e-9);
     qb_chain_fast_hits = qb_chain_slow_hits = 0;
-    bool ok = !(bad_fma | bad_mul | bad_add | bad_sqrt | bad_cast | bad_chain);
-    printf("%-18s n=%ld fma_bad=%ld chain_bad=%ld mul_bad=%ld add_bad=%ld sqrt_bad=%ld cast_bad=%ld fast=%.3f %s\n", names[reg], n, bad_fma,
-           bad_chain, bad_mul, bad_add, bad_sqrt, bad_cast, fastfrac, ok ? "OK" : "FAIL");
+    bool ok = !(bad_fma | bad_mul | bad_add | bad_sqrt | bad_cast | bad_chain | bad_nb);
+    printf("%-18s n=%ld fma_bad=%ld chain_bad=%ld mul_bad=%ld add_bad=%ld sqrt_bad=%ld cast_bad=%ld fast=%.3f nb_bad=%ld nb_fast=%.3f %s\n", names[reg], n, bad_fma,
+           bad_chain, bad_mul, bad_add, bad_sqrt, bad_cast, fastfrac, bad_nb, 1.0 - (double)nb_declined / (double)(nb_total + 1e-9), ok ? "OK" : "FAIL");
     if (!ok) ++failed;
   }
   printf("TOTAL fma vectors: %ld, failing regimes: %d\n", total, failed);
