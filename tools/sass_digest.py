@@ -9,7 +9,8 @@ want = [("k_oz_mmaILi1E", "k_oz_mma<1> (residue scheme tensor kernel)"), ("k_oz_
         ("k_crt_residuesILi5E", "k_crt_residues<5> (A rows, 5 words)"), ("k_crt_residues_tILi5E", "k_crt_residues_t<5> (B columns, transposing)"),
         ("k_crt_foldILi11E", "k_crt_fold<11> (41-44 moduli)"), ("k_crt_foldILi10E", "k_crt_fold<10> (37-40 moduli)"), ("k_crt_fixup", "k_crt_fixup"),
         ("k_oz_scan", "k_oz_scan"), ("k_gemv_f64ILb0E", "k_gemv_f64<row-major> (sliced FP64 qgemv: TMA tiles, DFMA)"), ("k_gemv_f64ILb1E", "k_gemv_f64<col-major>"),
-        ("k_sumsq_tma", "k_sumsq_tma (sliced FP64 sum of squares fed by cp.async.bulk)"), ("k_gemv_row_wide", "k_gemv_row_wide (window accumulate, first instance)"), ("6k_gemm", "k_gemm (reference-order integer-limb qgemm)")]
+        ("k_sumsq_tma", "k_sumsq_tma (sliced FP64 sum of squares fed by cp.async.bulk)"), ("k_gemv_row_wide", "k_gemv_row_wide (window accumulate, first instance)"), ("6k_gemm", "k_gemm (reference-order integer-limb qgemm, first version)"), ("9k_gemm_nb", "k_gemm_nb (reference-order qgemm, branch-free step: the default)"),
+        ("k_dot_wide_tmaILi128ELi4ELb0E", "k_dot_wide_tma (fast qdot of two contiguous vectors: cp.async.bulk tiles, window accumulate)")]
 funcs = collections.OrderedDict()
 cur = None
 for ln in out.splitlines():
