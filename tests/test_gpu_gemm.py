@@ -196,3 +196,47 @@ def test_baseline_config1_1000_cubed_full_matrix(qb, oracle, mode):
         idx = np.stack(np.meshgrid(rows, np.arange(S), indexing="ij"), axis=-1).reshape(-1, 2)
         want = oracle.gemm_sample("R", S, S, S, 1.0, A, S, B, S, 0.0, C0, S, idx)
         assert quad.same_bits(C.reshape(S, S, 2)[rows].reshape(-1, 2), want).all()
+
+
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_gemm_sparse_triangular_signed_zeros_both_kernels(qb, oracle, kernel):
+    """The branch-free kernel (k_gemm_nb) keeps zero operands on its fast path and redoes declined steps out of line; the first version
+    (k_gemm) sends both through the generic FMA.  Structured inputs — upper-triangular A (every row starts with +0 / -0 products into a
+    zero accumulator), zero rows and columns, signed zeros, heavy cancellation, a few Inf / NaN / subnormals, k spanning three panels —
+    must give the oracle's bits with either kernel."""
+    rng = np.random.default_rng(2026)
+    m, n, k = 70, 45, 300
+    A = qgen.matrix(rng, m, k, "Dexp"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n)
+    Am = A.reshape(m, k, 2); Bm = B.reshape(k, n, 2); Cm = C0.reshape(m, n, 2)
+    negzero = np.array([0, 0x8000 << 48], dtype=np.uint64)
+    for i in range(m):
+        Am[i, :min(k, 3 * i)] = 0                      # upper triangular (shifted): rows of leading zeros
+        if i % 3 == 1: Am[i, :min(k, 3 * i):2] = negzero
+    Am[17] = 0; Am[18] = negzero                       # a +0 row and a -0 row: the sign of 0 * C decides
+    Bm[:, 7] = 0; Bm[5::11, :] = negzero
+    # cancellation: pairs of equal and opposite products inside a panel
+    Am[40, 130:140] = Am[41, 130:140]; Bm[130:135, 3] = Bm[135:140, 3]
+    Am[40, 135:140, 1] ^= np.uint64(1 << 63)
+    Am[41, 131] = Am[41, 130]; Bm[131, 9] = Bm[130, 9]; Bm[131, 9, 1] ^= np.uint64(1 << 63)   # a*b - a*b = 0 exactly, then more terms
+    sa, sb, sc = qgen.triples(rng, 16, "specials")
+    Am[60:64, 200:204] = sa.reshape(4, 4, 2); Bm[250:254, 20:24] = sb.reshape(4, 4, 2)
+    Am[62, 210] = (0, 0x7FFF << 48); Bm[211, 30] = (1, 0x7FFF << 48); Am[63, 220] = (12345, 1 << 40)   # Inf, NaN, a subnormal
+    Am[64, 230] = (0, 0x7FFF << 48); Bm[230, :] = 0                                                  # Inf x 0 = NaN in a whole row
+    Cm[0, :5, 1] |= np.uint64(1 << 63)
+    alpha, beta = quad.random_quads(rng, 2)
+    qb.set_ref_gemm_kernel(kernel)
+    try:
+        for bt in (beta, quad.from_double(np.array([0.0]))[0], quad.from_double(np.array([-0.0]))[0]):
+            Cg, Co = C0.copy(), C0.copy()
+            qb.gemm("R", m, n, k, alpha, A, k, B, n, bt, Cg, n)
+            oracle.gemm("R", m, n, k, alpha, A, k, B, n, bt, Co, n)
+            assert quad.same_bits(Cg, Co).all()
+        # column-major storage of the same product, device path
+        At = np.ascontiguousarray(Am.transpose(1, 0, 2)).reshape(-1, 2); Bt = np.ascontiguousarray(Bm.transpose(1, 0, 2)).reshape(-1, 2)
+        Ct = np.ascontiguousarray(Cm.transpose(1, 0, 2)).reshape(-1, 2)
+        dC = to_dev(Ct); Co = Ct.copy()
+        qb.gemm("C", m, n, k, alpha, to_dev(At), m, to_dev(Bt), k, beta, dC, m)
+        oracle.gemm("C", m, n, k, alpha, At, m, Bt, k, beta, Co, m)
+        assert quad.same_bits(to_host(dC), Co).all()
+    finally:
+        qb.set_ref_gemm_kernel(1)
