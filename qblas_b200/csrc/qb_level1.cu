@@ -155,17 +155,6 @@ k_dot_fast_l2(const q128 *part, int count, int do_sqrt, q128 *result)
 
 
 /* ---- fast mode, unrounded window accumulator (qwide.cuh) ---- */
-__device__ __noinline__ qwide qw_merge_ni(qwide a, qwide b) { qw_merge(a, b); return a; }
-
-__device__ __forceinline__ qwide qw_shfl_down(const qwide &s, int off)
-{
-  qwide t;
-  t.w0 = __shfl_down_sync(0xffffffffu, s.w0, off); t.w1 = __shfl_down_sync(0xffffffffu, s.w1, off);
-  t.w2 = __shfl_down_sync(0xffffffffu, s.w2, off); t.w3 = __shfl_down_sync(0xffffffffu, s.w3, off);
-  t.w4 = __shfl_down_sync(0xffffffffu, s.w4, off); t.w5 = __shfl_down_sync(0xffffffffu, s.w5, off);
-  t.E = __shfl_down_sync(0xffffffffu, s.E, off);
-  return t;
-}
 /* partial record: 8 words {w0..w5, E, bad} = 32 B */
 __device__ __forceinline__ void qw_store(uint32_t *dst, const qwide &s, uint32_t bad)
 {
@@ -191,27 +180,75 @@ __device__ __forceinline__ qwide qw_load_cg(const uint32_t *src, uint32_t &bad)
   return s;
 }
 
-/* fixed tree over the B threads of a CTA: shuffle tree inside each warp (lane l += lane l+off),
- * then warp 0's thread 0 folds the warp results in warp order.  Result valid in thread 0. */
+/* Sum of the windows of the B threads of a CTA (result valid in thread 0), by qw_align7 / qw7_add of qwide.cuh: the largest anchor of the
+ * CTA (warp max + one exchange through shared memory), every window shifted ONCE to it, then 224-bit integer sums — five shuffle
+ * rounds inside the warps, thread 0 adds the warp results.  Integer addition is associative, so the result is the same bits for any
+ * order.  (The first version was a tree of pairwise qw_merge: 8 dependent merges per tree, 18 us of fixed cost per kernel.) */
 template <int B>
-__device__ __forceinline__ qwide qw_block_tree(qwide v, uint32_t &bad, uint32_t *sh /* 8 * B/32 words */)
+__device__ __forceinline__ int32_t qw_block_emax(int32_t e, uint32_t *sh /* B/32 words */)
 {
-#pragma unroll 1
-  for (int off = 16; off > 0; off >>= 1) v = qw_merge_ni(v, qw_shfl_down(v, off));
+  e = __reduce_max_sync(0xffffffffu, e);
+  __syncthreads();                                   /* sh may still be in use by the phase before */
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = (uint32_t)e;
+  __syncthreads();
+  int32_t E = (int32_t)sh[0];
+#pragma unroll
+  for (int w = 1; w < B / 32; ++w) E = max(E, (int32_t)sh[w]);
+  __syncthreads();
+  return E;
+}
+template <int B>
+__device__ __forceinline__ qwide qw_block_add7(uint32_t (&a)[7], int32_t E, uint32_t &bad, uint32_t *sh /* 8 * B/32 words */)
+{
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    uint32_t b[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) b[j] = __shfl_down_sync(0xffffffffu, a[j], off);
+    qw7_add(a, b);
+  }
   bad = __reduce_or_sync(0xffffffffu, bad);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) qw_store(sh + 8 * warp, v, bad);
+  if (lane == 0) {
+    reinterpret_cast<uint4 *>(sh + 8 * warp)[0] = make_uint4(a[0], a[1], a[2], a[3]);
+    reinterpret_cast<uint4 *>(sh + 8 * warp)[1] = make_uint4(a[4], a[5], a[6], bad);
+  }
   __syncthreads();
+  qwide v = qw_zero();
   if (threadIdx.x == 0) {
 #pragma unroll 1
     for (int w = 1; w < B / 32; ++w) {
-      uint32_t bw = 0;
-      const qwide t = qw_load(sh + 8 * w, bw);
-      bad |= bw;
-      v = qw_merge_ni(v, t);
+      const uint4 p = reinterpret_cast<const uint4 *>(sh + 8 * w)[0], q = reinterpret_cast<const uint4 *>(sh + 8 * w)[1];
+      const uint32_t b[7] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z};
+      qw7_add(a, b);
+      bad |= q.w;
     }
+    v = qw_from7(a, E);
   }
   return v;
+}
+template <int B>
+__device__ __forceinline__ qwide qw_block_tree(qwide v, uint32_t &bad, uint32_t *sh /* 8 * B/32 words */)
+{
+  const int32_t E = qw_block_emax<B>(v.E, sh);
+  uint32_t a[7];
+  qw_align7(v, E, a);
+  return qw_block_add7<B>(a, E, bad, sh);
+}
+/* the same over `count` records {w0..w5, E, bad} written by other CTAs (`stride` words apart): thread t takes the records t, t + B, ... */
+template <int B>
+__device__ __forceinline__ qwide qw_block_fold_records(const uint32_t *rec, int stride, int count, uint32_t &bad, uint32_t *sh)
+{
+  int32_t e = QW_EMPTY;
+  for (int i = threadIdx.x; i < count; i += B) e = max(e, (int32_t)__ldcg(rec + (int64_t)stride * i + 6));
+  const int32_t E = qw_block_emax<B>(e, sh);
+  uint32_t a[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  for (int i = threadIdx.x; i < count; i += B) {
+    uint32_t b[7];
+    qw_align7(qw_load_cg(rec + (int64_t)stride * i, bad), E, b);
+    qw7_add(a, b);
+  }
+  return qw_block_add7<B>(a, E, bad, sh);
 }
 
 /* U element pairs (2U 128-bit loads) in flight per thread; the U accumulate steps are branch-free
@@ -278,9 +315,7 @@ k_dot_wide_l1(DotArgs g)
   __threadfence();
   v = qw_zero();
   bad = 0;
-  for (int i = threadIdx.x; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, bad));
-  __syncthreads();
-  v = qw_block_tree<B>(v, bad, sh);
+  v = qw_block_fold_records<B>(rec, 8, (int)gridDim.x, bad, sh);
   if (threadIdx.x == 0) {
     const q128 r = qw_finish(v, bad);
     *g.result = g.do_sqrt ? q_sqrt(r) : r;
@@ -327,6 +362,20 @@ k_dot_wide_tma(DotArgs g)
     if (mine > 1) issue(1, 1);
   }
   auto ld = [](const uint4 &v) { q128 r; r.lo = ((uint64_t)v.y << 32) | v.x; r.hi = ((uint64_t)v.w << 32) | v.z; return r; };
+  if (mine > 0) {
+    /* an empty accumulator declines every product (its anchor is below everything) and the out-of-line step is slow, U of them in a
+     * row per thread (measured: 18.4 -> 16.4 us per call at n = 10^6).  The anchor is therefore set from the first tile before the
+     * loop, where the declined steps would have put it: QW_SLACK bits above the largest of this thread's first U products of
+     * normal operands. */
+    tc::mbar_wait(&full[0], 0u);
+    int32_t e0 = QW_EMPTY;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t ea = (tx[u * B + tid].w >> 16) & 0x7fffu, eb = SAME ? ea : ((ty[u * B + tid].w >> 16) & 0x7fffu);
+      if (ea - 1u < 0x7ffeu && eb - 1u < 0x7ffeu) e0 = max(e0, (int32_t)(ea + eb));
+    }
+    if (e0 != QW_EMPTY) acc.E = e0 + QW_SLACK;
+  }
   for (int64_t i = 0; i < mine; ++i) {
     const int s = (int)(i & 1);
     tc::mbar_wait(&full[s], (uint32_t)(i >> 1) & 1u);
@@ -367,9 +416,7 @@ k_dot_wide_tma(DotArgs g)
   __threadfence();
   v = qw_zero();
   bad = 0;
-  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, bad));
-  __syncthreads();
-  v = qw_block_tree<B>(v, bad, sh);
+  v = qw_block_fold_records<B>(rec, 8, (int)gridDim.x, bad, sh);
   if (tid == 0) {
     const q128 r = qw_finish(v, bad);
     *g.result = g.do_sqrt ? q_sqrt(r) : r;
@@ -482,9 +529,7 @@ k_sumsq_f64(DotArgs g)
   __threadfence();
   v = qw_zero();
   flags = 0;
-  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, flags));
-  __syncthreads();
-  v = qw_block_tree<B>(v, flags, sh);
+  v = qw_block_fold_records<B>(rec, 8, (int)gridDim.x, flags, sh);
   if (tid == 0) {
     if (flags & QS_FALLBACK) *g.only_if = 1u;
     else {
@@ -580,9 +625,7 @@ k_sumsq_tma(DotArgs g)
   __threadfence();
   v = qw_zero();
   flags = 0;
-  for (int i = tid; i < (int)gridDim.x; i += B) v = qw_merge_ni(v, qw_load_cg(rec + 8 * (int64_t)i, flags));
-  __syncthreads();
-  v = qw_block_tree<B>(v, flags, sh);
+  v = qw_block_fold_records<B>(rec, 8, (int)gridDim.x, flags, sh);
   if (tid == 0) {
     if (flags & QS_FALLBACK) *g.only_if = 1u;
     else {
@@ -716,13 +759,12 @@ k_dot_f64_tma(DotArgs g)
   asum = 0; dm = QS_EXNONE;
   for (int i = tid; i < (int)gridDim.x; i += B) {
     const uint32_t *src = rec + 12 * (int64_t)i;
-    v = qw_merge_ni(v, qw_load_cg(src, flags));
     asum = max(asum, (int)__ldcg(src + 8)); dm = max(dm, (int)__ldcg(src + 9));
   }
   asum = block_max<B>(asum, shm);
   dm = block_max<B>(dm, shm);
   __syncthreads();
-  v = qw_block_tree<B>(v, flags, sh);
+  v = qw_block_fold_records<B>(rec, 12, (int)gridDim.x, flags, sh);
   if (tid == 0) {
     if ((flags & QS_FALLBACK) || dm < asum - QS_ACCEPT) *g.only_if = 1u;
     else {

@@ -404,6 +404,83 @@ QB_HD void qw_merge(qwide &S, qwide T)
   if (top != 0 && top != -1) { qw_shr(S, 16); S.E += 16; }
 }
 
+/* ---- sum of many windows at once (the block reductions of the level-1 kernels) -------------------------------------------------
+ * A tree of pairwise qw_merge costs a dependent chain of merges (each with its own re-anchoring shift): 8 in a row for 128 threads,
+ * twice per kernel — 18 us of a 64 us qdot at n = 10^7.  Instead every window is shifted ONCE to the largest anchor of the group
+ * (the truncation qw_merge applies to the lower-anchored operand), extended to 224 bits, and the sum is plain two's-complement
+ * integer addition: associative and exact, so warps add by shuffles in any order and the result is the same bits.  Groups of up
+ * to 2^16 windows cannot overflow 224 bits (each |W| < 2^189). */
+
+/* v shifted to the anchor E >= v.E (arithmetic, floor) as 7 words; an empty window is zero.  Registers only (select network). */
+QB_HD void qw_align7(const qwide &v, int32_t E, uint32_t (&o)[7])
+{
+  if (v.E == QW_EMPTY) {
+    for (int j = 0; j < 7; ++j) o[j] = 0u;
+    return;
+  }
+  const uint32_t sg = (uint32_t)((int32_t)v.w5 >> 31);
+  uint32_t s = (uint32_t)(E - v.E);
+  if (s >= 192u) {                                        /* everything below the new window: 0 or -1 (floor) */
+    for (int j = 0; j < 7; ++j) o[j] = sg;
+    return;
+  }
+  uint32_t t0 = v.w0, t1 = v.w1, t2 = v.w2, t3 = v.w3, t4 = v.w4, t5 = v.w5;
+  if (s & 128u) { t0 = t4; t1 = t5; t2 = sg; t3 = sg; t4 = sg; t5 = sg; }
+  if (s & 64u) { t0 = t2; t1 = t3; t2 = t4; t3 = t5; t4 = sg; t5 = sg; }
+  if (s & 32u) { t0 = t1; t1 = t2; t2 = t3; t3 = t4; t4 = t5; t5 = sg; }
+  o[0] = fshr(t0, t1, s); o[1] = fshr(t1, t2, s); o[2] = fshr(t2, t3, s); o[3] = fshr(t3, t4, s); o[4] = fshr(t4, t5, s);
+  o[5] = fshr(t5, sg, s); o[6] = sg;
+}
+/* a += b (224-bit two's complement) */
+QB_HD void qw7_add(uint32_t (&a)[7], const uint32_t (&b)[7])
+{
+#if defined(__CUDA_ARCH__)
+  asm("add.cc.u32 %0, %0, %7;\n\t"
+      "addc.cc.u32 %1, %1, %8;\n\t"
+      "addc.cc.u32 %2, %2, %9;\n\t"
+      "addc.cc.u32 %3, %3, %10;\n\t"
+      "addc.cc.u32 %4, %4, %11;\n\t"
+      "addc.cc.u32 %5, %5, %12;\n\t"
+      "addc.u32 %6, %6, %13;"
+      : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6])
+      : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
+#else
+  uint64_t c = 0;
+  for (int j = 0; j < 7; ++j) { c += (uint64_t)a[j] + b[j]; a[j] = (uint32_t)c; c >>= 32; }
+#endif
+}
+/* the 224-bit sum at anchor E back as a window: while it does not leave the carry headroom of qw_merge (|W| < 2^188) 16 bits are
+ * given back at the bottom, as qw_merge does */
+QB_HD qwide qw_from7(const uint32_t (&a)[7], int32_t E)
+{
+  qwide S = qw_zero();
+  if (E == QW_EMPTY) return S;
+  uint32_t w[7] = {a[0], a[1], a[2], a[3], a[4], a[5], a[6]};
+  for (int it = 0; it < 3; ++it) {
+    const int64_t top = (int64_t)(((uint64_t)w[6] << 32) | w[5]) >> 28;   /* bits 188.. as a signed number */
+    if (top == 0 || top == -1) break;
+    const uint32_t sg = (uint32_t)((int32_t)w[6] >> 31);
+    for (int j = 0; j < 6; ++j) w[j] = fshr(w[j], w[j + 1], 16);
+    w[6] = fshr(w[6], sg, 16);
+    E += 16;
+  }
+  S.w0 = w[0]; S.w1 = w[1]; S.w2 = w[2]; S.w3 = w[3]; S.w4 = w[4]; S.w5 = w[5]; S.E = E;
+  return S;
+}
+/* the sum of n windows, the way the block reductions compute it (host tests; the kernels spread the same additions over a CTA) */
+QB_HD qwide qw_sum_aligned(const qwide *p, int64_t n)
+{
+  int32_t E = QW_EMPTY;
+  for (int64_t i = 0; i < n; ++i) E = p[i].E > E ? p[i].E : E;
+  uint32_t a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int64_t i = 0; i < n; ++i) {
+    uint32_t b[7];
+    qw_align7(p[i], E, b);
+    qw7_add(a, b);
+  }
+  return qw_from7(a, E);
+}
+
 /* one RNE rounding of the window to binary128 (overflow -> Inf, gradual underflow handled by
  * q_round_pack).  An empty or exactly cancelled window is +0, as the reference's chain from +0
  * gives for an empty sum (level1.hpp:83-84) and for x + (-x) under RNE. */

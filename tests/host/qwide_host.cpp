@@ -63,6 +63,18 @@ void qwide_tree(int64_t n, const q128 *x, const q128 *y, q128 *out)
   delete[] acc;
 }
 
+/* n single-product windows (after `lanes`-way pre-accumulation: window l takes the products l, l + lanes, ...) summed the way the
+ * block reductions of the level-1 kernels do it: one shift to the common anchor, 224-bit integer sum (qw_sum_aligned) */
+void qwide_blocksum(int64_t n, const q128 *x, const q128 *y, int lanes, q128 *out)
+{
+  qwide *acc = new qwide[lanes > 0 ? lanes : 1];
+  uint32_t bad = 0;
+  for (int l = 0; l < lanes; ++l) acc[l] = qw_zero();
+  for (int64_t i = 0; i < n; ++i) qw_fma(acc[i % lanes], qop_load(x[i]), qop_load(y[i]), bad);
+  *out = qw_finish(qw_sum_aligned(acc, lanes), bad);
+  delete[] acc;
+}
+
 /* the sliced FP64 accumulate (qslice.cuh) as k_gemv_row_f64 runs it on one row: thread t of `lanes` takes the elements t, t + lanes, ...
  * of the row a against x, flushes its columns every QS_TILE steps, the windows are merged in lane order and rounded once.
  * Returns 1 when the row passes the acceptance test (the kernel then stores this result), 0 when it would be recomputed by the

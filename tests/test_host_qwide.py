@@ -24,6 +24,7 @@ def qw(tmp_path_factory):
     vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
     lib.qwide_dot.argtypes = [i64, vp, i64, vp, i64, ci, ci, vp, vp]
     lib.qwide_tree.argtypes = [i64, vp, vp, vp]
+    lib.qwide_blocksum.argtypes = [i64, vp, vp, ci, vp]
     return lib
 
 
@@ -145,6 +146,29 @@ def test_window_merge_tree(qw):
         out = np.zeros((1, 2), dtype=np.uint64)
         qw.qwide_tree(n, x.ctypes.data, y.ctypes.data, out.ctypes.data)
         _check(out[0], x, y)
+
+
+@pytest.mark.parametrize("kind,n,lanes", [("D113", 257, 257), ("Dexp", 257, 257), ("D113", 3000, 128), ("Dexp", 5000, 444), ("wide", 600, 128),
+                                          ("D53", 1, 128), ("D113", 5, 128), ("cancel", 400, 128)])
+def test_window_aligned_block_sum(qw, kind, n, lanes):
+    """the block reduction of the level-1 kernels: every window shifted once to the largest anchor, then one 224-bit integer sum
+    (qw_sum_aligned): the exact sum rounded once up to the window truncation, whatever the spread of the anchors; empty windows
+    (more lanes than elements) are zeros; a sum that cancels keeps the small term that is left"""
+    rng = np.random.default_rng(n + lanes)
+    if kind == "wide":
+        x = quad.random_quads(rng, n, emin=-3000, emax=3000); y = quad.random_quads(rng, n, emin=-200, emax=200)
+    elif kind == "cancel":
+        x = quad.random_quads(rng, n, "D113"); y = quad.random_quads(rng, n, "D113")
+        x[n // 2:] = x[:n // 2]; y[n // 2:] = y[:n // 2]; y[n // 2:, 1] ^= np.uint64(1 << 63)      # the second half cancels the first ...
+        x[-1] = quad.from_double(np.array([3.0]))[0]; y[-1] = quad.from_double(np.array([2.0 ** -90]))[0]   # ... except one small term
+        x[n // 2 - 1] = 0
+    else:
+        x = quad.random_quads(rng, n, kind); y = quad.random_quads(rng, n, "D53" if kind == "D53" else "D113")
+    out = np.zeros((1, 2), dtype=np.uint64)
+    qw.qwide_blocksum(n, x.ctypes.data, y.ctypes.data, lanes, out.ctypes.data)
+    _check(out[0], x, y)
+    if kind == "cancel":       # every lane floors once when it moves to the common anchor: at most `lanes` units of the window's last bit
+        assert abs(_frac(out[0]) - Fraction(3, 2 ** 90)) <= Fraction(lanes, 2 ** 133)
 
 
 @pytest.mark.parametrize("variant", [0, 2])
