@@ -6,7 +6,7 @@ TAG=${1:-r2final}
 mkdir -p gpurun_out
 echo "== all gpu tests"; timeout 1200 python -m pytest tests -m gpu -q --timeout 600 2>&1 | grep -v "^    \|^$" | tail -12 | tee gpurun_out/${TAG}_pytest_all.log
 echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-echo "== bench"; /usr/bin/time -f "bench wall %e s" timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err
+echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -3 gpurun_out/${TAG}_bench.err
 python - <<PY
 import json
 try:
