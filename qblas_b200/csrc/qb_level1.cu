@@ -545,12 +545,12 @@ k_sumsq_f64(DotArgs g)
  * two-stage ring — 32 KB in flight per CTA and six CTAs per SM, without a register spent on it (k_sumsq_f64 above waits on its own
  * loads: long-scoreboard stalls 3.9 per issue at 24 warps per SM).  CTA b takes the tiles b, b + gridDim.x, ...; the last, partial
  * tile of the vector is read with plain loads by the CTA it falls to. */
-constexpr int SQ_PER = 8;
-template <int B, int MINB>
+template <int B, int MINB, int SQ_PER>
 __global__ void __launch_bounds__(B, MINB)
 k_sumsq_tma(DotArgs g)
 {
   constexpr int TE = B * SQ_PER;                       /* elements per tile */
+  constexpr int FLUSH_TILES = 56 / SQ_PER;             /* 56 elements: the accumulators are still exact */
   __shared__ __align__(128) uint4 tile[2][TE];
   __shared__ uint64_t win[4 * B];
   __shared__ __align__(16) uint32_t sh[8 * (B / 32)];
@@ -601,7 +601,7 @@ k_sumsq_tma(DotArgs g)
     const uint4 *tp = &tile[s][tid];
 #pragma unroll
     for (int k = 0; k < SQ_PER; ++k) one(tp[k * B]);
-    if ((i % 7) == 6) flush();                        /* 56 elements: the accumulators are still exact */
+    if ((i % FLUSH_TILES) == FLUSH_TILES - 1) flush();
     __syncthreads();                                   /* every thread is done with stage s */
     if (tid == 0 && i + 2 < mine) issue(i + 2, s);
   }
@@ -813,7 +813,9 @@ cudaError_t launch_dot(const DotArgs &a, int mode, cudaStream_t st)
       if (same && g.only_if != nullptr && ((fast_variant() == 2 && g.n >= (1 << 24)) || fast_variant() == 3)) {
         /* sum of squares on the FP64 pipe; the window kernel is queued behind it and runs only if an Inf / NaN / subnormal made
          * the sliced kernel decline */
-        if (g.incx == 1 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0) k_sumsq_tma<SUMSQ_B, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
+        /* tiles of 1024 elements at 6 CTAs per SM: measured against 512-element tiles at 8 / 9 / 10 CTAs (0.361 / 0.363 / 0.386 ms at n = 10^8)
+         * and 256-element tiles at 12 (0.439 ms) — more, smaller tiles only add barrier rounds; 0.341 ms as built */
+        if (g.incx == 1 && (reinterpret_cast<uintptr_t>(g.x) & 15u) == 0) k_sumsq_tma<SUMSQ_B, SUMSQ_CTAS, 8><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
         else k_sumsq_f64<SUMSQ_B, 4, SUMSQ_CTAS><<<SUMSQ_GRID, SUMSQ_B, 0, st>>>(g);
         k_dot_wide_l1<WIDE_B, 4, true, WIDE_GRID / 148><<<WIDE_GRID, WIDE_B, 0, st>>>(g);
         count_launch(2);
