@@ -615,7 +615,10 @@ QB_HD q128 qacc2_pack(const qacc2 &a)
   return r;
 }
 
-/* (g0..g4) = (s0..s3, 0) +- (f0..f4) in two's complement (minus iff subw != 0); bo = 0xffffffff iff the difference is negative */
+/* (g0..g4) = (s0..s3, 0) +- (f0..f4) in two's complement (minus iff subw != 0); bo = 0xffffffff iff the difference is negative.
+ * The borrow is read back inside the subtraction chain only: reading it with subc after the ADD chain (whose carry is known to be
+ * clear) would save an instruction, but ptxas keeps the flag of a subtraction in the inverted sense and does not convert between the
+ * two — tried, wrong results on the device. */
 QB_HD void addsub5(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3, uint32_t f4,
                    uint32_t subw, uint32_t &g0, uint32_t &g1, uint32_t &g2, uint32_t &g3, uint32_t &g4, uint32_t &bo)
 {
@@ -676,21 +679,35 @@ QB_HD void condneg5(uint32_t &g0, uint32_t &g1, uint32_t &g2, uint32_t &g3, uint
   }
 #endif
 }
-/* the leading one of (g4..g0) is in g4 or, if g4 = 0, in g3: move it to w4 (predicated moves: the copies may go to either pipe) */
-QB_HD void lead5(uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3, uint32_t g4, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
-                 uint32_t &w4)
+/* the leading one of (g4..g0) is in g4 or, if g4 = 0, in g3: move it to w4 (predicated moves: the copies may go to either pipe);
+ * returns 32 when the words moved up (the whole-word part of the leading-zero count), else 0 */
+QB_HD uint32_t lead5(uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3, uint32_t g4, uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3,
+                     uint32_t &w4)
 {
 #if defined(__CUDA_ARCH__)
+  uint32_t up;
   asm("{\n\t.reg .pred p;\n\t"
-      "setp.eq.u32 p, %9, 0;\n\t"
-      "mov.u32 %0, %5;\n\t" "mov.u32 %1, %6;\n\t" "mov.u32 %2, %7;\n\t" "mov.u32 %3, %8;\n\t" "mov.u32 %4, %9;\n\t"
-      "@p mov.u32 %4, %8;\n\t" "@p mov.u32 %3, %7;\n\t" "@p mov.u32 %2, %6;\n\t" "@p mov.u32 %1, %5;\n\t" "@p mov.u32 %0, 0;\n\t"
+      "setp.eq.u32 p, %10, 0;\n\t"
+      "mov.u32 %0, %6;\n\t" "mov.u32 %1, %7;\n\t" "mov.u32 %2, %8;\n\t" "mov.u32 %3, %9;\n\t" "mov.u32 %4, %10;\n\t"
+      "@p mov.u32 %4, %9;\n\t" "@p mov.u32 %3, %8;\n\t" "@p mov.u32 %2, %7;\n\t" "@p mov.u32 %1, %6;\n\t" "@p mov.u32 %0, 0;\n\t"
+      "selp.u32 %5, 32, 0, p;\n\t"
       "}"
-      : "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3), "=&r"(w4)
+      : "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3), "=&r"(w4), "=&r"(up)
       : "r"(g0), "r"(g1), "r"(g2), "r"(g3), "r"(g4));
+  return up;
 #else
   const bool top = (g4 != 0u);
   w4 = top ? g4 : g3; w3 = top ? g3 : g2; w2 = top ? g2 : g1; w1 = top ? g1 : g0; w0 = top ? g0 : 0u;
+  return top ? 0u : 32u;
+#endif
+}
+
+QB_HD uint32_t umin32(uint32_t a, uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+  return min(a, b);
+#else
+  return a < b ? a : b;
 #endif
 }
 
@@ -714,7 +731,7 @@ QB_HD bool round_commit(qacc2 &S, uint32_t n0, uint32_t n1, uint32_t n2, uint32_
       "@!p addc.cc.u32 %1, %8, 0;\n\t"
       "@!p addc.cc.u32 %2, %9, 0;\n\t"
       "@!p addc.cc.u32 t3, %10, 0;\n\t"
-      "@!p addc.u32 c, 0, 0;\n\t"
+      "addc.u32 c, 0, 0;\n\t"                                /* unpredicated: only predicated instructions read it */
       "@!p and.b32 %0, t, 0xffff8000;\n\t"
       "@!p mad.lo.u32 %3, c, 0x80000000, t3;\n\t"          /* a mantissa that rounded up to 2^113 left 0 */
       "@!p add.s32 %4, %12, c;\n\t"
@@ -770,18 +787,17 @@ QB_HD bool qacc_fma_nb(qacc2 &S, const uint32_t a0, const uint32_t a1, const uin
   condneg5(g0, g1, g2, g3, g4, bo, cx.zero);
 
   /* normalise: the leading one is in word 4 or, after a cancellation of up to 13 bits, in word 3 */
-  const bool top = (g4 != 0u);
   uint32_t w0, w1, w2, w3, w4;
-  lead5(g0, g1, g2, g3, g4, w0, w1, w2, w3, w4);
+  const uint32_t up = lead5(g0, g1, g2, g3, g4, w0, w1, w2, w3, w4);
   const uint32_t lzq = (uint32_t)clz32(w4);
-  const uint32_t lz = lzq + (top ? 0u : 32u);            /* > 45: more than 13 bits cancelled */
+  const uint32_t lz = lzq + up;                          /* > 45: more than 13 bits cancelled */
   const uint32_t n3 = fshl(w3, w4, lzq), n2 = fshl(w2, w3, lzq), n1 = fshl(w1, w2, lzq);
   uint32_t n0 = fshl(w0, w1, lzq);
   const uint32_t rest = w0 << (lzq & 31u);
   const int32_t es = s_zero ? esum - QBIAS : S.e;
   const int32_t en = es + 32 - (int32_t)lz;              /* before the carry of the rounding */
   const uint32_t rc = 0x3fffu + ((n0 >> 15) & 1u);       /* round to nearest even at bit 15 of n0 */
-  n0 |= (rest < 1u ? rest : 1u);
+  n0 |= umin32(rest, 1u);
   const uint32_t fl = wsum & QM_FLAGS;
   return round_commit(S, n0, n1, n2, n3, rc, en, wsum, subw, bo, sh_raw, lz, fl);
 }
