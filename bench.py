@@ -238,7 +238,7 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
                 "ms": ms, "gflops": gf,
                 "first_version_k_gemm": {"ms": ms_old, "gflops": 2.0 * Sr ** 3 / ms_old / 1e6},
                 "clk_per_warp_qfma_per_subpartition": clk,
-                "clk_model": "sum of dispatch clocks over the SASS of the hot block (tools/sass_cost.py, calibrated by tools/exp/mb_pipes.cu): 261 for k_gemm_nb, 273 for k_gemm; the 16 IMAD.WIDE of the 113x113-bit product alone are 69",
+                "clk_model": "sum of dispatch clocks over the SASS of the hot block (tools/sass_cost.py, calibrated by tools/exp/mb_pipes.cu): 252 for k_gemm_nb, 273 for k_gemm; the 16 IMAD.WIDE of the 113x113-bit product alone are 69",
                 "roofline": {"bound": "int-issue (IMAD/ALU pipes)", "achieved": gf, "peak": pk, "unit": "GFLOP/s (binary128)", "frac": gf / pk,
                              "peak_source": "live register-resident qFMA microbenchmark (first-version primitive, no memory); pipe utilisation from ncu is in profiles/"}}
             qb.set_mode(mode)
