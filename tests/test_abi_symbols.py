@@ -147,5 +147,6 @@ def test_measured_defaults():
     assert qblas_b200.get_tensor_unit() == (2048, 4096) and qblas_b200.get_tensor_ramp() == (0, 0)   # pipeline unit: A pass x B panel
     assert L.qb_get_tensor_pass_shape() == 0      # equal row passes
     assert L.qb_get_fast_variant() == 2           # large row-major qgemv: sliced FP64 accumulate; qdot / qnrm2 / the rest: window accumulator
+    assert L.qb_get_ref_gemm_kernel() == 1        # reference-order qgemm: the branch-free kernel (k_gemm_nb); 0 = the first version
     assert L.qb_get_gemm_peer_written() == 0
     assert L.qb_get_host_slabs() == 8             # pipelined all-host qgemm / qgemv: eight slabs
