@@ -175,6 +175,64 @@ static void gen_ties(uint64_t &s, q128 &a, q128 &b, q128 &c)
   }
 }
 
+/* Chains through the branch-free step the way k_gemm_nb runs them (qb_level3.cu): s starts at +0, every step that declines is redone
+ * by the generic q_fma from the staged operands (gemm_redo), the accumulator carries over in its unpacked / packed forms; panels of
+ * `kc` steps are folded with C = fma(alpha, s, beta * C).  Must give the bits of the same chain through libquadmath.  The inputs mix
+ * similar magnitudes (long fast stretches), exact zeros of both signs (leading zeros of a triangular row), cancelling pairs and
+ * a few subnormals / Inf / NaN. */
+static long chain_test(long nchains, uint64_t seed, long *declined_out, long *steps_out)
+{
+  long bad = 0, declined = 0, steps = 0;
+#pragma omp parallel reduction(+ : bad, declined, steps)
+  {
+    uint64_t s = seed * 7919ULL + (uint64_t)omp_get_thread_num() * 104729ULL + 1;
+#pragma omp for schedule(static)
+    for (long c = 0; c < nchains; ++c) {
+      const int flavour = (int)(splitmix(s) % 6);
+      const int len = 1 + (int)(splitmix(s) % 300), kc = (splitmix(s) & 1) ? 126 : 40;
+      const int lead = (flavour == 1) ? (int)(splitmix(s) % (uint64_t)len) : 0;
+      q128 alpha = gen(s, 1, 0, q128(), q128()), beta = gen(s, 1, 1, alpha, q128()), C = gen(s, 1, 2, alpha, beta), Cq = C;
+      if (flavour == 5) beta = mk(splitmix(s) & 1, 0, 0, 0);
+      qb::qacc2 acc = qb::qacc2_zero();
+      Q sq = 0;
+      int pc = 0, first = 1;
+      q128 pa = q128(), pb = q128();
+      for (int l = 0; l < len; ++l) {
+        q128 a = gen(s, 1, 0, q128(), q128()), b = gen(s, 1, 1, a, q128());
+        const uint64_t r = splitmix(s);
+        if (flavour <= 2 || flavour == 5) {   /* magnitudes within 2^8 of each other: long stretches of undeclined steps */
+          a.hi = (a.hi & 0x8000ffffffffffffULL) | ((uint64_t)(16383 - 4 + (r >> 8) % 8) << 48);
+          b.hi = (b.hi & 0x8000ffffffffffffULL) | ((uint64_t)(16383 - 4 + (r >> 16) % 8) << 48);
+        }
+        if (l < lead) a = mk(r & 1, 0, 0, 0);                                   /* triangular row: +-0 products into a zero accumulator */
+        else if (flavour == 2 && (l & 1)) { a = pa; b = pb; b.hi ^= 0x8000000000000000ULL; }   /* exact cancellation of the step before */
+        else if (flavour == 3 && r % 16 == 0) a = gen(s, 8, 0, q128(), q128());   /* specials */
+        else if (flavour == 4 && r % 8 == 0) b = mk(r >> 5 & 1, 0, 0, 0);
+        else if (flavour == 4 && r % 8 == 1) a = gen(s, 0, 0, q128(), q128());    /* any exponent: products far above / below the sum */
+        pa = a; pb = b;
+        const qb::qstaged A = qb::qstage(a), B = qb::qstage(b);
+        uint32_t col[24] = {0};
+        qb::qnbctx cx; cx.col = col; cx.stride = 2; cx.zero = 0u;
+        ++steps;
+        if (qb::qacc_fma_nb(acc, A.m0, A.m1, A.m2, A.m3, B.m0, B.m1, B.m2, B.m3, A.meta + B.meta, cx)) {
+          ++declined;
+          acc = qb::qacc2_from(qb::q_fma(qb::qstaged_pack(A), qb::qstaged_pack(B), qb::qacc2_pack(acc)));
+        }
+        sq = fmaq(toQ(a), toQ(b), sq);
+        if (++pc == kc || l == len - 1) {
+          const q128 sp = qb::qacc2_pack(acc);
+          C = qb::q_fma(alpha, sp, first ? qb::q_mul(beta, C) : C);
+          Cq = fromQ(fmaq(toQ(alpha), sq, first ? toQ(beta) * toQ(Cq) : toQ(Cq)));
+          if (!same(sp, fromQ(sq)) || !same(C, Cq)) { ++bad; break; }
+          acc = qb::qacc2_zero(); sq = 0; pc = 0; first = 0;
+        }
+      }
+    }
+  }
+  *declined_out = declined; *steps_out = steps;
+  return bad;
+}
+
 int main(int argc, char **argv)
 {
   long n = argc > 1 ? atol(argv[1]) : 2000000;
@@ -286,6 +344,13 @@ int main(int argc, char **argv)
     printf("%-18s n=%ld fma_bad=%ld chain_bad=%ld mul_bad=%ld add_bad=%ld sqrt_bad=%ld cast_bad=%ld fast=%.3f nb_bad=%ld nb_fast=%.3f %s\n", names[reg], n, bad_fma,
            bad_chain, bad_mul, bad_add, bad_sqrt, bad_cast, fastfrac, bad_nb, 1.0 - (double)nb_declined / (double)(nb_total + 1e-9), ok ? "OK" : "FAIL");
     if (!ok) ++failed;
+  }
+  {
+    long declined = 0, steps = 0;
+    const long nch = n / 40 + 1, badc = chain_test(nch, seed0, &declined, &steps);
+    printf("%-18s chains=%ld steps=%ld declined=%.4f chain_mismatches=%ld %s\n", "nb-chains", nch, steps, (double)declined / (double)(steps + 1e-9), badc,
+           badc ? "FAIL" : "OK");
+    if (badc) ++failed;
   }
   printf("TOTAL fma vectors: %ld, failing regimes: %d\n", total, failed);
   return failed;
