@@ -23,8 +23,8 @@ Own arm (default): one "step" = one quadblas qgemm of the workload, device resid
             buffers: H2D of A, B, C and D2H of C inside the timed region.
   `roofline` = the dominant kernel: fast mode -> k_oz_mma against the tensor peak (2 x the measured bf16
             figure, int8 dense), its own duration from CUDA events the library records around each launch;
-            ref mode -> k_gemm against the integer-issue ceiling measured live by the register-resident
-            qFMA microbenchmark.  HBM-bound qgemv / qdot figures are in `extra`.
+            ref mode -> k_gemm_nb against the dispatch clocks of its exact 113x113-bit product (16 IMAD.WIDE); the register-resident
+            qFMA microbenchmark of the first-version step is reported next to it.  HBM-bound qgemv / qdot figures are in `extra`.
   `cpu_baseline` = the reference's own loops (oracle/_ref, libquadmath arithmetic) on the host cores,
             bounded sample.
 Reference arm (--impl reference): times the reference's CPU implementation on the same metric.
@@ -233,14 +233,18 @@ def _secondary(qb, torch, dev, args, S, mode, extra):
             gf = 2.0 * Sr ** 3 / ms / 1e6
             sm_ghz = 1.965
             clk = ms * 1e-3 * sm_ghz * 1e9 * 148 * 4 / (Sr ** 3 / 32.0)     # dispatch clocks per warp-qFMA and SM sub-partition at the boost clock
+            floor_gf = 2.0 * 32.0 * 148 * 4 * sm_ghz / 69.0                   # GFLOP/s if the step were nothing but its 16 wide multiplies
             extra["qgemm_reference_order"] = {
                 "workload": f"quadblas_qgemm row-major {Sr}^3 alpha=1 beta=0, reference-order mode (bit exact vs the reference, kc=126), integer-limb kernel k_gemm_nb (branch-free step, staged decoded operands)",
                 "ms": ms, "gflops": gf,
                 "first_version_k_gemm": {"ms": ms_old, "gflops": 2.0 * Sr ** 3 / ms_old / 1e6},
                 "clk_per_warp_qfma_per_subpartition": clk,
                 "clk_model": "sum of dispatch clocks over the SASS of the hot block (tools/sass_cost.py, calibrated by tools/exp/mb_pipes.cu): 252 for k_gemm_nb, 273 for k_gemm; the 16 IMAD.WIDE of the 113x113-bit product alone are 69",
-                "roofline": {"bound": "int-issue (IMAD/ALU pipes)", "achieved": gf, "peak": pk, "unit": "GFLOP/s (binary128)", "frac": gf / pk,
-                             "peak_source": "live register-resident qFMA microbenchmark (first-version primitive, no memory); pipe utilisation from ncu is in profiles/"}}
+                "roofline": {"bound": "integer dispatch (the sum of the dispatch clocks of the step's instruction stream; no single pipe and no memory level is saturated)",
+                             "achieved": gf, "peak": floor_gf, "unit": "GFLOP/s (binary128)", "frac": gf / floor_gf,
+                             "peak_source": "the exact 113x113-bit product alone: 16 IMAD.WIDE x 4.3 dispatch clocks = 69 clocks per warp-qFMA and SM sub-partition at the boost clock; alignment, signed add, normalisation and rounding are what the kernel adds on top",
+                             "register_resident_microbench_first_version_gflops": pk, "frac_of_that_microbench": gf / pk,
+                             "ncu": "profiles/r2_kgemm_nb_ncu_full.txt: ALU pipe 73 %, fmaheavy 46 %, issue slots 62 %, DRAM < 1 %"}}
             qb.set_mode(mode)
             del Ar, Br, Cr
         mv = 32768 if S >= 8192 else 4096
@@ -633,9 +637,12 @@ def own_arm(args, rank, world, local_rank):
         else:
             pk = _int_issue_peak(qb, torch, dev)
             kern_gflops = 2.0 * m_loc * n * k / (res["ms_step"] * 1e-3) / 1e9
-            roof = {"bound": "int-issue (IMAD/ALU pipes; not hbm, not tensor)", "kernel": "k_gemm", "achieved": kern_gflops, "peak": pk,
-                    "unit": "GFLOP/s (binary128)", "frac": kern_gflops / pk, "traffic": None,
-                    "peak_source": "live register-resident qFMA microbenchmark (qb_fma_microbench_dev, best of 5 shapes; same qacc_fma as k_gemm, no global memory)",
+            floor_gf = 2.0 * 32.0 * 148 * 4 * 1.965 / 69.0   # the step as nothing but the 16 IMAD.WIDE of its exact product: 69 dispatch clocks per warp-qFMA
+            roof = {"bound": "integer dispatch (sum of the dispatch clocks of the qFMA's instruction stream; not hbm, not tensor)", "kernel": "k_gemm_nb",
+                    "achieved": kern_gflops, "peak": floor_gf,
+                    "unit": "GFLOP/s (binary128)", "frac": kern_gflops / floor_gf, "traffic": None,
+                    "peak_source": "16 IMAD.WIDE x 4.3 dispatch clocks per warp-qFMA and SM sub-partition at 1.965 GHz (tools/exp/mb_pipes.cu, tools/sass_cost.py); the register-resident microbenchmark of the first-version step is in register_resident_microbench_gflops",
+                    "register_resident_microbench_gflops": pk, "frac_of_that_microbench": kern_gflops / pk,
                     "algorithmic": f"2*m*n*k = {2.0 * m_loc * n * k:.4g} binary128 flops per launch; avg step {res['ms_step']:.2f} ms (CUDA events)"}
 
     # ---- e2e: reference-named C entry point with HOST buffers (pinned), copies inside the timed region
