@@ -10,11 +10,14 @@
  * C = fma(alpha, s, mul(q == 0 ? beta : 1, C)).  mc/nc/MR/NR and the thread count do not matter,
  * so the whole M x N plane is parallel and only the k order is kept.
  *
- * Kernel shape: a CTA owns a BM x BN tile of C; A/B k-slices are staged in shared memory as raw
- * 16-byte quads; each thread owns TM x TN accumulators kept UNPACKED in registers (qacc) and
- * steps them with qacc_fma.  One qFMA costs ~150 integer instructions, so operand traffic
- * (1 LDS.128 per several hundred instructions) is irrelevant: the kernel is bound by the
- * IMAD/ALU issue rate, not by HBM, L2 or shared memory.
+ * Kernel shape: a CTA owns a BM x BN tile of C; A/B k-slices are staged in shared memory; each
+ * thread owns TM x TN accumulators kept UNPACKED in registers and steps them with the chain FMA
+ * of q128_chain.cuh.  One qFMA costs ~140-170 integer instructions, so operand traffic
+ * (1 LDS.128 per several hundred instructions) is irrelevant: the kernel is bound by the dispatch
+ * clocks of that instruction stream, not by HBM, L2 or shared memory.
+ * Two kernels, same bits: k_gemm (first version: raw quads staged, qacc_fma with an inlined slow-path
+ * call per step) and k_gemm_nb (the default: operands staged decoded, branch-free qacc_fma_nb, declined
+ * steps redone out of line); qb_set_ref_gemm_kernel / QBLAS_GEMM_KERNEL choose.
  */
 #include "qb_internal.h"
 #include "q128_chain.cuh"
