@@ -112,3 +112,29 @@ def reference_benchmark_doubles(count, seed=42):
     s = (raw[0::2] + raw[1::2] * 4294967296.0) / 18446744073709551616.0
     s = np.where(s >= 1.0, np.nextafter(1.0, 0.0), s)
     return s * 2.0 - 1.0
+
+
+def structured_gemm_case(rng, m=70, n=45, k=300):
+    """Row-major A (m x k), B (k x n), C (m x n) with structure instead of noise: a shifted upper-triangular A whose rows start with +0 / -0
+    (zero products into a zero accumulator), a +0 row and a -0 row, a zero column and -0 rows of B, products that cancel exactly inside a
+    panel, specials (Inf, NaN, a subnormal, Inf x 0), negative entries of C.  Shared by the CPU test that pins the oracle against the
+    reference on these inputs and the GPU test that runs both reference-order qgemm kernels on them."""
+    assert m >= 65 and n >= 31 and k >= 254
+    A = matrix(rng, m, k, "Dexp"); B = matrix(rng, k, n, "D113"); C0 = matrix(rng, m, n)
+    Am = A.reshape(m, k, 2); Bm = B.reshape(k, n, 2); Cm = C0.reshape(m, n, 2)
+    negzero = np.array([0, 0x8000 << 48], dtype=np.uint64)
+    for i in range(m):
+        Am[i, :min(k, 3 * i)] = 0
+        if i % 3 == 1:
+            Am[i, :min(k, 3 * i):2] = negzero
+    Am[17] = 0; Am[18] = negzero
+    Bm[:, 7] = 0; Bm[5::11, :] = negzero
+    Am[40, 130:140] = Am[41, 130:140]; Bm[130:135, 3] = Bm[135:140, 3]
+    Am[40, 135:140, 1] ^= np.uint64(1 << 63)
+    Am[41, 131] = Am[41, 130]; Bm[131, 9] = Bm[130, 9]; Bm[131, 9, 1] ^= np.uint64(1 << 63)
+    sa, sb, _ = triples(rng, 16, "specials")
+    Am[60:64, 200:204] = sa.reshape(4, 4, 2); Bm[250:254, 20:24] = sb.reshape(4, 4, 2)
+    Am[62, 210] = (0, 0x7FFF << 48); Bm[211, 30] = (1, 0x7FFF << 48); Am[63, 220] = (12345, 1 << 40)
+    Am[64, 230] = (0, 0x7FFF << 48); Bm[230, :] = 0
+    Cm[0, :5, 1] |= np.uint64(1 << 63)
+    return A, B, C0

@@ -206,23 +206,8 @@ def test_gemm_sparse_triangular_signed_zeros_both_kernels(qb, oracle, kernel):
     must give the oracle's bits with either kernel."""
     rng = np.random.default_rng(2026)
     m, n, k = 70, 45, 300
-    A = qgen.matrix(rng, m, k, "Dexp"); B = qgen.matrix(rng, k, n, "D113"); C0 = qgen.matrix(rng, m, n)
+    A, B, C0 = qgen.structured_gemm_case(rng, m, n, k)
     Am = A.reshape(m, k, 2); Bm = B.reshape(k, n, 2); Cm = C0.reshape(m, n, 2)
-    negzero = np.array([0, 0x8000 << 48], dtype=np.uint64)
-    for i in range(m):
-        Am[i, :min(k, 3 * i)] = 0                      # upper triangular (shifted): rows of leading zeros
-        if i % 3 == 1: Am[i, :min(k, 3 * i):2] = negzero
-    Am[17] = 0; Am[18] = negzero                       # a +0 row and a -0 row: the sign of 0 * C decides
-    Bm[:, 7] = 0; Bm[5::11, :] = negzero
-    # cancellation: pairs of equal and opposite products inside a panel
-    Am[40, 130:140] = Am[41, 130:140]; Bm[130:135, 3] = Bm[135:140, 3]
-    Am[40, 135:140, 1] ^= np.uint64(1 << 63)
-    Am[41, 131] = Am[41, 130]; Bm[131, 9] = Bm[130, 9]; Bm[131, 9, 1] ^= np.uint64(1 << 63)   # a*b - a*b = 0 exactly, then more terms
-    sa, sb, sc = qgen.triples(rng, 16, "specials")
-    Am[60:64, 200:204] = sa.reshape(4, 4, 2); Bm[250:254, 20:24] = sb.reshape(4, 4, 2)
-    Am[62, 210] = (0, 0x7FFF << 48); Bm[211, 30] = (1, 0x7FFF << 48); Am[63, 220] = (12345, 1 << 40)   # Inf, NaN, a subnormal
-    Am[64, 230] = (0, 0x7FFF << 48); Bm[230, :] = 0                                                  # Inf x 0 = NaN in a whole row
-    Cm[0, :5, 1] |= np.uint64(1 << 63)
     alpha, beta = quad.random_quads(rng, 2)
     qb.set_ref_gemm_kernel(kernel)
     try:

@@ -24,6 +24,25 @@ def test_gemm_rowmajor(oracle, ref, m, n, k, kind):
     assert quad.same_bits(Cr, Co).all()
 
 
+def test_gemm_structured_inputs(oracle, ref):
+    """zeros of both signs (triangular rows, zero rows / columns), exact cancellation inside a panel, Inf / NaN / a subnormal, three
+    panels of k, beta = random / +0 / -0: the oracle must give the reference's bits here too — these are the inputs on which the
+    product's branch-free qgemm kernel takes its special paths (tests/test_gpu_gemm.py runs both kernels on the same case)."""
+    rng = np.random.default_rng(2026)
+    m, n, k = 70, 45, 300
+    A, B, C0 = qgen.structured_gemm_case(rng, m, n, k)
+    alpha, beta = quad.random_quads(rng, 2)
+    for bt in (beta, quad.from_double(np.array([0.0]))[0], quad.from_double(np.array([-0.0]))[0]):
+        Cr, Co = C0.copy(), C0.copy()
+        ref.gemm("R", m, n, k, alpha, A, k, B, n, bt, Cr, n)
+        oracle.gemm("R", m, n, k, alpha, A, k, B, n, bt, Co, n)
+        nan_r, nan_o = quad.is_nan(Cr), quad.is_nan(Co)
+        assert (nan_r == nan_o).all() and nan_r.any()
+        assert quad.same_bits(Cr[~nan_r], Co[~nan_o]).all()          # a NaN's payload is the arithmetic library's business
+        zero = (Cr[:, 0] == 0) & ((Cr[:, 1] & np.uint64(0x7FFFFFFFFFFFFFFF)) == 0)
+        assert zero.any() or bt is beta                                # the zero rows give signed zeros when beta is a zero
+
+
 @pytest.mark.parametrize("m,n,k", [(40, 33, 64), (7, 5, 3), (64, 64, 64)])
 def test_gemm_colmajor_simple_path(oracle, ref, m, n, k):
     """ColMajor is only correct in the reference when all dims <= 64 (gemm_simple); SURVEY bug 1."""
